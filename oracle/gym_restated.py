@@ -1,0 +1,353 @@
+"""CPU restatement of the gym==0.26.2 pieces the reference's PPO path calls.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  Never by the product path.
+
+PARITY UNPINNED at this boundary: gym 0.26.2 (reference pin:
+src/environment.yml:504) is a third-party dependency that is neither vendored
+under /root/reference nor installable here, and the reference has no tests or
+golden vectors for env transitions.  This file restates the published
+algorithm of
+
+  gym/envs/classic_control/cartpole.py    (CartPoleEnv.step / reset)
+  gym/envs/classic_control/pendulum.py    (PendulumEnv.step / reset / _get_obs)
+  gym/wrappers/time_limit.py              (TimeLimit)
+  gym/wrappers/record_episode_statistics.py
+  gym/wrappers/clip_action.py, normalize.py, transform_observation.py,
+  gym/wrappers/transform_reward.py
+  gym/vector/sync_vector_env.py           (reset(seed=list), step + autoreset)
+  gym/utils/seeding.py                    (np_random -> PCG64(SeedSequence(seed)))
+
+anchored on the reference's own call sites: ppo.py:66-68 (SyncVectorEnv of
+make_env thunks), ppo.py:87-97 (wrapper stack), ppo.py:110 (step), ppo.py:188
+(reset(seed=list(range(num_envs)))).  The one externally known answer,
+CartPole reset(seed=0) -> [0.01369617, -0.02302133, -0.04590265, -0.04834723],
+is checked in tests/test_oracle_envs.py.
+
+Arithmetic notes (reference pins NumPy 1.24.3, environment.yml:277):
+  * `x ** 2` on Python / NumPy float64 scalars is restated as `x * x`
+    (SURVEY.md section 7.2 item 1).
+  * NumPy 1.24 value-based promotion makes `python_float * np.float32 scalar`
+    a float64; this container has NumPy 2.x (NEP 50) where it would stay
+    float32, so the promotions are written out explicitly with float().
+  * `trig="libm"` uses math.sin/math.cos (what gym does); `trig="det"` uses
+    the deterministic routine shared with the GPU kernels through the C
+    checker (oracle/envs.c -> orc_sincos).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def np_random(seed: Optional[int]):
+    """gym/utils/seeding.py: Generator(PCG64(SeedSequence(seed)))."""
+    seed_seq = np.random.SeedSequence(seed)
+    return np.random.Generator(np.random.PCG64(seed_seq))
+
+
+def _libm_sincos(x: float) -> Tuple[float, float]:
+    return math.sin(x), math.cos(x)
+
+
+class CartPoleEnv:
+    """gym CartPole-v1 physics (cartpole.py), euler integrator."""
+
+    def __init__(self, sincos: Callable[[float], Tuple[float, float]] = _libm_sincos):
+        self.gravity = 9.8
+        self.masscart = 1.0
+        self.masspole = 0.1
+        self.total_mass = self.masspole + self.masscart
+        self.length = 0.5
+        self.polemass_length = self.masspole * self.length
+        self.force_mag = 10.0
+        self.tau = 0.02
+        self.theta_threshold_radians = 12 * 2 * math.pi / 360
+        self.x_threshold = 2.4
+        self.state = None
+        self.steps_beyond_terminated = None
+        self.np_random = None
+        self._sincos = sincos
+        self.obs_dim = 4
+
+    def reset(self, seed: Optional[int] = None):
+        if seed is not None or self.np_random is None:
+            self.np_random = np_random(seed)
+        self.state = tuple(float(v) for v in self.np_random.uniform(low=-0.05, high=0.05, size=(4,)))
+        self.steps_beyond_terminated = None
+        return np.array(self.state, dtype=np.float32), {}
+
+    def step(self, action):
+        x, x_dot, theta, theta_dot = self.state
+        force = self.force_mag if action == 1 else -self.force_mag
+        sintheta, costheta = self._sincos(theta)
+        temp = (force + self.polemass_length * (theta_dot * theta_dot) * sintheta) / self.total_mass
+        thetaacc = (self.gravity * sintheta - costheta * temp) / (
+            self.length * (4.0 / 3.0 - self.masspole * (costheta * costheta) / self.total_mass)
+        )
+        xacc = temp - self.polemass_length * thetaacc * costheta / self.total_mass
+        x = x + self.tau * x_dot
+        x_dot = x_dot + self.tau * xacc
+        theta = theta + self.tau * theta_dot
+        theta_dot = theta_dot + self.tau * thetaacc
+        self.state = (x, x_dot, theta, theta_dot)
+        terminated = bool(
+            x < -self.x_threshold
+            or x > self.x_threshold
+            or theta < -self.theta_threshold_radians
+            or theta > self.theta_threshold_radians
+        )
+        if not terminated:
+            reward = 1.0
+        elif self.steps_beyond_terminated is None:
+            self.steps_beyond_terminated = 0
+            reward = 1.0
+        else:
+            self.steps_beyond_terminated += 1
+            reward = 0.0
+        return np.array(self.state, dtype=np.float32), reward, terminated, False, {}
+
+
+def angle_normalize(x: float) -> float:
+    # ((x + pi) % (2 pi)) - pi ; Python float % == NumPy float64 % (fmod + sign fix)
+    return ((x + math.pi) % (2 * math.pi)) - math.pi
+
+
+class PendulumEnv:
+    """gym Pendulum-v1 physics (pendulum.py), g=10."""
+
+    def __init__(self, sincos: Callable[[float], Tuple[float, float]] = _libm_sincos):
+        self.max_speed = 8.0
+        self.max_torque = 2.0
+        self.dt = 0.05
+        self.g = 10.0
+        self.m = 1.0
+        self.l = 1.0
+        self.state = None
+        self.np_random = None
+        self._sincos = sincos
+        self.obs_dim = 3
+
+    def _get_obs(self):
+        theta, thetadot = self.state
+        s, c = self._sincos(theta)
+        return np.array([c, s, thetadot], dtype=np.float32)
+
+    def reset(self, seed: Optional[int] = None):
+        if seed is not None or self.np_random is None:
+            self.np_random = np_random(seed)
+        high = np.array([math.pi, 1.0])
+        st = self.np_random.uniform(low=-high, high=high)
+        self.state = (float(st[0]), float(st[1]))
+        return self._get_obs(), {}
+
+    def step(self, u):
+        th, thdot = self.state
+        g, m, l, dt = self.g, self.m, self.l, self.dt
+        u32 = np.float32(np.clip(np.asarray(u, dtype=np.float32), -self.max_torque, self.max_torque).reshape(-1)[0])
+        usq32 = np.float32(u32 * u32)               # u**2 stays float32
+        an = angle_normalize(th)
+        costs = an * an + 0.1 * (thdot * thdot) + 0.001 * float(usq32)
+        s, _ = self._sincos(th)
+        newthdot = thdot + (3 * g / (2 * l) * s + 3.0 / (m * (l * l)) * float(u32)) * dt
+        newthdot = min(max(newthdot, -self.max_speed), self.max_speed)
+        newth = th + newthdot * dt
+        self.state = (newth, newthdot)
+        return self._get_obs(), -costs, False, False, {}
+
+
+class TimeLimit:
+    def __init__(self, env, max_episode_steps: int):
+        self.env = env
+        self._max_episode_steps = max_episode_steps
+        self._elapsed_steps = 0
+
+    def reset(self, seed=None):
+        self._elapsed_steps = 0
+        return self.env.reset(seed=seed)
+
+    def step(self, action):
+        obs, rew, terminated, truncated, info = self.env.step(action)
+        self._elapsed_steps += 1
+        if self._elapsed_steps >= self._max_episode_steps:
+            truncated = True
+        return obs, rew, terminated, truncated, info
+
+
+class RecordEpisodeStatistics:
+    """Single-env form: float32 return accumulator, int32 length."""
+
+    def __init__(self, env):
+        self.env = env
+        self.episode_return = np.float32(0.0)
+        self.episode_length = 0
+
+    def reset(self, seed=None):
+        out = self.env.reset(seed=seed)
+        self.episode_return = np.float32(0.0)
+        self.episode_length = 0
+        return out
+
+    def step(self, action):
+        obs, rew, terminated, truncated, info = self.env.step(action)
+        self.episode_return = np.float32(self.episode_return + np.float32(rew))
+        self.episode_length += 1
+        if terminated or truncated:
+            info = dict(info)
+            info["episode"] = {"r": self.episode_return, "l": self.episode_length}
+            self.episode_return = np.float32(0.0)
+            self.episode_length = 0
+        return obs, rew, terminated, truncated, info
+
+
+class ClipAction:
+    def __init__(self, env, low: float, high: float):
+        self.env, self.low, self.high = env, np.float32(low), np.float32(high)
+
+    def reset(self, seed=None):
+        return self.env.reset(seed=seed)
+
+    def step(self, action):
+        return self.env.step(np.clip(np.asarray(action, dtype=np.float32), self.low, self.high))
+
+
+class RunningMeanStd:
+    """gym/wrappers/normalize.py with batch_count == 1 (one env per wrapper)."""
+
+    def __init__(self, shape=()):
+        self.mean = np.zeros(shape, "float64")
+        self.var = np.ones(shape, "float64")
+        self.count = 1e-4
+
+    def update1(self, x):
+        # batch_mean = x, batch_var = 0, batch_count = 1
+        delta = np.asarray(x, dtype=np.float64) - self.mean
+        tot_count = self.count + 1
+        new_mean = self.mean + delta * 1 / tot_count
+        m_a = self.var * self.count
+        m_b = 0.0 * 1
+        M2 = m_a + m_b + np.square(delta) * self.count * 1 / tot_count
+        self.mean, self.var, self.count = new_mean, M2 / tot_count, tot_count
+
+
+class NormalizeObservation:
+    def __init__(self, env, shape, epsilon=1e-8):
+        self.env, self.epsilon = env, epsilon
+        self.obs_rms = RunningMeanStd(shape)
+
+    def normalize(self, obs):
+        self.obs_rms.update1(obs)
+        return (np.asarray(obs, dtype=np.float64) - self.obs_rms.mean) / np.sqrt(self.obs_rms.var + self.epsilon)
+
+    def reset(self, seed=None):
+        obs, info = self.env.reset(seed=seed)
+        return self.normalize(obs), info
+
+    def step(self, action):
+        obs, rew, terminated, truncated, info = self.env.step(action)
+        return self.normalize(obs), rew, terminated, truncated, info
+
+
+class ClipObservation:
+    """TransformObservation(env, lambda obs: np.clip(obs, -10, 10)) (ppo.py:95)."""
+
+    def __init__(self, env):
+        self.env = env
+
+    def reset(self, seed=None):
+        obs, info = self.env.reset(seed=seed)
+        return np.clip(obs, -10, 10), info
+
+    def step(self, action):
+        obs, rew, terminated, truncated, info = self.env.step(action)
+        return np.clip(obs, -10, 10), rew, terminated, truncated, info
+
+
+class NormalizeReward:
+    def __init__(self, env, gamma=0.99, epsilon=1e-8):
+        self.env, self.gamma, self.epsilon = env, gamma, epsilon
+        self.return_rms = RunningMeanStd(())
+        self.returns = 0.0
+
+    def reset(self, seed=None):
+        return self.env.reset(seed=seed)
+
+    def step(self, action):
+        obs, rew, terminated, truncated, info = self.env.step(action)
+        self.returns = self.returns * self.gamma + float(rew)
+        self.return_rms.update1(self.returns)
+        rew = float(rew) / math.sqrt(float(self.return_rms.var) + self.epsilon)
+        if terminated or truncated:
+            self.returns = 0.0
+        return obs, rew, terminated, truncated, info
+
+
+class ClipReward:
+    """TransformReward(env, lambda r: np.clip(r, -10, 10)) (ppo.py:97)."""
+
+    def __init__(self, env):
+        self.env = env
+
+    def reset(self, seed=None):
+        return self.env.reset(seed=seed)
+
+    def step(self, action):
+        obs, rew, terminated, truncated, info = self.env.step(action)
+        return obs, float(min(max(rew, -10.0), 10.0)), terminated, truncated, info
+
+
+def make_env(gym_id: str, continuous: bool, sincos=_libm_sincos):
+    """The reference's make_env thunk (ppo.py:85-99) without video capture."""
+    if gym_id == "CartPole-v1":
+        env = TimeLimit(CartPoleEnv(sincos), 500)
+        obs_shape = (4,)
+    elif gym_id == "Pendulum-v1":
+        env = TimeLimit(PendulumEnv(sincos), 200)
+        obs_shape = (3,)
+    else:
+        raise ValueError(f"unsupported gym_id {gym_id!r}")
+    env = RecordEpisodeStatistics(env)
+    if continuous:
+        env = ClipAction(env, -2.0, 2.0)
+        env = NormalizeObservation(env, obs_shape)
+        env = ClipObservation(env)
+        env = NormalizeReward(env)
+        env = ClipReward(env)
+    return env
+
+
+class SyncVectorEnv:
+    """gym/vector/sync_vector_env.py: serial stepping, autoreset on
+    terminated-or-truncated, float32 observation buffer, float64 rewards."""
+
+    def __init__(self, envs: Sequence, obs_dim: int):
+        self.envs = list(envs)
+        self.num_envs = len(self.envs)
+        self.observations = np.zeros((self.num_envs, obs_dim), dtype=np.float32)
+        self._rewards = np.zeros((self.num_envs,), dtype=np.float64)
+        self._terminateds = np.zeros((self.num_envs,), dtype=np.bool_)
+        self._truncateds = np.zeros((self.num_envs,), dtype=np.bool_)
+
+    def reset(self, seed: Optional[List[int]] = None):
+        if seed is None:
+            seed = [None] * self.num_envs
+        for i, (env, s) in enumerate(zip(self.envs, seed)):
+            obs, _ = env.reset(seed=s)
+            self.observations[i] = obs
+        return np.copy(self.observations), {}
+
+    def step(self, actions):
+        final_info = [None] * self.num_envs
+        any_final = False
+        for i, (env, action) in enumerate(zip(self.envs, actions)):
+            obs, self._rewards[i], self._terminateds[i], self._truncateds[i], info = env.step(action)
+            if self._terminateds[i] or self._truncateds[i]:
+                final_info[i] = info
+                any_final = True
+                obs, _ = env.reset()
+            self.observations[i] = obs
+        infos = {"final_info": final_info} if any_final else {}
+        return (np.copy(self.observations), np.copy(self._rewards), np.copy(self._terminateds),
+                np.copy(self._truncateds), infos)

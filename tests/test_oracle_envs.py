@@ -1,0 +1,110 @@
+"""Pins the env checker (oracle/envs.c, oracle/gym_restated.py).  CPU only.
+
+The gym boundary is PARITY UNPINNED (third-party gym==0.26.2 is absent and the
+reference holds no env fixtures); what can be pinned is pinned here: NumPy's
+PCG64 stream, the published CartPole reset(seed=0) answer, C == Python
+restatement bit for bit, and the deterministic sincos against a 200-bit
+reference."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import envs as E
+from oracle import gym_restated as G
+
+
+def test_cartpole_reset_seed0_known_answer():
+    env = G.CartPoleEnv()
+    obs, _ = env.reset(seed=0)
+    full = [0.013696168732145436, -0.02302132862361297, -0.045902647606380534, -0.04834723644714709]
+    np.testing.assert_array_equal(obs, np.array(full, np.float32))
+    np.testing.assert_allclose(obs, [0.01369617, -0.02302133, -0.04590265, -0.04834723], rtol=2e-7)
+    assert env.state[0] == 0.013696168732145436
+    cv = E.CVecEnv(E.CARTPOLE, 3)
+    o, _ = cv.reset([0, 1, 2])
+    np.testing.assert_array_equal(o[0], obs)
+
+
+def test_pcg64_stream_matches_numpy():
+    for seed in (0, 1, 12345, 2**40 + 7):
+        st = E.pcg64_seed_states([seed])[0]
+        out = np.empty(64, np.float64)
+        E.lib().orc_pcg64_doubles(int(st[0]), int(st[1]), int(st[2]), int(st[3]), 64, out.ctypes.data)
+        want = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed))).random(64)
+        np.testing.assert_array_equal(out, want)
+
+
+@pytest.mark.parametrize("kind,gid,cont", [(E.CARTPOLE, "CartPole-v1", False), (E.PENDULUM, "Pendulum-v1", True),
+                                           (E.PENDULUM, "Pendulum-v1", False)])
+def test_c_checker_equals_python_restatement(kind, gid, cont):
+    N = 6
+    pv = G.SyncVectorEnv([G.make_env(gid, cont) for _ in range(N)], 4 if kind == 0 else 3)
+    cv = E.CVecEnv(kind, N, wrappers=cont, trig=E.TRIG_LIBM)
+    o1, _ = pv.reset(seed=list(range(N)))
+    o2, _ = cv.reset(list(range(N)))
+    np.testing.assert_array_equal(o1, o2)
+    rng = np.random.default_rng(5)
+    episodes = 0
+    for t in range(700):
+        a = rng.integers(0, 2, N) if kind == 0 else rng.normal(0, 1.5, (N, 1)).astype(np.float32)
+        r1, r2 = pv.step(a), cv.step(a)
+        for k in range(4):
+            np.testing.assert_array_equal(r1[k], r2[k], err_msg=f"t={t} field={k}")
+        if "final_info" in r1[4]:
+            for i, it in enumerate(r1[4]["final_info"]):
+                if it is not None:
+                    e2 = r2[4]["final_info"][i]["episode"]
+                    assert it["episode"]["r"] == e2["r"] and it["episode"]["l"] == e2["l"]
+                    episodes += 1
+    assert episodes > 0
+
+
+def test_timelimit_truncation_keeps_done_zero():
+    """ppo.py:110 discards `truncated`: a TimeLimit reset leaves done = 0."""
+    cv = E.CVecEnv(E.PENDULUM, 2, wrappers=True)
+    cv.reset([0, 1])
+    for t in range(200):
+        _, _, term, trunc, info = cv.step(np.zeros(2, np.float32))
+        assert not term.any()
+    assert trunc.all() and "final_info" in info and info["final_info"][0]["episode"]["l"] == 200
+
+
+def test_det_sincos_correctly_rounded_sample():
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-0.3, 0.3, 1500), rng.uniform(-100, 100, 1500), rng.uniform(-1.6e6, 1.6e6, 500),
+                        [0.0, -0.0, 1e-300, math.pi / 4, -math.pi / 4, math.pi / 2, 3 * math.pi, 1e-9]])
+    s, c = E.det_sincos(x)
+    bad = 0
+    for xi, si, ci in zip(x, s, c):
+        bad += (si != float(mp.sin(mp.mpf(float(xi))))) + (ci != float(mp.cos(mp.mpf(float(xi)))))
+    assert bad <= 1, bad     # correctly rounded except within ~2^-14 ulp of a tie
+
+
+def test_det_vs_libm_discrepancy_is_last_bit_only():
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-0.3, 0.3, 400_000)
+    s, c = E.det_sincos(x)
+    s2, c2 = E.libm_sincos(x)
+    ulp = np.maximum(np.abs(s - s2) / np.spacing(np.abs(s2)), np.abs(c - c2) / np.spacing(np.abs(c2)))
+    assert ulp.max() <= 1.0
+    assert np.mean(s != s2) < 0.01 and np.mean(c != c2) < 0.01
+
+
+def test_det_and_libm_trajectories_agree_on_float32_observations():
+    """Measures what the sincos choice changes at the interface the policy sees."""
+    N, T = 64, 600
+    a_env = E.CVecEnv(E.CARTPOLE, N, trig=E.TRIG_DET)
+    b_env = E.CVecEnv(E.CARTPOLE, N, trig=E.TRIG_LIBM)
+    a_env.reset(list(range(N))); b_env.reset(list(range(N)))
+    rng = np.random.default_rng(11)
+    obs_mismatch = done_mismatch = 0
+    for t in range(T):
+        a = rng.integers(0, 2, N)
+        ra, rb = a_env.step(a), b_env.step(a)
+        obs_mismatch += int((ra[0] != rb[0]).sum())
+        done_mismatch += int((ra[2] != rb[2]).sum())
+    assert done_mismatch == 0
+    assert obs_mismatch <= 4       # fp64 last-bit differences almost never cross a float32 rounding boundary
