@@ -1,0 +1,39 @@
+// Host-side plumbing shared by every entry point of libaurppo.so.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace aur {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return -(1000 + (int)e);
+}
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace aur
+
+extern "C" int aur_abi_version(void) { return AUR_ABI_VERSION; }
+extern "C" const char* aur_last_error(void) { return aur::g_err; }
+extern "C" int64_t aur_launch_count(void) { return aur::g_launches; }
+extern "C" void aur_launch_count_reset(void) { aur::g_launches = 0; }
