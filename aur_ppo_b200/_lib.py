@@ -19,6 +19,29 @@ HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "aur_ppo.h")
 _lib = None
 
 
+class PolicyDesc(ctypes.Structure):
+    _fields_ = [("obs_dim", c_int32), ("act_dim", c_int32), ("hidden_dim", c_int32), ("num_layers", c_int32),
+                ("continuous", c_int32)]
+
+
+class EnvState(ctypes.Structure):
+    _fields_ = [("phys", c_void_p), ("pcg", c_void_p), ("elapsed", c_void_p), ("ep_return", c_void_p),
+                ("ep_length", c_void_p), ("norm", c_void_p)]
+
+
+class EpisodeLog(ctypes.Structure):
+    _fields_ = [("entries", c_void_p), ("count", c_void_p), ("capacity", ctypes.c_uint32)]
+
+
+class RolloutArgs(ctypes.Structure):
+    _fields_ = [("env_kind", c_int32), ("wrappers", c_int32), ("N", c_int64), ("T", c_int32), ("_pad", c_int32),
+                ("policy", PolicyDesc), ("params", c_void_p), ("env", EnvState),
+                ("obs_buf", c_void_p), ("act_buf", c_void_p), ("logp_buf", c_void_p), ("val_buf", c_void_p),
+                ("rew_buf", c_void_p), ("done_buf", c_void_p), ("next_obs", c_void_p), ("next_done", c_void_p),
+                ("next_value", c_void_p), ("actions_in", c_void_p), ("seed", c_uint64), ("step0", c_uint64),
+                ("env_id0", c_uint64), ("log", EpisodeLog), ("gamma", c_double)]
+
+
 class AurError(RuntimeError):
     pass
 
@@ -58,6 +81,17 @@ def lib() -> ctypes.CDLL:
                               c_int32, c_void_p, c_void_p, c_void_p]
     L.aur_gae_kernel_kind.restype = c_int
     L.aur_gae_kernel_kind.argtypes = [c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.aur_policy_param_count.restype = c_int64
+    L.aur_policy_param_count.argtypes = [ctypes.POINTER(PolicyDesc)]
+    L.aur_policy_evaluate.restype = c_int
+    L.aur_policy_evaluate.argtypes = [ctypes.POINTER(PolicyDesc), c_void_p, c_int64, c_void_p, c_void_p, c_uint64,
+                                      c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.aur_env_reset.restype = c_int
+    L.aur_env_reset.argtypes = [c_int32, c_int64, c_int32, ctypes.POINTER(EnvState), c_void_p, c_void_p, c_void_p]
+    L.aur_rollout.restype = c_int
+    L.aur_rollout.argtypes = [ctypes.POINTER(RolloutArgs), c_void_p]
+    L.aur_sincos_f64.restype = c_int
+    L.aur_sincos_f64.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     _lib = L
     return L
 

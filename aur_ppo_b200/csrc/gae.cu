@@ -32,7 +32,7 @@ struct GaeStep {
   __device__ __forceinline__ void init(float next_value, float next_done) {
     v_next = next_value;
     nnt_next = __fsub_rn(1.0f, next_done);
-    last = 0.0f;
+    last = use_gae ? 0.0f : next_value;   // lastgaelam = 0 (ppo.py:127) / next_return = next_value (ppo.py:151)
   }
   // one reference loop iteration (ppo.py:129-140 / ppo.py:149-155)
   __device__ __forceinline__ void step(float r, float v, float term, float& adv, float& ret) {

@@ -1,0 +1,599 @@
+// Fused rollout: T env steps x N envs in one persistent kernel (rows R, Ec, Ep, Ev, M, D of the
+// scope table).  Replaces src/ppo.py:201-205 + rewards_to_go (src/ppo.py:103-123) and the gym
+// pieces it drives (CartPole-v1 / Pendulum-v1 physics, TimeLimit, RecordEpisodeStatistics,
+// SyncVectorEnv autoreset, the continuous wrapper stack of src/ppo.py:92-97).
+//
+// One env per thread (E envs per thread for the small-register discrete config), env state in
+// registers for all T steps, fp64 physics with one rounding per gym operation (--fmad=false),
+// deterministic double-double sin/cos (det_sincos.h), PCG64 reset streams identical to NumPy's,
+// policy MLPs from shared memory (policy.cuh), Philox4x32-10 sampling keyed by the GLOBAL env id.
+// Per step each env writes 36 B (CartPole) into the [T,N] buffers, coalesced across the warp.
+#include "det_sincos.h"
+#include "policy.cuh"
+
+namespace aur {
+
+typedef unsigned __int128 u128;
+
+// ---- PCG64 (setseq 128, XSL-RR) : the generator behind gym's np_random ------------------
+struct Pcg64 {
+  u128 state, inc;
+  __device__ __forceinline__ void load(const uint64_t* pcg, long long N, long long n) {
+    state = ((u128)pcg[0 * N + n] << 64) | pcg[1 * N + n];
+    inc = ((u128)pcg[2 * N + n] << 64) | pcg[3 * N + n];
+  }
+  __device__ __forceinline__ void store(uint64_t* pcg, long long N, long long n) const {
+    pcg[0 * N + n] = (uint64_t)(state >> 64);
+    pcg[1 * N + n] = (uint64_t)state;
+  }
+  __device__ __forceinline__ double next_double() {
+    const u128 MULT = ((u128)0x2360ED051FC65DA4ULL << 64) | 0x4385DF649FCCF645ULL;
+    state = state * MULT + inc;
+    const uint64_t hi = (uint64_t)(state >> 64), lo = (uint64_t)state;
+    const uint64_t x = hi ^ lo;
+    const unsigned rot = (unsigned)(hi >> 58);
+    const uint64_t r = (x >> rot) | (x << ((64u - rot) & 63u));
+    return (double)(r >> 11) * (1.0 / 9007199254740992.0);
+  }
+  // Generator.uniform(low, high) = low + (high - low) * next_double
+  __device__ __forceinline__ double uniform(double low, double range) { return low + range * next_double(); }
+};
+
+// ---- RunningMeanStd.update with batch_count == 1 (gym/wrappers/normalize.py) ------------
+__device__ __forceinline__ void rms_update1(double& mean, double& var, double count, double x) {
+  const double delta = x - mean;
+  const double tot = count + 1.0;
+  const double new_mean = mean + delta * 1.0 / tot;
+  const double m_a = var * count;
+  const double M2 = m_a + 0.0 + delta * delta * count * 1.0 / tot;
+  mean = new_mean;
+  var = M2 / tot;
+}
+__device__ __forceinline__ double clip10(double z) { return z < -10.0 ? -10.0 : (z > 10.0 ? 10.0 : z); }
+
+// Wrapper statistics of one env: obs mean[3], var[3], count; return-rms mean, var, count; acc.
+struct NormState {
+  double om[3], ov[3], oc, rm, rv, rc, racc;
+  __device__ __forceinline__ void init() {
+    for (int k = 0; k < 3; ++k) { om[k] = 0.0; ov[k] = 1.0; }
+    oc = 1e-4; rm = 0.0; rv = 1.0; rc = 1e-4; racc = 0.0;
+  }
+  __device__ __forceinline__ void load(const double* g, long long N, long long n) {
+    for (int k = 0; k < 3; ++k) { om[k] = g[k * N + n]; ov[k] = g[(3 + k) * N + n]; }
+    oc = g[6 * N + n]; rm = g[7 * N + n]; rv = g[8 * N + n]; rc = g[9 * N + n]; racc = g[10 * N + n];
+  }
+  __device__ __forceinline__ void store(double* g, long long N, long long n) const {
+    for (int k = 0; k < 3; ++k) { g[k * N + n] = om[k]; g[(3 + k) * N + n] = ov[k]; }
+    g[6 * N + n] = oc; g[7 * N + n] = rm; g[8 * N + n] = rv; g[9 * N + n] = rc; g[10 * N + n] = racc;
+  }
+  // NormalizeObservation.normalize + clip(-10, 10), result cast to the fp32 obs buffer
+  __device__ __forceinline__ void obs(const float (&raw)[3], float (&out)[POL_IN_PAD]) {
+    for (int k = 0; k < 3; ++k) rms_update1(om[k], ov[k], oc, (double)raw[k]);
+    oc = oc + 1.0;
+    for (int k = 0; k < 3; ++k) out[k] = (float)clip10(((double)raw[k] - om[k]) / sqrt(ov[k] + 1e-8));
+    out[3] = 0.0f;
+  }
+  // NormalizeReward.step + clip(-10, 10)
+  __device__ __forceinline__ double reward(double r, bool done, double gamma) {
+    racc = racc * gamma + r;
+    rms_update1(rm, rv, rc, racc);
+    rc = rc + 1.0;
+    double out = r / sqrt(rv + 1e-8);
+    if (done) racc = 0.0;
+    return clip10(out);
+  }
+};
+
+// ---- CartPole-v1 (gym/envs/classic_control/cartpole.py) ----------------------------------
+struct CartPole {
+  static constexpr int S = 4, OBS = 4, LIMIT = 500;
+  double x, xd, th, thd;
+  __device__ __forceinline__ void load(const double* g, long long N, long long n) {
+    x = g[n]; xd = g[N + n]; th = g[2 * N + n]; thd = g[3 * N + n];
+  }
+  __device__ __forceinline__ void store(double* g, long long N, long long n) const {
+    g[n] = x; g[N + n] = xd; g[2 * N + n] = th; g[3 * N + n] = thd;
+  }
+  __device__ __forceinline__ void reset(Pcg64& rng) {
+    x = rng.uniform(-0.05, 0.05 - (-0.05)); xd = rng.uniform(-0.05, 0.05 - (-0.05));
+    th = rng.uniform(-0.05, 0.05 - (-0.05)); thd = rng.uniform(-0.05, 0.05 - (-0.05));
+  }
+  __device__ __forceinline__ void raw_obs(float (&o)[POL_IN_PAD]) const {
+    o[0] = (float)x; o[1] = (float)xd; o[2] = (float)th; o[3] = (float)thd;
+  }
+  // returns reward; sets terminated
+  __device__ __forceinline__ double step(int action, bool& terminated) {
+    const double gravity = 9.8, masscart = 1.0, masspole = 0.1, length = 0.5, force_mag = 10.0, tau = 0.02;
+    const double total_mass = masspole + masscart, polemass_length = masspole * length;
+    const double theta_thr = 12 * 2 * 3.141592653589793 / 360, x_thr = 2.4;
+    const double force = action == 1 ? force_mag : -force_mag;
+    double sintheta, costheta;
+    aur_sincos(th, &sintheta, &costheta);
+    const double temp = (force + polemass_length * (thd * thd) * sintheta) / total_mass;
+    const double thetaacc = (gravity * sintheta - costheta * temp) /
+                            (length * (4.0 / 3.0 - masspole * (costheta * costheta) / total_mass));
+    const double xacc = temp - polemass_length * thetaacc * costheta / total_mass;
+    x = x + tau * xd;
+    xd = xd + tau * xacc;
+    th = th + tau * thd;
+    thd = thd + tau * thetaacc;
+    terminated = (x < -x_thr) || (x > x_thr) || (th < -theta_thr) || (th > theta_thr);
+    return 1.0;
+  }
+};
+
+// ---- Pendulum-v1 (gym/envs/classic_control/pendulum.py, g = 10) --------------------------
+struct Pendulum {
+  static constexpr int S = 2, OBS = 3, LIMIT = 200;
+  double th, thd;
+  double s_th, c_th;   // sin/cos of the CURRENT theta (the obs needs them, the next step reuses sin)
+  __device__ __forceinline__ void load(const double* g, long long N, long long n) {
+    th = g[n]; thd = g[N + n];
+    aur_sincos(th, &s_th, &c_th);
+  }
+  __device__ __forceinline__ void store(double* g, long long N, long long n) const { g[n] = th; g[N + n] = thd; }
+  __device__ __forceinline__ void reset(Pcg64& rng) {
+    const double PI = 3.141592653589793;
+    th = rng.uniform(-PI, PI - (-PI));
+    thd = rng.uniform(-1.0, 1.0 - (-1.0));
+    aur_sincos(th, &s_th, &c_th);
+  }
+  __device__ __forceinline__ void raw_obs(float (&o)[3]) const { o[0] = (float)c_th; o[1] = (float)s_th; o[2] = (float)thd; }
+  __device__ __forceinline__ double step(float u_in, bool clip_action, bool& terminated) {
+    const double max_speed = 8.0, dt = 0.05, g = 10.0, m = 1.0, l = 1.0, PI = 3.141592653589793;
+    float u = u_in;
+    if (clip_action) u = u < -2.0f ? -2.0f : (u > 2.0f ? 2.0f : u);   // ClipAction wrapper
+    u = u < -2.0f ? -2.0f : (u > 2.0f ? 2.0f : u);                    // np.clip(u, -max_torque, max_torque)
+    const float usq = __fmul_rn(u, u);
+    const double twopi = 2 * PI;
+    double an = fmod(th + PI, twopi);
+    if (an != 0.0 && an < 0.0) an += twopi;
+    an = an - PI;
+    const double costs = an * an + 0.1 * (thd * thd) + 0.001 * (double)usq;
+    double newthd = thd + (3 * g / (2 * l) * s_th + 3.0 / (m * (l * l)) * (double)u) * dt;
+    newthd = newthd < -max_speed ? -max_speed : (newthd > max_speed ? max_speed : newthd);
+    th = th + newthd * dt;
+    thd = newthd;
+    aur_sincos(th, &s_th, &c_th);
+    terminated = false;
+    return -costs;
+  }
+};
+
+struct RolloutDev {
+  long long N;
+  int T, wrappers;
+  int obs_dim, act_dim, nl, continuous;
+  const float* params;
+  aur_env_state env;
+  float *obs_buf, *act_buf, *logp_buf, *val_buf, *rew_buf, *done_buf, *next_obs, *next_done, *next_value;
+  const float* actions_in;
+  uint64_t seed, step0, env_id0;
+  aur_episode_log log;
+  double gamma;
+};
+
+template <int HID>
+__device__ __forceinline__ void load_policy_smem(float* smem, const RolloutDev& a, const float*& sActor,
+                                                 const float*& sCritic, const float*& sLogstd) {
+  const int nA = net_smem_floats(HID, a.nl, a.act_dim), nC = net_smem_floats(HID, a.nl, 1);
+  const int64_t gA = net_param_count(a.obs_dim, HID, a.nl, a.act_dim), gC = net_param_count(a.obs_dim, HID, a.nl, 1);
+  load_net_to_smem(smem, a.params, a.obs_dim, HID, a.nl, a.act_dim, threadIdx.x, blockDim.x);
+  load_net_to_smem(smem + nA, a.params + gA, a.obs_dim, HID, a.nl, 1, threadIdx.x, blockDim.x);
+  if (a.continuous && threadIdx.x < POL_OUT_MAX)
+    smem[nA + nC + threadIdx.x] = threadIdx.x < a.act_dim ? a.params[gA + gC + threadIdx.x] : 0.0f;
+  sActor = smem; sCritic = smem + nA; sLogstd = smem + nA + nC;
+}
+
+__device__ __forceinline__ void log_episode(const aur_episode_log& log, int step, int env, float ret, int len) {
+  if (!log.count) return;
+  const uint32_t idx = atomicAdd(log.count, 1u);
+  if (log.entries && idx < log.capacity) {
+    int4 v = make_int4(step, env, __float_as_int(ret), len);
+    *reinterpret_cast<int4*>(&log.entries[idx]) = v;
+  }
+}
+
+// ENV: CartPole or Pendulum.  E envs per thread (env n = base + e * nthreads_total keeps warps coalesced).
+template <class ENV, int HID, int E>
+__global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
+  extern __shared__ __align__(16) float smem[];
+  const float *sActor, *sCritic, *sLogstd;
+  load_policy_smem<HID>(smem, a, sActor, sCritic, sLogstd);
+  const int policy_floats = net_smem_floats(HID, a.nl, a.act_dim) + net_smem_floats(HID, a.nl, 1) + 4;
+  float* scratch = smem + policy_floats + threadIdx.x;   // [HID][blockDim] column (NL >= 3 only)
+  __syncthreads();
+
+  constexpr bool PEND = ENV::OBS == 3;
+  const long long N = a.N;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+
+  ENV env[E];
+  NormState nm[PEND ? E : 1];
+  float obs[E][POL_IN_PAD];
+  float done_prev[E], ep_ret[E];
+  int elapsed[E], ep_len[E];
+  bool live[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const long long n = base + e * stride;
+    live[e] = n < N;
+    const long long m = live[e] ? n : 0;
+    env[e].load(a.env.phys, N, m);
+    elapsed[e] = a.env.elapsed[m]; ep_ret[e] = a.env.ep_return[m]; ep_len[e] = a.env.ep_length[m];
+    done_prev[e] = a.next_done[m];
+#pragma unroll
+    for (int k = 0; k < POL_IN_PAD; ++k) obs[e][k] = k < ENV::OBS ? a.next_obs[m * ENV::OBS + k] : 0.0f;
+    if constexpr (PEND) { if (a.wrappers) nm[e].load(a.env.norm, N, m); }
+  }
+  NormalConsts nc;
+  if (a.continuous) nc = normal_consts(sLogstd, a.act_dim);
+
+  for (int t = 0; t < a.T; ++t) {
+    // ---- buffer.states[t] = next_obs; buffer.terminals[t] = next_done (ppo.py:203-204)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const long long n = base + e * stride;
+      if (live[e]) {
+        const size_t o = (size_t)t * (size_t)N + (size_t)n;
+        if constexpr (ENV::OBS == 4) {
+          *reinterpret_cast<float4*>(a.obs_buf + o * 4) = make_float4(obs[e][0], obs[e][1], obs[e][2], obs[e][3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < ENV::OBS; ++k) a.obs_buf[o * ENV::OBS + k] = obs[e][k];
+        }
+        a.done_buf[o] = done_prev[e];
+      }
+    }
+    // ---- policy.evaluate(next_obs) (ppo.py:105): actor head, critic value
+    float head[E][POL_OUT_MAX], value[E];
+#pragma unroll 1
+    for (int net = 0; net < 2; ++net) {
+      float o[E][POL_OUT_MAX];
+      mlp_forward<HID, E>(net == 0 ? sActor : sCritic, a.nl, net == 0 ? a.act_dim : 1, obs, o, scratch, blockDim.x);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if (net == 0) {
+#pragma unroll
+          for (int k = 0; k < POL_OUT_MAX; ++k) head[e][k] = o[e][k];
+        } else {
+          value[e] = o[e][0];
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const long long n = base + e * stride;
+      if (!live[e]) continue;
+      const size_t o = (size_t)t * (size_t)N + (size_t)n;
+      const uint64_t gid = a.env_id0 + (uint64_t)n, gstep = a.step0 + (uint64_t)t;
+      float logp, entropy, reward32;
+      bool terminated;
+      double reward;
+      if constexpr (!PEND) {
+        // ---- Categorical sample / replay, env.step
+        int action;
+        const bool sample = a.actions_in == nullptr;
+        float u = 0.0f;
+        if (sample) {
+          const Philox r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)gstep, (uint32_t)(gstep >> 32),
+                                         (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+          u = u01_24(r.c[0]);
+          action = 0;
+        } else {
+          action = (int)a.actions_in[o];
+        }
+        categorical(head[e], a.act_dim, sample, u, action, logp, entropy);
+        a.act_buf[o] = (float)action;
+        reward = env[e].step(action, terminated);
+      } else {
+        float act[POL_OUT_MAX] = {0.f, 0.f, 0.f, 0.f};
+        if (a.actions_in == nullptr) {
+          const Philox r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)gstep, (uint32_t)(gstep >> 32),
+                                         (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+          float z[POL_OUT_MAX];
+          normal4(r, z);
+#pragma unroll
+          for (int k = 0; k < POL_OUT_MAX; ++k) act[k] = fmaf(nc.std[k], z[k], head[e][k]);
+        } else {
+          for (int k = 0; k < a.act_dim; ++k) act[k] = a.actions_in[o * a.act_dim + k];
+        }
+        normal_logp(head[e], act, a.act_dim, nc, logp, entropy);
+        for (int k = 0; k < a.act_dim; ++k) a.act_buf[o * a.act_dim + k] = act[k];
+        reward = env[e].step(act[0], a.wrappers != 0, terminated);
+      }
+      a.logp_buf[o] = logp;
+      a.val_buf[o] = value[e];
+      // ---- TimeLimit, RecordEpisodeStatistics (raw reward, fp32 accumulator)
+      elapsed[e] += 1;
+      const bool truncated = elapsed[e] >= ENV::LIMIT;
+      ep_ret[e] = __fadd_rn(ep_ret[e], (float)reward);
+      ep_len[e] += 1;
+      const bool finished = terminated || truncated;
+      if constexpr (PEND) {
+        // wrappers see the stepped observation before SyncVectorEnv autoresets
+        float raw[3];
+        env[e].raw_obs(raw);
+        if (a.wrappers) {
+          nm[PEND ? e : 0].obs(raw, obs[e]);
+          reward = nm[PEND ? e : 0].reward(reward, finished, a.gamma);
+        } else {
+          obs[e][0] = raw[0]; obs[e][1] = raw[1]; obs[e][2] = raw[2]; obs[e][3] = 0.0f;
+        }
+      } else {
+        env[e].raw_obs(obs[e]);
+      }
+      reward32 = (float)reward;                      // torch.tensor(reward) fp64 -> fp32 buffer (ppo.py:111)
+      a.rew_buf[o] = reward32;
+      if (finished) {
+        // ---- SyncVectorEnv autoreset: the returned obs is the RESET obs; `done` keeps `terminated`
+        log_episode(a.log, (int)gstep, (int)gid, ep_ret[e], ep_len[e]);
+        Pcg64 rng;
+        rng.load(a.env.pcg, N, n);
+        env[e].reset(rng);
+        rng.store(a.env.pcg, N, n);
+        elapsed[e] = 0; ep_ret[e] = 0.0f; ep_len[e] = 0;
+        if constexpr (PEND) {
+          float raw[3];
+          env[e].raw_obs(raw);
+          if (a.wrappers) nm[PEND ? e : 0].obs(raw, obs[e]);
+          else { obs[e][0] = raw[0]; obs[e][1] = raw[1]; obs[e][2] = raw[2]; obs[e][3] = 0.0f; }
+        } else {
+          env[e].raw_obs(obs[e]);
+        }
+      }
+      done_prev[e] = terminated ? 1.0f : 0.0f;       // ppo.py:110 keeps `terminated`, drops `truncated`
+    }
+  }
+
+  // ---- write back: next_obs / next_done / env state, and critic(next_obs) for GAE (ppo.py:161)
+  if (a.next_value) {
+    float o[E][POL_OUT_MAX];
+    mlp_forward<HID, E>(sCritic, a.nl, 1, obs, o, scratch, blockDim.x);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const long long n = base + e * stride;
+      if (live[e]) a.next_value[n] = o[e][0];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const long long n = base + e * stride;
+    if (!live[e]) continue;
+    env[e].store(a.env.phys, N, n);
+    a.env.elapsed[n] = elapsed[e]; a.env.ep_return[n] = ep_ret[e]; a.env.ep_length[n] = ep_len[e];
+    a.next_done[n] = done_prev[e];
+#pragma unroll
+    for (int k = 0; k < ENV::OBS; ++k) a.next_obs[n * ENV::OBS + k] = obs[e][k];
+    if constexpr (PEND) { if (a.wrappers) nm[e].store(a.env.norm, N, n); }
+  }
+}
+
+// envs.reset(seed=list) (ppo.py:188)
+template <class ENV>
+__global__ void env_reset_kernel(long long N, int wrappers, aur_env_state st, float* obs_out, float* done_out) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  Pcg64 rng;
+  rng.load(st.pcg, N, n);
+  ENV env;
+  env.reset(rng);
+  rng.store(st.pcg, N, n);
+  env.store(st.phys, N, n);
+  st.elapsed[n] = 0; st.ep_return[n] = 0.0f; st.ep_length[n] = 0;
+  float obs[POL_IN_PAD];
+  if constexpr (ENV::OBS == 3) {
+    float raw[3];
+    env.raw_obs(raw);
+    if (wrappers) {
+      NormState nm;
+      nm.init();
+      nm.obs(raw, obs);
+      nm.store(st.norm, N, n);
+    } else {
+      obs[0] = raw[0]; obs[1] = raw[1]; obs[2] = raw[2];
+    }
+  } else {
+    env.raw_obs(obs);
+  }
+  for (int k = 0; k < ENV::OBS; ++k) obs_out[n * ENV::OBS + k] = obs[k];
+  if (done_out) done_out[n] = 0.0f;
+}
+
+// actor_critic.evaluate / value on a batch (models/actor_critic.py:31-51), no grad
+template <int HID>
+__global__ void __launch_bounds__(256, 1) policy_evaluate_kernel(RolloutDev a, long long B, const float* obs_in,
+                                                                 uint64_t row0, uint64_t step, float* act_out,
+                                                                 float* logp_out, float* ent_out, float* val_out) {
+  extern __shared__ __align__(16) float smem[];
+  const float *sActor, *sCritic, *sLogstd;
+  load_policy_smem<HID>(smem, a, sActor, sCritic, sLogstd);
+  const int policy_floats = net_smem_floats(HID, a.nl, a.act_dim) + net_smem_floats(HID, a.nl, 1) + 4;
+  float* scratch = smem + policy_floats + threadIdx.x;
+  __syncthreads();
+  NormalConsts nc;
+  if (a.continuous) nc = normal_consts(sLogstd, a.act_dim);
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    float x[1][POL_IN_PAD];
+    for (int k = 0; k < POL_IN_PAD; ++k) x[0][k] = k < a.obs_dim ? obs_in[b * a.obs_dim + k] : 0.0f;
+    float head[1][POL_OUT_MAX], v[1][POL_OUT_MAX];
+    mlp_forward<HID, 1>(sActor, a.nl, a.act_dim, x, head, scratch, blockDim.x);
+    mlp_forward<HID, 1>(sCritic, a.nl, 1, x, v, scratch, blockDim.x);
+    float logp, entropy;
+    const uint64_t gid = row0 + (uint64_t)b;
+    if (!a.continuous) {
+      int action = 0;
+      const bool sample = a.actions_in == nullptr;
+      float u = 0.0f;
+      if (sample) {
+        const Philox r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32),
+                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        u = u01_24(r.c[0]);
+      } else {
+        action = (int)a.actions_in[b];
+      }
+      categorical(head[0], a.act_dim, sample, u, action, logp, entropy);
+      if (act_out) act_out[b] = (float)action;
+    } else {
+      float act[POL_OUT_MAX] = {0.f, 0.f, 0.f, 0.f};
+      if (a.actions_in == nullptr) {
+        const Philox r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32),
+                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        float z[POL_OUT_MAX];
+        normal4(r, z);
+        for (int k = 0; k < POL_OUT_MAX; ++k) act[k] = fmaf(nc.std[k], z[k], head[0][k]);
+      } else {
+        for (int k = 0; k < a.act_dim; ++k) act[k] = a.actions_in[b * a.act_dim + k];
+      }
+      normal_logp(head[0], act, a.act_dim, nc, logp, entropy);
+      if (act_out) for (int k = 0; k < a.act_dim; ++k) act_out[b * a.act_dim + k] = act[k];
+    }
+    if (logp_out) logp_out[b] = logp;
+    if (ent_out) ent_out[b] = entropy;
+    if (val_out) val_out[b] = v[0][0];
+  }
+}
+
+__global__ void sincos_kernel(long long n, const double* x, double* s, double* c) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) aur_sincos(x[i], &s[i], &c[i]);
+}
+
+static int check_policy(const aur_policy_desc& p, const char* who) {
+  if (p.hidden_dim != 64) { set_error("%s: hidden_dim %d not compiled (64 only); no fallback", who, p.hidden_dim); return AUR_ERR_UNSUPPORTED; }
+  if (p.obs_dim < 1 || p.obs_dim > POL_IN_PAD) { set_error("%s: obs_dim %d outside 1..4", who, p.obs_dim); return AUR_ERR_UNSUPPORTED; }
+  if (p.act_dim < 1 || p.act_dim > POL_OUT_MAX) { set_error("%s: act_dim %d outside 1..4", who, p.act_dim); return AUR_ERR_UNSUPPORTED; }
+  if (p.num_layers < 1 || p.num_layers > 16) { set_error("%s: num_layers %d outside 1..16", who, p.num_layers); return AUR_ERR_UNSUPPORTED; }
+  return 0;
+}
+
+static size_t policy_smem_bytes(const aur_policy_desc& p, int threads, bool need_scratch) {
+  size_t f = net_smem_floats(p.hidden_dim, p.num_layers, p.act_dim) + net_smem_floats(p.hidden_dim, p.num_layers, 1) + 4;
+  if (need_scratch) f += (size_t)p.hidden_dim * threads;
+  return f * sizeof(float);
+}
+
+template <class K>
+static int launch_cfg(K kernel, size_t smem) {
+  if (smem > 227 * 1024) { set_error("policy does not fit shared memory (%zu B); no fallback", smem); return AUR_ERR_UNSUPPORTED; }
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  return 0;
+}
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace aur
+
+extern "C" int64_t aur_policy_param_count(const aur_policy_desc* d) {
+  if (!d) return AUR_ERR_ARG;
+  return aur::policy_param_count(*d);
+}
+
+extern "C" int aur_sincos_f64(int64_t n, const double* x, double* s, double* c, void* stream) {
+  using namespace aur;
+  if (n < 0 || (n > 0 && (!x || !s || !c))) { set_error("aur_sincos_f64: bad arguments"); return AUR_ERR_ARG; }
+  if (n == 0) return 0;
+  sincos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((long long)n, x, s, c);
+  AUR_LAUNCH_OK("sincos_kernel");
+  return 0;
+}
+
+extern "C" int aur_env_reset(int32_t env_kind, int64_t N, int32_t wrappers, const aur_env_state* st, float* obs_out,
+                             float* done_out, void* stream) {
+  using namespace aur;
+  if (!st || N < 0 || !obs_out) { set_error("aur_env_reset: bad arguments"); return AUR_ERR_ARG; }
+  if (N == 0) return 0;
+  if (!st->phys || !st->pcg || !st->elapsed || !st->ep_return || !st->ep_length) { set_error("aur_env_reset: null env state array"); return AUR_ERR_ARG; }
+  const unsigned grid = (unsigned)((N + 127) / 128);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (env_kind == AUR_ENV_CARTPOLE) {
+    env_reset_kernel<CartPole><<<grid, 128, 0, s>>>((long long)N, 0, *st, obs_out, done_out);
+  } else if (env_kind == AUR_ENV_PENDULUM) {
+    if (wrappers && !st->norm) { set_error("aur_env_reset: wrappers need env.norm"); return AUR_ERR_ARG; }
+    env_reset_kernel<Pendulum><<<grid, 128, 0, s>>>((long long)N, wrappers, *st, obs_out, done_out);
+  } else {
+    set_error("aur_env_reset: unknown env_kind %d", env_kind); return AUR_ERR_UNSUPPORTED;
+  }
+  AUR_LAUNCH_OK("env_reset_kernel");
+  return 0;
+}
+
+static aur::RolloutDev to_dev(const aur_rollout_args& a) {
+  aur::RolloutDev d;
+  d.N = a.N; d.T = a.T; d.wrappers = a.wrappers;
+  d.obs_dim = a.policy.obs_dim; d.act_dim = a.policy.act_dim; d.nl = a.policy.num_layers; d.continuous = a.policy.continuous;
+  d.params = a.params; d.env = a.env;
+  d.obs_buf = a.obs_buf; d.act_buf = a.act_buf; d.logp_buf = a.logp_buf; d.val_buf = a.val_buf; d.rew_buf = a.rew_buf;
+  d.done_buf = a.done_buf; d.next_obs = a.next_obs; d.next_done = a.next_done; d.next_value = a.next_value;
+  d.actions_in = a.actions_in; d.seed = a.seed; d.step0 = a.step0; d.env_id0 = a.env_id0; d.log = a.log; d.gamma = a.gamma;
+  return d;
+}
+
+extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
+  using namespace aur;
+  if (!args) { set_error("aur_rollout: null args"); return AUR_ERR_ARG; }
+  const aur_rollout_args& a = *args;
+  if (a.N < 0 || a.T < 0) { set_error("aur_rollout: negative N or T"); return AUR_ERR_ARG; }
+  if (a.N == 0 || a.T == 0) return 0;
+  int rc = check_policy(a.policy, "aur_rollout");
+  if (rc) return rc;
+  if (!a.params || !a.obs_buf || !a.act_buf || !a.logp_buf || !a.val_buf || !a.rew_buf || !a.done_buf || !a.next_obs ||
+      !a.next_done || !a.env.phys || !a.env.pcg || !a.env.elapsed || !a.env.ep_return || !a.env.ep_length) {
+    set_error("aur_rollout: null buffer"); return AUR_ERR_ARG;
+  }
+  const bool pend = a.env_kind == AUR_ENV_PENDULUM;
+  if (a.env_kind == AUR_ENV_CARTPOLE) {
+    if (a.policy.continuous || a.policy.obs_dim != 4 || a.policy.act_dim != 2) { set_error("aur_rollout: CartPole needs obs 4, 2 discrete actions"); return AUR_ERR_ARG; }
+  } else if (pend) {
+    if (!a.policy.continuous || a.policy.obs_dim != 3 || a.policy.act_dim != 1) { set_error("aur_rollout: Pendulum needs obs 3, 1 continuous action"); return AUR_ERR_ARG; }
+    if (a.wrappers && !a.env.norm) { set_error("aur_rollout: wrappers need env.norm"); return AUR_ERR_ARG; }
+  } else {
+    set_error("aur_rollout: unknown env_kind %d", a.env_kind); return AUR_ERR_UNSUPPORTED;
+  }
+  const RolloutDev d = to_dev(a);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int sms = sm_count();
+  const bool two = !pend && a.policy.num_layers <= 2 && a.N >= 2LL * 32 * sms;   // E = 2 needs enough envs to fill the chip
+  const long long threads_needed = two ? (a.N + 1) / 2 : a.N;
+  int block = round_up((int)((threads_needed + sms - 1) / sms < 256 ? (threads_needed + sms - 1) / sms : 256), 32);
+  if (block < 64) block = 64;
+  const long long grid = (threads_needed + block - 1) / block;
+  const size_t smem = policy_smem_bytes(a.policy, block, a.policy.num_layers >= 3);
+  if (pend) {
+    if ((rc = launch_cfg(rollout_kernel<Pendulum, 64, 1>, smem))) return rc;
+    rollout_kernel<Pendulum, 64, 1><<<(unsigned)grid, block, smem, s>>>(d);
+  } else if (two) {
+    if ((rc = launch_cfg(rollout_kernel<CartPole, 64, 2>, smem))) return rc;
+    rollout_kernel<CartPole, 64, 2><<<(unsigned)grid, block, smem, s>>>(d);
+  } else {
+    if ((rc = launch_cfg(rollout_kernel<CartPole, 64, 1>, smem))) return rc;
+    rollout_kernel<CartPole, 64, 1><<<(unsigned)grid, block, smem, s>>>(d);
+  }
+  AUR_LAUNCH_OK("rollout_kernel");
+  return 0;
+}
+
+extern "C" int aur_policy_evaluate(const aur_policy_desc* desc, const float* params, int64_t B, const float* obs,
+                                   const float* actions_in, uint64_t seed, uint64_t row0, uint64_t step,
+                                   float* actions_out, float* logp_out, float* entropy_out, float* value_out,
+                                   void* stream) {
+  using namespace aur;
+  if (!desc || !params || B < 0 || (B > 0 && !obs)) { set_error("aur_policy_evaluate: bad arguments"); return AUR_ERR_ARG; }
+  if (B == 0) return 0;
+  int rc = check_policy(*desc, "aur_policy_evaluate");
+  if (rc) return rc;
+  RolloutDev d{};
+  d.obs_dim = desc->obs_dim; d.act_dim = desc->act_dim; d.nl = desc->num_layers; d.continuous = desc->continuous;
+  d.params = params; d.actions_in = actions_in; d.seed = seed;
+  const int block = 128;
+  long long grid = (B + block - 1) / block;
+  if (grid > 4LL * sm_count()) grid = 4LL * sm_count();
+  const size_t smem = policy_smem_bytes(*desc, block, desc->num_layers >= 3);
+  if ((rc = launch_cfg(policy_evaluate_kernel<64>, smem))) return rc;
+  policy_evaluate_kernel<64><<<(unsigned)grid, block, smem, (cudaStream_t)stream>>>(d, (long long)B, obs, row0, step,
+                                                                                  actions_out, logp_out, entropy_out, value_out);
+  AUR_LAUNCH_OK("policy_evaluate_kernel");
+  return 0;
+}

@@ -46,3 +46,80 @@ def gae(rewards: torch.Tensor, values: torch.Tensor, terminals: torch.Tensor, ne
                                     int(bool(use_gae)), adv.data_ptr(), ret.data_ptr(), _stream())
     _lib.check(rc, "aur_gae_f32")
     return ret, adv
+
+
+# ---------------------------------------------------------------------------- policy
+def policy_desc(obs_dim: int, act_dim: int, hidden_dim: int, num_layers: int, continuous: bool) -> _lib.PolicyDesc:
+    return _lib.PolicyDesc(int(obs_dim), int(act_dim), int(hidden_dim), int(num_layers), int(bool(continuous)))
+
+
+def policy_param_count(desc: _lib.PolicyDesc) -> int:
+    import ctypes
+    return int(_lib.lib().aur_policy_param_count(ctypes.byref(desc)))
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def policy_evaluate(desc: _lib.PolicyDesc, params: torch.Tensor, obs: torch.Tensor,
+                    actions: Optional[torch.Tensor] = None, seed: int = 0, row0: int = 0, step: int = 0):
+    """(action, log_prob, entropy, value[B]) of actor_critic.evaluate (models/actor_critic.py:34-51), no grad."""
+    import ctypes
+    params, obs = _f32c(params, "params"), _f32c(obs, "obs")
+    B = obs.shape[0]
+    A = desc.act_dim if desc.continuous else 1
+    if actions is not None:
+        actions = _f32c(actions, "actions")
+    act = torch.empty((B, A) if desc.continuous else (B,), device=obs.device, dtype=torch.float32)
+    logp, ent, val = (torch.empty(B, device=obs.device, dtype=torch.float32) for _ in range(3))
+    with torch.cuda.device(obs.device):
+        rc = _lib.lib().aur_policy_evaluate(ctypes.byref(desc), params.data_ptr(), B, obs.data_ptr(), _ptr(actions),
+                                            seed, row0, step, act.data_ptr(), logp.data_ptr(), ent.data_ptr(),
+                                            val.data_ptr(), _stream())
+    _lib.check(rc, "aur_policy_evaluate")
+    return act, logp, ent, val
+
+
+def sincos_f64(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    if not x.is_cuda or x.dtype != torch.float64 or not x.is_contiguous():
+        raise _lib.AurError("x must be a contiguous CUDA float64 tensor")
+    s, c = torch.empty_like(x), torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().aur_sincos_f64(x.numel(), x.data_ptr(), s.data_ptr(), c.data_ptr(), _stream())
+    _lib.check(rc, "aur_sincos_f64")
+    return s, c
+
+
+# --------------------------------------------------------------------------- rollout
+class RolloutBuffers:
+    """The reference's torch_buffer (src/ppo.py:20-39) on device, same shapes and dtypes."""
+
+    def __init__(self, T: int, N: int, obs_dim: int, act_shape: tuple, device):
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+        self.states = z(T, N, obs_dim)
+        self.actions = z(T, N, *act_shape)
+        self.log_probs, self.rewards, self.terminals, self.values = z(T, N), z(T, N), z(T, N), z(T, N)
+        self.next_value = z(N)
+
+
+def rollout(env, desc: _lib.PolicyDesc, params: torch.Tensor, buf: RolloutBuffers, seed: int, step0: int,
+            actions_in: Optional[torch.Tensor] = None) -> None:
+    """T fused steps (ppo.py:201-205): fills `buf`, advances `env`, leaves critic(next_obs) in buf.next_value."""
+    import ctypes
+    T, N = buf.rewards.shape
+    a = _lib.RolloutArgs()
+    a.env_kind, a.wrappers, a.N, a.T = env.kind, int(env.wrappers), N, T
+    a.policy = desc
+    a.params = _f32c(params, "params").data_ptr()
+    a.env = env.state_struct()
+    a.obs_buf, a.act_buf, a.logp_buf = buf.states.data_ptr(), buf.actions.data_ptr(), buf.log_probs.data_ptr()
+    a.val_buf, a.rew_buf, a.done_buf = buf.values.data_ptr(), buf.rewards.data_ptr(), buf.terminals.data_ptr()
+    a.next_obs, a.next_done, a.next_value = env.next_obs.data_ptr(), env.next_done.data_ptr(), buf.next_value.data_ptr()
+    a.actions_in = None if actions_in is None else _f32c(actions_in, "actions_in").data_ptr()
+    a.seed, a.step0, a.env_id0 = int(seed), int(step0), int(env.env_id0)
+    a.log = env.log_struct()
+    a.gamma = env.gamma
+    with torch.cuda.device(params.device):
+        rc = _lib.lib().aur_rollout(ctypes.byref(a), _stream())
+    _lib.check(rc, "aur_rollout")

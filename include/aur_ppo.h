@@ -68,6 +68,116 @@ int aur_gae_f32(int32_t T, int64_t N, const float* rewards, const float* values,
 int aur_gae_kernel_kind(int32_t T, int64_t N, const float* rewards, const float* values, const float* terminals,
                         const float* adv_out, const float* ret_out);
 
+/* ------------------------------------------------------------- policy ----
+ * The reference's actor_critic (src/models/actor_critic.py:8-26): two
+ * independent MLPs Linear(obs,H)-Tanh-[Linear(H,H)-Tanh]*(num_layers-1)-
+ * Linear(H,out) (src/nets/nets.py:19-53), out = act_dim for the actor and 1
+ * for the critic, plus actor_logstd[act_dim] when continuous.
+ *
+ * Flat parameter buffer (fp32), the order every kernel reads and Adam updates:
+ *   actor : W0[H,obs] b0[H]  W1[H,H] b1[H] ... Wout[act,H] bout[act]
+ *   critic: W0[H,obs] b0[H]  W1[H,H] b1[H] ... Wout[1,H]   bout[1]
+ *   actor_logstd[act]                       (continuous only)
+ * every W row-major [out,in] exactly as torch.nn.Linear.weight. */
+typedef struct {
+  int32_t obs_dim;     /* 4 CartPole, 3 Pendulum (<= 4 compiled) */
+  int32_t act_dim;     /* number of discrete actions, or action dimensions if continuous */
+  int32_t hidden_dim;  /* 64 compiled */
+  int32_t num_layers;  /* number of hidden layers (the reference's num_layers), >= 1 */
+  int32_t continuous;  /* 0 Categorical, 1 diagonal Normal with state-independent std */
+} aur_policy_desc;
+
+int64_t aur_policy_param_count(const aur_policy_desc* desc);
+
+/* Replaces actor_critic.evaluate / .value (src/models/actor_critic.py:31-51) for a
+ * batch of B observations, no grad: obs [B,obs_dim]; actions_in nullable
+ * ([B] action index as fp32 if discrete, [B,act_dim] if continuous) -- when NULL
+ * actions are sampled from the Philox stream (seed, row0 + b, step);
+ * outputs (each nullable): actions [B(,act_dim)] fp32, logp [B], entropy [B], value [B]. */
+int aur_policy_evaluate(const aur_policy_desc* desc, const float* params, int64_t B, const float* obs,
+                        const float* actions_in, uint64_t seed, uint64_t row0, uint64_t step, float* actions_out,
+                        float* logp_out, float* entropy_out, float* value_out, void* stream);
+
+/* ---------------------------------------------------------------- envs ----
+ * Device-resident vector env: replaces gym.vector.SyncVectorEnv over the
+ * make_env thunks (src/ppo.py:66-68,85-99): gym CartPole-v1 / Pendulum-v1
+ * dynamics in fp64, TimeLimit (500 / 200), RecordEpisodeStatistics, autoreset,
+ * and -- when `wrappers` -- the continuous stack ClipAction, NormalizeObservation,
+ * clip +-10, NormalizeReward(gamma), clip +-10 (src/ppo.py:92-97), per env.
+ * All arrays are struct-of-arrays over the N envs this GPU owns. */
+typedef struct {
+  double* phys;       /* [S][N] fp64: CartPole x, x_dot, theta, theta_dot; Pendulum theta, theta_dot */
+  uint64_t* pcg;      /* [4][N] PCG64 state_hi, state_lo, inc_hi, inc_lo (np.random.PCG64(SeedSequence(seed_i))) */
+  int32_t* elapsed;   /* [N] TimeLimit step counter */
+  float* ep_return;   /* [N] RecordEpisodeStatistics accumulator (fp32 as in gym) */
+  int32_t* ep_length; /* [N] */
+  double* norm;       /* [11][N] or NULL: obs mean[3], var[3], count; return-rms mean, var, count; return acc */
+} aur_env_state;
+
+typedef struct {
+  int32_t step;   /* global step index (step0 + t) at which the episode ended */
+  int32_t env;    /* global env id */
+  float ret;      /* info["episode"]["r"] */
+  int32_t len;    /* info["episode"]["l"] */
+} aur_episode;
+
+typedef struct {
+  aur_episode* entries; /* [capacity] or NULL */
+  uint32_t* count;      /* device counter of finished episodes (may exceed capacity; extras are dropped) */
+  uint32_t capacity;
+} aur_episode_log;
+
+/* envs.reset(seed=[...]) (src/ppo.py:188): `st.pcg` must already hold each env's seeded PCG64
+ * state; draws the initial state from it, zeroes counters / wrapper statistics and writes the
+ * first observation [N,obs_dim] and next_done = 0 [N]. */
+int aur_env_reset(int32_t env_kind, int64_t N, int32_t wrappers, const aur_env_state* st, float* obs_out,
+                  float* done_out, void* stream);
+
+/* ------------------------------------------------------------- rollout ----
+ * Replaces the rollout loop src/ppo.py:201-205 + rewards_to_go src/ppo.py:103-123 for T
+ * steps over the N envs of this GPU in ONE kernel: per step store obs/done, run both MLPs,
+ * sample (or take actions_in), store action/logp/value, step the env in fp64, store the
+ * reward, autoreset.  Buffers are the reference's torch_buffer (src/ppo.py:20-29):
+ *   obs_buf [T,N,obs_dim], act_buf [T,N] (discrete, fp32 index) or [T,N,act_dim],
+ *   logp_buf / val_buf / rew_buf / done_buf [T,N]; done_buf[t] is the flag that arrived
+ *   with obs[t] (ppo.py:204) and carries `terminated` only (ppo.py:110 drops `truncated`).
+ * next_obs [N,obs_dim] and next_done [N] are in/out; next_value [N] (nullable) receives
+ * critic(next_obs) after the last step (ppo.py:161).
+ * Sampling: Philox4x32-10, key = seed, counter = (env_id0 + n, step0 + t): independent of how
+ * envs are sharded over GPUs.  actions_in (nullable, same layout as act_buf) replays given
+ * actions instead (parity mode). */
+typedef struct {
+  int32_t env_kind;
+  int32_t wrappers;
+  int64_t N;
+  int32_t T;
+  int32_t _pad;
+  aur_policy_desc policy;
+  const float* params;
+  aur_env_state env;
+  float* obs_buf;
+  float* act_buf;
+  float* logp_buf;
+  float* val_buf;
+  float* rew_buf;
+  float* done_buf;
+  float* next_obs;
+  float* next_done;
+  float* next_value;
+  const float* actions_in;
+  uint64_t seed;
+  uint64_t step0;
+  uint64_t env_id0;
+  aur_episode_log log;
+  double gamma; /* NormalizeReward discount (the wrapper's own default 0.99) */
+} aur_rollout_args;
+
+int aur_rollout(const aur_rollout_args* args, void* stream);
+
+/* Evaluates the deterministic fp64 sin/cos the env kernels use (csrc/det_sincos.h) on n
+ * device doubles -- exported so tests can compare it with the host copy bit for bit. */
+int aur_sincos_f64(int64_t n, const double* x, double* sin_out, double* cos_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,224 @@
+"""Rollout kernel vs the CPU checker (GPU).  Env transitions, rewards and done flags are
+compared BIT FOR BIT (north_star); log-probs and values within 2e-5 (fp32 MLP, fast tanh)."""
+import numpy as np
+import pytest
+import torch
+
+from aur_ppo_b200 import _lib, envs as denv, kernels
+from oracle import envs as E
+from oracle import ppo_ref as R
+from tests.helpers import flat_from_named, golden_policy, random_policy
+
+pytestmark = pytest.mark.gpu
+TOL = dict(rtol=2e-5, atol=2e-6)
+
+
+def test_device_sincos_equals_host_copy_bitwise():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-0.3, 0.3, 200_000), rng.uniform(-100, 100, 200_000),
+                        rng.uniform(-1.6e6, 1.6e6, 100_000), [0.0, -0.0, np.pi / 4, -np.pi / 4, 1e-300, 0.7853981633974484]])
+    s, c = kernels.sincos_f64(torch.from_numpy(x).cuda())
+    hs, hc = E.det_sincos(x)
+    assert np.array_equal(s.cpu().numpy(), hs) and np.array_equal(c.cpu().numpy(), hc)
+
+
+@pytest.mark.parametrize("tag", ["disc", "cont", "disc3", "cont2"])
+def test_policy_evaluate_matches_reference_golden(golden_dir, tag):
+    pol, named, g = golden_policy(golden_dir, tag)
+    nl = len([k for k in named if k.startswith("critic.net.") and k.endswith(".weight")]) - 1
+    obs, act = g[f"{tag}_obs"], g[f"{tag}_act"].astype(np.float32)
+    cont = pol.continuous
+    A = named["actor_logstd"].size if cont else int(named[[k for k in named if k.startswith("actor.net.")][-1]].shape[0])
+    if obs.shape[1] > 4:
+        pytest.skip("obs_dim > 4 is outside the compiled kernels")
+    desc = kernels.policy_desc(obs.shape[1], A, 64, nl, cont)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    assert flat.numel() == kernels.policy_param_count(desc)
+    a, lp, ent, v = kernels.policy_evaluate(desc, flat, torch.from_numpy(obs).cuda(), torch.from_numpy(act).cuda())
+    np.testing.assert_allclose(lp.cpu().numpy(), g[f"{tag}_logp"], **TOL)
+    np.testing.assert_allclose(ent.cpu().numpy(), g[f"{tag}_ent"], **TOL)
+    np.testing.assert_allclose(v.cpu().numpy(), g[f"{tag}_value_flat"], **TOL)
+    np.testing.assert_array_equal(a.cpu().numpy().reshape(act.shape), act)
+
+
+def test_unsupported_shapes_fail_loudly():
+    desc = kernels.policy_desc(4, 2, 128, 2, False)
+    with pytest.raises(_lib.AurError, match="hidden_dim"):
+        kernels.policy_evaluate(desc, torch.zeros(100000, device="cuda"), torch.zeros(4, 4, device="cuda"))
+    with pytest.raises(_lib.AurError, match="no device kernel"):
+        denv.DeviceVecEnv("Acrobot-v1", 4)
+
+
+def _oracle_replay(kind, N, wrappers, seeds, actions, T):
+    cv = E.CVecEnv(kind, N, wrappers=wrappers, trig=E.TRIG_DET)
+    obs0, _ = cv.reset(seeds)
+    D = cv.obs_dim
+    obs = np.zeros((T, N, D), np.float32); rew = np.zeros((T, N), np.float32); done = np.zeros((T, N), np.float32)
+    cur, cur_done = obs0, np.zeros(N, np.float32)
+    episodes = []
+    for t in range(T):
+        obs[t], done[t] = cur, cur_done
+        cur, r, term, trunc, info = cv.step(actions[t])
+        rew[t] = r.astype(np.float32)
+        cur_done = term.astype(np.float32)
+        if "final_info" in info:
+            for i, it in enumerate(info["final_info"]):
+                if it is not None:
+                    episodes.append((t, i, float(it["episode"]["r"]), int(it["episode"]["l"])))
+    return cv, obs0, obs, rew, done, cur, cur_done, episodes
+
+
+@pytest.mark.parametrize("N,T", [(5, 700), (300, 256), (16384, 96)])   # E=1 ragged, E=1, E=2 (>= 9472 envs)
+def test_cartpole_replay_is_bit_exact(N, T):
+    pol, named = random_policy(4, 2, 64, 2, False, seed=3)
+    desc = kernels.policy_desc(4, 2, 64, 2, False)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    seeds = list(range(N))
+    rng = np.random.default_rng(N)
+    actions = rng.integers(0, 2, (T, N))
+    cv, obs0, obs, rew, done, last_obs, last_done, episodes = _oracle_replay(E.CARTPOLE, N, False, seeds, actions, T)
+
+    env = denv.DeviceVecEnv("CartPole-v1", N)
+    o, _ = env.reset(seeds)
+    assert np.array_equal(o.cpu().numpy(), obs0)
+    buf = kernels.RolloutBuffers(T, N, 4, (), "cuda")
+    kernels.rollout(env, desc, flat, buf, seed=1, step0=0, actions_in=torch.from_numpy(actions.astype(np.float32)).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.states.cpu().numpy(), obs)
+    assert np.array_equal(buf.terminals.cpu().numpy(), done)
+    assert np.array_equal(buf.rewards.cpu().numpy(), rew)
+    assert np.array_equal(buf.actions.cpu().numpy(), actions.astype(np.float32))
+    assert np.array_equal(env.next_obs.cpu().numpy(), last_obs)
+    assert np.array_equal(env.next_done.cpu().numpy(), last_done)
+    assert np.array_equal(env.phys.cpu().numpy().T, cv.phys())          # fp64 state, bit for bit
+    got = env.drain_episodes()
+    assert got == sorted(episodes, key=lambda r: (r[0], r[1]))
+    assert len(got) > 0
+    # log-probs / values against the oracle model on the same observations
+    sub = slice(0, min(N, 64))
+    ot = torch.from_numpy(obs[:, sub].reshape(-1, 4)); at = torch.from_numpy(actions[:, sub].reshape(-1))
+    with torch.no_grad():
+        _, lp, _, v = pol.evaluate(ot, at)
+    np.testing.assert_allclose(buf.log_probs[:, sub].cpu().numpy().reshape(-1), lp.numpy(), **TOL)
+    np.testing.assert_allclose(buf.values[:, sub].cpu().numpy().reshape(-1), v.numpy().reshape(-1), **TOL)
+    with torch.no_grad():
+        nv = pol.value(torch.from_numpy(last_obs[sub]))
+    np.testing.assert_allclose(buf.next_value[sub].cpu().numpy(), nv.numpy(), **TOL)
+
+
+@pytest.mark.parametrize("wrappers", [True, False])
+def test_pendulum_replay_is_bit_exact(wrappers):
+    N, T = 200, 450           # crosses two TimeLimit truncations
+    pol, named = random_policy(3, 1, 64, 2, True, seed=4)
+    desc = kernels.policy_desc(3, 1, 64, 2, True)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    seeds = list(range(100, 100 + N))
+    rng = np.random.default_rng(9)
+    actions = rng.normal(0, 1.6, (T, N, 1)).astype(np.float32)
+    cv, obs0, obs, rew, done, last_obs, last_done, episodes = _oracle_replay(E.PENDULUM, N, wrappers, seeds, actions, T)
+    env = denv.DeviceVecEnv("Pendulum-v1", N, wrappers=wrappers)
+    o, _ = env.reset(seeds)
+    assert np.array_equal(o.cpu().numpy(), obs0)
+    buf = kernels.RolloutBuffers(T, N, 3, (1,), "cuda")
+    kernels.rollout(env, desc, flat, buf, seed=1, step0=0, actions_in=torch.from_numpy(actions).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.states.cpu().numpy(), obs)
+    assert np.array_equal(buf.rewards.cpu().numpy(), rew)
+    assert np.array_equal(buf.terminals.cpu().numpy(), done) and not done.any()
+    assert np.array_equal(env.next_obs.cpu().numpy(), last_obs)
+    assert np.array_equal(env.phys.cpu().numpy().T, cv.phys())
+    if wrappers:
+        assert np.array_equal(env.norm.cpu().numpy().T, cv.norm_stats())
+    got = env.drain_episodes()
+    assert [(g[0], g[1], g[3]) for g in got] == [(e[0], e[1], e[3]) for e in sorted(episodes, key=lambda r: (r[0], r[1]))]
+    np.testing.assert_array_equal([g[2] for g in got], [e[2] for e in sorted(episodes, key=lambda r: (r[0], r[1]))])
+    ot = torch.from_numpy(obs[:, :32].reshape(-1, 3)); at = torch.from_numpy(actions[:, :32].reshape(-1, 1))
+    with torch.no_grad():
+        _, lp, _, v = pol.evaluate(ot, at)
+    np.testing.assert_allclose(buf.log_probs[:, :32].cpu().numpy().reshape(-1), lp.numpy(), **TOL)
+    np.testing.assert_allclose(buf.values[:, :32].cpu().numpy().reshape(-1), v.numpy().reshape(-1), **TOL)
+
+
+def test_sampled_rollout_then_replay_on_the_checker():
+    """Sampled mode: the actions the kernel drew, replayed on the CPU checker, reproduce every
+    transition; and the draw follows the Philox stream restated in the oracle."""
+    N, T = 512, 200
+    pol, named = random_policy(4, 2, 64, 2, False, seed=5)
+    desc = kernels.policy_desc(4, 2, 64, 2, False)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    env = denv.DeviceVecEnv("CartPole-v1", N, env_id0=1000)
+    env.reset(list(range(N)))
+    buf = kernels.RolloutBuffers(T, N, 4, (), "cuda")
+    kernels.rollout(env, desc, flat, buf, seed=77, step0=5, actions_in=None)
+    actions = buf.actions.cpu().numpy().astype(np.int64)
+    cv, obs0, obs, rew, done, last_obs, last_done, _ = _oracle_replay(E.CARTPOLE, N, False, list(range(N)), actions, T)
+    assert np.array_equal(buf.states.cpu().numpy(), obs) and np.array_equal(buf.terminals.cpu().numpy(), done)
+    # inverse-CDF rule on the oracle's probabilities with the restated Philox uniform
+    with torch.no_grad():
+        logits = pol._mlp("actor", torch.from_numpy(obs[:3, :40].reshape(-1, 4)))
+        p0 = torch.softmax(logits, -1)[:, 0].numpy().reshape(3, 40)
+    mism = 0
+    for t in range(3):
+        for n in range(40):
+            u = R.u01(R.sampler_words(77, 1000 + n, 5 + t)[0])
+            want = 0 if u < p0[t, n] else 1
+            if abs(float(u) - p0[t, n]) > 1e-5:
+                mism += int(want != actions[t, n])
+    assert mism == 0
+    # action frequencies follow the policy (chi-square style bound on the mean)
+    with torch.no_grad():
+        lg = pol._mlp("actor", torch.from_numpy(obs.reshape(-1, 4)))
+        pm = torch.softmax(lg, -1)[:, 1].mean().item()
+    assert abs(actions.mean() - pm) < 4 * np.sqrt(0.25 / actions.size)
+
+
+def test_sharding_and_chunking_invariance():
+    """Two half-size launches with env_id0 offsets == one launch; two T/2 calls == one T call."""
+    N, T = 256, 64
+    _, named = random_policy(4, 2, 64, 2, False, seed=6)
+    desc = kernels.policy_desc(4, 2, 64, 2, False)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+
+    def run(n, id0, seeds, chunks):
+        env = denv.DeviceVecEnv("CartPole-v1", n, env_id0=id0)
+        env.reset(seeds)
+        outs, step = [], 0
+        for tc in chunks:
+            buf = kernels.RolloutBuffers(tc, n, 4, (), "cuda")
+            kernels.rollout(env, desc, flat, buf, seed=9, step0=step)
+            step += tc
+            outs.append(buf)
+        cat = lambda f: torch.cat([getattr(b, f) for b in outs], 0)
+        return cat("states"), cat("actions"), cat("rewards"), cat("terminals"), cat("log_probs"), env.phys.clone()
+
+    full = run(N, 0, list(range(N)), [T])
+    a = run(N // 2, 0, list(range(N // 2)), [T])
+    b = run(N // 2, N // 2, list(range(N // 2, N)), [T])
+    for i in range(5):
+        assert torch.equal(full[i], torch.cat([a[i], b[i]], 1))
+    assert torch.equal(full[5], torch.cat([a[5], b[5]], 1))
+    two = run(N, 0, list(range(N)), [T // 2, T // 2])
+    for i in range(6):
+        assert torch.equal(full[i], two[i])
+
+
+def test_pendulum_sampling_moments():
+    N, T = 4096, 8
+    pol, named = random_policy(3, 1, 64, 2, True, seed=8)
+    desc = kernels.policy_desc(3, 1, 64, 2, True)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    env = denv.DeviceVecEnv("Pendulum-v1", N, wrappers=True)
+    env.reset(list(range(N)))
+    buf = kernels.RolloutBuffers(T, N, 3, (1,), "cuda")
+    kernels.rollout(env, desc, flat, buf, seed=3, step0=0)
+    obs = buf.states.cpu().reshape(-1, 3)
+    with torch.no_grad():
+        mean = pol._mlp("actor", obs).reshape(-1)
+    std = float(np.exp(named["actor_logstd"].ravel()[0]))
+    z = (buf.actions.cpu().reshape(-1) - mean) / std
+    n = z.numel()
+    assert abs(z.mean().item()) < 5 / np.sqrt(n) and abs(z.var().item() - 1) < 5 * np.sqrt(2 / n)
+    assert abs((z ** 3).mean().item()) < 0.1 and abs((z ** 4).mean().item() - 3) < 0.2
+    with torch.no_grad():
+        _, lp, _, _ = pol.evaluate(obs, buf.actions.cpu().reshape(-1, 1))
+    np.testing.assert_allclose(buf.log_probs.cpu().reshape(-1).numpy(), lp.numpy(), rtol=2e-5, atol=5e-6)
