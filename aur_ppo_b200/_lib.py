@@ -42,6 +42,15 @@ class RolloutArgs(ctypes.Structure):
                 ("env_id0", c_uint64), ("log", EpisodeLog), ("gamma", c_double)]
 
 
+class UpdateArgs(ctypes.Structure):
+    _fields_ = [("policy", PolicyDesc), ("norm_adv", c_int32), ("clip_vloss", c_int32), ("_pad", c_int32),
+                ("m_local", c_int64), ("m_total", c_int64), ("idx", c_void_p), ("idx_offset", c_int64),
+                ("obs", c_void_p), ("actions", c_void_p), ("logprobs", c_void_p), ("advantages", c_void_p),
+                ("returns", c_void_p), ("values", c_void_p), ("params", c_void_p),
+                ("clip_coeff", ctypes.c_float), ("entropy_coeff", ctypes.c_float), ("value_coeff", ctypes.c_float),
+                ("_pad2", ctypes.c_float), ("adv_moments", c_void_p), ("workspace", c_void_p), ("grads_out", c_void_p)]
+
+
 class AurError(RuntimeError):
     pass
 
@@ -90,6 +99,16 @@ def lib() -> ctypes.CDLL:
     L.aur_env_reset.argtypes = [c_int32, c_int64, c_int32, ctypes.POINTER(EnvState), c_void_p, c_void_p, c_void_p]
     L.aur_rollout.restype = c_int
     L.aur_rollout.argtypes = [ctypes.POINTER(RolloutArgs), c_void_p]
+    L.aur_ppo_update_workspace_bytes.restype = c_int64
+    L.aur_ppo_update_workspace_bytes.argtypes = [ctypes.POINTER(PolicyDesc)]
+    L.aur_ppo_adv_moments.restype = c_int
+    L.aur_ppo_adv_moments.argtypes = [c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.aur_ppo_update_grad.restype = c_int
+    L.aur_ppo_update_grad.argtypes = [ctypes.POINTER(UpdateArgs), c_void_p]
+    L.aur_ppo_update_apply.restype = c_int
+    L.aur_ppo_update_apply.argtypes = [ctypes.POINTER(PolicyDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                                       c_double, c_double, c_double, c_int64, c_double, c_int64, c_double, c_double,
+                                       c_void_p, c_void_p]
     L.aur_sincos_f64.restype = c_int
     L.aur_sincos_f64.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     _lib = L

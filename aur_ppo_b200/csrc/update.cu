@@ -1,0 +1,594 @@
+// Fused PPO minibatch update (row U of the scope table): replaces src/ppo.py:220-269.
+//
+//   adv_moments_kernel   sum / sum-of-squares of advantages[idx] in fp64 (minibatch normalisation)
+//   ppo_grad_kernel      gather -> forward -> loss -> backward -> gradient reduction, one launch
+//   grad_reduce_kernel   fixed-order sum of the per-CTA partials -> packed [grads | stats]
+//   adam_kernel          clip_grad_norm_ + torch.optim.Adam math on the flat parameter buffer
+//
+// The actor and the critic are independent MLPs and the PPO loss is separable in them, so
+// blockIdx.y selects the net a CTA trains.  A CTA walks tiles of 256 samples.  Per tile the
+// per-sample work (forward, loss, backward-data) is thread-per-sample with weights broadcast from
+// shared memory into FFMA2 (policy.cuh); the three weight-gradient contractions over the samples
+// (dW3 = dout^T h2, dW2 = dz2^T h1, dW1 = dz1^T x) are CTA-level register-tiled GEMMs over
+// activations staged feature-major in shared memory, their accumulators living in registers for
+// the whole kernel.  This path is fp32-FMA bound (~50 kFLOP per sample vs 40 B gathered).
+#include "policy.cuh"
+
+namespace aur {
+
+constexpr int UPD_THREADS = 256;
+constexpr int UPD_S = 256;             // samples per tile (one per thread in the per-sample phases)
+constexpr int UPD_LD = UPD_S + 4;      // feature-major row stride: 16-B aligned, 4 banks per row
+constexpr int UPD_H = 64;
+constexpr int UPD_PSTRIDE = 4800;      // floats per CTA partial: net gradients + AUR_NUM_STATS
+constexpr int UPD_STAT_OFF = UPD_PSTRIDE - AUR_NUM_STATS;
+constexpr int UPD_SW = 4800;           // smem floats reserved for one net (padded layout)
+constexpr int UPD_SMEM_FLOATS = UPD_SW + UPD_H * UPD_H + UPD_H + 2 * UPD_H * UPD_LD + 2 * 4 * UPD_LD + 4 * UPD_H;
+constexpr size_t UPD_SMEM = sizeof(float) * UPD_SMEM_FLOATS;
+constexpr int MOM_CTAS = 148;
+
+struct UpdDev {
+  long long m_local;
+  const int32_t* idx;
+  long long idx_offset;
+  const float *obs, *actions, *logprobs, *advantages, *returns, *values, *params;
+  int obs_dim, act_dim, continuous, norm_adv, clip_vloss;
+  float clip, clip_lo, clip_hi, ent_c, vf_c, inv_m;
+  const double* moments;
+  float* partials;      // [2][gridDim.x][UPD_PSTRIDE]
+};
+
+__device__ __forceinline__ float block_sum_256(float v, float* sred) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.0f;
+  if (threadIdx.x < 8) t = sred[threadIdx.x];
+  if (threadIdx.x < 32) {
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+  }
+  return t;   // valid in thread 0
+}
+
+// Sum over 64 samples of one feature row (bias gradients): thread -> (row = tid % 64, quarter = tid / 64).
+__device__ __forceinline__ float row_quarter_sum(const float* __restrict__ buf, int tid) {
+  const float* p = buf + (tid & 63) * UPD_LD + (tid >> 6) * 64;
+  float s = 0.0f;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const float4 v = lds4(p + 4 * q);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  return s;
+}
+
+// KIND: 0 actor (Categorical), 1 actor (Normal), 2 critic.
+template <int KIND>
+__device__ void update_net(const UpdDev& a, float* smem) {
+  constexpr bool ACTOR = KIND != 2;
+  const int tid = threadIdx.x;
+  const int OUT = ACTOR ? a.act_dim : 1;
+  const int obs_dim = a.obs_dim;
+  float* sW = smem;
+  float* sW2T = sW + UPD_SW;
+  float* sZero = sW2T + UPD_H * UPD_H;
+  float* Hs = sZero + UPD_H;
+  float* B2 = Hs + UPD_H * UPD_LD;
+  float* sX = B2 + UPD_H * UPD_LD;
+  float* sDout = sX + 4 * UPD_LD;
+  float* sRed = sDout + 4 * UPD_LD;
+
+  // ---- weights of this net -> shared memory (padded layout + transposed copy of W2)
+  const int64_t gA = net_param_count(obs_dim, UPD_H, 2, a.act_dim), gC = net_param_count(obs_dim, UPD_H, 2, 1);
+  const float* gnet = ACTOR ? a.params : a.params + gA;
+  load_net_to_smem(sW, gnet, obs_dim, UPD_H, 2, OUT, tid, UPD_THREADS);
+  const float* sW0 = sW;
+  const float* sB0 = sW + UPD_H * POL_IN_PAD;
+  const float* sW2 = sB0 + UPD_H;
+  const float* sB2 = sW2 + UPD_H * UPD_H;
+  const float* sW3 = sB2 + UPD_H;
+  const float* sB3 = sW3 + OUT * UPD_H;
+  {
+    const float* gW2 = gnet + UPD_H * obs_dim + UPD_H;
+    for (int i = tid; i < UPD_H * UPD_H; i += UPD_THREADS) {
+      const int j = i >> 6, c = i & 63;          // W2[j][c] -> W2T[c][j]
+      sW2T[c * UPD_H + j] = gW2[i];
+    }
+    if (tid < UPD_H) sZero[tid] = 0.0f;
+  }
+  NormalConsts nc;
+  float logstd_g[POL_OUT_MAX] = {0.f, 0.f, 0.f, 0.f};
+  if (KIND == 1) nc = normal_consts(a.params + gA + gC, a.act_dim);
+  float adv_mean = 0.0f, adv_den = 1.0f;
+  if (ACTOR && a.norm_adv) {
+    const double n = a.moments[2], s = a.moments[0], ss = a.moments[1];
+    const double mean = s / n;
+    double var = (ss - s * mean) / (n - 1.0);        // unbiased (torch .std())
+    if (var < 0.0) var = 0.0;
+    adv_mean = (float)mean;
+    adv_den = (float)sqrt(var) + 1e-8f;
+  }
+  __syncthreads();
+
+  // persistent accumulators
+  float2 acc2[4][4];
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) acc2[jj][ii] = make_float2(0.f, 0.f);
+  float acc_w3 = 0.f, acc_b3 = 0.f, acc_w1 = 0.f, acc_b2 = 0.f, acc_b1 = 0.f;
+  float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f, st4 = 0.f;   // loss, entropy, -logr, r-1-logr, clipped
+
+  const int tj = tid >> 4, ti = tid & 15;
+  const long long ntiles = (a.m_local + UPD_S - 1) / UPD_S;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // ================= P1: gather, forward, loss =================
+    const long long gi = tile * UPD_S + tid;
+    const bool valid = gi < a.m_local;
+    const long long row = valid ? (a.idx ? (long long)a.idx[gi] : a.idx_offset + gi) : 0;
+    float x[1][POL_IN_PAD];
+#pragma unroll
+    for (int c = 0; c < POL_IN_PAD; ++c) {
+      x[0][c] = (valid && c < obs_dim) ? __ldg(a.obs + row * obs_dim + c) : 0.0f;
+      sX[c * UPD_LD + tid] = x[0][c];
+    }
+    float2 h1[1][UPD_H / 2];
+    mlp_first_layer<UPD_H, 1>(sW0, sB0, x, h1);
+#pragma unroll
+    for (int jp = 0; jp < UPD_H / 2; ++jp) {
+      Hs[(2 * jp) * UPD_LD + tid] = h1[0][jp].x;
+      Hs[(2 * jp + 1) * UPD_LD + tid] = h1[0][jp].y;
+    }
+    float2 o2[POL_OUT_MAX];
+#pragma unroll
+    for (int k = 0; k < POL_OUT_MAX; ++k) o2[k] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int j0 = 0; j0 < UPD_H; j0 += 8) {
+      float z[1][8];
+      mlp_hidden_block<UPD_H, 1>(sW2, sB2, j0, h1, z);
+      float2 t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        t[q] = make_float2(tanh_fast(z[0][2 * q]), tanh_fast(z[0][2 * q + 1]));
+        B2[(j0 + 2 * q) * UPD_LD + tid] = t[q].x;
+        B2[(j0 + 2 * q + 1) * UPD_LD + tid] = t[q].y;
+      }
+#pragma unroll
+      for (int k = 0; k < POL_OUT_MAX; ++k) {
+        if (k < OUT) {
+          const float4 wa = lds4(sW3 + k * UPD_H + j0), wb = lds4(sW3 + k * UPD_H + j0 + 4);
+          float2 s = __ffma2_rn(make_float2(wa.x, wa.y), t[0], o2[k]);
+          s = __ffma2_rn(make_float2(wa.z, wa.w), t[1], s);
+          s = __ffma2_rn(make_float2(wb.x, wb.y), t[2], s);
+          o2[k] = __ffma2_rn(make_float2(wb.z, wb.w), t[3], s);
+        }
+      }
+    }
+    float out[POL_OUT_MAX], dout[POL_OUT_MAX];
+#pragma unroll
+    for (int k = 0; k < POL_OUT_MAX; ++k) { out[k] = o2[k].x + o2[k].y + (k < OUT ? sB3[k] : 0.0f); dout[k] = 0.0f; }
+
+    if (valid) {
+      if (ACTOR) {
+        const float oldlp = __ldg(a.logprobs + row), adv = __ldg(a.advantages + row);
+        float newlogp, entropy;
+        float dlp[POL_OUT_MAX], dH[POL_OUT_MAX];     // d newlogp / d out_k , d entropy / d out_k
+        if (KIND == 0) {
+          float m = out[0];
+#pragma unroll
+          for (int k = 1; k < POL_OUT_MAX; ++k) if (k < OUT) m = fmaxf(m, out[k]);
+          float se = 0.0f;
+#pragma unroll
+          for (int k = 0; k < POL_OUT_MAX; ++k) if (k < OUT) se += expf(out[k] - m);
+          const float lse = m + logf(se);
+          const int act = (int)__ldg(a.actions + row);
+          float lp[POL_OUT_MAX], pr[POL_OUT_MAX];
+          entropy = 0.0f; newlogp = 0.0f;
+#pragma unroll
+          for (int k = 0; k < POL_OUT_MAX; ++k) {
+            lp[k] = out[k] - lse;
+            pr[k] = k < OUT ? expf(lp[k]) : 0.0f;
+            if (k < OUT) entropy -= pr[k] * lp[k];
+            if (k == act) newlogp = lp[k];
+          }
+#pragma unroll
+          for (int k = 0; k < POL_OUT_MAX; ++k) {
+            dlp[k] = (k == act ? 1.0f : 0.0f) - pr[k];
+            dH[k] = k < OUT ? -pr[k] * (lp[k] + entropy) : 0.0f;
+          }
+        } else {
+          float act[POL_OUT_MAX];
+#pragma unroll
+          for (int k = 0; k < POL_OUT_MAX; ++k) act[k] = k < OUT ? __ldg(a.actions + row * OUT + k) : 0.0f;
+          normal_logp(out, act, OUT, nc, newlogp, entropy);
+#pragma unroll
+          for (int k = 0; k < POL_OUT_MAX; ++k) {
+            const float d = act[k] - out[k], var = nc.std[k] * nc.std[k];
+            dlp[k] = k < OUT ? d / var : 0.0f;
+            dH[k] = 0.0f;
+          }
+        }
+        const float logr = newlogp - oldlp;
+        const float ratio = expf(logr);
+        const float advn = a.norm_adv ? (adv - adv_mean) / adv_den : adv;
+        const float l1 = -advn * ratio;
+        const float l2 = -advn * fminf(fmaxf(ratio, a.clip_lo), a.clip_hi);
+        const float w1 = l1 > l2 ? 1.0f : (l1 == l2 ? 0.5f : 0.0f);
+        const float inr = (ratio >= a.clip_lo && ratio <= a.clip_hi) ? 1.0f : 0.0f;
+        const float g_logp = -advn * (w1 + (1.0f - w1) * inr) * ratio * a.inv_m;
+        const float g_H = -a.ent_c * a.inv_m;
+#pragma unroll
+        for (int k = 0; k < POL_OUT_MAX; ++k) dout[k] = g_logp * dlp[k] + g_H * dH[k];
+        if (KIND == 1) {
+#pragma unroll
+          for (int k = 0; k < POL_OUT_MAX; ++k) {
+            if (k < OUT) {
+              const float d = out[k] - __ldg(a.actions + row * OUT + k);
+              logstd_g[k] += g_logp * (d * d / (nc.std[k] * nc.std[k]) - 1.0f) + g_H;
+            }
+          }
+        }
+        st0 += fmaxf(l1, l2); st1 += entropy; st2 += -logr; st3 += (ratio - 1.0f) - logr;
+        st4 += fabsf(ratio - 1.0f) > a.clip ? 1.0f : 0.0f;
+      } else {
+        const float R = __ldg(a.returns + row), vold = __ldg(a.values + row), v = out[0];
+        if (a.clip_vloss) {
+          const float du = v - R, vu = du * du;
+          const float d = v - vold, vc = vold + fminf(fmaxf(d, -a.clip), a.clip);
+          const float dc = vc - R, lc = dc * dc;
+          const float w1 = vu > lc ? 1.0f : (vu == lc ? 0.5f : 0.0f);
+          const float inr = (d >= -a.clip && d <= a.clip) ? 1.0f : 0.0f;
+          dout[0] = (w1 * du + (1.0f - w1) * dc * inr) * a.vf_c * a.inv_m;
+          st0 += 0.5f * fmaxf(vu, lc);
+        } else {
+          const float d = v - vold;                  // reference quirk ppo.py:261: b_values, not b_returns
+          dout[0] = d * a.vf_c * a.inv_m;
+          st0 += 0.5f * d * d;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < POL_OUT_MAX; ++k) sDout[k * UPD_LD + tid] = dout[k];
+    __syncthreads();
+
+    // ================= G1: dW3 += dout^T h2, db3 += sum dout =================
+    {
+      const int k = tid >> 6, j = tid & 63;
+      if (k < OUT) {
+        const float* hp = B2 + j * UPD_LD;
+        const float* dp = sDout + k * UPD_LD;
+        float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll 8
+        for (int s4 = 0; s4 < UPD_S / 4; ++s4) {
+          const float4 hv = lds4(hp + 4 * s4), dv = lds4(dp + 4 * s4);
+          s2 = __ffma2_rn(make_float2(hv.x, hv.y), make_float2(dv.x, dv.y), s2);
+          s2 = __ffma2_rn(make_float2(hv.z, hv.w), make_float2(dv.z, dv.w), s2);
+        }
+        acc_w3 += s2.x + s2.y;
+      }
+      if (tid < OUT) {
+        const float* dp = sDout + tid * UPD_LD;
+        float s = 0.0f;
+        for (int s4 = 0; s4 < UPD_S / 4; ++s4) { const float4 dv = lds4(dp + 4 * s4); s += (dv.x + dv.y) + (dv.z + dv.w); }
+        acc_b3 += s;
+      }
+    }
+    __syncthreads();
+
+    // ================= P2: dz2 = (W3^T dout) * (1 - h2^2), in place over h2 =================
+#pragma unroll 4
+    for (int j = 0; j < UPD_H; ++j) {
+      const float h2 = B2[j * UPD_LD + tid];
+      float dh = 0.0f;
+#pragma unroll
+      for (int k = 0; k < POL_OUT_MAX; ++k) if (k < OUT) dh = fmaf(sW3[k * UPD_H + j], dout[k], dh);
+      B2[j * UPD_LD + tid] = dh * fmaf(-h2, h2, 1.0f);
+    }
+    __syncthreads();
+
+    // ================= G2: dW2 += dz2^T h1 (64x64 outputs, K = 256 samples), db2 =================
+#pragma unroll 2
+    for (int s4 = 0; s4 < UPD_S / 4; ++s4) {
+      float4 av[4], bv[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) av[jj] = lds4(B2 + (tj + 16 * jj) * UPD_LD + 4 * s4);
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) bv[ii] = lds4(Hs + (ti + 16 * ii) * UPD_LD + 4 * s4);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          float2 s = __ffma2_rn(make_float2(av[jj].x, av[jj].y), make_float2(bv[ii].x, bv[ii].y), acc2[jj][ii]);
+          acc2[jj][ii] = __ffma2_rn(make_float2(av[jj].z, av[jj].w), make_float2(bv[ii].z, bv[ii].w), s);
+        }
+    }
+    acc_b2 += row_quarter_sum(B2, tid);
+
+    // ================= P3: dz1 = (W2^T dz2) * (1 - h1^2) =================
+    float dz1[UPD_H];
+    {
+      float2 dz[1][UPD_H / 2];
+#pragma unroll
+      for (int jp = 0; jp < UPD_H / 2; ++jp)
+        dz[0][jp] = make_float2(B2[(2 * jp) * UPD_LD + tid], B2[(2 * jp + 1) * UPD_LD + tid]);
+#pragma unroll
+      for (int i0 = 0; i0 < UPD_H; i0 += 8) {
+        float z[1][8];
+        mlp_hidden_block<UPD_H, 1>(sW2T, sZero, i0, dz, z);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const float hv = Hs[(i0 + jj) * UPD_LD + tid];
+          dz1[i0 + jj] = z[0][jj] * fmaf(-hv, hv, 1.0f);
+        }
+      }
+    }
+    __syncthreads();            // every thread is done reading h1 (G2, P3)
+#pragma unroll
+    for (int i = 0; i < UPD_H; ++i) Hs[i * UPD_LD + tid] = dz1[i];
+    __syncthreads();
+
+    // ================= G3: dW1 += dz1^T x, db1 =================
+    {
+      const int c = tid >> 6, j = tid & 63;
+      const float* zp = Hs + j * UPD_LD;
+      const float* xp = sX + c * UPD_LD;
+      float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll 8
+      for (int s4 = 0; s4 < UPD_S / 4; ++s4) {
+        const float4 zv = lds4(zp + 4 * s4), xv = lds4(xp + 4 * s4);
+        s2 = __ffma2_rn(make_float2(zv.x, zv.y), make_float2(xv.x, xv.y), s2);
+        s2 = __ffma2_rn(make_float2(zv.z, zv.w), make_float2(xv.z, xv.w), s2);
+      }
+      acc_w1 += s2.x + s2.y;
+      acc_b1 += row_quarter_sum(Hs, tid);
+    }
+    __syncthreads();            // tile buffers free for the next tile
+  }
+
+  // ---- write this CTA's partial (the net's flat parameter order, then statistics)
+  float* part = a.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * UPD_PSTRIDE;
+  const int oW1 = 0, oB1 = UPD_H * obs_dim, oW2 = oB1 + UPD_H, oB2 = oW2 + UPD_H * UPD_H, oW3 = oB2 + UPD_H,
+            oB3 = oW3 + OUT * UPD_H, oLS = oB3 + OUT;
+  {
+    const int c = tid >> 6, j = tid & 63;
+    if (c < obs_dim) part[oW1 + j * obs_dim + c] = acc_w1;
+    if (c < OUT) part[oW3 + c * UPD_H + j] = acc_w3;
+    if (tid < OUT) part[oB3 + tid] = acc_b3;
+  }
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+      part[oW2 + (tj + 16 * jj) * UPD_H + (ti + 16 * ii)] = acc2[jj][ii].x + acc2[jj][ii].y;
+  // bias row-sums: 4 quarter partials per row -> combine through shared memory
+  __syncthreads();
+  sRed[tid] = acc_b2;
+  Hs[tid] = acc_b1;
+  __syncthreads();
+  if (tid < UPD_H) {
+    part[oB2 + tid] = (sRed[tid] + sRed[tid + 64]) + (sRed[tid + 128] + sRed[tid + 192]);
+    part[oB1 + tid] = (Hs[tid] + Hs[tid + 64]) + (Hs[tid + 128] + Hs[tid + 192]);
+  }
+  float* sred8 = B2;   // scratch for block sums
+  float s;
+  if (KIND == 1) {
+    for (int k = 0; k < POL_OUT_MAX; ++k) {
+      s = block_sum_256(logstd_g[k], sred8);
+      if (tid == 0 && k < OUT) part[oLS + k] = s;
+    }
+  }
+  float* stat = part + UPD_STAT_OFF;
+  s = block_sum_256(st0, sred8); if (tid == 0) stat[ACTOR ? AUR_STAT_POLICY_LOSS : AUR_STAT_VALUE_LOSS] = s;
+  if (ACTOR) {
+    s = block_sum_256(st1, sred8); if (tid == 0) stat[AUR_STAT_ENTROPY] = s;
+    s = block_sum_256(st2, sred8); if (tid == 0) stat[AUR_STAT_OLD_APPROX_KL] = s;
+    s = block_sum_256(st3, sred8); if (tid == 0) stat[AUR_STAT_APPROX_KL] = s;
+    s = block_sum_256(st4, sred8); if (tid == 0) stat[AUR_STAT_CLIPFRAC] = s;
+  }
+}
+
+__global__ void __launch_bounds__(UPD_THREADS, 1) ppo_grad_kernel(UpdDev a) {
+  extern __shared__ __align__(16) float smem[];
+  if (blockIdx.y == 0) {
+    if (a.continuous) update_net<1>(a, smem);
+    else update_net<0>(a, smem);
+  } else {
+    update_net<2>(a, smem);
+  }
+}
+
+// grads_out[p] = sum over CTAs of the partials, in CTA order, fp64 accumulation.
+__global__ void grad_reduce_kernel(const float* __restrict__ partials, int ncta, int obs_dim, int act_dim, int continuous,
+                                   float* __restrict__ grads_out) {
+  const int64_t nA = net_param_count(obs_dim, UPD_H, 2, act_dim), nC = net_param_count(obs_dim, UPD_H, 2, 1);
+  const int64_t P = nA + nC + (continuous ? act_dim : 0);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P + AUR_NUM_STATS) return;
+  int net; int64_t off;
+  if (i < nA) { net = 0; off = i; }
+  else if (i < nA + nC) { net = 1; off = i - nA; }
+  else if (i < P) { net = 0; off = nA + (i - nA - nC); }          // actor_logstd sits after the actor's own params
+  else {
+    const int sidx = (int)(i - P);
+    net = (sidx == AUR_STAT_VALUE_LOSS) ? 1 : 0;
+    off = UPD_STAT_OFF + sidx;
+    if (sidx > AUR_STAT_CLIPFRAC) { grads_out[i] = 0.0f; return; }
+  }
+  const float* p = partials + (size_t)net * ncta * UPD_PSTRIDE + off;
+  double s = 0.0;
+  for (int c = 0; c < ncta; ++c) s += (double)p[(size_t)c * UPD_PSTRIDE];
+  grads_out[i] = (float)s;
+}
+
+// sum / sum of squares of advantages[idx] (fp64), finalised by the last CTA to finish.
+__global__ void __launch_bounds__(256) adv_moments_kernel(long long m, const int32_t* __restrict__ idx, long long idx_offset,
+                                                        const float* __restrict__ adv, double* __restrict__ partial,
+                                                        unsigned int* __restrict__ ticket, double* __restrict__ out) {
+  __shared__ double sh[2][8];
+  __shared__ bool last;
+  double s = 0.0, ss = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx ? (long long)idx[i] : idx_offset + i;
+    const double v = (double)__ldg(adv + row);
+    s += v; ss += v * v;
+  }
+  s = warp_sum(s); ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
+    partial[2 * blockIdx.x] = a; partial[2 * blockIdx.x + 1] = b;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (unsigned c = 0; c < gridDim.x; ++c) { a += partial[2 * c]; b += partial[2 * c + 1]; }   // fixed order
+    out[0] = a; out[1] = b; out[2] = (double)m;
+    *ticket = 0u;
+  }
+}
+
+// clip_grad_norm_ (all parameters, torch semantics) + Adam, one CTA (P ~ 9e3).
+__global__ void __launch_bounds__(1024) adam_kernel(int64_t P, float* __restrict__ params, const float* __restrict__ g_in,
+                                                   float* __restrict__ m1, float* __restrict__ m2, float lr_over_bc1,
+                                                   float beta1, float beta2, float eps, float sqrt_bc2, float max_norm,
+                                                   float inv_m, float ent_c, float vf_c, float* __restrict__ stats_out) {
+  __shared__ double sh[32];
+  __shared__ float coef_s, norm_s;
+  double ss = 0.0;
+  for (int64_t i = threadIdx.x; i < P; i += blockDim.x) { const double g = g_in[i]; ss += g * g; }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += sh[w];
+    const float total = (float)sqrt(t);
+    float coef = max_norm / (total + 1e-6f);
+    coef = coef > 1.0f ? 1.0f : coef;
+    coef_s = coef; norm_s = total;
+  }
+  __syncthreads();
+  const float coef = coef_s;
+  for (int64_t i = threadIdx.x; i < P; i += blockDim.x) {
+    const float g = g_in[i] * coef;
+    float m = m1[i], v = m2[i];
+    m = m + (g - m) * (1.0f - beta1);                        // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * beta2 + (1.0f - beta2) * g * g;                  // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    const float denom = sqrtf(v) / sqrt_bc2 + eps;
+    params[i] = params[i] - lr_over_bc1 * (m / denom);       // param.addcdiv_(exp_avg, denom, value=-step_size)
+    m1[i] = m; m2[i] = v;
+  }
+  if (stats_out && threadIdx.x < AUR_NUM_STATS) {
+    const float* st = g_in + P;
+    float v = 0.0f;
+    if (threadIdx.x <= AUR_STAT_CLIPFRAC) v = st[threadIdx.x] * inv_m;
+    if (threadIdx.x == AUR_STAT_GRAD_NORM) v = norm_s;
+    if (threadIdx.x == AUR_STAT_LOSS)
+      v = st[AUR_STAT_POLICY_LOSS] * inv_m - ent_c * (st[AUR_STAT_ENTROPY] * inv_m) + (st[AUR_STAT_VALUE_LOSS] * inv_m) * vf_c;
+    stats_out[threadIdx.x] = v;
+  }
+}
+
+static int upd_grid_x() {
+  int g = sm_count() / 2;
+  return g < 1 ? 1 : g;
+}
+// workspace: [2][grid_x][PSTRIDE] partials | moments partials (fp64) | ticket
+static size_t ws_partials_floats() { return (size_t)2 * upd_grid_x() * UPD_PSTRIDE; }
+static size_t ws_bytes() { return ws_partials_floats() * sizeof(float) + (2 * MOM_CTAS) * sizeof(double) + 64; }
+
+static int check_update_policy(const aur_policy_desc& p, const char* who) {
+  if (p.hidden_dim != 64 || p.num_layers != 2) {
+    set_error("%s: compiled for hidden_dim 64, num_layers 2 (got %d, %d); no fallback", who, p.hidden_dim, p.num_layers);
+    return AUR_ERR_UNSUPPORTED;
+  }
+  if (p.obs_dim < 1 || p.obs_dim > POL_IN_PAD || p.act_dim < 1 || p.act_dim > POL_OUT_MAX) {
+    set_error("%s: obs_dim %d / act_dim %d outside 1..4", who, p.obs_dim, p.act_dim);
+    return AUR_ERR_UNSUPPORTED;
+  }
+  return 0;
+}
+
+}  // namespace aur
+
+extern "C" int64_t aur_ppo_update_workspace_bytes(const aur_policy_desc* desc) {
+  if (!desc) return AUR_ERR_ARG;
+  return (int64_t)aur::ws_bytes();
+}
+
+extern "C" int aur_ppo_adv_moments(int64_t m, const int32_t* idx, int64_t idx_offset, const float* advantages,
+                                   double* moments_out, float* workspace, void* stream) {
+  using namespace aur;
+  if (m <= 0 || !advantages || !moments_out || !workspace) { set_error("aur_ppo_adv_moments: bad arguments"); return AUR_ERR_ARG; }
+  double* partial = reinterpret_cast<double*>(workspace + ws_partials_floats());
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + 2 * MOM_CTAS);
+  long long grid = (m + 255) / 256;
+  if (grid > MOM_CTAS) grid = MOM_CTAS;
+  adv_moments_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((long long)m, idx, (long long)idx_offset, advantages,
+                                                                      partial, ticket, moments_out);
+  AUR_LAUNCH_OK("adv_moments_kernel");
+  return 0;
+}
+
+extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
+  using namespace aur;
+  if (!args) { set_error("aur_ppo_update_grad: null args"); return AUR_ERR_ARG; }
+  const aur_update_args& u = *args;
+  int rc = check_update_policy(u.policy, "aur_ppo_update_grad");
+  if (rc) return rc;
+  if (u.m_local < 0 || u.m_total <= 0 || !u.obs || !u.actions || !u.logprobs || !u.advantages || !u.returns || !u.values ||
+      !u.params || !u.workspace || !u.grads_out || (u.norm_adv && !u.adv_moments)) {
+    set_error("aur_ppo_update_grad: bad arguments"); return AUR_ERR_ARG;
+  }
+  UpdDev d;
+  d.m_local = u.m_local; d.idx = u.idx; d.idx_offset = u.idx_offset;
+  d.obs = u.obs; d.actions = u.actions; d.logprobs = u.logprobs; d.advantages = u.advantages; d.returns = u.returns;
+  d.values = u.values; d.params = u.params;
+  d.obs_dim = u.policy.obs_dim; d.act_dim = u.policy.act_dim; d.continuous = u.policy.continuous;
+  d.norm_adv = u.norm_adv; d.clip_vloss = u.clip_vloss;
+  d.clip = u.clip_coeff;
+  d.clip_lo = (float)(1.0 - (double)u.clip_coeff); d.clip_hi = (float)(1.0 + (double)u.clip_coeff);
+  d.ent_c = u.entropy_coeff; d.vf_c = u.value_coeff; d.inv_m = (float)(1.0 / (double)u.m_total);
+  d.moments = u.adv_moments; d.partials = u.workspace;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AUR_CUDA_OK(cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
+    attr_set = true;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int gx = upd_grid_x();
+  ppo_grad_kernel<<<dim3(gx, 2), UPD_THREADS, UPD_SMEM, s>>>(d);
+  AUR_LAUNCH_OK("ppo_grad_kernel");
+  const int64_t P = policy_param_count(u.policy);
+  const int total = (int)(P + AUR_NUM_STATS);
+  grad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(u.workspace, gx, u.policy.obs_dim, u.policy.act_dim,
+                                                        u.policy.continuous, u.grads_out);
+  AUR_LAUNCH_OK("grad_reduce_kernel");
+  return 0;
+}
+
+extern "C" int aur_ppo_update_apply(const aur_policy_desc* desc, float* params, const float* grads_packed, float* adam_m,
+                                    float* adam_v, double lr, double beta1, double beta2, double eps, int64_t step,
+                                    double max_grad_norm, int64_t m_total, double entropy_coeff, double value_coeff,
+                                    float* stats_out, void* stream) {
+  using namespace aur;
+  if (!desc || !params || !grads_packed || !adam_m || !adam_v || step < 1 || m_total <= 0) {
+    set_error("aur_ppo_update_apply: bad arguments"); return AUR_ERR_ARG;
+  }
+  const int64_t P = policy_param_count(*desc);
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(P, params, grads_packed, adam_m, adam_v, (float)(lr / bc1), (float)beta1,
+                                                   (float)beta2, (float)eps, (float)sqrt(bc2), (float)max_grad_norm,
+                                                   (float)(1.0 / (double)m_total), (float)entropy_coeff, (float)value_coeff,
+                                                   stats_out);
+  AUR_LAUNCH_OK("adam_kernel");
+  return 0;
+}

@@ -123,3 +123,87 @@ def rollout(env, desc: _lib.PolicyDesc, params: torch.Tensor, buf: RolloutBuffer
     with torch.cuda.device(params.device):
         rc = _lib.lib().aur_rollout(ctypes.byref(a), _stream())
     _lib.check(rc, "aur_rollout")
+
+
+# ---------------------------------------------------------------------------- update
+STAT_NAMES = ["policy_loss", "value_loss", "entropy", "old_approx_kl", "approx_kl", "clipfrac", "grad_norm", "loss"]
+NUM_STATS = 16
+
+
+class Updater:
+    """Device state of the optimiser side of ppo.train (src/ppo.py:80,213-269): Adam moments,
+    packed gradient buffer, workspace.  `allreduce` (optional) is called on the fp64 advantage
+    moments and on the packed fp32 [grads | stats] buffer -- the only exchanges of a
+    data-parallel run."""
+
+    def __init__(self, desc: _lib.PolicyDesc, params: torch.Tensor, eps: float = 1e-5, betas=(0.9, 0.999),
+                 allreduce=None):
+        import ctypes
+        self.desc, self.params = desc, _f32c(params, "params")
+        dev = params.device
+        self.P = policy_param_count(desc)
+        if params.numel() != self.P:
+            raise _lib.AurError(f"flat parameter buffer has {params.numel()} elements, policy needs {self.P}")
+        self.exp_avg = torch.zeros(self.P, device=dev)
+        self.exp_avg_sq = torch.zeros(self.P, device=dev)
+        self.grads = torch.zeros(self.P + NUM_STATS, device=dev)
+        self.moments = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.stats = torch.zeros(NUM_STATS, device=dev)
+        ws = int(_lib.lib().aur_ppo_update_workspace_bytes(ctypes.byref(desc)))
+        self.workspace = torch.zeros((ws + 3) // 4, dtype=torch.float32, device=dev)
+        self.eps, self.betas, self.step_count, self.allreduce = float(eps), betas, 0, allreduce
+
+    def grad(self, b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values, idx: Optional[torch.Tensor],
+             m_total: Optional[int] = None, idx_offset: int = 0, m_local: Optional[int] = None, clip_coeff=0.2,
+             entropy_coeff=0.01, value_coeff=0.5, norm_adv=True, clip_vloss=True) -> torch.Tensor:
+        """Phases 1-2 (moments, gather+fwd+loss+bwd+reduce) -> packed [grads | stat sums] on device."""
+        import ctypes
+        L = _lib.lib()
+        if idx is not None:
+            if idx.dtype != torch.int32 or not idx.is_cuda or not idx.is_contiguous():
+                raise _lib.AurError("idx must be a contiguous CUDA int32 tensor")
+            m_local = idx.numel()
+        elif m_local is None:
+            raise _lib.AurError("give idx or m_local")
+        m_total = int(m_total if m_total is not None else m_local)
+        for n, t in (("obs", b_obs), ("actions", b_actions), ("logprobs", b_logprobs), ("advantages", b_advantages),
+                     ("returns", b_returns), ("values", b_values)):
+            _f32c(t, n)
+        with torch.cuda.device(self.params.device):
+            st = _stream()
+            if norm_adv:
+                _lib.check(L.aur_ppo_adv_moments(m_local, _ptr(idx), idx_offset, b_advantages.data_ptr(),
+                                                 self.moments.data_ptr(), self.workspace.data_ptr(), st), "aur_ppo_adv_moments")
+                if self.allreduce is not None:
+                    self.allreduce(self.moments)
+            a = _lib.UpdateArgs()
+            a.policy, a.norm_adv, a.clip_vloss = self.desc, int(bool(norm_adv)), int(bool(clip_vloss))
+            a.m_local, a.m_total, a.idx, a.idx_offset = m_local, m_total, _ptr(idx), idx_offset
+            a.obs, a.actions, a.logprobs = b_obs.data_ptr(), b_actions.data_ptr(), b_logprobs.data_ptr()
+            a.advantages, a.returns, a.values = b_advantages.data_ptr(), b_returns.data_ptr(), b_values.data_ptr()
+            a.params = self.params.data_ptr()
+            a.clip_coeff, a.entropy_coeff, a.value_coeff = float(clip_coeff), float(entropy_coeff), float(value_coeff)
+            a.adv_moments = self.moments.data_ptr() if norm_adv else None
+            a.workspace, a.grads_out = self.workspace.data_ptr(), self.grads.data_ptr()
+            _lib.check(L.aur_ppo_update_grad(ctypes.byref(a), st), "aur_ppo_update_grad")
+            if self.allreduce is not None:
+                self.allreduce(self.grads)
+        self._m_total, self._ent_c, self._vf_c = m_total, float(entropy_coeff), float(value_coeff)
+        return self.grads
+
+    def apply(self, lr: float, max_grad_norm: float = 0.5) -> torch.Tensor:
+        """Phase 3: clip_grad_norm_ + Adam in place on the flat parameters; returns the stats tensor (device)."""
+        import ctypes
+        self.step_count += 1
+        with torch.cuda.device(self.params.device):
+            rc = _lib.lib().aur_ppo_update_apply(ctypes.byref(self.desc), self.params.data_ptr(), self.grads.data_ptr(),
+                                                 self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), float(lr),
+                                                 self.betas[0], self.betas[1], self.eps, self.step_count,
+                                                 float(max_grad_norm), self._m_total, self._ent_c, self._vf_c,
+                                                 self.stats.data_ptr(), _stream())
+        _lib.check(rc, "aur_ppo_update_apply")
+        return self.stats
+
+    def step(self, *args, lr: float, max_grad_norm: float = 0.5, **kw) -> torch.Tensor:
+        self.grad(*args, **kw)
+        return self.apply(lr, max_grad_norm)

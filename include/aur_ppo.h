@@ -174,6 +174,67 @@ typedef struct {
 
 int aur_rollout(const aur_rollout_args* args, void* stream);
 
+/* -------------------------------------------------------------- update ----
+ * Replaces one minibatch step of src/ppo.py:220-269: gather of the shuffled indices,
+ * actor_critic.evaluate with grad, ratio / KL / clip-fraction diagnostics, minibatch
+ * advantage normalisation (unbiased std + 1e-8), clipped surrogate, clipped value loss,
+ * entropy bonus, backward, clip_grad_norm_(all params), Adam(eps=1e-5).
+ *
+ * Split in phases so that the one exchange of a data-parallel run (an allreduce of the
+ * packed gradient buffer, and of the three advantage moments) sits between them:
+ *   aur_ppo_adv_moments   sum / sum of squares / count of advantages[idx]      (fp64)
+ *   aur_ppo_update_grad   gather + forward + loss + backward, reduced over the minibatch
+ *                         into grads_out = [P gradient sums | 16 statistic sums]
+ *   aur_ppo_update_apply  grad-norm clip + Adam on the flat parameter buffer, statistics
+ * The actor and the critic are independent MLPs with separable losses, so half of the
+ * CTAs train each net.  Gradients are reduced in a fixed order (deterministic). */
+typedef struct {
+  aur_policy_desc policy;    /* num_layers == 2 compiled */
+  int32_t norm_adv;          /* ppo.py:238 */
+  int32_t clip_vloss;        /* ppo.py:250; 0 reproduces the reference's b_values quirk (ppo.py:261) */
+  int32_t _pad;
+  int64_t m_local;           /* samples of this GPU's share of the minibatch */
+  int64_t m_total;           /* samples of the whole minibatch (means divide by this) */
+  const int32_t* idx;        /* [m_local] row indices into the flattened buffers, or NULL: idx_offset + i */
+  int64_t idx_offset;
+  const float* obs;          /* b_obs        [B,obs_dim]            (ppo.py:33) */
+  const float* actions;      /* b_actions    [B] or [B,act_dim]     (ppo.py:35) */
+  const float* logprobs;     /* b_logprobs   [B] */
+  const float* advantages;   /* b_advantages [B] */
+  const float* returns;      /* b_returns    [B] */
+  const float* values;       /* b_values     [B] */
+  const float* params;       /* flat parameter buffer */
+  float clip_coeff, entropy_coeff, value_coeff, _pad2;
+  const double* adv_moments; /* [3] device: sum, sum of squares, count over the WHOLE minibatch; NULL iff !norm_adv */
+  float* workspace;          /* >= aur_ppo_update_workspace_bytes() */
+  float* grads_out;          /* [P + 16] */
+} aur_update_args;
+
+#define AUR_STAT_POLICY_LOSS 0   /* sums over samples; aur_ppo_update_apply turns them into means */
+#define AUR_STAT_VALUE_LOSS 1
+#define AUR_STAT_ENTROPY 2
+#define AUR_STAT_OLD_APPROX_KL 3
+#define AUR_STAT_APPROX_KL 4
+#define AUR_STAT_CLIPFRAC 5
+#define AUR_STAT_GRAD_NORM 6     /* written by aur_ppo_update_apply (pre-clip total norm) */
+#define AUR_STAT_LOSS 7          /* policy - ent_c * entropy + vf_c * value */
+#define AUR_NUM_STATS 16
+
+int64_t aur_ppo_update_workspace_bytes(const aur_policy_desc* desc);
+
+int aur_ppo_adv_moments(int64_t m, const int32_t* idx, int64_t idx_offset, const float* advantages,
+                        double* moments_out, float* workspace, void* stream);
+
+int aur_ppo_update_grad(const aur_update_args* args, void* stream);
+
+/* params / adam_m / adam_v: [P] fp32 updated in place (torch.optim.Adam single-tensor math, no
+ * weight decay, no amsgrad).  step is the 1-based Adam step count.  stats_out [AUR_NUM_STATS]
+ * (nullable) receives the minibatch means; entropy_coeff/value_coeff only enter stats_out[LOSS]. */
+int aur_ppo_update_apply(const aur_policy_desc* desc, float* params, const float* grads_packed, float* adam_m,
+                         float* adam_v, double lr, double beta1, double beta2, double eps, int64_t step,
+                         double max_grad_norm, int64_t m_total, double entropy_coeff, double value_coeff,
+                         float* stats_out, void* stream);
+
 /* Evaluates the deterministic fp64 sin/cos the env kernels use (csrc/det_sincos.h) on n
  * device doubles -- exported so tests can compare it with the host copy bit for bit. */
 int aur_sincos_f64(int64_t n, const double* x, double* sin_out, double* cos_out, void* stream);

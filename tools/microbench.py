@@ -43,9 +43,48 @@ def bench_gae(args):
         del rew, val, term, out
 
 
+def _policy(cont=False):
+    from tests.helpers import flat_from_named, random_policy
+    _, named = random_policy(3 if cont else 4, 1 if cont else 2, 64, 2, cont, seed=1)
+    desc = kernels.policy_desc(3 if cont else 4, 1 if cont else 2, 64, 2, cont)
+    return desc, torch.from_numpy(flat_from_named(named)).cuda()
+
+
+def bench_rollout(args):
+    from aur_ppo_b200 import envs as denv
+    for gym_id, N, T in [("CartPole-v1", 65536, 128), ("CartPole-v1", 131072, 128), ("CartPole-v1", 4096, 128),
+                         ("Pendulum-v1", 65536, 256)]:
+        cont = gym_id.startswith("Pend")
+        desc, flat = _policy(cont)
+        env = denv.DeviceVecEnv(gym_id, N, wrappers=cont)
+        env.reset(list(range(N)))
+        buf = kernels.RolloutBuffers(T, N, env.obs_dim, (1,) if cont else (), "cuda")
+        step = [0]
+        def run():
+            kernels.rollout(env, desc, flat, buf, seed=1, step0=step[0]); step[0] += T
+        med, best = timeit(run, iters=10, warmup=3)
+        print(json.dumps({"kernel": "rollout", "env": gym_id, "N": N, "T": T, "ms_median": med * 1e3,
+                          "env_steps_per_s": N * T / med, "HBM_GBps": 36 * N * T / med / 1e9,
+                          "fp32_TFLOPs": 17792 * N * T / med / 1e12}))
+
+
+def bench_update(args):
+    desc, flat = _policy(False)
+    for B, m in [(8388608, 2097152), (8388608, 524288), (512, 128)]:
+        g = torch.Generator(device="cuda").manual_seed(3)
+        dbuf = [torch.randn(B, 4, generator=g, device="cuda") * 0.5, torch.randint(0, 2, (B,), generator=g, device="cuda").float(),
+                -0.7 + 0.1 * torch.randn(B, generator=g, device="cuda"), torch.randn(B, generator=g, device="cuda"),
+                torch.randn(B, generator=g, device="cuda"), torch.randn(B, generator=g, device="cuda")]
+        idx = torch.randperm(B, generator=g, device="cuda")[:m].to(torch.int32)
+        up = kernels.Updater(desc, flat.clone())
+        med, best = timeit(lambda: up.step(*dbuf, idx, lr=2.5e-4), iters=10, warmup=3)
+        print(json.dumps({"kernel": "update(moments+grad+reduce+adam)", "B": B, "m": m, "ms_median": med * 1e3,
+                          "samples_per_s": m / med, "fp32_TFLOPs": 53400 * m / med / 1e12, "gather_GBps": 40 * m / med / 1e9}))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", nargs="*", default=["gae"])
+    ap.add_argument("which", nargs="*", default=["gae", "rollout", "update"])
     a = ap.parse_args()
     for w in a.which:
         globals()["bench_" + w](a)
