@@ -1,0 +1,283 @@
+"""Drop-in for the reference's `ppo` class (src/ppo.py:42-321) on the B200 hot path.
+
+Same constructor (`ppo(params)` with the run_ppo.py:53-81 dict), same attributes (`policy`,
+`optimizer`, `buffer`, `envs`, `batch_size`, `minibatch_size`, `num_updates`), same `train()`
+return value, same TensorBoard tags and checkpoint file.  What differs is where the work runs:
+
+  reference                                   here
+  ------------------------------------------  -----------------------------------------------
+  gym.vector.SyncVectorEnv on the host        DeviceVecEnv: env state lives in HBM
+  T x (evaluate, D2H, N env.step, H2D)        one aur_rollout launch per update   (ppo.py:201-205)
+  T x 9 elementwise kernels                   one aur_gae_f32 launch              (ppo.py:125-157)
+  ~100 kernels + 2 syncs per minibatch        moments, grad, reduce, adam         (ppo.py:220-269)
+  np.random.shuffle + index H2D per epoch     torch.randperm on device
+
+There is no CPU path: without a CUDA device or without libaurppo.so the constructor raises.
+Under torch.distributed (NCCL) each rank owns num_envs / world_size env columns; the only
+exchange is one all_reduce of the packed [grads | stats] buffer (and of three fp64 advantage
+moments) per minibatch.
+"""
+from __future__ import annotations
+
+import math
+import os
+import random
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, compat, kernels
+from .envs import DeviceVecEnv
+from .models.actor_critic import actor_critic
+
+
+class torch_buffer:
+    """src/ppo.py:20-39: [T,N,...] fp32 rollout storage (actions are fp32 even when discrete)."""
+
+    def __init__(self, observation_shape, action_shape, num_steps, num_envs, device="cuda"):
+        self.observation_shape = tuple(observation_shape)
+        self.action_shape = tuple(action_shape)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+        self.states = z(num_steps, num_envs, *self.observation_shape)
+        self.actions = z(num_steps, num_envs, *self.action_shape)
+        self.log_probs = z(num_steps, num_envs)
+        self.rewards = z(num_steps, num_envs)
+        self.terminals = z(num_steps, num_envs)
+        self.values = z(num_steps, num_envs)
+        self.next_value = z(num_envs)
+
+    def flatten(self, returns, advantages):
+        b_obs = self.states.reshape((-1,) + self.observation_shape)
+        b_logprobs = self.log_probs.reshape(-1)
+        b_actions = self.actions.reshape((-1,) + self.action_shape)
+        b_advantages = advantages.reshape(-1)
+        b_returns = returns.reshape(-1)
+        b_values = self.values.reshape(-1)
+        return b_obs, b_logprobs, b_actions, b_advantages, b_returns, b_values
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(lr, eps=1e-5) facade (src/ppo.py:80) over the fused clip+Adam kernel:
+    `param_groups[0]["lr"]` is what the kernel reads each step, the moments live in flat buffers."""
+
+    def __init__(self, params, updater: kernels.Updater, lr: float, eps: float = 1e-5, betas=(0.9, 0.999)):
+        super().__init__(list(params), dict(lr=lr, eps=eps, betas=betas, weight_decay=0, amsgrad=False))
+        self.updater = updater
+
+    def step(self, closure=None, max_grad_norm: float = 0.5):
+        return self.updater.apply(self.param_groups[0]["lr"], max_grad_norm)
+
+    def zero_grad(self, set_to_none: bool = True):
+        pass   # the gradient buffer is overwritten by every aur_ppo_update_grad call
+
+
+_SPACES = {"CartPole-v1": dict(obs=(4,), act_shape=(), n=2), "Pendulum-v1": dict(obs=(3,), act_shape=(1,), n=None)}
+
+
+class ppo:
+    def __init__(self, params: Dict):
+        self.params_dict = params
+        self.all_steps = None
+        self.minibatch_size = None
+        for key, value in params.items():
+            if key not in ("batch_size", "minibatch_size"):
+                setattr(self, key, value)
+        if not torch.cuda.is_available():
+            raise _lib.AurError("aur_ppo_b200.ppo needs a CUDA device: the hot path has no CPU fallback")
+        _lib.lib()
+        # ---- data-parallel layout: env columns sharded over ranks
+        self.world_size, self.rank = 1, 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world_size, self.rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        self.device = torch.device(params.get("device", f"cuda:{torch.cuda.current_device()}"))
+        if self.num_envs % self.world_size:
+            raise _lib.AurError(f"num_envs={self.num_envs} must divide over world_size={self.world_size}")
+        self.local_envs = self.num_envs // self.world_size
+        if self.gym_id not in _SPACES:
+            raise _lib.AurError(f"gym_id {self.gym_id!r} has no device kernel (compiled: {sorted(_SPACES)})")
+        sp = _SPACES[self.gym_id]
+        if bool(self.continuous) != (sp["n"] is None):
+            raise _lib.AurError(f"{self.gym_id} is {'continuous' if sp['n'] is None else 'discrete'}; got continuous={self.continuous}")
+
+        self.all_steps = self.num_steps * self.num_envs
+        self.batch_size = int(self.num_envs * self.num_steps)
+        self.minibatch_size = int(self.all_steps // self.num_minibatches)
+        self.num_updates = self.total_timesteps // self.batch_size
+        self.local_batch = self.local_envs * self.num_steps
+        self.local_minibatch = self.minibatch_size // self.world_size
+        self.run_name = f"{self.gym_id}__{self.exp_name}__{self.seed}__{int(time.time())}"
+
+        self.envs = DeviceVecEnv(self.gym_id, self.local_envs, wrappers=bool(self.continuous), device=self.device,
+                                 env_id0=self.rank * self.local_envs)
+        self.state_dim = sp["obs"]
+        self.action_dim = sp["act_shape"] if self.continuous else sp["n"]
+        with torch.cuda.device(self.device):
+            self.policy = actor_critic(self.state_dim[0], self.action_dim, self.hidden_dim, self.num_layers, self.dropout,
+                                       self.continuous).to(self.device)
+        if self.world_size > 1:      # identical initial weights on every rank
+            for p in self.policy.parameters():
+                torch.distributed.broadcast(p.data, 0)
+        self.flat = self.policy.flat_parameters()
+        self.desc = kernels.policy_desc(*self.policy.kernel_shape())
+        self.buffer = torch_buffer(self.state_dim, sp["act_shape"], self.num_steps, self.local_envs, self.device)
+        reduce_fn = None
+        if self.world_size > 1:
+            reduce_fn = lambda t: torch.distributed.all_reduce(t)
+        self.updater = kernels.Updater(self.desc, self.flat, eps=1e-5, allreduce=reduce_fn)
+        self.optimizer = FusedAdam(self.policy.parameters(), self.updater, lr=self.learning_rate, eps=1e-5)
+        self.philox_seed = int(params.get("philox_seed", 1))
+        self.total_returns: List[float] = []
+        self.total_episode_lengths: List[int] = []
+        self.x_indices: List[int] = []
+        self._returns = torch.empty_like(self.buffer.rewards)
+        self._advantages = torch.empty_like(self.buffer.rewards)
+        self._env_step = 0
+
+    # ------------------------------------------------------------------ hot path pieces
+    def make_env(self, gym_id, idx, capture_video):
+        raise _lib.AurError("envs are device-resident here; there are no per-env gym thunks (src/ppo.py:85-99)")
+
+    def rollout(self, actions_in: Optional[torch.Tensor] = None) -> None:
+        """ppo.py:201-205 for all T steps: fills self.buffer, leaves critic(next_obs) in buffer.next_value."""
+        kernels.rollout(self.envs, self.desc, self.flat, self.buffer, seed=self.philox_seed, step0=self._env_step,
+                        actions_in=actions_in)
+        self._env_step += self.num_steps
+
+    def advantages(self, next_obs=None, next_done=None):
+        """ppo.py:159-166 -> (returns, advantages) [T,N]."""
+        return kernels.gae(self.buffer.rewards, self.buffer.values, self.buffer.terminals, self.buffer.next_value,
+                           self.envs.next_done, self.gamma, self.gae_lambda, bool(self.gae),
+                           out=(self._returns, self._advantages))
+
+    def update_minibatch(self, flat_bufs, mb_inds: torch.Tensor) -> torch.Tensor:
+        """ppo.py:220-269 for one minibatch of local row indices -> device stats tensor."""
+        b_obs, b_logprobs, b_actions, b_advantages, b_returns, b_values = flat_bufs
+        self.updater.grad(b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values, mb_inds,
+                          m_total=mb_inds.numel() * self.world_size, clip_coeff=self.clip_coeff,
+                          entropy_coeff=self.entropy_coeff, value_coeff=self.value_coeff, norm_adv=bool(self.norm_adv),
+                          clip_vloss=bool(self.clip_vloss))
+        return self.optimizer.step(max_grad_norm=self.max_grad_norm)
+
+    def run_update(self, update: int) -> Dict[str, torch.Tensor]:
+        """One full iteration of the outer loop (ppo.py:192-273) without logging; returns device tensors."""
+        if self.anneal_lr:
+            frac = 1.0 - (update - 1.0) / self.num_updates
+            self.optimizer.param_groups[0]["lr"] = frac * self.learning_rate
+        self.rollout()
+        returns, advantages = self.advantages()
+        flat_bufs = self.buffer.flatten(returns, advantages)
+        n_mb = 0
+        stats_rows = self._stats_rows
+        for ep in range(self.num_update_epochs):
+            b_inds = torch.randperm(self.local_batch, device=self.device).to(torch.int32)
+            for start in range(0, self.local_batch, self.local_minibatch):
+                mb = b_inds[start:start + self.local_minibatch]
+                stats_rows[n_mb].copy_(self.update_minibatch(flat_bufs, mb))
+                n_mb += 1
+            if self.target_kl is not None:
+                if stats_rows[n_mb - 1, 4].item() > self.target_kl:
+                    break
+        return dict(stats=stats_rows[:n_mb], b_values=flat_bufs[5], b_returns=flat_bufs[4])
+
+    # --------------------------------------------------------------------------- train
+    def train(self):
+        writer = None
+        if self.rank == 0 and self.params_dict.get("tensorboard", True):
+            if self.track:
+                import wandb
+                wandb.init(project="ppo", entity="Aurelian", sync_tensorboard=True, config=None, name=self.run_name,
+                           monitor_gym=True, save_code=True)
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter(f"runs/{self.run_name}")
+            writer.add_text("parameters/what", "what")
+            writer.add_text("hyperparameters", "|param|value|\n|-|-|\n%s" % (
+                "\n".join([f"|{key}|{str(self.params_dict[key])}|" for key in self.params_dict])))
+        seed = 1                                    # hard-coded in the reference (ppo.py:180-184)
+        random.seed(seed)
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+
+        global_step = 0
+        start_time = time.time()
+        id0 = self.rank * self.local_envs
+        self.envs.reset(seed=list(range(id0, id0 + self.local_envs)))
+        self._env_step = 0
+        n_rows = self.num_update_epochs * math.ceil(self.local_batch / max(self.local_minibatch, 1))
+        self._stats_rows = torch.zeros(n_rows, kernels.NUM_STATS, device=self.device)
+
+        for update in range(1, self.num_updates + 1):
+            step_base = self._env_step
+            out = self.run_update(update)
+            # ---- episodic statistics (ppo.py:114-122): the first finished env of each step
+            last_t = None
+            for (t, env_id, ret, length) in self.envs.drain_episodes():
+                if t == last_t:
+                    continue
+                last_t = t
+                gs = (t + 1) * self.num_envs
+                if writer is not None:
+                    writer.add_scalar("charts/episodic_return", ret, gs)
+                    writer.add_scalar("charts/episodic_length", length, gs)
+                self.total_returns.append(ret)
+                self.total_episode_lengths.append(length)
+                self.x_indices.append(gs)
+            global_step = (step_base + self.num_steps) * self.num_envs
+            # ---- per-update scalars (ppo.py:277-292); explained variance computed on device
+            stats = out["stats"]
+            b_values, b_returns = out["b_values"], out["b_returns"]
+            var_y = torch.var(b_returns, unbiased=False)
+            ev = 1 - torch.var(b_returns - b_values, unbiased=False) / var_y
+            host = torch.cat([stats[-1, :8], stats[:, 5].mean().reshape(1), var_y.reshape(1), ev.reshape(1)]).cpu().numpy()
+            explained_var = float("nan") if host[9] == 0 else float(host[10])
+            self.last_stats = dict(value_loss=float(host[1]), policy_loss=float(host[0]), entropy=float(host[2]),
+                                   old_approx_kl=float(host[3]), approx_kl=float(host[4]), clipfrac=float(host[8]),
+                                   explained_variance=explained_var, grad_norm=float(host[6]))
+            if writer is not None:
+                writer.add_scalar("charts/learning_rate", self.optimizer.param_groups[0]["lr"], global_step)
+                writer.add_scalar("losses/value_loss", host[1], global_step)
+                writer.add_scalar("losses/policy_loss", host[0], global_step)
+                writer.add_scalar("losses/entropy", host[2], global_step)
+                writer.add_scalar("losses/old_approx_kl", host[3], global_step)
+                writer.add_scalar("losses/approx_kl", host[4], global_step)
+                writer.add_scalar("losses/clipfrac", host[8], global_step)
+                writer.add_scalar("losses/explained_variance", explained_var, global_step)
+                writer.add_scalar("charts/SPS", int(global_step / (time.time() - start_time)), global_step)
+
+        self.envs.close()
+        if writer is not None:
+            writer.close()
+        if self.rank == 0 and self.params_dict.get("save", True):
+            compat.save_policy(self.policy, "actor_critic_" + str(self.num_layers) + ".pt")
+            self.plot_episodic_returns(np.array(self.total_returns), np.array(self.x_indices), "episodic returns")
+            self.plot_episodic_returns(np.array(self.total_episode_lengths), np.array(self.x_indices), "episodic lengths")
+        return self.total_returns, self.total_episode_lengths, self.x_indices
+
+    # ---------------------------------------------------------------------------- plots
+    def moving_average(self, data, window_size):
+        return np.convolve(data, np.ones(window_size) / window_size, mode="valid")
+
+    def plot_episodic_returns(self, episodic_returns, x_indices, title, window_size=10):
+        """ppo.py:313-321; skipped (with a note) when matplotlib is not installed."""
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+        except Exception:
+            print(f"[aur_ppo_b200] matplotlib not available: skipping plot {title!r}")
+            return
+        if len(episodic_returns) < window_size:
+            return
+        plt.figure()
+        plt.plot(x_indices, episodic_returns, label="Episodic Returns")
+        plt.plot(x_indices[window_size - 1:], self.moving_average(episodic_returns, window_size),
+                 label=f"Moving Average (Window Size = {window_size})", color="red")
+        plt.title("Episodic Returns with Moving Average for " + self.gym_id)
+        plt.xlabel("Timestep")
+        plt.ylabel("Return")
+        plt.legend()
+        os.makedirs("../plots", exist_ok=True)
+        plt.savefig("../plots/" + title + "_num_layers_" + str(self.num_layers) + "_dropout_" + str(self.dropout) +
+                    "_num_envs_" + str(self.num_envs) + "_num_mb_" + str(self.num_minibatches) + ".png")
+        plt.close()

@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Headline benchmark: one PPO iteration (fused rollout -> GAE -> minibatch updates) per step.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): CartPole-v1 PPO, num_envs = 65536 PER GPU (weak scaling),
+T = 128, num_minibatches = 4, update_epochs = 4, 2-layer 64-wide MLP, synthetic = the env itself
+(seeds 0..N-1, reference-initialised weights).  A step = T*num_envs env steps, one GAE pass and
+epochs*num_minibatches fused updates.  Prints ONE JSON line (see the contract in the task brief).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_ENVS_PER_GPU = 65536
+T = 128
+NUM_MINIBATCHES = 4
+EPOCHS = 4
+METRIC = "env_steps_per_s"
+UNIT = "env-steps/s"
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 148 SMs x 128 FMA lanes x 2 flop x max SM clock (no measured figure)
+
+
+def workload_config(n_gpus):
+    return {"workload": "CartPole-v1 PPO iteration: fused rollout + GAE + update (BASELINE configs[1])",
+            "num_envs_per_gpu": NUM_ENVS_PER_GPU, "num_envs": NUM_ENVS_PER_GPU * n_gpus, "num_steps": T,
+            "num_minibatches": NUM_MINIBATCHES, "update_epochs": EPOCHS, "hidden_dim": 64, "num_layers": 2,
+            "parallelism": f"dp{n_gpus} (env columns sharded, one packed allreduce per minibatch)",
+            "l2": "working set 370 MB per iteration > 126 MB L2 (no explicit flush needed)"}
+
+
+def params(num_envs, total_iters):
+    return {'gym_id': 'CartPole-v1', 'seed': 1.0, 'num_steps': T, 'gae': True,
+            'total_timesteps': num_envs * T * max(total_iters, 1), 'anneal_lr': True, 'gae_lambda': 0.95,
+            'num_update_epochs': EPOCHS, 'num_envs': num_envs, 'num_minibatches': NUM_MINIBATCHES, 'entropy_coeff': 0.01,
+            'value_coeff': 0.5, 'clip_coeff': 0.2, 'clip_vloss': True, 'max_grad_norm': 0.5, 'target_kl': None,
+            'norm_adv': True, 'capture_video': False, 'hidden_dim': 64, 'continuous': False, 'learning_rate': 2.5e-4,
+            'exp_name': 'bench', 'num_layers': 2, 'dropout': 0.0, 'gamma': 0.99, 'track': False,
+            'tensorboard': False, 'save': False}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index=0, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period, [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference_iteration(num_envs, iters, warmup, seed=1):
+    """The reference's CPU path restated (oracle/): gym-style SyncVectorEnv of per-env Python objects
+    stepped serially, reference actor_critic math on torch CPU, run_gae loop, update loop with Adam.
+    Returns (seconds per iteration, env steps per iteration)."""
+    import numpy as np
+    import torch
+    from oracle import gym_restated as G
+    from oracle import ppo_ref as R
+    from tests.helpers import random_policy
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    pol, _ = random_policy(4, 2, 64, 2, False, seed=seed)
+    opt = R.RefAdam(pol.tensors(), lr=2.5e-4, eps=1e-5)
+    envs = G.SyncVectorEnv([G.make_env("CartPole-v1", False) for _ in range(num_envs)], 4)
+    next_obs = torch.from_numpy(envs.reset(seed=list(range(num_envs)))[0])
+    next_done = torch.zeros(num_envs)
+    N = num_envs
+    obs = torch.zeros(T, N, 4); actions = torch.zeros(T, N); logps = torch.zeros(T, N)
+    rewards = torch.zeros(T, N); dones = torch.zeros(T, N); values = torch.zeros(T, N)
+    batch, mb = N * T, N * T // NUM_MINIBATCHES
+    times = []
+    for it in range(warmup + iters):
+        t0 = time.perf_counter()
+        for t in range(T):                                   # ppo.py:201-205
+            obs[t], dones[t] = next_obs, next_done
+            with torch.no_grad():
+                a, lp, _, v = pol.evaluate(next_obs)
+            values[t], actions[t], logps[t] = v.flatten(), a, lp
+            o, r, term, trunc, info = envs.step(a.numpy())
+            rewards[t] = torch.tensor(r).view(-1)
+            next_obs, next_done = torch.from_numpy(o), torch.from_numpy(term.astype(np.float32))
+        with torch.no_grad():                                # ppo.py:159-166
+            ret, adv = R.gae(rewards, values, dones, pol.value(next_obs), next_done, 0.99, 0.95)
+        b = (obs.reshape(-1, 4), actions.reshape(-1), logps.reshape(-1), adv.reshape(-1), ret.reshape(-1), values.reshape(-1))
+        inds = np.arange(batch)
+        for ep in range(EPOCHS):                             # ppo.py:215-269
+            np.random.shuffle(inds)
+            for s in range(0, batch, mb):
+                mi = torch.from_numpy(inds[s:s + mb])
+                R.ppo_update_step(pol, opt, b[0][mi], b[1][mi], b[2][mi], b[3][mi], b[4][mi], b[5][mi])
+        times.append(time.perf_counter() - t0)
+    times = times[warmup:]
+    return sum(times) / len(times), N * T
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    sample_envs = 256
+    sec, steps = cpu_reference_iteration(sample_envs, args.steps, args.warmup)
+    v = steps / sec
+    sample = (f"oracle port of the reference CPU path (gym-style SyncVectorEnv of Python env objects + torch CPU), "
+              f"CartPole-v1 num_envs={sample_envs} x T={T}, {EPOCHS} epochs x {NUM_MINIBATCHES} minibatches per step; "
+              f"gym itself is not installed, so this is oracle/gym_restated.py + oracle/ppo_ref.py")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (MLP) / f64 (env state)", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ own arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from aur_ppo_b200 import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    from aur_ppo_b200.ppo import ppo
+    n_gpus = world
+    agent = ppo(params(NUM_ENVS_PER_GPU * n_gpus, args.steps + args.warmup))
+    import math
+    agent._stats_rows = torch.zeros(EPOCHS * math.ceil(agent.local_batch / agent.local_minibatch), 16, device=agent.device)
+    id0 = agent.rank * agent.local_envs
+    agent.envs.reset(seed=list(range(id0, id0 + agent.local_envs)))
+    L = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) with per-phase events
+    upd = 0
+    for _ in range(args.warmup):
+        upd += 1
+        agent.run_update(upd)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    L.aur_launch_count_reset()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for k in range(args.steps):
+        upd += 1
+        if agent.anneal_lr:
+            agent.optimizer.param_groups[0]["lr"] = (1.0 - (upd - 1.0) / agent.num_updates) * agent.learning_rate
+        ev[k][0].record()
+        agent.rollout()
+        ev[k][1].record()
+        returns, advantages = agent.advantages()
+        ev[k][2].record()
+        flat_bufs = agent.buffer.flatten(returns, advantages)
+        for ep in range(EPOCHS):
+            b_inds = torch.randperm(agent.local_batch, device=agent.device).to(torch.int32)
+            for s in range(0, agent.local_batch, agent.local_minibatch):
+                agent.update_minibatch(flat_bufs, b_inds[s:s + agent.local_minibatch])
+        ev[k][3].record()
+    end.record()
+    barrier()
+    launches = int(L.aur_launch_count())
+    clocks = sampler.finish()
+    ms_total = start.elapsed_time(end)
+    t_roll = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    t_gae = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    t_upd = sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps
+    tt = torch.tensor([ms_total, t_roll, t_gae, t_upd], device=agent.device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, t_roll, t_gae, t_upd = [float(x) for x in tt.cpu()]
+    ms_per_step = ms_total / args.steps
+    steps_per_iter = NUM_ENVS_PER_GPU * n_gpus * T
+    value = steps_per_iter / (ms_per_step * 1e-3)
+
+    # ---- e2e through the public API with host buffers: every step uploads the policy parameters and
+    # the learning rate from pinned host memory, runs ppo.run_update(), and reads back the updated
+    # parameters, the per-minibatch statistics and the finished-episode log.
+    P = agent.flat.numel()
+    h_params = torch.empty(P, dtype=torch.float32).pin_memory()
+    h_params.copy_(agent.flat.cpu())
+    h_stats = torch.empty(agent._stats_rows.shape, dtype=torch.float32).pin_memory()
+    barrier()
+    d2h = 0
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(args.steps):
+        upd += 1
+        agent.flat.copy_(h_params, non_blocking=True)                 # H2D: parameters
+        out = agent.run_update(min(upd, agent.num_updates))
+        h_params.copy_(agent.flat, non_blocking=True)                 # D2H: updated parameters
+        h_stats[:out["stats"].shape[0]].copy_(out["stats"], non_blocking=True)
+        eps = agent.envs.drain_episodes()                             # D2H: episode count + entries (syncs)
+        d2h += 4 + 16 * len(eps)
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1) / args.steps
+    te = torch.tensor([e2e_ms], device=agent.device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.cpu()[0])
+    e2e_value = steps_per_iter / (e2e_ms * 1e-3)
+    h2d_bytes = P * 4
+    d2h_bytes = P * 4 + h_stats.numel() * 4 + d2h // args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    m = agent.local_minibatch
+    n_mb = EPOCHS * NUM_MINIBATCHES
+    upd_samples_per_s = n_mb * m * n_gpus / (t_upd * 1e-3)
+    roll_steps_per_s = steps_per_iter / (t_roll * 1e-3)
+    gae_bytes = 20 * T * NUM_ENVS_PER_GPU + 8 * NUM_ENVS_PER_GPU
+    gae_gbps = gae_bytes / (t_gae * 1e-3) / 1e9
+    upd_gbps = 40.0 * m / (t_upd / n_mb * 1e-3) / 1e9
+    upd_tflops = 53400.0 * m / (t_upd / n_mb * 1e-3) / 1e12
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        traffic = {}
+    rooflines = [
+        {"kernel": "gae_bulk_kernel", "bound": "hbm", "achieved": gae_gbps, "peak": hbm_peak, "unit": "GB/s",
+         "frac": gae_gbps / hbm_peak, "traffic": traffic.get("gae_bulk_kernel"), "algorithmic_bytes": gae_bytes,
+         "ms": t_gae},
+        {"kernel": "rollout_kernel", "bound": "hbm", "achieved": 36.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e9,
+         "peak": hbm_peak, "unit": "GB/s", "frac": 36.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e9 / hbm_peak,
+         "traffic": traffic.get("rollout_kernel"), "ms": t_roll,
+         "fp32_tflops": 17792.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e12,
+         "fp32_frac_of_nominal": 17792.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e12 / FP32_PEAK_TFLOPS},
+        {"kernel": "ppo_grad_kernel (+moments, reduce, adam)", "bound": "hbm", "achieved": upd_gbps, "peak": hbm_peak,
+         "unit": "GB/s", "frac": upd_gbps / hbm_peak, "traffic": traffic.get("ppo_grad_kernel"), "ms": t_upd / n_mb,
+         "fp32_tflops": upd_tflops, "fp32_frac_of_nominal": upd_tflops / FP32_PEAK_TFLOPS,
+         "note": "fp32-FMA bound by design (53.4 kFLOP vs 40 B per sample); the HBM fraction is reported because the "
+                 "contract asks for it, the fp32 figures are the binding ones"},
+    ]
+    dominant = max(rooflines, key=lambda r: r["ms"] * (n_mb if r["kernel"].startswith("ppo_grad") else 1))
+    roofline = {k: dominant[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+    roofline["kernel"] = dominant["kernel"]
+    roofline["peak_source"] = peak_src
+    if "fp32_tflops" in dominant:
+        roofline["fp32_tflops"] = dominant["fp32_tflops"]
+        roofline["fp32_frac_of_nominal"] = dominant["fp32_frac_of_nominal"]
+
+    cpu_baseline = None
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        import torch as _t
+        sample_envs = 256
+        sec, steps = cpu_reference_iteration(sample_envs, 4, 1)
+        cpu_baseline = {"value": steps / sec, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
+                        "sample": f"oracle port (gym-style SyncVectorEnv of Python env objects + torch CPU), CartPole-v1 "
+                                  f"num_envs={sample_envs} x T={T}, {EPOCHS}x{NUM_MINIBATCHES} minibatch updates, 4 iterations"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (MLP, GAE, Adam) / f64 (env state)", "data": "synthetic", "config": workload_config(n_gpus),
+            "rollout_env_steps_per_s": roll_steps_per_s, "update_samples_per_s": upd_samples_per_s,
+            "gae_GBps": gae_gbps, "gae_frac_of_hbm_peak": gae_gbps / hbm_peak,
+            "phase_ms": {"rollout": t_roll, "gae": t_gae, "update": t_upd},
+            "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms,
+                    "what": "per step: H2D policy parameters from pinned memory -> ppo.run_update() -> D2H updated "
+                            "parameters, per-minibatch statistics, finished-episode log; env state stays in HBM"},
+            "gpu_launches": launches, "clocks": clocks}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,80 @@
+"""End-to-end drop-in: ppo(params).train() on the GPU (reference config A and a wide config)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from aur_ppo_b200 import compat, run_ppo
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(**kw):
+    p = run_ppo.params_from_args(run_ppo.build_parser().parse_args([]))
+    p.update(tensorboard=False, save=False)
+    p.update(kw)
+    return p
+
+
+def test_reference_config_a_learns_cartpole(tmp_path, monkeypatch):
+    """CartPole-v1, num_envs=4, num_minibatches=4, 2-layer MLP (run_ppo.py defaults): the reference's
+    only published outcome is the learning curve, so check the return climbs."""
+    from aur_ppo_b200.ppo import ppo
+    monkeypatch.chdir(tmp_path)
+    torch.manual_seed(1)
+    agent = ppo(_params(total_timesteps=80000, save=True))
+    for attr in ("policy", "optimizer", "buffer", "envs", "batch_size", "minibatch_size", "num_updates"):
+        assert hasattr(agent, attr)
+    assert (agent.batch_size, agent.minibatch_size, agent.num_updates) == (512, 128, 156)
+    assert agent.buffer.states.shape == (128, 4, 4) and agent.buffer.actions.shape == (128, 4)
+    assert agent.buffer.actions.dtype == torch.float32
+    rets, lens, xs = agent.train()
+    assert len(rets) == len(lens) == len(xs) > 50
+    assert xs == sorted(xs) and xs[-1] <= 80000
+    first, last = np.mean(rets[:20]), np.mean(rets[-20:])
+    assert first < 60 and last > 3 * first, (first, last)
+    assert abs(agent.optimizer.param_groups[0]["lr"] - 2.5e-4 * (1 - 155 / 156)) < 1e-12      # lr anneal ppo.py:195-198
+    st = agent.last_stats
+    assert np.isfinite([st[k] for k in ("value_loss", "policy_loss", "entropy", "approx_kl", "clipfrac")]).all()
+    # checkpoint: whole-module pickle, reference file name (ppo.py:296), loadable, same weights
+    assert os.path.exists("actor_critic_2.pt")
+    m = compat.load_policy("actor_critic_2.pt")
+    for (n, a), (_, b) in zip(agent.policy.named_parameters(), m.named_parameters()):
+        assert torch.equal(a.detach().cpu(), b.detach().cpu()), n
+    obs = torch.zeros(3, 4)
+    a, lp, v = m.act(obs)            # the checkpoint consumer of test.py:49-51
+    assert a.shape == (3,)
+
+
+def test_wide_config_runs_and_improves():
+    from aur_ppo_b200.ppo import ppo
+    torch.manual_seed(1)
+    agent = ppo(_params(num_envs=2048, total_timesteps=2048 * 128 * 12))
+    rets, lens, xs = agent.train()
+    assert agent.num_updates == 12 and len(rets) > 100
+    assert np.mean(rets[-50:]) > 1.5 * np.mean(rets[:50])
+
+
+def test_pendulum_continuous_runs():
+    from aur_ppo_b200.ppo import ppo
+    torch.manual_seed(1)
+    p = _params(gym_id="Pendulum-v1", continuous=True, num_envs=512, num_steps=256, num_minibatches=8,
+                num_update_epochs=4, total_timesteps=512 * 256 * 4, learning_rate=3e-4, entropy_coeff=0.0)
+    agent = ppo(p)
+    assert agent.buffer.actions.shape == (256, 512, 1) and agent.policy.actor_logstd.shape == (1, 1)
+    rets, lens, xs = agent.train()
+    assert all(l == 200 for l in lens) and len(rets) > 0
+    assert np.isfinite(list(agent.last_stats.values())).all()
+
+
+def test_unsupported_configs_fail_loudly():
+    from aur_ppo_b200 import _lib
+    from aur_ppo_b200.ppo import ppo
+    with pytest.raises(_lib.AurError):
+        ppo(_params(gym_id="LunarLander-v2"))
+    with pytest.raises(_lib.AurError):
+        ppo(_params(continuous=True))                    # CartPole is discrete
+    agent = ppo(_params(hidden_dim=32, total_timesteps=512))
+    with pytest.raises(_lib.AurError, match="hidden_dim"):
+        agent.train()
