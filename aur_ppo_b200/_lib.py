@@ -30,7 +30,8 @@ class EnvState(ctypes.Structure):
 
 
 class EpisodeLog(ctypes.Structure):
-    _fields_ = [("entries", c_void_p), ("count", c_void_p), ("capacity", ctypes.c_uint32)]
+    _fields_ = [("entries", c_void_p), ("count", c_void_p), ("capacity", ctypes.c_uint32), ("_pad", ctypes.c_uint32),
+                ("first_finished", c_void_p), ("totals", c_void_p)]
 
 
 class RolloutArgs(ctypes.Structure):

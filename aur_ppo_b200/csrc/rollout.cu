@@ -185,7 +185,18 @@ __device__ __forceinline__ void load_policy_smem(float* smem, const RolloutDev& 
   sActor = smem; sCritic = smem + nA; sLogstd = smem + nA + nC;
 }
 
-__device__ __forceinline__ void log_episode(const aur_episode_log& log, int step, int env, float ret, int len) {
+__device__ __forceinline__ void log_episode(const aur_episode_log& log, int t, long long local_env, int step, int env,
+                                            float ret, int len) {
+  if (log.first_finished) {
+    const unsigned long long key = ((unsigned long long)local_env << 41) | ((unsigned long long)(len & 511) << 32) |
+                                   (unsigned long long)__float_as_uint(ret);
+    atomicMin(log.first_finished + t, key);
+  }
+  if (log.totals) {
+    atomicAdd(log.totals + 0, 1.0);
+    atomicAdd(log.totals + 1, (double)ret);
+    atomicAdd(log.totals + 2, (double)len);
+  }
   if (!log.count) return;
   const uint32_t idx = atomicAdd(log.count, 1u);
   if (log.entries && idx < log.capacity) {
@@ -328,7 +339,7 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
       a.rew_buf[o] = reward32;
       if (finished) {
         // ---- SyncVectorEnv autoreset: the returned obs is the RESET obs; `done` keeps `terminated`
-        log_episode(a.log, (int)gstep, (int)gid, ep_ret[e], ep_len[e]);
+        log_episode(a.log, t, n, (int)gstep, (int)gid, ep_ret[e], ep_len[e]);
         Pcg64 rng;
         rng.load(a.env.pcg, N, n);
         env[e].reset(rng);

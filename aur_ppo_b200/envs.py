@@ -54,18 +54,36 @@ class DeviceVecEnv:
         self.norm = torch.zeros(11, n, dtype=torch.float64, device=dev) if self.wrappers else None
         self.next_obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, device=dev)
         self.next_done = torch.zeros(n, dtype=torch.float32, device=dev)
-        cap = int(log_capacity) if log_capacity is not None else max(1024, n * 16)
-        self.log_entries = torch.zeros(cap, 4, dtype=torch.int32, device=dev)
+        # full episode log: opt-in (tests / small runs); the training loop reads `first_finished`
+        cap = int(log_capacity) if log_capacity is not None else 0
+        self.log_entries = torch.zeros(max(cap, 1), 4, dtype=torch.int32, device=dev)
         self.log_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.log_capacity = cap
+        self.first_finished = None        # [T] uint64 keys, sized at the first rollout
+        self.totals = torch.zeros(3, dtype=torch.float64, device=dev)
 
     # ------------------------------------------------------------------ C structs
     def state_struct(self) -> _lib.EnvState:
         return _lib.EnvState(self.phys.data_ptr(), self.pcg.data_ptr(), self.elapsed.data_ptr(),
                              self.ep_return.data_ptr(), self.ep_length.data_ptr(), _ptr(self.norm))
 
-    def log_struct(self) -> _lib.EpisodeLog:
-        return _lib.EpisodeLog(self.log_entries.data_ptr(), self.log_count.data_ptr(), self.log_capacity)
+    def log_struct(self, T: int) -> _lib.EpisodeLog:
+        if self.first_finished is None or self.first_finished.numel() != T:
+            self.first_finished = torch.empty(T, dtype=torch.int64, device=self.device)
+        self.first_finished.fill_(-1)          # all ones
+        return _lib.EpisodeLog(self.log_entries.data_ptr() if self.log_capacity else None, self.log_count.data_ptr(),
+                               self.log_capacity, 0, self.first_finished.data_ptr(), self.totals.data_ptr())
+
+    def first_finished_episodes(self):
+        """Per step of the LAST rollout, the first finished env in env order (what ppo.py:114-122 logs):
+        numpy arrays (t, local_env, return, length), one D2H copy of T*8 bytes."""
+        keys = self.first_finished.cpu().numpy().view(np.uint64)
+        t = np.nonzero(keys != np.uint64(0xFFFFFFFFFFFFFFFF))[0]
+        k = keys[t]
+        env = (k >> np.uint64(41)).astype(np.int64)
+        length = ((k >> np.uint64(32)) & np.uint64(511)).astype(np.int64)
+        ret = (k & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32)
+        return t, env, ret, length
 
     # ---------------------------------------------------------------------- reset
     def reset(self, seed: Sequence[int]):

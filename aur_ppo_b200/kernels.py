@@ -118,7 +118,7 @@ def rollout(env, desc: _lib.PolicyDesc, params: torch.Tensor, buf: RolloutBuffer
     a.next_obs, a.next_done, a.next_value = env.next_obs.data_ptr(), env.next_done.data_ptr(), buf.next_value.data_ptr()
     a.actions_in = None if actions_in is None else _f32c(actions_in, "actions_in").data_ptr()
     a.seed, a.step0, a.env_id0 = int(seed), int(step0), int(env.env_id0)
-    a.log = env.log_struct()
+    a.log = env.log_struct(T)
     a.gamma = env.gamma
     with torch.cuda.device(params.device):
         rc = _lib.lib().aur_rollout(ctypes.byref(a), _stream())

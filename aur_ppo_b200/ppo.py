@@ -211,18 +211,15 @@ class ppo:
             step_base = self._env_step
             out = self.run_update(update)
             # ---- episodic statistics (ppo.py:114-122): the first finished env of each step
-            last_t = None
-            for (t, env_id, ret, length) in self.envs.drain_episodes():
-                if t == last_t:
-                    continue
-                last_t = t
-                gs = (t + 1) * self.num_envs
-                if writer is not None:
+            ts, _, rets, lens = self.envs.first_finished_episodes()
+            gss = (step_base + ts + 1) * self.num_envs
+            if writer is not None:
+                for gs, ret, length in zip(gss.tolist(), rets.tolist(), lens.tolist()):
                     writer.add_scalar("charts/episodic_return", ret, gs)
                     writer.add_scalar("charts/episodic_length", length, gs)
-                self.total_returns.append(ret)
-                self.total_episode_lengths.append(length)
-                self.x_indices.append(gs)
+            self.total_returns.extend(rets.tolist())
+            self.total_episode_lengths.extend(lens.tolist())
+            self.x_indices.extend(gss.tolist())
             global_step = (step_base + self.num_steps) * self.num_envs
             # ---- per-update scalars (ppo.py:277-292); explained variance computed on device
             stats = out["stats"]

@@ -246,8 +246,8 @@ def run_ours(args):
         out = agent.run_update(min(upd, agent.num_updates))
         h_params.copy_(agent.flat, non_blocking=True)                 # D2H: updated parameters
         h_stats[:out["stats"].shape[0]].copy_(out["stats"], non_blocking=True)
-        eps = agent.envs.drain_episodes()                             # D2H: episode count + entries (syncs)
-        d2h += 4 + 16 * len(eps)
+        agent.envs.first_finished_episodes()                          # D2H: per-step first finished episode (syncs)
+        d2h += 8 * T
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1) / args.steps

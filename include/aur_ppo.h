@@ -122,9 +122,15 @@ typedef struct {
 } aur_episode;
 
 typedef struct {
-  aur_episode* entries; /* [capacity] or NULL */
+  aur_episode* entries; /* [capacity] or NULL: full log of finished episodes (tests, small runs) */
   uint32_t* count;      /* device counter of finished episodes (may exceed capacity; extras are dropped) */
   uint32_t capacity;
+  uint32_t _pad;
+  /* [T] or NULL, caller-initialised to all ones: per rollout step, the FIRST finished env in env
+   * order -- what the reference logs (ppo.py:114-122 breaks after the first final_info item).
+   * Packed (local_env << 41) | (length << 32) | float_bits(return), merged with atomicMin. */
+  unsigned long long* first_finished;
+  double* totals;       /* [3] or NULL: += episodes, sum of returns, sum of lengths */
 } aur_episode_log;
 
 /* envs.reset(seed=[...]) (src/ppo.py:188): `st.pcg` must already hold each env's seeded PCG64

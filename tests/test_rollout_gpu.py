@@ -78,7 +78,7 @@ def test_cartpole_replay_is_bit_exact(N, T):
     actions = rng.integers(0, 2, (T, N))
     cv, obs0, obs, rew, done, last_obs, last_done, episodes = _oracle_replay(E.CARTPOLE, N, False, seeds, actions, T)
 
-    env = denv.DeviceVecEnv("CartPole-v1", N)
+    env = denv.DeviceVecEnv("CartPole-v1", N, log_capacity=N * 64)
     o, _ = env.reset(seeds)
     assert np.array_equal(o.cpu().numpy(), obs0)
     buf = kernels.RolloutBuffers(T, N, 4, (), "cuda")
@@ -91,6 +91,15 @@ def test_cartpole_replay_is_bit_exact(N, T):
     assert np.array_equal(env.next_obs.cpu().numpy(), last_obs)
     assert np.array_equal(env.next_done.cpu().numpy(), last_done)
     assert np.array_equal(env.phys.cpu().numpy().T, cv.phys())          # fp64 state, bit for bit
+    # what the training loop reads: per step, the first finished env in env order (ppo.py:114-122)
+    ft, fenv, fret, flen = env.first_finished_episodes()
+    want_first = {}
+    for (t, i, r, l) in sorted(episodes, key=lambda r: (r[0], r[1])):
+        want_first.setdefault(t, (i, r, l))
+    assert list(ft) == sorted(want_first)
+    assert [(int(e), float(r), int(l)) for e, r, l in zip(fenv, fret, flen)] == [want_first[t] for t in sorted(want_first)]
+    tot = env.totals.cpu().numpy()
+    assert tot[0] == len(episodes) and tot[2] == sum(e[3] for e in episodes)
     got = env.drain_episodes()
     assert got == sorted(episodes, key=lambda r: (r[0], r[1]))
     assert len(got) > 0
@@ -116,7 +125,7 @@ def test_pendulum_replay_is_bit_exact(wrappers):
     rng = np.random.default_rng(9)
     actions = rng.normal(0, 1.6, (T, N, 1)).astype(np.float32)
     cv, obs0, obs, rew, done, last_obs, last_done, episodes = _oracle_replay(E.PENDULUM, N, wrappers, seeds, actions, T)
-    env = denv.DeviceVecEnv("Pendulum-v1", N, wrappers=wrappers)
+    env = denv.DeviceVecEnv("Pendulum-v1", N, wrappers=wrappers, log_capacity=N * 8)
     o, _ = env.reset(seeds)
     assert np.array_equal(o.cpu().numpy(), obs0)
     buf = kernels.RolloutBuffers(T, N, 3, (1,), "cuda")
