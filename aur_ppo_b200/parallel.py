@@ -1,0 +1,79 @@
+"""Data-parallel plan of the PPO hot path: env columns are sharded over
+ranks, rollout and GAE need no communication, and each minibatch exchanges one packed fp32 buffer
+[P gradient sums | 16 statistic sums] plus three fp64 advantage moments with a SUM all-reduce
+(NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests).  Gradient seeds carry
+1/m_total, so the sum over ranks is the mean over the whole minibatch."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    world_size: int
+    rank: int
+    num_envs: int          # global (the reference's --num_envs)
+    num_steps: int
+    num_minibatches: int
+
+    def __post_init__(self):
+        if self.num_envs % self.world_size:
+            raise ValueError(f"num_envs={self.num_envs} must divide over world_size={self.world_size}")
+        if (self.local_envs * self.num_steps) % self.num_minibatches:
+            raise ValueError("local batch must divide into num_minibatches")
+
+    @property
+    def local_envs(self) -> int:
+        return self.num_envs // self.world_size
+
+    @property
+    def env_id0(self) -> int:
+        """First GLOBAL env id this rank owns: seeds the env (gym seed = env id, ppo.py:188) and keys Philox."""
+        return self.rank * self.local_envs
+
+    @property
+    def env_ids(self) -> range:
+        return range(self.env_id0, self.env_id0 + self.local_envs)
+
+    @property
+    def batch_size(self) -> int:
+        return self.num_envs * self.num_steps
+
+    @property
+    def local_batch(self) -> int:
+        return self.local_envs * self.num_steps
+
+    @property
+    def minibatch_size(self) -> int:
+        return self.batch_size // self.num_minibatches
+
+    @property
+    def local_minibatch(self) -> int:
+        return self.minibatch_size // self.world_size
+
+
+def current_plan(num_envs: int, num_steps: int, num_minibatches: int) -> ShardPlan:
+    ws, rk = 1, 0
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        ws, rk = torch.distributed.get_world_size(), torch.distributed.get_rank()
+    return ShardPlan(ws, rk, num_envs, num_steps, num_minibatches)
+
+
+def make_allreduce(plan: ShardPlan, group=None) -> Optional[Callable[[torch.Tensor], None]]:
+    """SUM all-reduce used on the advantage moments and on the packed [grads | stats] buffer."""
+    if plan.world_size == 1:
+        return None
+
+    def _reduce(t: torch.Tensor) -> None:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=group)
+    return _reduce
+
+
+def broadcast_parameters(module: torch.nn.Module, plan: ShardPlan, src: int = 0) -> None:
+    """Identical initial weights on every rank (after that, identical updates keep them in sync)."""
+    if plan.world_size > 1:
+        for p in module.parameters():
+            torch.distributed.broadcast(p.data, src)

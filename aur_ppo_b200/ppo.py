@@ -28,7 +28,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from . import _lib, compat, kernels
+from . import _lib, compat, kernels, parallel
 from .envs import DeviceVecEnv
 from .models.actor_critic import actor_critic
 
@@ -88,13 +88,13 @@ class ppo:
             raise _lib.AurError("aur_ppo_b200.ppo needs a CUDA device: the hot path has no CPU fallback")
         _lib.lib()
         # ---- data-parallel layout: env columns sharded over ranks
-        self.world_size, self.rank = 1, 0
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.world_size, self.rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        try:
+            self.plan = parallel.current_plan(self.num_envs, self.num_steps, self.num_minibatches)
+        except ValueError as e:
+            raise _lib.AurError(str(e))
+        self.world_size, self.rank = self.plan.world_size, self.plan.rank
         self.device = torch.device(params.get("device", f"cuda:{torch.cuda.current_device()}"))
-        if self.num_envs % self.world_size:
-            raise _lib.AurError(f"num_envs={self.num_envs} must divide over world_size={self.world_size}")
-        self.local_envs = self.num_envs // self.world_size
+        self.local_envs = self.plan.local_envs
         if self.gym_id not in _SPACES:
             raise _lib.AurError(f"gym_id {self.gym_id!r} has no device kernel (compiled: {sorted(_SPACES)})")
         sp = _SPACES[self.gym_id]
@@ -105,27 +105,22 @@ class ppo:
         self.batch_size = int(self.num_envs * self.num_steps)
         self.minibatch_size = int(self.all_steps // self.num_minibatches)
         self.num_updates = self.total_timesteps // self.batch_size
-        self.local_batch = self.local_envs * self.num_steps
-        self.local_minibatch = self.minibatch_size // self.world_size
+        self.local_batch = self.plan.local_batch
+        self.local_minibatch = self.plan.local_minibatch
         self.run_name = f"{self.gym_id}__{self.exp_name}__{self.seed}__{int(time.time())}"
 
         self.envs = DeviceVecEnv(self.gym_id, self.local_envs, wrappers=bool(self.continuous), device=self.device,
-                                 env_id0=self.rank * self.local_envs)
+                                 env_id0=self.plan.env_id0)
         self.state_dim = sp["obs"]
         self.action_dim = sp["act_shape"] if self.continuous else sp["n"]
         with torch.cuda.device(self.device):
             self.policy = actor_critic(self.state_dim[0], self.action_dim, self.hidden_dim, self.num_layers, self.dropout,
                                        self.continuous).to(self.device)
-        if self.world_size > 1:      # identical initial weights on every rank
-            for p in self.policy.parameters():
-                torch.distributed.broadcast(p.data, 0)
+        parallel.broadcast_parameters(self.policy, self.plan)      # identical initial weights on every rank
         self.flat = self.policy.flat_parameters()
         self.desc = kernels.policy_desc(*self.policy.kernel_shape())
         self.buffer = torch_buffer(self.state_dim, sp["act_shape"], self.num_steps, self.local_envs, self.device)
-        reduce_fn = None
-        if self.world_size > 1:
-            reduce_fn = lambda t: torch.distributed.all_reduce(t)
-        self.updater = kernels.Updater(self.desc, self.flat, eps=1e-5, allreduce=reduce_fn)
+        self.updater = kernels.Updater(self.desc, self.flat, eps=1e-5, allreduce=parallel.make_allreduce(self.plan))
         self.optimizer = FusedAdam(self.policy.parameters(), self.updater, lr=self.learning_rate, eps=1e-5)
         self.philox_seed = int(params.get("philox_seed", 1))
         self.total_returns: List[float] = []
@@ -201,8 +196,7 @@ class ppo:
 
         global_step = 0
         start_time = time.time()
-        id0 = self.rank * self.local_envs
-        self.envs.reset(seed=list(range(id0, id0 + self.local_envs)))
+        self.envs.reset(seed=list(self.plan.env_ids))
         self._env_step = 0
         n_rows = self.num_update_epochs * math.ceil(self.local_batch / max(self.local_minibatch, 1))
         self._stats_rows = torch.zeros(n_rows, kernels.NUM_STATS, device=self.device)
