@@ -110,6 +110,8 @@ def lib() -> ctypes.CDLL:
     L.aur_ppo_update_apply.argtypes = [ctypes.POINTER(PolicyDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                        c_double, c_double, c_double, c_int64, c_double, c_int64, c_double, c_double,
                                        c_void_p, c_void_p]
+    L.aur_tc_gemm_bf16.restype = c_int
+    L.aur_tc_gemm_bf16.argtypes = [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     L.aur_sincos_f64.restype = c_int
     L.aur_sincos_f64.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     _lib = L

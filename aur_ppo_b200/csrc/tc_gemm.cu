@@ -1,0 +1,141 @@
+// tcgen05 GEMM: C[M,N] (fp32) = A[M,K] * B[N,K]^T, A and B bf16 row-major (K contiguous).
+// TMA (128-B swizzle) -> 4-stage shared-memory ring -> tcgen05.mma kind::f16, accumulator in TMEM
+// -> tcgen05.ld epilogue.  One CTA per 128 x BN output tile; warp 0 = TMA producer, warp 1 = MMA
+// issuer (one elected thread), warp 2 = TMEM allocator, warps 4-7 = epilogue.
+// This is the dense-contraction core the equivariant encoder's convolutions are built from.
+#include "tc.cuh"
+
+namespace aur {
+namespace tc {
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return AUR_ERR_UNSUPPORTED; }
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return AUR_ERR_ARG; }
+  return 0;
+}
+
+constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 64, GEMM_STAGES = 4;
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2, GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;
+constexpr size_t GEMM_SMEM = (size_t)GEMM_STAGES * (GEMM_A_BYTES + GEMM_B_BYTES) + 1024 + 256;
+
+__global__ void __launch_bounds__(256, 1)
+tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
+                    int M, int N, int K, int ldc) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + GEMM_STAGES * GEMM_A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + GEMM_STAGES * GEMM_B_BYTES);
+  uint64_t* empty = full + GEMM_STAGES;
+  uint64_t* tmem_full = empty + GEMM_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * GEMM_BN;
+  const int nkb = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, GEMM_BN);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % GEMM_STAGES;
+      const uint32_t ph = (kb / GEMM_STAGES) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      mbar_arrive_expect_tx(&full[s], GEMM_A_BYTES + GEMM_B_BYTES);
+      tma_load_2d(sA + s * GEMM_A_BYTES, &tmA, kb * GEMM_BK, m0, &full[s]);
+      tma_load_2d(sB + s * GEMM_B_BYTES, &tmB, kb * GEMM_BK, n0, &full[s]);
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = instr_desc(FMT_BF16, GEMM_BM, GEMM_BN, 0, 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % GEMM_STAGES;
+      const uint32_t ph = (kb / GEMM_STAGES) & 1u;
+      mbar_wait(&full[s], ph);
+      fence_after_sync();
+      const uint64_t ad = smem_desc_k_sw128(sA + s * GEMM_A_BYTES), bd = smem_desc_k_sw128(sB + s * GEMM_B_BYTES);
+#pragma unroll
+      for (int k = 0; k < GEMM_BK / 16; ++k)          // UMMA_K = 16 bf16 = 32 B: advance the start address by 2 x 16 B
+        mma_f16(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+      mma_commit(&empty[s]);
+    }
+    mma_commit(tmem_full);
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    mbar_wait(tmem_full, 0);
+    fence_after_sync();
+    const int row = m0 + 32 * q + lane;
+#pragma unroll 1
+    for (int c = 0; c < GEMM_BN; c += 32) {
+      float v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+      if (row < M) {
+        float* dst = C + (size_t)row * ldc + n0 + c;
+        if (n0 + c + 32 <= N && (ldc & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+          for (int i = 0; i < 32; ++i) if (n0 + c + i < N) dst[i] = v[i];
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_d, GEMM_BN);
+}
+
+}  // namespace tc
+}  // namespace aur
+
+extern "C" int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, const void* B, float* C, void* stream) {
+  using namespace aur;
+  using namespace aur::tc;
+  if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) { set_error("aur_tc_gemm_bf16: bad arguments"); return AUR_ERR_ARG; }
+  if (K % 8 != 0) { set_error("aur_tc_gemm_bf16: K must be a multiple of 8 (16-byte row pitch for TMA)"); return AUR_ERR_UNSUPPORTED; }
+  CUtensorMap tmA, tmB;
+  const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, dB[2] = {(uint64_t)K, (uint64_t)N};
+  const uint64_t st[1] = {(uint64_t)K * 2};
+  const uint32_t boxA[2] = {GEMM_BK, GEMM_BM}, boxB[2] = {GEMM_BK, GEMM_BN};
+  int rc;
+  if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, dA, st, boxA))) return rc;
+  if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, dB, st, boxB))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    AUR_CUDA_OK(cudaFuncSetAttribute(tc_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    attr = true;
+  }
+  dim3 grid((unsigned)((M + GEMM_BM - 1) / GEMM_BM), (unsigned)((N + GEMM_BN - 1) / GEMM_BN));
+  tc_gemm_bf16_kernel<<<grid, 256, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, C, (int)M, (int)N, (int)K, (int)N);
+  AUR_LAUNCH_OK("tc_gemm_bf16_kernel");
+  return 0;
+}

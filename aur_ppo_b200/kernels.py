@@ -207,3 +207,17 @@ class Updater:
     def step(self, *args, lr: float, max_grad_norm: float = 0.5, **kw) -> torch.Tensor:
         self.grad(*args, **kw)
         return self.apply(lr, max_grad_norm)
+
+
+# ----------------------------------------------------------------------- tensor cores
+def tc_gemm_bf16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a [M,K] bf16, b [N,K] bf16 -> a @ b.T as fp32 [M,N] (tcgen05, fp32 accumulate)."""
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or not a.is_cuda or not a.is_contiguous() or not b.is_contiguous():
+        raise _lib.AurError("tc_gemm_bf16 needs contiguous CUDA bf16 operands")
+    M, K = a.shape
+    N = b.shape[0]
+    c = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().aur_tc_gemm_bf16(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), _stream())
+    _lib.check(rc, "aur_tc_gemm_bf16")
+    return c

@@ -241,6 +241,13 @@ int aur_ppo_update_apply(const aur_policy_desc* desc, float* params, const float
                          double max_grad_norm, int64_t m_total, double entropy_coeff, double value_coeff,
                          float* stats_out, void* stream);
 
+/* ------------------------------------------------------ tensor-core core ----
+ * C[M,N] (fp32, row-major) = A[M,K] * B[N,K]^T with A, B bf16 row-major (K contiguous), fp32
+ * accumulation in TMEM (tcgen05.mma kind::f16, TMA operand loads).  The dense-contraction core
+ * of the equivariant encoder's convolutions (src/nets/equiv.py:17-59), exported for tests.
+ * K must be a multiple of 8. */
+int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, const void* B, float* C, void* stream);
+
 /* Evaluates the deterministic fp64 sin/cos the env kernels use (csrc/det_sincos.h) on n
  * device doubles -- exported so tests can compare it with the host copy bit for bit. */
 int aur_sincos_f64(int64_t n, const double* x, double* sin_out, double* cos_out, void* stream);
