@@ -52,6 +52,12 @@ class UpdateArgs(ctypes.Structure):
                 ("_pad2", ctypes.c_float), ("adv_moments", c_void_p), ("workspace", c_void_p), ("grads_out", c_void_p)]
 
 
+class ConvArgs(ctypes.Structure):
+    _fields_ = [("B", c_int32), ("Hb", c_int32), ("Wb", c_int32), ("Cin", c_int32), ("Cout", c_int32),
+                ("epilogue", c_int32), ("out_Hb", c_int32), ("out_Wb", c_int32), ("out_off", c_int32), ("_pad", c_int32),
+                ("inp", c_void_p), ("wmat", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("pool_arg", c_void_p)]
+
+
 class AurError(RuntimeError):
     pass
 
@@ -112,6 +118,12 @@ def lib() -> ctypes.CDLL:
                                        c_void_p, c_void_p]
     L.aur_tc_gemm_bf16.restype = c_int
     L.aur_tc_gemm_bf16.argtypes = [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.aur_conv3x3_bf16.restype = c_int
+    L.aur_conv3x3_bf16.argtypes = [ctypes.POINTER(ConvArgs), c_void_p]
+    L.aur_equiv_expand_regular.restype = c_int
+    L.aur_equiv_expand_regular.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.aur_equiv_conv0.restype = c_int
+    L.aur_equiv_conv0.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
     L.aur_sincos_f64.restype = c_int
     L.aur_sincos_f64.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     _lib = L

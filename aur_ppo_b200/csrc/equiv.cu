@@ -1,0 +1,362 @@
+// Equivariant (C4) encoder convolutions on tensor cores (row X of the scope table).
+// Replaces the e2cnn R2Conv -> cuDNN conv2d calls of src/nets/equiv.py:17-59 for the
+// close_loop_block_picking-shaped observations ([B,2,128,128]).
+//
+// A C4-steerable 3x3 filter bank is a dense filter W = expand(psi) (p4 group convolution: rotate
+// the 3x3 taps by r and cyclically shift the input rotation index), so every layer is a dense
+// convolution = real contraction over (tap, Cin): implicit GEMM on tcgen05.
+//   A  = activations, NHWC bf16 with an explicit zero halo, loaded by 4-D TMA boxes
+//        {64 channels, TW, TH, images} -> 128 pixel rows x 64 channels, K-major, 128-B swizzle;
+//        the 9 taps are 9 shifted boxes of the SAME tensor map (no im2col buffer in HBM)
+//   B  = expanded weights [Cout][tap][Cin] bf16, 2-D TMA
+//   D  = fp32 accumulator in TMEM (128 lanes = pixels x 128 columns = output channels)
+//   epilogue (tcgen05.ld): + bias, ReLU, optional 2x2 max-pool through warp shuffles (a 2x2 window
+//        lives inside one warp by construction of the pixel tile), bf16 store into the NEXT
+//        layer's haloed buffer, 2-bit arg-max per pooled element for the backward pass.
+// The same kernel computes backward-data (input = haloed output gradient, weights = transposed,
+// tap-flipped filter, linear epilogue).
+#include "tc.cuh"
+
+namespace aur {
+namespace tc {
+
+constexpr int CV_BM = 128, CV_BN = 128, CV_BK = 64, CV_STAGES = 3;
+constexpr int CV_A_BYTES = CV_BM * CV_BK * 2, CV_B_BYTES = CV_BN * CV_BK * 2;
+constexpr size_t CV_SMEM = (size_t)CV_STAGES * (CV_A_BYTES + CV_B_BYTES) + 1024 + 256;
+
+struct ConvDev {
+  int B, Hb, Wb, Ho, Wo, Cin, Cout;
+  int TH, TW, NIMG, tiles_x, tiles_y;      // pixel tile = NIMG images x TH x TW = 128
+  int epi;                                 // 0 linear, 1 bias+ReLU, 2 bias+ReLU+maxpool2
+  int oHb, oWb, ooff;                      // output buffer geometry
+  const float* bias;
+  __nv_bfloat16* out;
+  unsigned char* pool_arg;
+};
+
+__global__ void __launch_bounds__(256, 2)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvDev a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + CV_STAGES * CV_A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + CV_STAGES * CV_B_BYTES);
+  uint64_t* empty = full + CV_STAGES;
+  uint64_t* tmem_full = empty + CV_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // pixel tile decode
+  int t = blockIdx.x;
+  const int tx = t % a.tiles_x; t /= a.tiles_x;
+  const int ty = t % a.tiles_y; t /= a.tiles_y;
+  const int b0 = t * a.NIMG, y0 = ty * a.TH, x0 = tx * a.TW;
+  const int n0 = blockIdx.y * CV_BN;
+  const int cchunks = a.Cin / CV_BK;
+  const int nkb = 9 * cchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CV_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, CV_BN);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer: K loop over (tap, channel chunk) =====
+    int kb = 0;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap - 3 * dy;
+      for (int cc = 0; cc < cchunks; ++cc, ++kb) {
+        const int s = kb % CV_STAGES;
+        const uint32_t ph = (kb / CV_STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[s], CV_A_BYTES + CV_B_BYTES);
+        tma_load_4d(sA + s * CV_A_BYTES, &tmA, cc * CV_BK, x0 + dx, y0 + dy, b0, &full[s]);
+        tma_load_2d(sB + s * CV_B_BYTES, &tmB, tap * a.Cin + cc * CV_BK, n0, &full[s]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = instr_desc(FMT_BF16, CV_BM, CV_BN, 0, 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % CV_STAGES;
+      const uint32_t ph = (kb / CV_STAGES) & 1u;
+      mbar_wait(&full[s], ph);
+      fence_after_sync();
+      const uint64_t ad = smem_desc_k_sw128(sA + s * CV_A_BYTES), bd = smem_desc_k_sw128(sB + s * CV_B_BYTES);
+#pragma unroll
+      for (int k = 0; k < CV_BK / 16; ++k) mma_f16(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+      mma_commit(&empty[s]);
+    }
+    mma_commit(tmem_full);
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> (bias, ReLU, pool) -> bf16 NHWC =====
+    const int q = warp - 4;
+    const int m = 32 * q + lane;
+    int r = m;
+    const int xx = r % a.TW; r /= a.TW;
+    const int yy = r % a.TH; r /= a.TH;
+    const int b = b0 + r, y = y0 + yy, x = x0 + xx;
+    const bool valid = b < a.B && y < a.Ho && x < a.Wo;
+    mbar_wait(tmem_full, 0);
+    fence_after_sync();
+#pragma unroll 1
+    for (int c = 0; c < CV_BN; c += 32) {
+      float v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+      const int ch = n0 + c;
+      if (ch >= a.Cout) break;
+      if (a.epi >= 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + (a.bias ? __ldg(a.bias + ch + i) : 0.0f), 0.0f);
+      }
+      if (a.epi == 2) {
+        // 2x2 max pool: window partners are lane^1 (x) and lane^TW (y); first maximum in (y,x) scan
+        // order wins ties, like torch's max_pool2d backward.
+        const int w = ((yy & 1) << 1) | (xx & 1);
+        unsigned int arg_pack[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) arg_pack[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float best = v[i];
+          int bw = w;
+          float o = __shfl_xor_sync(0xffffffffu, best, 1);
+          int ow = __shfl_xor_sync(0xffffffffu, bw, 1);
+          if (o > best || (o == best && ow < bw)) { best = o; bw = ow; }
+          o = __shfl_xor_sync(0xffffffffu, best, a.TW);
+          ow = __shfl_xor_sync(0xffffffffu, bw, a.TW);
+          if (o > best || (o == best && ow < bw)) { best = o; bw = ow; }
+          v[i] = best;
+          arg_pack[i >> 2] |= (unsigned int)bw << (8 * (i & 3));
+        }
+        if (valid && w == 0) {
+          const size_t pix = ((size_t)b * a.oHb + (y >> 1) + a.ooff) * a.oWb + (x >> 1) + a.ooff;
+          __nv_bfloat16* dst = a.out + pix * a.Cout + ch;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[i], v[i + 1]), t1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), t3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+            pk.x = *reinterpret_cast<unsigned int*>(&t0); pk.y = *reinterpret_cast<unsigned int*>(&t1);
+            pk.z = *reinterpret_cast<unsigned int*>(&t2); pk.w = *reinterpret_cast<unsigned int*>(&t3);
+            *reinterpret_cast<uint4*>(dst + i) = pk;
+          }
+          if (a.pool_arg) {
+            const size_t ppix = ((size_t)b * (a.Ho >> 1) + (y >> 1)) * (a.Wo >> 1) + (x >> 1);
+            uint4* ad = reinterpret_cast<uint4*>(a.pool_arg + ppix * a.Cout + ch);
+            ad[0] = make_uint4(arg_pack[0], arg_pack[1], arg_pack[2], arg_pack[3]);
+            ad[1] = make_uint4(arg_pack[4], arg_pack[5], arg_pack[6], arg_pack[7]);
+          }
+        }
+      } else if (valid) {
+        const size_t pix = ((size_t)b * a.oHb + y + a.ooff) * a.oWb + x + a.ooff;
+        __nv_bfloat16* dst = a.out + pix * a.Cout + ch;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pk;
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(v[i], v[i + 1]), t1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), t3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+          pk.x = *reinterpret_cast<unsigned int*>(&t0); pk.y = *reinterpret_cast<unsigned int*>(&t1);
+          pk.z = *reinterpret_cast<unsigned int*>(&t2); pk.w = *reinterpret_cast<unsigned int*>(&t3);
+          *reinterpret_cast<uint4*>(dst + i) = pk;
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_d, CV_BN);
+}
+
+// psi [Fo,Fi,4,3,3] fp32 -> Wmat [(o,r)][tap][(i,s)] bf16 (forward) and, if wt != NULL, the
+// backward-data matrix Wt [(i,s)][tap'][(o,r)] with tap' = 8 - tap (flipped filter).
+__device__ __forceinline__ void rot_src(int r, int y, int x, int& ys, int& xs) {
+  // torch.rot90(w, r, dims=(-2,-1)): r quarter turns counter-clockwise
+  switch (r & 3) {
+    case 0: ys = y; xs = x; break;
+    case 1: ys = x; xs = 2 - y; break;
+    case 2: ys = 2 - y; xs = 2 - x; break;
+    default: ys = 2 - x; xs = y; break;
+  }
+}
+__global__ void expand_reg_reg_kernel(const float* __restrict__ psi, int Fo, int Fi, __nv_bfloat16* __restrict__ wmat,
+                                      __nv_bfloat16* __restrict__ wt) {
+  const int Cout = Fo * 4, Cin = Fi * 4;
+  const long long total = (long long)Cout * 9 * Cin;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long rr = e;
+    const int ci = (int)(rr % Cin); rr /= Cin;
+    const int tap = (int)(rr % 9); rr /= 9;
+    const int co = (int)rr;
+    const int o = co >> 2, r = co & 3, i = ci >> 2, s = ci & 3;
+    const int y = tap / 3, x = tap - 3 * y;
+    int ys, xs;
+    rot_src(r, y, x, ys, xs);
+    const float w = psi[((((size_t)o * Fi + i) * 4 + ((s - r) & 3)) * 3 + ys) * 3 + xs];
+    const __nv_bfloat16 wb = __float2bfloat16(w);
+    wmat[e] = wb;
+    if (wt) wt[((size_t)ci * 9 + (8 - tap)) * Cout + co] = wb;
+  }
+}
+__global__ void expand_bias_kernel(const float* __restrict__ bias_f, int F, float* __restrict__ bias_ch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < F * 4) bias_ch[i] = bias_f[i >> 2];
+}
+
+// Layer 0 (trivial -> regular, Cin = 2: heightmap + tiled gripper state), fused with ReLU and the
+// 2x2 max pool.  K = 18 is far too small for the tensor pipe (and the layer is 1.3 % of the FLOPs):
+// direct convolution, one thread per pooled pixel x 16 output channels, weights in shared memory.
+// obs [B,1,128,128] fp32, state [B] fp32, psi [16,2,3,3], bias [16] -> out [B,66,66,64] bf16 interior.
+__global__ void __launch_bounds__(256)
+conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ state, const float* __restrict__ psi,
+                    const float* __restrict__ bias_f, int B, __nv_bfloat16* __restrict__ out, unsigned char* __restrict__ pool_arg) {
+  __shared__ float sW[64][2][9];
+  __shared__ float sBias[64];
+  for (int e = threadIdx.x; e < 64 * 18; e += blockDim.x) {
+    const int co = e / 18, rem = e - co * 18, ci = rem / 9, tap = rem - ci * 9;
+    const int o = co >> 2, r = co & 3, y = tap / 3, x = tap - 3 * y;
+    int ys, xs;
+    rot_src(r, y, x, ys, xs);
+    sW[co][ci][tap] = psi[((o * 2 + ci) * 3 + ys) * 3 + xs];
+  }
+  if (threadIdx.x < 64) sBias[threadIdx.x] = bias_f[threadIdx.x >> 2];
+  __syncthreads();
+  const long long total = (long long)B * 64 * 64 * 4;       // pooled pixels x 4 channel groups of 16
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long rr = e;
+    const int cg = (int)(rr & 3); rr >>= 2;
+    const int px = (int)(rr & 63); rr >>= 6;
+    const int py = (int)(rr & 63); rr >>= 6;
+    const int b = (int)rr;
+    const float st = state[b];
+    const float* img = obs + (size_t)b * 128 * 128;
+    // 4x4 input patch (rows 2py-1 .. 2py+2) of both channels, zero padded
+    float p0[4][4], p1[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int yy = 2 * py - 1 + i, xx = 2 * px - 1 + j;
+        const bool in = yy >= 0 && yy < 128 && xx >= 0 && xx < 128;
+        p0[i][j] = in ? __ldg(img + yy * 128 + xx) : 0.0f;
+        p1[i][j] = in ? st : 0.0f;
+      }
+    unsigned int packed[8];
+    unsigned int argp[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int co = cg * 16 + c;
+      float best = 0.0f; int bw = 0;
+#pragma unroll
+      for (int wy = 0; wy < 2; ++wy)
+#pragma unroll
+        for (int wx = 0; wx < 2; ++wx) {
+          float acc = sBias[co];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int dy = t / 3, dx = t - 3 * dy;
+            acc = fmaf(sW[co][0][t], p0[wy + dy][wx + dx], acc);
+            acc = fmaf(sW[co][1][t], p1[wy + dy][wx + dx], acc);
+          }
+          acc = fmaxf(acc, 0.0f);
+          const int w = wy * 2 + wx;
+          if (w == 0 || acc > best) { best = acc; bw = w; }
+        }
+      const __nv_bfloat16 hb = __float2bfloat16(best);
+      const unsigned int bits = (unsigned int)__bfloat16_as_ushort(hb);
+      if (c & 1) packed[c >> 1] |= bits << 16; else packed[c >> 1] = bits;
+      argp[c >> 2] |= (unsigned int)bw << (8 * (c & 3));
+    }
+    const size_t pix = ((size_t)b * 66 + py + 1) * 66 + px + 1;
+    uint4* dst = reinterpret_cast<uint4*>(out + pix * 64 + cg * 16);
+    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    if (pool_arg) {
+      const size_t ppix = ((size_t)b * 64 + py) * 64 + px;
+      *reinterpret_cast<uint4*>(pool_arg + ppix * 64 + cg * 16) = make_uint4(argp[0], argp[1], argp[2], argp[3]);
+    }
+  }
+}
+
+}  // namespace tc
+}  // namespace aur
+
+extern "C" int aur_equiv_expand_regular(const float* psi, int32_t Fo, int32_t Fi, const float* bias_f, void* wmat, void* wt,
+                                        float* bias_ch, void* stream) {
+  using namespace aur;
+  using namespace aur::tc;
+  if (!psi || !wmat || Fo <= 0 || Fi <= 0) { set_error("aur_equiv_expand_regular: bad arguments"); return AUR_ERR_ARG; }
+  const long long total = (long long)Fo * 4 * 9 * Fi * 4;
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  expand_reg_reg_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(psi, Fo, Fi, (__nv_bfloat16*)wmat, (__nv_bfloat16*)wt);
+  AUR_LAUNCH_OK("expand_reg_reg_kernel");
+  if (bias_f && bias_ch) {
+    expand_bias_kernel<<<(Fo * 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(bias_f, Fo, bias_ch);
+    AUR_LAUNCH_OK("expand_bias_kernel");
+  }
+  return 0;
+}
+
+extern "C" int aur_equiv_conv0(const float* obs, const float* state, const float* psi, const float* bias_f, int32_t B,
+                               void* out, uint8_t* pool_arg, void* stream) {
+  using namespace aur;
+  using namespace aur::tc;
+  if (!obs || !state || !psi || !bias_f || !out || B <= 0) { set_error("aur_equiv_conv0: bad arguments"); return AUR_ERR_ARG; }
+  const long long total = (long long)B * 64 * 64 * 4;
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  conv0_direct_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, state, psi, bias_f, B, (__nv_bfloat16*)out, pool_arg);
+  AUR_LAUNCH_OK("conv0_direct_kernel");
+  return 0;
+}
+
+extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
+  using namespace aur;
+  using namespace aur::tc;
+  if (!args || !args->in || !args->wmat || !args->out) { set_error("aur_conv3x3_bf16: null argument"); return AUR_ERR_ARG; }
+  const aur_conv_args& c = *args;
+  if (c.B <= 0 || c.Hb < 3 || c.Wb < 3 || c.Cin % 64 != 0 || c.Cout % 8 != 0 || c.Cin <= 0 || c.Cout <= 0) {
+    set_error("aur_conv3x3_bf16: needs Cin %% 64 == 0, Cout %% 8 == 0 (got Cin %d Cout %d)", c.Cin, c.Cout);
+    return AUR_ERR_UNSUPPORTED;
+  }
+  ConvDev d;
+  d.B = c.B; d.Hb = c.Hb; d.Wb = c.Wb; d.Ho = c.Hb - 2; d.Wo = c.Wb - 2; d.Cin = c.Cin; d.Cout = c.Cout;
+  d.epi = c.epilogue; d.oHb = c.out_Hb; d.oWb = c.out_Wb; d.ooff = c.out_off; d.bias = c.bias;
+  d.out = (__nv_bfloat16*)c.out; d.pool_arg = c.pool_arg;
+  if (c.epilogue == 2 && ((d.Ho | d.Wo) & 1)) { set_error("aur_conv3x3_bf16: pooling needs even output size"); return AUR_ERR_ARG; }
+  // pixel tile: 128 = NIMG x TH x TW with TW in {8,16} so a 2x2 pool window stays inside a warp
+  d.TW = d.Wo > 8 ? 16 : 8;
+  d.TH = 8;
+  d.NIMG = 128 / (d.TW * d.TH);
+  d.tiles_x = (d.Wo + d.TW - 1) / d.TW;
+  d.tiles_y = (d.Ho + d.TH - 1) / d.TH;
+  const long long img_groups = (c.B + d.NIMG - 1) / d.NIMG;
+  CUtensorMap tmA, tmB;
+  const uint64_t dA[4] = {(uint64_t)c.Cin, (uint64_t)c.Wb, (uint64_t)c.Hb, (uint64_t)c.B};
+  const uint64_t sA[3] = {(uint64_t)c.Cin * 2, (uint64_t)c.Wb * c.Cin * 2, (uint64_t)c.Hb * c.Wb * c.Cin * 2};
+  const uint32_t bA[4] = {CV_BK, (uint32_t)d.TW, (uint32_t)d.TH, (uint32_t)d.NIMG};
+  const uint64_t dB[2] = {(uint64_t)9 * c.Cin, (uint64_t)c.Cout};
+  const uint64_t sB[1] = {(uint64_t)9 * c.Cin * 2};
+  const uint32_t bB[2] = {CV_BK, CV_BN};
+  int rc;
+  if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, c.in, dA, sA, bA))) return rc;
+  if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.wmat, dB, sB, bB))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM));
+    attr = true;
+  }
+  dim3 grid((unsigned)(img_groups * d.tiles_y * d.tiles_x), (unsigned)((c.Cout + CV_BN - 1) / CV_BN));
+  conv_igemm_kernel<<<grid, 256, CV_SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
+  AUR_LAUNCH_OK("conv_igemm_kernel");
+  return 0;
+}

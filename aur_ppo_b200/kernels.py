@@ -221,3 +221,42 @@ def tc_gemm_bf16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         rc = _lib.lib().aur_tc_gemm_bf16(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), _stream())
     _lib.check(rc, "aur_tc_gemm_bf16")
     return c
+
+
+def equiv_expand_regular(psi: torch.Tensor, bias_f: Optional[torch.Tensor] = None, want_wt: bool = False):
+    """psi [Fo,Fi,4,3,3] fp32 -> (wmat [Fo*4, 9, Fi*4] bf16, wt [Fi*4, 9, Fo*4] bf16 | None, bias [Fo*4] | None)."""
+    psi = _f32c(psi, "psi")
+    Fo, Fi = psi.shape[0], psi.shape[1]
+    wmat = torch.empty(Fo * 4, 9, Fi * 4, dtype=torch.bfloat16, device=psi.device)
+    wt = torch.empty(Fi * 4, 9, Fo * 4, dtype=torch.bfloat16, device=psi.device) if want_wt else None
+    bias = torch.empty(Fo * 4, dtype=torch.float32, device=psi.device) if bias_f is not None else None
+    with torch.cuda.device(psi.device):
+        rc = _lib.lib().aur_equiv_expand_regular(psi.data_ptr(), Fo, Fi, _ptr(bias_f), wmat.data_ptr(), _ptr(wt),
+                                                 _ptr(bias), _stream())
+    _lib.check(rc, "aur_equiv_expand_regular")
+    return wmat, wt, bias
+
+
+def conv3x3_bf16(inp: torch.Tensor, wmat: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int,
+                 out: torch.Tensor, out_off: int, pool_arg: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """inp [B,Hb,Wb,Cin] bf16 (halo included) -> valid 3x3 conv (+bias/ReLU/pool) into out[:, off:, off:, :]."""
+    import ctypes
+    B, Hb, Wb, Cin = inp.shape
+    Cout = wmat.shape[0]
+    a = _lib.ConvArgs(B, Hb, Wb, Cin, Cout, epilogue, out.shape[1], out.shape[2], out_off, 0, inp.data_ptr(),
+                      wmat.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(pool_arg))
+    with torch.cuda.device(inp.device):
+        rc = _lib.lib().aur_conv3x3_bf16(ctypes.byref(a), _stream())
+    _lib.check(rc, "aur_conv3x3_bf16")
+    return out
+
+
+def equiv_conv0(obs: torch.Tensor, state: torch.Tensor, psi: torch.Tensor, bias_f: torch.Tensor, out: torch.Tensor,
+                pool_arg: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B = obs.shape[0]
+    with torch.cuda.device(obs.device):
+        rc = _lib.lib().aur_equiv_conv0(_f32c(obs, "obs").data_ptr(), _f32c(state, "state").data_ptr(),
+                                        _f32c(psi, "psi").data_ptr(), _f32c(bias_f, "bias").data_ptr(), B, out.data_ptr(),
+                                        _ptr(pool_arg), _stream())
+    _lib.check(rc, "aur_equiv_conv0")
+    return out

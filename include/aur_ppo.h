@@ -248,6 +248,36 @@ int aur_ppo_update_apply(const aur_policy_desc* desc, float* params, const float
  * K must be a multiple of 8. */
 int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, const void* B, float* C, void* stream);
 
+/* -------------------------------------------- equivariant encoder (row X) ----
+ * The C4-equivariant convolutions of EquivariantEncoder128 (src/nets/equiv.py:12-62), which the
+ * reference runs as e2cnn R2Conv -> cuDNN.  Activations are NHWC bf16 buffers that INCLUDE their
+ * zero halo; a 3x3 layer is a valid convolution over the buffer (output H = Hb - 2). */
+typedef struct {
+  int32_t B, Hb, Wb, Cin, Cout;   /* input buffer [B,Hb,Wb,Cin] bf16; Cin % 64 == 0, Cout % 32 == 0 */
+  int32_t epilogue;               /* 0 linear, 1 bias + ReLU, 2 bias + ReLU + 2x2 max-pool */
+  int32_t out_Hb, out_Wb, out_off;/* output buffer [B,out_Hb,out_Wb,Cout] bf16, written at (+off,+off) */
+  int32_t _pad;
+  const void* in;
+  const void* wmat;               /* [Cout][tap][Cin] bf16 (aur_equiv_expand_regular) */
+  const float* bias;              /* [Cout] fp32 or NULL */
+  void* out;
+  uint8_t* pool_arg;              /* [B,Ho/2,Wo/2,Cout] arg-max (0..3) of each pool window, or NULL */
+} aur_conv_args;
+
+/* implicit-GEMM 3x3 convolution on tcgen05 (TMA halo boxes, TMEM accumulator, fused epilogue). */
+int aur_conv3x3_bf16(const aur_conv_args* args, void* stream);
+
+/* psi [Fo,Fi,4,3,3] fp32 (regular -> regular p4 filter) -> wmat [(o,r)][tap][(i,s)] bf16, optional
+ * backward-data matrix wt [(i,s)][8-tap][(o,r)] bf16, optional per-channel bias from per-field bias. */
+int aur_equiv_expand_regular(const float* psi, int32_t Fo, int32_t Fi, const float* bias_f, void* wmat, void* wt,
+                             float* bias_ch, void* stream);
+
+/* layer 0 (trivial -> regular, 2 -> 64 channels at 128x128) + ReLU + max-pool, direct fp32 convolution:
+ * obs [B,1,128,128] fp32, state [B] fp32 (tiled second channel, robot_actor_critic.py:106-107),
+ * psi [16,2,3,3], bias [16] -> interior of out [B,66,66,64] bf16 (caller zeroes the halo once). */
+int aur_equiv_conv0(const float* obs, const float* state, const float* psi, const float* bias_f, int32_t B, void* out,
+                    uint8_t* pool_arg, void* stream);
+
 /* Evaluates the deterministic fp64 sin/cos the env kernels use (csrc/det_sincos.h) on n
  * device doubles -- exported so tests can compare it with the host copy bit for bit. */
 int aur_sincos_f64(int64_t n, const double* x, double* sin_out, double* cos_out, void* stream);
