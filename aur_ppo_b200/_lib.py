@@ -55,7 +55,17 @@ class UpdateArgs(ctypes.Structure):
 class ConvArgs(ctypes.Structure):
     _fields_ = [("B", c_int32), ("Hb", c_int32), ("Wb", c_int32), ("Cin", c_int32), ("Cout", c_int32),
                 ("epilogue", c_int32), ("out_Hb", c_int32), ("out_Wb", c_int32), ("out_off", c_int32), ("_pad", c_int32),
-                ("inp", c_void_p), ("wmat", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("pool_arg", c_void_p)]
+                ("inp", c_void_p), ("wmat", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("pool_arg", c_void_p),
+                ("relu_ref", c_void_p), ("ref_Hb", c_int32), ("ref_Wb", c_int32), ("ref_off", c_int32), ("_pad2", c_int32)]
+
+
+class EquivHeadArgs(ctypes.Structure):
+    _fields_ = [("B", c_int32), ("clip_vloss", c_int32), ("m_total", c_int64), ("a_out", c_void_p), ("a_bias", c_void_p),
+                ("c_pre", c_void_p), ("c_bias1", c_void_p), ("c_w2", c_void_p), ("c_b2", c_void_p), ("action", c_void_p),
+                ("oldlp", c_void_p), ("adv", c_void_p), ("ret", c_void_p), ("vold", c_void_p), ("adv_moments", c_void_p),
+                ("clip_coeff", ctypes.c_float), ("entropy_coeff", ctypes.c_float), ("value_coeff", ctypes.c_float),
+                ("_pad", ctypes.c_float), ("d_a_out", c_void_p), ("d_c_h", c_void_p), ("d_head", c_void_p),
+                ("stats", c_void_p), ("value_out", c_void_p), ("logp_out", c_void_p)]
 
 
 class AurError(RuntimeError):
@@ -124,6 +134,30 @@ def lib() -> ctypes.CDLL:
     L.aur_equiv_expand_regular.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.aur_equiv_conv0.restype = c_int
     L.aur_equiv_conv0.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
+    L.aur_wgrad3x3_bf16.restype = c_int
+    L.aur_wgrad3x3_bf16.argtypes = [c_int32, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]
+    L.aur_unpool_relu_bwd.restype = c_int
+    L.aur_unpool_relu_bwd.argtypes = [c_int32] * 4 + [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                                      c_int32, c_int32, c_int32, c_void_p]
+    L.aur_transpose_bf16.restype = c_int
+    L.aur_transpose_bf16.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p]
+    L.aur_equiv_project_regular.restype = c_int
+    L.aur_equiv_project_regular.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p]
+    L.aur_rowsum_bf16.restype = c_int
+    L.aur_rowsum_bf16.argtypes = [c_int32, c_int64, c_void_p, c_int32, c_void_p, c_void_p]
+    L.aur_equiv_conv0_wgrad.restype = c_int
+    L.aur_equiv_conv0_wgrad.argtypes = [c_void_p] * 5 + [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.aur_bias_relu_bf16.restype = c_int
+    L.aur_bias_relu_bf16.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.aur_relu_mask_bf16.restype = c_int
+    L.aur_relu_mask_bf16.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.aur_equiv_head_loss.restype = c_int
+    L.aur_equiv_head_loss.argtypes = [ctypes.POINTER(EquivHeadArgs), c_void_p]
+    L.aur_sumsq_f32.restype = c_int
+    L.aur_sumsq_f32.argtypes = [c_int64, c_void_p, c_void_p, c_void_p]
+    L.aur_adam_flat.restype = c_int
+    L.aur_adam_flat.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_double,
+                                c_int64, c_void_p, c_double, c_void_p]
     L.aur_sincos_f64.restype = c_int
     L.aur_sincos_f64.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     _lib = L

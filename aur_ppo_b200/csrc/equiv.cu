@@ -32,6 +32,8 @@ struct ConvDev {
   const float* bias;
   __nv_bfloat16* out;
   unsigned char* pool_arg;
+  const __nv_bfloat16* relu_ref;           // epi 3: out = acc * (relu_ref > 0), relu_ref buffer [B,rHb,rWb,Cout] at +roff
+  int rHb, rWb, roff;
 };
 
 __global__ void __launch_bounds__(256, 2)
@@ -113,7 +115,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
       const int ch = n0 + c;
       if (ch >= a.Cout) break;
-      if (a.epi >= 1) {
+      if (a.epi == 1 || a.epi == 2) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + (a.bias ? __ldg(a.bias + ch + i) : 0.0f), 0.0f);
       }
@@ -159,6 +161,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } else if (valid) {
         const size_t pix = ((size_t)b * a.oHb + y + a.ooff) * a.oWb + x + a.ooff;
         __nv_bfloat16* dst = a.out + pix * a.Cout + ch;
+        if (a.epi == 3) {
+          const __nv_bfloat16* ref = a.relu_ref + (((size_t)b * a.rHb + y + a.roff) * a.rWb + x + a.roff) * a.Cout + ch;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(ref + i);
+            const unsigned int rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // positive bf16 <=> sign bit clear and magnitude non-zero
+              if (!((rw[j] & 0x7FFFu) != 0 && !(rw[j] & 0x8000u))) v[i + 2 * j] = 0.0f;
+              if (!(((rw[j] >> 16) & 0x7FFFu) != 0 && !((rw[j] >> 16) & 0x8000u))) v[i + 2 * j + 1] = 0.0f;
+            }
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 pk;
@@ -331,7 +347,8 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   ConvDev d;
   d.B = c.B; d.Hb = c.Hb; d.Wb = c.Wb; d.Ho = c.Hb - 2; d.Wo = c.Wb - 2; d.Cin = c.Cin; d.Cout = c.Cout;
   d.epi = c.epilogue; d.oHb = c.out_Hb; d.oWb = c.out_Wb; d.ooff = c.out_off; d.bias = c.bias;
-  d.out = (__nv_bfloat16*)c.out; d.pool_arg = c.pool_arg;
+  d.out = (__nv_bfloat16*)c.out; d.pool_arg = c.pool_arg; d.relu_ref = (const __nv_bfloat16*)c.relu_ref; d.rHb = c.ref_Hb; d.rWb = c.ref_Wb; d.roff = c.ref_off;
+  if (c.epilogue == 3 && !c.relu_ref) { set_error("aur_conv3x3_bf16: epilogue 3 needs relu_ref"); return AUR_ERR_ARG; }
   if (c.epilogue == 2 && ((d.Ho | d.Wo) & 1)) { set_error("aur_conv3x3_bf16: pooling needs even output size"); return AUR_ERR_ARG; }
   // pixel tile: 128 = NIMG x TH x TW with TW in {8,16} so a 2x2 pool window stays inside a warp
   d.TW = d.Wo > 8 ? 16 : 8;

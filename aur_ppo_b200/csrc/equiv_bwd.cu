@@ -1,0 +1,618 @@
+// Backward pass and small layers of the equivariant actor-critic update (row X):
+//   wgrad3x3_kernel      weight gradient of a 3x3 layer as a split-K tcgen05 GEMM over the FLAT haloed
+//                        pixel index: dW[co][tap][ci] = sum_q dY_cm[co][q] * X_cm[ci][q + off(tap)]
+//   unpool_relu_bwd      max-pool + ReLU backward (routes to the stored arg-max, masks by output > 0)
+//   transpose_bf16       NHWC [Q][C] -> channel-major [C][Q] copies feeding the wgrad GEMM
+//   project_regular      dWmat -> dpsi (adjoint of the p4 filter expansion) and per-field bias gradients
+//   conv0_wgrad          layer-0 weight gradient fused with its un-pooling (direct, fp32)
+//   heads / loss         actor head decode + Normal log-prob / entropy + PPO loss seeds (robot_ppo.py:345-398),
+//                        critic head ReLU + GroupPooling + value and its backward
+//   adam_flat / sumsq    torch Adam math on large flat buffers, global-norm clipping
+#include "tc.cuh"
+
+namespace aur {
+namespace tc {
+
+constexpr int WG_BM = 128, WG_BN = 128, WG_BK = 64, WG_STAGES = 4;
+constexpr int WG_A_BYTES = WG_BM * WG_BK * 2, WG_B_BYTES = WG_BN * WG_BK * 2;
+constexpr size_t WG_SMEM = (size_t)WG_STAGES * (WG_A_BYTES + WG_B_BYTES) + 1024 + 256;
+
+// grid: x = (Cout tiles) * (Cin tiles), y = tap, z = split-K slice
+__global__ void __launch_bounds__(256, 1)
+wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Cout, int Cin,
+                long long Q, int base_off, int Wb, int n_tiles, float* __restrict__ dwmat) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + WG_STAGES * WG_A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + WG_STAGES * WG_B_BYTES);
+  uint64_t* empty = full + WG_STAGES;
+  uint64_t* tmem_full = empty + WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x / n_tiles, nt = blockIdx.x - mt * n_tiles;
+  const int m0 = mt * WG_BM, n0 = nt * WG_BN;
+  const int tap = blockIdx.y;
+  const int dy = tap / 3, dx = tap - 3 * dy;
+  const int off = base_off + dy * Wb + dx;
+  const long long nkb_total = (Q + WG_BK - 1) / WG_BK;
+  const long long per = (nkb_total + gridDim.z - 1) / gridDim.z;
+  const long long kb_lo = (long long)blockIdx.z * per;
+  long long kb_hi = kb_lo + per;
+  if (kb_hi > nkb_total) kb_hi = nkb_total;
+  const int nkb = kb_hi > kb_lo ? (int)(kb_hi - kb_lo) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, WG_BN);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0 && lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % WG_STAGES;
+        const uint32_t ph = (i / WG_STAGES) & 1u;
+        const long long k0 = (kb_lo + i) * WG_BK;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[s], WG_A_BYTES + WG_B_BYTES);
+        tma_load_2d(sA + s * WG_A_BYTES, &tmA, (int)k0, m0, &full[s]);
+        tma_load_2d(sB + s * WG_B_BYTES, &tmB, (int)(k0 + off), n0, &full[s]);
+      }
+    } else if (warp == 1 && lane == 0) {
+      constexpr uint32_t idesc = instr_desc(FMT_BF16, WG_BM, WG_BN, 0, 0);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % WG_STAGES;
+        const uint32_t ph = (i / WG_STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        fence_after_sync();
+        const uint64_t ad = smem_desc_k_sw128(sA + s * WG_A_BYTES), bd = smem_desc_k_sw128(sB + s * WG_B_BYTES);
+#pragma unroll
+        for (int k = 0; k < WG_BK / 16; ++k) mma_f16(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0);
+        mma_commit(&empty[s]);
+      }
+      mma_commit(tmem_full);
+    } else if (warp >= 4) {
+      const int q = warp - 4;
+      mbar_wait(tmem_full, 0);
+      fence_after_sync();
+      const int co = m0 + 32 * q + lane;
+#pragma unroll 1
+      for (int c = 0; c < WG_BN; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+        if (co < Cout) {
+          float* dst = dwmat + ((size_t)co * 9 + tap) * Cin + n0 + c;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (n0 + c + i < Cin) atomicAdd(dst + i, v[i]);
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_d, WG_BN);
+}
+
+// ---- max-pool(2) + ReLU backward: one thread per pooled pixel x 8 channels ------------------
+__global__ void unpool_relu_bwd_kernel(int B, int Hp, int Wp, int C, const __nv_bfloat16* __restrict__ dpool,
+                                       const __nv_bfloat16* __restrict__ act, int aHb, int aWb, int aoff,
+                                       const unsigned char* __restrict__ arg, __nv_bfloat16* __restrict__ dy, int dHb, int dWb,
+                                       int doff) {
+  const int cg = C >> 3;
+  const long long total = (long long)B * Hp * Wp * cg;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long r = e;
+    const int c8 = (int)(r % cg); r /= cg;
+    const int px = (int)(r % Wp); r /= Wp;
+    const int py = (int)(r % Hp); r /= Hp;
+    const int b = (int)r;
+    const size_t pp = (((size_t)b * Hp + py) * Wp + px) * C + c8 * 8;
+    const uint4 g = *reinterpret_cast<const uint4*>(dpool + pp);
+    const uint4 av = *reinterpret_cast<const uint4*>(act + (((size_t)b * aHb + py + aoff) * aWb + px + aoff) * C + c8 * 8);
+    const uint2 ar = *reinterpret_cast<const uint2*>(arg + pp);
+    const unsigned short* gs = reinterpret_cast<const unsigned short*>(&g);
+    const unsigned short* as = reinterpret_cast<const unsigned short*>(&av);
+    const unsigned char* ab = reinterpret_cast<const unsigned char*>(&ar);
+    unsigned short o[4][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool pos = (as[i] & 0x7FFFu) != 0 && !(as[i] & 0x8000u);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) o[w][i] = (pos && ab[i] == w) ? gs[i] : (unsigned short)0;
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int y = 2 * py + (w >> 1) + doff, x = 2 * px + (w & 1) + doff;
+      *reinterpret_cast<uint4*>(dy + (((size_t)b * dHb + y) * dWb + x) * C + c8 * 8) = *reinterpret_cast<const uint4*>(o[w]);
+    }
+  }
+}
+
+// ---- [R][C] bf16 -> [C][R] bf16 -----------------------------------------------------------------
+__global__ void transpose_bf16_kernel(long long R, int C, const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out) {
+  __shared__ unsigned short tile[64][66];
+  const long long r0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const unsigned short* src = reinterpret_cast<const unsigned short*>(in);
+  unsigned short* dst = reinterpret_cast<unsigned short*>(out);
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    const long long r = r0 + i;
+    for (int j = threadIdx.x; j < 64; j += blockDim.x) {
+      const int c = c0 + j;
+      tile[i][j] = (r < R && c < C) ? src[r * C + c] : (unsigned short)0;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 64; j += blockDim.y) {
+    const int c = c0 + j;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+      const long long r = r0 + i;
+      if (r < R && c < C) dst[(size_t)c * R + r] = tile[i][j];
+    }
+  }
+}
+
+// ---- adjoint of expand_reg_reg: dpsi[o,i,t,ys,xs] += dWmat[(o,r)][tap][(i,s)] -----------------------
+__device__ __forceinline__ void rot_src_b(int r, int y, int x, int& ys, int& xs) {
+  switch (r & 3) {
+    case 0: ys = y; xs = x; break;
+    case 1: ys = x; xs = 2 - y; break;
+    case 2: ys = 2 - y; xs = 2 - x; break;
+    default: ys = 2 - x; xs = y; break;
+  }
+}
+__global__ void project_reg_reg_kernel(const float* __restrict__ dwmat, int Fo, int Fi, float* __restrict__ dpsi) {
+  const int Cin = Fi * 4;
+  const long long total = (long long)Fo * 4 * 9 * Cin;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long rr = e;
+    const int ci = (int)(rr % Cin); rr /= Cin;
+    const int tap = (int)(rr % 9); rr /= 9;
+    const int co = (int)rr;
+    const int o = co >> 2, r = co & 3, i = ci >> 2, s = ci & 3;
+    const int y = tap / 3, x = tap - 3 * y;
+    int ys, xs;
+    rot_src_b(r, y, x, ys, xs);
+    atomicAdd(dpsi + ((((size_t)o * Fi + i) * 4 + ((s - r) & 3)) * 3 + ys) * 3 + xs, dwmat[e]);
+  }
+}
+// per-field bias gradient: dbias[c / group] += sum_q in_cm[c][q]   (one block per channel row)
+__global__ void __launch_bounds__(256) rowsum_bf16_kernel(int C, long long Q, const __nv_bfloat16* __restrict__ in, int group,
+                                                        float* __restrict__ out) {
+  __shared__ float sh[8];
+  const int c = blockIdx.x;
+  const __nv_bfloat16* p = in + (size_t)c * Q;
+  float s = 0.0f;
+  for (long long q = threadIdx.x; q < Q; q += blockDim.x) s += __bfloat162float(p[q]);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    atomicAdd(out + c / group, t);
+  }
+}
+
+// ---- layer-0 weight gradient fused with its un-pooling ---------------------------------------------
+// dpsi0[o][ci][ys][xs] += sum over pooled pixels of g * in[ci][2py+wy+dy-1][2px+wx+dx-1] routed through the
+// rotation; g = da1[b,py,px,co] where a1 > 0, (wy,wx) = arg.  Thread = output channel, block = pixel strip.
+__global__ void __launch_bounds__(256)
+conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ state, const __nv_bfloat16* __restrict__ da1,
+                   const __nv_bfloat16* __restrict__ a1 /*[B,66,66,64]*/, const unsigned char* __restrict__ arg, int B,
+                   float* __restrict__ dw0 /*[64][2][9] expanded-channel gradient*/, float* __restrict__ dbias_ch /*[64]*/) {
+  __shared__ float patch[4][2][4][4];      // 4 pooled pixels per iteration
+  const int co = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  float acc[2][9];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[c][t] = 0.0f;
+  float bacc = 0.0f;
+  const long long npix = (long long)B * 64 * 64;
+  for (long long base = (long long)blockIdx.x * 4; base < npix; base += (long long)gridDim.x * 4) {
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int pi = threadIdx.x >> 5, e = threadIdx.x & 31, ci = e >> 4, i = (e >> 2) & 3, j = e & 3;
+      const long long pix = base + pi;
+      float v = 0.0f;
+      if (pix < npix) {
+        const int px = (int)(pix & 63), py = (int)((pix >> 6) & 63), b = (int)(pix >> 12);
+        const int yy = 2 * py - 1 + i, xx = 2 * px - 1 + j;
+        if (yy >= 0 && yy < 128 && xx >= 0 && xx < 128) v = ci == 0 ? __ldg(obs + ((size_t)b * 128 + yy) * 128 + xx) : state[b];
+      }
+      patch[pi][ci][i][j] = v;
+    }
+    __syncthreads();
+    const long long pix = base + sub;
+    if (pix < npix) {
+      const int px = (int)(pix & 63), py = (int)((pix >> 6) & 63), b = (int)(pix >> 12);
+      const float act = __bfloat162float(a1[(((size_t)b * 66 + py + 1) * 66 + px + 1) * 64 + co]);
+      if (act > 0.0f) {
+        const float g = __bfloat162float(da1[(size_t)pix * 64 + co]);
+        const int w = arg[(size_t)pix * 64 + co];
+        const int wy = w >> 1, wx = w & 1;
+        bacc += g;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int dy = t / 3, dx = t - 3 * dy;
+          acc[0][t] = fmaf(g, patch[sub][0][wy + dy][wx + dx], acc[0][t]);
+          acc[1][t] = fmaf(g, patch[sub][1][wy + dy][wx + dx], acc[1][t]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) atomicAdd(dw0 + (co * 2 + c) * 9 + t, acc[c][t]);
+  atomicAdd(dbias_ch + co, bacc);
+}
+// dpsi0[o][ci][ys][xs] = sum_r dw0[(o,r)][ci][tap(r)] ; dbias_f[o] = sum_r dbias_ch[(o,r)]
+__global__ void project_conv0_kernel(const float* __restrict__ dw0, const float* __restrict__ dbias_ch, float* __restrict__ dpsi,
+                                     float* __restrict__ dbias_f) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < 64 * 18) {
+    const int co = e / 18, rem = e - co * 18, ci = rem / 9, tap = rem - ci * 9;
+    const int o = co >> 2, r = co & 3, y = tap / 3, x = tap - 3 * y;
+    int ys, xs;
+    rot_src_b(r, y, x, ys, xs);
+    atomicAdd(dpsi + ((o * 2 + ci) * 3 + ys) * 3 + xs, dw0[e]);
+  }
+  if (e < 64) atomicAdd(dbias_f + (e >> 2), dbias_ch[e]);
+}
+
+// ---- elementwise helpers ---------------------------------------------------------------------------
+// out_bf16[r][c] = relu(in_f32[r][c] + bias[c])
+__global__ void bias_relu_kernel(long long n, int C, const float* __restrict__ in, const float* __restrict__ bias,
+                                 __nv_bfloat16* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16(fmaxf(in[i] + bias[(int)(i % C)], 0.0f));
+}
+// out_bf16 = g_f32 * (ref_bf16 > 0)
+__global__ void relu_mask_kernel(long long n, const float* __restrict__ g, const __nv_bfloat16* __restrict__ ref,
+                                 __nv_bfloat16* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16(__bfloat162float(ref[i]) > 0.0f ? g[i] : 0.0f);
+}
+__global__ void f32_to_bf16_kernel(long long n, const float* __restrict__ in, __nv_bfloat16* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16(in[i]);
+}
+
+// ---- heads + loss: one warp per sample --------------------------------------------------------------
+struct HeadLossDev {
+  int B;
+  const float* a_out;      // [B,16] actor head pre-bias output (cols 0..9 used): irrep(1) dx,dy | 8 trivial
+  const float* a_bias;     // [10] (first two are zero: irrep fields carry no bias)
+  const float* c_pre;      // [B,512] critic head-1 pre-activation (no bias)
+  const float* c_bias1;    // [512] per-channel
+  const float* c_w2;       // [128]
+  const float* c_b2;       // [1]
+  const float *action, *oldlp, *adv, *ret, *vold;   // action [B,5]
+  const double* moments;   // [3] sum, sumsq, n of adv (NULL: no normalisation)
+  float clip, clip_lo, clip_hi, ent_c, vf_c, inv_m;
+  int clip_vloss;
+  __nv_bfloat16* d_a_out;  // [B,16] gradient wrt actor head output (bf16, zero padded)
+  __nv_bfloat16* d_c_h;    // [B,512] gradient wrt critic head-1 pre-activation
+  float* d_head;           // [10 + 128 + 1 + 512]: d a_bias | d c_w2 | d c_b2 | d c_bias1(per channel)
+  float* stats;            // [8] sums: policy loss, value loss (x vf_c as the reference), entropy, -logr, r-1-logr, clip
+  float* value_out;        // [B]
+  float* logp_out;         // [B]
+};
+__global__ void __launch_bounds__(256) head_loss_kernel(HeadLossDev a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float adv_mean = 0.0f, adv_den = 1.0f;
+  if (a.moments) {
+    const double n = a.moments[2], s = a.moments[0], ss = a.moments[1];
+    const double mean = s / n;
+    double var = (ss - s * mean) / (n - 1.0);
+    if (var < 0.0) var = 0.0;
+    adv_mean = (float)mean; adv_den = (float)sqrt(var) + 1e-8f;
+  }
+  float st[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float dbias_a[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) dbias_a[k] = 0.0f;
+  float db2 = 0.0f;
+  for (int b = warp; b < a.B; b += nwarps) {
+    // ---- critic head: relu(pre + bias) -> max over the 4 group channels -> dot w2
+    float hv[16];
+    int field_arg[4];
+    float pooled[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {          // lane owns fields lane, lane+32, lane+64, lane+96
+      const int fld = lane + 32 * f;
+      float best = 0.0f; int bi = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float h = fmaxf(a.c_pre[(size_t)b * 512 + fld * 4 + r] + a.c_bias1[fld * 4 + r], 0.0f);
+        hv[f * 4 + r] = h;
+        if (r == 0 || h > best) { best = h; bi = r; }
+      }
+      pooled[f] = best; field_arg[f] = bi;
+    }
+    float vpart = 0.0f;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) vpart = fmaf(pooled[f], a.c_w2[lane + 32 * f], vpart);
+    const float value = warp_sum(vpart) + a.c_b2[0];
+    // ---- actor head decode (equiv.py:86-90) + Normal (robot_actor_critic.py:115-130)
+    float o10[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) o10[k] = a.a_out[(size_t)b * 16 + k] + a.a_bias[k];
+    // mean = [inv0, dx, dy, inv1, inv2] = out[2], out[0], out[1], out[3], out[4]; log_std = clamp(out[5:10], -20, 2)
+    const int mean_src[5] = {2, 0, 1, 3, 4};
+    float logp = 0.0f, ent = 0.0f, dmean[5], dls[5];
+    const float LOG_SQRT_2PI = 0.91893853320467267f;
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      const float mu = o10[mean_src[d]];
+      const float lraw = o10[5 + d];
+      const float ls = fminf(fmaxf(lraw, -20.0f), 2.0f);
+      const float sd = expf(ls), var = sd * sd;
+      const float diff = a.action[(size_t)b * 5 + d] - mu;
+      const float lsc = logf(sd);
+      logp += -(diff * diff) / (2.0f * var) - lsc - LOG_SQRT_2PI;
+      ent += 0.5f + LOG_SQRT_2PI + lsc;
+      dmean[d] = diff / var;                                   // d logp / d mu
+      const float inr = (lraw >= -20.0f && lraw <= 2.0f) ? 1.0f : 0.0f;
+      dls[d] = (diff * diff / var - 1.0f) * inr;               // d logp / d log_std (through the clamp)
+      // d entropy / d log_std = inr
+      o10[5 + d] = inr;
+    }
+    // ---- PPO loss (robot_ppo.py:345-398)
+    const float logr = logp - a.oldlp[b];
+    const float ratio = expf(logr);
+    const float advn = a.moments ? (a.adv[b] - adv_mean) / adv_den : a.adv[b];
+    const float l1 = -advn * ratio, l2 = -advn * fminf(fmaxf(ratio, a.clip_lo), a.clip_hi);
+    const float w1 = l1 > l2 ? 1.0f : (l1 == l2 ? 0.5f : 0.0f);
+    const float inr = (ratio >= a.clip_lo && ratio <= a.clip_hi) ? 1.0f : 0.0f;
+    const float g_logp = -advn * (w1 + (1.0f - w1) * inr) * ratio * a.inv_m;
+    const float g_H = -a.ent_c * a.inv_m;
+    const float R = a.ret[b], vold = a.vold[b];
+    float dv, vl;
+    if (a.clip_vloss) {
+      const float du = value - R, vu = du * du;
+      const float dd = value - vold, vc = vold + fminf(fmaxf(dd, -a.clip), a.clip);
+      const float dc = vc - R, lc = dc * dc;
+      const float ww = vu > lc ? 1.0f : (vu == lc ? 0.5f : 0.0f);
+      const float ir = (dd >= -a.clip && dd <= a.clip) ? 1.0f : 0.0f;
+      dv = (ww * du + (1.0f - ww) * dc * ir) * a.vf_c * a.inv_m;
+      vl = 0.5f * fmaxf(vu, lc);
+    } else {
+      const float du = value - R;
+      dv = du * a.vf_c * a.inv_m;
+      vl = 0.5f * du * du;
+    }
+    if (lane == 0) {
+      st[0] += fmaxf(l1, l2); st[1] += vl * a.vf_c; st[2] += ent; st[3] += -logr; st[4] += (ratio - 1.0f) - logr;
+      st[5] += fabsf(ratio - 1.0f) > a.clip ? 1.0f : 0.0f;
+      if (a.value_out) a.value_out[b] = value;
+      if (a.logp_out) a.logp_out[b] = logp;
+      // gradient wrt the 10 head outputs
+      float d10[10];
+#pragma unroll
+      for (int d = 0; d < 5; ++d) {
+        d10[mean_src[d]] = g_logp * dmean[d];
+        d10[5 + d] = g_logp * dls[d] + g_H * o10[5 + d];
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a.d_a_out[(size_t)b * 16 + k] = __float2bfloat16(k < 10 ? d10[k] : 0.0f);
+#pragma unroll
+      for (int k = 0; k < 10; ++k) dbias_a[k] += d10[k];
+      db2 += dv;
+    }
+    // ---- critic head backward: dv -> pooled -> arg-max channel with relu mask
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int fld = lane + 32 * f;
+      const float gp = dv * a.c_w2[fld];
+      atomicAdd(a.d_head + 10 + fld, dv * pooled[f]);            // d c_w2
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float g = (r == field_arg[f] && hv[f * 4 + r] > 0.0f) ? gp : 0.0f;
+        a.d_c_h[(size_t)b * 512 + fld * 4 + r] = __float2bfloat16(g);
+        if (g != 0.0f) atomicAdd(a.d_head + 10 + 128 + 1 + fld * 4 + r, g);   // d c_bias1 (per channel)
+      }
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) atomicAdd(a.stats + k, st[k]);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) atomicAdd(a.d_head + k, dbias_a[k]);
+    atomicAdd(a.d_head + 10 + 128, db2);
+  }
+}
+
+// ---- Adam on large flat buffers + global-norm pieces ---------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(long long n, const float* __restrict__ g, double* __restrict__ out) {
+  __shared__ double sh[8];
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = g[i];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    atomicAdd(out, t);
+  }
+}
+// clip coefficient from *sumsq (NULL -> 1): min(1, max_norm / (sqrt(sumsq) + 1e-6))
+__global__ void adam_flat_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m1,
+                                 float* __restrict__ m2, float lr_over_bc1, float beta1, float beta2, float eps, float sqrt_bc2,
+                                 const double* __restrict__ sumsq, float max_norm) {
+  float coef = 1.0f;
+  if (sumsq) {
+    const float total = (float)sqrt(*sumsq);
+    coef = fminf(max_norm / (total + 1e-6f), 1.0f);
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    float m = m1[i], v = m2[i];
+    m = m + (gi - m) * (1.0f - beta1);
+    v = v * beta2 + (1.0f - beta2) * gi * gi;
+    p[i] = p[i] - lr_over_bc1 * (m / (sqrtf(v) / sqrt_bc2 + eps));
+    m1[i] = m; m2[i] = v;
+  }
+}
+
+static unsigned grid_for(long long n, int block = 256, int cap = 148 * 16) {
+  long long g = (n + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace tc
+}  // namespace aur
+
+using namespace aur;
+using namespace aur::tc;
+
+extern "C" int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const void* dy_cm, const void* x_cm, int32_t base_off,
+                                 int32_t Wb, float* dwmat, int32_t split_k, void* stream) {
+  if (Cout <= 0 || Cin <= 0 || Q <= 0 || !dy_cm || !x_cm || !dwmat || Q % 8 != 0) {
+    set_error("aur_wgrad3x3_bf16: bad arguments (Q must be a multiple of 8)"); return AUR_ERR_ARG;
+  }
+  CUtensorMap tmA, tmB;
+  const uint64_t dA[2] = {(uint64_t)Q, (uint64_t)Cout}, dB[2] = {(uint64_t)Q, (uint64_t)Cin};
+  const uint64_t st[1] = {(uint64_t)Q * 2};
+  const uint32_t bx[2] = {WG_BK, WG_BM};
+  int rc;
+  if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dy_cm, dA, st, bx))) return rc;
+  if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x_cm, dB, st, bx))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    AUR_CUDA_OK(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
+    attr = true;
+  }
+  const int mt = (Cout + WG_BM - 1) / WG_BM, nt = (Cin + WG_BN - 1) / WG_BN;
+  if (split_k < 1) {
+    const int tiles = mt * nt * 9;
+    split_k = (2 * sm_count() + tiles - 1) / tiles;
+    const long long nkb = (Q + WG_BK - 1) / WG_BK;
+    if (split_k > nkb / 8) split_k = (int)(nkb / 8 > 0 ? nkb / 8 : 1);
+    if (split_k < 1) split_k = 1;
+  }
+  dim3 grid((unsigned)(mt * nt), 9, (unsigned)split_k);
+  wgrad3x3_kernel<<<grid, 256, WG_SMEM, (cudaStream_t)stream>>>(tmA, tmB, Cout, Cin, (long long)Q, base_off, Wb, nt, dwmat);
+  AUR_LAUNCH_OK("wgrad3x3_kernel");
+  return 0;
+}
+
+extern "C" int aur_unpool_relu_bwd(int32_t B, int32_t Hp, int32_t Wp, int32_t C, const void* dpool, const void* act,
+                                   int32_t aHb, int32_t aWb, int32_t aoff, const uint8_t* arg, void* dy, int32_t dHb,
+                                   int32_t dWb, int32_t doff, void* stream) {
+  if (B <= 0 || C % 8 != 0 || !dpool || !act || !arg || !dy) { set_error("aur_unpool_relu_bwd: bad arguments"); return AUR_ERR_ARG; }
+  const long long total = (long long)B * Hp * Wp * (C / 8);
+  unpool_relu_bwd_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+      B, Hp, Wp, C, (const __nv_bfloat16*)dpool, (const __nv_bfloat16*)act, aHb, aWb, aoff, arg, (__nv_bfloat16*)dy, dHb, dWb, doff);
+  AUR_LAUNCH_OK("unpool_relu_bwd_kernel");
+  return 0;
+}
+
+extern "C" int aur_transpose_bf16(int64_t R, int32_t C, const void* in, void* out, void* stream) {
+  if (R <= 0 || C <= 0 || !in || !out) { set_error("aur_transpose_bf16: bad arguments"); return AUR_ERR_ARG; }
+  dim3 grid((unsigned)((R + 63) / 64), (unsigned)((C + 63) / 64));
+  transpose_bf16_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((long long)R, C, (const __nv_bfloat16*)in, (__nv_bfloat16*)out);
+  AUR_LAUNCH_OK("transpose_bf16_kernel");
+  return 0;
+}
+
+extern "C" int aur_equiv_project_regular(const float* dwmat, int32_t Fo, int32_t Fi, float* dpsi, void* stream) {
+  if (!dwmat || !dpsi || Fo <= 0 || Fi <= 0) { set_error("aur_equiv_project_regular: bad arguments"); return AUR_ERR_ARG; }
+  const long long total = (long long)Fo * 4 * 9 * Fi * 4;
+  project_reg_reg_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(dwmat, Fo, Fi, dpsi);
+  AUR_LAUNCH_OK("project_reg_reg_kernel");
+  return 0;
+}
+
+extern "C" int aur_rowsum_bf16(int32_t C, int64_t Q, const void* in_cm, int32_t group, float* out, void* stream) {
+  if (C <= 0 || Q <= 0 || !in_cm || !out || group <= 0) { set_error("aur_rowsum_bf16: bad arguments"); return AUR_ERR_ARG; }
+  rowsum_bf16_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(C, (long long)Q, (const __nv_bfloat16*)in_cm, group, out);
+  AUR_LAUNCH_OK("rowsum_bf16_kernel");
+  return 0;
+}
+
+extern "C" int aur_equiv_conv0_wgrad(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg,
+                                     int32_t B, float* scratch /*[64*18 + 64], zeroed by this call*/, float* dpsi, float* dbias_f,
+                                     void* stream) {
+  if (!obs || !state || !da1 || !a1 || !arg || !scratch || !dpsi || !dbias_f || B <= 0) {
+    set_error("aur_equiv_conv0_wgrad: bad arguments"); return AUR_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  AUR_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(float) * (64 * 18 + 64), s));
+  conv0_wgrad_kernel<<<148 * 4, 256, 0, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg, B, scratch,
+                                            scratch + 64 * 18);
+  AUR_LAUNCH_OK("conv0_wgrad_kernel");
+  project_conv0_kernel<<<(64 * 18 + 255) / 256, 256, 0, s>>>(scratch, scratch + 64 * 18, dpsi, dbias_f);
+  AUR_LAUNCH_OK("project_conv0_kernel");
+  return 0;
+}
+
+extern "C" int aur_bias_relu_bf16(int64_t rows, int32_t C, const float* in, const float* bias, void* out, void* stream) {
+  if (rows <= 0 || C <= 0 || !in || !bias || !out) { set_error("aur_bias_relu_bf16: bad arguments"); return AUR_ERR_ARG; }
+  bias_relu_kernel<<<grid_for(rows * C), 256, 0, (cudaStream_t)stream>>>(rows * C, C, in, bias, (__nv_bfloat16*)out);
+  AUR_LAUNCH_OK("bias_relu_kernel");
+  return 0;
+}
+extern "C" int aur_relu_mask_bf16(int64_t n, const float* g, const void* ref, void* out, void* stream) {
+  if (n <= 0 || !g || !out) { set_error("aur_relu_mask_bf16: bad arguments"); return AUR_ERR_ARG; }
+  if (ref) relu_mask_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, g, (const __nv_bfloat16*)ref, (__nv_bfloat16*)out);
+  else f32_to_bf16_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, g, (__nv_bfloat16*)out);
+  AUR_LAUNCH_OK("relu_mask_kernel");
+  return 0;
+}
+
+extern "C" int aur_equiv_head_loss(const aur_equiv_head_args* h, void* stream) {
+  if (!h || h->B <= 0 || !h->a_out || !h->a_bias || !h->c_pre || !h->c_bias1 || !h->c_w2 || !h->c_b2 || !h->action || !h->oldlp ||
+      !h->adv || !h->ret || !h->vold || !h->d_a_out || !h->d_c_h || !h->d_head || !h->stats || h->m_total <= 0) {
+    set_error("aur_equiv_head_loss: bad arguments"); return AUR_ERR_ARG;
+  }
+  HeadLossDev d;
+  d.B = h->B; d.a_out = h->a_out; d.a_bias = h->a_bias; d.c_pre = h->c_pre; d.c_bias1 = h->c_bias1; d.c_w2 = h->c_w2; d.c_b2 = h->c_b2;
+  d.action = h->action; d.oldlp = h->oldlp; d.adv = h->adv; d.ret = h->ret; d.vold = h->vold; d.moments = h->adv_moments;
+  d.clip = h->clip_coeff; d.clip_lo = (float)(1.0 - (double)h->clip_coeff); d.clip_hi = (float)(1.0 + (double)h->clip_coeff);
+  d.ent_c = h->entropy_coeff; d.vf_c = h->value_coeff; d.inv_m = (float)(1.0 / (double)h->m_total); d.clip_vloss = h->clip_vloss;
+  d.d_a_out = (__nv_bfloat16*)h->d_a_out; d.d_c_h = (__nv_bfloat16*)h->d_c_h; d.d_head = h->d_head; d.stats = h->stats;
+  d.value_out = h->value_out; d.logp_out = h->logp_out;
+  const unsigned grid = grid_for((long long)h->B * 32, 256, 148 * 4);
+  head_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d);
+  AUR_LAUNCH_OK("head_loss_kernel");
+  return 0;
+}
+
+extern "C" int aur_sumsq_f32(int64_t n, const float* g, double* out_accum, void* stream) {
+  if (n <= 0 || !g || !out_accum) { set_error("aur_sumsq_f32: bad arguments"); return AUR_ERR_ARG; }
+  sumsq_kernel<<<grid_for(n, 256, 148 * 2), 256, 0, (cudaStream_t)stream>>>(n, g, out_accum);
+  AUR_LAUNCH_OK("sumsq_kernel");
+  return 0;
+}
+
+extern "C" int aur_adam_flat(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, double lr,
+                             double beta1, double beta2, double eps, int64_t step, const double* clip_sumsq,
+                             double max_grad_norm, void* stream) {
+  if (n <= 0 || !params || !grads || !exp_avg || !exp_avg_sq || step < 1) { set_error("aur_adam_flat: bad arguments"); return AUR_ERR_ARG; }
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  adam_flat_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, params, grads, exp_avg, exp_avg_sq, (float)(lr / bc1),
+                                                                 (float)beta1, (float)beta2, (float)eps, (float)sqrt(bc2),
+                                                                 clip_sumsq, (float)max_grad_norm);
+  AUR_LAUNCH_OK("adam_flat_kernel");
+  return 0;
+}

@@ -1,0 +1,295 @@
+"""Equivariant actor-critic update on the B200 (row X): host-side mirror of
+`robot_actor_critic.evaluate` (src/models/robot_actor_critic.py:104-131) over
+`EquivariantActor` / `EquivariantCritic` (src/nets/equiv.py:65-157) and of the minibatch step of
+`robot_ppo.update` (src/robot_ppo.py:329-408: PPO loss, clip_grad_norm_ on the ACTOR only, one Adam
+over actor + critic, eps=1e-5).
+
+Every convolution / dense contraction runs on tcgen05 tensor cores through the C ABI
+(aur_conv3x3_bf16, aur_wgrad3x3_bf16, aur_tc_gemm_bf16); activations are bf16 NHWC with explicit
+halos, accumulation is fp32, parameters / gradients / Adam moments are fp32.  The free parameters are
+the p4 group-convolution filters psi (see oracle/equiv_ref.py for the restated architecture and why
+weights are not interchangeable with e2cnn checkpoints).  No CPU path.
+
+Host-side torch ops are used only for plumbing on tiny tensors: the expansion / projection of the
+two 1x1 head filters (<= 262k elements) and buffer zeroing.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from .kernels import _ptr, _stream, conv3x3_bf16, equiv_conv0, equiv_expand_regular, tc_gemm_bf16
+
+ENC_FIELDS = [16, 32, 64, 128, 256, 128, 128]
+N_ACT = 5
+
+
+def _chk(rc, what):
+    _lib.check(rc, what)
+
+
+def init_params(seed: int = 0, device="cuda", scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """He-style init of psi for one actor and one critic (separate encoders), fp32 on `device`."""
+    g = torch.Generator().manual_seed(seed)
+    p: Dict[str, torch.Tensor] = {}
+    for net in ("actor", "critic"):
+        cin_f = None
+        for l, fo in enumerate(ENC_FIELDS):
+            if l == 0:
+                p[f"{net}.enc{l}.psi"] = torch.randn(fo, 2, 3, 3, generator=g) * scale * math.sqrt(2.0 / 18)
+            else:
+                p[f"{net}.enc{l}.psi"] = torch.randn(fo, cin_f, 4, 3, 3, generator=g) * scale * math.sqrt(2.0 / (cin_f * 36))
+            p[f"{net}.enc{l}.bias"] = 0.01 * torch.randn(fo, generator=g)
+            cin_f = fo
+    F = ENC_FIELDS[-1]
+    p["actor.head.psi_irrep"] = torch.randn(F, 2, generator=g) * math.sqrt(1.0 / (F * 4))
+    p["actor.head.psi_triv"] = torch.randn(2 * N_ACT - 2, F, generator=g) * math.sqrt(1.0 / (F * 4))
+    p["actor.head.bias_triv"] = 0.01 * torch.randn(2 * N_ACT - 2, generator=g)
+    p["critic.head1.psi"] = torch.randn(F, F, 4, 1, 1, generator=g) * math.sqrt(2.0 / (F * 4))
+    p["critic.head1.bias"] = 0.01 * torch.randn(F, generator=g)
+    p["critic.head2.w"] = torch.randn(1, F, generator=g) * math.sqrt(1.0 / F)
+    p["critic.head2.bias"] = 0.01 * torch.randn(1, generator=g)
+    return {k: v.to(device).contiguous() for k, v in p.items()}
+
+
+class _Enc:
+    """Activation / gradient buffers of one encoder for a fixed batch size."""
+
+    def __init__(self, B: int, dev):
+        bf = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
+        u8 = lambda *s: torch.zeros(*s, dtype=torch.uint8, device=dev)
+        self.a = [bf(B, 66, 66, 64), bf(B, 34, 34, 128), bf(B, 18, 18, 256), bf(B, 10, 10, 512), bf(B, 8, 8, 1024),
+                  bf(B, 3, 3, 512)]
+        self.arg = [u8(B, 64, 64, 64), u8(B, 32, 32, 128), u8(B, 16, 16, 256), u8(B, 8, 8, 512), None, u8(B, 3, 3, 512)]
+        self.feat = bf(B, 512)
+
+
+class EquivActorCritic:
+    def __init__(self, params: Dict[str, torch.Tensor], batch: int, lr: float = 3e-4, eps: float = 1e-5,
+                 betas=(0.9, 0.999)):
+        if batch % 8:
+            raise _lib.AurError("batch must be a multiple of 8 (16-byte rows for the TMA weight-gradient maps)")
+        _lib.lib()
+        self.p = params
+        self.dev = next(iter(params.values())).device
+        if self.dev.type != "cuda":
+            raise _lib.AurError("EquivActorCritic needs CUDA parameters (no CPU fallback)")
+        self.B = batch
+        self.enc = {"actor": _Enc(batch, self.dev), "critic": _Enc(batch, self.dev)}
+        self.grads = {k: torch.zeros_like(v) for k, v in params.items()}
+        self.m1 = {k: torch.zeros_like(v) for k, v in params.items()}
+        self.m2 = {k: torch.zeros_like(v) for k, v in params.items()}
+        self.lr, self.eps, self.betas, self.step_count = lr, eps, betas, 0
+        self.stats = torch.zeros(8, device=self.dev)
+        self.d_head = torch.zeros(651, device=self.dev)
+        self.moments = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self.ws = torch.zeros(1 << 20, device=self.dev)
+        self.value = torch.zeros(batch, device=self.dev)
+        self.logp = torch.zeros(batch, device=self.dev)
+        self._idx11 = None
+        self._w = {}
+
+    # ------------------------------------------------------------------ weights
+    def _expand(self):
+        """psi -> bf16 contraction matrices (forward, backward-data) and per-channel biases."""
+        w = {}
+        for net in ("actor", "critic"):
+            for l in range(1, 6):
+                wm, wt, b = equiv_expand_regular(self.p[f"{net}.enc{l}.psi"], self.p[f"{net}.enc{l}.bias"], want_wt=True)
+                w[f"{net}.{l}"] = (wm, wt, b)
+            wm, _, b = equiv_expand_regular(self.p[f"{net}.enc6.psi"], self.p[f"{net}.enc6.bias"])
+            wm = wm.reshape(512, 4608)
+            w[f"{net}.6"] = (wm, wm.t().contiguous(), b)
+        # heads (tiny, torch plumbing): actor [16,512] (10 used), critic head-1 [512,512]
+        pi, pt = self.p["actor.head.psi_irrep"], self.p["actor.head.psi_triv"]
+        c = torch.tensor([1.0, 0.0, -1.0, 0.0], device=self.dev); s = torch.tensor([0.0, 1.0, 0.0, -1.0], device=self.dev)
+        a_, b_ = pi[:, 0:1], pi[:, 1:2]
+        Wa = torch.zeros(16, 512, device=self.dev)
+        Wa[0] = (c * a_ - s * b_).reshape(-1)
+        Wa[1] = (s * a_ + c * b_).reshape(-1)
+        Wa[2:10] = pt.unsqueeze(-1).expand(-1, -1, 4).reshape(8, 512)
+        w["actor.head"] = (Wa.bfloat16().contiguous(), Wa.t().contiguous().bfloat16().contiguous())
+        psi1 = self.p["critic.head1.psi"].reshape(128, 128, 4)
+        if self._idx11 is None:
+            o = torch.arange(128, device=self.dev).view(128, 1, 1, 1); r = torch.arange(4, device=self.dev).view(1, 4, 1, 1)
+            i = torch.arange(128, device=self.dev).view(1, 1, 128, 1); s_ = torch.arange(4, device=self.dev).view(1, 1, 1, 4)
+            self._idx11 = ((o * 128 + i) * 4 + ((s_ - r) % 4)).reshape(512, 512)
+        W1 = psi1.reshape(-1)[self._idx11]
+        w["critic.head1"] = (W1.bfloat16().contiguous(), W1.t().contiguous().bfloat16().contiguous(),
+                             self.p["critic.head1.bias"].repeat_interleave(4).contiguous())
+        self._w = w
+
+    # ------------------------------------------------------------------ forward
+    def _encoder_forward(self, net: str, state, obs):
+        e, w = self.enc[net], self._w
+        equiv_conv0(obs, state, self.p[f"{net}.enc0.psi"], self.p[f"{net}.enc0.bias"], e.a[0], e.arg[0])
+        for l, (epi, off) in zip(range(1, 6), [(2, 1), (2, 1), (2, 1), (1, 0), (2, 0)]):
+            wm, _, b = w[f"{net}.{l}"]
+            conv3x3_bf16(e.a[l - 1], wm, b, epi, e.a[l], off, e.arg[l])
+        wm6, _, b6 = w[f"{net}.6"]
+        pre = tc_gemm_bf16(e.a[5].reshape(self.B, 4608), wm6)
+        L = _lib.lib()
+        with torch.cuda.device(self.dev):
+            _chk(L.aur_bias_relu_bf16(self.B, 512, pre.data_ptr(), b6.data_ptr(), e.feat.data_ptr(), _stream()), "aur_bias_relu_bf16")
+
+    def forward(self, state: torch.Tensor, obs: torch.Tensor):
+        """Encoders + head GEMMs; returns (actor head output [B,16] fp32, critic head-1 pre-activation [B,512] fp32)."""
+        self._expand()
+        self._encoder_forward("actor", state, obs)
+        self._encoder_forward("critic", state, obs)
+        a_out = tc_gemm_bf16(self.enc["actor"].feat, self._w["actor.head"][0])
+        c_pre = tc_gemm_bf16(self.enc["critic"].feat, self._w["critic.head1"][0])
+        return a_out, c_pre
+
+    # ----------------------------------------------------------------- backward
+    def _t(self, x2d: torch.Tensor) -> torch.Tensor:
+        R, C = x2d.shape
+        out = torch.empty(C, R, dtype=torch.bfloat16, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _chk(_lib.lib().aur_transpose_bf16(R, C, x2d.data_ptr(), out.data_ptr(), _stream()), "aur_transpose_bf16")
+        return out
+
+    def _cast(self, g: torch.Tensor, ref: Optional[torch.Tensor]) -> torch.Tensor:
+        out = torch.empty(g.shape, dtype=torch.bfloat16, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _chk(_lib.lib().aur_relu_mask_bf16(g.numel(), g.data_ptr(), _ptr(ref), out.data_ptr(), _stream()), "aur_relu_mask_bf16")
+        return out
+
+    def _wgrad(self, net: str, l: int, dy_buf: torch.Tensor, x_buf: torch.Tensor, base_off: int):
+        """dpsi_l, dbias_l from the haloed output-gradient buffer and the layer's input buffer."""
+        L = _lib.lib()
+        B, Hb, Wb, Cin = x_buf.shape
+        Cout = dy_buf.shape[3]
+        Q = B * Hb * Wb
+        dy_cm, x_cm = self._t(dy_buf.reshape(Q, Cout)), self._t(x_buf.reshape(Q, Cin))
+        dw = torch.zeros(Cout, 9, Cin, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _chk(L.aur_wgrad3x3_bf16(Cout, Cin, Q, dy_cm.data_ptr(), x_cm.data_ptr(), base_off, Wb, dw.data_ptr(), 0, _stream()),
+                 "aur_wgrad3x3_bf16")
+            _chk(L.aur_equiv_project_regular(dw.data_ptr(), Cout // 4, Cin // 4, self.grads[f"{net}.enc{l}.psi"].data_ptr(), _stream()),
+                 "aur_equiv_project_regular")
+            _chk(L.aur_rowsum_bf16(Cout, Q, dy_cm.data_ptr(), 4, self.grads[f"{net}.enc{l}.bias"].data_ptr(), _stream()),
+                 "aur_rowsum_bf16")
+
+    def _unpool(self, dpool, act, aoff, arg, C, Hp, dHb, doff):
+        out = torch.zeros(self.B, dHb, dHb, C, dtype=torch.bfloat16, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _chk(_lib.lib().aur_unpool_relu_bwd(self.B, Hp, Hp, C, dpool.data_ptr(), act.data_ptr(), act.shape[1], act.shape[2],
+                                                aoff, arg.data_ptr(), out.data_ptr(), dHb, dHb, doff, _stream()), "aur_unpool_relu_bwd")
+        return out
+
+    def _encoder_backward(self, net: str, state, obs, dfeat: torch.Tensor):
+        """dfeat: fp32 [B,512] gradient wrt the encoder output (post-ReLU features)."""
+        L = _lib.lib()
+        e, w, B = self.enc[net], self._w, self.B
+        dz6 = self._cast(dfeat, e.feat)                                         # through the last ReLU
+        wm6, wm6t, _ = w[f"{net}.6"]
+        # layer 6 (dense 3x3 -> 1x1): weight gradient [512,4608] = dz6^T a6 ; data gradient = dz6 W6
+        dz6_cm = self._t(dz6)
+        dW6 = tc_gemm_bf16(dz6_cm, self._t(e.a[5].reshape(B, 4608)))
+        with torch.cuda.device(self.dev):
+            _chk(L.aur_equiv_project_regular(dW6.data_ptr(), 128, 128, self.grads[f"{net}.enc6.psi"].data_ptr(), _stream()),
+                 "aur_equiv_project_regular")
+            _chk(L.aur_rowsum_bf16(512, B, dz6_cm.data_ptr(), 4, self.grads[f"{net}.enc6.bias"].data_ptr(), _stream()),
+                 "aur_rowsum_bf16")
+        da6 = self._cast(tc_gemm_bf16(dz6, wm6t), None).reshape(B, 3, 3, 512)
+        # layer 5 (pad 0, pooled): un-pool into a 2-halo buffer (backward-data) and into the input geometry (weights)
+        dy5_d = self._unpool(da6, e.a[5], 0, e.arg[5], 512, 3, 10, 2)
+        dy5_w = self._unpool(da6, e.a[5], 0, e.arg[5], 512, 3, 8, 0)
+        self._wgrad(net, 5, dy5_w, e.a[4], 0)
+        dy4 = torch.zeros(B, 10, 10, 1024, dtype=torch.bfloat16, device=self.dev)
+        conv3x3_bf16(dy5_d, w[f"{net}.5"][1], None, 3, dy4, 1, None, relu_ref=e.a[4], ref_off=0)   # x ReLU mask of layer 4
+        # layer 4 (pad 1, ReLU only)
+        self._wgrad(net, 4, dy4, e.a[3], -(10 + 1))
+        da4 = torch.empty(B, 8, 8, 512, dtype=torch.bfloat16, device=self.dev)
+        conv3x3_bf16(dy4, w[f"{net}.4"][1], None, 0, da4, 0)
+        # layers 3, 2, 1 (pad 1, pooled)
+        dprev = da4
+        for l, Hp, C in ((3, 8, 512), (2, 16, 256), (1, 32, 128)):
+            Hb = 2 * Hp + 2
+            dy = self._unpool(dprev, e.a[l], 1, e.arg[l], C, Hp, Hb, 1)
+            self._wgrad(net, l, dy, e.a[l - 1], -(Hb + 1))
+            Cin = e.a[l - 1].shape[3]
+            dprev = torch.empty(B, 2 * Hp, 2 * Hp, Cin, dtype=torch.bfloat16, device=self.dev)
+            conv3x3_bf16(dy, w[f"{net}.{l}"][1], None, 0, dprev, 0)
+        # layer 0 (direct)
+        with torch.cuda.device(self.dev):
+            _chk(L.aur_equiv_conv0_wgrad(obs.data_ptr(), state.data_ptr(), dprev.data_ptr(), e.a[0].data_ptr(), e.arg[0].data_ptr(),
+                                         B, self.ws.data_ptr(), self.grads[f"{net}.enc0.psi"].data_ptr(),
+                                         self.grads[f"{net}.enc0.bias"].data_ptr(), _stream()), "aur_equiv_conv0_wgrad")
+
+    # ------------------------------------------------------------------- update
+    def loss_and_grads(self, state, obs, action, oldlp, adv, ret, vold, clip_coeff=0.2, entropy_coeff=0.01,
+                       value_coeff=0.5, norm_adv=True, clip_vloss=True) -> torch.Tensor:
+        """Forward + loss + full backward; gradients land in self.grads.  Returns the stats tensor (means)."""
+        L = _lib.lib()
+        B = self.B
+        for g in self.grads.values():
+            g.zero_()
+        self.stats.zero_(); self.d_head.zero_()
+        a_out, c_pre = self.forward(state, obs)
+        if norm_adv:
+            a64 = adv.double()
+            self.moments.copy_(torch.stack([a64.sum(), (a64 * a64).sum(), torch.tensor(float(B), dtype=torch.float64, device=self.dev)]))
+        d_a_out = torch.empty(B, 16, dtype=torch.bfloat16, device=self.dev)
+        d_c_h = torch.empty(B, 512, dtype=torch.bfloat16, device=self.dev)
+        a_bias = torch.cat([torch.zeros(2, device=self.dev), self.p["actor.head.bias_triv"]]).contiguous()
+        h = _lib.EquivHeadArgs()
+        h.B, h.clip_vloss, h.m_total = B, int(bool(clip_vloss)), B
+        h.a_out, h.a_bias, h.c_pre = a_out.data_ptr(), a_bias.data_ptr(), c_pre.data_ptr()
+        h.c_bias1 = self._w["critic.head1"][2].data_ptr()
+        w2 = self.p["critic.head2.w"].reshape(-1).contiguous()
+        h.c_w2, h.c_b2 = w2.data_ptr(), self.p["critic.head2.bias"].data_ptr()
+        h.action, h.oldlp, h.adv, h.ret, h.vold = (t.data_ptr() for t in (action, oldlp, adv, ret, vold))
+        h.adv_moments = self.moments.data_ptr() if norm_adv else None
+        h.clip_coeff, h.entropy_coeff, h.value_coeff = float(clip_coeff), float(entropy_coeff), float(value_coeff)
+        h.d_a_out, h.d_c_h, h.d_head, h.stats = d_a_out.data_ptr(), d_c_h.data_ptr(), self.d_head.data_ptr(), self.stats.data_ptr()
+        h.value_out, h.logp_out = self.value.data_ptr(), self.logp.data_ptr()
+        with torch.cuda.device(self.dev):
+            _chk(L.aur_equiv_head_loss(ctypes.byref(h), _stream()), "aur_equiv_head_loss")
+        # ---- head parameter gradients (contractions on tensor cores, projection = tiny torch plumbing)
+        fa, fc = self.enc["actor"].feat, self.enc["critic"].feat
+        dWa = tc_gemm_bf16(self._t(d_a_out), self._t(fa))                       # [16,512]
+        c = torch.tensor([1.0, 0.0, -1.0, 0.0], device=self.dev); s = torch.tensor([0.0, 1.0, 0.0, -1.0], device=self.dev)
+        g0, g1 = dWa[0].reshape(128, 4), dWa[1].reshape(128, 4)
+        self.grads["actor.head.psi_irrep"].copy_(torch.stack([(c * g0 + s * g1).sum(1), (-s * g0 + c * g1).sum(1)], 1))
+        self.grads["actor.head.psi_triv"].copy_(dWa[2:10].reshape(8, 128, 4).sum(2))
+        self.grads["actor.head.bias_triv"].copy_(self.d_head[2:10])
+        dW1 = tc_gemm_bf16(self._t(d_c_h), self._t(fc))                         # [512,512]
+        self.grads["critic.head1.psi"].reshape(-1).index_add_(0, self._idx11.reshape(-1), dW1.reshape(-1))
+        self.grads["critic.head1.bias"].copy_(self.d_head[139:651].reshape(128, 4).sum(1))
+        self.grads["critic.head2.w"].copy_(self.d_head[10:138].reshape(1, 128))
+        self.grads["critic.head2.bias"].copy_(self.d_head[138:139])
+        # ---- gradients wrt the encoder features, then the two encoders
+        dfa = tc_gemm_bf16(d_a_out, self._w["actor.head"][1])                   # [B,512] fp32
+        dfc = tc_gemm_bf16(d_c_h, self._w["critic.head1"][1])
+        self._encoder_backward("actor", state, obs, dfa)
+        self._encoder_backward("critic", state, obs, dfc)
+        st = self.stats / B
+        return st
+
+    def apply(self, lr: Optional[float] = None, max_grad_norm: float = 0.5):
+        """clip_grad_norm_ on the ACTOR parameters only (robot_ppo.py:401), then Adam over everything."""
+        L = _lib.lib()
+        self.step_count += 1
+        lr = self.lr if lr is None else lr
+        self.sumsq.zero_()
+        with torch.cuda.device(self.dev):
+            for k, g in self.grads.items():
+                if k.startswith("actor."):
+                    _chk(L.aur_sumsq_f32(g.numel(), g.data_ptr(), self.sumsq.data_ptr(), _stream()), "aur_sumsq_f32")
+            for k, p in self.p.items():
+                clip = self.sumsq.data_ptr() if k.startswith("actor.") else None
+                _chk(L.aur_adam_flat(p.numel(), p.data_ptr(), self.grads[k].data_ptr(), self.m1[k].data_ptr(), self.m2[k].data_ptr(),
+                                     lr, self.betas[0], self.betas[1], self.eps, self.step_count, clip, max_grad_norm, _stream()),
+                     "aur_adam_flat")
+
+    def update(self, state, obs, action, oldlp, adv, ret, vold, lr=None, max_grad_norm=0.5, **kw) -> torch.Tensor:
+        st = self.loss_and_grads(state, obs, action, oldlp, adv, ret, vold, **kw)
+        self.apply(lr, max_grad_norm)
+        return st

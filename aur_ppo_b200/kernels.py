@@ -238,13 +238,16 @@ def equiv_expand_regular(psi: torch.Tensor, bias_f: Optional[torch.Tensor] = Non
 
 
 def conv3x3_bf16(inp: torch.Tensor, wmat: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int,
-                 out: torch.Tensor, out_off: int, pool_arg: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 out: torch.Tensor, out_off: int, pool_arg: Optional[torch.Tensor] = None,
+                 relu_ref: Optional[torch.Tensor] = None, ref_off: int = 0) -> torch.Tensor:
     """inp [B,Hb,Wb,Cin] bf16 (halo included) -> valid 3x3 conv (+bias/ReLU/pool) into out[:, off:, off:, :]."""
     import ctypes
     B, Hb, Wb, Cin = inp.shape
     Cout = wmat.shape[0]
     a = _lib.ConvArgs(B, Hb, Wb, Cin, Cout, epilogue, out.shape[1], out.shape[2], out_off, 0, inp.data_ptr(),
-                      wmat.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(pool_arg))
+                      wmat.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(pool_arg), _ptr(relu_ref),
+                      relu_ref.shape[1] if relu_ref is not None else 0, relu_ref.shape[2] if relu_ref is not None else 0,
+                      ref_off, 0)
     with torch.cuda.device(inp.device):
         rc = _lib.lib().aur_conv3x3_bf16(ctypes.byref(a), _stream())
     _lib.check(rc, "aur_conv3x3_bf16")

@@ -254,7 +254,8 @@ int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, const void*
  * zero halo; a 3x3 layer is a valid convolution over the buffer (output H = Hb - 2). */
 typedef struct {
   int32_t B, Hb, Wb, Cin, Cout;   /* input buffer [B,Hb,Wb,Cin] bf16; Cin % 64 == 0, Cout % 32 == 0 */
-  int32_t epilogue;               /* 0 linear, 1 bias + ReLU, 2 bias + ReLU + 2x2 max-pool */
+  int32_t epilogue;               /* 0 linear, 1 bias + ReLU, 2 bias + ReLU + 2x2 max-pool,
+                                     3 linear * (relu_ref > 0): backward-data through a ReLU-only layer */
   int32_t out_Hb, out_Wb, out_off;/* output buffer [B,out_Hb,out_Wb,Cout] bf16, written at (+off,+off) */
   int32_t _pad;
   const void* in;
@@ -262,6 +263,8 @@ typedef struct {
   const float* bias;              /* [Cout] fp32 or NULL */
   void* out;
   uint8_t* pool_arg;              /* [B,Ho/2,Wo/2,Cout] arg-max (0..3) of each pool window, or NULL */
+  const void* relu_ref;           /* epilogue 3: forward activation buffer [B,ref_Hb,ref_Wb,Cout], interior at +ref_off */
+  int32_t ref_Hb, ref_Wb, ref_off, _pad2;
 } aur_conv_args;
 
 /* implicit-GEMM 3x3 convolution on tcgen05 (TMA halo boxes, TMEM accumulator, fused epilogue). */
@@ -277,6 +280,67 @@ int aur_equiv_expand_regular(const float* psi, int32_t Fo, int32_t Fi, const flo
  * psi [16,2,3,3], bias [16] -> interior of out [B,66,66,64] bf16 (caller zeroes the halo once). */
 int aur_equiv_conv0(const float* obs, const float* state, const float* psi, const float* bias_f, int32_t B, void* out,
                     uint8_t* pool_arg, void* stream);
+
+/* weight gradient of a 3x3 layer: dwmat[co][tap][ci] (fp32, ACCUMULATED with atomics: zero it first) +=
+ * sum_q dy_cm[co][q] * x_cm[ci][q + base_off + dy*Wb + dx], q the flat pixel index of the haloed buffers
+ * (channel-major bf16 copies, Q % 8 == 0).  Split-K tcgen05 GEMM; split_k <= 0 picks it. */
+int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const void* dy_cm, const void* x_cm, int32_t base_off,
+                      int32_t Wb, float* dwmat, int32_t split_k, void* stream);
+
+/* max-pool(2) + ReLU backward: dpool [B,Hp,Wp,C] bf16, forward pooled activations `act` (buffer
+ * [B,aHb,aWb,C], interior at +aoff), arg [B,Hp,Wp,C] -> dy buffer [B,dHb,dWb,C] interior at +doff. */
+int aur_unpool_relu_bwd(int32_t B, int32_t Hp, int32_t Wp, int32_t C, const void* dpool, const void* act, int32_t aHb,
+                        int32_t aWb, int32_t aoff, const uint8_t* arg, void* dy, int32_t dHb, int32_t dWb, int32_t doff,
+                        void* stream);
+
+int aur_transpose_bf16(int64_t R, int32_t C, const void* in, void* out, void* stream);   /* [R][C] -> [C][R] */
+
+/* adjoint of aur_equiv_expand_regular: dpsi [Fo,Fi,4,3,3] += projection of dwmat [Fo*4][9][Fi*4] */
+int aur_equiv_project_regular(const float* dwmat, int32_t Fo, int32_t Fi, float* dpsi, void* stream);
+
+/* out[c / group] += sum_q in_cm[c][q]  (bias gradients from the channel-major output gradient) */
+int aur_rowsum_bf16(int32_t C, int64_t Q, const void* in_cm, int32_t group, float* out, void* stream);
+
+/* layer-0 weight gradient fused with its un-pooling: dpsi [16,2,3,3] +=, dbias_f [16] += */
+int aur_equiv_conv0_wgrad(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg, int32_t B,
+                          float* scratch, float* dpsi, float* dbias_f, void* stream);
+
+int aur_bias_relu_bf16(int64_t rows, int32_t C, const float* in, const float* bias, void* out, void* stream);
+int aur_relu_mask_bf16(int64_t n, const float* g, const void* ref, void* out, void* stream); /* ref NULL: plain cast */
+
+/* Heads + loss of the equivariant update: actor head decode (src/nets/equiv.py:86-90), Normal log-prob and
+ * entropy summed over the 5 action dims (src/models/robot_actor_critic.py:115-130), critic head ReLU +
+ * GroupPooling + value (src/nets/equiv.py:138-150), PPO loss seeds (src/robot_ppo.py:345-398). */
+typedef struct {
+  int32_t B;
+  int32_t clip_vloss;
+  int64_t m_total;
+  const float* a_out;        /* [B,16] actor head output before bias (10 used) */
+  const float* a_bias;       /* [10] */
+  const float* c_pre;        /* [B,512] critic head-1 output before bias */
+  const float* c_bias1;      /* [512] */
+  const float* c_w2;         /* [128] */
+  const float* c_b2;         /* [1] */
+  const float* action;       /* [B,5] */
+  const float* oldlp;
+  const float* adv;
+  const float* ret;
+  const float* vold;
+  const double* adv_moments; /* [3] or NULL */
+  float clip_coeff, entropy_coeff, value_coeff, _pad;
+  void* d_a_out;             /* [B,16] bf16 out */
+  void* d_c_h;               /* [B,512] bf16 out */
+  float* d_head;             /* [651] accumulated: a_bias 10 | c_w2 128 | c_b2 1 | c_bias1 512 */
+  float* stats;              /* [8] accumulated sums */
+  float* value_out;          /* [B] or NULL */
+  float* logp_out;           /* [B] or NULL */
+} aur_equiv_head_args;
+int aur_equiv_head_loss(const aur_equiv_head_args* args, void* stream);
+
+int aur_sumsq_f32(int64_t n, const float* g, double* out_accum, void* stream);
+/* torch.optim.Adam math on a flat buffer; clip_sumsq (nullable) = device sum of squares of the clipped group */
+int aur_adam_flat(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, double lr, double beta1,
+                  double beta2, double eps, int64_t step, const double* clip_sumsq, double max_grad_norm, void* stream);
 
 /* Evaluates the deterministic fp64 sin/cos the env kernels use (csrc/det_sincos.h) on n
  * device doubles -- exported so tests can compare it with the host copy bit for bit. */
