@@ -143,8 +143,8 @@ def lib() -> ctypes.CDLL:
     L.aur_transpose_bf16.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p]
     L.aur_equiv_project_regular.restype = c_int
     L.aur_equiv_project_regular.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p]
-    L.aur_rowsum_bf16.restype = c_int
-    L.aur_rowsum_bf16.argtypes = [c_int32, c_int64, c_void_p, c_int32, c_void_p, c_void_p]
+    L.aur_colsum_bf16.restype = c_int
+    L.aur_colsum_bf16.argtypes = [c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p]
     L.aur_equiv_conv0_wgrad.restype = c_int
     L.aur_equiv_conv0_wgrad.argtypes = [c_void_p] * 5 + [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
     L.aur_bias_relu_bf16.restype = c_int

@@ -17,7 +17,12 @@ constexpr int WG_BM = 128, WG_BN = 128, WG_BK = 64, WG_STAGES = 4;
 constexpr int WG_A_BYTES = WG_BM * WG_BK * 2, WG_B_BYTES = WG_BN * WG_BK * 2;
 constexpr size_t WG_SMEM = (size_t)WG_STAGES * (WG_A_BYTES + WG_B_BYTES) + 1024 + 256;
 
-// grid: x = (Cout tiles) * (Cin tiles), y = tap, z = split-K slice
+// grid: x = (Cout tiles) * (Cin tiles), y = tap, z = split-K slice.
+// Operands come STRAIGHT from the NHWC buffers (pixel rows, channels contiguous) as MN-major UMMA
+// operands: a stage holds, per operand, two TMA boxes of [64 pixel rows][64 channels] (128-B rows,
+// 128-B swizzle); 8 pixel rows form one 1024-B swizzle atom, the two channel halves are 8192 B apart
+// (LBO), successive groups of 8 pixel rows 1024 B apart (SBO).  The tap shift is a shift of the PIXEL
+// (row) coordinate of the input map, which TMA takes at element granularity.
 __global__ void __launch_bounds__(256, 1)
 wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Cout, int Cin,
                 long long Q, int base_off, int Wb, int n_tiles, float* __restrict__ dwmat) {
@@ -64,19 +69,25 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const long long k0 = (kb_lo + i) * WG_BK;
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&full[s], WG_A_BYTES + WG_B_BYTES);
-        tma_load_2d(sA + s * WG_A_BYTES, &tmA, (int)k0, m0, &full[s]);
-        tma_load_2d(sB + s * WG_B_BYTES, &tmB, (int)(k0 + off), n0, &full[s]);
+        unsigned char* a = sA + s * WG_A_BYTES;
+        unsigned char* b = sB + s * WG_B_BYTES;
+        tma_load_2d(a, &tmA, m0, (int)k0, &full[s]);
+        tma_load_2d(a + 8192, &tmA, m0 + 64, (int)k0, &full[s]);
+        tma_load_2d(b, &tmB, n0, (int)(k0 + off), &full[s]);
+        tma_load_2d(b + 8192, &tmB, n0 + 64, (int)(k0 + off), &full[s]);
       }
     } else if (warp == 1 && lane == 0) {
-      constexpr uint32_t idesc = instr_desc(FMT_BF16, WG_BM, WG_BN, 0, 0);
+      constexpr uint32_t idesc = instr_desc(FMT_BF16, WG_BM, WG_BN, 1, 1);     // both operands MN-major
       for (int i = 0; i < nkb; ++i) {
         const int s = i % WG_STAGES;
         const uint32_t ph = (i / WG_STAGES) & 1u;
         mbar_wait(&full[s], ph);
         fence_after_sync();
-        const uint64_t ad = smem_desc_k_sw128(sA + s * WG_A_BYTES), bd = smem_desc_k_sw128(sB + s * WG_B_BYTES);
+        const uint64_t ad = smem_desc_mn_sw128(sA + s * WG_A_BYTES, 8192, 1024);
+        const uint64_t bd = smem_desc_mn_sw128(sB + s * WG_B_BYTES, 8192, 1024);
 #pragma unroll
-        for (int k = 0; k < WG_BK / 16; ++k) mma_f16(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0);
+        for (int k = 0; k < WG_BK / 16; ++k)        // 16 pixel rows per MMA = 2048 B = 128 x 16 B
+          mma_f16(tmem_d, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (i | k) != 0);
         mma_commit(&empty[s]);
       }
       mma_commit(tmem_full);
@@ -186,21 +197,20 @@ __global__ void project_reg_reg_kernel(const float* __restrict__ dwmat, int Fo, 
     atomicAdd(dpsi + ((((size_t)o * Fi + i) * 4 + ((s - r) & 3)) * 3 + ys) * 3 + xs, dwmat[e]);
   }
 }
-// per-field bias gradient: dbias[c / group] += sum_q in_cm[c][q]   (one block per channel row)
-__global__ void __launch_bounds__(256) rowsum_bf16_kernel(int C, long long Q, const __nv_bfloat16* __restrict__ in, int group,
+// per-field bias gradient from an NHWC gradient buffer [Q][C]: out[c / group] += sum_q in[q][c]
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(long long Q, int C, const __nv_bfloat16* __restrict__ in, int group,
                                                         float* __restrict__ out) {
-  __shared__ float sh[8];
-  const int c = blockIdx.x;
-  const __nv_bfloat16* p = in + (size_t)c * Q;
-  float s = 0.0f;
-  for (long long q = threadIdx.x; q < Q; q += blockDim.x) s += __bfloat162float(p[q]);
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.0f;
-    for (int w = 0; w < 8; ++w) t += sh[w];
-    atomicAdd(out + c / group, t);
+  // blockDim = 256 threads = (256 / cpt) row lanes x cpt channel lanes, cpt = min(C, 256)
+  const int cpt = C < 256 ? C : 256;
+  const int rl = threadIdx.x / cpt, cl = threadIdx.x - rl * cpt, nrl = 256 / cpt;
+  const long long rows_per_block = (Q + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > Q) r1 = Q;
+  for (int c = cl; c < C; c += cpt) {
+    float s = 0.0f;
+    for (long long r = r0 + rl; r < r1; r += nrl) s += __bfloat162float(in[r * C + c]);
+    if (s != 0.0f) atomicAdd(out + c / group, s);
   }
 }
 
@@ -485,18 +495,18 @@ static unsigned grid_for(long long n, int block = 256, int cap = 148 * 16) {
 using namespace aur;
 using namespace aur::tc;
 
-extern "C" int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const void* dy_cm, const void* x_cm, int32_t base_off,
+extern "C" int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const void* dy, const void* x, int32_t base_off,
                                  int32_t Wb, float* dwmat, int32_t split_k, void* stream) {
-  if (Cout <= 0 || Cin <= 0 || Q <= 0 || !dy_cm || !x_cm || !dwmat || Q % 8 != 0) {
-    set_error("aur_wgrad3x3_bf16: bad arguments (Q must be a multiple of 8)"); return AUR_ERR_ARG;
+  if (Cout <= 0 || Cin <= 0 || Q <= 0 || !dy || !x || !dwmat || Cout % 8 != 0 || Cin % 8 != 0) {
+    set_error("aur_wgrad3x3_bf16: bad arguments (channel counts must be multiples of 8)"); return AUR_ERR_ARG;
   }
   CUtensorMap tmA, tmB;
-  const uint64_t dA[2] = {(uint64_t)Q, (uint64_t)Cout}, dB[2] = {(uint64_t)Q, (uint64_t)Cin};
-  const uint64_t st[1] = {(uint64_t)Q * 2};
-  const uint32_t bx[2] = {WG_BK, WG_BM};
+  const uint64_t dA[2] = {(uint64_t)Cout, (uint64_t)Q}, dB[2] = {(uint64_t)Cin, (uint64_t)Q};
+  const uint64_t stA[1] = {(uint64_t)Cout * 2}, stB[1] = {(uint64_t)Cin * 2};
+  const uint32_t bx[2] = {64, WG_BK};
   int rc;
-  if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dy_cm, dA, st, bx))) return rc;
-  if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x_cm, dB, st, bx))) return rc;
+  if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dy, dA, stA, bx))) return rc;
+  if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dB, stB, bx))) return rc;
   static bool attr = false;
   if (!attr) {
     AUR_CUDA_OK(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
@@ -543,10 +553,12 @@ extern "C" int aur_equiv_project_regular(const float* dwmat, int32_t Fo, int32_t
   return 0;
 }
 
-extern "C" int aur_rowsum_bf16(int32_t C, int64_t Q, const void* in_cm, int32_t group, float* out, void* stream) {
-  if (C <= 0 || Q <= 0 || !in_cm || !out || group <= 0) { set_error("aur_rowsum_bf16: bad arguments"); return AUR_ERR_ARG; }
-  rowsum_bf16_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(C, (long long)Q, (const __nv_bfloat16*)in_cm, group, out);
-  AUR_LAUNCH_OK("rowsum_bf16_kernel");
+extern "C" int aur_colsum_bf16(int64_t Q, int32_t C, const void* in, int32_t group, float* out, void* stream) {
+  if (C <= 0 || Q <= 0 || !in || !out || group <= 0 || (C < 256 && 256 % C != 0)) { set_error("aur_colsum_bf16: bad arguments"); return AUR_ERR_ARG; }
+  long long grid = (Q + 255) / 256;
+  if (grid > 148 * 4) grid = 148 * 4;
+  colsum_bf16_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((long long)Q, C, (const __nv_bfloat16*)in, group, out);
+  AUR_LAUNCH_OK("colsum_bf16_kernel");
   return 0;
 }
 

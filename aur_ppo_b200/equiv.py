@@ -166,15 +166,14 @@ class EquivActorCritic:
         B, Hb, Wb, Cin = x_buf.shape
         Cout = dy_buf.shape[3]
         Q = B * Hb * Wb
-        dy_cm, x_cm = self._t(dy_buf.reshape(Q, Cout)), self._t(x_buf.reshape(Q, Cin))
         dw = torch.zeros(Cout, 9, Cin, device=self.dev)
         with torch.cuda.device(self.dev):
-            _chk(L.aur_wgrad3x3_bf16(Cout, Cin, Q, dy_cm.data_ptr(), x_cm.data_ptr(), base_off, Wb, dw.data_ptr(), 0, _stream()),
+            _chk(L.aur_wgrad3x3_bf16(Cout, Cin, Q, dy_buf.data_ptr(), x_buf.data_ptr(), base_off, Wb, dw.data_ptr(), 0, _stream()),
                  "aur_wgrad3x3_bf16")
             _chk(L.aur_equiv_project_regular(dw.data_ptr(), Cout // 4, Cin // 4, self.grads[f"{net}.enc{l}.psi"].data_ptr(), _stream()),
                  "aur_equiv_project_regular")
-            _chk(L.aur_rowsum_bf16(Cout, Q, dy_cm.data_ptr(), 4, self.grads[f"{net}.enc{l}.bias"].data_ptr(), _stream()),
-                 "aur_rowsum_bf16")
+            _chk(L.aur_colsum_bf16(Q, Cout, dy_buf.data_ptr(), 4, self.grads[f"{net}.enc{l}.bias"].data_ptr(), _stream()),
+                 "aur_colsum_bf16")
 
     def _unpool(self, dpool, act, aoff, arg, C, Hp, dHb, doff):
         out = torch.zeros(self.B, dHb, dHb, C, dtype=torch.bfloat16, device=self.dev)
@@ -195,8 +194,8 @@ class EquivActorCritic:
         with torch.cuda.device(self.dev):
             _chk(L.aur_equiv_project_regular(dW6.data_ptr(), 128, 128, self.grads[f"{net}.enc6.psi"].data_ptr(), _stream()),
                  "aur_equiv_project_regular")
-            _chk(L.aur_rowsum_bf16(512, B, dz6_cm.data_ptr(), 4, self.grads[f"{net}.enc6.bias"].data_ptr(), _stream()),
-                 "aur_rowsum_bf16")
+            _chk(L.aur_colsum_bf16(B, 512, dz6.data_ptr(), 4, self.grads[f"{net}.enc6.bias"].data_ptr(), _stream()),
+                 "aur_colsum_bf16")
         da6 = self._cast(tc_gemm_bf16(dz6, wm6t), None).reshape(B, 3, 3, 512)
         # layer 5 (pad 0, pooled): un-pool into a 2-halo buffer (backward-data) and into the input geometry (weights)
         dy5_d = self._unpool(da6, e.a[5], 0, e.arg[5], 512, 3, 10, 2)

@@ -282,9 +282,9 @@ int aur_equiv_conv0(const float* obs, const float* state, const float* psi, cons
                     uint8_t* pool_arg, void* stream);
 
 /* weight gradient of a 3x3 layer: dwmat[co][tap][ci] (fp32, ACCUMULATED with atomics: zero it first) +=
- * sum_q dy_cm[co][q] * x_cm[ci][q + base_off + dy*Wb + dx], q the flat pixel index of the haloed buffers
- * (channel-major bf16 copies, Q % 8 == 0).  Split-K tcgen05 GEMM; split_k <= 0 picks it. */
-int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const void* dy_cm, const void* x_cm, int32_t base_off,
+ * sum_q dy[q][co] * x[q + base_off + dy*Wb + dx][ci], q the flat pixel index of the haloed NHWC bf16
+ * buffers (same geometry for both).  Split-K tcgen05 GEMM with MN-major operands; split_k <= 0 picks it. */
+int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const void* dy, const void* x, int32_t base_off,
                       int32_t Wb, float* dwmat, int32_t split_k, void* stream);
 
 /* max-pool(2) + ReLU backward: dpool [B,Hp,Wp,C] bf16, forward pooled activations `act` (buffer
@@ -298,8 +298,8 @@ int aur_transpose_bf16(int64_t R, int32_t C, const void* in, void* out, void* st
 /* adjoint of aur_equiv_expand_regular: dpsi [Fo,Fi,4,3,3] += projection of dwmat [Fo*4][9][Fi*4] */
 int aur_equiv_project_regular(const float* dwmat, int32_t Fo, int32_t Fi, float* dpsi, void* stream);
 
-/* out[c / group] += sum_q in_cm[c][q]  (bias gradients from the channel-major output gradient) */
-int aur_rowsum_bf16(int32_t C, int64_t Q, const void* in_cm, int32_t group, float* out, void* stream);
+/* out[c / group] += sum_q in[q][c]  (bias gradients from an NHWC output-gradient buffer [Q][C]) */
+int aur_colsum_bf16(int64_t Q, int32_t C, const void* in, int32_t group, float* out, void* stream);
 
 /* layer-0 weight gradient fused with its un-pooling: dpsi [16,2,3,3] +=, dbias_f [16] += */
 int aur_equiv_conv0_wgrad(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg, int32_t B,
@@ -341,6 +341,9 @@ int aur_sumsq_f32(int64_t n, const float* g, double* out_accum, void* stream);
 /* torch.optim.Adam math on a flat buffer; clip_sumsq (nullable) = device sum of squares of the clipped group */
 int aur_adam_flat(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, double lr, double beta1,
                   double beta2, double eps, int64_t step, const double* clip_sumsq, double max_grad_norm, void* stream);
+
+/* diagnostic: shared-window address of the first dynamic shared-memory byte of a kernel */
+int aur_debug_smem_base(unsigned int* out_dev, void* stream);
 
 /* Evaluates the deterministic fp64 sin/cos the env kernels use (csrc/det_sincos.h) on n
  * device doubles -- exported so tests can compare it with the host copy bit for bit. */
