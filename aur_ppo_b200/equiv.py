@@ -251,6 +251,7 @@ class EquivActorCritic:
         h.value_out, h.logp_out = self.value.data_ptr(), self.logp.data_ptr()
         with torch.cuda.device(self.dev):
             _chk(L.aur_equiv_head_loss(ctypes.byref(h), _stream()), "aur_equiv_head_loss")
+        self._last_head = (a_out, c_pre, d_a_out, d_c_h)
         # ---- head parameter gradients (contractions on tensor cores, projection = tiny torch plumbing)
         fa, fc = self.enc["actor"].feat, self.enc["critic"].feat
         dWa = tc_gemm_bf16(self._t(d_a_out), self._t(fa))                       # [16,512]

