@@ -82,6 +82,35 @@ def bench_update(args):
                           "samples_per_s": m / med, "fp32_TFLOPs": 53400 * m / med / 1e12, "gather_GBps": 40 * m / med / 1e9}))
 
 
+def bench_equiv(args):
+    """Config D: equivariant actor-critic update on synthetic close_loop_block_picking-shaped obs, minibatch 4096."""
+    from aur_ppo_b200 import equiv
+    B = int(os.environ.get("EQUIV_B", "4096"))
+    params = equiv.init_params(seed=0)
+    for k in ("actor.head.psi_triv", "actor.head.psi_irrep", "critic.head2.w"):
+        params[k].mul_(0.1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    obs = torch.rand(B, 1, 128, 128, generator=g, device="cuda") * 0.32
+    state = (torch.rand(B, generator=g, device="cuda") > 0.5).float()
+    action = torch.randn(B, 5, generator=g, device="cuda")
+    adv, ret, vold = (torch.randn(B, generator=g, device="cuda") for _ in range(3))
+    oldlp = torch.full((B,), -7.0, device="cuda")
+    model = equiv.EquivActorCritic(params, B)
+    iters = int(os.environ.get("EQUIV_ITERS", "3"))
+    def fwd():
+        model.forward(state, obs)
+    def upd():
+        model.update(state, obs, action, oldlp, adv, ret, vold)
+    med_f, _ = timeit(fwd, iters=iters, warmup=1, flush=False)
+    med_u, _ = timeit(upd, iters=iters, warmup=1, flush=False)
+    flops_fwd = 2 * 2.80e9 * B          # two encoders
+    flops_upd = 3 * flops_fwd
+    print(json.dumps({"kernel": "equiv update (2 encoders fwd+bwd+Adam)", "B": B, "ms_forward": med_f * 1e3, "ms_update": med_u * 1e3,
+                      "samples_per_s": B / med_u, "TFLOPs_forward": flops_fwd / med_f / 1e12, "TFLOPs_update": flops_upd / med_u / 1e12,
+                      "frac_of_bf16_sustained_peak": flops_upd / med_u / 1e12 / 1414.7,
+                      "mem_GB": torch.cuda.max_memory_allocated() / 1e9}))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="*", default=["gae", "rollout", "update"])
