@@ -23,7 +23,8 @@ constexpr int UPD_H = 64;
 constexpr int UPD_PSTRIDE = 4800;      // floats per CTA partial: net gradients + AUR_NUM_STATS
 constexpr int UPD_STAT_OFF = UPD_PSTRIDE - AUR_NUM_STATS;
 constexpr int UPD_SW = 4800;           // smem floats reserved for one net (padded layout)
-constexpr int UPD_SMEM_FLOATS = UPD_SW + UPD_H * UPD_H + UPD_H + 2 * UPD_H * UPD_LD + 2 * 4 * UPD_LD + 4 * UPD_H;
+constexpr int UPD_WD = 2 * UPD_H * UPD_H;   // a 64x64 matrix with every entry duplicated: [k][n][2]
+constexpr int UPD_SMEM_FLOATS = UPD_SW + 2 * UPD_WD + UPD_H + 2 * UPD_H * UPD_LD + 2 * 4 * UPD_LD + 4 * UPD_H;
 constexpr size_t UPD_SMEM = sizeof(float) * UPD_SMEM_FLOATS;
 constexpr int MOM_CTAS = 148;
 
@@ -65,6 +66,46 @@ __device__ __forceinline__ float row_quarter_sum(const float* __restrict__ buf, 
   return s;
 }
 
+// CTA-level register-tiled contraction over 64 input features for a tile of 256 samples:
+//   out[n][s] = sum_k Wd[k][n] * X[k][s]      X feature-major [64][UPD_LD], Wd = weights duplicated [k][n][2]
+// Thread (256 per CTA) = 8 samples x 8 outputs: samples s = sgh*64 + t*32 + sgl*4 + q (t<2, q<4), outputs
+// n = ngh*32 + u*8 + ngl*2 + v (u<4, v<2); lane = ngl*8 + sgl, warp = ngh*4 + sgh.  Per k: 2 LDS.128 of X
+// (8 lanes x 16 B contiguous: one wavefront each) + 4 LDS.128 of Wd (4 x 16 B contiguous) feed 32 FFMA2 whose
+// two halves are two adjacent samples, so nothing is duplicated in registers.  acc[p][o]: p = sample pair
+// (t*2 + q/2), o = u*2 + v.
+struct GemmMap {
+  int s_base, n_base;
+  __device__ __forceinline__ GemmMap(int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int sgl = lane & 7, ngl = lane >> 3, sgh = warp & 3, ngh = warp >> 2;
+    s_base = sgh * 64 + sgl * 4;          // + t*32 + q
+    n_base = ngh * 32 + ngl * 2;          // + u*8 + v
+  }
+};
+__device__ __forceinline__ void cta_gemm64(const float* __restrict__ X, const float* __restrict__ Wd, const GemmMap& gm,
+                                           float2 (&acc)[4][8]) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[p][o] = make_float2(0.f, 0.f);
+  const float* xp = X + gm.s_base;
+  const float* wp = Wd + 2 * gm.n_base;
+#pragma unroll 4
+  for (int k = 0; k < UPD_H; ++k) {
+    const float4 x0 = lds4(xp + k * UPD_LD), x1 = lds4(xp + k * UPD_LD + 32);
+    const float2 xs[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y), make_float2(x1.z, x1.w)};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 w = lds4(wp + k * (2 * UPD_H) + u * 16);     // (w_n, w_n, w_n+1, w_n+1)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        acc[p][2 * u] = __ffma2_rn(make_float2(w.x, w.y), xs[p], acc[p][2 * u]);
+        acc[p][2 * u + 1] = __ffma2_rn(make_float2(w.z, w.w), xs[p], acc[p][2 * u + 1]);
+      }
+    }
+  }
+}
+
 // KIND: 0 actor (Categorical), 1 actor (Normal), 2 critic.
 template <int KIND>
 __device__ void update_net(const UpdDev& a, float* smem) {
@@ -73,8 +114,9 @@ __device__ void update_net(const UpdDev& a, float* smem) {
   const int OUT = ACTOR ? a.act_dim : 1;
   const int obs_dim = a.obs_dim;
   float* sW = smem;
-  float* sW2T = sW + UPD_SW;
-  float* sZero = sW2T + UPD_H * UPD_H;
+  float* sW2d = sW + UPD_SW;             // W2 duplicated, [i][j][2]   (forward:  z2[j] = sum_i W2[j][i] h1[i])
+  float* sW2Td = sW2d + UPD_WD;          // W2^T duplicated, [j][i][2] (backward: dh1[i] = sum_j W2[j][i] dz2[j])
+  float* sZero = sW2Td + UPD_WD;
   float* Hs = sZero + UPD_H;
   float* B2 = Hs + UPD_H * UPD_LD;
   float* sX = B2 + UPD_H * UPD_LD;
@@ -93,9 +135,11 @@ __device__ void update_net(const UpdDev& a, float* smem) {
   const float* sB3 = sW3 + OUT * UPD_H;
   {
     const float* gW2 = gnet + UPD_H * obs_dim + UPD_H;
-    for (int i = tid; i < UPD_H * UPD_H; i += UPD_THREADS) {
-      const int j = i >> 6, c = i & 63;          // W2[j][c] -> W2T[c][j]
-      sW2T[c * UPD_H + j] = gW2[i];
+    for (int e = tid; e < UPD_H * UPD_H; e += UPD_THREADS) {
+      const int j = e >> 6, i = e & 63;          // W2[j][i]
+      const float w = gW2[e];
+      *reinterpret_cast<float2*>(sW2d + (i * UPD_H + j) * 2) = make_float2(w, w);
+      *reinterpret_cast<float2*>(sW2Td + (j * UPD_H + i) * 2) = make_float2(w, w);
     }
     if (tid < UPD_H) sZero[tid] = 0.0f;
   }
@@ -123,6 +167,7 @@ __device__ void update_net(const UpdDev& a, float* smem) {
   float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f, st4 = 0.f;   // loss, entropy, -logr, r-1-logr, clipped
 
   const int tj = tid >> 4, ti = tid & 15;
+  const GemmMap gm(tid);
   const long long ntiles = (a.m_local + UPD_S - 1) / UPD_S;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // ================= P1: gather, forward, loss =================
@@ -135,37 +180,45 @@ __device__ void update_net(const UpdDev& a, float* smem) {
       x[0][c] = (valid && c < obs_dim) ? __ldg(a.obs + row * obs_dim + c) : 0.0f;
       sX[c * UPD_LD + tid] = x[0][c];
     }
-    float2 h1[1][UPD_H / 2];
-    mlp_first_layer<UPD_H, 1>(sW0, sB0, x, h1);
+    {
+      float2 h1[1][UPD_H / 2];
+      mlp_first_layer<UPD_H, 1>(sW0, sB0, x, h1);
 #pragma unroll
-    for (int jp = 0; jp < UPD_H / 2; ++jp) {
-      Hs[(2 * jp) * UPD_LD + tid] = h1[0][jp].x;
-      Hs[(2 * jp + 1) * UPD_LD + tid] = h1[0][jp].y;
+      for (int jp = 0; jp < UPD_H / 2; ++jp) {
+        Hs[(2 * jp) * UPD_LD + tid] = h1[0][jp].x;
+        Hs[(2 * jp + 1) * UPD_LD + tid] = h1[0][jp].y;
+      }
     }
+    __syncthreads();
+    // ---- hidden layer 2 for the whole tile: h2 = tanh(W2 h1 + b2), CTA-level GEMM -> B2 (feature-major)
+    {
+      float2 acc[4][8];
+      cta_gemm64(Hs, sW2d, gm, acc);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int n = gm.n_base + u * 8 + v;
+          const float b = sB2[n];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const float2 a0 = acc[2 * t][2 * u + v], a1 = acc[2 * t + 1][2 * u + v];
+            *reinterpret_cast<float4*>(B2 + n * UPD_LD + gm.s_base + t * 32) =
+                make_float4(tanh_fast(a0.x + b), tanh_fast(a0.y + b), tanh_fast(a1.x + b), tanh_fast(a1.y + b));
+          }
+        }
+    }
+    __syncthreads();
+    // ---- head (thread per sample): out = W3 h2 + b3
     float2 o2[POL_OUT_MAX];
 #pragma unroll
     for (int k = 0; k < POL_OUT_MAX; ++k) o2[k] = make_float2(0.f, 0.f);
-#pragma unroll 1
-    for (int j0 = 0; j0 < UPD_H; j0 += 8) {
-      float z[1][8];
-      mlp_hidden_block<UPD_H, 1>(sW2, sB2, j0, h1, z);
-      float2 t[4];
+#pragma unroll 4
+    for (int j = 0; j < UPD_H; j += 2) {
+      const float2 t = make_float2(B2[j * UPD_LD + tid], B2[(j + 1) * UPD_LD + tid]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        t[q] = make_float2(tanh_fast(z[0][2 * q]), tanh_fast(z[0][2 * q + 1]));
-        B2[(j0 + 2 * q) * UPD_LD + tid] = t[q].x;
-        B2[(j0 + 2 * q + 1) * UPD_LD + tid] = t[q].y;
-      }
-#pragma unroll
-      for (int k = 0; k < POL_OUT_MAX; ++k) {
-        if (k < OUT) {
-          const float4 wa = lds4(sW3 + k * UPD_H + j0), wb = lds4(sW3 + k * UPD_H + j0 + 4);
-          float2 s = __ffma2_rn(make_float2(wa.x, wa.y), t[0], o2[k]);
-          s = __ffma2_rn(make_float2(wa.z, wa.w), t[1], s);
-          s = __ffma2_rn(make_float2(wb.x, wb.y), t[2], s);
-          o2[k] = __ffma2_rn(make_float2(wb.z, wb.w), t[3], s);
-        }
-      }
+      for (int k = 0; k < POL_OUT_MAX; ++k)
+        if (k < OUT) o2[k] = __ffma2_rn(lds2(sW3 + k * UPD_H + j), t, o2[k]);
     }
     float out[POL_OUT_MAX], dout[POL_OUT_MAX];
 #pragma unroll
@@ -307,27 +360,34 @@ __device__ void update_net(const UpdDev& a, float* smem) {
     }
     acc_b2 += row_quarter_sum(B2, tid);
 
-    // ================= P3: dz1 = (W2^T dz2) * (1 - h1^2) =================
-    float dz1[UPD_H];
+    // ================= P3: dz1 = (W2^T dz2) * (1 - h1^2), CTA-level GEMM =================
     {
-      float2 dz[1][UPD_H / 2];
+      float2 acc[4][8];
+      cta_gemm64(B2, sW2Td, gm, acc);
+      float4 dzv[8][2];
 #pragma unroll
-      for (int jp = 0; jp < UPD_H / 2; ++jp)
-        dz[0][jp] = make_float2(B2[(2 * jp) * UPD_LD + tid], B2[(2 * jp + 1) * UPD_LD + tid]);
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int i0 = 0; i0 < UPD_H; i0 += 8) {
-        float z[1][8];
-        mlp_hidden_block<UPD_H, 1>(sW2T, sZero, i0, dz, z);
+        for (int v = 0; v < 2; ++v) {
+          const int n = gm.n_base + u * 8 + v;
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const float hv = Hs[(i0 + jj) * UPD_LD + tid];
-          dz1[i0 + jj] = z[0][jj] * fmaf(-hv, hv, 1.0f);
+          for (int t = 0; t < 2; ++t) {
+            const float4 hv = lds4(Hs + n * UPD_LD + gm.s_base + t * 32);
+            const float2 a0 = acc[2 * t][2 * u + v], a1 = acc[2 * t + 1][2 * u + v];
+            dzv[2 * u + v][t] = make_float4(a0.x * fmaf(-hv.x, hv.x, 1.0f), a0.y * fmaf(-hv.y, hv.y, 1.0f),
+                                            a1.x * fmaf(-hv.z, hv.z, 1.0f), a1.y * fmaf(-hv.w, hv.w, 1.0f));
+          }
         }
-      }
-    }
-    __syncthreads();            // every thread is done reading h1 (G2, P3)
+      __syncthreads();            // every thread is done reading h1 (G2, P3)
 #pragma unroll
-    for (int i = 0; i < UPD_H; ++i) Hs[i * UPD_LD + tid] = dz1[i];
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int n = gm.n_base + u * 8 + v;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) *reinterpret_cast<float4*>(Hs + n * UPD_LD + gm.s_base + t * 32) = dzv[2 * u + v][t];
+        }
+    }
     __syncthreads();
 
     // ================= G3: dW1 += dz1^T x, db1 =================
