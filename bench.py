@@ -332,6 +332,78 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_equiv(args):
+    """BASELINE configs[3]: equivariant actor-critic update on synthetic close_loop_block_picking-shaped
+    observations (1x128x128 heightmap + gripper state), minibatch 4096.  One step = one full update
+    (two encoders forward + loss + backward + clip + Adam)."""
+    import torch
+    from aur_ppo_b200 import _lib, equiv
+    B = 4096
+    torch.cuda.set_device(0)
+    params = equiv.init_params(seed=0)
+    for k in ("actor.head.psi_triv", "actor.head.psi_irrep", "critic.head2.w"):
+        params[k].mul_(0.1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    obs = torch.rand(B, 1, 128, 128, generator=g, device="cuda") * 0.32
+    state = (torch.rand(B, generator=g, device="cuda") > 0.5).float()
+    action = torch.randn(B, 5, generator=g, device="cuda")
+    adv, ret, vold = (torch.randn(B, generator=g, device="cuda") for _ in range(3))
+    oldlp = torch.full((B,), -7.0, device="cuda")
+    model = equiv.EquivActorCritic(params, B)
+    for _ in range(args.warmup):
+        model.update(state, obs, action, oldlp, adv, ret, vold)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    L = _lib.lib()
+    L.aur_launch_count_reset()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        model.update(state, obs, action, oldlp, adv, ret, vold)
+    t1.record()
+    torch.cuda.synchronize()
+    launches = int(L.aur_launch_count())
+    clocks = sampler.finish()
+    ms = t0.elapsed_time(t1) / args.steps
+    # e2e: observations, states, actions and targets uploaded from pinned host memory every step, stats read back
+    host = [t.cpu().pin_memory() for t in (obs, state, action, oldlp, adv, ret, vold)]
+    dev = [torch.empty_like(t) for t in (obs, state, action, oldlp, adv, ret, vold)]
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        for d, h in zip(dev, host):
+            d.copy_(h, non_blocking=True)
+        st = model.update(dev[1], dev[0], dev[2], dev[3], dev[4], dev[5], dev[6])
+        st_host = st.cpu()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / args.steps
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    flops = 3 * 2 * 2.80e9 * B
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    tf = flops / (ms * 1e-3) / 1e12
+    line = {"metric": "update_samples_per_s", "value": B / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 operands / fp32 accumulate (tcgen05), fp32 parameters and Adam", "data": "synthetic",
+            "config": {"workload": "equivariant actor-critic update, minibatch 4096, obs 1x128x128 + gripper state "
+                                   "(BASELINE configs[3])", "l2": "activations 25 GB per step >> L2"},
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+                         "kernel": "conv_igemm_kernel + wgrad3x3_kernel (whole update, 68.8 TFLOP algorithmic)",
+                         "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "fallback"},
+            "cpu_baseline": None,
+            "e2e": {"value": B / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": launches, "clocks": clocks}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -339,11 +411,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "equiv"],
+                    help="ppo = BASELINE configs[1] (default, the headline line); equiv = configs[3]")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "equiv":
+        run_equiv(args)
     else:
         run_ours(args)
 
