@@ -197,21 +197,37 @@ __global__ void project_reg_reg_kernel(const float* __restrict__ dwmat, int Fo, 
     atomicAdd(dpsi + ((((size_t)o * Fi + i) * 4 + ((s - r) & 3)) * 3 + ys) * 3 + xs, dwmat[e]);
   }
 }
-// per-field bias gradient from an NHWC gradient buffer [Q][C]: out[c / group] += sum_q in[q][c]
+// per-field bias gradient from an NHWC gradient buffer [Q][C]: out[c / group] += sum_q in[q][c].
+// HBM-bound column reduction: a thread owns 8 adjacent channels (one 16-B load per row), the CTA's 256 threads
+// are (C/8) channel lanes x row lanes, rows are strided over the whole grid; partial sums meet in shared memory
+// before one atomicAdd per channel and CTA.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(long long Q, int C, const __nv_bfloat16* __restrict__ in, int group,
                                                         float* __restrict__ out) {
-  // blockDim = 256 threads = (256 / cpt) row lanes x cpt channel lanes, cpt = min(C, 256)
-  const int cpt = C < 256 ? C : 256;
-  const int rl = threadIdx.x / cpt, cl = threadIdx.x - rl * cpt, nrl = 256 / cpt;
-  const long long rows_per_block = (Q + gridDim.x - 1) / gridDim.x;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  long long r1 = r0 + rows_per_block;
-  if (r1 > Q) r1 = Q;
-  for (int c = cl; c < C; c += cpt) {
-    float s = 0.0f;
-    for (long long r = r0 + rl; r < r1; r += nrl) s += __bfloat162float(in[r * C + c]);
-    if (s != 0.0f) atomicAdd(out + c / group, s);
+  __shared__ float sacc[1024];
+  const int c8n = C >> 3;                              // 8-channel groups per row (<= 128)
+  const int rl_n = 256 / c8n;                          // row lanes per CTA
+  const int cl = threadIdx.x % c8n, rl = threadIdx.x / c8n;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < rl_n) {
+    for (long long r = (long long)blockIdx.x * rl_n + rl; r < Q; r += (long long)gridDim.x * rl_n) {
+      const uint4 v = *reinterpret_cast<const uint4*>(in + r * C + cl * 8);
+      const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += __uint_as_float(w[j] << 16);
+        acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+      }
+    }
   }
+  for (int i = threadIdx.x; i < C; i += 256) sacc[i] = 0.0f;
+  __syncthreads();
+  if (rl < rl_n) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sacc[cl * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256)
+    if (sacc[i] != 0.0f) atomicAdd(out + i / group, sacc[i]);
 }
 
 // ---- layer-0 weight gradient fused with its un-pooling ---------------------------------------------
@@ -554,9 +570,10 @@ extern "C" int aur_equiv_project_regular(const float* dwmat, int32_t Fo, int32_t
 }
 
 extern "C" int aur_colsum_bf16(int64_t Q, int32_t C, const void* in, int32_t group, float* out, void* stream) {
-  if (C <= 0 || Q <= 0 || !in || !out || group <= 0 || (C < 256 && 256 % C != 0)) { set_error("aur_colsum_bf16: bad arguments"); return AUR_ERR_ARG; }
-  long long grid = (Q + 255) / 256;
-  if (grid > 148 * 4) grid = 148 * 4;
+  if (C <= 0 || C > 1024 || C % 8 != 0 || Q <= 0 || !in || !out || group <= 0) { set_error("aur_colsum_bf16: bad arguments (C % 8 == 0, C <= 1024)"); return AUR_ERR_ARG; }
+  const int rl_n = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
+  long long grid = (Q + rl_n - 1) / rl_n;
+  if (grid > 148 * 8) grid = 148 * 8;
   colsum_bf16_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((long long)Q, C, (const __nv_bfloat16*)in, group, out);
   AUR_LAUNCH_OK("colsum_bf16_kernel");
   return 0;

@@ -12,17 +12,14 @@
 //
 // Arithmetic: fp32, one rounding per reference operation, explicit __fmul_rn/__fadd_rn so
 // nvcc cannot contract: bit-identical to the reference's torch CPU loop.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace aur {
 
-constexpr int GAE_W = 128;      // columns per tile (512 B rows)
-constexpr int GAE_TT = 8;       // rows per stage
-constexpr int GAE_STAGES = 4;   // ring depth
-constexpr int GAE_CONSUMER_WARPS = GAE_W / 32;
-constexpr int GAE_THREADS = GAE_W + 32;   // consumers + one producer warp
-constexpr int GAE_STAGE_FLOATS = 3 * GAE_TT * GAE_W;
-constexpr size_t GAE_SMEM = sizeof(float) * GAE_STAGES * GAE_STAGE_FLOATS + 2 * GAE_STAGES * sizeof(uint64_t);
+// Tile shape: GAE_W columns per tile, GAE_TT rows per stage, GAE_STAGES ring depth (template parameters;
+// the default is picked in aur_gae_f32, AUR_GAE_VARIANT overrides it for tuning sweeps).
 
 struct GaeStep {
   float g32, gl32;
@@ -51,11 +48,14 @@ struct GaeStep {
   }
 };
 
-__global__ void __launch_bounds__(GAE_THREADS)
+template <int GAE_W, int GAE_TT, int GAE_STAGES>
+__global__ void __launch_bounds__(GAE_W + 32)
 gae_bulk_kernel(int T, long long N, const float* __restrict__ rew, const float* __restrict__ val,
                 const float* __restrict__ term, const float* __restrict__ next_value,
                 const float* __restrict__ next_done, float g32, float gl32, int use_gae,
                 float* __restrict__ adv_out, float* __restrict__ ret_out) {
+  constexpr int GAE_CONSUMER_WARPS = GAE_W / 32;
+  constexpr int GAE_STAGE_FLOATS = 3 * GAE_TT * GAE_W;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ring = reinterpret_cast<float*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + sizeof(float) * GAE_STAGES * GAE_STAGE_FLOATS);
@@ -188,6 +188,29 @@ gae_column_kernel(int T, long long N, const float* __restrict__ rew, const float
   }
 }
 
+template <int W, int TT, int STAGES>
+static int launch_gae_bulk(int32_t T, int64_t N, const float* rewards, const float* values, const float* terminals,
+                           const float* next_value, const float* next_done, float g32, float gl32, int use_gae,
+                           float* adv_out, float* ret_out, cudaStream_t st) {
+  constexpr size_t smem = sizeof(float) * STAGES * 3 * TT * W + 2 * STAGES * sizeof(uint64_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AUR_CUDA_OK(cudaFuncSetAttribute(gae_bulk_kernel<W, TT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const long long ntiles = (N + W - 1) / W;
+  int per_sm = (int)(220 * 1024 / (smem + 1024));
+  const int by_threads = 2048 / (W + 32);
+  if (per_sm > by_threads) per_sm = by_threads;
+  if (per_sm < 1) per_sm = 1;
+  const long long cap = (long long)sm_count() * per_sm;
+  const long long grid = ntiles < cap ? ntiles : cap;
+  gae_bulk_kernel<W, TT, STAGES><<<(unsigned)grid, W + 32, smem, st>>>(T, (long long)N, rewards, values, terminals, next_value,
+                                                                     next_done, g32, gl32, use_gae, adv_out, ret_out);
+  AUR_LAUNCH_OK("gae_bulk_kernel");
+  return 0;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int gae_kind(int32_t T, int64_t N, const float* rew, const float* val, const float* term,
@@ -216,18 +239,22 @@ extern "C" int aur_gae_f32(int32_t T, int64_t N, const float* rewards, const flo
   const float g32 = (float)gamma;                 // torch: tensor * python-float -> scalar cast to fp32
   const float gl32 = (float)(gamma * gae_lambda); // python computes gamma*gae_lambda in double first
   if (gae_kind(T, N, rewards, values, terminals, adv_out, ret_out)) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      AUR_CUDA_OK(cudaFuncSetAttribute(gae_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GAE_SMEM));
-      attr_set = true;
+    static int variant = -1;
+    if (variant < 0) {
+      const char* e = getenv("AUR_GAE_VARIANT");
+      variant = e ? atoi(e) : 0;
     }
-    const long long ntiles = (N + GAE_W - 1) / GAE_W;
-    const int per_sm = 4;   // 4 x 49 KB of ring per SM
-    const long long grid = ntiles < (long long)sm_count() * per_sm ? ntiles : (long long)sm_count() * per_sm;
-    gae_bulk_kernel<<<(unsigned)grid, GAE_THREADS, GAE_SMEM, st>>>(T, (long long)N, rewards, values, terminals,
-                                                                   next_value, next_done, g32, gl32, use_gae,
-                                                                   adv_out, ret_out);
-    AUR_LAUNCH_OK("gae_bulk_kernel");
+    int rc = 0;
+    switch (variant) {
+      case 1: rc = launch_gae_bulk<64, 8, 4>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
+      case 2: rc = launch_gae_bulk<64, 16, 3>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
+      case 3: rc = launch_gae_bulk<128, 16, 3>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
+      case 4: rc = launch_gae_bulk<128, 4, 6>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
+      case 5: rc = launch_gae_bulk<64, 4, 8>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
+      case 6: rc = launch_gae_bulk<256, 4, 4>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
+      default: rc = launch_gae_bulk<128, 8, 4>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
+    }
+    if (rc) return rc;
   } else {
     const unsigned grid = (unsigned)((N + 127) / 128);
     gae_column_kernel<<<grid, 128, 0, st>>>(T, (long long)N, rewards, values, terminals, next_value, next_done, g32,
