@@ -242,17 +242,17 @@ extern "C" int aur_gae_f32(int32_t T, int64_t N, const float* rewards, const flo
     static int variant = -1;
     if (variant < 0) {
       const char* e = getenv("AUR_GAE_VARIANT");
-      variant = e ? atoi(e) : 0;
+      variant = e ? atoi(e) : 1;    // <64,8,4>: best of the round-1 sweep (tools/sweep_gae.sh) at [128,65536]..[2048,131072]
     }
     int rc = 0;
     switch (variant) {
-      case 1: rc = launch_gae_bulk<64, 8, 4>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
+      case 7: rc = launch_gae_bulk<128, 8, 4>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
       case 2: rc = launch_gae_bulk<64, 16, 3>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
       case 3: rc = launch_gae_bulk<128, 16, 3>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
       case 4: rc = launch_gae_bulk<128, 4, 6>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
       case 5: rc = launch_gae_bulk<64, 4, 8>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
       case 6: rc = launch_gae_bulk<256, 4, 4>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
-      default: rc = launch_gae_bulk<128, 8, 4>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
+      default: rc = launch_gae_bulk<64, 8, 4>(T, N, rewards, values, terminals, next_value, next_done, g32, gl32, use_gae, adv_out, ret_out, st); break;
     }
     if (rc) return rc;
   } else {

@@ -12,32 +12,11 @@
 // (dW3 = dout^T h2, dW2 = dz2^T h1, dW1 = dz1^T x) are CTA-level register-tiled GEMMs over
 // activations staged feature-major in shared memory, their accumulators living in registers for
 // the whole kernel.  This path is fp32-FMA bound (~50 kFLOP per sample vs 40 B gathered).
-#include "policy.cuh"
+#include <stdlib.h>
+
+#include "update.cuh"
 
 namespace aur {
-
-constexpr int UPD_THREADS = 256;
-constexpr int UPD_S = 256;             // samples per tile (one per thread in the per-sample phases)
-constexpr int UPD_LD = UPD_S + 4;      // feature-major row stride: 16-B aligned, 4 banks per row
-constexpr int UPD_H = 64;
-constexpr int UPD_PSTRIDE = 4800;      // floats per CTA partial: net gradients + AUR_NUM_STATS
-constexpr int UPD_STAT_OFF = UPD_PSTRIDE - AUR_NUM_STATS;
-constexpr int UPD_SW = 4800;           // smem floats reserved for one net (padded layout)
-constexpr int UPD_WD = 2 * UPD_H * UPD_H;   // a 64x64 matrix with every entry duplicated: [k][n][2]
-constexpr int UPD_SMEM_FLOATS = UPD_SW + 2 * UPD_WD + UPD_H + 2 * UPD_H * UPD_LD + 2 * 4 * UPD_LD + 4 * UPD_H;
-constexpr size_t UPD_SMEM = sizeof(float) * UPD_SMEM_FLOATS;
-constexpr int MOM_CTAS = 148;
-
-struct UpdDev {
-  long long m_local;
-  const int32_t* idx;
-  long long idx_offset;
-  const float *obs, *actions, *logprobs, *advantages, *returns, *values, *params;
-  int obs_dim, act_dim, continuous, norm_adv, clip_vloss;
-  float clip, clip_lo, clip_hi, ent_c, vf_c, inv_m;
-  const double* moments;
-  float* partials;      // [2][gridDim.x][UPD_PSTRIDE]
-};
 
 __device__ __forceinline__ float block_sum_256(float v, float* sred) {
   v = warp_sum(v);
@@ -557,12 +536,15 @@ __global__ void __launch_bounds__(1024) adam_kernel(int64_t P, float* __restrict
   }
 }
 
+#ifndef AUR_UPDATE_DEFAULT_TC
+#define AUR_UPDATE_DEFAULT_TC 0
+#endif
 static int upd_grid_x() {
   int g = sm_count() / 2;
   return g < 1 ? 1 : g;
 }
 // workspace: [2][grid_x][PSTRIDE] partials | moments partials (fp64) | ticket
-static size_t ws_partials_floats() { return (size_t)2 * upd_grid_x() * UPD_PSTRIDE; }
+static size_t ws_partials_floats() { return (size_t)2 * sm_count() * UPD_PSTRIDE; }
 static size_t ws_bytes() { return ws_partials_floats() * sizeof(float) + (2 * MOM_CTAS) * sizeof(double) + 64; }
 
 static int check_update_policy(const aur_policy_desc& p, const char* who) {
@@ -624,9 +606,21 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
     attr_set = true;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const int gx = upd_grid_x();
-  ppo_grad_kernel<<<dim3(gx, 2), UPD_THREADS, UPD_SMEM, s>>>(d);
-  AUR_LAUNCH_OK("ppo_grad_kernel");
+  static int impl = -1;        // 0 = SIMT fp32 (ppo_grad_kernel), 1 = tcgen05 bf16x2-split (ppo_grad_tc_kernel)
+  if (impl < 0) {
+    const char* e = getenv("AUR_UPDATE_IMPL");
+    impl = e ? (e[0] == 't' || e[0] == '1') : AUR_UPDATE_DEFAULT_TC;
+  }
+  int gx;
+  if (impl == 1) {
+    gx = sm_count();
+    int rc2 = launch_ppo_grad_tc(d, gx, s);
+    if (rc2) return rc2;
+  } else {
+    gx = upd_grid_x();
+    ppo_grad_kernel<<<dim3(gx, 2), UPD_THREADS, UPD_SMEM, s>>>(d);
+    AUR_LAUNCH_OK("ppo_grad_kernel");
+  }
   const int64_t P = policy_param_count(u.policy);
   const int total = (int)(P + AUR_NUM_STATS);
   grad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(u.workspace, gx, u.policy.obs_dim, u.policy.act_dim,
