@@ -137,10 +137,7 @@ __global__ void __launch_bounds__(TCU_THREADS, 1) ppo_grad_tc_kernel(UpdDev a) {
     if (tid < 64) {                                   // W2 row j = tid -> hi / mid swizzled rows
       float row[64];
 #pragma unroll
-      for (int i = 0; i < 64; i += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(gW2 + tid * 64 + i);
-        row[i] = v.x; row[i + 1] = v.y; row[i + 2] = v.z; row[i + 3] = v.w;
-      }
+      for (int i = 0; i < 64; ++i) row[i] = gW2[tid * 64 + i];      // the critic's block is only 4-byte aligned
       store_split_row(P.w2(net, 0), P.w2(net, 1), tid, row);
     }
   }
