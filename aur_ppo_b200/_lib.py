@@ -122,6 +122,9 @@ def lib() -> ctypes.CDLL:
     L.aur_ppo_adv_moments.argtypes = [c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     L.aur_ppo_update_grad.restype = c_int
     L.aur_ppo_update_grad.argtypes = [ctypes.POINTER(UpdateArgs), c_void_p]
+    L.aur_ppo_update_set_impl.restype = c_int
+    L.aur_ppo_update_set_impl.argtypes = [c_int]
+    L.aur_ppo_update_get_impl.restype = c_int
     L.aur_ppo_update_apply.restype = c_int
     L.aur_ppo_update_apply.argtypes = [ctypes.POINTER(PolicyDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                        c_double, c_double, c_double, c_int64, c_double, c_int64, c_double, c_double,

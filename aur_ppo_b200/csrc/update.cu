@@ -536,9 +536,16 @@ __global__ void __launch_bounds__(1024) adam_kernel(int64_t P, float* __restrict
   }
 }
 
-#ifndef AUR_UPDATE_DEFAULT_TC
-#define AUR_UPDATE_DEFAULT_TC 0
-#endif
+// 0 = SIMT fp32 (ppo_grad_kernel, kept as an independent cross-check), 1 = tcgen05 bf16x2-split
+// (ppo_grad_tc_kernel, the default).  AUR_UPDATE_IMPL=simt|tc or aur_ppo_update_set_impl() select it.
+static int g_update_impl = -1;
+static int update_impl() {
+  if (g_update_impl < 0) {
+    const char* e = getenv("AUR_UPDATE_IMPL");
+    g_update_impl = e ? ((e[0] == 's' || e[0] == '0') ? 0 : 1) : 1;
+  }
+  return g_update_impl;
+}
 static int upd_grid_x() {
   int g = sm_count() / 2;
   return g < 1 ? 1 : g;
@@ -580,6 +587,13 @@ extern "C" int aur_ppo_adv_moments(int64_t m, const int32_t* idx, int64_t idx_of
   return 0;
 }
 
+extern "C" int aur_ppo_update_set_impl(int impl) {
+  if (impl != 0 && impl != 1) { aur::set_error("aur_ppo_update_set_impl: impl must be 0 (simt) or 1 (tensor core)"); return AUR_ERR_ARG; }
+  aur::g_update_impl = impl;
+  return 0;
+}
+extern "C" int aur_ppo_update_get_impl(void) { return aur::update_impl(); }
+
 extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
   using namespace aur;
   if (!args) { set_error("aur_ppo_update_grad: null args"); return AUR_ERR_ARG; }
@@ -606,11 +620,7 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
     attr_set = true;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  static int impl = -1;        // 0 = SIMT fp32 (ppo_grad_kernel), 1 = tcgen05 bf16x2-split (ppo_grad_tc_kernel)
-  if (impl < 0) {
-    const char* e = getenv("AUR_UPDATE_IMPL");
-    impl = e ? (e[0] == 't' || e[0] == '1') : AUR_UPDATE_DEFAULT_TC;
-  }
+  const int impl = update_impl();
   int gx;
   if (impl == 1) {
     gx = sm_count();

@@ -233,6 +233,12 @@ int aur_ppo_adv_moments(int64_t m, const int32_t* idx, int64_t idx_offset, const
 
 int aur_ppo_update_grad(const aur_update_args* args, void* stream);
 
+/* Kernel behind aur_ppo_update_grad: 1 = tcgen05 (bf16 two-term split operands, fp32 TMEM accumulators; the
+ * default), 0 = SIMT fp32 (independent implementation kept as a cross-check).  Both are CUDA; there is no
+ * CPU path.  The environment variable AUR_UPDATE_IMPL=simt|tc sets the initial choice. */
+int aur_ppo_update_set_impl(int impl);
+int aur_ppo_update_get_impl(void);
+
 /* params / adam_m / adam_v: [P] fp32 updated in place (torch.optim.Adam single-tensor math, no
  * weight decay, no amsgrad).  step is the 1-based Adam step count.  stats_out [AUR_NUM_STATS]
  * (nullable) receives the minibatch means; entropy_coeff/value_coeff only enter stats_out[LOSS]. */

@@ -13,6 +13,18 @@ from tests.helpers import flat_from_named, random_policy
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["tc", "simt"])
+def update_impl(request):
+    """Every test runs against both CUDA implementations of aur_ppo_update_grad: the tcgen05 kernel (default)
+    and the independent SIMT fp32 kernel."""
+    from aur_ppo_b200 import _lib
+    L = _lib.lib()
+    prev = L.aur_ppo_update_get_impl()
+    assert L.aur_ppo_update_set_impl(1 if request.param == "tc" else 0) == 0
+    yield request.param
+    L.aur_ppo_update_set_impl(prev)
+
+
 def _flat_grads(names, grads):
     return flat_from_named({n: g for n, g in zip(names, grads)})
 
