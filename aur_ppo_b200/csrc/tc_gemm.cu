@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256, 1)
 tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
                     int M, int N, int K, int ldc) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   unsigned char* sA = smem;
   unsigned char* sB = smem + GEMM_STAGES * GEMM_A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + GEMM_STAGES * GEMM_B_BYTES);

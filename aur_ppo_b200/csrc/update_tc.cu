@@ -632,7 +632,7 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
 
 __global__ void __launch_bounds__(T2_THREADS, 2) ppo_grad_tc_kernel(UpdDev a) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   const int ncta = gridDim.x >> 1;                     // CTAs per net; blockIdx < ncta: actor, else critic
   if ((int)blockIdx.x < ncta) tc_update_net<true>(a, base, blockIdx.x, ncta);
   else tc_update_net<false>(a, base, blockIdx.x - ncta, ncta);
