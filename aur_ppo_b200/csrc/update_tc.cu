@@ -20,12 +20,13 @@
 // (forward / backward-data) and as MN-major A/B operands of the contractions over samples, whose accumulators
 // (dW2 64x64, [db2], [db1 | dW1]) live in TMEM for the whole kernel.  The bias and first-layer gradients use a
 // 16-column K-major "aux" tile [1, x0..x3].  Only dW3 / db3 (out_dim <= 4 columns) stay SIMT, staged through
-// shared memory in two 32-feature rounds.
+// shared memory warp by warp.
 //
 // Pipeline per tile t (two elected threads issue the MMA batches, mbarriers track them):
 //   wait bwd/wgrad(t-1) | store dz1(t-1), h1(t) (+ fp32 copy in TMEM), aux(t) | issue fwd(t), aux_w1(t-1)
+//   (h1(t) itself was computed at the end of iteration t-1, ahead of that wait)
 //   gather(t+1) and index(t+2) loads | wait fwd(t) | h2, head, loss | wait aux_w1(t-1) | store dz2(t)
-//   issue bwd(t), wgrad(t), aux_b2(t) | dW3 rounds (overlap the MMAs)
+//   issue bwd(t), wgrad(t), aux_b2(t) | warp-local dW3 passes (overlap the MMAs)
 #include "tc.cuh"
 #include "update.cuh"
 
@@ -103,16 +104,17 @@ __device__ __forceinline__ void mma_split(uint32_t d, uint64_t a_hi, uint64_t a_
   for (int k = 0; k < ksteps; ++k) tc::mma_f16(d, a_hi + (uint64_t)(a_step * k), b_mid + (uint64_t)(b_step * k), idesc, 1u);
   for (int k = 0; k < ksteps; ++k) tc::mma_f16(d, a_mid + (uint64_t)(a_step * k), b_hi + (uint64_t)(b_step * k), idesc, 1u);
 }
-// D[128][16] (+)= A^T (MN-major, K = 128 samples) x aux (K-major, two 64-sample blocks of 1 KB)
-__device__ __forceinline__ void mma_aux(uint32_t d, uint64_t a_hi, uint64_t a_mid, uint64_t b_hi, uint64_t b_mid, uint32_t idesc,
-                                        bool accumulate) {
-#pragma unroll 1
-  for (int p = 0; p < 3; ++p) {
-    const uint64_t ad = p == 2 ? a_mid : a_hi, bd = p == 1 ? b_mid : b_hi;
-    for (int k = 0; k < 8; ++k)
-      tc::mma_f16(d, ad + (uint64_t)(128 * k), bd + (uint64_t)((k & 3) * 2 + (k >> 2) * 64), idesc,
-                  (accumulate || p > 0 || k > 0) ? 1u : 0u);
-  }
+// Contractions over the 128 samples of a tile (K = 8 steps of 16 rows) with only 64 output rows (features): the A
+// descriptor's second 64-row atom is the MID tile (LBO = one tile), so one M = 128 MMA yields hi^T B in accumulator
+// rows 0..63 and mid^T B in rows 64..127; two passes (B_hi, B_mid) give all four split products and the epilogue
+// adds the two row blocks.  b_step / b_block: 16-B units per K step inside / across the 64-sample blocks of B.
+__device__ __forceinline__ void mma_over_samples(uint32_t d, uint64_t a_himid, uint64_t b_hi, uint64_t b_mid, uint32_t idesc,
+                                                 uint32_t b_step, uint32_t b_block, bool accumulate) {
+  for (int k = 0; k < 8; ++k)
+    tc::mma_f16(d, a_himid + (uint64_t)(128 * k), b_hi + (uint64_t)((k & 3) * b_step + (k >> 2) * b_block), idesc,
+                (accumulate || k > 0) ? 1u : 0u);
+  for (int k = 0; k < 8; ++k)
+    tc::mma_f16(d, a_himid + (uint64_t)(128 * k), b_mid + (uint64_t)((k & 3) * b_step + (k >> 2) * b_block), idesc, 1u);
 }
 
 template <bool ACTOR>
@@ -187,9 +189,6 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
 
   constexpr uint32_t ID_FWD = tc::instr_desc(tc::FMT_BF16, 128, 64, 0, 0);
   constexpr uint32_t ID_BWD = tc::instr_desc(tc::FMT_BF16, 128, 64, 0, 1);
-  // Contractions over samples have only 64 output rows (features).  M = 64 would cost the same tensor time as
-  // M = 128, so they run as M = 128 whose second 64-row atom (LBO = one tile further: the mid tile, resp. the
-  // W2 tile behind it, finite bf16 data either way) lands in accumulator rows 64..127, which nobody reads.
   constexpr uint32_t ID_WG = tc::instr_desc(tc::FMT_BF16, 128, 64, 1, 1);
   constexpr uint32_t ID_AUX = tc::instr_desc(tc::FMT_BF16, 128, 16, 1, 0);
 
@@ -197,9 +196,9 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
   float* sdo = P.sdout();
 
   // accumulators that stay in registers for the whole kernel
-  float acc_w3[2][POL_OUT_MAX];        // dW3[k][32 r + (tid & 31)] over this thread's 16-sample slice
+  float acc_w3[4][POL_OUT_MAX];        // dW3[k][f0 + 8 p + (lane & 7)] over samples 8 (lane >> 3) .. + 7 of this warp
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int k = 0; k < POL_OUT_MAX; ++k) acc_w3[r][k] = 0.0f;
   float acc_b3 = 0.0f;
@@ -207,17 +206,18 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
   float st[NST];
 #pragma unroll
   for (int i = 0; i < NST; ++i) st[i] = 0.0f;
-  const int ri = tid & 31, c8 = tid >> 5;
 
   const long long ntiles = (a.m_local + T2_S - 1) / T2_S;
   const bool any = (long long)cta < ntiles;
   const bool obs_vec = obs_dim == 4 && (reinterpret_cast<uintptr_t>(a.obs) & 15) == 0;
   // gather pipeline: row index two tiles ahead, observation one tile ahead (row < 0: no sample)
-  auto fetch_row = [&](long long tile) -> long long {
+  // (kept as the raw 32-bit load result; widened one iteration later, so nothing waits on the load here)
+  auto fetch_row = [&](long long tile) -> int {
     const long long gi = tile * T2_S + s;
     if (tile >= ntiles || gi >= a.m_local) return -1;
-    return a.idx ? (long long)__ldg(a.idx + gi) : a.idx_offset + gi;
+    return a.idx ? __ldg(a.idx + gi) : (int)gi;
   };
+  const long long row_off = a.idx ? 0 : a.idx_offset;
   float xn[POL_IN_PAD];
   auto fetch_obs = [&](long long row) {
     if (row >= 0 && obs_vec) {
@@ -232,8 +232,31 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
       else { prefetch_l2(a.returns + row); prefetch_l2(a.values + row); }
     }
   };
-  long long rown = fetch_row(cta), rownn = fetch_row((long long)cta + ncta);
+  int rownn = fetch_row((long long)cta + ncta);
+  long long rown;
+  { const int r0 = fetch_row(cta); rown = r0 < 0 ? -1 : row_off + r0; }
   fetch_obs(rown);
+
+  // first layer of one tile: 32 features of this thread from the prefetched observation
+  auto first_layer = [&](float (&hv)[32]) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int f = f0 + 4 * g;
+      const float4 b = lds4(sw + S2_B1 + f);
+      float2 a01 = make_float2(b.x, b.y), a23 = make_float2(b.z, b.w);
+#pragma unroll
+      for (int cc = 0; cc < POL_IN_PAD; ++cc) {
+        const float4 w = lds4(sw + S2_W1T + cc * 64 + f);
+        const float2 xx = make_float2(xn[cc], xn[cc]);
+        a01 = __ffma2_rn(make_float2(w.x, w.y), xx, a01);
+        a23 = __ffma2_rn(make_float2(w.z, w.w), xx, a23);
+      }
+      hv[4 * g] = tanh_fast(a01.x); hv[4 * g + 1] = tanh_fast(a01.y);
+      hv[4 * g + 2] = tanh_fast(a23.x); hv[4 * g + 3] = tanh_fast(a23.y);
+    }
+  };
+  float h1n[32];
+  first_layer(h1n);
 
   uint32_t it = 0;
 #pragma unroll 1
@@ -244,17 +267,15 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
     for (int c = 0; c < POL_IN_PAD; ++c) x[c] = xn[c];
     const long long row = rown;
     const bool valid = row >= 0;
-    // ---- backward of the previous tile (dz1 = dh1 * (1 - h1^2), h1 kept as an fp32 copy in TMEM) and first layer
-    // of this tile, in 8-feature chunks straight into the operand tiles: nothing 32 wide stays in registers.
-    // bwd + wgrad + aux_b2 of t-1 have retired once BAR_WG flips: dh is ready and the dz / h1 tiles are free.
+    // ---- backward of the previous tile (dz1 = dh1 * (1 - h1^2), h1 kept as an fp32 copy in TMEM) in 8-feature
+    // chunks straight into the operand tile, then this tile's first layer (computed an iteration ago, ahead of this
+    // wait).  bwd + wgrad + aux_b2 of t-1 have retired once BAR_WG flips: dh is ready, the dz / h1 tiles are free.
     if (it > 0) {
       mbar_wait(P.bar(BAR_WG), ph ^ 1u);
       tc::fence_after_sync();
-    }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint32_t col = lane_base + (uint32_t)(f0 + 8 * c);
-      if (it > 0) {
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t col = lane_base + (uint32_t)(f0 + 8 * c);
         float d[8], hp[8];
         tc::tmem_ld8_nowait(tm_dh + col, d);
         tc::tmem_ld8_nowait(tm_h1 + col, hp);
@@ -263,24 +284,14 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
         for (int e = 0; e < 8; ++e) d[e] *= fmaf(-hp[e], hp[e], 1.0f);
         store_split_chunk(P.dz(0), P.dz(1), s, 4 * half + c, d);
       }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      store_split_chunk(P.h1(0), P.h1(1), s, 4 * half + c, h1n + 8 * c);
       float hv[8];
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int f = f0 + 8 * c + 4 * g;
-        const float4 b = lds4(sw + S2_B1 + f);
-        float2 a01 = make_float2(b.x, b.y), a23 = make_float2(b.z, b.w);
-#pragma unroll
-        for (int cc = 0; cc < POL_IN_PAD; ++cc) {
-          const float4 w = lds4(sw + S2_W1T + cc * 64 + f);
-          const float2 xx = make_float2(x[cc], x[cc]);
-          a01 = __ffma2_rn(make_float2(w.x, w.y), xx, a01);
-          a23 = __ffma2_rn(make_float2(w.z, w.w), xx, a23);
-        }
-        hv[4 * g] = tanh_fast(a01.x); hv[4 * g + 1] = tanh_fast(a01.y);
-        hv[4 * g + 2] = tanh_fast(a23.x); hv[4 * g + 3] = tanh_fast(a23.y);
-      }
-      store_split_chunk(P.h1(0), P.h1(1), s, 4 * half + c, hv);
-      tc::tmem_st8(tm_h1 + col, hv);
+      for (int e = 0; e < 8; ++e) hv[e] = h1n[8 * c + e];
+      tc::tmem_st8(tm_h1 + lane_base + (uint32_t)(f0 + 8 * c), hv);
     }
     tc::tmem_wait_st();
     {
@@ -307,12 +318,12 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
                 tc::smem_desc_k_sw128(P.w2(1)), ID_FWD, 4, 2, 2, false);
       tc::mma_commit(P.bar(BAR_FWD));
       if (it > 0)
-        mma_aux(tm_w1, tc::smem_desc_mn_sw128(P.dz(0), T2_TILE, 1024), tc::smem_desc_mn_sw128(P.dz(1), T2_TILE, 1024),
-                tc::smem_desc_k_sw128(P.aux(ph ^ 1u, 0)), tc::smem_desc_k_sw128(P.aux(ph ^ 1u, 1)), ID_AUX, it > 1);
+        mma_over_samples(tm_w1, tc::smem_desc_mn_sw128(P.dz(0), T2_TILE, 1024), tc::smem_desc_k_sw128(P.aux(ph ^ 1u, 0)),
+                         tc::smem_desc_k_sw128(P.aux(ph ^ 1u, 1)), ID_AUX, 2, 64, it > 1);
       tc::mma_commit(P.bar(BAR_AUX));
     }
     // ---- gather: observation of tile t+1 (its row index arrived an iteration ago), row index of tile t+2
-    rown = rownn;
+    rown = rownn < 0 ? -1 : row_off + rownn;
     rownn = fetch_row(tile + 2LL * ncta);
     fetch_obs(rown);
     // per-sample scalars of this tile (L2 hits: prefetched one tile ago), in flight across the second layer
@@ -440,10 +451,6 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
       }
 #pragma unroll
       for (int k = 0; k < POL_OUT_MAX; ++k) sdo[k * T2_LD + s] = dout[k];
-    } else {
-      // the other half stages its h2 for the first dW3 round meanwhile (round order: features 32..63 first)
-#pragma unroll
-      for (int i = 0; i < 32; ++i) stg[i * T2_LD + s] = h2[i];
     }
     __syncthreads();
     float dout[POL_OUT_MAX];
@@ -478,49 +485,42 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
       mma_split(tm_dh, tc::smem_desc_k_sw128(P.dz(0)), tc::smem_desc_k_sw128(P.dz(1)), tc::smem_desc_mn_sw128(P.w2(0), 8192, 1024),
                 tc::smem_desc_mn_sw128(P.w2(1), 8192, 1024), ID_BWD, 4, 2, 128, false);
       // D_w[j][i] (+)= sum_s dz2[s][j] h1[s][i], K = 128 samples = 8 steps of 16 rows
-      mma_split(tm_w, tc::smem_desc_mn_sw128(P.dz(0), T2_TILE, 1024), tc::smem_desc_mn_sw128(P.dz(1), T2_TILE, 1024),
-                tc::smem_desc_mn_sw128(P.h1(0), T2_TILE, 1024), tc::smem_desc_mn_sw128(P.h1(1), T2_TILE, 1024), ID_WG, 8, 128, 128,
-                it > 0);
-      mma_aux(tm_b2, tc::smem_desc_mn_sw128(P.dz(0), T2_TILE, 1024), tc::smem_desc_mn_sw128(P.dz(1), T2_TILE, 1024),
-              tc::smem_desc_k_sw128(P.aux(ph, 0)), tc::smem_desc_k_sw128(P.aux(ph, 1)), ID_AUX, it > 0);
+      mma_over_samples(tm_w, tc::smem_desc_mn_sw128(P.dz(0), T2_TILE, 1024), tc::smem_desc_mn_sw128(P.h1(0), T2_TILE, 1024),
+                       tc::smem_desc_mn_sw128(P.h1(1), T2_TILE, 1024), ID_WG, 128, 512, it > 0);
+      mma_over_samples(tm_b2, tc::smem_desc_mn_sw128(P.dz(0), T2_TILE, 1024), tc::smem_desc_k_sw128(P.aux(ph, 0)),
+                       tc::smem_desc_k_sw128(P.aux(ph, 1)), ID_AUX, 2, 64, it > 0);
       tc::mma_commit(P.bar(BAR_WG));
     }
-    // ---- dW3[k][j] += sum_s dout[s][k] h2[s][j], db3[k] += sum_s dout[s][k]: two rounds of 32 features through
-    // smem; round 0 = features 32..63 (staged by half 1 during the loss), round 1 = features 0..31
+    // ---- dW3[k][j] += sum_s dout[s][k] h2[s][j], db3[k] += sum_s dout[s][k], warp-local (overlaps the MMAs):
+    // a warp transposes its 32 samples x 8 features through a private smem patch ([8][36] floats, conflict-free
+    // both ways), lane = (feature jj, sample octet qd) then sums 8 samples; 4 passes, no CTA barrier.
+    {
+      float* patch = stg + warp * (8 * 36);
+      const int lane = tid & 31, jj = lane & 7, qd = lane >> 3;
+      const float* dbase = sdo + 32 * (warp & 3) + 8 * qd;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      if (r == 1) {
-        __syncthreads();
-        if (half == 0) {
+      for (int p = 0; p < 4; ++p) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) stg[i * T2_LD + s] = h2[i];
-        }
-        __syncthreads();
-      }
-      const float* hp = stg + ri * T2_LD + 16 * c8;
-      const float4 hv[4] = {lds4(hp), lds4(hp + 4), lds4(hp + 8), lds4(hp + 12)};
+        for (int j = 0; j < 8; ++j) patch[j * 36 + lane] = h2[8 * p + j];
+        __syncwarp();
+        const float4 ha = lds4(patch + jj * 36 + 8 * qd), hb = lds4(patch + jj * 36 + 8 * qd + 4);
 #pragma unroll
-      for (int k = 0; k < POL_OUT_MAX; ++k) {
-        if (k < OUT) {
-          const float* dp = sdo + k * T2_LD + 16 * c8;
-          float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 dv = lds4(dp + 4 * g);
-            s0 = fmaf(hv[g].x, dv.x, s0); s1 = fmaf(hv[g].y, dv.y, s1);
-            s0 = fmaf(hv[g].z, dv.z, s0); s1 = fmaf(hv[g].w, dv.w, s1);
+        for (int k = 0; k < POL_OUT_MAX; ++k) {
+          if (k < OUT) {
+            const float4 da = lds4(dbase + k * T2_LD), db = lds4(dbase + k * T2_LD + 4);
+            float s0 = ha.x * da.x, s1 = ha.y * da.y;
+            s0 = fmaf(ha.z, da.z, s0); s1 = fmaf(ha.w, da.w, s1);
+            s0 = fmaf(hb.x, db.x, s0); s1 = fmaf(hb.y, db.y, s1);
+            s0 = fmaf(hb.z, db.z, s0); s1 = fmaf(hb.w, db.w, s1);
+            acc_w3[p][k] += s0 + s1;
+            if (p == 0 && half == 0 && jj == k) acc_b3 += ((da.x + da.y) + (da.z + da.w)) + ((db.x + db.y) + (db.z + db.w));
           }
-          acc_w3[r][k] += s0 + s1;
         }
-      }
-      if (r == 0 && ri < OUT) {
-        const float* dp = sdo + ri * T2_LD + 16 * c8;
-        float sb = 0.0f;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) { const float4 dv = lds4(dp + 4 * g); sb += (dv.x + dv.y) + (dv.z + dv.w); }
-        acc_b3 += sb;
+        __syncwarp();
       }
     }
+    // ---- first layer of the next tile (its observation was requested right after this tile's forward MMAs)
+    first_layer(h1n);
   }
 
   // ---- tail: first-layer gradients of the last tile
@@ -544,8 +544,8 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
     __syncthreads();
     if (tid == 128) {
       tc::fence_after_sync();
-      mma_aux(tm_w1, tc::smem_desc_mn_sw128(P.dz(0), T2_TILE, 1024), tc::smem_desc_mn_sw128(P.dz(1), T2_TILE, 1024),
-              tc::smem_desc_k_sw128(P.aux(ph, 0)), tc::smem_desc_k_sw128(P.aux(ph, 1)), ID_AUX, it > 1);
+      mma_over_samples(tm_w1, tc::smem_desc_mn_sw128(P.dz(0), T2_TILE, 1024), tc::smem_desc_k_sw128(P.aux(ph, 0)),
+                       tc::smem_desc_k_sw128(P.aux(ph, 1)), ID_AUX, 2, 64, it > 1);
       tc::mma_commit(P.bar(BAR_FIN));
     }
     mbar_wait(P.bar(BAR_FIN), 0);
@@ -557,60 +557,77 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
   float* part = a.partials + ((size_t)(ACTOR ? 0 : 1) * ncta + cta) * UPD_PSTRIDE;
   const int oB1 = 64 * obs_dim, oW2 = oB1 + 64, oB2 = oW2 + 4096, oW3 = oB2 + 64, oB3 = oW3 + OUT * 64, oLS = oB3 + OUT;
   {
-    // TMEM accumulators, rows 0..63 = feature j: warps 0,1 (and 4,5) hold them; thread (j, half) reads 32 columns
-    if ((warp & 3) < 2) {
-      const int j = s;
-      float v[32];
-      if (any) tc::tmem_ld32(tm_w + lane_base + f0, v);
+    // TMEM accumulators: rows 0..63 (hi^T B) + rows 64..127 (mid^T B) = feature j; thread (row, half) reads 32 columns
+    float v[32];
+    uint32_t u[16];
+    if (any) {
+      tc::tmem_ld32(tm_w + lane_base + f0, v);
+      tc::tmem_ld16((half == 0 ? tm_b2 : tm_w1) + lane_base, u);
+    } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) part[oW2 + j * 64 + f0 + i] = any ? v[i] : 0.0f;
-      uint32_t u[16];
-      if (half == 0) {
-        if (any) tc::tmem_ld16(tm_b2 + lane_base, u);
-        part[oB2 + j] = any ? __uint_as_float(u[0]) : 0.0f;
-      } else {
-        if (any) tc::tmem_ld16(tm_w1 + lane_base, u);
-        part[oB1 + j] = any ? __uint_as_float(u[0]) : 0.0f;
+      for (int i = 0; i < 32; ++i) v[i] = 0.0f;
 #pragma unroll
-        for (int c = 0; c < POL_IN_PAD; ++c)
-          if (c < obs_dim) part[j * obs_dim + c] = any ? __uint_as_float(u[1 + c]) : 0.0f;
+      for (int i = 0; i < 16; ++i) u[i] = 0u;
+    }
+    if (s >= 64) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) stg[(s - 64) * 65 + f0 + i] = v[i];
+      if (half == 0) sdo[s - 64] = __uint_as_float(u[0]);
+      else {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) sdo[64 + (s - 64) * 5 + c] = __uint_as_float(u[c]);
       }
     }
+    __syncthreads();
+    if (s < 64) {
+      const int j = s;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) part[oW2 + j * 64 + f0 + i] = v[i] + stg[j * 65 + f0 + i];
+      if (half == 0) part[oB2 + j] = __uint_as_float(u[0]) + sdo[j];
+      else {
+        part[oB1 + j] = __uint_as_float(u[0]) + sdo[64 + j * 5];
+#pragma unroll
+        for (int c = 0; c < POL_IN_PAD; ++c)
+          if (c < obs_dim) part[j * obs_dim + c] = __uint_as_float(u[1 + c]) + sdo[64 + j * 5 + 1 + c];
+      }
+    }
+    __syncthreads();
   }
   {
     // SIMT accumulators: dW3 / db3 summed over the 8 sample slices, statistics over the warps of half 0
-    float* red = stg;                                   // [(r*4 + k)][c8][32]  then db3 [4][8], then stats [9][4]
+    float* red = stg;   // dW3 [(half*4 + p)*4 + k][warp & 3][qd][jj] (4096), db3 [k][warp & 3][qd] (64), stats [9][4]
+    const int lane = tid & 31, jj = lane & 7, qd = lane >> 3, wq = warp & 3;
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int k = 0; k < POL_OUT_MAX; ++k) red[((r * 4 + k) * 8 + c8) * 32 + ri] = acc_w3[r][k];
-    if (ri < POL_OUT_MAX) red[2048 + ri * 8 + c8] = acc_b3;
+      for (int k = 0; k < POL_OUT_MAX; ++k) red[((((half * 4 + p) * 4 + k) * 4 + wq) * 4 + qd) * 8 + jj] = acc_w3[p][k];
+    if (half == 0 && jj < POL_OUT_MAX) red[4096 + (jj * 4 + wq) * 4 + qd] = acc_b3;
     if (half == 0) {
 #pragma unroll
       for (int i = 0; i < NST; ++i) {
         const float v = warp_sum(st[i]);
-        if ((tid & 31) == 0) red[2048 + 32 + i * 4 + warp] = v;
+        if (lane == 0) red[4160 + i * 4 + wq] = v;
       }
     }
     __syncthreads();
     {
       const int f = tid & 63, k = tid >> 6;
       if (k < OUT) {
-        const int r = f < 32 ? 1 : 0, i = f & 31;       // round 0 carried features 32..63
+        const float* q = red + ((((f >> 5) * 4 + ((f & 31) >> 3)) * 4 + k) * 16) * 8 + (f & 7);
         float sum = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) sum += red[((r * 4 + k) * 8 + c) * 32 + i];
+        for (int c = 0; c < 16; ++c) sum += q[c * 8];
         part[oW3 + k * 64 + f] = sum;
       }
       if (tid < OUT) {
         float sum = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) sum += red[2048 + tid * 8 + c];
+        for (int c = 0; c < 16; ++c) sum += red[4096 + tid * 16 + c];
         part[oB3 + tid] = sum;
       }
       if (tid < NST) {
-        const float* p = red + 2048 + 32 + tid * 4;
-        const float sum = (p[0] + p[1]) + (p[2] + p[3]);
+        const float* q = red + 4160 + tid * 4;
+        const float sum = (q[0] + q[1]) + (q[2] + q[3]);
         float* stat = part + UPD_STAT_OFF;
         if (ACTOR) {
           if (tid == 0) stat[AUR_STAT_POLICY_LOSS] = sum;
