@@ -130,6 +130,17 @@ STAT_NAMES = ["policy_loss", "value_loss", "entropy", "old_approx_kl", "approx_k
 NUM_STATS = 16
 
 
+def shuffle_indices(n: int, seed: int, stream_id: int, device="cuda", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`np.random.shuffle(arange(n))` of ppo.py:214-215 as a keyed bijection computed on the device -> int32 [n]."""
+    if out is None:
+        out = torch.empty(n, dtype=torch.int32, device=device)
+    if out.dtype != torch.int32 or out.numel() != n or not out.is_contiguous() or not out.is_cuda:
+        raise _lib.AurError("shuffle_indices: out must be a contiguous CUDA int32 tensor of n elements")
+    _lib.check(_lib.lib().aur_shuffle_indices(n, seed & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFFFFFFFFFF, out.data_ptr(),
+                                              _stream()), "aur_shuffle_indices")
+    return out
+
+
 class Updater:
     """Device state of the optimiser side of ppo.train (src/ppo.py:80,213-269): Adam moments,
     packed gradient buffer, workspace.  `allreduce` (optional) is called on the fp64 advantage

@@ -10,7 +10,7 @@ return value, same TensorBoard tags and checkpoint file.  What differs is where 
   T x (evaluate, D2H, N env.step, H2D)        one aur_rollout launch per update   (ppo.py:201-205)
   T x 9 elementwise kernels                   one aur_gae_f32 launch              (ppo.py:125-157)
   ~100 kernels + 2 syncs per minibatch        moments, grad, reduce, adam         (ppo.py:220-269)
-  np.random.shuffle + index H2D per epoch     torch.randperm on device
+  np.random.shuffle + index H2D per epoch     keyed bijection written by shuffle_kernel (no sort)
 
 There is no CPU path: without a CUDA device or without libaurppo.so the constructor raises.
 Under torch.distributed (NCCL) each rank owns num_envs / world_size env columns; the only
@@ -123,6 +123,10 @@ class ppo:
         self.updater = kernels.Updater(self.desc, self.flat, eps=1e-5, allreduce=parallel.make_allreduce(self.plan))
         self.optimizer = FusedAdam(self.policy.parameters(), self.updater, lr=self.learning_rate, eps=1e-5)
         self.philox_seed = int(params.get("philox_seed", 1))
+        # minibatch shuffles: one stream per (rank, epoch) so that ranks draw independent permutations
+        self.shuffle_seed = int(params.get("shuffle_seed", self.philox_seed))
+        self._shuffle_count = self.rank << 40
+        self._b_inds = torch.empty(self.local_batch, dtype=torch.int32, device=self.device)
         self.total_returns: List[float] = []
         self.total_episode_lengths: List[int] = []
         self.x_indices: List[int] = []
@@ -166,7 +170,9 @@ class ppo:
         n_mb = 0
         stats_rows = self._stats_rows
         for ep in range(self.num_update_epochs):
-            b_inds = torch.randperm(self.local_batch, device=self.device).to(torch.int32)
+            b_inds = kernels.shuffle_indices(self.local_batch, seed=self.shuffle_seed, stream_id=self._shuffle_count,
+                                             out=self._b_inds)
+            self._shuffle_count += 1
             for start in range(0, self.local_batch, self.local_minibatch):
                 mb = b_inds[start:start + self.local_minibatch]
                 stats_rows[n_mb].copy_(self.update_minibatch(flat_bufs, mb))

@@ -226,6 +226,11 @@ typedef struct {
 #define AUR_STAT_LOSS 7          /* policy - ent_c * entropy + vf_c * value */
 #define AUR_NUM_STATS 16
 
+/* Replaces `np.random.shuffle(b_inds)` (ppo.py:214-215): out[i] = pi(i), pi a keyed pseudo-random bijection of
+ * [0, n), n < 2^31 (Feistel network + cycle walking; keys from Philox4x32-10(seed, stream_id)).  Use a new
+ * stream_id per epoch (and per rank).  Restated bit for bit in oracle/ppo_ref.py::feistel_shuffle. */
+int aur_shuffle_indices(int64_t n, uint64_t seed, uint64_t stream_id, int32_t* out, void* stream);
+
 int64_t aur_ppo_update_workspace_bytes(const aur_policy_desc* desc);
 
 int aur_ppo_adv_moments(int64_t m, const int32_t* idx, int64_t idx_offset, const float* advantages,

@@ -240,3 +240,48 @@ def sampler_words(seed: int, env_id: int, step: int) -> Tuple[int, int, int, int
 def u01(word: int) -> np.float32:
     """24-bit uniform in [0,1): (w >> 8) * 2^-24."""
     return np.float32((word >> 8) * (1.0 / 16777216.0))
+
+
+# ------------------------------------------------- device minibatch shuffle, restated on CPU
+SHUF_ROUNDS = 8
+
+
+def _shuf_mix(v: np.ndarray) -> np.ndarray:
+    v = (v * np.uint64(0x9E3779B1)) & np.uint64(0xFFFFFFFF); v ^= v >> np.uint64(15)
+    v = (v * np.uint64(0x85EBCA77)) & np.uint64(0xFFFFFFFF); v ^= v >> np.uint64(13)
+    v = (v * np.uint64(0xC2B2AE3D)) & np.uint64(0xFFFFFFFF); v ^= v >> np.uint64(16)
+    return v
+
+
+def feistel_shuffle(n: int, seed: int, stream_id: int) -> np.ndarray:
+    """aur_shuffle_indices (aur_ppo_b200/csrc/shuffle.cu), the device stand-in for `np.random.shuffle(b_inds)`
+    (src/ppo.py:214-215): alternating unbalanced Feistel network over ceil(log2 n) bits with cycle walking -> int32
+    permutation of [0, n)."""
+    if n == 0:
+        return np.zeros(0, np.int32)
+    bits = 1
+    while (1 << bits) < n:
+        bits += 1
+    wa = (bits + 1) // 2
+    wb = max(bits - wa, 0)
+    ma, mb = np.uint64((1 << wa) - 1), np.uint64((1 << wb) - 1)
+    m32 = np.uint64(0xFFFFFFFF)
+    keys = [np.uint64(philox4x32_10((r, stream_id & 0xFFFFFFFF, (stream_id >> 32) & 0xFFFFFFFF, 0x5AFE5EED),
+                                    (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))[0]) for r in range(SHUF_ROUNDS)]
+
+    def encrypt(x):
+        L, R = x >> np.uint64(wb), x & mb
+        for r in range(0, SHUF_ROUNDS, 2):
+            t = L ^ (_shuf_mix((R + keys[r]) & m32) & ma)
+            L, R = R, t
+            t = L ^ (_shuf_mix((R + keys[r + 1]) & m32) & mb)
+            L, R = R, t
+        return (L << np.uint64(wb)) | R
+
+    x = encrypt(np.arange(n, dtype=np.uint64))
+    while True:
+        bad = x >= np.uint64(n)
+        if not bad.any():
+            break
+        x[bad] = encrypt(x[bad])
+    return x.astype(np.int32)

@@ -95,3 +95,12 @@ def test_explained_variance_and_anneal():
     assert np.isnan(R.explained_variance(v, np.ones(4, np.float32)))
     assert R.lr_anneal(2.5e-4, 1, 10) == 2.5e-4
     assert abs(R.lr_anneal(2.5e-4, 6, 10) - 1.25e-4) < 1e-18
+
+
+def test_feistel_shuffle_restatement_is_a_permutation():
+    for n in (1, 2, 5, 1000, 4097, 1 << 16):
+        p = R.feistel_shuffle(n, seed=9, stream_id=n)
+        assert p.dtype == np.int32 and np.array_equal(np.sort(p), np.arange(n))
+    a, b = R.feistel_shuffle(4096, 1, 0), R.feistel_shuffle(4096, 1, 1)
+    assert (a == b).mean() < 0.01 and np.array_equal(a, R.feistel_shuffle(4096, 1, 0))
+    assert abs(np.corrcoef(a, np.arange(4096))[0, 1]) < 0.08
