@@ -49,7 +49,16 @@ class UpdateArgs(ctypes.Structure):
                 ("obs", c_void_p), ("actions", c_void_p), ("logprobs", c_void_p), ("advantages", c_void_p),
                 ("returns", c_void_p), ("values", c_void_p), ("params", c_void_p),
                 ("clip_coeff", ctypes.c_float), ("entropy_coeff", ctypes.c_float), ("value_coeff", ctypes.c_float),
-                ("_pad2", ctypes.c_float), ("adv_moments", c_void_p), ("workspace", c_void_p), ("grads_out", c_void_p)]
+                ("_pad2", ctypes.c_float), ("adv_moments", c_void_p), ("workspace", c_void_p), ("grads_out", c_void_p),
+                ("dp", c_void_p), ("dp_seq", ctypes.c_uint32), ("_pad3", ctypes.c_uint32)]
+
+
+DP_MAX_RANKS = 16
+DP_HANDLE_BYTES = 64
+
+
+class DpCtx(ctypes.Structure):
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("peer", c_void_p * DP_MAX_RANKS)]
 
 
 class ConvArgs(ctypes.Structure):
@@ -124,6 +133,25 @@ def lib() -> ctypes.CDLL:
     L.aur_ppo_adv_moments.argtypes = [c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     L.aur_ppo_update_grad.restype = c_int
     L.aur_ppo_update_grad.argtypes = [ctypes.POINTER(UpdateArgs), c_void_p]
+    L.aur_dp_area_bytes.restype = c_int64
+    L.aur_dp_area_bytes.argtypes = [ctypes.POINTER(PolicyDesc)]
+    L.aur_dp_alloc.restype = c_int
+    L.aur_dp_alloc.argtypes = [c_int64, ctypes.POINTER(c_void_p), c_void_p]
+    L.aur_dp_open.restype = c_int
+    L.aur_dp_open.argtypes = [c_void_p, ctypes.POINTER(c_void_p)]
+    L.aur_dp_close.restype = c_int
+    L.aur_dp_close.argtypes = [c_void_p]
+    L.aur_dp_free.restype = c_int
+    L.aur_dp_free.argtypes = [c_void_p]
+    L.aur_dp_status.restype = c_int
+    L.aur_dp_status.argtypes = [c_void_p, c_void_p]
+    L.aur_ppo_adv_moments_dp.restype = c_int
+    L.aur_ppo_adv_moments_dp.argtypes = [c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint32,
+                                         c_void_p]
+    L.aur_ppo_update_apply_dp.restype = c_int
+    L.aur_ppo_update_apply_dp.argtypes = [ctypes.POINTER(PolicyDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                                          c_double, c_double, c_double, c_int64, c_double, c_int64, c_double, c_double,
+                                          c_void_p, c_void_p, ctypes.c_uint32, c_void_p]
     L.aur_ppo_update_set_impl.restype = c_int
     L.aur_ppo_update_set_impl.argtypes = [c_int]
     L.aur_ppo_update_get_impl.restype = c_int

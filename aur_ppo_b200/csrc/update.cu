@@ -126,14 +126,9 @@ __device__ void update_net(const UpdDev& a, float* smem) {
   float logstd_g[POL_OUT_MAX] = {0.f, 0.f, 0.f, 0.f};
   if (KIND == 1) nc = normal_consts(a.params + gA + gC, a.act_dim);
   float adv_mean = 0.0f, adv_den = 1.0f;
-  if (ACTOR && a.norm_adv) {
-    const double n = a.moments[2], s = a.moments[0], ss = a.moments[1];
-    const double mean = s / n;
-    double var = (ss - s * mean) / (n - 1.0);        // unbiased (torch .std())
-    if (var < 0.0) var = 0.0;
-    adv_mean = (float)mean;
-    adv_den = (float)sqrt(var) + 1e-8f;
-  }
+  if (ACTOR && a.norm_adv && tid == 0) adv_norm_consts(a, sRed[0], sRed[1]);
+  __syncthreads();
+  if (ACTOR && a.norm_adv) { adv_mean = sRed[0]; adv_den = sRed[1]; }
   __syncthreads();
 
   // persistent accumulators
@@ -441,31 +436,54 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) ppo_grad_kernel(UpdDev a) {
 
 // grads_out[p] = sum over CTAs of the partials, in CTA order, fp64 accumulation.
 __global__ void grad_reduce_kernel(const float* __restrict__ partials, int ncta, int obs_dim, int act_dim, int continuous,
-                                   float* __restrict__ grads_out) {
+                                   float* __restrict__ grads_out, DpDev dp, unsigned int* __restrict__ ticket) {
   const int64_t nA = net_param_count(obs_dim, UPD_H, 2, act_dim), nC = net_param_count(obs_dim, UPD_H, 2, 1);
   const int64_t P = nA + nC + (continuous ? act_dim : 0);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P + AUR_NUM_STATS) return;
-  int net; int64_t off;
-  if (i < nA) { net = 0; off = i; }
-  else if (i < nA + nC) { net = 1; off = i - nA; }
-  else if (i < P) { net = 0; off = nA + (i - nA - nC); }          // actor_logstd sits after the actor's own params
-  else {
-    const int sidx = (int)(i - P);
-    net = (sidx == AUR_STAT_VALUE_LOSS) ? 1 : 0;
-    off = UPD_STAT_OFF + sidx;
-    if (sidx > AUR_STAT_CLIPFRAC) { grads_out[i] = 0.0f; return; }
+  if (i < P + AUR_NUM_STATS) {
+    int net; int64_t off;
+    float v = 0.0f;
+    bool zero = false;
+    if (i < nA) { net = 0; off = i; }
+    else if (i < nA + nC) { net = 1; off = i - nA; }
+    else if (i < P) { net = 0; off = nA + (i - nA - nC); }          // actor_logstd sits after the actor's own params
+    else {
+      const int sidx = (int)(i - P);
+      net = (sidx == AUR_STAT_VALUE_LOSS) ? 1 : 0;
+      off = UPD_STAT_OFF + sidx;
+      zero = sidx > AUR_STAT_CLIPFRAC;
+    }
+    if (!zero) {
+      const float* p = partials + (size_t)net * ncta * UPD_PSTRIDE + off;
+      double s = 0.0;
+      for (int c = 0; c < ncta; ++c) s += (double)p[(size_t)c * UPD_PSTRIDE];
+      v = (float)s;
+    }
+    grads_out[i] = v;
+    if (dp.world > 1) {                                  // push this rank's sums into every rank's exchange area
+      const size_t slot_off = DP_OFF_GRAD + ((size_t)(dp.seq & 1u) * DP_MAX + dp.rank) * dp_grad_stride(P) * sizeof(float);
+      for (int r = 0; r < dp.world; ++r) reinterpret_cast<float*>(dp.peer[r] + slot_off)[i] = v;
+    }
   }
-  const float* p = partials + (size_t)net * ncta * UPD_PSTRIDE + off;
-  double s = 0.0;
-  for (int c = 0; c < ncta; ++c) s += (double)p[(size_t)c * UPD_PSTRIDE];
-  grads_out[i] = (float)s;
+  if (dp.world > 1) {                                    // the last block to finish releases the flags
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+      __threadfence_system();
+      if ((int)threadIdx.x < dp.world)
+        st_release_sys(reinterpret_cast<uint32_t*>(dp.peer[threadIdx.x] + DP_OFF_FLAG_GRAD) + dp.rank, dp.seq);
+      if (threadIdx.x == 0) *ticket = 0u;
+    }
+  }
 }
 
 // sum / sum of squares of advantages[idx] (fp64), finalised by the last CTA to finish.
 __global__ void __launch_bounds__(256) adv_moments_kernel(long long m, const int32_t* __restrict__ idx, long long idx_offset,
                                                         const float* __restrict__ adv, double* __restrict__ partial,
-                                                        unsigned int* __restrict__ ticket, double* __restrict__ out) {
+                                                        unsigned int* __restrict__ ticket, double* __restrict__ out, DpDev dp) {
   __shared__ double sh[2][8];
   __shared__ bool last;
   double s = 0.0, ss = 0.0;
@@ -490,18 +508,45 @@ __global__ void __launch_bounds__(256) adv_moments_kernel(long long m, const int
     double a = 0.0, b = 0.0;
     for (unsigned c = 0; c < gridDim.x; ++c) { a += partial[2 * c]; b += partial[2 * c + 1]; }   // fixed order
     out[0] = a; out[1] = b; out[2] = (double)m;
+    sh[0][0] = a; sh[1][0] = b;
     *ticket = 0u;
+  }
+  if (dp.world > 1 && last) {                            // push the local moments to every rank, then release the flags
+    __syncthreads();
+    if ((int)threadIdx.x < dp.world) {
+      unsigned char* area = dp.peer[threadIdx.x];
+      double* rm = reinterpret_cast<double*>(area + DP_OFF_MOM) + ((size_t)(dp.seq & 1u) * DP_MAX + dp.rank) * 4;
+      rm[0] = sh[0][0]; rm[1] = sh[1][0]; rm[2] = (double)m;
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<uint32_t*>(area + DP_OFF_FLAG_MOM) + dp.rank, dp.seq);
+    }
   }
 }
 
 // clip_grad_norm_ (all parameters, torch semantics) + Adam, one CTA (P ~ 9e3).
-__global__ void __launch_bounds__(1024) adam_kernel(int64_t P, float* __restrict__ params, const float* __restrict__ g_in,
+__global__ void __launch_bounds__(1024) adam_kernel(int64_t P, float* __restrict__ params, float* __restrict__ g_in,
                                                    float* __restrict__ m1, float* __restrict__ m2, float lr_over_bc1,
                                                    float beta1, float beta2, float eps, float sqrt_bc2, float max_norm,
-                                                   float inv_m, float ent_c, float vf_c, float* __restrict__ stats_out) {
+                                                   float inv_m, float ent_c, float vf_c, float* __restrict__ stats_out, DpDev dp) {
   __shared__ double sh[32];
   __shared__ float coef_s, norm_s;
   double ss = 0.0;
+  if (dp.world > 1) {
+    // data-parallel: the all-reduce happens HERE.  Every rank pushed its [grads | stats] sums into our exchange
+    // area (grad_reduce_kernel); wait for the flags, add the G vectors in rank order (bit-identical on every
+    // rank), keep the global sums in g_in, then clip + Adam as usual on replicated parameters.
+    unsigned char* me = dp.peer[dp.rank];
+    if ((int)threadIdx.x < dp.world) dp_wait_flag(reinterpret_cast<const uint32_t*>(me + DP_OFF_FLAG_GRAD) + threadIdx.x, dp.seq, me);
+    __syncthreads();
+    const int gs = dp_grad_stride(P);
+    const float* rg = reinterpret_cast<const float*>(me + DP_OFF_GRAD) + (size_t)(dp.seq & 1u) * DP_MAX * gs;
+    for (int64_t i = threadIdx.x; i < P + AUR_NUM_STATS; i += blockDim.x) {
+      float g = 0.0f;
+      for (int r = 0; r < dp.world; ++r) g += __ldcg(rg + (size_t)r * gs + i);
+      g_in[i] = g;
+    }
+    __syncthreads();
+  }
   for (int64_t i = threadIdx.x; i < P; i += blockDim.x) { const double g = g_in[i]; ss += g * g; }
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
@@ -573,16 +618,40 @@ extern "C" int64_t aur_ppo_update_workspace_bytes(const aur_policy_desc* desc) {
   return (int64_t)aur::ws_bytes();
 }
 
+namespace aur {
+static int make_dp(const aur_dp_ctx* c, uint32_t seq, DpDev& d, const char* who) {
+  d.world = 1; d.rank = 0; d.seq = seq;
+  for (int r = 0; r < DP_MAX; ++r) d.peer[r] = nullptr;
+  if (!c || c->world <= 1) return 0;
+  if (c->world > DP_MAX || c->rank < 0 || c->rank >= c->world || seq == 0) {
+    set_error("%s: bad data-parallel context (world %d, rank %d, seq %u)", who, c->world, c->rank, seq); return AUR_ERR_ARG;
+  }
+  for (int r = 0; r < c->world; ++r) {
+    if (!c->peer[r]) { set_error("%s: exchange area of rank %d is not mapped", who, r); return AUR_ERR_ARG; }
+    d.peer[r] = static_cast<unsigned char*>(c->peer[r]);
+  }
+  d.world = c->world; d.rank = c->rank;
+  return 0;
+}
+}  // namespace aur
+
 extern "C" int aur_ppo_adv_moments(int64_t m, const int32_t* idx, int64_t idx_offset, const float* advantages,
                                    double* moments_out, float* workspace, void* stream) {
+  return aur_ppo_adv_moments_dp(m, idx, idx_offset, advantages, moments_out, workspace, nullptr, 0, stream);
+}
+
+extern "C" int aur_ppo_adv_moments_dp(int64_t m, const int32_t* idx, int64_t idx_offset, const float* advantages,
+                                      double* moments_out, float* workspace, const aur_dp_ctx* dp, uint32_t seq, void* stream) {
   using namespace aur;
+  DpDev dpd;
+  { int rc = make_dp(dp, seq, dpd, "aur_ppo_adv_moments_dp"); if (rc) return rc; }
   if (m <= 0 || !advantages || !moments_out || !workspace) { set_error("aur_ppo_adv_moments: bad arguments"); return AUR_ERR_ARG; }
   double* partial = reinterpret_cast<double*>(workspace + ws_partials_floats());
   unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + 2 * MOM_CTAS);
   long long grid = (m + 255) / 256;
   if (grid > MOM_CTAS) grid = MOM_CTAS;
   adv_moments_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((long long)m, idx, (long long)idx_offset, advantages,
-                                                                      partial, ticket, moments_out);
+                                                                      partial, ticket, moments_out, dpd);
   AUR_LAUNCH_OK("adv_moments_kernel");
   return 0;
 }
@@ -614,6 +683,7 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
   d.clip_lo = (float)(1.0 - (double)u.clip_coeff); d.clip_hi = (float)(1.0 + (double)u.clip_coeff);
   d.ent_c = u.entropy_coeff; d.vf_c = u.value_coeff; d.inv_m = (float)(1.0 / (double)u.m_total);
   d.moments = u.adv_moments; d.partials = u.workspace;
+  { int rc2 = make_dp(u.dp, u.dp_seq, d.dp, "aur_ppo_update_grad"); if (rc2) return rc2; }
   static bool attr_set = false;
   if (!attr_set) {
     AUR_CUDA_OK(cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
@@ -633,17 +703,28 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
   }
   const int64_t P = policy_param_count(u.policy);
   const int total = (int)(P + AUR_NUM_STATS);
+  unsigned int* ticket2 = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(u.workspace + ws_partials_floats()) + 2 * MOM_CTAS) + 1;
   grad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(u.workspace, gx, u.policy.obs_dim, u.policy.act_dim,
-                                                        u.policy.continuous, u.grads_out);
+                                                        u.policy.continuous, u.grads_out, d.dp, ticket2);
   AUR_LAUNCH_OK("grad_reduce_kernel");
   return 0;
 }
 
-extern "C" int aur_ppo_update_apply(const aur_policy_desc* desc, float* params, const float* grads_packed, float* adam_m,
+extern "C" int aur_ppo_update_apply(const aur_policy_desc* desc, float* params, float* grads_packed, float* adam_m,
                                     float* adam_v, double lr, double beta1, double beta2, double eps, int64_t step,
                                     double max_grad_norm, int64_t m_total, double entropy_coeff, double value_coeff,
                                     float* stats_out, void* stream) {
+  return aur_ppo_update_apply_dp(desc, params, grads_packed, adam_m, adam_v, lr, beta1, beta2, eps, step, max_grad_norm, m_total,
+                                 entropy_coeff, value_coeff, stats_out, nullptr, 0, stream);
+}
+
+extern "C" int aur_ppo_update_apply_dp(const aur_policy_desc* desc, float* params, float* grads_packed, float* adam_m,
+                                       float* adam_v, double lr, double beta1, double beta2, double eps, int64_t step,
+                                       double max_grad_norm, int64_t m_total, double entropy_coeff, double value_coeff,
+                                       float* stats_out, const aur_dp_ctx* dp, uint32_t seq, void* stream) {
   using namespace aur;
+  DpDev dpd;
+  { int rc = make_dp(dp, seq, dpd, "aur_ppo_update_apply_dp"); if (rc) return rc; }
   if (!desc || !params || !grads_packed || !adam_m || !adam_v || step < 1 || m_total <= 0) {
     set_error("aur_ppo_update_apply: bad arguments"); return AUR_ERR_ARG;
   }
@@ -652,7 +733,7 @@ extern "C" int aur_ppo_update_apply(const aur_policy_desc* desc, float* params, 
   adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(P, params, grads_packed, adam_m, adam_v, (float)(lr / bc1), (float)beta1,
                                                    (float)beta2, (float)eps, (float)sqrt(bc2), (float)max_grad_norm,
                                                    (float)(1.0 / (double)m_total), (float)entropy_coeff, (float)value_coeff,
-                                                   stats_out);
+                                                   stats_out, dpd);
   AUR_LAUNCH_OK("adam_kernel");
   return 0;
 }

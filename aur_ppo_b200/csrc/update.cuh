@@ -16,6 +16,49 @@ constexpr int UPD_SMEM_FLOATS = UPD_SW + 2 * UPD_WD + UPD_H + 2 * UPD_H * UPD_LD
 constexpr size_t UPD_SMEM = sizeof(float) * UPD_SMEM_FLOATS;
 constexpr int MOM_CTAS = 148;
 
+// ---- data-parallel exchange over peer memory (dp.cu): every rank owns one exchange area that all ranks of the
+// node map (CUDA IPC).  Producers PUSH their values into every peer's area over NVLink and then release a
+// sequence-numbered flag there; consumers only ever poll and read their OWN area.  Two slots (seq & 1) because a
+// rank can run at most one minibatch ahead of a peer that is still reading.
+constexpr int DP_MAX = 16;
+constexpr int DP_OFF_FLAG_MOM = 0;         // u32 [DP_MAX]
+constexpr int DP_OFF_FLAG_GRAD = 64;       // u32 [DP_MAX]
+constexpr int DP_OFF_STATUS = 128;         // u32: 1 = a wait timed out
+constexpr int DP_OFF_MOM = 256;            // f64 [2][DP_MAX][4]
+constexpr int DP_OFF_GRAD = DP_OFF_MOM + 2 * DP_MAX * 4 * 8;   // f32 [2][DP_MAX][dp_grad_stride]
+__host__ __device__ inline int dp_grad_stride(int64_t P) { return (int)((P + AUR_NUM_STATS + 63) / 64 * 64); }
+__host__ __device__ inline int64_t dp_area_bytes(int64_t P) { return DP_OFF_GRAD + (int64_t)2 * DP_MAX * dp_grad_stride(P) * 4; }
+struct DpDev {
+  int world, rank;                         // world <= 1: not data-parallel
+  uint32_t seq;                            // minibatch sequence number (same on every rank), starts at 1
+  unsigned char* peer[DP_MAX];             // exchange area of every rank as mapped here; peer[rank] is local
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// wait until the peer's flag in OUR area reaches seq; gives up after 20 s (status word) instead of hanging the GPU
+__device__ __forceinline__ void dp_wait_flag(const uint32_t* flag, uint32_t seq, unsigned char* my_area) {
+  if ((int32_t)(ld_acquire_sys(flag) - seq) >= 0) return;
+  const uint64_t t0 = global_timer_ns();
+  while ((int32_t)(ld_acquire_sys(flag) - seq) < 0) {
+    __nanosleep(64);
+    if (global_timer_ns() - t0 > 20000000000ull) { *reinterpret_cast<volatile uint32_t*>(my_area + DP_OFF_STATUS) = 1u; break; }
+  }
+}
+#endif
+
 struct UpdDev {
   long long m_local;
   const int32_t* idx;
@@ -25,7 +68,37 @@ struct UpdDev {
   float clip, clip_lo, clip_hi, ent_c, vf_c, inv_m;
   const double* moments;
   float* partials;      // [2][gridDim.x][UPD_PSTRIDE]
+  DpDev dp;
 };
+
+#ifdef __CUDACC__
+// sum, sum of squares and count of the advantages of the WHOLE minibatch: local (a.moments) or, data-parallel, the
+// per-rank moments every rank pushed into our exchange area, added in rank order (identical on every rank)
+__device__ __forceinline__ void load_adv_moments(const UpdDev& a, double& s, double& ss, double& n) {
+  if (a.dp.world > 1) {
+    unsigned char* me = a.dp.peer[a.dp.rank];
+    const uint32_t* flags = reinterpret_cast<const uint32_t*>(me + DP_OFF_FLAG_MOM);
+    const double* rm = reinterpret_cast<const double*>(me + DP_OFF_MOM) + (a.dp.seq & 1u) * DP_MAX * 4;
+    s = 0.0; ss = 0.0; n = 0.0;
+    for (int r = 0; r < a.dp.world; ++r) {
+      dp_wait_flag(flags + r, a.dp.seq, me);
+      s += __ldcg(rm + r * 4); ss += __ldcg(rm + r * 4 + 1); n += __ldcg(rm + r * 4 + 2);
+    }
+  } else {
+    s = a.moments[0]; ss = a.moments[1]; n = a.moments[2];
+  }
+}
+__device__ __forceinline__ void adv_norm_consts(const UpdDev& a, float& mean_out, float& den_out) {
+  double s, ss, n;
+  load_adv_moments(a, s, ss, n);
+  const double mean = s / n;
+  double var = (ss - s * mean) / (n - 1.0);          // unbiased (torch .std())
+  if (var < 0.0) var = 0.0;
+  mean_out = (float)mean;
+  den_out = (float)sqrt(var) + 1e-8f;
+}
+#endif
+
 
 
 // tensor-core implementation (update_tc.cu): both nets per CTA, grid = gx CTAs; same partial layout

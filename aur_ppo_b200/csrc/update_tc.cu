@@ -53,7 +53,7 @@ constexpr size_t T2_SMEM = T2_SMEM_USED + 1024;
 static_assert(2 * (T2_SMEM + 1024) <= 233472, "two CTAs per SM");
 
 // small-weight block (floats): W1^T [4][64] (zero rows >= obs_dim), b1 [64], b2 [64], W3 [4][64], b3 [4]
-constexpr int S2_W1T = 0, S2_B1 = 256, S2_B2 = 320, S2_W3 = 384, S2_B3 = 640, S2_NC = 644;   // S2_NC: Normal constants [3][4]
+constexpr int S2_W1T = 0, S2_B1 = 256, S2_B2 = 320, S2_W3 = 384, S2_B3 = 640, S2_NC = 644;   // S2_NC: Normal constants [3][4], then advantage mean / std + 1e-8
 enum { BAR_FWD = 0, BAR_AUX = 1, BAR_WG = 2, BAR_FIN = 3 };
 constexpr int T2_TMEM_COLS = 256;           // z / dh 64 (never live together) | dW2 64 | db2 16 | [db1 dW1] 16 | h1 (fp32 copy) 64
 
@@ -171,19 +171,13 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
 #pragma unroll
     for (int k = 0; k < POL_OUT_MAX; ++k) { sw[S2_NC + k] = nc.std[k]; sw[S2_NC + 4 + k] = nc.inv2var[k]; sw[S2_NC + 8 + k] = nc.log_scale[k]; }
   }
-  float adv_mean = 0.0f, adv_den = 1.0f;
-  if (ACTOR && a.norm_adv) {
-    const double n = a.moments[2], sm = a.moments[0], ss = a.moments[1];
-    const double mean = sm / n;
-    double var = (ss - sm * mean) / (n - 1.0);
-    if (var < 0.0) var = 0.0;
-    adv_mean = (float)mean; adv_den = (float)sqrt(var) + 1e-8f;
-  }
+  if (ACTOR && a.norm_adv && tid == 32) adv_norm_consts(a, sw[S2_NC + 12], sw[S2_NC + 13]);   // (waits for the peers' moments when data-parallel)
   tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *P.tmem_slot();
+  const float adv_mean = (ACTOR && a.norm_adv) ? sw[S2_NC + 12] : 0.0f, adv_den = (ACTOR && a.norm_adv) ? sw[S2_NC + 13] : 1.0f;
   const uint32_t tm_z = tmem, tm_dh = tmem, tm_w = tmem + 64, tm_b2 = tmem + 128, tm_w1 = tmem + 144, tm_h1 = tmem + 160;
   const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
 

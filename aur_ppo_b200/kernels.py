@@ -148,7 +148,7 @@ class Updater:
     data-parallel run."""
 
     def __init__(self, desc: _lib.PolicyDesc, params: torch.Tensor, eps: float = 1e-5, betas=(0.9, 0.999),
-                 allreduce=None):
+                 allreduce=None, exchange=None):
         import ctypes
         self.desc, self.params = desc, _f32c(params, "params")
         dev = params.device
@@ -163,6 +163,10 @@ class Updater:
         ws = int(_lib.lib().aur_ppo_update_workspace_bytes(ctypes.byref(desc)))
         self.workspace = torch.zeros((ws + 3) // 4, dtype=torch.float32, device=dev)
         self.eps, self.betas, self.step_count, self.allreduce = float(eps), betas, 0, allreduce
+        # exchange (parallel.PeerExchange): the kernels all-reduce over peer memory themselves; excludes `allreduce`
+        self.exchange = exchange
+        if exchange is not None and allreduce is not None:
+            raise _lib.AurError("give either a peer exchange or an allreduce callable, not both")
 
     def grad(self, b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values, idx: Optional[torch.Tensor],
              m_total: Optional[int] = None, idx_offset: int = 0, m_local: Optional[int] = None, clip_coeff=0.2,
@@ -182,9 +186,12 @@ class Updater:
             _f32c(t, n)
         with torch.cuda.device(self.params.device):
             st = _stream()
+            dp, seq = (ctypes.addressof(self.exchange.ctx), self.exchange.next_seq()) if self.exchange is not None else (None, 0)
+            self._seq = seq
             if norm_adv:
-                _lib.check(L.aur_ppo_adv_moments(m_local, _ptr(idx), idx_offset, b_advantages.data_ptr(),
-                                                 self.moments.data_ptr(), self.workspace.data_ptr(), st), "aur_ppo_adv_moments")
+                _lib.check(L.aur_ppo_adv_moments_dp(m_local, _ptr(idx), idx_offset, b_advantages.data_ptr(),
+                                                    self.moments.data_ptr(), self.workspace.data_ptr(), dp, seq, st),
+                           "aur_ppo_adv_moments")
                 if self.allreduce is not None:
                     self.allreduce(self.moments)
             a = _lib.UpdateArgs()
@@ -196,6 +203,7 @@ class Updater:
             a.clip_coeff, a.entropy_coeff, a.value_coeff = float(clip_coeff), float(entropy_coeff), float(value_coeff)
             a.adv_moments = self.moments.data_ptr() if norm_adv else None
             a.workspace, a.grads_out = self.workspace.data_ptr(), self.grads.data_ptr()
+            a.dp, a.dp_seq = dp, seq
             _lib.check(L.aur_ppo_update_grad(ctypes.byref(a), st), "aur_ppo_update_grad")
             if self.allreduce is not None:
                 self.allreduce(self.grads)
@@ -207,11 +215,12 @@ class Updater:
         import ctypes
         self.step_count += 1
         with torch.cuda.device(self.params.device):
-            rc = _lib.lib().aur_ppo_update_apply(ctypes.byref(self.desc), self.params.data_ptr(), self.grads.data_ptr(),
-                                                 self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), float(lr),
-                                                 self.betas[0], self.betas[1], self.eps, self.step_count,
-                                                 float(max_grad_norm), self._m_total, self._ent_c, self._vf_c,
-                                                 self.stats.data_ptr(), _stream())
+            dp = ctypes.addressof(self.exchange.ctx) if self.exchange is not None else None
+            rc = _lib.lib().aur_ppo_update_apply_dp(ctypes.byref(self.desc), self.params.data_ptr(), self.grads.data_ptr(),
+                                                    self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), float(lr),
+                                                    self.betas[0], self.betas[1], self.eps, self.step_count,
+                                                    float(max_grad_norm), self._m_total, self._ent_c, self._vf_c,
+                                                    self.stats.data_ptr(), dp, getattr(self, "_seq", 0) if dp else 0, _stream())
         _lib.check(rc, "aur_ppo_update_apply")
         return self.stats
 

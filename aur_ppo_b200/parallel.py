@@ -1,8 +1,13 @@
 """Data-parallel plan of the PPO hot path: env columns are sharded over
 ranks, rollout and GAE need no communication, and each minibatch exchanges one packed fp32 buffer
-[P gradient sums | 16 statistic sums] plus three fp64 advantage moments with a SUM all-reduce
-(NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests).  Gradient seeds carry
-1/m_total, so the sum over ranks is the mean over the whole minibatch."""
+[P gradient sums | 16 statistic sums] plus three fp64 advantage moments.  Gradient seeds carry
+1/m_total, so the sum over ranks is the mean over the whole minibatch.
+
+On the GPU box the exchange is done by the update kernels themselves over NVLink / NVSwitch peer
+memory (`PeerExchange`: CUDA-IPC-mapped exchange areas, push + flag, gather inside the Adam kernel);
+torch.distributed (NCCL) only carries the set-up: parameter broadcast, IPC handles, barriers.
+`make_allreduce` (a library SUM all-reduce between the kernels) is kept for `exchange="nccl"` and for
+the gloo CPU tests of the host logic."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -77,3 +82,52 @@ def broadcast_parameters(module: torch.nn.Module, plan: ShardPlan, src: int = 0)
     if plan.world_size > 1:
         for p in module.parameters():
             torch.distributed.broadcast(p.data, src)
+
+
+class PeerExchange:
+    """Exchange areas of the in-kernel gradient all-reduce: one cudaMalloc'ed area per rank, mapped into every
+    rank of the node with CUDA IPC (handles travel through torch.distributed)."""
+
+    def __init__(self, plan: ShardPlan, desc, group=None):
+        import ctypes
+        from . import _lib
+        if plan.world_size > _lib.DP_MAX_RANKS:
+            raise _lib.AurError(f"PeerExchange supports up to {_lib.DP_MAX_RANKS} ranks of one node")
+        L = _lib.lib()
+        self.plan, self._L, self._opened = plan, L, []
+        self.bytes = int(L.aur_dp_area_bytes(ctypes.byref(desc)))
+        own, handle = ctypes.c_void_p(), ctypes.create_string_buffer(_lib.DP_HANDLE_BYTES)
+        _lib.check(L.aur_dp_alloc(self.bytes, ctypes.byref(own), handle), "aur_dp_alloc")
+        self.own = own.value
+        handles = [None] * plan.world_size
+        torch.distributed.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.ctx = _lib.DpCtx()
+        self.ctx.world, self.ctx.rank = plan.world_size, plan.rank
+        for r, h in enumerate(handles):
+            if r == plan.rank:
+                self.ctx.peer[r] = self.own
+            else:
+                p = ctypes.c_void_p()
+                _lib.check(L.aur_dp_open(ctypes.create_string_buffer(h, _lib.DP_HANDLE_BYTES), ctypes.byref(p)), "aur_dp_open")
+                self.ctx.peer[r] = p.value
+                self._opened.append(p.value)
+        self.seq = 0
+        torch.distributed.barrier(group=group)
+
+    def next_seq(self) -> int:
+        self.seq += 1
+        return self.seq
+
+    def status(self) -> int:
+        return int(self._L.aur_dp_status(self.own, None))
+
+    def close(self) -> None:
+        if self._L is None:
+            return
+        torch.cuda.synchronize()
+        if torch.distributed.is_initialized():
+            torch.distributed.barrier()
+        for p in self._opened:
+            self._L.aur_dp_close(p)
+        self._L.aur_dp_free(self.own)
+        self._opened, self._L = [], None

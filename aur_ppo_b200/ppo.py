@@ -120,7 +120,14 @@ class ppo:
         self.flat = self.policy.flat_parameters()
         self.desc = kernels.policy_desc(*self.policy.kernel_shape())
         self.buffer = torch_buffer(self.state_dim, sp["act_shape"], self.num_steps, self.local_envs, self.device)
-        self.updater = kernels.Updater(self.desc, self.flat, eps=1e-5, allreduce=parallel.make_allreduce(self.plan))
+        # data-parallel exchange: "peer" = in-kernel all-reduce over NVLink peer memory (default), "nccl" = library all-reduce
+        self.exchange_kind = str(params.get("exchange", os.environ.get("AUR_DP_EXCHANGE", "peer")))
+        self.exchange = None
+        if self.plan.world_size > 1 and self.exchange_kind == "peer":
+            self.exchange = parallel.PeerExchange(self.plan, self.desc)
+            self.updater = kernels.Updater(self.desc, self.flat, eps=1e-5, exchange=self.exchange)
+        else:
+            self.updater = kernels.Updater(self.desc, self.flat, eps=1e-5, allreduce=parallel.make_allreduce(self.plan))
         self.optimizer = FusedAdam(self.policy.parameters(), self.updater, lr=self.learning_rate, eps=1e-5)
         self.philox_seed = int(params.get("philox_seed", 1))
         # minibatch shuffles: one stream per (rank, epoch) so that ranks draw independent permutations
@@ -133,6 +140,12 @@ class ppo:
         self._returns = torch.empty_like(self.buffer.rewards)
         self._advantages = torch.empty_like(self.buffer.rewards)
         self._env_step = 0
+
+    def close(self) -> None:
+        """Unmap the peer exchange areas (data-parallel runs); collective: every rank calls it."""
+        if getattr(self, "exchange", None) is not None:
+            self.exchange.close()
+            self.exchange = None
 
     # ------------------------------------------------------------------ hot path pieces
     def make_env(self, gym_id, idx, capture_video):
@@ -243,6 +256,9 @@ class ppo:
                 writer.add_scalar("charts/SPS", int(global_step / (time.time() - start_time)), global_step)
 
         self.envs.close()
+        if self.exchange is not None and self.exchange.status() != 0:
+            raise _lib.AurError("data-parallel exchange: a kernel timed out waiting for a peer rank")
+        self.close()
         if writer is not None:
             writer.close()
         if self.rank == 0 and self.params_dict.get("save", True):

@@ -34,7 +34,8 @@ def workload_config(n_gpus):
     return {"workload": "CartPole-v1 PPO iteration: fused rollout + GAE + update (BASELINE configs[1])",
             "num_envs_per_gpu": NUM_ENVS_PER_GPU, "num_envs": NUM_ENVS_PER_GPU * n_gpus, "num_steps": T,
             "num_minibatches": NUM_MINIBATCHES, "update_epochs": EPOCHS, "hidden_dim": 64, "num_layers": 2,
-            "parallelism": f"dp{n_gpus} (env columns sharded, one packed allreduce per minibatch)",
+            "parallelism": f"dp{n_gpus} (env columns sharded; per minibatch one packed [grads|stats] exchange done by the "
+                           f"update kernels over NVLink peer memory, AUR_DP_EXCHANGE=nccl selects a library all-reduce)",
             "l2": "working set 370 MB per iteration > 126 MB L2 (no explicit flush needed)"}
 
 
@@ -261,6 +262,10 @@ def run_ours(args):
     h2d_bytes = P * 4
     d2h_bytes = P * 4 + h_stats.numel() * 4 + d2h // args.steps
 
+    exchange_kind = "in-kernel all-reduce over NVLink peer memory" if agent.exchange is not None else ("nccl all_reduce" if world > 1 else "none")
+    if agent.exchange is not None and agent.exchange.status() != 0:
+        raise SystemExit("data-parallel exchange: a kernel timed out waiting for a peer rank")
+    agent.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -330,7 +335,7 @@ def run_ours(args):
             "rollout_env_steps_per_s": roll_steps_per_s, "update_samples_per_s": upd_samples_per_s,
             "gae_GBps": gae_gbps, "gae_frac_of_hbm_peak": gae_gbps / hbm_peak,
             "phase_ms": {"rollout": t_roll, "gae": t_gae, "update": t_upd},
-            "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu_baseline, "dp_exchange": exchange_kind,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms,
                     "what": "per step: H2D policy parameters from pinned memory -> ppo.run_update() -> D2H updated "

@@ -194,6 +194,26 @@ int aur_rollout(const aur_rollout_args* args, void* stream);
  *   aur_ppo_update_apply  grad-norm clip + Adam on the flat parameter buffer, statistics
  * The actor and the critic are independent MLPs with separable losses, so half of the
  * CTAs train each net.  Gradients are reduced in a fixed order (deterministic). */
+/* Data-parallel context (one process per GPU, ranks of ONE node): the exchange area of every rank, mapped into
+ * this process with aur_dp_alloc / aur_dp_open.  With world > 1 the update kernels do the gradient all-reduce
+ * themselves over NVLink peer memory: aur_ppo_adv_moments_dp pushes the local advantage moments to every rank,
+ * aur_ppo_update_grad waits for them inside the gradient kernel and pushes its packed [grads | stats] sums,
+ * aur_ppo_update_apply_dp gathers the world's sums in rank order (bit-identical on every rank) and applies
+ * clip + Adam.  seq is the 1-based minibatch counter, the same on every rank.  NULL / world <= 1: single GPU.
+ * This replaces the per-minibatch allreduce a multi-GPU port of ppo.py:266-269 would issue. */
+#define AUR_DP_MAX_RANKS 16
+#define AUR_DP_HANDLE_BYTES 64
+typedef struct {
+  int32_t world, rank;
+  void* peer[AUR_DP_MAX_RANKS];   /* peer[r]: exchange area of rank r (peer[rank] = own allocation) */
+} aur_dp_ctx;
+int64_t aur_dp_area_bytes(const aur_policy_desc* desc);
+int aur_dp_alloc(int64_t bytes, void** area_out, void* ipc_handle_out /* AUR_DP_HANDLE_BYTES */);
+int aur_dp_open(const void* ipc_handle, void** area_out);
+int aur_dp_close(void* area);
+int aur_dp_free(void* area);
+int aur_dp_status(const void* area, void* stream);   /* 0 ok, 1 = a kernel timed out waiting for a peer */
+
 typedef struct {
   aur_policy_desc policy;    /* num_layers == 2 compiled */
   int32_t norm_adv;          /* ppo.py:238 */
@@ -214,6 +234,9 @@ typedef struct {
   const double* adv_moments; /* [3] device: sum, sum of squares, count over the WHOLE minibatch; NULL iff !norm_adv */
   float* workspace;          /* >= aur_ppo_update_workspace_bytes() */
   float* grads_out;          /* [P + 16] */
+  const aur_dp_ctx* dp;      /* NULL: single GPU */
+  uint32_t dp_seq;
+  uint32_t _pad3;
 } aur_update_args;
 
 #define AUR_STAT_POLICY_LOSS 0   /* sums over samples; aur_ppo_update_apply turns them into means */
@@ -236,6 +259,9 @@ int64_t aur_ppo_update_workspace_bytes(const aur_policy_desc* desc);
 int aur_ppo_adv_moments(int64_t m, const int32_t* idx, int64_t idx_offset, const float* advantages,
                         double* moments_out, float* workspace, void* stream);
 
+int aur_ppo_adv_moments_dp(int64_t m, const int32_t* idx, int64_t idx_offset, const float* advantages,
+                           double* moments_out, float* workspace, const aur_dp_ctx* dp, uint32_t seq, void* stream);
+
 int aur_ppo_update_grad(const aur_update_args* args, void* stream);
 
 /* Kernel behind aur_ppo_update_grad: 1 = tcgen05 (bf16 two-term split operands, fp32 TMEM accumulators; the
@@ -247,10 +273,15 @@ int aur_ppo_update_get_impl(void);
 /* params / adam_m / adam_v: [P] fp32 updated in place (torch.optim.Adam single-tensor math, no
  * weight decay, no amsgrad).  step is the 1-based Adam step count.  stats_out [AUR_NUM_STATS]
  * (nullable) receives the minibatch means; entropy_coeff/value_coeff only enter stats_out[LOSS]. */
-int aur_ppo_update_apply(const aur_policy_desc* desc, float* params, const float* grads_packed, float* adam_m,
+int aur_ppo_update_apply(const aur_policy_desc* desc, float* params, float* grads_packed, float* adam_m,
                          float* adam_v, double lr, double beta1, double beta2, double eps, int64_t step,
                          double max_grad_norm, int64_t m_total, double entropy_coeff, double value_coeff,
                          float* stats_out, void* stream);
+/* Data-parallel form: first replaces grads_packed by the sum over all ranks (gathered from the exchange area). */
+int aur_ppo_update_apply_dp(const aur_policy_desc* desc, float* params, float* grads_packed, float* adam_m,
+                            float* adam_v, double lr, double beta1, double beta2, double eps, int64_t step,
+                            double max_grad_norm, int64_t m_total, double entropy_coeff, double value_coeff,
+                            float* stats_out, const aur_dp_ctx* dp, uint32_t seq, void* stream);
 
 /* ------------------------------------------------------ tensor-core core ----
  * C[M,N] (fp32, row-major) = A[M,K] * B[N,K]^T with A, B bf16 row-major (K contiguous), fp32
