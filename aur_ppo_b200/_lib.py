@@ -125,6 +125,9 @@ def lib() -> ctypes.CDLL:
     L.aur_env_reset.argtypes = [c_int32, c_int64, c_int32, ctypes.POINTER(EnvState), c_void_p, c_void_p, c_void_p]
     L.aur_rollout.restype = c_int
     L.aur_rollout.argtypes = [ctypes.POINTER(RolloutArgs), c_void_p]
+    L.aur_squashed_gaussian_sample.restype = c_int
+    L.aur_squashed_gaussian_sample.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_void_p]
     L.aur_shuffle_indices.restype = c_int
     L.aur_shuffle_indices.argtypes = [c_int64, c_uint64, c_uint64, c_void_p, c_void_p]
     L.aur_ppo_update_workspace_bytes.restype = c_int64

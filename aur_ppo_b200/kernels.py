@@ -130,6 +130,26 @@ STAT_NAMES = ["policy_loss", "value_loss", "entropy", "old_approx_kl", "approx_k
 NUM_STATS = 16
 
 
+def squashed_gaussian_sample(mean: torch.Tensor, log_std: torch.Tensor, action: Optional[torch.Tensor] = None, seed: int = 0,
+                             stream_id: int = 0, return_pre_tanh: bool = False):
+    """PPOGaussianPolicyBase.sample (src/nets/nets.py:90-105) -> (action, log_prob [B,1], tanh(mean), entropy [B,A])."""
+    mean, log_std = _f32c(mean, "mean"), _f32c(log_std, "log_std")
+    if mean.dim() != 2 or mean.shape != log_std.shape:
+        raise _lib.AurError("squashed_gaussian_sample: mean and log_std must be [B,A]")
+    if action is not None and _f32c(action, "action").shape != mean.shape:
+        raise _lib.AurError("squashed_gaussian_sample: action must be [B,A]")
+    B, A = mean.shape
+    y, mo, ent = torch.empty_like(mean), torch.empty_like(mean), torch.empty_like(mean)
+    lp = torch.empty(B, 1, device=mean.device)
+    pre = torch.empty_like(mean) if return_pre_tanh else None
+    with torch.cuda.device(mean.device):
+        rc = _lib.lib().aur_squashed_gaussian_sample(B, A, mean.data_ptr(), log_std.data_ptr(), _ptr(action),
+                                                     seed & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFFFFFFFFFF, y.data_ptr(),
+                                                     lp.data_ptr(), mo.data_ptr(), ent.data_ptr(), _ptr(pre), _stream())
+    _lib.check(rc, "aur_squashed_gaussian_sample")
+    return (y, lp, mo, ent, pre) if return_pre_tanh else (y, lp, mo, ent)
+
+
 def shuffle_indices(n: int, seed: int, stream_id: int, device="cuda", out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """`np.random.shuffle(arange(n))` of ppo.py:214-215 as a keyed bijection computed on the device -> int32 [n]."""
     if out is None:

@@ -283,6 +283,15 @@ int aur_ppo_update_apply_dp(const aur_policy_desc* desc, float* params, float* g
                             double max_grad_norm, int64_t m_total, double entropy_coeff, double value_coeff,
                             float* stats_out, const aur_dp_ctx* dp, uint32_t seq, void* stream);
 
+/* ------------------------------------------------ squashed Gaussian head ----
+ * PPOGaussianPolicyBase.sample (src/nets/nets.py:90-105): y = tanh(action), log_prob = sum_k Normal(mean,
+ * exp(log_std)).log_prob(action) - log(1 - y^2 + 1e-6) ([B], the reference keeps dim 1), tanh(mean), and the
+ * unsummed Normal entropy [B,A].  action_in NULL: action = mean + std * N(0,1) from Philox(seed; row, stream_id).
+ * pre_tanh_out (nullable) receives the un-squashed action.  mean / log_std / outputs: [B,A] fp32, A <= 16. */
+int aur_squashed_gaussian_sample(int64_t B, int32_t A, const float* mean, const float* log_std, const float* action_in,
+                                 uint64_t seed, uint64_t stream_id, float* action_out, float* logp_out, float* mean_out,
+                                 float* entropy_out, float* pre_tanh_out, void* stream);
+
 /* ------------------------------------------------------ tensor-core core ----
  * C[M,N] (fp32, row-major) = A[M,K] * B[N,K]^T with A, B bf16 row-major (K contiguous), fp32
  * accumulation in TMEM (tcgen05.mma kind::f16, TMA operand loads).  The dense-contraction core
