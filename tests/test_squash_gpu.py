@@ -31,7 +31,12 @@ def test_squashed_sample_sampled_mode_replays_on_oracle(B, A):
     # replay the drawn pre-tanh actions on the checker
     y2, lp2, mo2, ent2 = R.squashed_sample(mean.cpu(), log_std.cpu(), pre.cpu())
     np.testing.assert_allclose(y.cpu().numpy(), y2.numpy(), rtol=1e-6, atol=1e-7)
-    np.testing.assert_allclose(lp.cpu().numpy(), lp2.numpy(), rtol=1e-5, atol=1e-5)
+    # log(1 - y^2 + 1e-6) is ill-conditioned once tanh saturates (one ulp of y moves it by up to 6e-8 / (1 - y^2 + 1e-6)):
+    # tight tolerance where |action| < 3, conditioning-scaled tolerance elsewhere
+    tame = (pre.abs().max(dim=1).values < 3.0).cpu().numpy()
+    np.testing.assert_allclose(lp.cpu().numpy()[tame], lp2.numpy()[tame], rtol=1e-5, atol=2e-5)
+    cond = (1.2e-7 / (1.0 - y.double() ** 2 + 1e-6)).sum(dim=1, keepdim=True).cpu().numpy()
+    assert (np.abs(lp.cpu().numpy() - lp2.numpy()) <= 2e-5 + 1e-5 * np.abs(lp2.numpy()) + 2 * cond).all()
     np.testing.assert_allclose(ent.cpu().numpy(), ent2.numpy(), rtol=1e-6)
     # and the same rows fed back as given actions reproduce the sampled outputs exactly
     y3, lp3, _, _ = kernels.squashed_gaussian_sample(mean, log_std, pre)
