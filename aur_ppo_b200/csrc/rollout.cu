@@ -13,6 +13,8 @@
 
 namespace aur {
 
+int launch_critic_values_tc(const float* critic, int obs_dim, const float* obs, long long M, float* out, cudaStream_t s);
+
 typedef unsigned __int128 u128;
 
 // ---- PCG64 (setseq 128, XSL-RR) : the generator behind gym's np_random ------------------
@@ -206,7 +208,8 @@ __device__ __forceinline__ void log_episode(const aur_episode_log& log, int t, l
 }
 
 // ENV: CartPole or Pendulum.  E envs per thread (env n = base + e * nthreads_total keeps warps coalesced).
-template <class ENV, int HID, int E>
+// CRITIC = false: the values are filled afterwards by critic_values_tc_kernel (values_tc.cu) from the observation rows.
+template <class ENV, int HID, int E, bool CRITIC>
 __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
   extern __shared__ __align__(16) float smem[];
   const float *sActor, *sCritic, *sLogstd;
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
     // ---- policy.evaluate(next_obs) (ppo.py:105): actor head, critic value
     float head[E][POL_OUT_MAX], value[E];
 #pragma unroll 1
-    for (int net = 0; net < 2; ++net) {
+    for (int net = 0; net < (CRITIC ? 2 : 1); ++net) {
       float o[E][POL_OUT_MAX];
       mlp_forward<HID, E>(net == 0 ? sActor : sCritic, a.nl, net == 0 ? a.act_dim : 1, obs, o, scratch, blockDim.x);
 #pragma unroll
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
         reward = env[e].step(act[0], a.wrappers != 0, terminated);
       }
       a.logp_buf[o] = logp;
-      a.val_buf[o] = value[e];
+      if (CRITIC) a.val_buf[o] = value[e];
       // ---- TimeLimit, RecordEpisodeStatistics (raw reward, fp32 accumulator)
       elapsed[e] += 1;
       const bool truncated = elapsed[e] >= ENV::LIMIT;
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
   }
 
   // ---- write back: next_obs / next_done / env state, and critic(next_obs) for GAE (ppo.py:161)
-  if (a.next_value) {
+  if (CRITIC && a.next_value) {
     float o[E][POL_OUT_MAX];
     mlp_forward<HID, E>(sCritic, a.nl, 1, obs, o, scratch, blockDim.x);
 #pragma unroll
@@ -572,17 +575,28 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
   if (block < 64) block = 64;
   const long long grid = (threads_needed + block - 1) / block;
   const size_t smem = policy_smem_bytes(a.policy, block, a.policy.num_layers >= 3);
-  if (pend) {
-    if ((rc = launch_cfg(rollout_kernel<Pendulum, 64, 1>, smem))) return rc;
-    rollout_kernel<Pendulum, 64, 1><<<(unsigned)grid, block, smem, s>>>(d);
-  } else if (two) {
-    if ((rc = launch_cfg(rollout_kernel<CartPole, 64, 2>, smem))) return rc;
-    rollout_kernel<CartPole, 64, 2><<<(unsigned)grid, block, smem, s>>>(d);
-  } else {
-    if ((rc = launch_cfg(rollout_kernel<CartPole, 64, 1>, smem))) return rc;
-    rollout_kernel<CartPole, 64, 1><<<(unsigned)grid, block, smem, s>>>(d);
-  }
+  // hidden 64 / 2 layers: the critic leaves the sequential kernel and runs as one batched tensor-core pass afterwards
+  const bool split_critic = a.policy.num_layers == 2;
+#define AUR_LAUNCH_ROLLOUT(ENVT, EE)                                                                   \
+  do {                                                                                                 \
+    if (split_critic) {                                                                                \
+      if ((rc = launch_cfg(rollout_kernel<ENVT, 64, EE, false>, smem))) return rc;                     \
+      rollout_kernel<ENVT, 64, EE, false><<<(unsigned)grid, block, smem, s>>>(d);                      \
+    } else {                                                                                           \
+      if ((rc = launch_cfg(rollout_kernel<ENVT, 64, EE, true>, smem))) return rc;                      \
+      rollout_kernel<ENVT, 64, EE, true><<<(unsigned)grid, block, smem, s>>>(d);                       \
+    }                                                                                                  \
+  } while (0)
+  if (pend) AUR_LAUNCH_ROLLOUT(Pendulum, 1);
+  else if (two) AUR_LAUNCH_ROLLOUT(CartPole, 2);
+  else AUR_LAUNCH_ROLLOUT(CartPole, 1);
+#undef AUR_LAUNCH_ROLLOUT
   AUR_LAUNCH_OK("rollout_kernel");
+  if (split_critic) {
+    const float* critic = a.params + net_param_count(a.policy.obs_dim, 64, 2, a.policy.act_dim);
+    if ((rc = launch_critic_values_tc(critic, a.policy.obs_dim, a.obs_buf, (long long)a.T * a.N, a.val_buf, s))) return rc;
+    if (a.next_value && (rc = launch_critic_values_tc(critic, a.policy.obs_dim, a.next_obs, a.N, a.next_value, s))) return rc;
+  }
   return 0;
 }
 

@@ -27,7 +27,7 @@
 //   (h1(t) itself was computed at the end of iteration t-1, ahead of that wait)
 //   gather(t+1) and index(t+2) loads | wait fwd(t) | h2, head, loss | wait aux_w1(t-1) | store dz2(t)
 //   issue bwd(t), wgrad(t), aux_b2(t) | warp-local dW3 passes (overlap the MMAs)
-#include "tc.cuh"
+#include "tc_split.cuh"
 #include "update.cuh"
 
 namespace aur {
@@ -59,23 +59,6 @@ constexpr int T2_TMEM_COLS = 256;           // z / dh 64 (never live together) |
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// 8 fp32 values -> one 16-B chunk of bf16 hi and one of bf16 mid (v - hi), chunk `c` of row `r` (128-B swizzle)
-__device__ __forceinline__ void store_split_chunk(unsigned char* tile_hi, unsigned char* tile_mid, int r, int c, const float* v) {
-  unsigned int hi[4], mid[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float a = v[2 * e], b = v[2 * e + 1];
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    const unsigned int hw = *reinterpret_cast<unsigned int*>(&h);
-    hi[e] = hw;
-    __nv_bfloat162 m = __floats2bfloat162_rn(a - __uint_as_float(hw << 16), b - __uint_as_float(hw & 0xFFFF0000u));
-    mid[e] = *reinterpret_cast<unsigned int*>(&m);
-  }
-  const int off = r * 128 + ((c ^ (r & 7)) << 4);
-  *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(tile_mid + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-}
-
 struct T2Ptrs {
   unsigned char* base;
   __device__ __forceinline__ unsigned char* h1(int part) const { return base + O2_H1 + part * T2_TILE; }
@@ -96,14 +79,6 @@ __device__ __forceinline__ int aux_off(int n, int s) {
   return (s >> 6) * 1024 + n * 128 + (((((s & 63) >> 3) ^ n)) << 4) + (s & 7) * 2;
 }
 
-// three-product split MMA: D (+)= A_hi B_hi + A_hi B_mid + A_mid B_hi over `ksteps` steps of K = 16
-__device__ __forceinline__ void mma_split(uint32_t d, uint64_t a_hi, uint64_t a_mid, uint64_t b_hi, uint64_t b_mid, uint32_t idesc,
-                                          int ksteps, uint32_t a_step, uint32_t b_step, bool accumulate) {
-  for (int k = 0; k < ksteps; ++k)
-    tc::mma_f16(d, a_hi + (uint64_t)(a_step * k), b_hi + (uint64_t)(b_step * k), idesc, (accumulate || k > 0) ? 1u : 0u);
-  for (int k = 0; k < ksteps; ++k) tc::mma_f16(d, a_hi + (uint64_t)(a_step * k), b_mid + (uint64_t)(b_step * k), idesc, 1u);
-  for (int k = 0; k < ksteps; ++k) tc::mma_f16(d, a_mid + (uint64_t)(a_step * k), b_hi + (uint64_t)(b_step * k), idesc, 1u);
-}
 // Contractions over the 128 samples of a tile (K = 8 steps of 16 rows) with only 64 output rows (features): the A
 // descriptor's second 64-row atom is the MID tile (LBO = one tile), so one M = 128 MMA yields hi^T B in accumulator
 // rows 0..63 and mid^T B in rows 64..127; two passes (B_hi, B_mid) give all four split products and the epilogue
