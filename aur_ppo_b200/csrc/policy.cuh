@@ -53,6 +53,15 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return fmaf(-2.0f, r, 1.0f);
 }
 
+// same, for an argument already multiplied by 2 log2(e) (the scale folded into the producing weights / FMA): 4 instructions
+constexpr float TANH_PRESCALE = 2.8853900817779268f;
+__device__ __forceinline__ float tanh_prescaled(float y) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
+
 // h[e][.] = tanh(W0 x + b0)
 template <int HID, int E>
 __device__ __forceinline__ void mlp_first_layer(const float* __restrict__ sW0, const float* __restrict__ sB0,

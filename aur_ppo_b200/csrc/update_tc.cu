@@ -118,10 +118,10 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
     const float* gb3 = gW3 + OUT * 64;
     {
       const int c = tid >> 6, j = tid & 63;
-      sw[S2_W1T + tid] = c < obs_dim ? g[j * obs_dim + c] : 0.0f;
+      sw[S2_W1T + tid] = c < obs_dim ? TANH_PRESCALE * g[j * obs_dim + c] : 0.0f;     // tanh argument scale folded in
       sw[S2_W3 + tid] = tid < OUT * 64 ? gW3[tid] : 0.0f;
     }
-    if (tid < 64) { sw[S2_B1 + tid] = gb1[tid]; sw[S2_B2 + tid] = gb2[tid]; }
+    if (tid < 64) { sw[S2_B1 + tid] = TANH_PRESCALE * gb1[tid]; sw[S2_B2 + tid] = TANH_PRESCALE * gb2[tid]; }
     if (tid < 4) sw[S2_B3 + tid] = tid < OUT ? gb3[tid] : 0.0f;
     {                                                  // W2 row j, 32 columns per thread (block only 4-byte aligned)
       const int j = tid & 63, cq = tid >> 6;
@@ -220,8 +220,8 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
         a01 = __ffma2_rn(make_float2(w.x, w.y), xx, a01);
         a23 = __ffma2_rn(make_float2(w.z, w.w), xx, a23);
       }
-      hv[4 * g] = tanh_fast(a01.x); hv[4 * g + 1] = tanh_fast(a01.y);
-      hv[4 * g + 2] = tanh_fast(a23.x); hv[4 * g + 3] = tanh_fast(a23.y);
+      hv[4 * g] = tanh_prescaled(a01.x); hv[4 * g + 1] = tanh_prescaled(a01.y);
+      hv[4 * g + 2] = tanh_prescaled(a23.x); hv[4 * g + 3] = tanh_prescaled(a23.y);
     }
   };
   float h1n[32];
@@ -313,8 +313,8 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const float4 b = lds4(sw + S2_B2 + f0 + 4 * g);
-      h2[4 * g] = tanh_fast(h2[4 * g] + b.x); h2[4 * g + 1] = tanh_fast(h2[4 * g + 1] + b.y);
-      h2[4 * g + 2] = tanh_fast(h2[4 * g + 2] + b.z); h2[4 * g + 3] = tanh_fast(h2[4 * g + 3] + b.w);
+      h2[4 * g] = tanh_prescaled(fmaf(h2[4 * g], TANH_PRESCALE, b.x)); h2[4 * g + 1] = tanh_prescaled(fmaf(h2[4 * g + 1], TANH_PRESCALE, b.y));
+      h2[4 * g + 2] = tanh_prescaled(fmaf(h2[4 * g + 2], TANH_PRESCALE, b.z)); h2[4 * g + 3] = tanh_prescaled(fmaf(h2[4 * g + 3], TANH_PRESCALE, b.w));
     }
     float outp[POL_OUT_MAX];             // this half's share of the head pre-activations
 #pragma unroll

@@ -45,8 +45,8 @@ __global__ void __launch_bounds__(VT_THREADS, 3) critic_values_tc_kernel(const f
     const float* gb2 = gW2 + 4096;
     const float* gW3 = gb2 + 64;
     const int c = tid >> 6, j = tid & 63;
-    sw[VS_W1T + tid] = c < obs_dim ? critic[j * obs_dim + c] : 0.0f;
-    if (tid < 64) { sw[VS_B1 + tid] = gb1[tid]; sw[VS_B2 + tid] = gb2[tid]; sw[VS_W3 + tid] = gW3[tid]; }
+    sw[VS_W1T + tid] = c < obs_dim ? TANH_PRESCALE * critic[j * obs_dim + c] : 0.0f;      // tanh argument scale folded in
+    if (tid < 64) { sw[VS_B1 + tid] = TANH_PRESCALE * gb1[tid]; sw[VS_B2 + tid] = TANH_PRESCALE * gb2[tid]; sw[VS_W3 + tid] = gW3[tid]; }
     if (tid == 0) sw[VS_B3] = gW3[64];
 #pragma unroll 1
     for (int ch = 2 * c; ch < 2 * c + 2; ++ch) {
@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(VT_THREADS, 3) critic_values_tc_kernel(const f
           a01 = __ffma2_rn(make_float2(w.x, w.y), xx, a01);
           a23 = __ffma2_rn(make_float2(w.z, w.w), xx, a23);
         }
-        hv[4 * g] = tanh_fast(a01.x); hv[4 * g + 1] = tanh_fast(a01.y);
-        hv[4 * g + 2] = tanh_fast(a23.x); hv[4 * g + 3] = tanh_fast(a23.y);
+        hv[4 * g] = tanh_prescaled(a01.x); hv[4 * g + 1] = tanh_prescaled(a01.y);
+        hv[4 * g + 2] = tanh_prescaled(a23.x); hv[4 * g + 3] = tanh_prescaled(a23.y);
       }
       store_split3_chunk(h1t[0], h1t[1], h1t[2], s, 4 * half + c, hv);
     }
@@ -122,8 +122,10 @@ __global__ void __launch_bounds__(VT_THREADS, 3) critic_values_tc_kernel(const f
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const float4 b = lds4(sw + VS_B2 + f0 + 4 * g), w = lds4(sw + VS_W3 + f0 + 4 * g);
-      p0 = fmaf(w.x, tanh_fast(z[4 * g] + b.x), p0); p1 = fmaf(w.y, tanh_fast(z[4 * g + 1] + b.y), p1);
-      p0 = fmaf(w.z, tanh_fast(z[4 * g + 2] + b.z), p0); p1 = fmaf(w.w, tanh_fast(z[4 * g + 3] + b.w), p1);
+      p0 = fmaf(w.x, tanh_prescaled(fmaf(z[4 * g], TANH_PRESCALE, b.x)), p0);
+      p1 = fmaf(w.y, tanh_prescaled(fmaf(z[4 * g + 1], TANH_PRESCALE, b.y)), p1);
+      p0 = fmaf(w.z, tanh_prescaled(fmaf(z[4 * g + 2], TANH_PRESCALE, b.z)), p0);
+      p1 = fmaf(w.w, tanh_prescaled(fmaf(z[4 * g + 3], TANH_PRESCALE, b.w)), p1);
     }
     if (half == 1) xch[s] = p0 + p1;
     tc::fence_before_sync();
