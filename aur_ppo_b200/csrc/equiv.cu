@@ -234,22 +234,29 @@ __global__ void expand_bias_kernel(const float* __restrict__ bias_f, int F, floa
 __global__ void __launch_bounds__(256)
 conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ state, const float* __restrict__ psi,
                     const float* __restrict__ bias_f, int B, __nv_bfloat16* __restrict__ out, unsigned char* __restrict__ pool_arg) {
-  __shared__ float sW[64][2][9];
-  __shared__ float sBias[64];
-  for (int e = threadIdx.x; e < 64 * 18; e += blockDim.x) {
-    const int co = e / 18, rem = e - co * 18, ci = rem / 9, tap = rem - ci * 9;
-    const int o = co >> 2, r = co & 3, y = tap / 3, x = tap - 3 * y;
-    int ys, xs;
-    rot_src(r, y, x, ys, xs);
-    sW[co][ci][tap] = psi[((o * 2 + ci) * 3 + ys) * 3 + xs];
+  // weights of one output channel: 18 taps + bias + pad = 20 floats, read as five warp-uniform LDS.128
+  __shared__ __align__(16) float sW[64][20];
+  for (int e = threadIdx.x; e < 64 * 20; e += blockDim.x) {
+    const int co = e / 20, rem = e - co * 20;
+    float v = 0.0f;
+    if (rem < 18) {
+      const int ci = rem / 9, tap = rem - ci * 9;
+      const int o = co >> 2, r = co & 3, y = tap / 3, x = tap - 3 * y;
+      int ys, xs;
+      rot_src(r, y, x, ys, xs);
+      v = psi[((o * 2 + ci) * 3 + ys) * 3 + xs];
+    } else if (rem == 18) {
+      v = bias_f[co >> 2];
+    }
+    sW[co][rem] = v;
   }
-  if (threadIdx.x < 64) sBias[threadIdx.x] = bias_f[threadIdx.x >> 2];
   __syncthreads();
   const long long total = (long long)B * 64 * 64 * 4;       // pooled pixels x 4 channel groups of 16
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    // px fastest, then the channel group: a warp shares its weights (broadcast loads) and reads adjacent pixels
     long long rr = e;
-    const int cg = (int)(rr & 3); rr >>= 2;
     const int px = (int)(rr & 63); rr >>= 6;
+    const int cg = (int)(rr & 3); rr >>= 2;
     const int py = (int)(rr & 63); rr >>= 6;
     const int b = (int)rr;
     const float st = state[b];
@@ -270,17 +277,23 @@ conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ sta
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       const int co = cg * 16 + c;
+      float wv[20];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&sW[co][4 * q]);
+        wv[4 * q] = w4.x; wv[4 * q + 1] = w4.y; wv[4 * q + 2] = w4.z; wv[4 * q + 3] = w4.w;
+      }
       float best = 0.0f; int bw = 0;
 #pragma unroll
       for (int wy = 0; wy < 2; ++wy)
 #pragma unroll
         for (int wx = 0; wx < 2; ++wx) {
-          float acc = sBias[co];
+          float acc = wv[18];
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const int dy = t / 3, dx = t - 3 * dy;
-            acc = fmaf(sW[co][0][t], p0[wy + dy][wx + dx], acc);
-            acc = fmaf(sW[co][1][t], p1[wy + dy][wx + dx], acc);
+            acc = fmaf(wv[t], p0[wy + dy][wx + dx], acc);
+            acc = fmaf(wv[9 + t], p1[wy + dy][wx + dx], acc);
           }
           acc = fmaxf(acc, 0.0f);
           const int w = wy * 2 + wx;

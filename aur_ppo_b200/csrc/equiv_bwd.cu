@@ -209,7 +209,24 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(long long Q, int C, co
   const int cl = threadIdx.x % c8n, rl = threadIdx.x / c8n;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (rl < rl_n) {
-    for (long long r = (long long)blockIdx.x * rl_n + rl; r < Q; r += (long long)gridDim.x * rl_n) {
+    const long long step = (long long)gridDim.x * rl_n;
+    long long r = (long long)blockIdx.x * rl_n + rl;
+    // four independent 16-B loads in flight per thread (the accumulation order per thread stays row order)
+    for (; r + 3 * step < Q; r += 4 * step) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const uint4*>(in + (r + u * step) * C + cl * 8));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned int w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += __uint_as_float(w[j] << 16);
+          acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+      }
+    }
+    for (; r < Q; r += step) {
       const uint4 v = *reinterpret_cast<const uint4*>(in + r * C + cl * 8);
       const unsigned int w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -233,11 +250,12 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(long long Q, int C, co
 // ---- layer-0 weight gradient fused with its un-pooling ---------------------------------------------
 // dpsi0[o][ci][ys][xs] += sum over pooled pixels of g * in[ci][2py+wy+dy-1][2px+wx+dx-1] routed through the
 // rotation; g = da1[b,py,px,co] where a1 > 0, (wy,wx) = arg.  Thread = output channel, block = pixel strip.
+constexpr int C0W_PIX = 32;               // pooled pixels staged per barrier pair
 __global__ void __launch_bounds__(256)
 conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ state, const __nv_bfloat16* __restrict__ da1,
                    const __nv_bfloat16* __restrict__ a1 /*[B,66,66,64]*/, const unsigned char* __restrict__ arg, int B,
                    float* __restrict__ dw0 /*[64][2][9] expanded-channel gradient*/, float* __restrict__ dbias_ch /*[64]*/) {
-  __shared__ float patch[4][2][4][4];      // 4 pooled pixels per iteration
+  __shared__ float patch[C0W_PIX][2][4][4];
   const int co = threadIdx.x & 63, sub = threadIdx.x >> 6;
   float acc[2][9];
 #pragma unroll
@@ -246,34 +264,48 @@ conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ stat
     for (int t = 0; t < 9; ++t) acc[c][t] = 0.0f;
   float bacc = 0.0f;
   const long long npix = (long long)B * 64 * 64;
-  for (long long base = (long long)blockIdx.x * 4; base < npix; base += (long long)gridDim.x * 4) {
+  for (long long base = (long long)blockIdx.x * C0W_PIX; base < npix; base += (long long)gridDim.x * C0W_PIX) {
     __syncthreads();
-    if (threadIdx.x < 128) {
-      const int pi = threadIdx.x >> 5, e = threadIdx.x & 31, ci = e >> 4, i = (e >> 2) & 3, j = e & 3;
+#pragma unroll
+    for (int q = 0; q < C0W_PIX * 32 / 256; ++q) {
+      const int idx = q * 256 + threadIdx.x;
+      const int pi = idx >> 5, e = idx & 31, ci = e >> 4, i = (e >> 2) & 3, j = e & 3;
       const long long pix = base + pi;
       float v = 0.0f;
       if (pix < npix) {
         const int px = (int)(pix & 63), py = (int)((pix >> 6) & 63), b = (int)(pix >> 12);
         const int yy = 2 * py - 1 + i, xx = 2 * px - 1 + j;
-        if (yy >= 0 && yy < 128 && xx >= 0 && xx < 128) v = ci == 0 ? __ldg(obs + ((size_t)b * 128 + yy) * 128 + xx) : state[b];
+        if (yy >= 0 && yy < 128 && xx >= 0 && xx < 128) v = ci == 0 ? __ldg(obs + ((size_t)b * 128 + yy) * 128 + xx) : __ldg(state + b);
       }
       patch[pi][ci][i][j] = v;
     }
     __syncthreads();
-    const long long pix = base + sub;
-    if (pix < npix) {
-      const int px = (int)(pix & 63), py = (int)((pix >> 6) & 63), b = (int)(pix >> 12);
-      const float act = __bfloat162float(a1[(((size_t)b * 66 + py + 1) * 66 + px + 1) * 64 + co]);
-      if (act > 0.0f) {
-        const float g = __bfloat162float(da1[(size_t)pix * 64 + co]);
-        const int w = arg[(size_t)pix * 64 + co];
-        const int wy = w >> 1, wx = w & 1;
+    // this thread's channel over 8 of the staged pixels; the three per-pixel loads of all 8 are issued up front
+    float av[C0W_PIX / 4], gv[C0W_PIX / 4];
+    int wv[C0W_PIX / 4];
+#pragma unroll
+    for (int k = 0; k < C0W_PIX / 4; ++k) {
+      const long long pix = base + sub + 4 * k;
+      av[k] = 0.0f; gv[k] = 0.0f; wv[k] = 0;
+      if (pix < npix) {
+        const int px = (int)(pix & 63), py = (int)((pix >> 6) & 63), b = (int)(pix >> 12);
+        av[k] = __bfloat162float(a1[(((size_t)b * 66 + py + 1) * 66 + px + 1) * 64 + co]);
+        gv[k] = __bfloat162float(da1[(size_t)pix * 64 + co]);
+        wv[k] = arg[(size_t)pix * 64 + co];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < C0W_PIX / 4; ++k) {
+      if (av[k] > 0.0f) {
+        const float g = gv[k];
+        const int wy = wv[k] >> 1, wx = wv[k] & 1;
+        const float* pp = &patch[sub + 4 * k][0][wy][wx];
         bacc += g;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const int dy = t / 3, dx = t - 3 * dy;
-          acc[0][t] = fmaf(g, patch[sub][0][wy + dy][wx + dx], acc[0][t]);
-          acc[1][t] = fmaf(g, patch[sub][1][wy + dy][wx + dx], acc[1][t]);
+          acc[0][t] = fmaf(g, pp[dy * 4 + dx], acc[0][t]);
+          acc[1][t] = fmaf(g, pp[16 + dy * 4 + dx], acc[1][t]);
         }
       }
     }
@@ -587,7 +619,7 @@ extern "C" int aur_equiv_conv0_wgrad(const float* obs, const float* state, const
   }
   cudaStream_t s = (cudaStream_t)stream;
   AUR_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(float) * (64 * 18 + 64), s));
-  conv0_wgrad_kernel<<<148 * 4, 256, 0, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg, B, scratch,
+  conv0_wgrad_kernel<<<148 * 8, 256, 0, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg, B, scratch,
                                             scratch + 64 * 18);
   AUR_LAUNCH_OK("conv0_wgrad_kernel");
   project_conv0_kernel<<<(64 * 18 + 255) / 256, 256, 0, s>>>(scratch, scratch + 64 * 18, dpsi, dbias_f);
