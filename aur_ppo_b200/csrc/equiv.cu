@@ -234,8 +234,9 @@ __global__ void expand_bias_kernel(const float* __restrict__ bias_f, int F, floa
 __global__ void __launch_bounds__(256)
 conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ state, const float* __restrict__ psi,
                     const float* __restrict__ bias_f, int B, __nv_bfloat16* __restrict__ out, unsigned char* __restrict__ pool_arg) {
-  // weights of one output channel: 18 taps + bias + pad = 20 floats, read as five warp-uniform LDS.128
-  __shared__ __align__(16) float sW[64][20];
+  // weights of a PAIR of output channels interleaved: [pair][18 taps + bias + pad][2], read as ten warp-uniform
+  // LDS.128 and fed to FFMA2 (the two halves are the two channels)
+  __shared__ __align__(16) float sW[32][20][2];
   for (int e = threadIdx.x; e < 64 * 20; e += blockDim.x) {
     const int co = e / 20, rem = e - co * 20;
     float v = 0.0f;
@@ -248,7 +249,7 @@ conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ sta
     } else if (rem == 18) {
       v = bias_f[co >> 2];
     }
-    sW[co][rem] = v;
+    sW[co >> 1][rem][co & 1] = v;
   }
   __syncthreads();
   const long long total = (long long)B * 64 * 64 * 4;       // pooled pixels x 4 channel groups of 16
@@ -275,34 +276,38 @@ conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ sta
     unsigned int packed[8];
     unsigned int argp[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const int co = cg * 16 + c;
-      float wv[20];
+    for (int cp = 0; cp < 8; ++cp) {
+      float2 wv[20];
 #pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const float4 w4 = *reinterpret_cast<const float4*>(&sW[co][4 * q]);
-        wv[4 * q] = w4.x; wv[4 * q + 1] = w4.y; wv[4 * q + 2] = w4.z; wv[4 * q + 3] = w4.w;
+      for (int q = 0; q < 10; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&sW[cg * 8 + cp][2 * q][0]);
+        wv[2 * q] = make_float2(w4.x, w4.y); wv[2 * q + 1] = make_float2(w4.z, w4.w);
       }
-      float best = 0.0f; int bw = 0;
+      float2 best = make_float2(0.0f, 0.0f);
+      int bw0 = 0, bw1 = 0;
 #pragma unroll
       for (int wy = 0; wy < 2; ++wy)
 #pragma unroll
         for (int wx = 0; wx < 2; ++wx) {
-          float acc = wv[18];
+          float2 acc = wv[18];
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const int dy = t / 3, dx = t - 3 * dy;
-            acc = fmaf(wv[t], p0[wy + dy][wx + dx], acc);
-            acc = fmaf(wv[9 + t], p1[wy + dy][wx + dx], acc);
+            const float a0 = p0[wy + dy][wx + dx], a1 = p1[wy + dy][wx + dx];
+            acc = __ffma2_rn(wv[t], make_float2(a0, a0), acc);
+            acc = __ffma2_rn(wv[9 + t], make_float2(a1, a1), acc);
           }
-          acc = fmaxf(acc, 0.0f);
+          acc.x = fmaxf(acc.x, 0.0f); acc.y = fmaxf(acc.y, 0.0f);
           const int w = wy * 2 + wx;
-          if (w == 0 || acc > best) { best = acc; bw = w; }
+          if (w == 0 || acc.x > best.x) { best.x = acc.x; bw0 = w; }
+          if (w == 0 || acc.y > best.y) { best.y = acc.y; bw1 = w; }
         }
-      const __nv_bfloat16 hb = __float2bfloat16(best);
-      const unsigned int bits = (unsigned int)__bfloat16_as_ushort(hb);
-      if (c & 1) packed[c >> 1] |= bits << 16; else packed[c >> 1] = bits;
-      argp[c >> 2] |= (unsigned int)bw << (8 * (c & 3));
+      const unsigned int b0 = (unsigned int)__bfloat16_as_ushort(__float2bfloat16(best.x));
+      const unsigned int b1 = (unsigned int)__bfloat16_as_ushort(__float2bfloat16(best.y));
+      packed[cp] = b0 | (b1 << 16);
+      const int c = 2 * cp;
+      if ((c & 3) == 0) argp[c >> 2] = 0u;
+      argp[c >> 2] |= ((unsigned int)bw0 << (8 * (c & 3))) | ((unsigned int)bw1 << (8 * ((c + 1) & 3)));
     }
     const size_t pix = ((size_t)b * 66 + py + 1) * 66 + px + 1;
     uint4* dst = reinterpret_cast<uint4*>(out + pix * 64 + cg * 16);

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256)
 conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ state, const __nv_bfloat16* __restrict__ da1,
                    const __nv_bfloat16* __restrict__ a1 /*[B,66,66,64]*/, const unsigned char* __restrict__ arg, int B,
                    float* __restrict__ dw0 /*[64][2][9] expanded-channel gradient*/, float* __restrict__ dbias_ch /*[64]*/) {
-  __shared__ float patch[C0W_PIX][2][4][4];
+  __shared__ __align__(16) float patch[C0W_PIX][2][4][4];
   const int co = threadIdx.x & 63, sub = threadIdx.x >> 6;
   float acc[2][9];
 #pragma unroll
@@ -281,31 +281,52 @@ conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ stat
     }
     __syncthreads();
     // this thread's channel over 8 of the staged pixels; the three per-pixel loads of all 8 are issued up front
+    // raw loads first (nothing consumes them inside this loop, so all 24 are in flight together), conversions after
+    unsigned short ar[C0W_PIX / 4], gr[C0W_PIX / 4];
+    unsigned char wr[C0W_PIX / 4];
+    const unsigned short* a1u = reinterpret_cast<const unsigned short*>(a1);
+    const unsigned short* da1u = reinterpret_cast<const unsigned short*>(da1);
+#pragma unroll
+    for (int k = 0; k < C0W_PIX / 4; ++k) {
+      long long pix = base + sub + 4 * k;
+      const bool ok = pix < npix;
+      if (!ok) pix = npix - 1;                         // clamp instead of branching; masked below
+      const int px = (int)(pix & 63), py = (int)((pix >> 6) & 63), b = (int)(pix >> 12);
+      ar[k] = __ldg(a1u + (((size_t)b * 66 + py + 1) * 66 + px + 1) * 64 + co);
+      gr[k] = __ldg(da1u + (size_t)pix * 64 + co);
+      wr[k] = __ldg(arg + (size_t)pix * 64 + co);
+      if (!ok) ar[k] = 0;
+    }
     float av[C0W_PIX / 4], gv[C0W_PIX / 4];
     int wv[C0W_PIX / 4];
 #pragma unroll
     for (int k = 0; k < C0W_PIX / 4; ++k) {
-      const long long pix = base + sub + 4 * k;
-      av[k] = 0.0f; gv[k] = 0.0f; wv[k] = 0;
-      if (pix < npix) {
-        const int px = (int)(pix & 63), py = (int)((pix >> 6) & 63), b = (int)(pix >> 12);
-        av[k] = __bfloat162float(a1[(((size_t)b * 66 + py + 1) * 66 + px + 1) * 64 + co]);
-        gv[k] = __bfloat162float(da1[(size_t)pix * 64 + co]);
-        wv[k] = arg[(size_t)pix * 64 + co];
-      }
+      av[k] = __uint_as_float((unsigned int)ar[k] << 16);
+      gv[k] = __uint_as_float((unsigned int)gr[k] << 16);
+      wv[k] = wr[k];
     }
 #pragma unroll
     for (int k = 0; k < C0W_PIX / 4; ++k) {
-      if (av[k] > 0.0f) {
-        const float g = gv[k];
-        const int wy = wv[k] >> 1, wx = wv[k] & 1;
-        const float* pp = &patch[sub + 4 * k][0][wy][wx];
-        bacc += g;
+      // the 4x4 patch of both channels is warp-uniform: broadcast loads into registers, then the pool window
+      // (wy, wx) of THIS channel picks its 3x3 view with selects (no lane-divergent shared-memory addresses)
+      const float g = av[k] > 0.0f ? gv[k] : 0.0f;
+      const bool wy = (wv[k] >> 1) != 0, wx = (wv[k] & 1) != 0;
+      bacc += g;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const int dy = t / 3, dx = t - 3 * dy;
-          acc[0][t] = fmaf(g, pp[dy * 4 + dx], acc[0][t]);
-          acc[1][t] = fmaf(g, pp[16 + dy * 4 + dx], acc[1][t]);
+      for (int c = 0; c < 2; ++c) {
+        float p[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 r = *reinterpret_cast<const float4*>(&patch[sub + 4 * k][c][i][0]);
+          p[i][0] = r.x; p[i][1] = r.y; p[i][2] = r.z; p[i][3] = r.w;
+        }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          float q[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[j] = wy ? p[dy + 1][j] : p[dy][j];
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) acc[c][dy * 3 + dx] = fmaf(g, wx ? q[dx + 1] : q[dx], acc[c][dy * 3 + dx]);
         }
       }
     }
