@@ -296,7 +296,7 @@ def run_ours(args):
         {"kernel": "gae_bulk_kernel", "bound": "hbm", "achieved": gae_gbps, "peak": hbm_peak, "unit": "GB/s",
          "frac": gae_gbps / hbm_peak, "traffic": traffic.get("gae_bulk_kernel"), "algorithmic_bytes": gae_bytes,
          "ms": t_gae},
-        {"kernel": "rollout_kernel", "bound": "hbm", "achieved": 36.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e9,
+        {"kernel": "rollout_kernel (+ critic_values_tc_kernel)", "bound": "hbm", "achieved": 36.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e9,
          "peak": hbm_peak, "unit": "GB/s", "frac": 36.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e9 / hbm_peak,
          "traffic": traffic.get("rollout_kernel"), "ms": t_roll,
          "fp32_tflops": 17792.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e12,
