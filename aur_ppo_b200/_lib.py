@@ -50,7 +50,8 @@ class UpdateArgs(ctypes.Structure):
                 ("returns", c_void_p), ("values", c_void_p), ("params", c_void_p),
                 ("clip_coeff", ctypes.c_float), ("entropy_coeff", ctypes.c_float), ("value_coeff", ctypes.c_float),
                 ("_pad2", ctypes.c_float), ("adv_moments", c_void_p), ("workspace", c_void_p), ("grads_out", c_void_p),
-                ("dp", c_void_p), ("dp_seq", ctypes.c_uint32), ("_pad3", ctypes.c_uint32)]
+                ("dp", c_void_p), ("dp_seq", ctypes.c_uint32), ("_pad3", ctypes.c_uint32),
+                ("rec_actor", c_void_p), ("rec_critic", c_void_p)]
 
 
 DP_MAX_RANKS = 16
@@ -128,6 +129,8 @@ def lib() -> ctypes.CDLL:
     L.aur_squashed_gaussian_sample.restype = c_int
     L.aur_squashed_gaussian_sample.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p,
                                                c_void_p, c_void_p, c_void_p, c_void_p]
+    L.aur_ppo_pack_records.restype = c_int
+    L.aur_ppo_pack_records.argtypes = [c_int64, c_int32, c_int32] + [c_void_p] * 9
     L.aur_shuffle_indices.restype = c_int
     L.aur_shuffle_indices.argtypes = [c_int64, c_uint64, c_uint64, c_void_p, c_void_p]
     L.aur_ppo_update_workspace_bytes.restype = c_int64

@@ -684,6 +684,9 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
   d.ent_c = u.entropy_coeff; d.vf_c = u.value_coeff; d.inv_m = (float)(1.0 / (double)u.m_total);
   d.moments = u.adv_moments; d.partials = u.workspace;
   { int rc2 = make_dp(u.dp, u.dp_seq, d.dp, "aur_ppo_update_grad"); if (rc2) return rc2; }
+  if ((u.rec_actor != nullptr) != (u.rec_critic != nullptr)) { set_error("aur_ppo_update_grad: give both record arrays or neither"); return AUR_ERR_ARG; }
+  if (u.rec_actor && u.policy.continuous && u.policy.act_dim > 2) { set_error("aur_ppo_update_grad: records hold at most 2 action dims"); return AUR_ERR_ARG; }
+  d.rec_actor = reinterpret_cast<const float4*>(u.rec_actor); d.rec_critic = reinterpret_cast<const float4*>(u.rec_critic);
   static bool attr_set = false;
   if (!attr_set) {
     AUR_CUDA_OK(cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));

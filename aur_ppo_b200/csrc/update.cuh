@@ -68,6 +68,7 @@ struct UpdDev {
   float clip, clip_lo, clip_hi, ent_c, vf_c, inv_m;
   const double* moments;
   float* partials;      // [2][gridDim.x][UPD_PSTRIDE]
+  const float4 *rec_actor, *rec_critic;   // optional packed records (aur_ppo_pack_records): 2 x float4 per sample, else NULL
   DpDev dp;
 };
 

@@ -188,7 +188,13 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
   };
   const long long row_off = a.idx ? 0 : a.idx_offset;
   float xn[POL_IN_PAD];
+  const float4* rec = ACTOR ? a.rec_actor : a.rec_critic;      // packed records: one 32-B sector per sample
   auto fetch_obs = [&](long long row) {
+    if (row >= 0 && rec) {
+      const float4 v = __ldg(rec + 2 * row);
+      xn[0] = v.x; xn[1] = v.y; xn[2] = v.z; xn[3] = v.w;
+      return;
+    }
     if (row >= 0 && obs_vec) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(a.obs) + row);
       xn[0] = v.x; xn[1] = v.y; xn[2] = v.z; xn[3] = v.w;
@@ -296,9 +302,13 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
     rownn = fetch_row(tile + 2LL * ncta);
     fetch_obs(rown);
     // per-sample scalars of this tile (L2 hits: prefetched one tile ago), in flight across the second layer
-    float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
+    float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f, e3 = 0.0f;
     if (half == 0 && valid) {
-      if (ACTOR) {
+      if (rec) {                                       // second half of the record: same sector as the observation
+        const float4 v = __ldg(rec + 2 * row + 1);
+        if (ACTOR) { e2 = v.x; e0 = v.y; e1 = v.z; e3 = v.w; }
+        else { e0 = v.x; e1 = v.y; }
+      } else if (ACTOR) {
         e0 = __ldg(a.logprobs + row); e1 = __ldg(a.advantages + row);
         e2 = __ldg(a.actions + row * (a.continuous ? A : 1));
       } else {
@@ -375,7 +385,7 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
             float act[POL_OUT_MAX];
             act[0] = e2;
 #pragma unroll
-            for (int k = 1; k < POL_OUT_MAX; ++k) act[k] = k < OUT ? __ldg(a.actions + row * OUT + k) : 0.0f;
+            for (int k = 1; k < POL_OUT_MAX; ++k) act[k] = k < OUT ? (rec ? (k == 1 ? e3 : 0.0f) : __ldg(a.actions + row * OUT + k)) : 0.0f;
             normal_logp(out, act, OUT, nc, newlogp, entropy);
 #pragma unroll
             for (int k = 0; k < POL_OUT_MAX; ++k) {

@@ -161,6 +161,26 @@ def shuffle_indices(n: int, seed: int, stream_id: int, device="cuda", out: Optio
     return out
 
 
+def pack_records(b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values, out=None):
+    """Gather-friendly copy of the flattened batch: (rec_actor, rec_critic), each [B,8] fp32 (one 32-byte sector per
+    sample).  Supports obs_dim <= 4 and one or two action columns; returns None otherwise (use the plain arrays)."""
+    for n, t in (("obs", b_obs), ("actions", b_actions), ("logprobs", b_logprobs), ("advantages", b_advantages),
+                 ("returns", b_returns), ("values", b_values)):
+        _f32c(t, n)
+    B, obs_dim = b_obs.shape[0], b_obs.shape[1]
+    act_w = 1 if b_actions.dim() == 1 else b_actions.shape[1]
+    if obs_dim > 4 or act_w > 2:
+        return None
+    if out is None:
+        out = (torch.empty(B, 8, device=b_obs.device), torch.empty(B, 8, device=b_obs.device))
+    with torch.cuda.device(b_obs.device):
+        rc = _lib.lib().aur_ppo_pack_records(B, obs_dim, act_w, b_obs.data_ptr(), b_actions.data_ptr(), b_logprobs.data_ptr(),
+                                             b_advantages.data_ptr(), b_returns.data_ptr(), b_values.data_ptr(),
+                                             out[0].data_ptr(), out[1].data_ptr(), _stream())
+    _lib.check(rc, "aur_ppo_pack_records")
+    return out
+
+
 class Updater:
     """Device state of the optimiser side of ppo.train (src/ppo.py:80,213-269): Adam moments,
     packed gradient buffer, workspace.  `allreduce` (optional) is called on the fp64 advantage
@@ -190,7 +210,7 @@ class Updater:
 
     def grad(self, b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values, idx: Optional[torch.Tensor],
              m_total: Optional[int] = None, idx_offset: int = 0, m_local: Optional[int] = None, clip_coeff=0.2,
-             entropy_coeff=0.01, value_coeff=0.5, norm_adv=True, clip_vloss=True) -> torch.Tensor:
+             entropy_coeff=0.01, value_coeff=0.5, norm_adv=True, clip_vloss=True, records=None) -> torch.Tensor:
         """Phases 1-2 (moments, gather+fwd+loss+bwd+reduce) -> packed [grads | stat sums] on device."""
         import ctypes
         L = _lib.lib()
@@ -224,6 +244,8 @@ class Updater:
             a.adv_moments = self.moments.data_ptr() if norm_adv else None
             a.workspace, a.grads_out = self.workspace.data_ptr(), self.grads.data_ptr()
             a.dp, a.dp_seq = dp, seq
+            if records is not None:
+                a.rec_actor, a.rec_critic = records[0].data_ptr(), records[1].data_ptr()
             _lib.check(L.aur_ppo_update_grad(ctypes.byref(a), st), "aur_ppo_update_grad")
             if self.allreduce is not None:
                 self.allreduce(self.grads)

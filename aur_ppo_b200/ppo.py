@@ -134,6 +134,7 @@ class ppo:
         self.shuffle_seed = int(params.get("shuffle_seed", self.philox_seed))
         self._shuffle_count = self.rank << 40
         self._b_inds = torch.empty(self.local_batch, dtype=torch.int32, device=self.device)
+        self._records = None
         self.total_returns: List[float] = []
         self.total_episode_lengths: List[int] = []
         self.x_indices: List[int] = []
@@ -163,13 +164,19 @@ class ppo:
                            self.envs.next_done, self.gamma, self.gae_lambda, bool(self.gae),
                            out=(self._returns, self._advantages))
 
+    def pack(self, flat_bufs) -> None:
+        """Gather-friendly per-sample records of this iteration's batch (one 32-byte sector per sample and net)."""
+        b_obs, b_logprobs, b_actions, b_advantages, b_returns, b_values = flat_bufs
+        self._records = kernels.pack_records(b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values,
+                                             out=self._records)
+
     def update_minibatch(self, flat_bufs, mb_inds: torch.Tensor) -> torch.Tensor:
         """ppo.py:220-269 for one minibatch of local row indices -> device stats tensor."""
         b_obs, b_logprobs, b_actions, b_advantages, b_returns, b_values = flat_bufs
         self.updater.grad(b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values, mb_inds,
                           m_total=mb_inds.numel() * self.world_size, clip_coeff=self.clip_coeff,
                           entropy_coeff=self.entropy_coeff, value_coeff=self.value_coeff, norm_adv=bool(self.norm_adv),
-                          clip_vloss=bool(self.clip_vloss))
+                          clip_vloss=bool(self.clip_vloss), records=self._records)
         return self.optimizer.step(max_grad_norm=self.max_grad_norm)
 
     def run_update(self, update: int) -> Dict[str, torch.Tensor]:
@@ -180,6 +187,7 @@ class ppo:
         self.rollout()
         returns, advantages = self.advantages()
         flat_bufs = self.buffer.flatten(returns, advantages)
+        self.pack(flat_bufs)
         n_mb = 0
         stats_rows = self._stats_rows
         for ep in range(self.num_update_epochs):

@@ -209,6 +209,7 @@ def run_ours(args):
         returns, advantages = agent.advantages()
         ev[k][2].record()
         flat_bufs = agent.buffer.flatten(returns, advantages)
+        agent.pack(flat_bufs)
         for ep in range(EPOCHS):
             b_inds = kernels.shuffle_indices(agent.local_batch, seed=agent.shuffle_seed, stream_id=agent._shuffle_count,
                                              out=agent._b_inds)

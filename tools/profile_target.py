@@ -23,8 +23,10 @@ if "update" in which:
     ret, adv = kernels.gae(buf.rewards, buf.values, buf.terminals, buf.next_value, env.next_done, 0.99, 0.95, True, out)
     up = kernels.Updater(desc, flat.clone())
     idx = torch.randperm(N * T, device="cuda")[: N * T // 4].to(torch.int32)
+    flat_bufs = (buf.states.reshape(-1, 4), buf.actions.reshape(-1), buf.log_probs.reshape(-1), adv.reshape(-1),
+                 ret.reshape(-1), buf.values.reshape(-1))
+    rec = kernels.pack_records(*flat_bufs)
     for i in range(3):
-        up.step(buf.states.reshape(-1, 4), buf.actions.reshape(-1), buf.log_probs.reshape(-1), adv.reshape(-1),
-                ret.reshape(-1), buf.values.reshape(-1), idx, lr=2.5e-4)
+        up.step(*flat_bufs, idx, lr=2.5e-4, records=rec)
 torch.cuda.synchronize()
 print("profile target done")
