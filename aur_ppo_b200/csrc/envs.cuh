@@ -1,0 +1,203 @@
+// Device-side environments and their bookkeeping, shared by the rollout kernels (rollout.cu, rollout_tc.cu):
+// PCG64 reset streams, gym's CartPole-v1 / Pendulum-v1 dynamics, the continuous wrapper stack's running statistics,
+// the kernel argument block and the episode log.  Third-party behaviour restated from gym 0.26.2.
+#pragma once
+#include "det_sincos.h"
+#include "policy.cuh"
+
+namespace aur {
+
+typedef unsigned __int128 u128;
+
+// ---- PCG64 (setseq 128, XSL-RR) : the generator behind gym's np_random ------------------
+struct Pcg64 {
+  u128 state, inc;
+  __device__ __forceinline__ void load(const uint64_t* pcg, long long N, long long n) {
+    state = ((u128)pcg[0 * N + n] << 64) | pcg[1 * N + n];
+    inc = ((u128)pcg[2 * N + n] << 64) | pcg[3 * N + n];
+  }
+  __device__ __forceinline__ void store(uint64_t* pcg, long long N, long long n) const {
+    pcg[0 * N + n] = (uint64_t)(state >> 64);
+    pcg[1 * N + n] = (uint64_t)state;
+  }
+  __device__ __forceinline__ double next_double() {
+    const u128 MULT = ((u128)0x2360ED051FC65DA4ULL << 64) | 0x4385DF649FCCF645ULL;
+    state = state * MULT + inc;
+    const uint64_t hi = (uint64_t)(state >> 64), lo = (uint64_t)state;
+    const uint64_t x = hi ^ lo;
+    const unsigned rot = (unsigned)(hi >> 58);
+    const uint64_t r = (x >> rot) | (x << ((64u - rot) & 63u));
+    return (double)(r >> 11) * (1.0 / 9007199254740992.0);
+  }
+  // Generator.uniform(low, high) = low + (high - low) * next_double
+  __device__ __forceinline__ double uniform(double low, double range) { return low + range * next_double(); }
+};
+
+// ---- RunningMeanStd.update with batch_count == 1 (gym/wrappers/normalize.py) ------------
+__device__ __forceinline__ void rms_update1(double& mean, double& var, double count, double x) {
+  const double delta = x - mean;
+  const double tot = count + 1.0;
+  const double new_mean = mean + delta * 1.0 / tot;
+  const double m_a = var * count;
+  const double M2 = m_a + 0.0 + delta * delta * count * 1.0 / tot;
+  mean = new_mean;
+  var = M2 / tot;
+}
+__device__ __forceinline__ double clip10(double z) { return z < -10.0 ? -10.0 : (z > 10.0 ? 10.0 : z); }
+
+// Wrapper statistics of one env: obs mean[3], var[3], count; return-rms mean, var, count; acc.
+struct NormState {
+  double om[3], ov[3], oc, rm, rv, rc, racc;
+  __device__ __forceinline__ void init() {
+    for (int k = 0; k < 3; ++k) { om[k] = 0.0; ov[k] = 1.0; }
+    oc = 1e-4; rm = 0.0; rv = 1.0; rc = 1e-4; racc = 0.0;
+  }
+  __device__ __forceinline__ void load(const double* g, long long N, long long n) {
+    for (int k = 0; k < 3; ++k) { om[k] = g[k * N + n]; ov[k] = g[(3 + k) * N + n]; }
+    oc = g[6 * N + n]; rm = g[7 * N + n]; rv = g[8 * N + n]; rc = g[9 * N + n]; racc = g[10 * N + n];
+  }
+  __device__ __forceinline__ void store(double* g, long long N, long long n) const {
+    for (int k = 0; k < 3; ++k) { g[k * N + n] = om[k]; g[(3 + k) * N + n] = ov[k]; }
+    g[6 * N + n] = oc; g[7 * N + n] = rm; g[8 * N + n] = rv; g[9 * N + n] = rc; g[10 * N + n] = racc;
+  }
+  // NormalizeObservation.normalize + clip(-10, 10), result cast to the fp32 obs buffer
+  __device__ __forceinline__ void obs(const float (&raw)[3], float (&out)[POL_IN_PAD]) {
+    for (int k = 0; k < 3; ++k) rms_update1(om[k], ov[k], oc, (double)raw[k]);
+    oc = oc + 1.0;
+    for (int k = 0; k < 3; ++k) out[k] = (float)clip10(((double)raw[k] - om[k]) / sqrt(ov[k] + 1e-8));
+    out[3] = 0.0f;
+  }
+  // NormalizeReward.step + clip(-10, 10)
+  __device__ __forceinline__ double reward(double r, bool done, double gamma) {
+    racc = racc * gamma + r;
+    rms_update1(rm, rv, rc, racc);
+    rc = rc + 1.0;
+    double out = r / sqrt(rv + 1e-8);
+    if (done) racc = 0.0;
+    return clip10(out);
+  }
+};
+
+// ---- CartPole-v1 (gym/envs/classic_control/cartpole.py) ----------------------------------
+struct CartPole {
+  static constexpr int S = 4, OBS = 4, LIMIT = 500;
+  double x, xd, th, thd;
+  __device__ __forceinline__ void load(const double* g, long long N, long long n) {
+    x = g[n]; xd = g[N + n]; th = g[2 * N + n]; thd = g[3 * N + n];
+  }
+  __device__ __forceinline__ void store(double* g, long long N, long long n) const {
+    g[n] = x; g[N + n] = xd; g[2 * N + n] = th; g[3 * N + n] = thd;
+  }
+  __device__ __forceinline__ void reset(Pcg64& rng) {
+    x = rng.uniform(-0.05, 0.05 - (-0.05)); xd = rng.uniform(-0.05, 0.05 - (-0.05));
+    th = rng.uniform(-0.05, 0.05 - (-0.05)); thd = rng.uniform(-0.05, 0.05 - (-0.05));
+  }
+  __device__ __forceinline__ void raw_obs(float (&o)[POL_IN_PAD]) const {
+    o[0] = (float)x; o[1] = (float)xd; o[2] = (float)th; o[3] = (float)thd;
+  }
+  // returns reward; sets terminated
+  __device__ __forceinline__ double step(int action, bool& terminated) {
+    const double gravity = 9.8, masscart = 1.0, masspole = 0.1, length = 0.5, force_mag = 10.0, tau = 0.02;
+    const double total_mass = masspole + masscart, polemass_length = masspole * length;
+    const double theta_thr = 12 * 2 * 3.141592653589793 / 360, x_thr = 2.4;
+    const double force = action == 1 ? force_mag : -force_mag;
+    double sintheta, costheta;
+    aur_sincos(th, &sintheta, &costheta);
+    const double temp = (force + polemass_length * (thd * thd) * sintheta) / total_mass;
+    const double thetaacc = (gravity * sintheta - costheta * temp) /
+                            (length * (4.0 / 3.0 - masspole * (costheta * costheta) / total_mass));
+    const double xacc = temp - polemass_length * thetaacc * costheta / total_mass;
+    x = x + tau * xd;
+    xd = xd + tau * xacc;
+    th = th + tau * thd;
+    thd = thd + tau * thetaacc;
+    terminated = (x < -x_thr) || (x > x_thr) || (th < -theta_thr) || (th > theta_thr);
+    return 1.0;
+  }
+};
+
+// ---- Pendulum-v1 (gym/envs/classic_control/pendulum.py, g = 10) --------------------------
+struct Pendulum {
+  static constexpr int S = 2, OBS = 3, LIMIT = 200;
+  double th, thd;
+  double s_th, c_th;   // sin/cos of the CURRENT theta (the obs needs them, the next step reuses sin)
+  __device__ __forceinline__ void load(const double* g, long long N, long long n) {
+    th = g[n]; thd = g[N + n];
+    aur_sincos(th, &s_th, &c_th);
+  }
+  __device__ __forceinline__ void store(double* g, long long N, long long n) const { g[n] = th; g[N + n] = thd; }
+  __device__ __forceinline__ void reset(Pcg64& rng) {
+    const double PI = 3.141592653589793;
+    th = rng.uniform(-PI, PI - (-PI));
+    thd = rng.uniform(-1.0, 1.0 - (-1.0));
+    aur_sincos(th, &s_th, &c_th);
+  }
+  __device__ __forceinline__ void raw_obs(float (&o)[3]) const { o[0] = (float)c_th; o[1] = (float)s_th; o[2] = (float)thd; }
+  __device__ __forceinline__ double step(float u_in, bool clip_action, bool& terminated) {
+    const double max_speed = 8.0, dt = 0.05, g = 10.0, m = 1.0, l = 1.0, PI = 3.141592653589793;
+    float u = u_in;
+    if (clip_action) u = u < -2.0f ? -2.0f : (u > 2.0f ? 2.0f : u);   // ClipAction wrapper
+    u = u < -2.0f ? -2.0f : (u > 2.0f ? 2.0f : u);                    // np.clip(u, -max_torque, max_torque)
+    const float usq = __fmul_rn(u, u);
+    const double twopi = 2 * PI;
+    double an = fmod(th + PI, twopi);
+    if (an != 0.0 && an < 0.0) an += twopi;
+    an = an - PI;
+    const double costs = an * an + 0.1 * (thd * thd) + 0.001 * (double)usq;
+    double newthd = thd + (3 * g / (2 * l) * s_th + 3.0 / (m * (l * l)) * (double)u) * dt;
+    newthd = newthd < -max_speed ? -max_speed : (newthd > max_speed ? max_speed : newthd);
+    th = th + newthd * dt;
+    thd = newthd;
+    aur_sincos(th, &s_th, &c_th);
+    terminated = false;
+    return -costs;
+  }
+};
+
+struct RolloutDev {
+  long long N;
+  int T, wrappers;
+  int obs_dim, act_dim, nl, continuous;
+  const float* params;
+  aur_env_state env;
+  float *obs_buf, *act_buf, *logp_buf, *val_buf, *rew_buf, *done_buf, *next_obs, *next_done, *next_value;
+  const float* actions_in;
+  uint64_t seed, step0, env_id0;
+  aur_episode_log log;
+  double gamma;
+};
+
+template <int HID>
+__device__ __forceinline__ void load_policy_smem(float* smem, const RolloutDev& a, const float*& sActor,
+                                                 const float*& sCritic, const float*& sLogstd) {
+  const int nA = net_smem_floats(HID, a.nl, a.act_dim), nC = net_smem_floats(HID, a.nl, 1);
+  const int64_t gA = net_param_count(a.obs_dim, HID, a.nl, a.act_dim), gC = net_param_count(a.obs_dim, HID, a.nl, 1);
+  load_net_to_smem(smem, a.params, a.obs_dim, HID, a.nl, a.act_dim, threadIdx.x, blockDim.x);
+  load_net_to_smem(smem + nA, a.params + gA, a.obs_dim, HID, a.nl, 1, threadIdx.x, blockDim.x);
+  if (a.continuous && threadIdx.x < POL_OUT_MAX)
+    smem[nA + nC + threadIdx.x] = threadIdx.x < a.act_dim ? a.params[gA + gC + threadIdx.x] : 0.0f;
+  sActor = smem; sCritic = smem + nA; sLogstd = smem + nA + nC;
+}
+
+__device__ __forceinline__ void log_episode(const aur_episode_log& log, int t, long long local_env, int step, int env,
+                                            float ret, int len) {
+  if (log.first_finished) {
+    const unsigned long long key = ((unsigned long long)local_env << 41) | ((unsigned long long)(len & 511) << 32) |
+                                   (unsigned long long)__float_as_uint(ret);
+    atomicMin(log.first_finished + t, key);
+  }
+  if (log.totals) {
+    atomicAdd(log.totals + 0, 1.0);
+    atomicAdd(log.totals + 1, (double)ret);
+    atomicAdd(log.totals + 2, (double)len);
+  }
+  if (!log.count) return;
+  const uint32_t idx = atomicAdd(log.count, 1u);
+  if (log.entries && idx < log.capacity) {
+    int4 v = make_int4(step, env, __float_as_int(ret), len);
+    *reinterpret_cast<int4*>(&log.entries[idx]) = v;
+  }
+}
+
+
+}  // namespace aur

@@ -1,0 +1,279 @@
+// Fused rollout with the actor's hidden layer on tensor cores (rows R, Ec, Ep, Ev, M, D; hidden 64, 2 layers).
+// Same contract as rollout_kernel (rollout.cu): T env steps x N envs in one launch, env state in registers, fp64
+// physics bit-identical to the checker, Philox sampling keyed by the global env id.  The difference is where the
+// 64x64 layer of the actor runs: a CTA owns 128 envs (thread = env = TMEM lane), every step the threads write their
+// h1 row as a bf16 hi/mid split into a 128-B-swizzled tile, ONE tcgen05 MMA batch (four split products, fp32
+// accumulate in TMEM) produces z2 for all 128 envs, and each thread reads its row back (tcgen05.ld 32x32b) for tanh,
+// head, sampling and the env step.  Four CTAs per SM (52 KB of shared memory, 64 TMEM columns each) interleave
+// their per-step MMA round trips.  The critic is not evaluated here (critic_values_tc_kernel does all T*N values).
+#include <stdlib.h>
+
+#include "envs.cuh"
+#include "tc_split.cuh"
+
+namespace aur {
+
+constexpr int RT_S = 128;
+constexpr int RT_TILE = RT_S * 128, RT_WTILE = 64 * 128;
+constexpr int RO_H1 = 0;                          // [hi][mid]
+constexpr int RO_W2 = RO_H1 + 2 * RT_TILE;        // [hi][mid]
+constexpr int RO_SMALL = RO_W2 + 2 * RT_WTILE;    // fp32: W1^T [4][64] and b1, b2 pre-scaled for tanh, W3 [4][64], b3 [4], logstd [4]
+constexpr int RO_BAR = RO_SMALL + 768 * 4;
+constexpr size_t RT_SMEM = RO_BAR + 64 + 1024;
+constexpr int RS_W1T = 0, RS_B1 = 256, RS_B2 = 320, RS_W3 = 384, RS_B3 = 640, RS_LS = 644;
+
+template <class ENV>
+__global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* h1t[2] = {base + RO_H1, base + RO_H1 + RT_TILE};
+  unsigned char* w2t[2] = {base + RO_W2, base + RO_W2 + RT_WTILE};
+  float* sw = reinterpret_cast<float*>(base + RO_SMALL);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + RO_BAR);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(base + RO_BAR + 32);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr bool PEND = ENV::OBS == 3;
+  const int A = a.act_dim, obs_dim = a.obs_dim;
+
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  if (warp == 0) tc::tmem_alloc(tslot, 64);
+  {
+    const float* g = a.params;                    // the actor comes first in the flat buffer
+    const float* gb1 = g + 64 * obs_dim;
+    const float* gW2 = gb1 + 64;
+    const float* gb2 = gW2 + 4096;
+    const float* gW3 = gb2 + 64;
+    const float* gb3 = gW3 + A * 64;
+    for (int e = tid; e < 256; e += RT_S) {
+      const int c = e >> 6, j = e & 63;
+      sw[RS_W1T + e] = c < obs_dim ? TANH_PRESCALE * g[j * obs_dim + c] : 0.0f;
+      sw[RS_W3 + e] = e < A * 64 ? gW3[e] : 0.0f;
+    }
+    if (tid < 64) { sw[RS_B1 + tid] = TANH_PRESCALE * gb1[tid]; sw[RS_B2 + tid] = TANH_PRESCALE * gb2[tid]; }
+    if (tid < 4) {
+      sw[RS_B3 + tid] = tid < A ? gb3[tid] : 0.0f;
+      const int64_t gA = net_param_count(obs_dim, 64, 2, A), gC = net_param_count(obs_dim, 64, 2, 1);
+      sw[RS_LS + tid] = (a.continuous && tid < A) ? a.params[gA + gC + tid] : 0.0f;
+    }
+    const int j = tid & 63, c0 = 4 * (tid >> 6);
+#pragma unroll 1
+    for (int ch = c0; ch < c0 + 4; ++ch) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = gW2[j * 64 + 8 * ch + e];
+      store_split_chunk(w2t[0], w2t[1], j, ch, v);
+    }
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tm_z = *tslot;
+  const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+  constexpr uint32_t ID_FWD = tc::instr_desc(tc::FMT_BF16, 128, 64, 0, 0);
+
+  const long long N = a.N;
+  const long long n = (long long)blockIdx.x * RT_S + tid;
+  const bool live = n < N;
+  const long long m0 = live ? n : 0;
+  ENV env;
+  NormState nm;
+  float obs[POL_IN_PAD];
+  env.load(a.env.phys, N, m0);
+  int elapsed = a.env.elapsed[m0], ep_len = a.env.ep_length[m0];
+  float ep_ret = a.env.ep_return[m0], done_prev = a.next_done[m0];
+#pragma unroll
+  for (int k = 0; k < POL_IN_PAD; ++k) obs[k] = k < ENV::OBS ? a.next_obs[m0 * ENV::OBS + k] : 0.0f;
+  if constexpr (PEND) { if (a.wrappers) nm.load(a.env.norm, N, m0); }
+  NormalConsts nc;
+  if (a.continuous) nc = normal_consts(sw + RS_LS, A);
+
+  for (int t = 0; t < a.T; ++t) {
+    const size_t o = (size_t)t * (size_t)N + (size_t)n;
+    // ---- buffer.states[t] = next_obs; buffer.terminals[t] = next_done (ppo.py:203-204)
+    if (live) {
+      if constexpr (ENV::OBS == 4) {
+        *reinterpret_cast<float4*>(a.obs_buf + o * 4) = make_float4(obs[0], obs[1], obs[2], obs[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < ENV::OBS; ++k) a.obs_buf[o * ENV::OBS + k] = obs[k];
+      }
+      a.done_buf[o] = done_prev;
+    }
+    // ---- actor, first layer: this env's h1 row straight into the operand tile (8-feature chunks)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float hv[8];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int f = 8 * c + 4 * g;
+        const float4 b = lds4(sw + RS_B1 + f);
+        float2 a01 = make_float2(b.x, b.y), a23 = make_float2(b.z, b.w);
+#pragma unroll
+        for (int cc = 0; cc < POL_IN_PAD; ++cc) {
+          const float4 w = lds4(sw + RS_W1T + cc * 64 + f);
+          const float2 xx = make_float2(obs[cc], obs[cc]);
+          a01 = __ffma2_rn(make_float2(w.x, w.y), xx, a01);
+          a23 = __ffma2_rn(make_float2(w.z, w.w), xx, a23);
+        }
+        hv[4 * g] = tanh_prescaled(a01.x); hv[4 * g + 1] = tanh_prescaled(a01.y);
+        hv[4 * g + 2] = tanh_prescaled(a23.x); hv[4 * g + 3] = tanh_prescaled(a23.y);
+      }
+      store_split_chunk(h1t[0], h1t[1], tid, c, hv);
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();                               // also: every thread has read last step's z2 out of TMEM
+    if (tid == 0) {
+      tc::fence_after_sync();
+      mma_split4(tm_z, tc::smem_desc_k_sw128(h1t[0]), tc::smem_desc_k_sw128(h1t[1]), tc::smem_desc_k_sw128(w2t[0]),
+                 tc::smem_desc_k_sw128(w2t[1]), ID_FWD, 4, 2, 2, false);
+      tc::mma_commit(bar);
+    }
+    // the step's random numbers do not depend on the logits: draw them while the MMAs run
+    const uint64_t gid = a.env_id0 + (uint64_t)n, gstep = a.step0 + (uint64_t)t;
+    Philox rnd;
+    rnd.c[0] = rnd.c[1] = rnd.c[2] = rnd.c[3] = 0u;
+    if (a.actions_in == nullptr)
+      rnd = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)gstep, (uint32_t)(gstep >> 32), (uint32_t)a.seed,
+                          (uint32_t)(a.seed >> 32));
+    mbar_wait(bar, (uint32_t)t & 1u);
+    tc::fence_after_sync();
+    // ---- second layer activation + head from this env's TMEM lane
+    float head[POL_OUT_MAX];
+#pragma unroll
+    for (int k = 0; k < POL_OUT_MAX; ++k) head[k] = sw[RS_B3 + k];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t zr[16];
+      tc::tmem_ld16(tm_z + lane_base + 16 * c, zr);
+      float h2[16];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float4 b = lds4(sw + RS_B2 + 16 * c + 4 * g);
+        h2[4 * g] = tanh_prescaled(fmaf(__uint_as_float(zr[4 * g]), TANH_PRESCALE, b.x));
+        h2[4 * g + 1] = tanh_prescaled(fmaf(__uint_as_float(zr[4 * g + 1]), TANH_PRESCALE, b.y));
+        h2[4 * g + 2] = tanh_prescaled(fmaf(__uint_as_float(zr[4 * g + 2]), TANH_PRESCALE, b.z));
+        h2[4 * g + 3] = tanh_prescaled(fmaf(__uint_as_float(zr[4 * g + 3]), TANH_PRESCALE, b.w));
+      }
+#pragma unroll
+      for (int k = 0; k < POL_OUT_MAX; ++k) {
+        if (k < A) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 w = lds4(sw + RS_W3 + k * 64 + 16 * c + 4 * g);
+            head[k] = fmaf(w.x, h2[4 * g], head[k]); head[k] = fmaf(w.y, h2[4 * g + 1], head[k]);
+            head[k] = fmaf(w.z, h2[4 * g + 2], head[k]); head[k] = fmaf(w.w, h2[4 * g + 3], head[k]);
+          }
+        }
+      }
+    }
+    if (!live) continue;
+    // ---- distribution, env step, bookkeeping: as rollout_kernel (rollout.cu)
+    float logp, entropy, reward32;
+    bool terminated;
+    double reward;
+    if constexpr (!PEND) {
+      int action;
+      const bool sample = a.actions_in == nullptr;
+      float u = 0.0f;
+      if (sample) { u = u01_24(rnd.c[0]); action = 0; }
+      else action = (int)a.actions_in[o];
+      categorical(head, A, sample, u, action, logp, entropy);
+      a.act_buf[o] = (float)action;
+      reward = env.step(action, terminated);
+    } else {
+      float act[POL_OUT_MAX] = {0.f, 0.f, 0.f, 0.f};
+      if (a.actions_in == nullptr) {
+        float z[POL_OUT_MAX];
+        normal4(rnd, z);
+#pragma unroll
+        for (int k = 0; k < POL_OUT_MAX; ++k) act[k] = fmaf(nc.std[k], z[k], head[k]);
+      } else {
+        for (int k = 0; k < A; ++k) act[k] = a.actions_in[o * A + k];
+      }
+      normal_logp(head, act, A, nc, logp, entropy);
+      for (int k = 0; k < A; ++k) a.act_buf[o * A + k] = act[k];
+      reward = env.step(act[0], a.wrappers != 0, terminated);
+    }
+    a.logp_buf[o] = logp;
+    // ---- TimeLimit, RecordEpisodeStatistics (raw reward, fp32 accumulator)
+    elapsed += 1;
+    const bool truncated = elapsed >= ENV::LIMIT;
+    ep_ret = __fadd_rn(ep_ret, (float)reward);
+    ep_len += 1;
+    const bool finished = terminated || truncated;
+    if constexpr (PEND) {
+      float raw[3];
+      env.raw_obs(raw);
+      if (a.wrappers) {
+        nm.obs(raw, obs);
+        reward = nm.reward(reward, finished, a.gamma);
+      } else {
+        obs[0] = raw[0]; obs[1] = raw[1]; obs[2] = raw[2]; obs[3] = 0.0f;
+      }
+    } else {
+      env.raw_obs(obs);
+    }
+    reward32 = (float)reward;                        // torch.tensor(reward) fp64 -> fp32 buffer (ppo.py:111)
+    a.rew_buf[o] = reward32;
+    if (finished) {
+      // ---- SyncVectorEnv autoreset: the returned obs is the RESET obs; `done` keeps `terminated`
+      log_episode(a.log, t, n, (int)gstep, (int)gid, ep_ret, ep_len);
+      Pcg64 rng;
+      rng.load(a.env.pcg, N, n);
+      env.reset(rng);
+      rng.store(a.env.pcg, N, n);
+      elapsed = 0; ep_ret = 0.0f; ep_len = 0;
+      if constexpr (PEND) {
+        float raw[3];
+        env.raw_obs(raw);
+        if (a.wrappers) nm.obs(raw, obs);
+        else { obs[0] = raw[0]; obs[1] = raw[1]; obs[2] = raw[2]; obs[3] = 0.0f; }
+      } else {
+        env.raw_obs(obs);
+      }
+    }
+    done_prev = terminated ? 1.0f : 0.0f;            // ppo.py:110 keeps `terminated`, drops `truncated`
+  }
+
+  if (live) {
+    env.store(a.env.phys, N, n);
+    a.env.elapsed[n] = elapsed; a.env.ep_return[n] = ep_ret; a.env.ep_length[n] = ep_len;
+    a.next_done[n] = done_prev;
+#pragma unroll
+    for (int k = 0; k < ENV::OBS; ++k) a.next_obs[n * ENV::OBS + k] = obs[k];
+    if constexpr (PEND) { if (a.wrappers) nm.store(a.env.norm, N, n); }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tm_z, 64);
+}
+
+// 1 = tensor-core rollout (default for hidden 64 / 2 layers), 0 = SIMT rollout_kernel; AUR_ROLLOUT_IMPL=simt|tc
+int rollout_impl() {
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("AUR_ROLLOUT_IMPL");
+    impl = e ? ((e[0] == 's' || e[0] == '0') ? 0 : 1) : 1;
+  }
+  return impl;
+}
+
+int launch_rollout_tc(const RolloutDev& d, bool pendulum, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<CartPole>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM));
+    AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<Pendulum>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM));
+    AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<CartPole>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<Pendulum>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr = true;
+  }
+  const unsigned grid = (unsigned)((d.N + RT_S - 1) / RT_S);
+  if (pendulum) rollout_tc_kernel<Pendulum><<<grid, RT_S, RT_SMEM, s>>>(d);
+  else rollout_tc_kernel<CartPole><<<grid, RT_S, RT_SMEM, s>>>(d);
+  AUR_LAUNCH_OK("rollout_tc_kernel");
+  return 0;
+}
+
+}  // namespace aur
