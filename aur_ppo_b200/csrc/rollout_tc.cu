@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
   ENV env;
   NormState nm;
   float obs[POL_IN_PAD];
+  Pcg64 rng;                                     // reset stream in registers: a reset costs no global round trip
+  rng.load(a.env.pcg, N, m0);
   env.load(a.env.phys, N, m0);
   int elapsed = a.env.elapsed[m0], ep_len = a.env.ep_length[m0];
   float ep_ret = a.env.ep_return[m0], done_prev = a.next_done[m0];
@@ -220,10 +222,7 @@ __global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
     if (finished) {
       // ---- SyncVectorEnv autoreset: the returned obs is the RESET obs; `done` keeps `terminated`
       log_episode(a.log, t, n, (int)gstep, (int)gid, ep_ret, ep_len);
-      Pcg64 rng;
-      rng.load(a.env.pcg, N, n);
       env.reset(rng);
-      rng.store(a.env.pcg, N, n);
       elapsed = 0; ep_ret = 0.0f; ep_len = 0;
       if constexpr (PEND) {
         float raw[3];
@@ -238,6 +237,7 @@ __global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
   }
 
   if (live) {
+    rng.store(a.env.pcg, N, n);
     env.store(a.env.phys, N, n);
     a.env.elapsed[n] = elapsed; a.env.ep_return[n] = ep_ret; a.env.ep_length[n] = ep_len;
     a.next_done[n] = done_prev;

@@ -71,7 +71,8 @@ class DeviceVecEnv:
         if self.first_finished is None or self.first_finished.numel() != T:
             self.first_finished = torch.empty(T, dtype=torch.int64, device=self.device)
         self.first_finished.fill_(-1)          # all ones
-        return _lib.EpisodeLog(self.log_entries.data_ptr() if self.log_capacity else None, self.log_count.data_ptr(),
+        return _lib.EpisodeLog(self.log_entries.data_ptr() if self.log_capacity else None,
+                               self.log_count.data_ptr() if self.log_capacity else None,   # full log (tests): a returning atomic
                                self.log_capacity, 0, self.first_finished.data_ptr(), self.totals.data_ptr())
 
     def first_finished_episodes(self):
