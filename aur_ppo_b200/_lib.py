@@ -158,6 +158,9 @@ def lib() -> ctypes.CDLL:
     L.aur_ppo_update_apply_dp.argtypes = [ctypes.POINTER(PolicyDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                           c_double, c_double, c_double, c_int64, c_double, c_int64, c_double, c_double,
                                           c_void_p, c_void_p, ctypes.c_uint32, c_void_p]
+    L.aur_rollout_set_impl.restype = c_int
+    L.aur_rollout_set_impl.argtypes = [c_int]
+    L.aur_rollout_get_impl.restype = c_int
     L.aur_ppo_update_set_impl.restype = c_int
     L.aur_ppo_update_set_impl.argtypes = [c_int]
     L.aur_ppo_update_get_impl.restype = c_int

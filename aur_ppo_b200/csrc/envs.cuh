@@ -116,6 +116,32 @@ struct CartPole {
   }
 };
 
+// ---- MountainCar-v0 (gym/envs/classic_control/mountain_car.py) ------------------------------
+struct MountainCar {
+  static constexpr int S = 2, OBS = 2, LIMIT = 200;
+  double pos, vel;
+  __device__ __forceinline__ void load(const double* g, long long N, long long n) { pos = g[n]; vel = g[N + n]; }
+  __device__ __forceinline__ void store(double* g, long long N, long long n) const { g[n] = pos; g[N + n] = vel; }
+  __device__ __forceinline__ void reset(Pcg64& rng) {
+    pos = rng.uniform(-0.6, -0.4 - (-0.6));
+    vel = 0.0;
+  }
+  __device__ __forceinline__ void raw_obs(float (&o)[POL_IN_PAD]) const { o[0] = (float)pos; o[1] = (float)vel; o[2] = 0.0f; o[3] = 0.0f; }
+  __device__ __forceinline__ double step(int action, bool& terminated) {
+    const double min_position = -1.2, max_position = 0.6, max_speed = 0.07, goal_position = 0.5, goal_velocity = 0.0;
+    const double force = 0.001, gravity = 0.0025;
+    double s3, c3;
+    aur_sincos(3 * pos, &s3, &c3);
+    vel = vel + ((double)(action - 1) * force + c3 * (-gravity));
+    vel = vel < -max_speed ? -max_speed : (vel > max_speed ? max_speed : vel);
+    pos = pos + vel;
+    pos = pos < min_position ? min_position : (pos > max_position ? max_position : pos);
+    if (pos == min_position && vel < 0) vel = 0;
+    terminated = (pos >= goal_position) && (vel >= goal_velocity);
+    return -1.0;
+  }
+};
+
 // ---- Pendulum-v1 (gym/envs/classic_control/pendulum.py, g = 10) --------------------------
 struct Pendulum {
   static constexpr int S = 2, OBS = 3, LIMIT = 200;

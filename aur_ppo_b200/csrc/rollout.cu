@@ -13,7 +13,7 @@
 namespace aur {
 
 int launch_critic_values_tc(const float* critic, int obs_dim, const float* obs, long long M, float* out, cudaStream_t s);
-int launch_rollout_tc(const RolloutDev& d, bool pendulum, cudaStream_t s);
+int launch_rollout_tc(const RolloutDev& d, int env_kind, cudaStream_t s);
 int rollout_impl();
 
 // ENV: CartPole or Pendulum.  E envs per thread (env n = base + e * nthreads_total keeps warps coalesced).
@@ -333,6 +333,8 @@ extern "C" int aur_env_reset(int32_t env_kind, int64_t N, int32_t wrappers, cons
   cudaStream_t s = (cudaStream_t)stream;
   if (env_kind == AUR_ENV_CARTPOLE) {
     env_reset_kernel<CartPole><<<grid, 128, 0, s>>>((long long)N, 0, *st, obs_out, done_out);
+  } else if (env_kind == AUR_ENV_MOUNTAINCAR) {
+    env_reset_kernel<MountainCar><<<grid, 128, 0, s>>>((long long)N, 0, *st, obs_out, done_out);
   } else if (env_kind == AUR_ENV_PENDULUM) {
     if (wrappers && !st->norm) { set_error("aur_env_reset: wrappers need env.norm"); return AUR_ERR_ARG; }
     env_reset_kernel<Pendulum><<<grid, 128, 0, s>>>((long long)N, wrappers, *st, obs_out, done_out);
@@ -369,6 +371,8 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
   const bool pend = a.env_kind == AUR_ENV_PENDULUM;
   if (a.env_kind == AUR_ENV_CARTPOLE) {
     if (a.policy.continuous || a.policy.obs_dim != 4 || a.policy.act_dim != 2) { set_error("aur_rollout: CartPole needs obs 4, 2 discrete actions"); return AUR_ERR_ARG; }
+  } else if (a.env_kind == AUR_ENV_MOUNTAINCAR) {
+    if (a.policy.continuous || a.policy.obs_dim != 2 || a.policy.act_dim != 3) { set_error("aur_rollout: MountainCar needs obs 2, 3 discrete actions"); return AUR_ERR_ARG; }
   } else if (pend) {
     if (!a.policy.continuous || a.policy.obs_dim != 3 || a.policy.act_dim != 1) { set_error("aur_rollout: Pendulum needs obs 3, 1 continuous action"); return AUR_ERR_ARG; }
     if (a.wrappers && !a.env.norm) { set_error("aur_rollout: wrappers need env.norm"); return AUR_ERR_ARG; }
@@ -378,7 +382,7 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
   const RolloutDev d = to_dev(a);
   cudaStream_t s = (cudaStream_t)stream;
   const int sms = sm_count();
-  const bool two = !pend && a.policy.num_layers <= 2 && a.N >= 2LL * 32 * sms;   // E = 2 needs enough envs to fill the chip
+  const bool two = a.env_kind == AUR_ENV_CARTPOLE && a.policy.num_layers <= 2 && a.N >= 2LL * 32 * sms;   // E = 2 needs enough envs to fill the chip
   const long long threads_needed = two ? (a.N + 1) / 2 : a.N;
   int block = round_up((int)((threads_needed + sms - 1) / sms < 256 ? (threads_needed + sms - 1) / sms : 256), 32);
   if (block < 64) block = 64;
@@ -396,10 +400,12 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
       rollout_kernel<ENVT, 64, EE, true><<<(unsigned)grid, block, smem, s>>>(d);                       \
     }                                                                                                  \
   } while (0)
+  const bool mcar = a.env_kind == AUR_ENV_MOUNTAINCAR;
   if (split_critic && rollout_impl() == 1) {
-    if ((rc = launch_rollout_tc(d, pend, s))) return rc;     // actor hidden layer on tcgen05 (rollout_tc.cu)
+    if ((rc = launch_rollout_tc(d, a.env_kind, s))) return rc;     // actor hidden layer on tcgen05 (rollout_tc.cu)
   } else {
     if (pend) AUR_LAUNCH_ROLLOUT(Pendulum, 1);
+    else if (mcar) AUR_LAUNCH_ROLLOUT(MountainCar, 1);
     else if (two) AUR_LAUNCH_ROLLOUT(CartPole, 2);
     else AUR_LAUNCH_ROLLOUT(CartPole, 1);
     AUR_LAUNCH_OK("rollout_kernel");

@@ -251,29 +251,43 @@ __global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
 }
 
 // 1 = tensor-core rollout (default for hidden 64 / 2 layers), 0 = SIMT rollout_kernel; AUR_ROLLOUT_IMPL=simt|tc
+static int g_rollout_impl = -1;
 int rollout_impl() {
-  static int impl = -1;
-  if (impl < 0) {
+  if (g_rollout_impl < 0) {
     const char* e = getenv("AUR_ROLLOUT_IMPL");
-    impl = e ? ((e[0] == 's' || e[0] == '0') ? 0 : 1) : 1;
+    g_rollout_impl = e ? ((e[0] == 's' || e[0] == '0') ? 0 : 1) : 1;
   }
-  return impl;
+  return g_rollout_impl;
+}
+void set_rollout_impl(int impl) { g_rollout_impl = impl; }
+
+template <class ENV>
+static int rollout_tc_attrs() {
+  AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM));
+  AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<ENV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  return 0;
 }
 
-int launch_rollout_tc(const RolloutDev& d, bool pendulum, cudaStream_t s) {
+int launch_rollout_tc(const RolloutDev& d, int env_kind, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<CartPole>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM));
-    AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<Pendulum>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM));
-    AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<CartPole>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<Pendulum>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int rc;
+    if ((rc = rollout_tc_attrs<CartPole>()) || (rc = rollout_tc_attrs<Pendulum>()) || (rc = rollout_tc_attrs<MountainCar>())) return rc;
     attr = true;
   }
   const unsigned grid = (unsigned)((d.N + RT_S - 1) / RT_S);
-  if (pendulum) rollout_tc_kernel<Pendulum><<<grid, RT_S, RT_SMEM, s>>>(d);
+  if (env_kind == AUR_ENV_PENDULUM) rollout_tc_kernel<Pendulum><<<grid, RT_S, RT_SMEM, s>>>(d);
+  else if (env_kind == AUR_ENV_MOUNTAINCAR) rollout_tc_kernel<MountainCar><<<grid, RT_S, RT_SMEM, s>>>(d);
   else rollout_tc_kernel<CartPole><<<grid, RT_S, RT_SMEM, s>>>(d);
   AUR_LAUNCH_OK("rollout_tc_kernel");
   return 0;
 }
 
 }  // namespace aur
+
+extern "C" int aur_rollout_set_impl(int impl) {
+  if (impl != 0 && impl != 1) { aur::set_error("aur_rollout_set_impl: impl must be 0 (simt) or 1 (tensor core)"); return AUR_ERR_ARG; }
+  aur::set_rollout_impl(impl);
+  return 0;
+}
+extern "C" int aur_rollout_get_impl(void) { return aur::rollout_impl(); }

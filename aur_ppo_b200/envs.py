@@ -16,10 +16,10 @@ import torch
 from . import _lib
 from .kernels import _stream, _ptr
 
-CARTPOLE, PENDULUM = 0, 1
-ENV_IDS = {"CartPole-v1": CARTPOLE, "Pendulum-v1": PENDULUM}
-OBS_DIM = {CARTPOLE: 4, PENDULUM: 3}
-PHYS_DIM = {CARTPOLE: 4, PENDULUM: 2}
+CARTPOLE, PENDULUM, MOUNTAINCAR = 0, 1, 2
+ENV_IDS = {"CartPole-v1": CARTPOLE, "Pendulum-v1": PENDULUM, "MountainCar-v0": MOUNTAINCAR}
+OBS_DIM = {CARTPOLE: 4, PENDULUM: 3, MOUNTAINCAR: 2}
+PHYS_DIM = {CARTPOLE: 4, PENDULUM: 2, MOUNTAINCAR: 2}
 
 
 def pcg64_seed_states(seeds: Sequence[int]) -> np.ndarray:

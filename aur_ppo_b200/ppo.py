@@ -73,7 +73,8 @@ class FusedAdam(torch.optim.Optimizer):
         pass   # the gradient buffer is overwritten by every aur_ppo_update_grad call
 
 
-_SPACES = {"CartPole-v1": dict(obs=(4,), act_shape=(), n=2), "Pendulum-v1": dict(obs=(3,), act_shape=(1,), n=None)}
+_SPACES = {"CartPole-v1": dict(obs=(4,), act_shape=(), n=2), "Pendulum-v1": dict(obs=(3,), act_shape=(1,), n=None),
+           "MountainCar-v0": dict(obs=(2,), act_shape=(), n=3)}
 
 
 class ppo:

@@ -35,6 +35,7 @@ extern "C" {
 
 #define AUR_ENV_CARTPOLE 0 /* gym CartPole-v1 */
 #define AUR_ENV_PENDULUM 1 /* gym Pendulum-v1 */
+#define AUR_ENV_MOUNTAINCAR 2 /* gym MountainCar-v0 (discrete, 3 actions, obs 2) */
 
 int aur_abi_version(void);
 const char* aur_last_error(void);
@@ -106,7 +107,7 @@ int aur_policy_evaluate(const aur_policy_desc* desc, const float* params, int64_
  * clip +-10, NormalizeReward(gamma), clip +-10 (src/ppo.py:92-97), per env.
  * All arrays are struct-of-arrays over the N envs this GPU owns. */
 typedef struct {
-  double* phys;       /* [S][N] fp64: CartPole x, x_dot, theta, theta_dot; Pendulum theta, theta_dot */
+  double* phys;       /* [S][N] fp64: CartPole x, x_dot, theta, theta_dot; Pendulum theta, theta_dot; MountainCar position, velocity */
   uint64_t* pcg;      /* [4][N] PCG64 state_hi, state_lo, inc_hi, inc_lo (np.random.PCG64(SeedSequence(seed_i))) */
   int32_t* elapsed;   /* [N] TimeLimit step counter */
   float* ep_return;   /* [N] RecordEpisodeStatistics accumulator (fp32 as in gym) */
@@ -179,6 +180,12 @@ typedef struct {
 } aur_rollout_args;
 
 int aur_rollout(const aur_rollout_args* args, void* stream);
+
+/* Kernel behind aur_rollout for hidden 64 / 2 layers: 1 = actor hidden layer on tcgen05 (rollout_tc_kernel, default),
+ * 0 = SIMT rollout_kernel (also the path for other layer counts).  Both are followed by the batched tensor-core
+ * value pass.  AUR_ROLLOUT_IMPL=simt|tc sets the initial choice. */
+int aur_rollout_set_impl(int impl);
+int aur_rollout_get_impl(void);
 
 /* -------------------------------------------------------------- update ----
  * Replaces one minibatch step of src/ppo.py:220-269: gather of the shuffled indices,

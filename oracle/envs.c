@@ -37,6 +37,9 @@ static inline double pcg64_double(pcg64_t* g) { return (double)(pcg64_next(g) >>
 /* Generator.uniform(low, high): low + (high - low) * next_double */
 static inline double pcg64_uniform(pcg64_t* g, double low, double range) { return low + range * pcg64_double(g); }
 
+static inline int obs_dim_of(int kind) { return kind == 0 ? 4 : (kind == 1 ? 3 : 2); }
+static inline int time_limit_of(int kind) { return kind == 0 ? 500 : 200; }
+
 static inline void trig(int mode, double x, double* s, double* c) {
   if (mode == 0) { *s = sin(x); *c = cos(x); }
   else aur_sincos(x, s, c);
@@ -66,7 +69,7 @@ static inline void rms_update1(double* mean, double* var, double* count, double 
 
 /* ---- vector env ---- */
 typedef struct {
-  int kind;        /* 0 CartPole-v1, 1 Pendulum-v1 */
+  int kind;        /* 0 CartPole-v1, 1 Pendulum-v1, 2 MountainCar-v0 */
   int wrappers;    /* 1 = the reference's continuous wrapper stack (ppo.py:92-97) */
   int trig_mode;
   int64_t n;
@@ -132,12 +135,18 @@ static void env_reset(orc_vec_t* v, int64_t i, float* obs_out) {
     for (int k = 0; k < 4; ++k) st[k] = pcg64_uniform(&v->rng[i], -0.05, 0.05 - (-0.05));
     double raw[4]; for (int k = 0; k < 4; ++k) raw[k] = (double)(float)st[k];
     emit_obs(v, i, raw, 4, obs_out);
-  } else {
+  } else if (v->kind == 1) {
     st[0] = pcg64_uniform(&v->rng[i], -M_PI, M_PI - (-M_PI));
     st[1] = pcg64_uniform(&v->rng[i], -1.0, 1.0 - (-1.0));
     double s, c; trig(v->trig_mode, st[0], &s, &c);
     double raw[3] = {(double)(float)c, (double)(float)s, (double)(float)st[1]};
     emit_obs(v, i, raw, 3, obs_out);
+  } else {
+    /* MountainCar-v0 (mountain_car.py reset): state = [uniform(-0.6, -0.4), 0] */
+    st[0] = pcg64_uniform(&v->rng[i], -0.6, -0.4 - (-0.6));
+    st[1] = 0.0;
+    double raw[2] = {(double)(float)st[0], (double)(float)st[1]};
+    emit_obs(v, i, raw, 2, obs_out);
   }
 }
 
@@ -145,7 +154,7 @@ static void env_reset(orc_vec_t* v, int64_t i, float* obs_out) {
  * Python side: [n][4] = state_hi, state_lo, inc_hi, inc_lo */
 void orc_vec_reset(void* h, const uint64_t* pcg, float* obs_out) {
   orc_vec_t* v = (orc_vec_t*)h;
-  int d = v->kind == 0 ? 4 : 3;
+  int d = obs_dim_of(v->kind);
   for (int64_t i = 0; i < v->n; ++i) {
     v->rng[i].state = ((u128)pcg[i * 4 + 0] << 64) | pcg[i * 4 + 1];
     v->rng[i].inc = ((u128)pcg[i * 4 + 2] << 64) | pcg[i * 4 + 3];
@@ -153,7 +162,7 @@ void orc_vec_reset(void* h, const uint64_t* pcg, float* obs_out) {
   }
 }
 
-/* One SyncVectorEnv.step.  actions: CartPole int32 [n]; Pendulum float32 [n].
+/* One SyncVectorEnv.step.  actions: CartPole / MountainCar int32 [n]; Pendulum float32 [n].
  * Outputs: obs [n][d] float32 (the RESET obs where an episode ended), reward
  * [n] float64, terminated/truncated [n] uint8, and for finished episodes
  * final_ret [n] float32 / final_len [n] int32 (else len = 0). */
@@ -163,7 +172,7 @@ void orc_vec_step(void* h, const void* actions, float* obs_out, double* rew_out,
   for (int64_t i = 0; i < v->n; ++i) {
     double* st = &v->phys[i * 4];
     double reward; int terminated = 0, truncated = 0;
-    float* o = &obs_out[i * (v->kind == 0 ? 4 : 3)];
+    float* o = &obs_out[i * obs_dim_of(v->kind)];
     double raw[4]; int d;
     if (v->kind == 0) {
       const double gravity = 9.8, masscart = 1.0, masspole = 0.1, length = 0.5, force_mag = 10.0, tau = 0.02;
@@ -184,6 +193,23 @@ void orc_vec_step(void* h, const void* actions, float* obs_out, double* rew_out,
       reward = 1.0;
       for (int k = 0; k < 4; ++k) raw[k] = (double)(float)st[k];
       d = 4;
+    } else if (v->kind == 2) {
+      /* MountainCar-v0 (gym/envs/classic_control/mountain_car.py step) */
+      const double min_position = -1.2, max_position = 0.6, max_speed = 0.07, goal_position = 0.5, goal_velocity = 0.0;
+      const double force = 0.001, gravity = 0.0025;
+      int a = ((const int32_t*)actions)[i];
+      double position = st[0], velocity = st[1];
+      double s3, c3; trig(v->trig_mode, 3 * position, &s3, &c3);
+      velocity = velocity + ((a - 1) * force + c3 * (-gravity));
+      velocity = velocity < -max_speed ? -max_speed : (velocity > max_speed ? max_speed : velocity);   /* np.clip */
+      position = position + velocity;
+      position = position < min_position ? min_position : (position > max_position ? max_position : position);
+      if (position == min_position && velocity < 0) velocity = 0;
+      terminated = (position >= goal_position) && (velocity >= goal_velocity);
+      reward = -1.0;
+      st[0] = position; st[1] = velocity;
+      raw[0] = (double)(float)position; raw[1] = (double)(float)velocity;
+      d = 2;
     } else {
       const double max_speed = 8.0, max_torque = 2.0, dt = 0.05, g = 10.0, m = 1.0, l = 1.0;
       float u32 = ((const float*)actions)[i];
@@ -208,7 +234,7 @@ void orc_vec_step(void* h, const void* actions, float* obs_out, double* rew_out,
     }
     /* TimeLimit */
     v->elapsed[i] += 1;
-    if (v->elapsed[i] >= (v->kind == 0 ? 500 : 200)) truncated = 1;
+    if (v->elapsed[i] >= time_limit_of(v->kind)) truncated = 1;
     /* RecordEpisodeStatistics (raw reward, float32 accumulator) */
     v->ep_ret[i] = v->ep_ret[i] + (float)reward;
     v->ep_len[i] += 1;

@@ -16,7 +16,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-CARTPOLE, PENDULUM = 0, 1
+CARTPOLE, PENDULUM, MOUNTAINCAR = 0, 1, 2
+OBS_DIM = {CARTPOLE: 4, PENDULUM: 3, MOUNTAINCAR: 2}
+PHYS_DIM = {CARTPOLE: 4, PENDULUM: 2, MOUNTAINCAR: 2}
 TRIG_LIBM, TRIG_DET = 0, 1
 
 
@@ -79,7 +81,7 @@ def det_sincos_scalar(x: float):
 class CVecEnv:
     def __init__(self, kind: int, num_envs: int, wrappers: bool = False, trig: int = TRIG_DET, gamma: float = 0.99):
         self.kind, self.num_envs = kind, num_envs
-        self.obs_dim = 4 if kind == CARTPOLE else 3
+        self.obs_dim = OBS_DIM[kind]
         self._h = lib().orc_vec_create(kind, num_envs, int(wrappers), trig, gamma)
         n = num_envs
         self._obs = np.zeros((n, self.obs_dim), np.float32)
@@ -100,7 +102,7 @@ class CVecEnv:
         return self._obs.copy(), {}
 
     def step(self, actions):
-        if self.kind == CARTPOLE:
+        if self.kind != PENDULUM:
             a = np.ascontiguousarray(actions, dtype=np.int32)
         else:
             a = np.ascontiguousarray(np.asarray(actions, dtype=np.float32).reshape(self.num_envs))
@@ -116,7 +118,7 @@ class CVecEnv:
     def phys(self) -> np.ndarray:
         out = np.zeros((self.num_envs, 4 if self.kind == CARTPOLE else 2), np.float64)
         lib().orc_vec_get_phys(self._h, out.ctypes.data)
-        return out
+        return out[:, :PHYS_DIM[self.kind]]
 
     def norm_stats(self) -> np.ndarray:
         out = np.zeros((self.num_envs, 11), np.float64)

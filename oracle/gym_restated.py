@@ -110,6 +110,42 @@ class CartPoleEnv:
         return np.array(self.state, dtype=np.float32), reward, terminated, False, {}
 
 
+class MountainCarEnv:
+    """gym MountainCar-v0 (mountain_car.py): fp64 state, reward -1 per step, goal at position 0.5."""
+
+    def __init__(self, sincos: Callable[[float], Tuple[float, float]] = _libm_sincos):
+        self.min_position = -1.2
+        self.max_position = 0.6
+        self.max_speed = 0.07
+        self.goal_position = 0.5
+        self.goal_velocity = 0
+        self.force = 0.001
+        self.gravity = 0.0025
+        self.state = None
+        self.np_random = None
+        self._sincos = sincos
+        self.obs_dim = 2
+
+    def reset(self, seed: Optional[int] = None):
+        if seed is not None or self.np_random is None:
+            self.np_random = np_random(seed)
+        self.state = np.array([self.np_random.uniform(low=-0.6, high=-0.4), 0])
+        return np.array(self.state, dtype=np.float32), {}
+
+    def step(self, action):
+        position, velocity = self.state
+        velocity += (action - 1) * self.force + self._sincos(3 * position)[1] * (-self.gravity)
+        velocity = np.clip(velocity, -self.max_speed, self.max_speed)
+        position += velocity
+        position = np.clip(position, self.min_position, self.max_position)
+        if position == self.min_position and velocity < 0:
+            velocity = 0
+        terminated = bool(position >= self.goal_position and velocity >= self.goal_velocity)
+        reward = -1.0
+        self.state = (position, velocity)
+        return np.array(self.state, dtype=np.float32), reward, terminated, False, {}
+
+
 def angle_normalize(x: float) -> float:
     # ((x + pi) % (2 pi)) - pi ; Python float % == NumPy float64 % (fmod + sign fix)
     return ((x + math.pi) % (2 * math.pi)) - math.pi
@@ -306,6 +342,9 @@ def make_env(gym_id: str, continuous: bool, sincos=_libm_sincos):
     elif gym_id == "Pendulum-v1":
         env = TimeLimit(PendulumEnv(sincos), 200)
         obs_shape = (3,)
+    elif gym_id == "MountainCar-v0":
+        env = TimeLimit(MountainCarEnv(sincos), 200)
+        obs_shape = (2,)
     else:
         raise ValueError(f"unsupported gym_id {gym_id!r}")
     env = RecordEpisodeStatistics(env)

@@ -36,10 +36,10 @@ def test_pcg64_stream_matches_numpy():
 
 
 @pytest.mark.parametrize("kind,gid,cont", [(E.CARTPOLE, "CartPole-v1", False), (E.PENDULUM, "Pendulum-v1", True),
-                                           (E.PENDULUM, "Pendulum-v1", False)])
+                                           (E.PENDULUM, "Pendulum-v1", False), (E.MOUNTAINCAR, "MountainCar-v0", False)])
 def test_c_checker_equals_python_restatement(kind, gid, cont):
     N = 6
-    pv = G.SyncVectorEnv([G.make_env(gid, cont) for _ in range(N)], 4 if kind == 0 else 3)
+    pv = G.SyncVectorEnv([G.make_env(gid, cont) for _ in range(N)], E.OBS_DIM[kind])
     cv = E.CVecEnv(kind, N, wrappers=cont, trig=E.TRIG_LIBM)
     o1, _ = pv.reset(seed=list(range(N)))
     o2, _ = cv.reset(list(range(N)))
@@ -47,7 +47,8 @@ def test_c_checker_equals_python_restatement(kind, gid, cont):
     rng = np.random.default_rng(5)
     episodes = 0
     for t in range(700):
-        a = rng.integers(0, 2, N) if kind == 0 else rng.normal(0, 1.5, (N, 1)).astype(np.float32)
+        a = (rng.integers(0, 2, N) if kind == E.CARTPOLE else rng.integers(0, 3, N) if kind == E.MOUNTAINCAR
+             else rng.normal(0, 1.5, (N, 1)).astype(np.float32))
         r1, r2 = pv.step(a), cv.step(a)
         for k in range(4):
             np.testing.assert_array_equal(r1[k], r2[k], err_msg=f"t={t} field={k}")
@@ -108,3 +109,27 @@ def test_det_and_libm_trajectories_agree_on_float32_observations():
         done_mismatch += int((ra[2] != rb[2]).sum())
     assert done_mismatch == 0
     assert obs_mismatch <= 4       # fp64 last-bit differences almost never cross a float32 rounding boundary
+
+
+def test_mountaincar_restatement_behaviour():
+    """MountainCar-v0: reward -1 per step, left wall stops the car, full throttle right never reaches the flag from
+    rest (the classic under-powered car), the energy-pumping policy does within the 200-step TimeLimit."""
+    env = G.make_env("MountainCar-v0", False)
+    obs, _ = env.reset(seed=0)
+    assert obs.dtype == np.float32 and -0.6 <= obs[0] <= -0.4 and obs[1] == 0
+    for t in range(200):
+        obs, r, term, trunc, info = env.step(2)
+        assert r == -1.0 and not term
+    assert trunc and info["episode"]["l"] == 200
+    env = G.make_env("MountainCar-v0", False)
+    obs, _ = env.reset(seed=0)
+    for t in range(200):
+        obs, r, term, trunc, info = env.step(2 if obs[1] >= 0 else 0)
+        if term:
+            break
+    assert term and obs[0] >= 0.5 and 80 < t < 200
+    env = G.make_env("MountainCar-v0", False)
+    obs, _ = env.reset(seed=1)
+    for t in range(60):
+        obs, *_ = env.step(0)
+    assert obs[0] >= -1.2 and (obs[0] > -1.2 or obs[1] >= 0)

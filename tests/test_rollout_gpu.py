@@ -13,6 +13,17 @@ pytestmark = pytest.mark.gpu
 TOL = dict(rtol=2e-5, atol=2e-6)
 
 
+@pytest.fixture(autouse=True, params=["tc", "simt"])
+def rollout_impl(request):
+    """Every test runs against both rollout kernels: actor hidden layer on tcgen05 (default) and the SIMT kernel."""
+    L = _lib.lib()
+    prev = L.aur_rollout_get_impl()
+    assert L.aur_rollout_set_impl(1 if request.param == "tc" else 0) == 0
+    yield request.param
+    L.aur_rollout_set_impl(prev)
+
+
+
 def test_device_sincos_equals_host_copy_bitwise():
     rng = np.random.default_rng(0)
     x = np.concatenate([rng.uniform(-0.3, 0.3, 200_000), rng.uniform(-100, 100, 200_000),
@@ -113,6 +124,61 @@ def test_cartpole_replay_is_bit_exact(N, T):
     with torch.no_grad():
         nv = pol.value(torch.from_numpy(last_obs[sub]))
     np.testing.assert_allclose(buf.next_value[sub].cpu().numpy(), nv.numpy(), **TOL)
+
+
+@pytest.mark.parametrize("N,T", [(7, 450), (300, 256)])
+def test_mountaincar_replay_is_bit_exact(N, T):
+    """MountainCar-v0 ((f) rank 4: more classic-control envs behind --gym_id): obs 2, 3 discrete actions, TimeLimit 200."""
+    pol, named = random_policy(2, 3, 64, 2, False, seed=8)
+    desc = kernels.policy_desc(2, 3, 64, 2, False)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    seeds = list(range(N))
+    rng = np.random.default_rng(N)
+    # energy pumping on half of the envs so that some episodes terminate before the TimeLimit truncation
+    actions = rng.integers(0, 3, (T, N))
+    cv, obs0, obs, rew, done, last_obs, last_done, episodes = _oracle_replay_adaptive(E.MOUNTAINCAR, N, seeds, actions, T)
+    env = denv.DeviceVecEnv("MountainCar-v0", N, log_capacity=N * 16)
+    o, _ = env.reset(seeds)
+    assert np.array_equal(o.cpu().numpy(), obs0)
+    buf = kernels.RolloutBuffers(T, N, 2, (), "cuda")
+    kernels.rollout(env, desc, flat, buf, seed=1, step0=0, actions_in=torch.from_numpy(actions.astype(np.float32)).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.states.cpu().numpy(), obs)
+    assert np.array_equal(buf.terminals.cpu().numpy(), done)
+    assert np.array_equal(buf.rewards.cpu().numpy(), rew)
+    assert np.array_equal(env.next_obs.cpu().numpy(), last_obs)
+    assert np.array_equal(env.phys.cpu().numpy().T, cv.phys())
+    got = env.drain_episodes()
+    assert got == sorted(episodes, key=lambda r: (r[0], r[1])) and len(got) > 0
+    assert any(l < 200 for (_, _, _, l) in got) and done.sum() > 0           # real terminations, not only truncations
+    sub = slice(0, min(N, 64))
+    ot = torch.from_numpy(obs[:, sub].reshape(-1, 2)); at = torch.from_numpy(actions[:, sub].reshape(-1))
+    with torch.no_grad():
+        _, lp, _, v = pol.evaluate(ot, at)
+    np.testing.assert_allclose(buf.log_probs[:, sub].cpu().numpy().reshape(-1), lp.numpy(), **TOL)
+    np.testing.assert_allclose(buf.values[:, sub].cpu().numpy().reshape(-1), v.numpy().reshape(-1), **TOL)
+
+
+def _oracle_replay_adaptive(kind, N, seeds, actions, T):
+    """Like _oracle_replay, but even-numbered envs follow the energy-pumping policy (push in the direction of motion):
+    `actions` is overwritten in place with what was actually played."""
+    cv = E.CVecEnv(kind, N, wrappers=False, trig=E.TRIG_DET)
+    obs0, _ = cv.reset(seeds)
+    D = cv.obs_dim
+    obs = np.zeros((T, N, D), np.float32); rew = np.zeros((T, N), np.float32); done = np.zeros((T, N), np.float32)
+    cur, cur_done = obs0, np.zeros(N, np.float32)
+    episodes = []
+    for t in range(T):
+        obs[t], done[t] = cur, cur_done
+        actions[t, ::2] = np.where(cur[::2, 1] >= 0, 2, 0)
+        cur, r, term, trunc, info = cv.step(actions[t])
+        rew[t] = r.astype(np.float32)
+        cur_done = term.astype(np.float32)
+        if "final_info" in info:
+            for i, it in enumerate(info["final_info"]):
+                if it is not None:
+                    episodes.append((t, i, float(it["episode"]["r"]), int(it["episode"]["l"])))
+    return cv, obs0, obs, rew, done, cur, cur_done, episodes
 
 
 @pytest.mark.parametrize("wrappers", [True, False])

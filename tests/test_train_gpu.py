@@ -78,3 +78,15 @@ def test_unsupported_configs_fail_loudly():
     agent = ppo(_params(hidden_dim=32, total_timesteps=512))
     with pytest.raises(_lib.AurError, match="hidden_dim"):
         agent.train()
+
+
+def test_mountaincar_runs_through_the_drop_in_api():
+    """--gym_id MountainCar-v0 ((f) rank 4): obs 2 / 3 actions flow through rollout, GAE, packed records and the update."""
+    from aur_ppo_b200.ppo import ppo
+    torch.manual_seed(1)
+    agent = ppo(_params(gym_id="MountainCar-v0", num_envs=256, total_timesteps=256 * 128 * 3))
+    assert agent.buffer.states.shape == (128, 256, 2) and agent.policy.actor.net[-1].out_features == 3
+    rets, lens, xs = agent.train()
+    assert agent.num_updates == 3 and len(rets) > 0
+    assert all(l <= 200 for l in lens) and all(r == -float(l) for r, l in zip(rets, lens))     # reward -1 per step
+    assert np.isfinite([agent.last_stats[k] for k in ("value_loss", "policy_loss", "entropy", "approx_kl")]).all()
