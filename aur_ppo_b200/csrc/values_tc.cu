@@ -8,7 +8,7 @@
 // written as a THREE-term bf16 split (hi + mid + lo, fp32-equivalent: values are compared with the reference at
 // 2e-6) into 128-B-swizzled tiles, z2 = h1 W2^T on tcgen05 as six products with fp32 accumulation in TMEM, tanh +
 // 64->1 head from TMEM lanes.
-// Three CTAs per SM cover each other's MMA round trip.  HBM: 16 + 4 B per sample.
+// Three CTAs per SM (75 KB of shared memory each) cover each other's MMA round trip.  HBM: 16 + 4 B per sample.
 #include "tc_split.cuh"
 #include "policy.cuh"
 
@@ -18,10 +18,10 @@ constexpr int VT_S = 128, VT_THREADS = 256;
 constexpr int VT_TILE = VT_S * 128, VT_WTILE = 64 * 128;
 constexpr int VO_H1 = 0;                         // [hi][mid][lo]
 constexpr int VO_W2 = VO_H1 + 3 * VT_TILE;       // [hi][mid][lo]
-constexpr int VO_SMALL = VO_W2 + 3 * VT_WTILE;   // W1^T [4][64], b1 [64], b2 [64], W3 [64], b3
-constexpr int VO_XCH = VO_SMALL + 512 * 4;       // [128] head partials of the upper feature half
-constexpr int VO_BAR = VO_XCH + VT_S * 4;
-constexpr size_t VT_SMEM = VO_BAR + 64 + 1024;
+constexpr int VO_SMALL = VO_W2 + 3 * VT_WTILE;   // W1^T [4][64], b1 [64], b2 [64], W3 [64], b3 (452 floats)
+constexpr int VO_BAR = VO_SMALL + 452 * 4;
+constexpr size_t VT_SMEM = VO_BAR + 16 + 1024;
+static_assert(3 * (VT_SMEM + 1024) <= 233472, "three CTAs per SM");
 constexpr int VS_W1T = 0, VS_B1 = 256, VS_B2 = 320, VS_W3 = 384, VS_B3 = 448;
 
 __global__ void __launch_bounds__(VT_THREADS, 3) critic_values_tc_kernel(const float* __restrict__ critic, int obs_dim,
@@ -32,9 +32,8 @@ __global__ void __launch_bounds__(VT_THREADS, 3) critic_values_tc_kernel(const f
   unsigned char* h1t[3] = {base + VO_H1, base + VO_H1 + VT_TILE, base + VO_H1 + 2 * VT_TILE};
   unsigned char* w2t[3] = {base + VO_W2, base + VO_W2 + VT_WTILE, base + VO_W2 + 2 * VT_WTILE};
   float* sw = reinterpret_cast<float*>(base + VO_SMALL);
-  float* xch = reinterpret_cast<float*>(base + VO_XCH);
   uint64_t* bar = reinterpret_cast<uint64_t*>(base + VO_BAR);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(base + VO_BAR + 32);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(base + VO_BAR + 8);
   const int tid = threadIdx.x, warp = tid >> 5, s = tid & 127, half = tid >> 7, f0 = 32 * half;
 
   if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
@@ -127,12 +126,15 @@ __global__ void __launch_bounds__(VT_THREADS, 3) critic_values_tc_kernel(const f
       p0 = fmaf(w.z, tanh_prescaled(fmaf(z[4 * g + 2], TANH_PRESCALE, b.z)), p0);
       p1 = fmaf(w.w, tanh_prescaled(fmaf(z[4 * g + 3], TANH_PRESCALE, b.w)), p1);
     }
-    if (half == 1) xch[s] = p0 + p1;
+    // the upper half hands its head partial over through a TMEM column of its own (already consumed) z range
+    if (half == 1) { tc::tmem_st1(tm_z + lane_base + 32, p0 + p1); tc::tmem_wait_st(); }
     tc::fence_before_sync();
-    __syncthreads();                                  // head partials visible; z and the h1 tile are free again
+    __syncthreads();                                  // head partials visible; the h1 tile is free again
     if (half == 0) {
+      tc::fence_after_sync();
+      const float other = tc::tmem_ld1(tm_z + lane_base + 32);
       const long long row = tile * VT_S + s;
-      if (row < M) out[row] = ((p0 + p1) + xch[s]) + sw[VS_B3];
+      if (row < M) out[row] = ((p0 + p1) + other) + sw[VS_B3];
     }
   }
   tc::fence_before_sync();
