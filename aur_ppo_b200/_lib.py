@@ -13,7 +13,7 @@ import subprocess
 from ctypes import c_double, c_int, c_int32, c_int64, c_uint64, c_void_p, c_char_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libaurppo.so")
+LIB_PATH = os.environ.get("AUR_LIB_PATH", os.path.join(_PKG, "libaurppo.so"))
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "aur_ppo.h")
 
 _lib = None

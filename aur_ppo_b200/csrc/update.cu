@@ -581,13 +581,20 @@ __global__ void __launch_bounds__(1024) adam_kernel(int64_t P, float* __restrict
   }
 }
 
-// 0 = SIMT fp32 (ppo_grad_kernel, kept as an independent cross-check), 1 = tcgen05 bf16x2-split
-// (ppo_grad_tc_kernel, the default).  AUR_UPDATE_IMPL=simt|tc or aur_ppo_update_set_impl() select it.
+// 0 = SIMT fp32 (ppo_grad_kernel, kept as an independent cross-check), 1 = tcgen05 bf16x2-split with two threads per
+// sample, 2 = the same with four threads per sample (ppo_grad_tc_kernel<2|4>).  AUR_UPDATE_IMPL=simt|tc|tc4 or
+// aur_ppo_update_set_impl() select it.
+#ifndef AUR_UPDATE_DEFAULT_IMPL
+#define AUR_UPDATE_DEFAULT_IMPL 1
+#endif
 static int g_update_impl = -1;
 static int update_impl() {
   if (g_update_impl < 0) {
     const char* e = getenv("AUR_UPDATE_IMPL");
-    g_update_impl = e ? ((e[0] == 's' || e[0] == '0') ? 0 : 1) : 1;
+    if (!e) g_update_impl = AUR_UPDATE_DEFAULT_IMPL;
+    else if (e[0] == 's' || e[0] == '0') g_update_impl = 0;
+    else if (e[0] == '2' || (e[0] == 't' && e[1] == 'c' && e[2] == '4')) g_update_impl = 2;
+    else g_update_impl = 1;
   }
   return g_update_impl;
 }
@@ -657,7 +664,7 @@ extern "C" int aur_ppo_adv_moments_dp(int64_t m, const int32_t* idx, int64_t idx
 }
 
 extern "C" int aur_ppo_update_set_impl(int impl) {
-  if (impl != 0 && impl != 1) { aur::set_error("aur_ppo_update_set_impl: impl must be 0 (simt) or 1 (tensor core)"); return AUR_ERR_ARG; }
+  if (impl < 0 || impl > 2) { aur::set_error("aur_ppo_update_set_impl: impl must be 0 (simt), 1 (tensor core) or 2 (tensor core, 4 threads per sample)"); return AUR_ERR_ARG; }
   aur::g_update_impl = impl;
   return 0;
 }
@@ -695,9 +702,9 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int impl = update_impl();
   int gx;
-  if (impl == 1) {
+  if (impl >= 1) {
     gx = sm_count();
-    int rc2 = launch_ppo_grad_tc(d, gx, s);
+    int rc2 = launch_ppo_grad_tc(d, gx, impl == 2 ? 4 : 2, s);
     if (rc2) return rc2;
   } else {
     gx = upd_grid_x();

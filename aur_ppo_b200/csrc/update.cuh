@@ -103,7 +103,7 @@ __device__ __forceinline__ void adv_norm_consts(const UpdDev& a, float& mean_out
 
 
 // tensor-core implementation (update_tc.cu): both nets per CTA, grid = gx CTAs; same partial layout
-int launch_ppo_grad_tc(const UpdDev& d, int gx, cudaStream_t s);
+int launch_ppo_grad_tc(const UpdDev& d, int gx, int threads_per_sample, cudaStream_t s);
 size_t ppo_grad_tc_smem_bytes();
 
 }  // namespace aur

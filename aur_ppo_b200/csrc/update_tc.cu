@@ -33,7 +33,6 @@
 namespace aur {
 
 constexpr int T2_S = 128;                   // samples per tile
-constexpr int T2_THREADS = 256;
 constexpr int T2_LD = T2_S + 4;             // fp32 staging row stride
 constexpr int T2_TILE = T2_S * 128;         // operand tile: 128 rows x 128 B
 constexpr int T2_WTILE = 64 * 128;          // W2 tile: 64 rows x 128 B
@@ -43,17 +42,18 @@ constexpr int T2_SW = 768;                  // small-weight floats
 constexpr int O2_H1 = 0;                                // [hi][mid]
 constexpr int O2_DZ = O2_H1 + 2 * T2_TILE;              // [hi][mid]
 constexpr int O2_W2 = O2_DZ + 2 * T2_TILE;              // [hi][mid]   (follows dz mid: see the M = 128 note below)
-constexpr int O2_AUX = O2_W2 + 2 * T2_WTILE;            // [buffer 2][hi, mid] + 1 KB of zeros
-constexpr int O2_SMALL = O2_AUX + 4 * T2_AUXT + 1024;   // fp32 small weights
-constexpr int O2_STAGE = O2_SMALL + T2_SW * 4;          // fp32 [32][T2_LD]; also epilogue scratch
-constexpr int O2_DOUT = O2_STAGE + 32 * T2_LD * 4;      // fp32 [4][T2_LD]: head exchange, then dout
+constexpr int O2_AUX = O2_W2 + 2 * T2_WTILE;            // [buffer 2][hi, mid]
+constexpr int O2_SMALL = O2_AUX + 4 * T2_AUXT;          // fp32 small weights (also what the aux tiles' unused rows 8..15 over-read)
+constexpr int T2_STAGE_BYTES = 16 * 8 * 36 * 4;         // 16 warp patches of [8][36] floats; also head exchange / epilogue scratch
+constexpr int O2_STAGE = O2_SMALL + T2_SW * 4;
+constexpr int O2_DOUT = O2_STAGE + T2_STAGE_BYTES;      // fp32 [4][T2_LD]: dout
 constexpr int O2_BAR = O2_DOUT + 4 * T2_LD * 4;         // mbarriers + tmem slot
 constexpr int T2_SMEM_USED = O2_BAR + 128;
 constexpr size_t T2_SMEM = T2_SMEM_USED + 1024;
 static_assert(2 * (T2_SMEM + 1024) <= 233472, "two CTAs per SM");
 
 // small-weight block (floats): W1^T [4][64] (zero rows >= obs_dim), b1 [64], b2 [64], W3 [4][64], b3 [4]
-constexpr int S2_W1T = 0, S2_B1 = 256, S2_B2 = 320, S2_W3 = 384, S2_B3 = 640, S2_NC = 644;   // S2_NC: Normal constants [3][4], then advantage mean / std + 1e-8
+constexpr int S2_W1T = 0, S2_B1 = 256, S2_B2 = 320, S2_W3 = 384, S2_B3 = 640, S2_NC = 644, S2_ST = 660;   // S2_NC: Normal constants [3][4], then advantage mean / std + 1e-8; S2_ST: statistics slots [4 warps][9]
 enum { BAR_FWD = 0, BAR_AUX = 1, BAR_WG = 2, BAR_FIN = 3 };
 constexpr int T2_TMEM_COLS = 256;           // z / dh 64 (never live together) | dW2 64 | db2 16 | [db1 dW1] 16 | h1 (fp32 copy) 64
 
@@ -73,8 +73,8 @@ struct T2Ptrs {
 };
 
 // byte offset of element (n < 8, s) of an aux tile (K-major, 128-B swizzle): row n holds 64 samples of one block.
-// The MMA reads N = 16 rows; rows 8..15 fall 1 KB further (the next block / tile / the zero pad) and only reach
-// accumulator columns 8..15, which nobody reads.
+// The MMA reads N = 16 rows; rows 8..15 fall 1 KB further (the next block / tile / the small weights behind the aux
+// region) and only reach accumulator columns 8..15, which nobody reads.
 __device__ __forceinline__ int aux_off(int n, int s) {
   return (s >> 6) * 1024 + n * 128 + (((((s & 63) >> 3) ^ n)) << 4) + (s & 7) * 2;
 }
@@ -83,21 +83,25 @@ __device__ __forceinline__ int aux_off(int n, int s) {
 // descriptor's second 64-row atom is the MID tile (LBO = one tile), so one M = 128 MMA yields hi^T B in accumulator
 // rows 0..63 and mid^T B in rows 64..127; two passes (B_hi, B_mid) give all four split products and the epilogue
 // adds the two row blocks.  b_step / b_block: 16-B units per K step inside / across the 64-sample blocks of B.
+// b_mid_pass = false skips the second pass (B's mid part is known to be zero where it matters: the ones column).
 __device__ __forceinline__ void mma_over_samples(uint32_t d, uint64_t a_himid, uint64_t b_hi, uint64_t b_mid, uint32_t idesc,
-                                                 uint32_t b_step, uint32_t b_block, bool accumulate) {
+                                                 uint32_t b_step, uint32_t b_block, bool accumulate, bool b_mid_pass = true) {
   for (int k = 0; k < 8; ++k)
     tc::mma_f16(d, a_himid + (uint64_t)(128 * k), b_hi + (uint64_t)((k & 3) * b_step + (k >> 2) * b_block), idesc,
                 (accumulate || k > 0) ? 1u : 0u);
+  if (!b_mid_pass) return;
   for (int k = 0; k < 8; ++k)
     tc::mma_f16(d, a_himid + (uint64_t)(128 * k), b_mid + (uint64_t)((k & 3) * b_step + (k >> 2) * b_block), idesc, 1u);
 }
 
-template <bool ACTOR>
+// TPS = threads per sample (2 or 4): each owns FPT = 64 / TPS hidden features of its sample.
+template <bool ACTOR, int TPS>
 __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* smem_base, int cta, int ncta) {
+  constexpr int THREADS = 128 * TPS, FPT = 64 / TPS, CPT = FPT / 8;
   T2Ptrs P;
   P.base = smem_base;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int s = tid & 127, half = tid >> 7, f0 = 32 * half;
+  const int s = tid & 127, half = tid >> 7, f0 = FPT * half;      // `half`: which feature slice of the sample (0 .. TPS-1)
   const int obs_dim = a.obs_dim, A = a.act_dim;
   const int OUT = ACTOR ? A : 1;
   const int64_t gA = net_param_count(obs_dim, UPD_H, 2, A), gC = net_param_count(obs_dim, UPD_H, 2, 1);
@@ -116,17 +120,18 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
     const float* gb2 = gW2 + 4096;
     const float* gW3 = gb2 + 64;
     const float* gb3 = gW3 + OUT * 64;
-    {
+    if (tid < 256) {
       const int c = tid >> 6, j = tid & 63;
       sw[S2_W1T + tid] = c < obs_dim ? TANH_PRESCALE * g[j * obs_dim + c] : 0.0f;     // tanh argument scale folded in
       sw[S2_W3 + tid] = tid < OUT * 64 ? gW3[tid] : 0.0f;
     }
     if (tid < 64) { sw[S2_B1 + tid] = TANH_PRESCALE * gb1[tid]; sw[S2_B2 + tid] = TANH_PRESCALE * gb2[tid]; }
     if (tid < 4) sw[S2_B3 + tid] = tid < OUT ? gb3[tid] : 0.0f;
-    {                                                  // W2 row j, 32 columns per thread (block only 4-byte aligned)
+    {                                                  // W2 row j, 512 / THREADS chunks per thread (block only 4-byte aligned)
+      constexpr int CW = 512 / THREADS;
       const int j = tid & 63, cq = tid >> 6;
 #pragma unroll 1
-      for (int c = 2 * cq; c < 2 * cq + 2; ++c) {
+      for (int c = CW * cq; c < CW * cq + CW; ++c) {
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = gW2[j * 64 + 8 * c + e];
@@ -136,10 +141,10 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
   }
   {                                                    // aux tiles + pad: zero, then the row of ones (n = 0)
     uint4* ax = reinterpret_cast<uint4*>(P.aux(0, 0));
-    for (int e = tid; e < (4 * T2_AUXT + 1024) / 16; e += T2_THREADS) ax[e] = make_uint4(0u, 0u, 0u, 0u);
+    for (int e = tid; e < (4 * T2_AUXT) / 16; e += THREADS) ax[e] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
-  *reinterpret_cast<unsigned short*>(P.aux(tid >> 7, 0) + aux_off(0, tid & 127)) = 0x3F80;
+  if (tid < 256) *reinterpret_cast<unsigned short*>(P.aux(tid >> 7, 0) + aux_off(0, tid & 127)) = 0x3F80;
 
   if (ACTOR && a.continuous && tid == 0) {
     const NormalConsts nc = normal_consts(a.params + gA + gC, A);
@@ -165,16 +170,25 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
   float* sdo = P.sdout();
 
   // accumulators that stay in registers for the whole kernel
-  float acc_w3[4][POL_OUT_MAX];        // dW3[k][f0 + 8 p + (lane & 7)] over samples 8 (lane >> 3) .. + 7 of this warp
+  float acc_w3[CPT][POL_OUT_MAX];      // dW3[k][f0 + 8 p + (lane & 7)] over samples 8 (lane >> 3) .. + 7 of this warp
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < CPT; ++r)
 #pragma unroll
     for (int k = 0; k < POL_OUT_MAX; ++k) acc_w3[r][k] = 0.0f;
   float acc_b3 = 0.0f;
   constexpr int NST = ACTOR ? 9 : 1;   // actor: policy loss, entropy, old kl, kl, clipfrac, d logstd[4]; critic: value loss
-  float st[NST];
+  // statistics: per-thread registers (TPS 2) or, to stay inside 64 registers (TPS 4), one smem slot per loss warp that its
+  // lane 0 owns (warp sums added tile by tile: still a fixed order)
+  constexpr bool ST_REGS = TPS == 2;
+  float st[ST_REGS ? NST : 1];
 #pragma unroll
-  for (int i = 0; i < NST; ++i) st[i] = 0.0f;
+  for (int i = 0; i < (ST_REGS ? NST : 1); ++i) st[i] = 0.0f;
+  float* sst = sw + S2_ST + (warp & 3) * 9;
+  if (!ST_REGS && tid < 36) sw[S2_ST + tid] = 0.0f;
+  auto stat_add = [&](int i, float v) {
+    if (ST_REGS) st[ST_REGS ? i : 0] += v;
+    else { const float w = warp_sum(v); if ((tid & 31) == 0) sst[i] += w; }
+  };
 
   const long long ntiles = (a.m_local + T2_S - 1) / T2_S;
   const bool any = (long long)cta < ntiles;
@@ -212,10 +226,10 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
   { const int r0 = fetch_row(cta); rown = r0 < 0 ? -1 : row_off + r0; }
   fetch_obs(rown);
 
-  // first layer of one tile: 32 features of this thread from the prefetched observation
-  auto first_layer = [&](float (&hv)[32]) {
+  // first layer of one tile: this thread's FPT features from the prefetched observation
+  auto first_layer = [&](float (&hv)[FPT]) {
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
+    for (int g = 0; g < FPT / 4; ++g) {
       const int f = f0 + 4 * g;
       const float4 b = lds4(sw + S2_B1 + f);
       float2 a01 = make_float2(b.x, b.y), a23 = make_float2(b.z, b.w);
@@ -230,8 +244,11 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
       hv[4 * g + 2] = tanh_prescaled(a23.x); hv[4 * g + 3] = tanh_prescaled(a23.y);
     }
   };
-  float h1n[32];
-  first_layer(h1n);
+  // TPS 2 computes the next tile's first layer ahead of the MMA wait and carries it across the loop edge; TPS 4 has
+  // no registers for that (and twice the warps to cover the wait): it computes it right before storing
+  constexpr bool H1_AHEAD = TPS == 2;
+  float h1n[FPT];
+  if (H1_AHEAD) first_layer(h1n);
 
   uint32_t it = 0;
 #pragma unroll 1
@@ -249,7 +266,7 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
       mbar_wait(P.bar(BAR_WG), ph ^ 1u);
       tc::fence_after_sync();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         const uint32_t col = lane_base + (uint32_t)(f0 + 8 * c);
         float d[8], hp[8];
         tc::tmem_ld8_nowait(tm_dh + col, d);
@@ -257,12 +274,13 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
         tc::tmem_wait_ld();
 #pragma unroll
         for (int e = 0; e < 8; ++e) d[e] *= fmaf(-hp[e], hp[e], 1.0f);
-        store_split_chunk(P.dz(0), P.dz(1), s, 4 * half + c, d);
+        store_split_chunk(P.dz(0), P.dz(1), s, CPT * half + c, d);
       }
     }
+    if (!H1_AHEAD) first_layer(h1n);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      store_split_chunk(P.h1(0), P.h1(1), s, 4 * half + c, h1n + 8 * c);
+    for (int c = 0; c < CPT; ++c) {
+      store_split_chunk(P.h1(0), P.h1(1), s, CPT * half + c, h1n + 8 * c);
       float hv[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) hv[e] = h1n[8 * c + e];
@@ -270,13 +288,16 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
     }
     tc::tmem_wait_st();
     {
-      // aux(t): x columns, two per thread of the sample pair
+      // aux(t): x columns, 4 / TPS per thread of the sample group
       unsigned char* ah = P.aux(ph, 0);
       unsigned char* am = P.aux(ph, 1);
+      constexpr int XC = 4 / TPS;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = 2 * half + cc;
-        const float xv = half == 0 ? x[cc] : x[2 + cc];
+      for (int cc = 0; cc < XC; ++cc) {
+        const int c = XC * half + cc;
+        float xv = x[0];
+#pragma unroll
+        for (int q = 1; q < POL_IN_PAD; ++q) xv = c == q ? x[q] : xv;
         const __nv_bfloat16 hb = __float2bfloat16_rn(xv);
         const __nv_bfloat16 mb = __float2bfloat16_rn(xv - __bfloat162float(hb));
         const int off = aux_off(1 + c, s);
@@ -318,10 +339,17 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
     // ---- second layer, head, loss
     mbar_wait(P.bar(BAR_FWD), ph);
     tc::fence_after_sync();
-    float h2[32];
-    tc::tmem_ld32(tm_z + lane_base + f0, h2);
+    float h2[FPT];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
+    for (int c = 0; c < CPT; ++c) {
+      float zc[8];
+      tc::tmem_ld8_nowait(tm_z + lane_base + (uint32_t)(f0 + 8 * c), zc);
+      tc::tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h2[8 * c + e] = zc[e];
+    }
+#pragma unroll
+    for (int g = 0; g < FPT / 4; ++g) {
       const float4 b = lds4(sw + S2_B2 + f0 + 4 * g);
       h2[4 * g] = tanh_prescaled(fmaf(h2[4 * g], TANH_PRESCALE, b.x)); h2[4 * g + 1] = tanh_prescaled(fmaf(h2[4 * g + 1], TANH_PRESCALE, b.y));
       h2[4 * g + 2] = tanh_prescaled(fmaf(h2[4 * g + 2], TANH_PRESCALE, b.z)); h2[4 * g + 3] = tanh_prescaled(fmaf(h2[4 * g + 3], TANH_PRESCALE, b.w));
@@ -333,21 +361,35 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
       if (k < OUT) {
         float p0 = 0.0f, p1 = 0.0f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < FPT / 4; ++g) {
           const float4 w = lds4(sw + S2_W3 + k * 64 + f0 + 4 * g);
           p0 = fmaf(w.x, h2[4 * g], p0); p1 = fmaf(w.y, h2[4 * g + 1], p1);
           p0 = fmaf(w.z, h2[4 * g + 2], p0); p1 = fmaf(w.w, h2[4 * g + 3], p1);
         }
         outp[k] = p0 + p1;
-        if (half == 1) sdo[k * T2_LD + s] = outp[k];
+        if (half > 0) stg[((half - 1) * POL_OUT_MAX + k) * T2_LD + s] = outp[k];     // head exchange: [slice - 1][k][sample]
       }
+    }
+    if (TPS == 4) {                                    // park h2 in its (consumed) z columns across the loss: registers
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        float hv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hv[e] = h2[8 * c + e];
+        tc::tmem_st8(tm_z + lane_base + (uint32_t)(f0 + 8 * c), hv);
+      }
+      tc::tmem_wait_st();
     }
     __syncthreads();
     if (half == 0) {
       float out[POL_OUT_MAX], dout[POL_OUT_MAX];
+      float sv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // this sample's statistic terms
 #pragma unroll
       for (int k = 0; k < POL_OUT_MAX; ++k) {
-        out[k] = k < OUT ? (outp[k] + sdo[k * T2_LD + s]) + sw[S2_B3 + k] : 0.0f;
+        float o = outp[k];
+#pragma unroll
+        for (int q = 1; q < TPS; ++q) o += stg[((q - 1) * POL_OUT_MAX + k) * T2_LD + s];
+        out[k] = k < OUT ? o + sw[S2_B3 + k] : 0.0f;
         dout[k] = 0.0f;
       }
       if (valid) {
@@ -406,11 +448,10 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
           for (int k = 0; k < POL_OUT_MAX; ++k) dout[k] = g_logp * dlp[k] + g_H * dH[k];
           if (a.continuous) {
 #pragma unroll
-            for (int k = 0; k < POL_OUT_MAX; ++k) if (k < OUT) st[(ACTOR ? 5 : 0) + k] += g_logp * g_ls[k] + g_H;
+            for (int k = 0; k < POL_OUT_MAX; ++k) if (k < OUT) sv[5 + k] = g_logp * g_ls[k] + g_H;
           }
-          st[0] += fmaxf(l1, l2); st[ACTOR ? 1 : 0] += entropy; st[ACTOR ? 2 : 0] += -logr;
-          st[ACTOR ? 3 : 0] += (ratio - 1.0f) - logr;
-          st[ACTOR ? 4 : 0] += fabsf(ratio - 1.0f) > a.clip ? 1.0f : 0.0f;
+          sv[0] = fmaxf(l1, l2); sv[1] = entropy; sv[2] = -logr; sv[3] = (ratio - 1.0f) - logr;
+          sv[4] = fabsf(ratio - 1.0f) > a.clip ? 1.0f : 0.0f;
         } else {
           const float R = e0, vold = e1, v = out[0];
           if (a.clip_vloss) {
@@ -420,25 +461,40 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
             const float w1 = vu > lc ? 1.0f : (vu == lc ? 0.5f : 0.0f);
             const float inr = (d >= -a.clip && d <= a.clip) ? 1.0f : 0.0f;
             dout[0] = (w1 * du + (1.0f - w1) * dc * inr) * a.vf_c * a.inv_m;
-            st[0] += 0.5f * fmaxf(vu, lc);
+            sv[0] = 0.5f * fmaxf(vu, lc);
           } else {
             const float d = v - vold;
             dout[0] = d * a.vf_c * a.inv_m;
-            st[0] += 0.5f * d * d;
+            sv[0] = 0.5f * d * d;
           }
         }
       }
 #pragma unroll
       for (int k = 0; k < POL_OUT_MAX; ++k) sdo[k * T2_LD + s] = dout[k];
+#pragma unroll
+      for (int i = 0; i < NST; ++i) {
+        if (ACTOR && i >= 5 && !a.continuous) break;
+        stat_add(i, sv[i]);
+      }
     }
     __syncthreads();
+    if (TPS == 4) {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        float hv[8];
+        tc::tmem_ld8_nowait(tm_z + lane_base + (uint32_t)(f0 + 8 * c), hv);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) h2[8 * c + e] = hv[e];
+      }
+    }
     float dout[POL_OUT_MAX];
 #pragma unroll
     for (int k = 0; k < POL_OUT_MAX; ++k) dout[k] = sdo[k * T2_LD + s];
     // ---- dz2 = (W3^T dout) * (1 - h2^2): operand rows of the backward MMAs (the dz tiles are free once aux_w1(t-1) retired)
     mbar_wait(P.bar(BAR_AUX), ph);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < CPT; ++c) {
       float dz2[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) dz2[e] = 0.0f;
@@ -454,7 +510,7 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) dz2[e] *= fmaf(-h2[8 * c + e], h2[8 * c + e], 1.0f);
-      store_split_chunk(P.dz(0), P.dz(1), s, 4 * half + c, dz2);
+      store_split_chunk(P.dz(0), P.dz(1), s, CPT * half + c, dz2);
     }
     tc::fence_proxy_async();
     tc::fence_before_sync();
@@ -466,8 +522,9 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
       // D_w[j][i] (+)= sum_s dz2[s][j] h1[s][i], K = 128 samples = 8 steps of 16 rows
       mma_over_samples(tm_w, tc::smem_desc_mn_sw128(P.dz(0), T2_TILE, 1024), tc::smem_desc_mn_sw128(P.h1(0), T2_TILE, 1024),
                        tc::smem_desc_mn_sw128(P.h1(1), T2_TILE, 1024), ID_WG, 128, 512, it > 0);
+      // db2 only needs the ones column of the aux tile, whose mid part is zero: one pass
       mma_over_samples(tm_b2, tc::smem_desc_mn_sw128(P.dz(0), T2_TILE, 1024), tc::smem_desc_k_sw128(P.aux(ph, 0)),
-                       tc::smem_desc_k_sw128(P.aux(ph, 1)), ID_AUX, 2, 64, it > 0);
+                       tc::smem_desc_k_sw128(P.aux(ph, 1)), ID_AUX, 2, 64, it > 0, false);
       tc::mma_commit(P.bar(BAR_WG));
     }
     // ---- dW3[k][j] += sum_s dout[s][k] h2[s][j], db3[k] += sum_s dout[s][k], warp-local (overlaps the MMAs):
@@ -478,7 +535,7 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
       const int lane = tid & 31, jj = lane & 7, qd = lane >> 3;
       const float* dbase = sdo + 32 * (warp & 3) + 8 * qd;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
+      for (int p = 0; p < CPT; ++p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) patch[j * 36 + lane] = h2[8 * p + j];
         __syncwarp();
@@ -499,7 +556,7 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
       }
     }
     // ---- first layer of the next tile (its observation was requested right after this tile's forward MMAs)
-    first_layer(h1n);
+    if (H1_AHEAD) first_layer(h1n);
   }
 
   // ---- tail: first-layer gradients of the last tile
@@ -508,7 +565,7 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
     mbar_wait(P.bar(BAR_WG), ph);
     tc::fence_after_sync();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < CPT; ++c) {
       const uint32_t col = lane_base + (uint32_t)(f0 + 8 * c);
       float d[8], hp[8];
       tc::tmem_ld8_nowait(tm_dh + col, d);
@@ -516,7 +573,7 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
       tc::tmem_wait_ld();
 #pragma unroll
       for (int e = 0; e < 8; ++e) d[e] *= fmaf(-hp[e], hp[e], 1.0f);
-      store_split_chunk(P.dz(0), P.dz(1), s, 4 * half + c, d);
+      store_split_chunk(P.dz(0), P.dz(1), s, CPT * half + c, d);
     }
     tc::fence_proxy_async();
     tc::fence_before_sync();
@@ -536,23 +593,29 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
   float* part = a.partials + ((size_t)(ACTOR ? 0 : 1) * ncta + cta) * UPD_PSTRIDE;
   const int oB1 = 64 * obs_dim, oW2 = oB1 + 64, oB2 = oW2 + 4096, oW3 = oB2 + 64, oB3 = oW3 + OUT * 64, oLS = oB3 + OUT;
   {
-    // TMEM accumulators: rows 0..63 (hi^T B) + rows 64..127 (mid^T B) = feature j; thread (row, half) reads 32 columns
-    float v[32];
+    // TMEM accumulators: rows 0..63 (hi^T B) + rows 64..127 (mid^T B) = feature j; thread (row, slice) reads FPT columns
+    float v[FPT];
     uint32_t u[16];
+#pragma unroll
+    for (int i = 0; i < FPT; ++i) v[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) u[i] = 0u;
     if (any) {
-      tc::tmem_ld32(tm_w + lane_base + f0, v);
-      tc::tmem_ld16((half == 0 ? tm_b2 : tm_w1) + lane_base, u);
-    } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+      for (int c = 0; c < CPT; ++c) {
+        float vc[8];
+        tc::tmem_ld8_nowait(tm_w + lane_base + (uint32_t)(f0 + 8 * c), vc);
+        tc::tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) u[i] = 0u;
+        for (int e = 0; e < 8; ++e) v[8 * c + e] = vc[e];
+      }
+      if (half < 2) tc::tmem_ld16((half == 0 ? tm_b2 : tm_w1) + lane_base, u);
     }
     if (s >= 64) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) stg[(s - 64) * 65 + f0 + i] = v[i];
+      for (int i = 0; i < FPT; ++i) stg[(s - 64) * 65 + f0 + i] = v[i];
       if (half == 0) sdo[s - 64] = __uint_as_float(u[0]);
-      else {
+      else if (half == 1) {
 #pragma unroll
         for (int c = 0; c < 5; ++c) sdo[64 + (s - 64) * 5 + c] = __uint_as_float(u[c]);
       }
@@ -561,9 +624,9 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
     if (s < 64) {
       const int j = s;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) part[oW2 + j * 64 + f0 + i] = v[i] + stg[j * 65 + f0 + i];
+      for (int i = 0; i < FPT; ++i) part[oW2 + j * 64 + f0 + i] = v[i] + stg[j * 65 + f0 + i];
       if (half == 0) part[oB2 + j] = __uint_as_float(u[0]) + sdo[j];
-      else {
+      else if (half == 1) {
         part[oB1 + j] = __uint_as_float(u[0]) + sdo[64 + j * 5];
 #pragma unroll
         for (int c = 0; c < POL_IN_PAD; ++c)
@@ -574,25 +637,29 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
   }
   {
     // SIMT accumulators: dW3 / db3 summed over the 8 sample slices, statistics over the warps of half 0
-    float* red = stg;   // dW3 [(half*4 + p)*4 + k][warp & 3][qd][jj] (4096), db3 [k][warp & 3][qd] (64), stats [9][4]
+    float* red = stg;   // dW3 [feature octet (f0 / 8 + p)][k][warp & 3][qd][jj] (4096), db3 [k][warp & 3][qd] (64), stats [9][4]
     const int lane = tid & 31, jj = lane & 7, qd = lane >> 3, wq = warp & 3;
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+    for (int p = 0; p < CPT; ++p)
 #pragma unroll
-      for (int k = 0; k < POL_OUT_MAX; ++k) red[((((half * 4 + p) * 4 + k) * 4 + wq) * 4 + qd) * 8 + jj] = acc_w3[p][k];
+      for (int k = 0; k < POL_OUT_MAX; ++k) red[((((half * CPT + p) * 4 + k) * 4 + wq) * 4 + qd) * 8 + jj] = acc_w3[p][k];
     if (half == 0 && jj < POL_OUT_MAX) red[4096 + (jj * 4 + wq) * 4 + qd] = acc_b3;
     if (half == 0) {
 #pragma unroll
       for (int i = 0; i < NST; ++i) {
-        const float v = warp_sum(st[i]);
-        if (lane == 0) red[4160 + i * 4 + wq] = v;
+        if (ST_REGS) {
+          const float v = warp_sum(st[ST_REGS ? i : 0]);
+          if (lane == 0) red[4160 + i * 4 + wq] = v;
+        } else if (lane == 0) {
+          red[4160 + i * 4 + wq] = sst[i];
+        }
       }
     }
     __syncthreads();
-    {
+    if (tid < 256) {
       const int f = tid & 63, k = tid >> 6;
       if (k < OUT) {
-        const float* q = red + ((((f >> 5) * 4 + ((f & 31) >> 3)) * 4 + k) * 16) * 8 + (f & 7);
+        const float* q = red + (((f >> 3) * 4 + k) * 16) * 8 + (f & 7);
         float sum = 0.0f;
 #pragma unroll
         for (int c = 0; c < 16; ++c) sum += q[c * 8];
@@ -626,26 +693,35 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
   if (warp == 0) tc::tmem_dealloc(tmem, T2_TMEM_COLS);
 }
 
-__global__ void __launch_bounds__(T2_THREADS, 2) ppo_grad_tc_kernel(UpdDev a) {
+template <int TPS>
+__global__ void __launch_bounds__(128 * TPS, 2) ppo_grad_tc_kernel(UpdDev a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   const int ncta = gridDim.x >> 1;                     // CTAs per net; blockIdx < ncta: actor, else critic
-  if ((int)blockIdx.x < ncta) tc_update_net<true>(a, base, blockIdx.x, ncta);
-  else tc_update_net<false>(a, base, blockIdx.x - ncta, ncta);
+  if ((int)blockIdx.x < ncta) tc_update_net<true, TPS>(a, base, blockIdx.x, ncta);
+  else tc_update_net<false, TPS>(a, base, blockIdx.x - ncta, ncta);
 }
 
 size_t ppo_grad_tc_smem_bytes() { return T2_SMEM; }
 
-// gx = CTAs per net (partials are [2][gx][UPD_PSTRIDE]); the grid is 2 * gx
-int launch_ppo_grad_tc(const UpdDev& d, int gx, cudaStream_t s) {
+template <int TPS>
+static int tc_attrs() {
+  AUR_CUDA_OK(cudaFuncSetAttribute(ppo_grad_tc_kernel<TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM));
+  // two CTAs per SM need the full shared-memory carve-out
+  AUR_CUDA_OK(cudaFuncSetAttribute(ppo_grad_tc_kernel<TPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  return 0;
+}
+
+// gx = CTAs per net (partials are [2][gx][UPD_PSTRIDE]); the grid is 2 * gx.  tps = threads per sample (2 or 4).
+int launch_ppo_grad_tc(const UpdDev& d, int gx, int tps, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    AUR_CUDA_OK(cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM));
-    // two CTAs per SM need the full shared-memory carve-out
-    AUR_CUDA_OK(cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int rc;
+    if ((rc = tc_attrs<2>()) || (rc = tc_attrs<4>())) return rc;
     attr = true;
   }
-  ppo_grad_tc_kernel<<<2 * gx, T2_THREADS, T2_SMEM, s>>>(d);
+  if (tps == 4) ppo_grad_tc_kernel<4><<<2 * gx, 512, T2_SMEM, s>>>(d);
+  else ppo_grad_tc_kernel<2><<<2 * gx, 256, T2_SMEM, s>>>(d);
   AUR_LAUNCH_OK("ppo_grad_tc_kernel");
   return 0;
 }

@@ -13,14 +13,14 @@ from tests.helpers import flat_from_named, random_policy
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["tc", "simt"])
+@pytest.fixture(autouse=True, params=["tc", "tc4", "simt"])
 def update_impl(request):
-    """Every test runs against both CUDA implementations of aur_ppo_update_grad: the tcgen05 kernel (default)
-    and the independent SIMT fp32 kernel."""
+    """Every test runs against all CUDA implementations of aur_ppo_update_grad: the tcgen05 kernel with two or four
+    threads per sample and the independent SIMT fp32 kernel."""
     from aur_ppo_b200 import _lib
     L = _lib.lib()
     prev = L.aur_ppo_update_get_impl()
-    assert L.aur_ppo_update_set_impl(1 if request.param == "tc" else 0) == 0
+    assert L.aur_ppo_update_set_impl({"simt": 0, "tc": 1, "tc4": 2}[request.param]) == 0
     yield request.param
     L.aur_ppo_update_set_impl(prev)
 
