@@ -297,9 +297,9 @@ def run_ours(args):
         {"kernel": "gae_bulk_kernel", "bound": "hbm", "achieved": gae_gbps, "peak": hbm_peak, "unit": "GB/s",
          "frac": gae_gbps / hbm_peak, "traffic": traffic.get("gae_bulk_kernel"), "algorithmic_bytes": gae_bytes,
          "ms": t_gae},
-        {"kernel": "rollout_kernel (+ critic_values_tc_kernel)", "bound": "hbm", "achieved": 36.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e9,
+        {"kernel": "rollout_tc_kernel + critic_values_tc_kernel", "bound": "hbm", "achieved": 36.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e9,
          "peak": hbm_peak, "unit": "GB/s", "frac": 36.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e9 / hbm_peak,
-         "traffic": traffic.get("rollout_kernel"), "ms": t_roll,
+         "traffic": (traffic.get("rollout_tc_kernel", 0) + traffic.get("critic_values_tc_kernel", 0)) or None, "ms": t_roll,
          "fp32_tflops": 17792.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e12,
          "fp32_frac_of_nominal": 17792.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e12 / FP32_PEAK_TFLOPS},
         {"kernel": "ppo_grad_tc_kernel (+shuffle, moments, reduce, adam)", "bound": "tensor", "achieved": upd_tflops,
