@@ -20,13 +20,14 @@
 namespace aur {
 namespace tc {
 
-constexpr int CV_BM = 128, CV_BN = 128, CV_BK = 64, CV_STAGES = 3;
+constexpr int CV_BM = 128, CV_BN = 128, CV_BK = 64, CV_STAGES = 6;
 constexpr int CV_A_BYTES = CV_BM * CV_BK * 2, CV_B_BYTES = CV_BN * CV_BK * 2;
 constexpr size_t CV_SMEM = (size_t)CV_STAGES * (CV_A_BYTES + CV_B_BYTES) + 1024 + 256;
 
 struct ConvDev {
   int B, Hb, Wb, Ho, Wo, Cin, Cout;
   int TH, TW, NIMG, tiles_x, tiles_y;      // pixel tile = NIMG images x TH x TW = 128
+  int pix_tiles, n_tiles;                  // work items: pix_tiles x n_tiles (output-channel blocks), walked by a persistent grid
   int epi;                                 // 0 linear, 1 bias+ReLU, 2 bias+ReLU+maxpool2
   int oHb, oWb, ooff;                      // output buffer geometry
   const float* bias;
@@ -36,7 +37,10 @@ struct ConvDev {
   int rHb, rWb, roff;
 };
 
-__global__ void __launch_bounds__(256, 2)
+// Persistent: one CTA per SM walks the (pixel tile, channel block) items with a grid stride; the smem ring runs
+// across items and the accumulator is double-buffered in TMEM (2 x 128 columns), so the epilogue of item i (TMEM ->
+// bias / ReLU / pool -> bf16 stores) overlaps the TMA + MMA main loop of item i+1.
+__global__ void __launch_bounds__(256, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvDev a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
@@ -44,60 +48,75 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   unsigned char* sB = smem + CV_STAGES * CV_A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + CV_STAGES * CV_B_BYTES);
   uint64_t* empty = full + CV_STAGES;
-  uint64_t* tmem_full = empty + CV_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + CV_STAGES;       // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // pixel tile decode
-  int t = blockIdx.x;
-  const int tx = t % a.tiles_x; t /= a.tiles_x;
-  const int ty = t % a.tiles_y; t /= a.tiles_y;
-  const int b0 = t * a.NIMG, y0 = ty * a.TH, x0 = tx * a.TW;
-  const int n0 = blockIdx.y * CV_BN;
   const int cchunks = a.Cin / CV_BK;
   const int nkb = 9 * cchunks;
+  const long long items = (long long)a.pix_tiles * a.n_tiles;
+  // item -> (pixel tile, channel block): channel blocks of one pixel tile are adjacent, so the CTAs of a wave share A
+  auto decode = [&](long long item, int& b0, int& y0, int& x0, int& n0) {
+    n0 = (int)(item % a.n_tiles) * CV_BN;
+    int t = (int)(item / a.n_tiles);
+    const int tx = t % a.tiles_x; t /= a.tiles_x;
+    const int ty = t % a.tiles_y; t /= a.tiles_y;
+    b0 = t * a.NIMG; y0 = ty * a.TH; x0 = tx * a.TW;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CV_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     mbar_fence_init();
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
   }
-  if (warp == 2) tmem_alloc(tmem_slot, CV_BN);
+  if (warp == 2) tmem_alloc(tmem_slot, 2 * CV_BN);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    // ===== TMA producer: K loop over (tap, channel chunk) =====
-    int kb = 0;
-    for (int tap = 0; tap < 9; ++tap) {
-      const int dy = tap / 3, dx = tap - 3 * dy;
-      for (int cc = 0; cc < cchunks; ++cc, ++kb) {
-        const int s = kb % CV_STAGES;
-        const uint32_t ph = (kb / CV_STAGES) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[s], CV_A_BYTES + CV_B_BYTES);
-        tma_load_4d(sA + s * CV_A_BYTES, &tmA, cc * CV_BK, x0 + dx, y0 + dy, b0, &full[s]);
-        tma_load_2d(sB + s * CV_B_BYTES, &tmB, tap * a.Cin + cc * CV_BK, n0, &full[s]);
+    // ===== TMA producer: per item, K loop over (tap, channel chunk); the ring index runs across items =====
+    uint32_t kg = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+      int b0, y0, x0, n0;
+      decode(item, b0, y0, x0, n0);
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3, dx = tap - 3 * dy;
+        for (int cc = 0; cc < cchunks; ++cc, ++kg) {
+          const int s = kg % CV_STAGES;
+          const uint32_t ph = (kg / CV_STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], CV_A_BYTES + CV_B_BYTES);
+          tma_load_4d(sA + s * CV_A_BYTES, &tmA, cc * CV_BK, x0 + dx, y0 + dy, b0, &full[s]);
+          tma_load_2d(sB + s * CV_B_BYTES, &tmB, tap * a.Cin + cc * CV_BK, n0, &full[s]);
+        }
       }
     }
   } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: accumulator (it & 1) once the epilogue has drained its previous use =====
     constexpr uint32_t idesc = instr_desc(FMT_BF16, CV_BM, CV_BN, 0, 0);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % CV_STAGES;
-      const uint32_t ph = (kb / CV_STAGES) & 1u;
-      mbar_wait(&full[s], ph);
+    uint32_t kg = 0, it = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u;
+      mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
       fence_after_sync();
-      const uint64_t ad = smem_desc_k_sw128(sA + s * CV_A_BYTES), bd = smem_desc_k_sw128(sB + s * CV_B_BYTES);
+      for (int kb = 0; kb < nkb; ++kb, ++kg) {
+        const int s = kg % CV_STAGES;
+        const uint32_t ph = (kg / CV_STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        fence_after_sync();
+        const uint64_t ad = smem_desc_k_sw128(sA + s * CV_A_BYTES), bd = smem_desc_k_sw128(sB + s * CV_B_BYTES);
 #pragma unroll
-      for (int k = 0; k < CV_BK / 16; ++k) mma_f16(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-      mma_commit(&empty[s]);
+        for (int k = 0; k < CV_BK / 16; ++k)
+          mma_f16(tmem_d + acc * CV_BN, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+        mma_commit(&empty[s]);
+      }
+      mma_commit(&tmem_full[acc]);
     }
-    mma_commit(tmem_full);
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> (bias, ReLU, pool) -> bf16 NHWC =====
     const int q = warp - 4;
@@ -105,16 +124,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int r = m;
     const int xx = r % a.TW; r /= a.TW;
     const int yy = r % a.TH; r /= a.TH;
+    uint32_t it = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+    int b0, y0, x0, n0;
+    decode(item, b0, y0, x0, n0);
+    const uint32_t acc = it & 1u;
     const int b = b0 + r, y = y0 + yy, x = x0 + xx;
     const bool valid = b < a.B && y < a.Ho && x < a.Wo;
-    mbar_wait(tmem_full, 0);
+    mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
     fence_after_sync();
 #pragma unroll 1
     for (int c = 0; c < CV_BN; c += 32) {
       float v[32];
-      tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+      tmem_ld32(tmem_d + acc * CV_BN + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+      if (c + 32 == CV_BN) {                            // last read of this accumulator: hand it back to the MMA warp
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
       const int ch = n0 + c;
-      if (ch >= a.Cout) break;
+      if (ch >= a.Cout) continue;
       if (a.epi == 1 || a.epi == 2) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + (a.bias ? __ldg(a.bias + ch + i) : 0.0f), 0.0f);
@@ -186,10 +215,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
+    }   // items
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_d, CV_BN);
+  if (warp == 2) tmem_dealloc(tmem_d, 2 * CV_BN);
 }
 
 // psi [Fo,Fi,4,3,3] fp32 -> Wmat [(o,r)][tap][(i,s)] bf16 (forward) and, if wt != NULL, the
@@ -390,7 +420,10 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM));
     attr = true;
   }
-  dim3 grid((unsigned)(img_groups * d.tiles_y * d.tiles_x), (unsigned)((c.Cout + CV_BN - 1) / CV_BN));
+  d.pix_tiles = (int)(img_groups * d.tiles_y * d.tiles_x);
+  d.n_tiles = (c.Cout + CV_BN - 1) / CV_BN;
+  const long long items = (long long)d.pix_tiles * d.n_tiles;
+  const unsigned grid = (unsigned)(items < sm_count() ? items : sm_count());
   conv_igemm_kernel<<<grid, 256, CV_SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
   AUR_LAUNCH_OK("conv_igemm_kernel");
   return 0;
