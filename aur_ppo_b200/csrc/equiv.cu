@@ -40,7 +40,8 @@ struct ConvDev {
 // Persistent: one CTA per SM walks the (pixel tile, channel block) items with a grid stride; the smem ring runs
 // across items and the accumulator is double-buffered in TMEM (2 x 128 columns), so the epilogue of item i (TMEM ->
 // bias / ReLU / pool -> bf16 stores) overlaps the TMA + MMA main loop of item i+1.
-__global__ void __launch_bounds__(256, 1)
+constexpr int CV_THREADS = 384;   // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 epilogue (two per TMEM lane quarter)
+__global__ void __launch_bounds__(CV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvDev a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
@@ -67,7 +68,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CV_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
     mbar_fence_init();
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
@@ -119,7 +120,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> (bias, ReLU, pool) -> bf16 NHWC =====
-    const int q = warp - 4;
+    const int q = (warp - 4) & 3, chalf = (warp - 4) >> 2;     // TMEM lane quarter, half of the 128 accumulator columns
     const int m = 32 * q + lane;
     int r = m;
     const int xx = r % a.TW; r /= a.TW;
@@ -134,10 +135,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
     fence_after_sync();
 #pragma unroll 1
-    for (int c = 0; c < CV_BN; c += 32) {
+    for (int c = 64 * chalf; c < 64 * chalf + 64; c += 32) {
       float v[32];
       tmem_ld32(tmem_d + acc * CV_BN + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
-      if (c + 32 == CV_BN) {                            // last read of this accumulator: hand it back to the MMA warp
+      if (c + 32 == 64 * chalf + 64) {                  // last read of this accumulator: hand it back to the MMA warp
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -149,24 +150,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + (a.bias ? __ldg(a.bias + ch + i) : 0.0f), 0.0f);
       }
       if (a.epi == 2) {
-        // 2x2 max pool: window partners are lane^1 (x) and lane^TW (y); first maximum in (y,x) scan
-        // order wins ties, like torch's max_pool2d backward.
-        const int w = ((yy & 1) << 1) | (xx & 1);
+        // 2x2 max pool: window partners are lane^1 (x) and lane^TW (y); first maximum in (y,x) scan order wins
+        // ties, like torch's max_pool2d backward.  Post-ReLU values are >= 0, so their bit patterns order like
+        // unsigned integers: the window index rides in the two lowest mantissa bits (as 3 - w, so that the earlier
+        // position wins a tie) and ONE shuffle + max per partner does value and arg-max together; the 2^-22
+        // relative truncation disappears in the bf16 rounding of the stored activation.
+        const unsigned int w = (unsigned int)(((yy & 1) << 1) | (xx & 1));
         unsigned int arg_pack[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) arg_pack[i] = 0u;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float best = v[i];
-          int bw = w;
-          float o = __shfl_xor_sync(0xffffffffu, best, 1);
-          int ow = __shfl_xor_sync(0xffffffffu, bw, 1);
-          if (o > best || (o == best && ow < bw)) { best = o; bw = ow; }
-          o = __shfl_xor_sync(0xffffffffu, best, a.TW);
-          ow = __shfl_xor_sync(0xffffffffu, bw, a.TW);
-          if (o > best || (o == best && ow < bw)) { best = o; bw = ow; }
-          v[i] = best;
-          arg_pack[i >> 2] |= (unsigned int)bw << (8 * (i & 3));
+          unsigned int key = (__float_as_uint(v[i]) & 0x7FFFFFFCu) | (3u - w);     // (sign bit cleared: fmaxf may return -0)
+          key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
+          key = max(key, __shfl_xor_sync(0xffffffffu, key, a.TW));
+          v[i] = __uint_as_float(key & ~3u);
+          arg_pack[i >> 2] |= (3u - (key & 3u)) << (8 * (i & 3));
         }
         if (valid && w == 0) {
           const size_t pix = ((size_t)b * a.oHb + (y >> 1) + a.ooff) * a.oWb + (x >> 1) + a.ooff;
@@ -424,7 +423,7 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   d.n_tiles = (c.Cout + CV_BN - 1) / CV_BN;
   const long long items = (long long)d.pix_tiles * d.n_tiles;
   const unsigned grid = (unsigned)(items < sm_count() ? items : sm_count());
-  conv_igemm_kernel<<<grid, 256, CV_SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
+  conv_igemm_kernel<<<grid, CV_THREADS, CV_SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
   AUR_LAUNCH_OK("conv_igemm_kernel");
   return 0;
 }
