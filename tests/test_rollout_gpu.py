@@ -297,3 +297,44 @@ def test_pendulum_sampling_moments():
     with torch.no_grad():
         _, lp, _, _ = pol.evaluate(obs, buf.actions.cpu().reshape(-1, 1))
     np.testing.assert_allclose(buf.log_probs.cpu().reshape(-1).numpy(), lp.numpy(), rtol=2e-5, atol=5e-6)
+
+
+def test_full_size_rollout_properties():
+    """BASELINE config B rollout (65536 envs x 128 steps, sampled actions), through size-independent properties: a
+    random subset of env columns replays bit-exactly on the CPU checker with the actions the device drew, every reward
+    is 1, and the episode totals merged on the device equal what the done / truncation pattern implies."""
+    N, T = 65536, 128
+    pol, named = random_policy(4, 2, 64, 2, False, seed=4)
+    desc = kernels.policy_desc(4, 2, 64, 2, False)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    env = denv.DeviceVecEnv("CartPole-v1", N)
+    env.reset(list(range(N)))
+    buf = kernels.RolloutBuffers(T, N, 4, (), "cuda")
+    kernels.rollout(env, desc, flat, buf, seed=7, step0=0)
+    torch.cuda.synchronize()
+    assert torch.all(buf.rewards == 1.0)
+    acts = buf.actions.cpu().numpy()
+    assert set(np.unique(acts)) <= {0.0, 1.0} and 0.3 < acts.mean() < 0.7
+    cols = np.sort(np.random.default_rng(0).choice(N, 96, replace=False))
+    cv = E.CVecEnv(E.CARTPOLE, len(cols), wrappers=False, trig=E.TRIG_DET)
+    cur, _ = cv.reset([int(c) for c in cols])            # env i is seeded with its global id
+    cur_done = np.zeros(len(cols), np.float32)
+    states, terminals = buf.states.cpu().numpy(), buf.terminals.cpu().numpy()
+    finished = 0
+    for t in range(T):
+        assert np.array_equal(states[t, cols], cur) and np.array_equal(terminals[t, cols], cur_done), t
+        cur, r, term, trunc, info = cv.step(acts[t, cols].astype(np.int32))
+        cur_done = term.astype(np.float32)
+        finished += int((term | trunc).sum())
+    assert np.array_equal(env.next_obs.cpu().numpy()[cols], cur)
+    assert np.array_equal(env.phys.cpu().numpy().T[cols], cv.phys())
+    tot = env.totals.cpu().numpy()
+    # every terminated step is followed by a `done` flag in the next row (or in next_done after the last row)
+    n_term = int(buf.terminals[1:].sum().item() + env.next_done.sum().item())
+    assert tot[0] == n_term and finished > 0              # no TimeLimit truncation can occur in 128 steps
+    # log-probs / values of the subset against the oracle model
+    ot = torch.from_numpy(states[:, cols[:16]].reshape(-1, 4)); at = torch.from_numpy(acts[:, cols[:16]].reshape(-1))
+    with torch.no_grad():
+        _, lp, _, v = pol.evaluate(ot, at)
+    np.testing.assert_allclose(buf.log_probs.cpu().numpy()[:, cols[:16]].reshape(-1), lp.numpy(), **TOL)
+    np.testing.assert_allclose(buf.values.cpu().numpy()[:, cols[:16]].reshape(-1), v.numpy().reshape(-1), **TOL)

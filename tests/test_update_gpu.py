@@ -176,3 +176,42 @@ def test_packed_records_give_the_same_update(cont, update_impl):
         assert torch.equal(ga, gb)
     assert torch.equal(a.params, b.params)
     assert kernels.pack_records(torch.zeros(8, 6, device="cuda"), *bufs[1:]) is None   # obs_dim > 4 does not fit a record
+
+
+def test_full_size_minibatch_properties():
+    """BASELINE config B minibatch (2,097,152 samples of an 8,388,608-sample batch), through size-independent properties:
+    (1) the tensor-core and the independent SIMT kernel agree within the 1e-4 bar, (2) gradient sums are additive over a
+    split of the minibatch (checksum of checksums), (3) packed records give bit-identical results."""
+    from aur_ppo_b200 import _lib
+    L = _lib.lib()
+    B, m = 8388608, 2097152
+    _, named = random_policy(4, 2, 64, 2, False, seed=2)
+    desc = kernels.policy_desc(4, 2, 64, 2, False)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    bufs = [torch.randn(B, 4, generator=g, device="cuda") * 0.5, torch.randint(0, 2, (B,), generator=g, device="cuda").float(),
+            -0.7 + 0.1 * torch.randn(B, generator=g, device="cuda"), torch.randn(B, generator=g, device="cuda"),
+            torch.randn(B, generator=g, device="cuda"), torch.randn(B, generator=g, device="cuda")]
+    idx = kernels.shuffle_indices(B, seed=5, stream_id=0)[:m].contiguous()
+    prev = L.aur_ppo_update_get_impl()
+    try:
+        out = {}
+        for name, impl in (("tc", 1), ("simt", 0)):
+            L.aur_ppo_update_set_impl(impl)
+            up = kernels.Updater(desc, flat.clone())
+            out[name] = up.grad(*bufs, idx).clone()
+            if name == "tc":
+                rec = kernels.pack_records(*bufs)
+                assert torch.equal(up.grad(*bufs, idx, records=rec), out["tc"])
+                # additivity (advantage normalisation off so that the halves share nothing but the weights)
+                whole = up.grad(*bufs, idx, norm_adv=False).clone()
+                a = up.grad(*bufs, idx[: m // 2].contiguous(), m_total=m, norm_adv=False).clone()
+                b = up.grad(*bufs, idx[m // 2:].contiguous(), m_total=m, norm_adv=False).clone()
+                scale = whole[:up.P].abs().max().item()
+                np.testing.assert_allclose((a + b).cpu().numpy(), whole.cpu().numpy(), rtol=2e-5, atol=2e-6 * scale + 1e-9)
+        P = policy_p = kernels.policy_param_count(desc)
+        gt, gs = out["tc"][:P].cpu().numpy(), out["simt"][:P].cpu().numpy()
+        np.testing.assert_allclose(gt, gs, rtol=1e-4, atol=1e-4 * float(np.abs(gs).max()))
+        np.testing.assert_allclose(out["tc"][P:P + 6].cpu().numpy(), out["simt"][P:P + 6].cpu().numpy(), rtol=1e-4)
+    finally:
+        L.aur_ppo_update_set_impl(prev)
