@@ -8,10 +8,15 @@
 //   heads / loss         actor head decode + Normal log-prob / entropy + PPO loss seeds (robot_ppo.py:345-398),
 //                        critic head ReLU + GroupPooling + value and its backward
 //   adam_flat / sumsq    torch Adam math on large flat buffers, global-norm clipping
+#include <stdlib.h>
+
 #include "tc.cuh"
 
 namespace aur {
 namespace tc {
+
+int launch_conv0_wgrad_tc(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg, int B,
+                          float* dw0, float* dbias_ch, cudaStream_t s);
 
 constexpr int WG_BM = 128, WG_BN = 128, WG_BK = 64, WG_STAGES = 4;
 constexpr int WG_A_BYTES = WG_BM * WG_BK * 2, WG_B_BYTES = WG_BN * WG_BK * 2;
@@ -640,9 +645,16 @@ extern "C" int aur_equiv_conv0_wgrad(const float* obs, const float* state, const
   }
   cudaStream_t s = (cudaStream_t)stream;
   AUR_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(float) * (64 * 18 + 64), s));
-  conv0_wgrad_kernel<<<148 * 8, 256, 0, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg, B, scratch,
-                                            scratch + 64 * 18);
-  AUR_LAUNCH_OK("conv0_wgrad_kernel");
+  static int simt = -1;                              // AUR_CONV0_WGRAD=simt keeps the fp32 SIMT kernel (cross-check)
+  if (simt < 0) { const char* e = getenv("AUR_CONV0_WGRAD"); simt = (e && e[0] == 's') ? 1 : 0; }
+  if (simt) {
+    conv0_wgrad_kernel<<<148 * 8, 256, 0, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg, B, scratch,
+                                              scratch + 64 * 18);
+    AUR_LAUNCH_OK("conv0_wgrad_kernel");
+  } else {
+    int rc = aur::tc::launch_conv0_wgrad_tc(obs, state, da1, a1, arg, B, scratch, scratch + 64 * 18, s);
+    if (rc) return rc;
+  }
   project_conv0_kernel<<<(64 * 18 + 255) / 256, 256, 0, s>>>(scratch, scratch + 64 * 18, dpsi, dbias_f);
   AUR_LAUNCH_OK("project_conv0_kernel");
   return 0;

@@ -78,6 +78,35 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
+def test_conv0_weight_gradient_matches_autograd():
+    """aur_equiv_conv0_wgrad (tensor-core kernel: per-window masked gradients x bf16 hi/mid patches) against torch
+    autograd through conv2d + ReLU + max_pool2d, with the device's own forward (activations, arg-max) as the routing."""
+    import ctypes
+    from aur_ppo_b200 import _lib
+    g = torch.Generator().manual_seed(11)
+    B = 5
+    psi = (torch.randn(16, 2, 3, 3, generator=g) * 0.3).requires_grad_(True)
+    bias = (0.1 * torch.randn(16, generator=g)).requires_grad_(True)
+    obs = torch.rand(B, 1, 128, 128, generator=g) * 0.32
+    state = (torch.rand(B, generator=g) > 0.5).float()
+    out = torch.zeros(B, 66, 66, 64, dtype=torch.bfloat16, device="cuda")
+    arg = torch.zeros(B, 64, 64, 64, dtype=torch.uint8, device="cuda")
+    kernels.equiv_conv0(obs.cuda(), state.cuda(), psi.detach().cuda(), bias.detach().cuda(), out, arg)
+    da1 = (torch.randn(B, 64, 64, 64, generator=g) * 0.1).to(torch.bfloat16)          # upstream gradient, NHWC
+    x = Q.cat_obs(state, obs)
+    y = F.max_pool2d(F.relu(F.conv2d(x, Q.expand_trivial_to_regular(psi), Q.expand_bias_regular(bias), padding=1)), 2)
+    y.backward(da1.float().permute(0, 3, 1, 2))
+    ws = torch.zeros(64 * 18 + 64, device="cuda")
+    dpsi, dbias = torch.zeros(16, 2, 3, 3, device="cuda"), torch.zeros(16, device="cuda")
+    rc = _lib.lib().aur_equiv_conv0_wgrad(obs.cuda().data_ptr(), state.cuda().data_ptr(), da1.cuda().data_ptr(), out.data_ptr(),
+                                          arg.data_ptr(), B, ws.data_ptr(), dpsi.data_ptr(), dbias.data_ptr(), None)
+    _lib.check(rc, "aur_equiv_conv0_wgrad")
+    torch.cuda.synchronize()
+    # the only difference: fp32 vs bf16-stored forward decides a few near-tie arg-max / ReLU routings
+    assert _rel(dpsi.cpu(), psi.grad) < 2e-2, _rel(dpsi.cpu(), psi.grad)
+    assert _rel(dbias.cpu(), bias.grad) < 2e-2, _rel(dbias.cpu(), bias.grad)
+
+
 def test_full_update_gradients_match_oracle_autograd():
     """Whole row X on a small batch: forward values, loss statistics and EVERY parameter gradient
     against torch autograd of the restated model.
