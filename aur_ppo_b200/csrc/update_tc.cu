@@ -531,14 +531,23 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
     // a warp transposes its 32 samples x 8 features through a private smem patch ([8][36] floats, conflict-free
     // both ways), lane = (feature jj, sample octet qd) then sums 8 samples; 4 passes, no CTA barrier.
     {
-      float* patch = stg + warp * (8 * 36);
+      // TPS 2: two patches per warp, the stores of pass p+1 are issued before the loads of pass p (one __syncwarp per
+      // pass instead of a store -> sync -> load -> sync chain); TPS 4 has room for one patch per warp
+      constexpr int NPATCH = TPS == 2 ? 2 : 1;
+      float* patch0 = stg + warp * (NPATCH * 8 * 36);
       const int lane = tid & 31, jj = lane & 7, qd = lane >> 3;
       const float* dbase = sdo + 32 * (warp & 3) + 8 * qd;
-#pragma unroll
-      for (int p = 0; p < CPT; ++p) {
+      auto put = [&](int p) {
+        float* patch = patch0 + (p % NPATCH) * (8 * 36);
 #pragma unroll
         for (int j = 0; j < 8; ++j) patch[j * 36 + lane] = h2[8 * p + j];
-        __syncwarp();
+      };
+      put(0);
+      __syncwarp();
+#pragma unroll
+      for (int p = 0; p < CPT; ++p) {
+        if (NPATCH == 2 && p + 1 < CPT) put(p + 1);
+        const float* patch = patch0 + (p % NPATCH) * (8 * 36);
         const float4 ha = lds4(patch + jj * 36 + 8 * qd), hb = lds4(patch + jj * 36 + 8 * qd + 4);
 #pragma unroll
         for (int k = 0; k < POL_OUT_MAX; ++k) {
@@ -553,6 +562,7 @@ __device__ __forceinline__ void tc_update_net(const UpdDev& a, unsigned char* sm
           }
         }
         __syncwarp();
+        if (NPATCH == 1 && p + 1 < CPT) { put(p + 1); __syncwarp(); }
       }
     }
     // ---- first layer of the next tile (its observation was requested right after this tile's forward MMAs)
