@@ -18,11 +18,13 @@ namespace tc {
 int launch_conv0_wgrad_tc(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg, int B,
                           float* dw0, float* dbias_ch, cudaStream_t s);
 
-constexpr int WG_BM = 128, WG_BN = 128, WG_BK = 64, WG_STAGES = 4;
+constexpr int WG_BM = 128, WG_BN = 128, WG_BK = 64, WG_STAGES = 3, WG_TAPS = 3;
 constexpr int WG_A_BYTES = WG_BM * WG_BK * 2, WG_B_BYTES = WG_BN * WG_BK * 2;
-constexpr size_t WG_SMEM = (size_t)WG_STAGES * (WG_A_BYTES + WG_B_BYTES) + 1024 + 256;
+constexpr size_t WG_SMEM = (size_t)WG_STAGES * (WG_A_BYTES + WG_TAPS * WG_B_BYTES) + 1024 + 256;
 
-// grid: x = (Cout tiles) * (Cin tiles), y = tap, z = split-K slice.
+// grid: x = (Cout tiles) * (Cin tiles), y = tap ROW dy, z = split-K slice.  A CTA computes the three taps dx = 0, 1, 2 of
+// its row from ONE load of the output-gradient tile per stage (three shifted input tiles, three TMEM accumulators): the
+// gradient operand is fetched 3x instead of 9x, 85 B of operands per MMA cycle instead of 128.
 // Operands come STRAIGHT from the NHWC buffers (pixel rows, channels contiguous) as MN-major UMMA
 // operands: a stage holds, per operand, two TMA boxes of [64 pixel rows][64 channels] (128-B rows,
 // 128-B swizzle); 8 pixel rows form one 1024-B swizzle atom, the two channel halves are 8192 B apart
@@ -35,7 +37,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   unsigned char* sA = smem;
   unsigned char* sB = smem + WG_STAGES * WG_A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + WG_STAGES * WG_B_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + WG_STAGES * WG_TAPS * WG_B_BYTES);
   uint64_t* empty = full + WG_STAGES;
   uint64_t* tmem_full = empty + WG_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -43,9 +45,8 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x / n_tiles, nt = blockIdx.x - mt * n_tiles;
   const int m0 = mt * WG_BM, n0 = nt * WG_BN;
-  const int tap = blockIdx.y;
-  const int dy = tap / 3, dx = tap - 3 * dy;
-  const int off = base_off + dy * Wb + dx;
+  const int dy = blockIdx.y;
+  const int off = base_off + dy * Wb;                  // + dx for the three taps of this row
   const long long nkb_total = (Q + WG_BK - 1) / WG_BK;
   const long long per = (nkb_total + gridDim.z - 1) / gridDim.z;
   const long long kb_lo = (long long)blockIdx.z * per;
@@ -60,7 +61,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
   }
-  if (warp == 2) tmem_alloc(tmem_slot, WG_BN);
+  if (warp == 2) tmem_alloc(tmem_slot, 512);          // 3 x 128 accumulator columns (power of two)
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -73,13 +74,15 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t ph = (i / WG_STAGES) & 1u;
         const long long k0 = (kb_lo + i) * WG_BK;
         mbar_wait(&empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[s], WG_A_BYTES + WG_B_BYTES);
+        mbar_arrive_expect_tx(&full[s], WG_A_BYTES + WG_TAPS * WG_B_BYTES);
         unsigned char* a = sA + s * WG_A_BYTES;
-        unsigned char* b = sB + s * WG_B_BYTES;
         tma_load_2d(a, &tmA, m0, (int)k0, &full[s]);
         tma_load_2d(a + 8192, &tmA, m0 + 64, (int)k0, &full[s]);
-        tma_load_2d(b, &tmB, n0, (int)(k0 + off), &full[s]);
-        tma_load_2d(b + 8192, &tmB, n0 + 64, (int)(k0 + off), &full[s]);
+        for (int dx = 0; dx < WG_TAPS; ++dx) {
+          unsigned char* b = sB + (s * WG_TAPS + dx) * WG_B_BYTES;
+          tma_load_2d(b, &tmB, n0, (int)(k0 + off + dx), &full[s]);
+          tma_load_2d(b + 8192, &tmB, n0 + 64, (int)(k0 + off + dx), &full[s]);
+        }
       }
     } else if (warp == 1 && lane == 0) {
       constexpr uint32_t idesc = instr_desc(FMT_BF16, WG_BM, WG_BN, 1, 1);     // both operands MN-major
@@ -89,10 +92,12 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&full[s], ph);
         fence_after_sync();
         const uint64_t ad = smem_desc_mn_sw128(sA + s * WG_A_BYTES, 8192, 1024);
-        const uint64_t bd = smem_desc_mn_sw128(sB + s * WG_B_BYTES, 8192, 1024);
+        for (int dx = 0; dx < WG_TAPS; ++dx) {
+          const uint64_t bd = smem_desc_mn_sw128(sB + (s * WG_TAPS + dx) * WG_B_BYTES, 8192, 1024);
 #pragma unroll
-        for (int k = 0; k < WG_BK / 16; ++k)        // 16 pixel rows per MMA = 2048 B = 128 x 16 B
-          mma_f16(tmem_d, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (i | k) != 0);
+          for (int k = 0; k < WG_BK / 16; ++k)      // 16 pixel rows per MMA = 2048 B = 128 x 16 B
+            mma_f16(tmem_d + dx * WG_BN, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (i | k) != 0);
+        }
         mma_commit(&empty[s]);
       }
       mma_commit(tmem_full);
@@ -102,9 +107,10 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       fence_after_sync();
       const int co = m0 + 32 * q + lane;
 #pragma unroll 1
-      for (int c = 0; c < WG_BN; c += 32) {
+      for (int cc = 0; cc < WG_TAPS * WG_BN; cc += 32) {
+        const int dx = cc / WG_BN, c = cc - dx * WG_BN, tap = dy * 3 + dx;
         float v[32];
-        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)cc, v);
         if (co < Cout) {
           float* dst = dwmat + ((size_t)co * 9 + tap) * Cin + n0 + c;
 #pragma unroll
@@ -116,7 +122,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_d, WG_BN);
+  if (warp == 2) tmem_dealloc(tmem_d, 512);
 }
 
 // ---- max-pool(2) + ReLU backward: one thread per pooled pixel x 8 channels ------------------
@@ -588,13 +594,13 @@ extern "C" int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const voi
   }
   const int mt = (Cout + WG_BM - 1) / WG_BM, nt = (Cin + WG_BN - 1) / WG_BN;
   if (split_k < 1) {
-    const int tiles = mt * nt * 9;
+    const int tiles = mt * nt * 3;
     split_k = (2 * sm_count() + tiles - 1) / tiles;
     const long long nkb = (Q + WG_BK - 1) / WG_BK;
     if (split_k > nkb / 8) split_k = (int)(nkb / 8 > 0 ? nkb / 8 : 1);
     if (split_k < 1) split_k = 1;
   }
-  dim3 grid((unsigned)(mt * nt), 9, (unsigned)split_k);
+  dim3 grid((unsigned)(mt * nt), 3, (unsigned)split_k);
   wgrad3x3_kernel<<<grid, 256, WG_SMEM, (cudaStream_t)stream>>>(tmA, tmB, Cout, Cin, (long long)Q, base_off, Wb, nt, dwmat);
   AUR_LAUNCH_OK("wgrad3x3_kernel");
   return 0;
