@@ -20,9 +20,15 @@
 namespace aur {
 namespace tc {
 
-constexpr int CV_BM = 128, CV_BN = 128, CV_BK = 64, CV_STAGES = 6;
-constexpr int CV_A_BYTES = CV_BM * CV_BK * 2, CV_B_BYTES = CV_BN * CV_BK * 2;
-constexpr size_t CV_SMEM = (size_t)CV_STAGES * (CV_A_BYTES + CV_B_BYTES) + 1024 + 256;
+// Output-channel tile BN = 128 (6 stages) or 256 (4 stages; one pixel tile then feeds twice the MMA work: 94 B of
+// operands per MMA cycle instead of 128).  Both use 192 KB of operand stages and 2 x BN TMEM columns.
+constexpr int CV_BM = 128, CV_BK = 64;
+constexpr int CV_A_BYTES = CV_BM * CV_BK * 2;
+template <int BN> struct CvCfg {
+  static constexpr int STAGES = BN == 128 ? 6 : 4;
+  static constexpr int B_BYTES = BN * CV_BK * 2;
+  static constexpr size_t SMEM = (size_t)STAGES * (CV_A_BYTES + B_BYTES) + 1024 + 256;
+};
 
 struct ConvDev {
   int B, Hb, Wb, Ho, Wo, Cin, Cout;
@@ -41,10 +47,12 @@ struct ConvDev {
 // across items and the accumulator is double-buffered in TMEM (2 x 128 columns), so the epilogue of item i (TMEM ->
 // bias / ReLU / pool -> bf16 stores) overlaps the TMA + MMA main loop of item i+1.
 constexpr int CV_THREADS = 384;   // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 epilogue (two per TMEM lane quarter)
+template <int CV_BN>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvDev a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
+  constexpr int CV_STAGES = CvCfg<CV_BN>::STAGES, CV_B_BYTES = CvCfg<CV_BN>::B_BYTES;
   unsigned char* sA = smem;
   unsigned char* sB = smem + CV_STAGES * CV_A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + CV_STAGES * CV_B_BYTES);
@@ -120,7 +128,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> (bias, ReLU, pool) -> bf16 NHWC =====
-    const int q = (warp - 4) & 3, chalf = (warp - 4) >> 2;     // TMEM lane quarter, half of the 128 accumulator columns
+    const int q = (warp - 4) & 3, chalf = (warp - 4) >> 2;     // TMEM lane quarter, half of the BN accumulator columns
     const int m = 32 * q + lane;
     int r = m;
     const int xx = r % a.TW; r /= a.TW;
@@ -135,10 +143,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
     fence_after_sync();
 #pragma unroll 1
-    for (int c = 64 * chalf; c < 64 * chalf + 64; c += 32) {
+    for (int c = (CV_BN / 2) * chalf; c < (CV_BN / 2) * (chalf + 1); c += 32) {
       float v[32];
       tmem_ld32(tmem_d + acc * CV_BN + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
-      if (c + 32 == 64 * chalf + 64) {                  // last read of this accumulator: hand it back to the MMA warp
+      if (c + 32 == (CV_BN / 2) * (chalf + 1)) {        // last read of this accumulator: hand it back to the MMA warp
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -410,20 +418,24 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   const uint32_t bA[4] = {CV_BK, (uint32_t)d.TW, (uint32_t)d.TH, (uint32_t)d.NIMG};
   const uint64_t dB[2] = {(uint64_t)9 * c.Cin, (uint64_t)c.Cout};
   const uint64_t sB[1] = {(uint64_t)9 * c.Cin * 2};
-  const uint32_t bB[2] = {CV_BK, CV_BN};
+  const bool wide = c.Cout % 256 == 0;
+  const int BN = wide ? 256 : 128;
+  const uint32_t bB[2] = {CV_BK, (uint32_t)BN};
   int rc;
   if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, c.in, dA, sA, bA))) return rc;
   if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.wmat, dB, sB, bB))) return rc;
   static bool attr = false;
   if (!attr) {
-    AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM));
+    AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<128>::SMEM));
+    AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<256>::SMEM));
     attr = true;
   }
   d.pix_tiles = (int)(img_groups * d.tiles_y * d.tiles_x);
-  d.n_tiles = (c.Cout + CV_BN - 1) / CV_BN;
+  d.n_tiles = (c.Cout + BN - 1) / BN;
   const long long items = (long long)d.pix_tiles * d.n_tiles;
   const unsigned grid = (unsigned)(items < sm_count() ? items : sm_count());
-  conv_igemm_kernel<<<grid, CV_THREADS, CV_SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
+  if (wide) conv_igemm_kernel<256><<<grid, CV_THREADS, CvCfg<256>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
+  else conv_igemm_kernel<128><<<grid, CV_THREADS, CvCfg<128>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
   AUR_LAUNCH_OK("conv_igemm_kernel");
   return 0;
 }
