@@ -195,6 +195,9 @@ def lib() -> ctypes.CDLL:
     L.aur_relu_mask_bf16.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     L.aur_equiv_head_loss.restype = c_int
     L.aur_equiv_head_loss.argtypes = [ctypes.POINTER(EquivHeadArgs), c_void_p]
+    L.aur_equiv_head_eval.restype = c_int
+    L.aur_equiv_head_eval.argtypes = [c_int32] + [c_void_p] * 7 + [c_uint64, c_uint64, ctypes.POINTER(ctypes.c_float)] + \
+        [c_void_p] * 8
     L.aur_sumsq_f32.restype = c_int
     L.aur_sumsq_f32.argtypes = [c_int64, c_void_p, c_void_p, c_void_p]
     L.aur_adam_flat.restype = c_int

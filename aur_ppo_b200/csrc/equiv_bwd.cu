@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "tc.cuh"
+#include "policy.cuh"
 
 namespace aur {
 namespace tc {
@@ -526,6 +527,75 @@ __global__ void __launch_bounds__(256) head_loss_kernel(HeadLossDev a) {
   }
 }
 
+// ---- heads, inference: robot_actor_critic.evaluate / value (src/models/robot_actor_critic.py:57-60,104-131) -------------
+// One warp per sample (the critic head needs 512 channels), lane 0 decodes the actor head: Normal(mean, exp(log_std)),
+// action = given or mean + std * N(0,1) (Philox keyed like squash.cu), summed log-prob / entropy, decodeActions scaling
+// (robot_actor_critic.py:63-82) with the reference's operation order (no FMA contraction: bit-exact with torch).
+struct HeadEvalDev {
+  int B;
+  const float *a_out, *a_bias, *c_pre, *c_bias1, *c_w2, *c_b2, *action_in;
+  unsigned long long seed, stream_id;
+  float lo[5], hi[5];      // action ranges in the order p, dx, dy, dz, dtheta
+  float *unscaled_out, *scaled_out, *logp_out, *ent_out, *value_out, *mean_out, *logstd_out;
+};
+__global__ void __launch_bounds__(256) head_eval_kernel(HeadEvalDev a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int b = warp; b < a.B; b += nwarps) {
+    if (a.c_pre) {
+      float vpart = 0.0f;
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int fld = lane + 32 * f;
+        float best = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) best = fmaxf(best, fmaxf(a.c_pre[(size_t)b * 512 + fld * 4 + r] + a.c_bias1[fld * 4 + r], 0.0f));
+        vpart = fmaf(best, a.c_w2[fld], vpart);
+      }
+      const float value = warp_sum(vpart) + a.c_b2[0];
+      if (lane == 0) a.value_out[b] = value;
+    }
+    if (a.a_out && lane == 0) {
+      float o10[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) o10[k] = a.a_out[(size_t)b * 16 + k] + a.a_bias[k];
+      const int mean_src[5] = {2, 0, 1, 3, 4};
+      const float LOG_SQRT_2PI = 0.91893853320467267f;
+      float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (!a.action_in) {
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          const Philox r = philox4x32_10((uint32_t)b, 0u, (uint32_t)a.stream_id, (uint32_t)(a.stream_id >> 32) ^ ((uint32_t)blk << 24),
+                                         (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+          float zz[POL_OUT_MAX];
+          normal4(r, zz);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) z[blk * 4 + j] = zz[j];
+        }
+      }
+      float logp = 0.0f, ent = 0.0f;
+#pragma unroll
+      for (int d = 0; d < 5; ++d) {
+        const float mu = o10[mean_src[d]];
+        const float ls = fminf(fmaxf(o10[5 + d], -20.0f), 2.0f);
+        const float sd = expf(ls), var = sd * sd;
+        const float x = a.action_in ? a.action_in[(size_t)b * 5 + d] : __fadd_rn(mu, __fmul_rn(sd, z[d]));
+        const float diff = x - mu, lsc = logf(sd);
+        logp += -(diff * diff) / (2.0f * var) - lsc - LOG_SQRT_2PI;
+        ent += 0.5f + LOG_SQRT_2PI + lsc;
+        a.unscaled_out[(size_t)b * 5 + d] = x;
+        // 0.5 * (u + 1) * (hi - lo) + lo, evaluated left to right as torch does
+        const float t = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(x, 1.0f)), __fsub_rn(a.hi[d], a.lo[d]));
+        a.scaled_out[(size_t)b * 5 + d] = __fadd_rn(t, a.lo[d]);
+        if (a.mean_out) a.mean_out[(size_t)b * 5 + d] = mu;
+        if (a.logstd_out) a.logstd_out[(size_t)b * 5 + d] = ls;
+      }
+      a.logp_out[b] = logp;
+      a.ent_out[b] = ent;
+    }
+  }
+}
+
 // ---- Adam on large flat buffers + global-norm pieces ---------------------------------------------------
 __global__ void __launch_bounds__(256) sumsq_kernel(long long n, const float* __restrict__ g, double* __restrict__ out) {
   __shared__ double sh[8];
@@ -695,6 +765,28 @@ extern "C" int aur_equiv_head_loss(const aur_equiv_head_args* h, void* stream) {
   const unsigned grid = grid_for((long long)h->B * 32, 256, 148 * 4);
   head_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d);
   AUR_LAUNCH_OK("head_loss_kernel");
+  return 0;
+}
+
+extern "C" int aur_equiv_head_eval(int32_t B, const float* a_out, const float* a_bias, const float* c_pre, const float* c_bias1,
+                                   const float* c_w2, const float* c_b2, const float* action_in, uint64_t seed, uint64_t stream_id,
+                                   const float* ranges_lo_hi, float* unscaled_out, float* scaled_out, float* logp_out,
+                                   float* entropy_out, float* value_out, float* mean_out, float* logstd_out, void* stream) {
+  if (B <= 0 || (!a_out && !c_pre)) { set_error("aur_equiv_head_eval: bad arguments"); return AUR_ERR_ARG; }
+  if (a_out && (!a_bias || !ranges_lo_hi || !unscaled_out || !scaled_out || !logp_out || !entropy_out)) {
+    set_error("aur_equiv_head_eval: actor head needs a_bias, ranges and the four outputs"); return AUR_ERR_ARG;
+  }
+  if (c_pre && (!c_bias1 || !c_w2 || !c_b2 || !value_out)) {
+    set_error("aur_equiv_head_eval: critic head needs c_bias1, c_w2, c_b2, value_out"); return AUR_ERR_ARG;
+  }
+  HeadEvalDev d;
+  d.B = B; d.a_out = a_out; d.a_bias = a_bias; d.c_pre = c_pre; d.c_bias1 = c_bias1; d.c_w2 = c_w2; d.c_b2 = c_b2;
+  d.action_in = action_in; d.seed = seed; d.stream_id = stream_id;
+  for (int k = 0; k < 5; ++k) { d.lo[k] = a_out ? ranges_lo_hi[2 * k] : 0.f; d.hi[k] = a_out ? ranges_lo_hi[2 * k + 1] : 0.f; }
+  d.unscaled_out = unscaled_out; d.scaled_out = scaled_out; d.logp_out = logp_out; d.ent_out = entropy_out; d.value_out = value_out;
+  d.mean_out = mean_out; d.logstd_out = logstd_out;
+  head_eval_kernel<<<grid_for((long long)B * 32, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(d);
+  AUR_LAUNCH_OK("head_eval_kernel");
   return 0;
 }
 

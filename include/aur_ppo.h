@@ -404,6 +404,17 @@ typedef struct {
 } aur_equiv_head_args;
 int aur_equiv_head_loss(const aur_equiv_head_args* args, void* stream);
 
+/* Heads at inference: robot_actor_critic.evaluate / value (src/models/robot_actor_critic.py:57-60,104-131) on the
+ * head GEMM outputs.  Actor part (a_out non-NULL): Normal(mean, exp(clamp(log_std))) log-prob and entropy summed
+ * over the 5 dims, action = action_in or mean + std * N(0,1) from Philox(seed; row, stream_id), and decodeActions
+ * (robot_actor_critic.py:63-82): scaled = 0.5 * (u + 1) * (hi - lo) + lo with ranges_lo_hi = host float[10]
+ * {lo,hi} for p, dx, dy, dz, dtheta.  Critic part (c_pre non-NULL): ReLU + GroupPooling + 1x1 -> value [B].
+ * Either part may be skipped by passing NULL.  mean_out / logstd_out [B,5] nullable. */
+int aur_equiv_head_eval(int32_t B, const float* a_out, const float* a_bias, const float* c_pre, const float* c_bias1,
+                        const float* c_w2, const float* c_b2, const float* action_in, uint64_t seed, uint64_t stream_id,
+                        const float* ranges_lo_hi, float* unscaled_out, float* scaled_out, float* logp_out,
+                        float* entropy_out, float* value_out, float* mean_out, float* logstd_out, void* stream);
+
 int aur_sumsq_f32(int64_t n, const float* g, double* out_accum, void* stream);
 /* torch.optim.Adam math on a flat buffer; clip_sumsq (nullable) = device sum of squares of the clipped group */
 int aur_adam_flat(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, double lr, double beta1,

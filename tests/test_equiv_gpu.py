@@ -227,3 +227,49 @@ def test_full_update_gradients_match_oracle_autograd():
     biga = ga.abs() > 1e-3
     if biga.any():
         torch.testing.assert_close(stepa[biga], -3e-4 * ga[biga] / (ga[biga].abs() + 1e-5), rtol=2e-2, atol=1e-6)
+
+
+def test_robot_actor_critic_facade_matches_oracle_evaluate():
+    """robot_actor_critic.evaluate / value / decodeActions (src/models/robot_actor_critic.py:57-131) through the nn.Module
+    facade: log-prob, entropy, value vs the restated model at the bf16 storage points (same bars as the update test);
+    action scaling and the sampled-action replay bit-exact."""
+    from aur_ppo_b200.models import robot_actor_critic
+    B = 6                                                     # not a multiple of 8: the facade pads and slices
+    m = robot_actor_critic("cuda", True, seed=5)
+    with torch.no_grad():
+        for k in ("head_psi_triv", "head_psi_irrep"):
+            getattr(m.actor, k).mul_(0.1)
+        m.critic.head2_w.mul_(0.1)
+    cpu = {k: v.detach().cpu().clone() for k, v in m.tensors().items()}
+    g = torch.Generator().manual_seed(3)
+    obs = torch.rand(B, 1, 128, 128, generator=g) * 0.32
+    state = (torch.rand(B, generator=g) > 0.5).float()
+    action = torch.randn(B, 5, generator=g)
+    with torch.no_grad():
+        lp_ref, ent_ref, v_ref = Q.evaluate(cpu, state, obs, action, quant=True)
+    scaled, unscaled, lp, ent, val = m.evaluate(state, obs, action.cuda())
+    assert val.shape == (B, 1) and lp.shape == (B,) and scaled.shape == (B, 5)
+    torch.testing.assert_close(lp.cpu(), lp_ref, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(ent.cpu(), ent_ref, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(val.cpu().reshape(-1), v_ref, rtol=1e-2, atol=2e-3)
+    torch.testing.assert_close(m.value(state, obs).cpu(), val.cpu(), rtol=0, atol=0)
+    assert torch.equal(unscaled.cpu(), action)
+    # decodeActions: kernel scaling == the reference's torch expression, bit for bit
+    un_t, sc_t = m.decodeActions(*[action.cuda()[:, i] for i in range(5)])
+    assert torch.equal(sc_t, scaled) and torch.equal(un_t, unscaled)
+    # sampling: a second call draws new noise; replaying the drawn action reproduces log-prob and scaling exactly
+    s1, u1, lp1, ent1, _ = m.evaluate(state, obs)
+    s2, u2, lp2, _, _ = m.evaluate(state, obs)
+    assert not torch.equal(u1, u2)
+    s3, u3, lp3, ent3, _ = m.evaluate(state, obs, u1)
+    assert torch.equal(u3, u1) and torch.equal(s3, s1) and torch.equal(lp3, lp1) and torch.equal(ent3, ent1)
+    # getActionFromPlan (robot_actor_critic.py:85-102): in-range scaled plan -> unscaled -> the same scaled plan
+    plan = torch.stack([torch.rand(B), *(0.04 * torch.rand(3, B) - 0.02), 0.7 * torch.rand(B) - 0.35], dim=1)
+    un_p, sc_p = m.getActionFromPlan(plan)
+    assert float(un_p.abs().max()) <= 1.0 + 1e-6
+    torch.testing.assert_close(sc_p, plan, rtol=1e-5, atol=1e-7)
+    # the update engine trains the module's own storage
+    e = m.engine(8)
+    assert e.p["actor.enc3.psi"].data_ptr() == m.actor.enc3_psi.data_ptr()
+    d = m.checkpoint_dict()
+    assert set(d) == {"actor_state", "critic_state", "optimizer_state"} and "enc0_psi" in d["actor_state"]

@@ -129,3 +129,13 @@ def test_ppo_class_fails_loudly_without_cuda():
     p = run_ppo.params_from_args(run_ppo.build_parser().parse_args([]))
     with pytest.raises(_lib.AurError, match="no CPU fallback"):
         ppo(p)
+
+
+def test_robot_actor_critic_refuses_unbuilt_paths():
+    """No CPU path and no plain-CNN fallback behind the robot_actor_critic facade."""
+    from aur_ppo_b200 import _lib
+    from aur_ppo_b200.models import robot_actor_critic
+    with pytest.raises(_lib.AurError):
+        robot_actor_critic("cpu", True)
+    with pytest.raises(_lib.AurError):
+        robot_actor_critic("cuda", False)
