@@ -436,8 +436,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) ppo_grad_kernel(UpdDev a) {
 
 // grads_out[p] = sum over CTAs of the partials, in CTA order, fp64 accumulation.
 __global__ void grad_reduce_kernel(const float* __restrict__ partials, int ncta, int obs_dim, int act_dim, int continuous,
-                                   float* __restrict__ grads_out, DpDev dp, unsigned int* __restrict__ ticket) {
-  const int64_t nA = net_param_count(obs_dim, UPD_H, 2, act_dim), nC = net_param_count(obs_dim, UPD_H, 2, 1);
+                                   int hidden, int nl, int pstride, float* __restrict__ grads_out, DpDev dp,
+                                   unsigned int* __restrict__ ticket) {
+  const int64_t nA = net_param_count(obs_dim, hidden, nl, act_dim), nC = net_param_count(obs_dim, hidden, nl, 1);
   const int64_t P = nA + nC + (continuous ? act_dim : 0);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < P + AUR_NUM_STATS) {
@@ -450,13 +451,13 @@ __global__ void grad_reduce_kernel(const float* __restrict__ partials, int ncta,
     else {
       const int sidx = (int)(i - P);
       net = (sidx == AUR_STAT_VALUE_LOSS) ? 1 : 0;
-      off = UPD_STAT_OFF + sidx;
+      off = (pstride - AUR_NUM_STATS) + sidx;
       zero = sidx > AUR_STAT_CLIPFRAC;
     }
     if (!zero) {
-      const float* p = partials + (size_t)net * ncta * UPD_PSTRIDE + off;
+      const float* p = partials + (size_t)net * ncta * pstride + off;
       double s = 0.0;
-      for (int c = 0; c < ncta; ++c) s += (double)p[(size_t)c * UPD_PSTRIDE];
+      for (int c = 0; c < ncta; ++c) s += (double)p[(size_t)c * pstride];
       v = (float)s;
     }
     grads_out[i] = v;
@@ -594,6 +595,7 @@ static int update_impl() {
     if (!e) g_update_impl = AUR_UPDATE_DEFAULT_IMPL;
     else if (e[0] == 's' || e[0] == '0') g_update_impl = 0;
     else if (e[0] == '2' || (e[0] == 't' && e[1] == 'c' && e[2] == '4')) g_update_impl = 2;
+    else if (e[0] == '3' || e[0] == 'g') g_update_impl = 3;
     else g_update_impl = 1;
   }
   return g_update_impl;
@@ -606,23 +608,29 @@ static int upd_grid_x() {
 static size_t ws_partials_floats() { return (size_t)2 * sm_count() * UPD_PSTRIDE; }
 static size_t ws_bytes() { return ws_partials_floats() * sizeof(float) + (2 * MOM_CTAS) * sizeof(double) + 64; }
 
+// update_generic.cu: the kernel for every shape other than 64 x 2 / widths <= 4 (and, with impl 3, a cross-check there)
+int check_generic_policy(const aur_policy_desc& p, const char* who);
+size_t gen_workspace_floats(const aur_policy_desc& p);
+int gen_pstride(const aur_policy_desc& p);
+int launch_ppo_grad_generic(const UpdDev& d, const aur_policy_desc& p, float* ws, int* gx_out, float** part_out, cudaStream_t s);
+
+static bool is_headline_shape(const aur_policy_desc& p) {
+  return p.hidden_dim == 64 && p.num_layers == 2 && p.obs_dim >= 1 && p.obs_dim <= POL_IN_PAD && p.act_dim >= 1 &&
+         p.act_dim <= POL_OUT_MAX;
+}
 static int check_update_policy(const aur_policy_desc& p, const char* who) {
-  if (p.hidden_dim != 64 || p.num_layers != 2) {
-    set_error("%s: compiled for hidden_dim 64, num_layers 2 (got %d, %d); no fallback", who, p.hidden_dim, p.num_layers);
-    return AUR_ERR_UNSUPPORTED;
-  }
-  if (p.obs_dim < 1 || p.obs_dim > POL_IN_PAD || p.act_dim < 1 || p.act_dim > POL_OUT_MAX) {
-    set_error("%s: obs_dim %d / act_dim %d outside 1..4", who, p.obs_dim, p.act_dim);
-    return AUR_ERR_UNSUPPORTED;
-  }
-  return 0;
+  if (is_headline_shape(p)) return 0;
+  return check_generic_policy(p, who);
 }
 
 }  // namespace aur
 
 extern "C" int64_t aur_ppo_update_workspace_bytes(const aur_policy_desc* desc) {
   if (!desc) return AUR_ERR_ARG;
-  return (int64_t)aur::ws_bytes();
+  int rc = aur::check_update_policy(*desc, "aur_ppo_update_workspace_bytes");
+  if (rc) return rc;
+  // [specialised kernels' partials | moments partials | tickets] then the generic kernel's staged parameters + slabs
+  return (int64_t)(aur::ws_bytes() + aur::gen_workspace_floats(*desc) * sizeof(float));
 }
 
 namespace aur {
@@ -664,7 +672,7 @@ extern "C" int aur_ppo_adv_moments_dp(int64_t m, const int32_t* idx, int64_t idx
 }
 
 extern "C" int aur_ppo_update_set_impl(int impl) {
-  if (impl < 0 || impl > 2) { aur::set_error("aur_ppo_update_set_impl: impl must be 0 (simt), 1 (tensor core) or 2 (tensor core, 4 threads per sample)"); return AUR_ERR_ARG; }
+  if (impl < 0 || impl > 3) { aur::set_error("aur_ppo_update_set_impl: impl must be 0 (simt), 1 (tensor core), 2 (tensor core, 4 threads per sample) or 3 (shape-generic)"); return AUR_ERR_ARG; }
   aur::g_update_impl = impl;
   return 0;
 }
@@ -700,9 +708,15 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
     attr_set = true;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const int impl = update_impl();
-  int gx;
-  if (impl >= 1) {
+  const int impl = is_headline_shape(u.policy) ? update_impl() : 3;
+  int gx, pstride = UPD_PSTRIDE;
+  const float* partials = u.workspace;
+  if (impl == 3) {
+    float* part = nullptr;
+    int rc2 = launch_ppo_grad_generic(d, u.policy, u.workspace + ws_bytes() / sizeof(float), &gx, &part, s);
+    if (rc2) return rc2;
+    partials = part; pstride = gen_pstride(u.policy);
+  } else if (impl >= 1) {
     gx = sm_count();
     int rc2 = launch_ppo_grad_tc(d, gx, impl == 2 ? 4 : 2, s);
     if (rc2) return rc2;
@@ -714,8 +728,9 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
   const int64_t P = policy_param_count(u.policy);
   const int total = (int)(P + AUR_NUM_STATS);
   unsigned int* ticket2 = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(u.workspace + ws_partials_floats()) + 2 * MOM_CTAS) + 1;
-  grad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(u.workspace, gx, u.policy.obs_dim, u.policy.act_dim,
-                                                        u.policy.continuous, u.grads_out, d.dp, ticket2);
+  grad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(partials, gx, u.policy.obs_dim, u.policy.act_dim, u.policy.continuous,
+                                                        u.policy.hidden_dim, u.policy.num_layers, pstride, u.grads_out, d.dp,
+                                                        ticket2);
   AUR_LAUNCH_OK("grad_reduce_kernel");
   return 0;
 }

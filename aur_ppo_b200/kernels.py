@@ -201,6 +201,8 @@ class Updater:
         self.moments = torch.zeros(3, dtype=torch.float64, device=dev)
         self.stats = torch.zeros(NUM_STATS, device=dev)
         ws = int(_lib.lib().aur_ppo_update_workspace_bytes(ctypes.byref(desc)))
+        if ws < 0:
+            _lib.check(ws, "aur_ppo_update_workspace_bytes")
         self.workspace = torch.zeros((ws + 3) // 4, dtype=torch.float32, device=dev)
         self.eps, self.betas, self.step_count, self.allreduce = float(eps), betas, 0, allreduce
         # exchange (parallel.PeerExchange): the kernels all-reduce over peer memory themselves; excludes `allreduce`
