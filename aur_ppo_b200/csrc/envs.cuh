@@ -184,6 +184,7 @@ struct RolloutDev {
   long long N;
   int T, wrappers;
   int obs_dim, act_dim, nl, continuous;
+  int hid, dyn_smem;          // runtime-width path (hidden_dim != 64): hidden units, 1 = both nets are copied to shared memory
   const float* params;
   aur_env_state env;
   float *obs_buf, *act_buf, *logp_buf, *val_buf, *rew_buf, *done_buf, *next_obs, *next_done, *next_value;
@@ -203,6 +204,44 @@ __device__ __forceinline__ void load_policy_smem(float* smem, const RolloutDev& 
   if (a.continuous && threadIdx.x < POL_OUT_MAX)
     smem[nA + nC + threadIdx.x] = threadIdx.x < a.act_dim ? a.params[gA + gC + threadIdx.x] : 0.0f;
   sActor = smem; sCritic = smem + nA; sLogstd = smem + nA + nC;
+}
+
+// Runtime-width policies (rollout_kernel<ENV, 0, 1, true>, policy_evaluate_dyn_kernel): the flat nets are copied to
+// 16-byte aligned shared memory when they fit (a.dyn_smem), else read in place from global memory; `scratch` is the
+// calling thread's activation column ([2][hid][blockDim] floats behind the weights).
+__device__ __forceinline__ void load_policy_dyn(float* smem, const RolloutDev& a, const float*& act, const float*& cri,
+                                                const float*& ls, float*& scratch, bool& vec_critic) {
+  const int64_t gA = net_param_count(a.obs_dim, a.hid, a.nl, a.act_dim), gC = net_param_count(a.obs_dim, a.hid, a.nl, 1);
+  if (a.dyn_smem) {
+    const int64_t oC = (gA + 3) & ~3LL, oL = oC + ((gC + 3) & ~3LL);
+    for (int64_t i = threadIdx.x; i < gA; i += blockDim.x) smem[i] = a.params[i];
+    for (int64_t i = threadIdx.x; i < gC; i += blockDim.x) smem[oC + i] = a.params[gA + i];
+    if (threadIdx.x < 8) smem[oL + threadIdx.x] = (a.continuous && (int)threadIdx.x < a.act_dim) ? a.params[gA + gC + threadIdx.x] : 0.0f;
+    act = smem; cri = smem + oC; ls = smem + oL;
+    scratch = smem + oL + 8 + threadIdx.x;
+    vec_critic = true;
+  } else {
+    act = a.params; cri = a.params + gA; ls = a.params + gA + gC;
+    scratch = smem + threadIdx.x;
+    vec_critic = (gA & 3) == 0;
+  }
+}
+__host__ __device__ inline int64_t dyn_policy_smem_floats(int obs, int H, int NL, int act) {
+  return ((net_param_count(obs, H, NL, act) + 3) & ~3LL) + ((net_param_count(obs, H, NL, 1) + 3) & ~3LL) + 8;
+}
+
+// forward of one net for E envs of a thread: compiled 64-wide path (registers) or the runtime-width path (HID == 0)
+template <int HID, int E>
+__device__ __forceinline__ void policy_net_forward(const RolloutDev& a, const float* __restrict__ net, bool vec, int out_dim,
+                                                   const float (&x)[E][POL_IN_PAD], float (&o)[E][POL_OUT_MAX],
+                                                   float* __restrict__ scratch) {
+  if constexpr (HID == 0) {
+    static_assert(E == 1, "runtime-width policies run one env per thread");
+    if (vec) mlp_forward_dyn<true, POL_IN_PAD, POL_OUT_MAX>(net, a.obs_dim, a.hid, a.nl, out_dim, x[0], o[0], scratch, blockDim.x);
+    else mlp_forward_dyn<false, POL_IN_PAD, POL_OUT_MAX>(net, a.obs_dim, a.hid, a.nl, out_dim, x[0], o[0], scratch, blockDim.x);
+  } else {
+    mlp_forward<HID, E>(net, a.nl, out_dim, x, o, scratch, blockDim.x);
+  }
 }
 
 __device__ __forceinline__ void log_episode(const aur_episode_log& log, int t, long long local_env, int step, int env,

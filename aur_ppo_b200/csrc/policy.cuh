@@ -191,8 +191,72 @@ __device__ __forceinline__ void mlp_forward(const float* __restrict__ sNet, int 
     for (int k = 0; k < POL_OUT_MAX; ++k) out[e][k] = o2[e][k].x + o2[e][k].y + bb[k];
 }
 
+// ---- runtime-width forward (hidden_dim != 64, or observation / action widths above 4) ----------------------------
+// One sample per thread.  Activations ping-pong through two per-thread columns of shared memory (col[i * stride],
+// col[(H + i) * stride]); the weights are read through `net` in torch's flat [out][in] order, from shared or global
+// memory, every lane of a warp at the same address (one broadcast transaction).  VEC: rows of the hidden / output
+// matrices are 16-byte aligned (net base aligned and H a multiple of 4), so they load as float4.
+template <bool VEC>
+__device__ __forceinline__ void dyn_row4(const float* __restrict__ w, float (&v)[4]) {
+  if constexpr (VEC) {
+    const float4 t = *reinterpret_cast<const float4*>(w);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    v[0] = w[0]; v[1] = w[1]; v[2] = w[2]; v[3] = w[3];
+  }
+}
+template <bool VEC, int IN_MAX, int OUT_MAX>
+__device__ inline void mlp_forward_dyn(const float* __restrict__ net, int obs_dim, int H, int NL, int out_dim,
+                                       const float (&x)[IN_MAX], float (&out)[OUT_MAX], float* __restrict__ col, int stride) {
+  const float* p = net;
+  float* cur = col;
+  float* nxt = col + (size_t)H * stride;
+  for (int j = 0; j < H; ++j) {                                    // first layer: obs_dim inputs, scalar loads
+    float z = p[(size_t)H * obs_dim + j];
+#pragma unroll
+    for (int c = 0; c < IN_MAX; ++c) if (c < obs_dim) z = fmaf(p[(size_t)j * obs_dim + c], x[c], z);
+    cur[(size_t)j * stride] = tanh_fast(z);
+  }
+  p += (size_t)H * obs_dim + H;
+  for (int l = 1; l < NL; ++l) {
+    for (int j = 0; j < H; j += 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < H; i += 4) {
+        float hv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hv[q] = cur[(size_t)(i + q) * stride];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float w[4];
+          dyn_row4<VEC>(p + (size_t)(j + jj) * H + i, w);
+          acc[jj] = fmaf(w[3], hv[3], fmaf(w[2], hv[2], fmaf(w[1], hv[1], fmaf(w[0], hv[0], acc[jj]))));
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) nxt[(size_t)(j + jj) * stride] = tanh_fast(acc[jj] + p[(size_t)H * H + j + jj]);
+    }
+    float* t = cur; cur = nxt; nxt = t;
+    p += (size_t)H * H + H;
+  }
+#pragma unroll
+  for (int k = 0; k < OUT_MAX; ++k) {
+    float acc = 0.0f;
+    if (k < out_dim) {
+      for (int i = 0; i < H; i += 4) {
+        float w[4];
+        dyn_row4<VEC>(p + (size_t)k * H + i, w);
+        acc = fmaf(w[3], cur[(size_t)(i + 3) * stride], fmaf(w[2], cur[(size_t)(i + 2) * stride],
+              fmaf(w[1], cur[(size_t)(i + 1) * stride], fmaf(w[0], cur[(size_t)i * stride], acc))));
+      }
+      acc += p[(size_t)out_dim * H + k];
+    }
+    out[k] = acc;
+  }
+}
+
 // ---- distributions (models/actor_critic.py:34-51) ---------------------------------------
 // Categorical(logits): normalised log-probs, then sample by inverse CDF or take `action_in`.
+template <int POL_OUT_MAX>
 __device__ __forceinline__ void categorical(const float (&logits)[POL_OUT_MAX], int A, bool sample, float u,
                                             int& action, float& logp, float& entropy) {
   float m = logits[0];
@@ -225,11 +289,14 @@ __device__ __forceinline__ void categorical(const float (&logits)[POL_OUT_MAX], 
   for (int k = 1; k < POL_OUT_MAX; ++k) if (k == action) logp = lp[k];
 }
 
-struct NormalConsts {   // per action dimension, from actor_logstd
-  float std[POL_OUT_MAX], inv2var[POL_OUT_MAX], log_scale[POL_OUT_MAX];
+template <int M>
+struct NormalConstsT {   // per action dimension, from actor_logstd
+  float std[M], inv2var[M], log_scale[M];
 };
-__device__ __forceinline__ NormalConsts normal_consts(const float* logstd, int A) {
-  NormalConsts c;
+using NormalConsts = NormalConstsT<POL_OUT_MAX>;
+template <int POL_OUT_MAX = aur::POL_OUT_MAX>
+__device__ __forceinline__ NormalConstsT<POL_OUT_MAX> normal_consts(const float* logstd, int A) {
+  NormalConstsT<POL_OUT_MAX> c;
 #pragma unroll
   for (int k = 0; k < POL_OUT_MAX; ++k) {
     const float ls = k < A ? logstd[k] : 0.0f;
@@ -241,8 +308,9 @@ __device__ __forceinline__ NormalConsts normal_consts(const float* logstd, int A
   return c;
 }
 // Normal(mean, std): log_prob summed over dims, entropy summed over dims.
+template <int POL_OUT_MAX>
 __device__ __forceinline__ void normal_logp(const float (&mean)[POL_OUT_MAX], const float (&act)[POL_OUT_MAX], int A,
-                                            const NormalConsts& c, float& logp, float& entropy) {
+                                            const NormalConstsT<POL_OUT_MAX>& c, float& logp, float& entropy) {
   const float LOG_SQRT_2PI = 0.91893853320467267f;
   logp = 0.0f; entropy = 0.0f;
 #pragma unroll

@@ -22,9 +22,15 @@ template <class ENV, int HID, int E, bool CRITIC>
 __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
   extern __shared__ __align__(16) float smem[];
   const float *sActor, *sCritic, *sLogstd;
-  load_policy_smem<HID>(smem, a, sActor, sCritic, sLogstd);
-  const int policy_floats = net_smem_floats(HID, a.nl, a.act_dim) + net_smem_floats(HID, a.nl, 1) + 4;
-  float* scratch = smem + policy_floats + threadIdx.x;   // [HID][blockDim] column (NL >= 3 only)
+  float* scratch;
+  bool vec_critic = true;
+  if constexpr (HID == 0) {
+    load_policy_dyn(smem, a, sActor, sCritic, sLogstd, scratch, vec_critic);
+  } else {
+    load_policy_smem<HID>(smem, a, sActor, sCritic, sLogstd);
+    const int policy_floats = net_smem_floats(HID, a.nl, a.act_dim) + net_smem_floats(HID, a.nl, 1) + 4;
+    scratch = smem + policy_floats + threadIdx.x;   // [HID][blockDim] column (NL >= 3 only)
+  }
   __syncthreads();
 
   constexpr bool PEND = ENV::OBS == 3;
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
 #pragma unroll 1
     for (int net = 0; net < (CRITIC ? 2 : 1); ++net) {
       float o[E][POL_OUT_MAX];
-      mlp_forward<HID, E>(net == 0 ? sActor : sCritic, a.nl, net == 0 ? a.act_dim : 1, obs, o, scratch, blockDim.x);
+      policy_net_forward<HID, E>(a, net == 0 ? sActor : sCritic, net == 0 || vec_critic, net == 0 ? a.act_dim : 1, obs, o, scratch);
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         if (net == 0) {
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
   // ---- write back: next_obs / next_done / env state, and critic(next_obs) for GAE (ppo.py:161)
   if (CRITIC && a.next_value) {
     float o[E][POL_OUT_MAX];
-    mlp_forward<HID, E>(sCritic, a.nl, 1, obs, o, scratch, blockDim.x);
+    policy_net_forward<HID, E>(a, sCritic, vec_critic, 1, obs, o, scratch);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const long long n = base + e * stride;
@@ -278,17 +284,107 @@ __global__ void __launch_bounds__(256, 1) policy_evaluate_kernel(RolloutDev a, l
   }
 }
 
+// the same for runtime hidden widths and observation / action widths up to 8 (e.g. the reference's shipped
+// actor_critic_2.pt: state 8, 4 actions): mlp_forward_dyn, one sample per thread
+constexpr int DYN_IO = 8;
+__global__ void __launch_bounds__(128, 1) policy_evaluate_dyn_kernel(RolloutDev a, long long B, const float* obs_in,
+                                                                     uint64_t row0, uint64_t step, float* act_out,
+                                                                     float* logp_out, float* ent_out, float* val_out) {
+  extern __shared__ __align__(16) float smem[];
+  const float *sActor, *sCritic, *sLogstd;
+  float* scratch;
+  bool vec_critic = true;
+  load_policy_dyn(smem, a, sActor, sCritic, sLogstd, scratch, vec_critic);
+  __syncthreads();
+  NormalConstsT<DYN_IO> nc;
+  if (a.continuous) nc = normal_consts<DYN_IO>(sLogstd, a.act_dim);
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    float x[DYN_IO], head[DYN_IO], v[DYN_IO];
+#pragma unroll
+    for (int k = 0; k < DYN_IO; ++k) x[k] = k < a.obs_dim ? obs_in[b * a.obs_dim + k] : 0.0f;
+    mlp_forward_dyn<true, DYN_IO, DYN_IO>(sActor, a.obs_dim, a.hid, a.nl, a.act_dim, x, head, scratch, blockDim.x);
+    if (vec_critic) mlp_forward_dyn<true, DYN_IO, DYN_IO>(sCritic, a.obs_dim, a.hid, a.nl, 1, x, v, scratch, blockDim.x);
+    else mlp_forward_dyn<false, DYN_IO, DYN_IO>(sCritic, a.obs_dim, a.hid, a.nl, 1, x, v, scratch, blockDim.x);
+    float logp, entropy;
+    const uint64_t gid = row0 + (uint64_t)b;
+    if (!a.continuous) {
+      int action = 0;
+      const bool sample = a.actions_in == nullptr;
+      float u = 0.0f;
+      if (sample) {
+        const Philox r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32),
+                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        u = u01_24(r.c[0]);
+      } else {
+        action = (int)a.actions_in[b];
+      }
+      categorical(head, a.act_dim, sample, u, action, logp, entropy);
+      if (act_out) act_out[b] = (float)action;
+    } else {
+      float act[DYN_IO];
+#pragma unroll
+      for (int k = 0; k < DYN_IO; ++k) act[k] = 0.0f;
+      if (a.actions_in == nullptr) {
+        // dims 0..3 from the Philox block the 4-wide kernels use, dims 4..7 from a second block (counter word 3 ^ 1 << 24)
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          if (blk * 4 < a.act_dim) {
+            const Philox r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step,
+                                           (uint32_t)(step >> 32) ^ ((uint32_t)blk << 24), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            float z[POL_OUT_MAX];
+            normal4(r, z);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) act[blk * 4 + k] = fmaf(nc.std[blk * 4 + k], z[k], head[blk * 4 + k]);
+          }
+        }
+      } else {
+        for (int k = 0; k < a.act_dim; ++k) act[k] = a.actions_in[b * a.act_dim + k];
+      }
+      normal_logp(head, act, a.act_dim, nc, logp, entropy);
+      if (act_out) for (int k = 0; k < a.act_dim; ++k) act_out[b * a.act_dim + k] = act[k];
+    }
+    if (logp_out) logp_out[b] = logp;
+    if (ent_out) ent_out[b] = entropy;
+    if (val_out) val_out[b] = v[0];
+  }
+}
+
 __global__ void sincos_kernel(long long n, const double* x, double* s, double* c) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) aur_sincos(x[i], &s[i], &c[i]);
 }
 
-static int check_policy(const aur_policy_desc& p, const char* who) {
-  if (p.hidden_dim != 64) { set_error("%s: hidden_dim %d not compiled (64 only); no fallback", who, p.hidden_dim); return AUR_ERR_UNSUPPORTED; }
-  if (p.obs_dim < 1 || p.obs_dim > POL_IN_PAD) { set_error("%s: obs_dim %d outside 1..4", who, p.obs_dim); return AUR_ERR_UNSUPPORTED; }
-  if (p.act_dim < 1 || p.act_dim > POL_OUT_MAX) { set_error("%s: act_dim %d outside 1..4", who, p.act_dim); return AUR_ERR_UNSUPPORTED; }
+static bool is_compiled_width(const aur_policy_desc& p) {
+  return p.hidden_dim == 64 && p.obs_dim >= 1 && p.obs_dim <= POL_IN_PAD && p.act_dim >= 1 && p.act_dim <= POL_OUT_MAX;
+}
+// 64 hidden units and widths <= 4 run the register-resident kernels; everything else the runtime-width path
+static int check_policy(const aur_policy_desc& p, const char* who, int io_max) {
   if (p.num_layers < 1 || p.num_layers > 16) { set_error("%s: num_layers %d outside 1..16", who, p.num_layers); return AUR_ERR_UNSUPPORTED; }
+  if (is_compiled_width(p)) return 0;
+  if (p.hidden_dim < 4 || p.hidden_dim > 256 || (p.hidden_dim & 3)) {
+    set_error("%s: hidden_dim %d outside the compiled range (multiples of 4 in 4..256); no fallback", who, p.hidden_dim);
+    return AUR_ERR_UNSUPPORTED;
+  }
+  if (p.obs_dim < 1 || p.obs_dim > io_max) { set_error("%s: obs_dim %d outside 1..%d", who, p.obs_dim, io_max); return AUR_ERR_UNSUPPORTED; }
+  if (p.act_dim < 1 || p.act_dim > io_max) { set_error("%s: act_dim %d outside 1..%d", who, p.act_dim, io_max); return AUR_ERR_UNSUPPORTED; }
   return 0;
+}
+// runtime-width launch shape: keep the nets in shared memory when they fit beside the activation columns, shrinking the
+// block down to 64 threads first; else read them from global memory.  Returns the smem bytes, sets block / in_smem.
+static size_t dyn_launch_shape(const aur_policy_desc& p, int& block, int& in_smem) {
+  const size_t pf = (size_t)dyn_policy_smem_floats(p.obs_dim, p.hidden_dim, p.num_layers, p.act_dim);
+  const size_t limit = 200 * 1024;
+  for (int b = block; b >= 64; b -= 32) {
+    const size_t need = (pf + (size_t)2 * p.hidden_dim * b) * sizeof(float);
+    if (need <= limit) { block = b; in_smem = 1; return need; }
+  }
+  in_smem = 0;
+  for (int b = block; b >= 32; b -= 32) {
+    const size_t need = (size_t)2 * p.hidden_dim * b * sizeof(float);
+    if (need <= limit) { block = b; return need; }
+  }
+  block = 32;
+  return (size_t)2 * p.hidden_dim * 32 * sizeof(float);
 }
 
 static size_t policy_smem_bytes(const aur_policy_desc& p, int threads, bool need_scratch) {
@@ -349,6 +445,7 @@ static aur::RolloutDev to_dev(const aur_rollout_args& a) {
   aur::RolloutDev d;
   d.N = a.N; d.T = a.T; d.wrappers = a.wrappers;
   d.obs_dim = a.policy.obs_dim; d.act_dim = a.policy.act_dim; d.nl = a.policy.num_layers; d.continuous = a.policy.continuous;
+  d.hid = a.policy.hidden_dim; d.dyn_smem = 0;
   d.params = a.params; d.env = a.env;
   d.obs_buf = a.obs_buf; d.act_buf = a.act_buf; d.logp_buf = a.logp_buf; d.val_buf = a.val_buf; d.rew_buf = a.rew_buf;
   d.done_buf = a.done_buf; d.next_obs = a.next_obs; d.next_done = a.next_done; d.next_value = a.next_value;
@@ -362,7 +459,7 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
   const aur_rollout_args& a = *args;
   if (a.N < 0 || a.T < 0) { set_error("aur_rollout: negative N or T"); return AUR_ERR_ARG; }
   if (a.N == 0 || a.T == 0) return 0;
-  int rc = check_policy(a.policy, "aur_rollout");
+  int rc = check_policy(a.policy, "aur_rollout", POL_IN_PAD);
   if (rc) return rc;
   if (!a.params || !a.obs_buf || !a.act_buf || !a.logp_buf || !a.val_buf || !a.rew_buf || !a.done_buf || !a.next_obs ||
       !a.next_done || !a.env.phys || !a.env.pcg || !a.env.elapsed || !a.env.ep_return || !a.env.ep_length) {
@@ -379,9 +476,28 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
   } else {
     set_error("aur_rollout: unknown env_kind %d", a.env_kind); return AUR_ERR_UNSUPPORTED;
   }
-  const RolloutDev d = to_dev(a);
+  RolloutDev d = to_dev(a);
   cudaStream_t s = (cudaStream_t)stream;
   const int sms = sm_count();
+  if (!is_compiled_width(a.policy)) {
+    // runtime-width policy: one env per thread, both nets in the sequential kernel
+    if (((uintptr_t)a.params & 15) != 0) { set_error("aur_rollout: params must be 16-byte aligned"); return AUR_ERR_ARG; }
+    int block = round_up((int)((a.N + sms - 1) / sms < 256 ? (a.N + sms - 1) / sms : 256), 32);
+    if (block < 64) block = 64;
+    const size_t smem = dyn_launch_shape(a.policy, block, d.dyn_smem);
+    const long long grid = (a.N + block - 1) / block;
+#define AUR_LAUNCH_DYN(ENVT)                                                             \
+  do {                                                                                   \
+    if ((rc = launch_cfg(rollout_kernel<ENVT, 0, 1, true>, smem))) return rc;            \
+    rollout_kernel<ENVT, 0, 1, true><<<(unsigned)grid, block, smem, s>>>(d);             \
+  } while (0)
+    if (pend) AUR_LAUNCH_DYN(Pendulum);
+    else if (a.env_kind == AUR_ENV_MOUNTAINCAR) AUR_LAUNCH_DYN(MountainCar);
+    else AUR_LAUNCH_DYN(CartPole);
+#undef AUR_LAUNCH_DYN
+    AUR_LAUNCH_OK("rollout_kernel (runtime width)");
+    return 0;
+  }
   const bool two = a.env_kind == AUR_ENV_CARTPOLE && a.policy.num_layers <= 2 && a.N >= 2LL * 32 * sms;   // E = 2 needs enough envs to fill the chip
   const long long threads_needed = two ? (a.N + 1) / 2 : a.N;
   int block = round_up((int)((threads_needed + sms - 1) / sms < 256 ? (threads_needed + sms - 1) / sms : 256), 32);
@@ -426,11 +542,24 @@ extern "C" int aur_policy_evaluate(const aur_policy_desc* desc, const float* par
   using namespace aur;
   if (!desc || !params || B < 0 || (B > 0 && !obs)) { set_error("aur_policy_evaluate: bad arguments"); return AUR_ERR_ARG; }
   if (B == 0) return 0;
-  int rc = check_policy(*desc, "aur_policy_evaluate");
+  int rc = check_policy(*desc, "aur_policy_evaluate", DYN_IO);
   if (rc) return rc;
   RolloutDev d{};
   d.obs_dim = desc->obs_dim; d.act_dim = desc->act_dim; d.nl = desc->num_layers; d.continuous = desc->continuous;
+  d.hid = desc->hidden_dim; d.dyn_smem = 0;
   d.params = params; d.actions_in = actions_in; d.seed = seed;
+  if (!is_compiled_width(*desc)) {
+    if (((uintptr_t)params & 15) != 0) { set_error("aur_policy_evaluate: params must be 16-byte aligned"); return AUR_ERR_ARG; }
+    int block = 128;
+    const size_t smem = dyn_launch_shape(*desc, block, d.dyn_smem);
+    long long grid = (B + block - 1) / block;
+    if (grid > 4LL * sm_count()) grid = 4LL * sm_count();
+    if ((rc = launch_cfg(policy_evaluate_dyn_kernel, smem))) return rc;
+    policy_evaluate_dyn_kernel<<<(unsigned)grid, block, smem, (cudaStream_t)stream>>>(d, (long long)B, obs, row0, step, actions_out,
+                                                                                    logp_out, entropy_out, value_out);
+    AUR_LAUNCH_OK("policy_evaluate_dyn_kernel");
+    return 0;
+  }
   const int block = 128;
   long long grid = (B + block - 1) / block;
   if (grid > 4LL * sm_count()) grid = 4LL * sm_count();

@@ -40,8 +40,6 @@ def test_policy_evaluate_matches_reference_golden(golden_dir, tag):
     obs, act = g[f"{tag}_obs"], g[f"{tag}_act"].astype(np.float32)
     cont = pol.continuous
     A = named["actor_logstd"].size if cont else int(named[[k for k in named if k.startswith("actor.net.")][-1]].shape[0])
-    if obs.shape[1] > 4:
-        pytest.skip("obs_dim > 4 is outside the compiled kernels")
     desc = kernels.policy_desc(obs.shape[1], A, 64, nl, cont)
     flat = torch.from_numpy(flat_from_named(named)).cuda()
     assert flat.numel() == kernels.policy_param_count(desc)
@@ -53,9 +51,11 @@ def test_policy_evaluate_matches_reference_golden(golden_dir, tag):
 
 
 def test_unsupported_shapes_fail_loudly():
-    desc = kernels.policy_desc(4, 2, 128, 2, False)
-    with pytest.raises(_lib.AurError, match="hidden_dim"):
-        kernels.policy_evaluate(desc, torch.zeros(100000, device="cuda"), torch.zeros(4, 4, device="cuda"))
+    for desc in (kernels.policy_desc(4, 2, 66, 2, False), kernels.policy_desc(4, 2, 512, 2, False)):
+        with pytest.raises(_lib.AurError, match="hidden_dim"):
+            kernels.policy_evaluate(desc, torch.zeros(1000000, device="cuda"), torch.zeros(4, 4, device="cuda"))
+    with pytest.raises(_lib.AurError, match="obs_dim"):
+        kernels.policy_evaluate(kernels.policy_desc(9, 2, 64, 2, False), torch.zeros(100000, device="cuda"), torch.zeros(4, 9, device="cuda"))
     with pytest.raises(_lib.AurError, match="no device kernel"):
         denv.DeviceVecEnv("Acrobot-v1", 4)
 
@@ -338,3 +338,99 @@ def test_full_size_rollout_properties():
         _, lp, _, v = pol.evaluate(ot, at)
     np.testing.assert_allclose(buf.log_probs.cpu().numpy()[:, cols[:16]].reshape(-1), lp.numpy(), **TOL)
     np.testing.assert_allclose(buf.values.cpu().numpy()[:, cols[:16]].reshape(-1), v.numpy().reshape(-1), **TOL)
+
+
+# ---- runtime-width policies (hidden_dim != 64, widths up to 8): csrc/policy.cuh::mlp_forward_dyn ---------------------
+@pytest.mark.parametrize("obs_dim,act_dim,hidden,layers,cont", [(4, 2, 32, 2, False), (4, 2, 128, 3, False), (8, 4, 64, 2, False),
+                                                                (6, 3, 256, 2, False), (3, 1, 100, 1, True), (8, 8, 64, 2, True),
+                                                                (5, 6, 20, 4, True), (4, 3, 256, 4, False)])
+def test_policy_evaluate_runtime_widths_vs_oracle(obs_dim, act_dim, hidden, layers, cont, rollout_impl):
+    """actor_critic.evaluate / value (models/actor_critic.py:31-51) for the shapes `-d` / `-nl` and the shipped checkpoints
+    (state 8 / 4 actions) produce, against the restated torch model."""
+    if rollout_impl != "tc":
+        pytest.skip("one kernel behind this path")
+    pol, named = random_policy(obs_dim, act_dim, hidden, layers, cont, seed=hidden)
+    desc = kernels.policy_desc(obs_dim, act_dim, hidden, layers, cont)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    g = torch.Generator().manual_seed(1)
+    B = 3000
+    obs = torch.randn(B, obs_dim, generator=g)
+    act = torch.randn(B, act_dim, generator=g) if cont else torch.randint(0, act_dim, (B,), generator=g).float()
+    with torch.no_grad():
+        _, lp, ent, v = pol.evaluate(obs, act)
+    a, glp, gent, gv = kernels.policy_evaluate(desc, flat, obs.cuda(), act.cuda())
+    np.testing.assert_allclose(glp.cpu().numpy(), lp.numpy(), rtol=2e-5, atol=5e-6)
+    np.testing.assert_allclose(gent.cpu().numpy(), ent.numpy(), rtol=2e-5, atol=5e-6)
+    np.testing.assert_allclose(gv.cpu().numpy().reshape(-1), v.numpy().reshape(-1), rtol=2e-5, atol=5e-6)
+    # sampling: replaying the drawn actions reproduces the log-probs bit for bit; discrete frequencies follow the softmax
+    a1, lp1, _, _ = kernels.policy_evaluate(desc, flat, obs.cuda(), None, seed=7, step=3)
+    a2, lp2, _, _ = kernels.policy_evaluate(desc, flat, obs.cuda(), a1, seed=7, step=3)
+    assert torch.equal(lp1, lp2) and torch.equal(a1, a2)
+    if cont:
+        z = a1.cpu().reshape(B, act_dim)
+        assert torch.isfinite(z).all()
+        if act_dim > 4:   # the second Philox block feeds dims 4..7: they must not repeat dims 0..3
+            assert not torch.equal(z[:, 0], z[:, 4])
+    else:
+        assert set(np.unique(a1.cpu().numpy())) <= set(range(act_dim))
+
+
+@pytest.mark.parametrize("hidden,layers,N,T", [(32, 2, 300, 200), (128, 2, 70, 300), (256, 2, 40, 120), (96, 3, 64, 150)])
+def test_cartpole_replay_runtime_width(hidden, layers, N, T, rollout_impl):
+    """`--hidden_dim` other than 64: transitions stay bit-exact (same env code), log-probs / values follow the wider MLP."""
+    if rollout_impl != "tc":
+        pytest.skip("one kernel behind this path")
+    pol, named = random_policy(4, 2, hidden, layers, False, seed=hidden)
+    desc = kernels.policy_desc(4, 2, hidden, layers, False)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    seeds = list(range(N))
+    actions = np.random.default_rng(N).integers(0, 2, (T, N))
+    cv, obs0, obs, rew, done, last_obs, last_done, episodes = _oracle_replay(E.CARTPOLE, N, False, seeds, actions, T)
+    env = denv.DeviceVecEnv("CartPole-v1", N, log_capacity=N * 64)
+    env.reset(seeds)
+    buf = kernels.RolloutBuffers(T, N, 4, (), "cuda")
+    kernels.rollout(env, desc, flat, buf, seed=1, step0=0, actions_in=torch.from_numpy(actions.astype(np.float32)).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.states.cpu().numpy(), obs)
+    assert np.array_equal(buf.terminals.cpu().numpy(), done)
+    assert np.array_equal(buf.rewards.cpu().numpy(), rew)
+    assert np.array_equal(env.phys.cpu().numpy().T, cv.phys())
+    assert env.drain_episodes() == sorted(episodes, key=lambda r: (r[0], r[1]))
+    ot = torch.from_numpy(obs.reshape(-1, 4)); at = torch.from_numpy(actions.reshape(-1))
+    with torch.no_grad():
+        _, lp, _, v = pol.evaluate(ot, at)
+        nv = pol.value(torch.from_numpy(last_obs))
+    np.testing.assert_allclose(buf.log_probs.cpu().numpy().reshape(-1), lp.numpy(), **TOL)
+    np.testing.assert_allclose(buf.values.cpu().numpy().reshape(-1), v.numpy().reshape(-1), **TOL)
+    np.testing.assert_allclose(buf.next_value.cpu().numpy(), nv.numpy(), **TOL)
+    # sampled actions: same Philox stream as the 64-wide kernels -> a sampled rollout replays on the checker
+    env.reset(seeds)
+    buf2 = kernels.RolloutBuffers(T, N, 4, (), "cuda")
+    kernels.rollout(env, desc, flat, buf2, seed=5, step0=0)
+    acts = buf2.actions.cpu().numpy().astype(np.int64)
+    _, _, obs_s, rew_s, done_s, _, _, _ = _oracle_replay(E.CARTPOLE, N, False, seeds, acts, T)
+    assert np.array_equal(buf2.states.cpu().numpy(), obs_s) and np.array_equal(buf2.rewards.cpu().numpy(), rew_s)
+    assert np.array_equal(buf2.terminals.cpu().numpy(), done_s)
+
+
+def test_pendulum_replay_runtime_width(rollout_impl):
+    if rollout_impl != "tc":
+        pytest.skip("one kernel behind this path")
+    N, T, hidden = 50, 260, 128
+    pol, named = random_policy(3, 1, hidden, 2, True, seed=9)
+    desc = kernels.policy_desc(3, 1, hidden, 2, True)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    seeds = list(range(N))
+    env = denv.DeviceVecEnv("Pendulum-v1", N, wrappers=True, log_capacity=N * 8)
+    env.reset(seeds)
+    buf = kernels.RolloutBuffers(T, N, 3, (1,), "cuda")
+    kernels.rollout(env, desc, flat, buf, seed=2, step0=0)
+    torch.cuda.synchronize()
+    acts = buf.actions.cpu().numpy()
+    cv, obs0, obs, rew, done, last_obs, last_done, episodes = _oracle_replay(E.PENDULUM, N, True, seeds, acts, T)
+    assert np.array_equal(buf.states.cpu().numpy(), obs)
+    assert np.array_equal(buf.rewards.cpu().numpy(), rew)
+    with torch.no_grad():
+        _, lp, _, v = pol.evaluate(torch.from_numpy(obs.reshape(-1, 3)), torch.from_numpy(acts.reshape(-1, 1)))
+    np.testing.assert_allclose(buf.log_probs.cpu().numpy().reshape(-1), lp.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(buf.values.cpu().numpy().reshape(-1), v.numpy().reshape(-1), rtol=2e-5, atol=5e-6)

@@ -75,9 +75,22 @@ def test_unsupported_configs_fail_loudly():
         ppo(_params(gym_id="LunarLander-v2"))
     with pytest.raises(_lib.AurError):
         ppo(_params(continuous=True))                    # CartPole is discrete
-    agent = ppo(_params(hidden_dim=32, total_timesteps=512))
+    agent = ppo(_params(hidden_dim=66, total_timesteps=512))
     with pytest.raises(_lib.AurError, match="hidden_dim"):
         agent.train()
+
+
+@pytest.mark.parametrize("kw", [dict(hidden_dim=32), dict(hidden_dim=128, num_layers=3), dict(num_layers=1), dict(num_layers=4)])
+def test_other_widths_and_depths_train_through_the_drop_in_api(kw):
+    """`-d` / `-nl` (src/run_ppo.py:36,38) other than 64 / 2: runtime-width rollout + shape-generic update; CartPole
+    returns improve within a short budget like the 64 x 2 config."""
+    from aur_ppo_b200.ppo import ppo
+    torch.manual_seed(1)
+    agent = ppo(_params(num_envs=64, total_timesteps=64 * 128 * 12, **kw))
+    rets, lens, xs = agent.train()
+    assert len(rets) > 20 and np.isfinite(list(agent.last_stats.values())).all()
+    k = max(5, len(rets) // 5)
+    assert np.mean(rets[-k:]) > np.mean(rets[:k]) + 5, (np.mean(rets[:k]), np.mean(rets[-k:]))
 
 
 def test_mountaincar_runs_through_the_drop_in_api():
