@@ -75,9 +75,8 @@ def test_unsupported_configs_fail_loudly():
         ppo(_params(gym_id="LunarLander-v2"))
     with pytest.raises(_lib.AurError):
         ppo(_params(continuous=True))                    # CartPole is discrete
-    agent = ppo(_params(hidden_dim=66, total_timesteps=512))
     with pytest.raises(_lib.AurError, match="hidden_dim"):
-        agent.train()
+        ppo(_params(hidden_dim=66, total_timesteps=512)).train()
 
 
 @pytest.mark.parametrize("kw", [dict(hidden_dim=32), dict(hidden_dim=128, num_layers=3), dict(num_layers=1), dict(num_layers=4)])
