@@ -142,6 +142,86 @@ struct MountainCar {
   }
 };
 
+// ---- Acrobot-v1 (gym/envs/classic_control/acrobot.py, "book" dynamics, no torque noise) -------------------------------
+// fp64 state [theta1, theta2, dtheta1, dtheta2], one classic RK4 step of dt = 0.2 per env step with the torque carried as a
+// fifth, constant component; every expression keeps the operation order of the Python source so that each fp64 operation
+// rounds once (the library is compiled with --fmad=false).  reset() rounds the uniform draws to fp32 as gym does
+// (`.astype(np.float32)`).  Trigonometry goes through the deterministic sin/cos shared with the CPU checker.
+struct Acrobot {
+  static constexpr int S = 4, OBS = 6, LIMIT = 500;
+  double s0, s1, s2, s3;
+  __device__ __forceinline__ void load(const double* g, long long N, long long n) {
+    s0 = g[n]; s1 = g[N + n]; s2 = g[2 * N + n]; s3 = g[3 * N + n];
+  }
+  __device__ __forceinline__ void store(double* g, long long N, long long n) const {
+    g[n] = s0; g[N + n] = s1; g[2 * N + n] = s2; g[3 * N + n] = s3;
+  }
+  __device__ __forceinline__ void reset(Pcg64& rng) {
+    s0 = (double)(float)rng.uniform(-0.1, 0.1 - (-0.1)); s1 = (double)(float)rng.uniform(-0.1, 0.1 - (-0.1));
+    s2 = (double)(float)rng.uniform(-0.1, 0.1 - (-0.1)); s3 = (double)(float)rng.uniform(-0.1, 0.1 - (-0.1));
+  }
+  __device__ __forceinline__ void raw_obs(float (&o)[8]) const {
+    double sa, ca, sb, cb;
+    aur_sincos(s0, &sa, &ca);
+    aur_sincos(s1, &sb, &cb);
+    o[0] = (float)ca; o[1] = (float)sa; o[2] = (float)cb; o[3] = (float)sb; o[4] = (float)s2; o[5] = (float)s3;
+    o[6] = 0.0f; o[7] = 0.0f;
+  }
+  // AcrobotEnv._dsdt: y = [theta1, theta2, dtheta1, dtheta2], a = torque -> k = d/dt of the four components
+  static __device__ __forceinline__ void dsdt(const double (&y)[4], double a, double (&k)[4]) {
+    const double m1 = 1.0, m2 = 1.0, l1 = 1.0, lc1 = 0.5, lc2 = 0.5, I1 = 1.0, I2 = 1.0, g = 9.8;
+    const double PI = 3.141592653589793;
+    const double theta1 = y[0], theta2 = y[1], dtheta1 = y[2], dtheta2 = y[3];
+    double sin2, cos2, sd, c12, c1;
+    aur_sincos(theta2, &sin2, &cos2);
+    aur_sincos(theta1 + theta2 - PI / 2.0, &sd, &c12);
+    aur_sincos(theta1 - PI / 2, &sd, &c1);
+    const double d1 = m1 * (lc1 * lc1) + m2 * (l1 * l1 + lc2 * lc2 + 2 * l1 * lc2 * cos2) + I1 + I2;
+    const double d2 = m2 * (lc2 * lc2 + l1 * lc2 * cos2) + I2;
+    const double phi2 = m2 * lc2 * g * c12;
+    const double phi1 = -m2 * l1 * lc2 * (dtheta2 * dtheta2) * sin2 - 2 * m2 * l1 * lc2 * dtheta2 * dtheta1 * sin2 +
+                        (m1 * lc1 + m2 * l1) * g * c1 + phi2;
+    const double ddtheta2 = (a + d2 / d1 * phi1 - m2 * l1 * lc2 * (dtheta1 * dtheta1) * sin2 - phi2) /
+                            (m2 * (lc2 * lc2) + I2 - (d2 * d2) / d1);
+    const double ddtheta1 = -(d2 * ddtheta2 + phi1) / d1;
+    k[0] = dtheta1; k[1] = dtheta2; k[2] = ddtheta1; k[3] = ddtheta2;
+  }
+  __device__ __forceinline__ double step(int action, bool& terminated) {
+    const double PI = 3.141592653589793, dt = 0.2 - 0, dt2 = dt / 2.0;
+    const double torque = (double)(action - 1);                 // AVAIL_TORQUE = [-1., 0., +1]
+    const double y0[4] = {s0, s1, s2, s3};
+    double k1[4], k2[4], k3[4], k4[4], y[4];
+    dsdt(y0, torque, k1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = y0[i] + dt2 * k1[i];
+    dsdt(y, torque, k2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = y0[i] + dt2 * k2[i];
+    dsdt(y, torque, k3);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = y0[i] + dt * k3[i];
+    dsdt(y, torque, k4);
+    double ns[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ns[i] = y0[i] + dt / 6.0 * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+    const double diff = PI - (-PI);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                               // wrap(x, -pi, pi)
+      while (ns[i] > PI) ns[i] = ns[i] - diff;
+      while (ns[i] < -PI) ns[i] = ns[i] + diff;
+    }
+    const double mv1 = 4 * PI, mv2 = 9 * PI;                    // bound(x, -MAX_VEL, MAX_VEL) = min(max(x, m), M)
+    ns[2] = ns[2] < -mv1 ? -mv1 : ns[2]; ns[2] = ns[2] > mv1 ? mv1 : ns[2];
+    ns[3] = ns[3] < -mv2 ? -mv2 : ns[3]; ns[3] = ns[3] > mv2 ? mv2 : ns[3];
+    s0 = ns[0]; s1 = ns[1]; s2 = ns[2]; s3 = ns[3];
+    double sa, ca, sb, cb;
+    aur_sincos(s0, &sa, &ca);
+    aur_sincos(s1 + s0, &sb, &cb);
+    terminated = (-ca - cb) > 1.0;
+    return terminated ? 0.0 : -1.0;
+  }
+};
+
 // ---- Pendulum-v1 (gym/envs/classic_control/pendulum.py, g = 10) --------------------------
 struct Pendulum {
   static constexpr int S = 2, OBS = 3, LIMIT = 200;
@@ -231,15 +311,16 @@ __host__ __device__ inline int64_t dyn_policy_smem_floats(int obs, int H, int NL
 }
 
 // forward of one net for E envs of a thread: compiled 64-wide path (registers) or the runtime-width path (HID == 0)
-template <int HID, int E>
+template <int HID, int E, int INP>
 __device__ __forceinline__ void policy_net_forward(const RolloutDev& a, const float* __restrict__ net, bool vec, int out_dim,
-                                                   const float (&x)[E][POL_IN_PAD], float (&o)[E][POL_OUT_MAX],
+                                                   const float (&x)[E][INP], float (&o)[E][POL_OUT_MAX],
                                                    float* __restrict__ scratch) {
   if constexpr (HID == 0) {
     static_assert(E == 1, "runtime-width policies run one env per thread");
-    if (vec) mlp_forward_dyn<true, POL_IN_PAD, POL_OUT_MAX>(net, a.obs_dim, a.hid, a.nl, out_dim, x[0], o[0], scratch, blockDim.x);
-    else mlp_forward_dyn<false, POL_IN_PAD, POL_OUT_MAX>(net, a.obs_dim, a.hid, a.nl, out_dim, x[0], o[0], scratch, blockDim.x);
+    if (vec) mlp_forward_dyn<true, INP, POL_OUT_MAX>(net, a.obs_dim, a.hid, a.nl, out_dim, x[0], o[0], scratch, blockDim.x);
+    else mlp_forward_dyn<false, INP, POL_OUT_MAX>(net, a.obs_dim, a.hid, a.nl, out_dim, x[0], o[0], scratch, blockDim.x);
   } else {
+    static_assert(INP == POL_IN_PAD, "the register-resident 64-wide path takes at most 4 observation dims");
     mlp_forward<HID, E>(net, a.nl, out_dim, x, o, scratch, blockDim.x);
   }
 }

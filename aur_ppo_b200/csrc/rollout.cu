@@ -34,13 +34,15 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
   __syncthreads();
 
   constexpr bool PEND = ENV::OBS == 3;
+  constexpr int INP = ENV::OBS > POL_IN_PAD ? 8 : POL_IN_PAD;     // observation registers per env (Acrobot: 6 -> 8)
+  static_assert(HID == 0 || INP == POL_IN_PAD, "observations wider than 4 run the runtime-width policy path");
   const long long N = a.N;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 
   ENV env[E];
   NormState nm[PEND ? E : 1];
-  float obs[E][POL_IN_PAD];
+  float obs[E][INP];
   float done_prev[E], ep_ret[E];
   int elapsed[E], ep_len[E];
   bool live[E];
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
     elapsed[e] = a.env.elapsed[m]; ep_ret[e] = a.env.ep_return[m]; ep_len[e] = a.env.ep_length[m];
     done_prev[e] = a.next_done[m];
 #pragma unroll
-    for (int k = 0; k < POL_IN_PAD; ++k) obs[e][k] = k < ENV::OBS ? a.next_obs[m * ENV::OBS + k] : 0.0f;
+    for (int k = 0; k < INP; ++k) obs[e][k] = k < ENV::OBS ? a.next_obs[m * ENV::OBS + k] : 0.0f;
     if constexpr (PEND) { if (a.wrappers) nm[e].load(a.env.norm, N, m); }
   }
   NormalConsts nc;
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
 #pragma unroll 1
     for (int net = 0; net < (CRITIC ? 2 : 1); ++net) {
       float o[E][POL_OUT_MAX];
-      policy_net_forward<HID, E>(a, net == 0 ? sActor : sCritic, net == 0 || vec_critic, net == 0 ? a.act_dim : 1, obs, o, scratch);
+      policy_net_forward<HID, E, INP>(a, net == 0 ? sActor : sCritic, net == 0 || vec_critic, net == 0 ? a.act_dim : 1, obs, o, scratch);
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         if (net == 0) {
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
   // ---- write back: next_obs / next_done / env state, and critic(next_obs) for GAE (ppo.py:161)
   if (CRITIC && a.next_value) {
     float o[E][POL_OUT_MAX];
-    policy_net_forward<HID, E>(a, sCritic, vec_critic, 1, obs, o, scratch);
+    policy_net_forward<HID, E, INP>(a, sCritic, vec_critic, 1, obs, o, scratch);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const long long n = base + e * stride;
@@ -211,7 +213,7 @@ __global__ void env_reset_kernel(long long N, int wrappers, aur_env_state st, fl
   rng.store(st.pcg, N, n);
   env.store(st.phys, N, n);
   st.elapsed[n] = 0; st.ep_return[n] = 0.0f; st.ep_length[n] = 0;
-  float obs[POL_IN_PAD];
+  float obs[ENV::OBS > POL_IN_PAD ? 8 : POL_IN_PAD];
   if constexpr (ENV::OBS == 3) {
     float raw[3];
     env.raw_obs(raw);
@@ -431,6 +433,8 @@ extern "C" int aur_env_reset(int32_t env_kind, int64_t N, int32_t wrappers, cons
     env_reset_kernel<CartPole><<<grid, 128, 0, s>>>((long long)N, 0, *st, obs_out, done_out);
   } else if (env_kind == AUR_ENV_MOUNTAINCAR) {
     env_reset_kernel<MountainCar><<<grid, 128, 0, s>>>((long long)N, 0, *st, obs_out, done_out);
+  } else if (env_kind == AUR_ENV_ACROBOT) {
+    env_reset_kernel<Acrobot><<<grid, 128, 0, s>>>((long long)N, 0, *st, obs_out, done_out);
   } else if (env_kind == AUR_ENV_PENDULUM) {
     if (wrappers && !st->norm) { set_error("aur_env_reset: wrappers need env.norm"); return AUR_ERR_ARG; }
     env_reset_kernel<Pendulum><<<grid, 128, 0, s>>>((long long)N, wrappers, *st, obs_out, done_out);
@@ -459,7 +463,7 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
   const aur_rollout_args& a = *args;
   if (a.N < 0 || a.T < 0) { set_error("aur_rollout: negative N or T"); return AUR_ERR_ARG; }
   if (a.N == 0 || a.T == 0) return 0;
-  int rc = check_policy(a.policy, "aur_rollout", POL_IN_PAD);
+  int rc = check_policy(a.policy, "aur_rollout", DYN_IO);
   if (rc) return rc;
   if (!a.params || !a.obs_buf || !a.act_buf || !a.logp_buf || !a.val_buf || !a.rew_buf || !a.done_buf || !a.next_obs ||
       !a.next_done || !a.env.phys || !a.env.pcg || !a.env.elapsed || !a.env.ep_return || !a.env.ep_length) {
@@ -470,6 +474,8 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
     if (a.policy.continuous || a.policy.obs_dim != 4 || a.policy.act_dim != 2) { set_error("aur_rollout: CartPole needs obs 4, 2 discrete actions"); return AUR_ERR_ARG; }
   } else if (a.env_kind == AUR_ENV_MOUNTAINCAR) {
     if (a.policy.continuous || a.policy.obs_dim != 2 || a.policy.act_dim != 3) { set_error("aur_rollout: MountainCar needs obs 2, 3 discrete actions"); return AUR_ERR_ARG; }
+  } else if (a.env_kind == AUR_ENV_ACROBOT) {
+    if (a.policy.continuous || a.policy.obs_dim != 6 || a.policy.act_dim != 3) { set_error("aur_rollout: Acrobot needs obs 6, 3 discrete actions"); return AUR_ERR_ARG; }
   } else if (pend) {
     if (!a.policy.continuous || a.policy.obs_dim != 3 || a.policy.act_dim != 1) { set_error("aur_rollout: Pendulum needs obs 3, 1 continuous action"); return AUR_ERR_ARG; }
     if (a.wrappers && !a.env.norm) { set_error("aur_rollout: wrappers need env.norm"); return AUR_ERR_ARG; }
@@ -493,6 +499,7 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
   } while (0)
     if (pend) AUR_LAUNCH_DYN(Pendulum);
     else if (a.env_kind == AUR_ENV_MOUNTAINCAR) AUR_LAUNCH_DYN(MountainCar);
+    else if (a.env_kind == AUR_ENV_ACROBOT) AUR_LAUNCH_DYN(Acrobot);
     else AUR_LAUNCH_DYN(CartPole);
 #undef AUR_LAUNCH_DYN
     AUR_LAUNCH_OK("rollout_kernel (runtime width)");

@@ -16,10 +16,10 @@ import torch
 from . import _lib
 from .kernels import _stream, _ptr
 
-CARTPOLE, PENDULUM, MOUNTAINCAR = 0, 1, 2
-ENV_IDS = {"CartPole-v1": CARTPOLE, "Pendulum-v1": PENDULUM, "MountainCar-v0": MOUNTAINCAR}
-OBS_DIM = {CARTPOLE: 4, PENDULUM: 3, MOUNTAINCAR: 2}
-PHYS_DIM = {CARTPOLE: 4, PENDULUM: 2, MOUNTAINCAR: 2}
+CARTPOLE, PENDULUM, MOUNTAINCAR, ACROBOT = 0, 1, 2, 3
+ENV_IDS = {"CartPole-v1": CARTPOLE, "Pendulum-v1": PENDULUM, "MountainCar-v0": MOUNTAINCAR, "Acrobot-v1": ACROBOT}
+OBS_DIM = {CARTPOLE: 4, PENDULUM: 3, MOUNTAINCAR: 2, ACROBOT: 6}
+PHYS_DIM = {CARTPOLE: 4, PENDULUM: 2, MOUNTAINCAR: 2, ACROBOT: 4}
 
 
 def pcg64_seed_states(seeds: Sequence[int]) -> np.ndarray:

@@ -36,6 +36,7 @@ extern "C" {
 #define AUR_ENV_CARTPOLE 0 /* gym CartPole-v1 */
 #define AUR_ENV_PENDULUM 1 /* gym Pendulum-v1 */
 #define AUR_ENV_MOUNTAINCAR 2 /* gym MountainCar-v0 (discrete, 3 actions, obs 2) */
+#define AUR_ENV_ACROBOT 3     /* gym Acrobot-v1 (discrete, 3 actions, obs 6; runtime-width policy path) */
 
 int aur_abi_version(void);
 const char* aur_last_error(void);
@@ -107,7 +108,7 @@ int aur_policy_evaluate(const aur_policy_desc* desc, const float* params, int64_
  * clip +-10, NormalizeReward(gamma), clip +-10 (src/ppo.py:92-97), per env.
  * All arrays are struct-of-arrays over the N envs this GPU owns. */
 typedef struct {
-  double* phys;       /* [S][N] fp64: CartPole x, x_dot, theta, theta_dot; Pendulum theta, theta_dot; MountainCar position, velocity */
+  double* phys;       /* [S][N] fp64: CartPole x, x_dot, theta, theta_dot; Pendulum theta, theta_dot; MountainCar position, velocity; Acrobot theta1, theta2, dtheta1, dtheta2 */
   uint64_t* pcg;      /* [4][N] PCG64 state_hi, state_lo, inc_hi, inc_lo (np.random.PCG64(SeedSequence(seed_i))) */
   int32_t* elapsed;   /* [N] TimeLimit step counter */
   float* ep_return;   /* [N] RecordEpisodeStatistics accumulator (fp32 as in gym) */

@@ -37,8 +37,8 @@ static inline double pcg64_double(pcg64_t* g) { return (double)(pcg64_next(g) >>
 /* Generator.uniform(low, high): low + (high - low) * next_double */
 static inline double pcg64_uniform(pcg64_t* g, double low, double range) { return low + range * pcg64_double(g); }
 
-static inline int obs_dim_of(int kind) { return kind == 0 ? 4 : (kind == 1 ? 3 : 2); }
-static inline int time_limit_of(int kind) { return kind == 0 ? 500 : 200; }
+static inline int obs_dim_of(int kind) { return kind == 0 ? 4 : (kind == 1 ? 3 : (kind == 3 ? 6 : 2)); }
+static inline int time_limit_of(int kind) { return (kind == 0 || kind == 3) ? 500 : 200; }
 
 static inline void trig(int mode, double x, double* s, double* c) {
   if (mode == 0) { *s = sin(x); *c = cos(x); }
@@ -67,9 +67,63 @@ static inline void rms_update1(double* mean, double* var, double* count, double 
   *mean = new_mean; *var = M2 / tot; *count = tot;
 }
 
+/* ---- Acrobot-v1 (gym/envs/classic_control/acrobot.py: AcrobotEnv._dsdt with book_or_nips = "book", rk4, wrap, bound) ---- */
+static void acrobot_dsdt(int mode, const double* y, double a, double* k) {
+  const double m1 = 1.0, m2 = 1.0, l1 = 1.0, lc1 = 0.5, lc2 = 0.5, I1 = 1.0, I2 = 1.0, g = 9.8;
+  const double pi = 3.141592653589793;
+  double theta1 = y[0], theta2 = y[1], dtheta1 = y[2], dtheta2 = y[3];
+  double sin2, cos2, sd, c12, c1;
+  trig(mode, theta2, &sin2, &cos2);
+  trig(mode, theta1 + theta2 - pi / 2.0, &sd, &c12);
+  trig(mode, theta1 - pi / 2, &sd, &c1);
+  double d1 = m1 * (lc1 * lc1) + m2 * (l1 * l1 + lc2 * lc2 + 2 * l1 * lc2 * cos2) + I1 + I2;
+  double d2 = m2 * (lc2 * lc2 + l1 * lc2 * cos2) + I2;
+  double phi2 = m2 * lc2 * g * c12;
+  double phi1 = -m2 * l1 * lc2 * (dtheta2 * dtheta2) * sin2 - 2 * m2 * l1 * lc2 * dtheta2 * dtheta1 * sin2 +
+                (m1 * lc1 + m2 * l1) * g * c1 + phi2;
+  double ddtheta2 = (a + d2 / d1 * phi1 - m2 * l1 * lc2 * (dtheta1 * dtheta1) * sin2 - phi2) /
+                    (m2 * (lc2 * lc2) + I2 - (d2 * d2) / d1);
+  double ddtheta1 = -(d2 * ddtheta2 + phi1) / d1;
+  k[0] = dtheta1; k[1] = dtheta2; k[2] = ddtheta1; k[3] = ddtheta2;
+}
+/* one env.step of Acrobot: st[4] updated in place, returns terminated */
+static int acrobot_step(int mode, double* st, int action) {
+  const double pi = 3.141592653589793, dt = 0.2 - 0, dt2 = dt / 2.0;
+  double torque = (double)(action - 1);     /* AVAIL_TORQUE = [-1., 0., +1] */
+  double k1[4], k2[4], k3[4], k4[4], y[4], ns[4];
+  acrobot_dsdt(mode, st, torque, k1);
+  for (int i = 0; i < 4; ++i) y[i] = st[i] + dt2 * k1[i];
+  acrobot_dsdt(mode, y, torque, k2);
+  for (int i = 0; i < 4; ++i) y[i] = st[i] + dt2 * k2[i];
+  acrobot_dsdt(mode, y, torque, k3);
+  for (int i = 0; i < 4; ++i) y[i] = st[i] + dt * k3[i];
+  acrobot_dsdt(mode, y, torque, k4);
+  for (int i = 0; i < 4; ++i) ns[i] = st[i] + dt / 6.0 * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+  double diff = pi - (-pi);
+  for (int i = 0; i < 2; ++i) {
+    while (ns[i] > pi) ns[i] = ns[i] - diff;
+    while (ns[i] < -pi) ns[i] = ns[i] + diff;
+  }
+  double mv1 = 4 * pi, mv2 = 9 * pi;
+  ns[2] = ns[2] < -mv1 ? -mv1 : ns[2]; ns[2] = ns[2] > mv1 ? mv1 : ns[2];
+  ns[3] = ns[3] < -mv2 ? -mv2 : ns[3]; ns[3] = ns[3] > mv2 ? mv2 : ns[3];
+  for (int i = 0; i < 4; ++i) st[i] = ns[i];
+  double sa, ca, sb, cb;
+  trig(mode, st[0], &sa, &ca);
+  trig(mode, st[1] + st[0], &sb, &cb);
+  return (-ca - cb) > 1.0;
+}
+static void acrobot_raw_obs(int mode, const double* st, double* raw) {
+  double sa, ca, sb, cb;
+  trig(mode, st[0], &sa, &ca);
+  trig(mode, st[1], &sb, &cb);
+  raw[0] = (double)(float)ca; raw[1] = (double)(float)sa; raw[2] = (double)(float)cb; raw[3] = (double)(float)sb;
+  raw[4] = (double)(float)st[2]; raw[5] = (double)(float)st[3];
+}
+
 /* ---- vector env ---- */
 typedef struct {
-  int kind;        /* 0 CartPole-v1, 1 Pendulum-v1, 2 MountainCar-v0 */
+  int kind;        /* 0 CartPole-v1, 1 Pendulum-v1, 2 MountainCar-v0, 3 Acrobot-v1 */
   int wrappers;    /* 1 = the reference's continuous wrapper stack (ppo.py:92-97) */
   int trig_mode;
   int64_t n;
@@ -141,6 +195,13 @@ static void env_reset(orc_vec_t* v, int64_t i, float* obs_out) {
     double s, c; trig(v->trig_mode, st[0], &s, &c);
     double raw[3] = {(double)(float)c, (double)(float)s, (double)(float)st[1]};
     emit_obs(v, i, raw, 3, obs_out);
+  } else if (v->kind == 3) {
+    /* Acrobot-v1 reset: uniform(-0.1, 0.1, size=4).astype(np.float32); the observation's sin / cos are evaluated in
+     * fp64 and rounded (NumPy evaluates them in float32 on the float32 state: may differ by one ulp in rare cases) */
+    for (int k = 0; k < 4; ++k) st[k] = (double)(float)pcg64_uniform(&v->rng[i], -0.1, 0.1 - (-0.1));
+    double raw[6];
+    acrobot_raw_obs(v->trig_mode, st, raw);
+    emit_obs(v, i, raw, 6, obs_out);
   } else {
     /* MountainCar-v0 (mountain_car.py reset): state = [uniform(-0.6, -0.4), 0] */
     st[0] = pcg64_uniform(&v->rng[i], -0.6, -0.4 - (-0.6));
@@ -173,8 +234,13 @@ void orc_vec_step(void* h, const void* actions, float* obs_out, double* rew_out,
     double* st = &v->phys[i * 4];
     double reward; int terminated = 0, truncated = 0;
     float* o = &obs_out[i * obs_dim_of(v->kind)];
-    double raw[4]; int d;
-    if (v->kind == 0) {
+    double raw[6]; int d;
+    if (v->kind == 3) {
+      terminated = acrobot_step(v->trig_mode, st, ((const int32_t*)actions)[i]);
+      reward = terminated ? 0.0 : -1.0;
+      acrobot_raw_obs(v->trig_mode, st, raw);
+      d = 6;
+    } else if (v->kind == 0) {
       const double gravity = 9.8, masscart = 1.0, masspole = 0.1, length = 0.5, force_mag = 10.0, tau = 0.02;
       const double total_mass = masspole + masscart, polemass_length = masspole * length;
       const double theta_thr = 12 * 2 * M_PI / 360, x_thr = 2.4;
@@ -242,7 +308,7 @@ void orc_vec_step(void* h, const void* actions, float* obs_out, double* rew_out,
     if (terminated || truncated) { final_ret[i] = v->ep_ret[i]; final_len[i] = v->ep_len[i]; }
     /* NormalizeObservation + clip for the stepped obs (updates the running stats
      * even when the env is about to be reset: the wrapper runs before autoreset) */
-    float stepped[4];
+    float stepped[6];
     emit_obs(v, i, raw, d, stepped);
     if (v->wrappers) {
       /* NormalizeReward + clip */
@@ -260,7 +326,7 @@ void orc_vec_step(void* h, const void* actions, float* obs_out, double* rew_out,
 
 /* raw fp64 physical state, [n][S] (S = 4 CartPole, 2 Pendulum) */
 void orc_vec_get_phys(void* h, double* out) {
-  orc_vec_t* v = (orc_vec_t*)h; int S = v->kind == 0 ? 4 : 2;
+  orc_vec_t* v = (orc_vec_t*)h; int S = (v->kind == 0 || v->kind == 3) ? 4 : 2;
   for (int64_t i = 0; i < v->n; ++i) for (int k = 0; k < S; ++k) out[i * S + k] = v->phys[i * 4 + k];
 }
 /* wrapper statistics, [n][11]: o_mean[3], o_var[3], o_count, r_mean, r_var, r_count, r_ret */

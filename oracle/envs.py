@@ -16,9 +16,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-CARTPOLE, PENDULUM, MOUNTAINCAR = 0, 1, 2
-OBS_DIM = {CARTPOLE: 4, PENDULUM: 3, MOUNTAINCAR: 2}
-PHYS_DIM = {CARTPOLE: 4, PENDULUM: 2, MOUNTAINCAR: 2}
+CARTPOLE, PENDULUM, MOUNTAINCAR, ACROBOT = 0, 1, 2, 3
+OBS_DIM = {CARTPOLE: 4, PENDULUM: 3, MOUNTAINCAR: 2, ACROBOT: 6}
+PHYS_DIM = {CARTPOLE: 4, PENDULUM: 2, MOUNTAINCAR: 2, ACROBOT: 4}
 TRIG_LIBM, TRIG_DET = 0, 1
 
 
@@ -116,7 +116,7 @@ class CVecEnv:
         return (self._obs.copy(), self._rew.copy(), self._term.astype(bool), self._trunc.astype(bool), info)
 
     def phys(self) -> np.ndarray:
-        out = np.zeros((self.num_envs, 4 if self.kind == CARTPOLE else 2), np.float64)
+        out = np.zeros((self.num_envs, PHYS_DIM[self.kind]), np.float64)
         lib().orc_vec_get_phys(self._h, out.ctypes.data)
         return out[:, :PHYS_DIM[self.kind]]
 

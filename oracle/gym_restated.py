@@ -11,6 +11,7 @@ algorithm of
 
   gym/envs/classic_control/cartpole.py    (CartPoleEnv.step / reset)
   gym/envs/classic_control/pendulum.py    (PendulumEnv.step / reset / _get_obs)
+  gym/envs/classic_control/mountain_car.py, acrobot.py (step / reset; rk4, wrap, bound)
   gym/wrappers/time_limit.py              (TimeLimit)
   gym/wrappers/record_episode_statistics.py
   gym/wrappers/clip_action.py, normalize.py, transform_observation.py,
@@ -144,6 +145,111 @@ class MountainCarEnv:
         reward = -1.0
         self.state = (position, velocity)
         return np.array(self.state, dtype=np.float32), reward, terminated, False, {}
+
+
+class AcrobotEnv:
+    """gym Acrobot-v1 (acrobot.py): two-link pendulum, "book" dynamics, torque noise 0, one RK4 step of dt = 0.2.
+
+    Written the way the gym source reads (NumPy fp64 arrays through rk4 / _dsdt / wrap / bound) so that the C checker
+    (oracle/envs.c, scalar code) is an independent restatement.  One deliberate difference: right after reset the state
+    is a float32 array and NumPy would evaluate the observation's sin / cos in float32; here they are evaluated in
+    fp64 and rounded (at most one ulp apart, rarely), because NumPy's float32 trig kernels are platform specific."""
+
+    dt = 0.2
+    LINK_LENGTH_1 = 1.0
+    LINK_LENGTH_2 = 1.0
+    LINK_MASS_1 = 1.0
+    LINK_MASS_2 = 1.0
+    LINK_COM_POS_1 = 0.5
+    LINK_COM_POS_2 = 0.5
+    LINK_MOI = 1.0
+    MAX_VEL_1 = 4 * math.pi
+    MAX_VEL_2 = 9 * math.pi
+    AVAIL_TORQUE = [-1.0, 0.0, +1]
+
+    def __init__(self, sincos: Callable[[float], Tuple[float, float]] = _libm_sincos):
+        self.state = None
+        self.np_random = None
+        self._sincos = sincos
+        self.obs_dim = 6
+
+    def _sin(self, x):
+        return self._sincos(float(x))[0]
+
+    def _cos(self, x):
+        return self._sincos(float(x))[1]
+
+    def reset(self, seed: Optional[int] = None):
+        if seed is not None or self.np_random is None:
+            self.np_random = np_random(seed)
+        self.state = self.np_random.uniform(low=-0.1, high=0.1, size=(4,)).astype(np.float32)
+        return self._get_ob(), {}
+
+    def step(self, a):
+        s = self.state
+        torque = self.AVAIL_TORQUE[int(a)]
+        s_augmented = np.append(np.asarray(s, dtype=np.float64), torque)
+        ns = self._rk4(s_augmented, [0, self.dt])
+        ns[0] = self._wrap(ns[0], -math.pi, math.pi)
+        ns[1] = self._wrap(ns[1], -math.pi, math.pi)
+        ns[2] = min(max(ns[2], -self.MAX_VEL_1), self.MAX_VEL_1)
+        ns[3] = min(max(ns[3], -self.MAX_VEL_2), self.MAX_VEL_2)
+        self.state = ns
+        terminated = self._terminal()
+        reward = -1.0 if not terminated else 0.0
+        return self._get_ob(), reward, terminated, False, {}
+
+    def _get_ob(self):
+        s = self.state
+        return np.array([self._cos(s[0]), self._sin(s[0]), self._cos(s[1]), self._sin(s[1]), s[2], s[3]], dtype=np.float32)
+
+    def _terminal(self):
+        s = self.state
+        return bool(-self._cos(s[0]) - self._cos(float(s[1]) + float(s[0])) > 1.0)
+
+    def _dsdt(self, s_augmented):
+        m1, m2 = self.LINK_MASS_1, self.LINK_MASS_2
+        l1 = self.LINK_LENGTH_1
+        lc1, lc2 = self.LINK_COM_POS_1, self.LINK_COM_POS_2
+        I1 = I2 = self.LINK_MOI
+        g = 9.8
+        pi = math.pi
+        a = float(s_augmented[-1])
+        theta1, theta2, dtheta1, dtheta2 = (float(v) for v in s_augmented[:-1])
+        sin, cos = self._sin, self._cos
+        d1 = m1 * (lc1 * lc1) + m2 * (l1 * l1 + lc2 * lc2 + 2 * l1 * lc2 * cos(theta2)) + I1 + I2
+        d2 = m2 * (lc2 * lc2 + l1 * lc2 * cos(theta2)) + I2
+        phi2 = m2 * lc2 * g * cos(theta1 + theta2 - pi / 2.0)
+        phi1 = (-m2 * l1 * lc2 * (dtheta2 * dtheta2) * sin(theta2) - 2 * m2 * l1 * lc2 * dtheta2 * dtheta1 * sin(theta2)
+                + (m1 * lc1 + m2 * l1) * g * cos(theta1 - pi / 2) + phi2)
+        ddtheta2 = (a + d2 / d1 * phi1 - m2 * l1 * lc2 * (dtheta1 * dtheta1) * sin(theta2) - phi2) / \
+                   (m2 * (lc2 * lc2) + I2 - (d2 * d2) / d1)
+        ddtheta1 = -(d2 * ddtheta2 + phi1) / d1
+        return dtheta1, dtheta2, ddtheta1, ddtheta2, 0.0
+
+    def _rk4(self, y0, t):
+        yout = np.zeros((len(t), len(y0)), np.float64)
+        yout[0] = y0
+        for i in np.arange(len(t) - 1):
+            this = t[i]
+            dt = t[i + 1] - this
+            dt2 = dt / 2.0
+            y0 = yout[i]
+            k1 = np.asarray(self._dsdt(y0))
+            k2 = np.asarray(self._dsdt(y0 + dt2 * k1))
+            k3 = np.asarray(self._dsdt(y0 + dt2 * k2))
+            k4 = np.asarray(self._dsdt(y0 + dt * k3))
+            yout[i + 1] = y0 + dt / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+        return yout[-1][:4]
+
+    @staticmethod
+    def _wrap(x, m, M):
+        diff = M - m
+        while x > M:
+            x = x - diff
+        while x < m:
+            x = x + diff
+        return x
 
 
 def angle_normalize(x: float) -> float:
@@ -345,6 +451,9 @@ def make_env(gym_id: str, continuous: bool, sincos=_libm_sincos):
     elif gym_id == "MountainCar-v0":
         env = TimeLimit(MountainCarEnv(sincos), 200)
         obs_shape = (2,)
+    elif gym_id == "Acrobot-v1":
+        env = TimeLimit(AcrobotEnv(sincos), 500)
+        obs_shape = (6,)
     else:
         raise ValueError(f"unsupported gym_id {gym_id!r}")
     env = RecordEpisodeStatistics(env)

@@ -36,7 +36,8 @@ def test_pcg64_stream_matches_numpy():
 
 
 @pytest.mark.parametrize("kind,gid,cont", [(E.CARTPOLE, "CartPole-v1", False), (E.PENDULUM, "Pendulum-v1", True),
-                                           (E.PENDULUM, "Pendulum-v1", False), (E.MOUNTAINCAR, "MountainCar-v0", False)])
+                                           (E.PENDULUM, "Pendulum-v1", False), (E.MOUNTAINCAR, "MountainCar-v0", False),
+                                           (E.ACROBOT, "Acrobot-v1", False)])
 def test_c_checker_equals_python_restatement(kind, gid, cont):
     N = 6
     pv = G.SyncVectorEnv([G.make_env(gid, cont) for _ in range(N)], E.OBS_DIM[kind])
@@ -47,7 +48,7 @@ def test_c_checker_equals_python_restatement(kind, gid, cont):
     rng = np.random.default_rng(5)
     episodes = 0
     for t in range(700):
-        a = (rng.integers(0, 2, N) if kind == E.CARTPOLE else rng.integers(0, 3, N) if kind == E.MOUNTAINCAR
+        a = (rng.integers(0, 2, N) if kind == E.CARTPOLE else rng.integers(0, 3, N) if kind in (E.MOUNTAINCAR, E.ACROBOT)
              else rng.normal(0, 1.5, (N, 1)).astype(np.float32))
         r1, r2 = pv.step(a), cv.step(a)
         for k in range(4):
@@ -133,3 +134,33 @@ def test_mountaincar_restatement_behaviour():
     for t in range(60):
         obs, *_ = env.step(0)
     assert obs[0] >= -1.2 and (obs[0] > -1.2 or obs[1] >= 0)
+
+
+def test_acrobot_restatement_behaviour():
+    """Acrobot-v1: reward -1 until the tip passes the bar (then 0 and terminated), angles stay wrapped to [-pi, pi],
+    velocities bounded by 4 pi / 9 pi, torque-free motion from rest at the bottom stays at the bottom, an energy-pumping
+    controller swings up well inside the 500-step limit while zero torque never does."""
+    env = G.make_env("Acrobot-v1", False)
+    env.reset(seed=3)
+    inner = env.env.env
+    inner.state = np.zeros(4)
+    for _ in range(20):
+        obs, r, term, trunc, _ = env.step(1)
+        assert r == -1.0 and not term
+    np.testing.assert_allclose(inner.state, 0.0, atol=1e-12)
+    env.reset(seed=4)
+    steps, term = 0, False
+    while not term and steps < 500:
+        a = 2 if inner.state[3] > 0 else 0          # torque along the actuated joint's velocity pumps energy in
+        obs, r, term, trunc, _ = env.step(a)
+        steps += 1
+        assert abs(inner.state[0]) <= np.pi and abs(inner.state[1]) <= np.pi
+        assert abs(inner.state[2]) <= 4 * np.pi and abs(inner.state[3]) <= 9 * np.pi
+        assert obs.dtype == np.float32 and obs.shape == (6,)
+        np.testing.assert_allclose(obs[0] ** 2 + obs[1] ** 2, 1.0, atol=1e-6)
+    assert term and r == 0.0 and steps < 200, steps     # good Acrobot-v1 policies finish in roughly 60-120 steps
+    env.reset(seed=5)
+    for t in range(500):
+        obs, r, term, trunc, info = env.step(1)
+        assert not term
+    assert trunc and info["episode"]["l"] == 500 and info["episode"]["r"] == -500.0

@@ -57,7 +57,7 @@ def test_unsupported_shapes_fail_loudly():
     with pytest.raises(_lib.AurError, match="obs_dim"):
         kernels.policy_evaluate(kernels.policy_desc(9, 2, 64, 2, False), torch.zeros(100000, device="cuda"), torch.zeros(4, 9, device="cuda"))
     with pytest.raises(_lib.AurError, match="no device kernel"):
-        denv.DeviceVecEnv("Acrobot-v1", 4)
+        denv.DeviceVecEnv("LunarLander-v2", 4)
 
 
 def _oracle_replay(kind, N, wrappers, seeds, actions, T):
@@ -434,3 +434,46 @@ def test_pendulum_replay_runtime_width(rollout_impl):
         _, lp, _, v = pol.evaluate(torch.from_numpy(obs.reshape(-1, 3)), torch.from_numpy(acts.reshape(-1, 1)))
     np.testing.assert_allclose(buf.log_probs.cpu().numpy().reshape(-1), lp.numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(buf.values.cpu().numpy().reshape(-1), v.numpy().reshape(-1), rtol=2e-5, atol=5e-6)
+
+
+@pytest.mark.parametrize("N,T,hidden", [(9, 600, 64), (300, 256, 64), (64, 200, 32)])
+def test_acrobot_replay_is_bit_exact(N, T, hidden, rollout_impl):
+    """Acrobot-v1 ((f) rank 4; obs 6 -> the runtime-width policy path): RK4 transitions, wrap / bound, termination and
+    TimeLimit bit for bit against the C checker; log-probs / values against the restated model."""
+    if rollout_impl != "tc":
+        pytest.skip("one kernel behind this path")
+    pol, named = random_policy(6, 3, hidden, 2, False, seed=21)
+    desc = kernels.policy_desc(6, 3, hidden, 2, False)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    seeds = list(range(N))
+    rng = np.random.default_rng(N)
+    # torque along the second joint's velocity most of the time, so that episodes actually terminate inside T
+    actions = rng.integers(0, 3, (T, N))
+    cv = E.CVecEnv(E.ACROBOT, N, trig=E.TRIG_DET)
+    cv.reset(seeds)
+    for t in range(T):
+        greedy = np.where(cv.phys()[:, 3] > 0, 2, 0)
+        actions[t] = np.where(rng.random(N) < 0.8, greedy, actions[t])
+        cv.step(actions[t])
+    cv, obs0, obs, rew, done, last_obs, last_done, episodes = _oracle_replay(E.ACROBOT, N, False, seeds, actions, T)
+    assert done.any() and (rew == 0).any()
+    env = denv.DeviceVecEnv("Acrobot-v1", N, log_capacity=N * 64)
+    o, _ = env.reset(seeds)
+    assert np.array_equal(o.cpu().numpy(), obs0)
+    buf = kernels.RolloutBuffers(T, N, 6, (), "cuda")
+    kernels.rollout(env, desc, flat, buf, seed=1, step0=0, actions_in=torch.from_numpy(actions.astype(np.float32)).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.states.cpu().numpy(), obs)
+    assert np.array_equal(buf.terminals.cpu().numpy(), done)
+    assert np.array_equal(buf.rewards.cpu().numpy(), rew)
+    assert np.array_equal(env.next_obs.cpu().numpy(), last_obs)
+    assert np.array_equal(env.next_done.cpu().numpy(), last_done)
+    assert np.array_equal(env.phys.cpu().numpy().T, cv.phys())
+    assert env.drain_episodes() == sorted(episodes, key=lambda r: (r[0], r[1]))
+    ot = torch.from_numpy(obs.reshape(-1, 6)); at = torch.from_numpy(actions.reshape(-1))
+    with torch.no_grad():
+        _, lp, _, v = pol.evaluate(ot, at)
+        nv = pol.value(torch.from_numpy(last_obs))
+    np.testing.assert_allclose(buf.log_probs.cpu().numpy().reshape(-1), lp.numpy(), **TOL)
+    np.testing.assert_allclose(buf.values.cpu().numpy().reshape(-1), v.numpy().reshape(-1), **TOL)
+    np.testing.assert_allclose(buf.next_value.cpu().numpy(), nv.numpy(), **TOL)

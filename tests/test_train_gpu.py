@@ -72,7 +72,7 @@ def test_unsupported_configs_fail_loudly():
     from aur_ppo_b200 import _lib
     from aur_ppo_b200.ppo import ppo
     with pytest.raises(_lib.AurError):
-        ppo(_params(gym_id="LunarLander-v2"))
+        ppo(_params(gym_id="LunarLander-v2"))                    # Box2D: no device kernel
     with pytest.raises(_lib.AurError):
         ppo(_params(continuous=True))                    # CartPole is discrete
     with pytest.raises(_lib.AurError, match="hidden_dim"):
@@ -102,3 +102,16 @@ def test_mountaincar_runs_through_the_drop_in_api():
     assert agent.num_updates == 3 and len(rets) > 0
     assert all(l <= 200 for l in lens) and all(r == -float(l) for r, l in zip(rets, lens))     # reward -1 per step
     assert np.isfinite([agent.last_stats[k] for k in ("value_loss", "policy_loss", "entropy", "approx_kl")]).all()
+
+
+def test_acrobot_runs_through_the_drop_in_api():
+    """--gym_id Acrobot-v1 ((f) rank 4): obs 6 / 3 actions through the runtime-width rollout, GAE and the shape-generic
+    update; the policy learns to swing up (episodes get shorter than the 500-step limit)."""
+    from aur_ppo_b200.ppo import ppo
+    torch.manual_seed(1)
+    agent = ppo(_params(gym_id="Acrobot-v1", num_envs=16, total_timesteps=16 * 128 * 200))
+    assert agent.buffer.states.shape == (128, 16, 6)
+    rets, lens, xs = agent.train()
+    assert len(rets) > 20 and np.isfinite(list(agent.last_stats.values())).all()
+    k = max(5, len(rets) // 5)
+    assert np.mean(lens[-k:]) < 0.6 * np.mean(lens[:k]), (np.mean(lens[:k]), np.mean(lens[-k:]))
