@@ -45,27 +45,30 @@ __device__ __forceinline__ void rms_update1(double& mean, double& var, double co
 }
 __device__ __forceinline__ double clip10(double z) { return z < -10.0 ? -10.0 : (z > 10.0 ? 10.0 : z); }
 
-// Wrapper statistics of one env: obs mean[3], var[3], count; return-rms mean, var, count; acc.
-struct NormState {
-  double om[3], ov[3], oc, rm, rv, rc, racc;
+// Wrapper statistics of one env: obs mean[D], var[D], count; return-rms mean, var, count; acc -> [2 D + 5][N] in HBM.
+template <int D>
+struct NormStateT {
+  double om[D], ov[D], oc, rm, rv, rc, racc;
   __device__ __forceinline__ void init() {
-    for (int k = 0; k < 3; ++k) { om[k] = 0.0; ov[k] = 1.0; }
+    for (int k = 0; k < D; ++k) { om[k] = 0.0; ov[k] = 1.0; }
     oc = 1e-4; rm = 0.0; rv = 1.0; rc = 1e-4; racc = 0.0;
   }
   __device__ __forceinline__ void load(const double* g, long long N, long long n) {
-    for (int k = 0; k < 3; ++k) { om[k] = g[k * N + n]; ov[k] = g[(3 + k) * N + n]; }
-    oc = g[6 * N + n]; rm = g[7 * N + n]; rv = g[8 * N + n]; rc = g[9 * N + n]; racc = g[10 * N + n];
+    for (int k = 0; k < D; ++k) { om[k] = g[k * N + n]; ov[k] = g[(D + k) * N + n]; }
+    oc = g[(2 * D) * N + n]; rm = g[(2 * D + 1) * N + n]; rv = g[(2 * D + 2) * N + n]; rc = g[(2 * D + 3) * N + n];
+    racc = g[(2 * D + 4) * N + n];
   }
   __device__ __forceinline__ void store(double* g, long long N, long long n) const {
-    for (int k = 0; k < 3; ++k) { g[k * N + n] = om[k]; g[(3 + k) * N + n] = ov[k]; }
-    g[6 * N + n] = oc; g[7 * N + n] = rm; g[8 * N + n] = rv; g[9 * N + n] = rc; g[10 * N + n] = racc;
+    for (int k = 0; k < D; ++k) { g[k * N + n] = om[k]; g[(D + k) * N + n] = ov[k]; }
+    g[(2 * D) * N + n] = oc; g[(2 * D + 1) * N + n] = rm; g[(2 * D + 2) * N + n] = rv; g[(2 * D + 3) * N + n] = rc;
+    g[(2 * D + 4) * N + n] = racc;
   }
   // NormalizeObservation.normalize + clip(-10, 10), result cast to the fp32 obs buffer
-  __device__ __forceinline__ void obs(const float (&raw)[3], float (&out)[POL_IN_PAD]) {
-    for (int k = 0; k < 3; ++k) rms_update1(om[k], ov[k], oc, (double)raw[k]);
+  __device__ __forceinline__ void obs(const float (&raw)[D], float (&out)[POL_IN_PAD]) {
+    for (int k = 0; k < D; ++k) rms_update1(om[k], ov[k], oc, (double)raw[k]);
     oc = oc + 1.0;
-    for (int k = 0; k < 3; ++k) out[k] = (float)clip10(((double)raw[k] - om[k]) / sqrt(ov[k] + 1e-8));
-    out[3] = 0.0f;
+    for (int k = 0; k < D; ++k) out[k] = (float)clip10(((double)raw[k] - om[k]) / sqrt(ov[k] + 1e-8));
+    for (int k = D; k < POL_IN_PAD; ++k) out[k] = 0.0f;
   }
   // NormalizeReward.step + clip(-10, 10)
   __device__ __forceinline__ double reward(double r, bool done, double gamma) {
@@ -77,10 +80,12 @@ struct NormState {
     return clip10(out);
   }
 };
+using NormState = NormStateT<3>;
 
 // ---- CartPole-v1 (gym/envs/classic_control/cartpole.py) ----------------------------------
 struct CartPole {
   static constexpr int S = 4, OBS = 4, LIMIT = 500;
+  static constexpr bool CONT = false;
   double x, xd, th, thd;
   __device__ __forceinline__ void load(const double* g, long long N, long long n) {
     x = g[n]; xd = g[N + n]; th = g[2 * N + n]; thd = g[3 * N + n];
@@ -119,6 +124,7 @@ struct CartPole {
 // ---- MountainCar-v0 (gym/envs/classic_control/mountain_car.py) ------------------------------
 struct MountainCar {
   static constexpr int S = 2, OBS = 2, LIMIT = 200;
+  static constexpr bool CONT = false;
   double pos, vel;
   __device__ __forceinline__ void load(const double* g, long long N, long long n) { pos = g[n]; vel = g[N + n]; }
   __device__ __forceinline__ void store(double* g, long long N, long long n) const { g[n] = pos; g[N + n] = vel; }
@@ -149,6 +155,7 @@ struct MountainCar {
 // (`.astype(np.float32)`).  Trigonometry goes through the deterministic sin/cos shared with the CPU checker.
 struct Acrobot {
   static constexpr int S = 4, OBS = 6, LIMIT = 500;
+  static constexpr bool CONT = false;
   double s0, s1, s2, s3;
   __device__ __forceinline__ void load(const double* g, long long N, long long n) {
     s0 = g[n]; s1 = g[N + n]; s2 = g[2 * N + n]; s3 = g[3 * N + n];
@@ -222,9 +229,49 @@ struct Acrobot {
   }
 };
 
+// ---- MountainCarContinuous-v0 (gym/envs/classic_control/continuous_mountain_car.py) -----------------------------------
+// The env keeps its state as a float32 array after every step (np.array([position, velocity], dtype=np.float32)) and
+// computes in float64 in between (NumPy 1.24 scalar promotion: float32 scalar with a Python float -> float64), so the
+// fp64 state here always holds float32-representable values except right after reset (float64 uniform draw).
+struct MountainCarContinuous {
+  static constexpr int S = 2, OBS = 2, LIMIT = 999;
+  static constexpr bool CONT = true;
+  double pos, vel;
+  __device__ __forceinline__ void load(const double* g, long long N, long long n) { pos = g[n]; vel = g[N + n]; }
+  __device__ __forceinline__ void store(double* g, long long N, long long n) const { g[n] = pos; g[N + n] = vel; }
+  __device__ __forceinline__ void reset(Pcg64& rng) {
+    pos = rng.uniform(-0.6, -0.4 - (-0.6));
+    vel = 0.0;
+  }
+  __device__ __forceinline__ void raw_obs(float (&o)[2]) const { o[0] = (float)pos; o[1] = (float)vel; }
+  __device__ __forceinline__ double step(float u_in, bool clip_action, bool& terminated) {
+    const double min_position = -1.2, max_position = 0.6, max_speed = 0.07, goal_position = 0.45, goal_velocity = 0.0;
+    const double power = 0.0015;
+    float u = u_in;
+    if (clip_action) u = u < -1.0f ? -1.0f : (u > 1.0f ? 1.0f : u);      // ClipAction wrapper (action space [-1, 1])
+    const float f32 = u < -1.0f ? -1.0f : (u > 1.0f ? 1.0f : u);         // min(max(action[0], min_action), max_action)
+    double s3, c3;
+    aur_sincos(3 * pos, &s3, &c3);
+    double velocity = vel + ((double)f32 * power - 0.0025 * c3);
+    if (velocity > max_speed) velocity = max_speed;
+    if (velocity < -max_speed) velocity = -max_speed;
+    double position = pos + velocity;
+    if (position > max_position) position = max_position;
+    if (position < min_position) position = min_position;
+    if (position == min_position && velocity < 0) velocity = 0;
+    terminated = (position >= goal_position) && (velocity >= goal_velocity);
+    double reward = 0;
+    if (terminated) reward = 100.0;
+    reward -= ((double)u * (double)u) * 0.1;                             // math.pow(action[0], 2) * 0.1
+    pos = (double)(float)position; vel = (double)(float)velocity;
+    return reward;
+  }
+};
+
 // ---- Pendulum-v1 (gym/envs/classic_control/pendulum.py, g = 10) --------------------------
 struct Pendulum {
   static constexpr int S = 2, OBS = 3, LIMIT = 200;
+  static constexpr bool CONT = true;
   double th, thd;
   double s_th, c_th;   // sin/cos of the CURRENT theta (the obs needs them, the next step reuses sin)
   __device__ __forceinline__ void load(const double* g, long long N, long long n) {
@@ -328,7 +375,7 @@ __device__ __forceinline__ void policy_net_forward(const RolloutDev& a, const fl
 __device__ __forceinline__ void log_episode(const aur_episode_log& log, int t, long long local_env, int step, int env,
                                             float ret, int len) {
   if (log.first_finished) {
-    const unsigned long long key = ((unsigned long long)local_env << 41) | ((unsigned long long)(len & 511) << 32) |
+    const unsigned long long key = ((unsigned long long)local_env << 42) | ((unsigned long long)(len & 1023) << 32) |
                                    (unsigned long long)__float_as_uint(ret);
     atomicMin(log.first_finished + t, key);
   }

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
   }
   __syncthreads();
 
-  constexpr bool PEND = ENV::OBS == 3;
+  constexpr bool PEND = ENV::CONT;            // continuous env: Normal policy, optional wrapper stack
   constexpr int INP = ENV::OBS > POL_IN_PAD ? 8 : POL_IN_PAD;     // observation registers per env (Acrobot: 6 -> 8)
   static_assert(HID == 0 || INP == POL_IN_PAD, "observations wider than 4 run the runtime-width policy path");
   const long long N = a.N;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
   const long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 
   ENV env[E];
-  NormState nm[PEND ? E : 1];
+  NormStateT<ENV::OBS> nm[PEND ? E : 1];
   float obs[E][INP];
   float done_prev[E], ep_ret[E];
   int elapsed[E], ep_len[E];
@@ -144,13 +144,14 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
       const bool finished = terminated || truncated;
       if constexpr (PEND) {
         // wrappers see the stepped observation before SyncVectorEnv autoresets
-        float raw[3];
+        float raw[ENV::OBS];
         env[e].raw_obs(raw);
         if (a.wrappers) {
           nm[PEND ? e : 0].obs(raw, obs[e]);
           reward = nm[PEND ? e : 0].reward(reward, finished, a.gamma);
         } else {
-          obs[e][0] = raw[0]; obs[e][1] = raw[1]; obs[e][2] = raw[2]; obs[e][3] = 0.0f;
+#pragma unroll
+          for (int k = 0; k < POL_IN_PAD; ++k) obs[e][k] = k < ENV::OBS ? raw[k < ENV::OBS ? k : 0] : 0.0f;
         }
       } else {
         env[e].raw_obs(obs[e]);
@@ -166,10 +167,13 @@ __global__ void __launch_bounds__(256, 1) rollout_kernel(RolloutDev a) {
         rng.store(a.env.pcg, N, n);
         elapsed[e] = 0; ep_ret[e] = 0.0f; ep_len[e] = 0;
         if constexpr (PEND) {
-          float raw[3];
+          float raw[ENV::OBS];
           env[e].raw_obs(raw);
           if (a.wrappers) nm[PEND ? e : 0].obs(raw, obs[e]);
-          else { obs[e][0] = raw[0]; obs[e][1] = raw[1]; obs[e][2] = raw[2]; obs[e][3] = 0.0f; }
+          else {
+#pragma unroll
+            for (int k = 0; k < POL_IN_PAD; ++k) obs[e][k] = k < ENV::OBS ? raw[k < ENV::OBS ? k : 0] : 0.0f;
+          }
         } else {
           env[e].raw_obs(obs[e]);
         }
@@ -214,16 +218,16 @@ __global__ void env_reset_kernel(long long N, int wrappers, aur_env_state st, fl
   env.store(st.phys, N, n);
   st.elapsed[n] = 0; st.ep_return[n] = 0.0f; st.ep_length[n] = 0;
   float obs[ENV::OBS > POL_IN_PAD ? 8 : POL_IN_PAD];
-  if constexpr (ENV::OBS == 3) {
-    float raw[3];
+  if constexpr (ENV::CONT) {
+    float raw[ENV::OBS];
     env.raw_obs(raw);
     if (wrappers) {
-      NormState nm;
+      NormStateT<ENV::OBS> nm;
       nm.init();
       nm.obs(raw, obs);
       nm.store(st.norm, N, n);
     } else {
-      obs[0] = raw[0]; obs[1] = raw[1]; obs[2] = raw[2];
+      for (int k = 0; k < ENV::OBS; ++k) obs[k] = raw[k];
     }
   } else {
     env.raw_obs(obs);
@@ -435,6 +439,9 @@ extern "C" int aur_env_reset(int32_t env_kind, int64_t N, int32_t wrappers, cons
     env_reset_kernel<MountainCar><<<grid, 128, 0, s>>>((long long)N, 0, *st, obs_out, done_out);
   } else if (env_kind == AUR_ENV_ACROBOT) {
     env_reset_kernel<Acrobot><<<grid, 128, 0, s>>>((long long)N, 0, *st, obs_out, done_out);
+  } else if (env_kind == AUR_ENV_MOUNTAINCAR_CONT) {
+    if (wrappers && !st->norm) { set_error("aur_env_reset: wrappers need env.norm"); return AUR_ERR_ARG; }
+    env_reset_kernel<MountainCarContinuous><<<grid, 128, 0, s>>>((long long)N, wrappers, *st, obs_out, done_out);
   } else if (env_kind == AUR_ENV_PENDULUM) {
     if (wrappers && !st->norm) { set_error("aur_env_reset: wrappers need env.norm"); return AUR_ERR_ARG; }
     env_reset_kernel<Pendulum><<<grid, 128, 0, s>>>((long long)N, wrappers, *st, obs_out, done_out);
@@ -474,6 +481,9 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
     if (a.policy.continuous || a.policy.obs_dim != 4 || a.policy.act_dim != 2) { set_error("aur_rollout: CartPole needs obs 4, 2 discrete actions"); return AUR_ERR_ARG; }
   } else if (a.env_kind == AUR_ENV_MOUNTAINCAR) {
     if (a.policy.continuous || a.policy.obs_dim != 2 || a.policy.act_dim != 3) { set_error("aur_rollout: MountainCar needs obs 2, 3 discrete actions"); return AUR_ERR_ARG; }
+  } else if (a.env_kind == AUR_ENV_MOUNTAINCAR_CONT) {
+    if (!a.policy.continuous || a.policy.obs_dim != 2 || a.policy.act_dim != 1) { set_error("aur_rollout: MountainCarContinuous needs obs 2, 1 continuous action"); return AUR_ERR_ARG; }
+    if (a.wrappers && !a.env.norm) { set_error("aur_rollout: wrappers need env.norm"); return AUR_ERR_ARG; }
   } else if (a.env_kind == AUR_ENV_ACROBOT) {
     if (a.policy.continuous || a.policy.obs_dim != 6 || a.policy.act_dim != 3) { set_error("aur_rollout: Acrobot needs obs 6, 3 discrete actions"); return AUR_ERR_ARG; }
   } else if (pend) {
@@ -500,6 +510,7 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
     if (pend) AUR_LAUNCH_DYN(Pendulum);
     else if (a.env_kind == AUR_ENV_MOUNTAINCAR) AUR_LAUNCH_DYN(MountainCar);
     else if (a.env_kind == AUR_ENV_ACROBOT) AUR_LAUNCH_DYN(Acrobot);
+    else if (a.env_kind == AUR_ENV_MOUNTAINCAR_CONT) AUR_LAUNCH_DYN(MountainCarContinuous);
     else AUR_LAUNCH_DYN(CartPole);
 #undef AUR_LAUNCH_DYN
     AUR_LAUNCH_OK("rollout_kernel (runtime width)");
@@ -523,11 +534,12 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
       rollout_kernel<ENVT, 64, EE, true><<<(unsigned)grid, block, smem, s>>>(d);                       \
     }                                                                                                  \
   } while (0)
-  const bool mcar = a.env_kind == AUR_ENV_MOUNTAINCAR;
-  if (split_critic && rollout_impl() == 1) {
+  const bool mcar = a.env_kind == AUR_ENV_MOUNTAINCAR, mcc = a.env_kind == AUR_ENV_MOUNTAINCAR_CONT;
+  if (split_critic && rollout_impl() == 1 && !mcc) {
     if ((rc = launch_rollout_tc(d, a.env_kind, s))) return rc;     // actor hidden layer on tcgen05 (rollout_tc.cu)
   } else {
     if (pend) AUR_LAUNCH_ROLLOUT(Pendulum, 1);
+    else if (mcc) AUR_LAUNCH_ROLLOUT(MountainCarContinuous, 1);
     else if (mcar) AUR_LAUNCH_ROLLOUT(MountainCar, 1);
     else if (two) AUR_LAUNCH_ROLLOUT(CartPole, 2);
     else AUR_LAUNCH_ROLLOUT(CartPole, 1);

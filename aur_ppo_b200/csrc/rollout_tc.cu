@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(base + RO_BAR);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(base + RO_BAR + 32);
   const int tid = threadIdx.x, warp = tid >> 5;
-  constexpr bool PEND = ENV::OBS == 3;
+  constexpr bool PEND = ENV::CONT;
   const int A = a.act_dim, obs_dim = a.obs_dim;
 
   if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }

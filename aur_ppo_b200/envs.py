@@ -16,10 +16,12 @@ import torch
 from . import _lib
 from .kernels import _stream, _ptr
 
-CARTPOLE, PENDULUM, MOUNTAINCAR, ACROBOT = 0, 1, 2, 3
-ENV_IDS = {"CartPole-v1": CARTPOLE, "Pendulum-v1": PENDULUM, "MountainCar-v0": MOUNTAINCAR, "Acrobot-v1": ACROBOT}
-OBS_DIM = {CARTPOLE: 4, PENDULUM: 3, MOUNTAINCAR: 2, ACROBOT: 6}
-PHYS_DIM = {CARTPOLE: 4, PENDULUM: 2, MOUNTAINCAR: 2, ACROBOT: 4}
+CARTPOLE, PENDULUM, MOUNTAINCAR, ACROBOT, MOUNTAINCAR_CONT = 0, 1, 2, 3, 4
+ENV_IDS = {"CartPole-v1": CARTPOLE, "Pendulum-v1": PENDULUM, "MountainCar-v0": MOUNTAINCAR, "Acrobot-v1": ACROBOT,
+           "MountainCarContinuous-v0": MOUNTAINCAR_CONT}
+OBS_DIM = {CARTPOLE: 4, PENDULUM: 3, MOUNTAINCAR: 2, ACROBOT: 6, MOUNTAINCAR_CONT: 2}
+PHYS_DIM = {CARTPOLE: 4, PENDULUM: 2, MOUNTAINCAR: 2, ACROBOT: 4, MOUNTAINCAR_CONT: 2}
+CONTINUOUS = {PENDULUM, MOUNTAINCAR_CONT}
 
 
 def pcg64_seed_states(seeds: Sequence[int]) -> np.ndarray:
@@ -39,7 +41,7 @@ class DeviceVecEnv:
         if gym_id not in ENV_IDS:
             raise _lib.AurError(f"gym_id {gym_id!r} has no device kernel (compiled: {sorted(ENV_IDS)}); no CPU fallback")
         self.gym_id, self.kind, self.num_envs = gym_id, ENV_IDS[gym_id], int(num_envs)
-        self.wrappers = bool(wrappers) and self.kind == PENDULUM
+        self.wrappers = bool(wrappers) and self.kind in CONTINUOUS
         self.device = torch.device(device)
         self.env_id0 = int(env_id0)
         self.obs_dim = OBS_DIM[self.kind]
@@ -51,7 +53,7 @@ class DeviceVecEnv:
         self.elapsed = torch.zeros(n, dtype=torch.int32, device=dev)
         self.ep_return = torch.zeros(n, dtype=torch.float32, device=dev)
         self.ep_length = torch.zeros(n, dtype=torch.int32, device=dev)
-        self.norm = torch.zeros(11, n, dtype=torch.float64, device=dev) if self.wrappers else None
+        self.norm = torch.zeros(2 * OBS_DIM[self.kind] + 5, n, dtype=torch.float64, device=dev) if self.wrappers else None
         self.next_obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, device=dev)
         self.next_done = torch.zeros(n, dtype=torch.float32, device=dev)
         # full episode log: opt-in (tests / small runs); the training loop reads `first_finished`
@@ -81,8 +83,8 @@ class DeviceVecEnv:
         keys = self.first_finished.cpu().numpy().view(np.uint64)
         t = np.nonzero(keys != np.uint64(0xFFFFFFFFFFFFFFFF))[0]
         k = keys[t]
-        env = (k >> np.uint64(41)).astype(np.int64)
-        length = ((k >> np.uint64(32)) & np.uint64(511)).astype(np.int64)
+        env = (k >> np.uint64(42)).astype(np.int64)
+        length = ((k >> np.uint64(32)) & np.uint64(1023)).astype(np.int64)
         ret = (k & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32)
         return t, env, ret, length
 

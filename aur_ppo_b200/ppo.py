@@ -74,7 +74,8 @@ class FusedAdam(torch.optim.Optimizer):
 
 
 _SPACES = {"CartPole-v1": dict(obs=(4,), act_shape=(), n=2), "Pendulum-v1": dict(obs=(3,), act_shape=(1,), n=None),
-           "MountainCar-v0": dict(obs=(2,), act_shape=(), n=3), "Acrobot-v1": dict(obs=(6,), act_shape=(), n=3)}
+           "MountainCar-v0": dict(obs=(2,), act_shape=(), n=3), "Acrobot-v1": dict(obs=(6,), act_shape=(), n=3),
+           "MountainCarContinuous-v0": dict(obs=(2,), act_shape=(1,), n=None)}
 
 
 class ppo:

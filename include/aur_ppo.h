@@ -36,6 +36,7 @@ extern "C" {
 #define AUR_ENV_CARTPOLE 0 /* gym CartPole-v1 */
 #define AUR_ENV_PENDULUM 1 /* gym Pendulum-v1 */
 #define AUR_ENV_MOUNTAINCAR 2 /* gym MountainCar-v0 (discrete, 3 actions, obs 2) */
+#define AUR_ENV_MOUNTAINCAR_CONT 4 /* gym MountainCarContinuous-v0 (1 continuous action, obs 2, 999 steps) */
 #define AUR_ENV_ACROBOT 3     /* gym Acrobot-v1 (discrete, 3 actions, obs 6; runtime-width policy path) */
 
 int aur_abi_version(void);
@@ -113,7 +114,7 @@ typedef struct {
   int32_t* elapsed;   /* [N] TimeLimit step counter */
   float* ep_return;   /* [N] RecordEpisodeStatistics accumulator (fp32 as in gym) */
   int32_t* ep_length; /* [N] */
-  double* norm;       /* [11][N] or NULL: obs mean[3], var[3], count; return-rms mean, var, count; return acc */
+  double* norm;       /* [2 D + 5][N] or NULL (D = obs_dim; Pendulum: 11 rows): obs mean[D], var[D], count; return-rms mean, var, count; return acc */
 } aur_env_state;
 
 typedef struct {
@@ -130,7 +131,7 @@ typedef struct {
   uint32_t _pad;
   /* [T] or NULL, caller-initialised to all ones: per rollout step, the FIRST finished env in env
    * order -- what the reference logs (ppo.py:114-122 breaks after the first final_info item).
-   * Packed (local_env << 41) | (length << 32) | float_bits(return), merged with atomicMin. */
+   * Packed (local_env << 42) | (length << 32) | float_bits(return), merged with atomicMin (length < 1024). */
   unsigned long long* first_finished;
   double* totals;       /* [3] or NULL: += episodes, sum of returns, sum of lengths */
 } aur_episode_log;

@@ -38,7 +38,7 @@ static inline double pcg64_double(pcg64_t* g) { return (double)(pcg64_next(g) >>
 static inline double pcg64_uniform(pcg64_t* g, double low, double range) { return low + range * pcg64_double(g); }
 
 static inline int obs_dim_of(int kind) { return kind == 0 ? 4 : (kind == 1 ? 3 : (kind == 3 ? 6 : 2)); }
-static inline int time_limit_of(int kind) { return (kind == 0 || kind == 3) ? 500 : 200; }
+static inline int time_limit_of(int kind) { return (kind == 0 || kind == 3) ? 500 : (kind == 4 ? 999 : 200); }
 
 static inline void trig(int mode, double x, double* s, double* c) {
   if (mode == 0) { *s = sin(x); *c = cos(x); }
@@ -123,7 +123,7 @@ static void acrobot_raw_obs(int mode, const double* st, double* raw) {
 
 /* ---- vector env ---- */
 typedef struct {
-  int kind;        /* 0 CartPole-v1, 1 Pendulum-v1, 2 MountainCar-v0, 3 Acrobot-v1 */
+  int kind;        /* 0 CartPole-v1, 1 Pendulum-v1, 2 MountainCar-v0, 3 Acrobot-v1, 4 MountainCarContinuous-v0 */
   int wrappers;    /* 1 = the reference's continuous wrapper stack (ppo.py:92-97) */
   int trig_mode;
   int64_t n;
@@ -203,7 +203,7 @@ static void env_reset(orc_vec_t* v, int64_t i, float* obs_out) {
     acrobot_raw_obs(v->trig_mode, st, raw);
     emit_obs(v, i, raw, 6, obs_out);
   } else {
-    /* MountainCar-v0 (mountain_car.py reset): state = [uniform(-0.6, -0.4), 0] */
+    /* MountainCar-v0 / MountainCarContinuous-v0 (reset): state = [uniform(-0.6, -0.4), 0] */
     st[0] = pcg64_uniform(&v->rng[i], -0.6, -0.4 - (-0.6));
     st[1] = 0.0;
     double raw[2] = {(double)(float)st[0], (double)(float)st[1]};
@@ -240,6 +240,29 @@ void orc_vec_step(void* h, const void* actions, float* obs_out, double* rew_out,
       reward = terminated ? 0.0 : -1.0;
       acrobot_raw_obs(v->trig_mode, st, raw);
       d = 6;
+    } else if (v->kind == 4) {
+      /* MountainCarContinuous-v0 (continuous_mountain_car.py step): float32 state array, float64 arithmetic */
+      const double min_position = -1.2, max_position = 0.6, max_speed = 0.07, goal_position = 0.45, goal_velocity = 0.0;
+      const double power = 0.0015;
+      float a32 = ((const float*)actions)[i];
+      if (v->wrappers) a32 = a32 < -1.0f ? -1.0f : (a32 > 1.0f ? 1.0f : a32);     /* ClipAction: Box(-1, 1) */
+      float f32 = a32 < -1.0f ? -1.0f : (a32 > 1.0f ? 1.0f : a32);                /* min(max(action[0], -1), 1) */
+      double position = st[0], velocity = st[1];
+      double s3, c3; trig(v->trig_mode, 3 * position, &s3, &c3);
+      velocity = velocity + ((double)f32 * power - 0.0025 * c3);
+      if (velocity > max_speed) velocity = max_speed;
+      if (velocity < -max_speed) velocity = -max_speed;
+      position = position + velocity;
+      if (position > max_position) position = max_position;
+      if (position < min_position) position = min_position;
+      if (position == min_position && velocity < 0) velocity = 0;
+      terminated = (position >= goal_position) && (velocity >= goal_velocity);
+      reward = 0;
+      if (terminated) reward = 100.0;
+      reward -= ((double)a32 * (double)a32) * 0.1;                                /* math.pow(action[0], 2) * 0.1 */
+      st[0] = (double)(float)position; st[1] = (double)(float)velocity;           /* np.array([...], dtype=np.float32) */
+      raw[0] = st[0]; raw[1] = st[1];
+      d = 2;
     } else if (v->kind == 0) {
       const double gravity = 9.8, masscart = 1.0, masspole = 0.1, length = 0.5, force_mag = 10.0, tau = 0.02;
       const double total_mass = masspole + masscart, polemass_length = masspole * length;
@@ -329,12 +352,14 @@ void orc_vec_get_phys(void* h, double* out) {
   orc_vec_t* v = (orc_vec_t*)h; int S = (v->kind == 0 || v->kind == 3) ? 4 : 2;
   for (int64_t i = 0; i < v->n; ++i) for (int k = 0; k < S; ++k) out[i * S + k] = v->phys[i * 4 + k];
 }
-/* wrapper statistics, [n][11]: o_mean[3], o_var[3], o_count, r_mean, r_var, r_count, r_ret */
+/* wrapper statistics, [n][2 D + 5] (D = obs dim; Pendulum 11): o_mean[D], o_var[D], o_count, r_mean, r_var, r_count, r_ret */
 void orc_vec_get_norm(void* h, double* out) {
   orc_vec_t* v = (orc_vec_t*)h;
+  int D = obs_dim_of(v->kind);
   for (int64_t i = 0; i < v->n; ++i) {
-    double* o = &out[i * 11];
-    for (int k = 0; k < 3; ++k) { o[k] = v->o_mean[i * 3 + k]; o[3 + k] = v->o_var[i * 3 + k]; }
-    o[6] = v->o_count[i]; o[7] = v->r_mean[i]; o[8] = v->r_var[i]; o[9] = v->r_count[i]; o[10] = v->r_ret[i];
+    double* o = &out[i * (2 * D + 5)];
+    for (int k = 0; k < D; ++k) { o[k] = v->o_mean[i * 3 + k]; o[D + k] = v->o_var[i * 3 + k]; }
+    o[2 * D] = v->o_count[i]; o[2 * D + 1] = v->r_mean[i]; o[2 * D + 2] = v->r_var[i]; o[2 * D + 3] = v->r_count[i];
+    o[2 * D + 4] = v->r_ret[i];
   }
 }

@@ -16,9 +16,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-CARTPOLE, PENDULUM, MOUNTAINCAR, ACROBOT = 0, 1, 2, 3
-OBS_DIM = {CARTPOLE: 4, PENDULUM: 3, MOUNTAINCAR: 2, ACROBOT: 6}
-PHYS_DIM = {CARTPOLE: 4, PENDULUM: 2, MOUNTAINCAR: 2, ACROBOT: 4}
+CARTPOLE, PENDULUM, MOUNTAINCAR, ACROBOT, MOUNTAINCAR_CONT = 0, 1, 2, 3, 4
+OBS_DIM = {CARTPOLE: 4, PENDULUM: 3, MOUNTAINCAR: 2, ACROBOT: 6, MOUNTAINCAR_CONT: 2}
+PHYS_DIM = {CARTPOLE: 4, PENDULUM: 2, MOUNTAINCAR: 2, ACROBOT: 4, MOUNTAINCAR_CONT: 2}
+CONTINUOUS = (PENDULUM, MOUNTAINCAR_CONT)
 TRIG_LIBM, TRIG_DET = 0, 1
 
 
@@ -102,7 +103,7 @@ class CVecEnv:
         return self._obs.copy(), {}
 
     def step(self, actions):
-        if self.kind != PENDULUM:
+        if self.kind not in CONTINUOUS:
             a = np.ascontiguousarray(actions, dtype=np.int32)
         else:
             a = np.ascontiguousarray(np.asarray(actions, dtype=np.float32).reshape(self.num_envs))
@@ -121,6 +122,6 @@ class CVecEnv:
         return out[:, :PHYS_DIM[self.kind]]
 
     def norm_stats(self) -> np.ndarray:
-        out = np.zeros((self.num_envs, 11), np.float64)
+        out = np.zeros((self.num_envs, 2 * self.obs_dim + 5), np.float64)
         lib().orc_vec_get_norm(self._h, out.ctypes.data)
         return out

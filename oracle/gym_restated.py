@@ -252,6 +252,57 @@ class AcrobotEnv:
         return x
 
 
+class Continuous_MountainCarEnv:
+    """gym MountainCarContinuous-v0 (continuous_mountain_car.py): the state is re-created as a float32 array every step,
+    the arithmetic in between is float64 (NumPy 1.24: a float32 scalar combined with a Python float or int gives float64;
+    written out with float() because this container has NumPy 2)."""
+
+    def __init__(self, sincos: Callable[[float], Tuple[float, float]] = _libm_sincos):
+        self.min_action = -1.0
+        self.max_action = 1.0
+        self.min_position = -1.2
+        self.max_position = 0.6
+        self.max_speed = 0.07
+        self.goal_position = 0.45
+        self.goal_velocity = 0
+        self.power = 0.0015
+        self.state = None
+        self.np_random = None
+        self._sincos = sincos
+        self.obs_dim = 2
+
+    def reset(self, seed: Optional[int] = None):
+        if seed is not None or self.np_random is None:
+            self.np_random = np_random(seed)
+        self.state = np.array([self.np_random.uniform(low=-0.6, high=-0.4), 0])
+        return np.array(self.state, dtype=np.float32), {}
+
+    def step(self, action):
+        position = float(self.state[0])
+        velocity = float(self.state[1])
+        a0 = np.float32(np.asarray(action, dtype=np.float32).reshape(-1)[0])
+        force = min(max(a0, self.min_action), self.max_action)
+        velocity += float(force) * self.power - 0.0025 * self._sincos(3 * position)[1]
+        if velocity > self.max_speed:
+            velocity = self.max_speed
+        if velocity < -self.max_speed:
+            velocity = -self.max_speed
+        position += velocity
+        if position > self.max_position:
+            position = self.max_position
+        if position < self.min_position:
+            position = self.min_position
+        if position == self.min_position and velocity < 0:
+            velocity = 0
+        terminated = bool(position >= self.goal_position and velocity >= self.goal_velocity)
+        reward = 0
+        if terminated:
+            reward = 100.0
+        reward -= math.pow(float(a0), 2) * 0.1
+        self.state = np.array([position, velocity], dtype=np.float32)
+        return self.state, reward, terminated, False, {}
+
+
 def angle_normalize(x: float) -> float:
     # ((x + pi) % (2 pi)) - pi ; Python float % == NumPy float64 % (fmod + sign fix)
     return ((x + math.pi) % (2 * math.pi)) - math.pi
@@ -454,11 +505,15 @@ def make_env(gym_id: str, continuous: bool, sincos=_libm_sincos):
     elif gym_id == "Acrobot-v1":
         env = TimeLimit(AcrobotEnv(sincos), 500)
         obs_shape = (6,)
+    elif gym_id == "MountainCarContinuous-v0":
+        env = TimeLimit(Continuous_MountainCarEnv(sincos), 999)
+        obs_shape = (2,)
     else:
         raise ValueError(f"unsupported gym_id {gym_id!r}")
     env = RecordEpisodeStatistics(env)
     if continuous:
-        env = ClipAction(env, -2.0, 2.0)
+        bound = 1.0 if gym_id == "MountainCarContinuous-v0" else 2.0     # env.action_space.low / high
+        env = ClipAction(env, -bound, bound)
         env = NormalizeObservation(env, obs_shape)
         env = ClipObservation(env)
         env = NormalizeReward(env)

@@ -37,7 +37,9 @@ def test_pcg64_stream_matches_numpy():
 
 @pytest.mark.parametrize("kind,gid,cont", [(E.CARTPOLE, "CartPole-v1", False), (E.PENDULUM, "Pendulum-v1", True),
                                            (E.PENDULUM, "Pendulum-v1", False), (E.MOUNTAINCAR, "MountainCar-v0", False),
-                                           (E.ACROBOT, "Acrobot-v1", False)])
+                                           (E.ACROBOT, "Acrobot-v1", False),
+                                           (E.MOUNTAINCAR_CONT, "MountainCarContinuous-v0", True),
+                                           (E.MOUNTAINCAR_CONT, "MountainCarContinuous-v0", False)])
 def test_c_checker_equals_python_restatement(kind, gid, cont):
     N = 6
     pv = G.SyncVectorEnv([G.make_env(gid, cont) for _ in range(N)], E.OBS_DIM[kind])
@@ -47,7 +49,7 @@ def test_c_checker_equals_python_restatement(kind, gid, cont):
     np.testing.assert_array_equal(o1, o2)
     rng = np.random.default_rng(5)
     episodes = 0
-    for t in range(700):
+    for t in range(1100 if kind == E.MOUNTAINCAR_CONT else 700):
         a = (rng.integers(0, 2, N) if kind == E.CARTPOLE else rng.integers(0, 3, N) if kind in (E.MOUNTAINCAR, E.ACROBOT)
              else rng.normal(0, 1.5, (N, 1)).astype(np.float32))
         r1, r2 = pv.step(a), cv.step(a)
@@ -164,3 +166,34 @@ def test_acrobot_restatement_behaviour():
         obs, r, term, trunc, info = env.step(1)
         assert not term
     assert trunc and info["episode"]["l"] == 500 and info["episode"]["r"] == -500.0
+
+
+def test_mountaincar_continuous_restatement_behaviour():
+    """MountainCarContinuous-v0: reward -0.1 a^2 per step (+100 at the flag), the state is float32 after every step, full
+    throttle from the valley floor does not reach the flag but rocking with the velocity does, TimeLimit 999."""
+    env = G.make_env("MountainCarContinuous-v0", False)
+    env.reset(seed=0)
+    inner = env.env.env
+    for _ in range(999):
+        obs, r, term, trunc, info = env.step(np.array([1.0], np.float32))
+        assert inner.state.dtype == np.float32 and not term
+        assert abs(r + 0.1) < 1e-15
+    assert trunc and info["episode"]["l"] == 999
+    env.reset(seed=1)
+    steps, term = 0, False
+    while not term and steps < 999:
+        a = 1.0 if inner.state[1] >= 0 else -1.0
+        obs, r, term, trunc, _ = env.step(np.array([a], np.float32))
+        steps += 1
+    assert term and steps < 300 and abs(r - 99.9) < 1e-12, (steps, r)
+    # out-of-range actions: the env clips the force but charges the raw action (no ClipAction without the wrapper stack)
+    env.reset(seed=2)
+    _, r, _, _, _ = env.step(np.array([3.0], np.float32))
+    assert abs(r + 0.9) < 1e-12
+    wenv = G.make_env("MountainCarContinuous-v0", True)
+    wenv.reset(seed=2)
+    w_inner = wenv
+    while hasattr(w_inner, "env"):
+        w_inner = w_inner.env
+    _, r_w, _, _, _ = wenv.step(np.array([3.0], np.float32))
+    np.testing.assert_allclose(w_inner.state, inner.state)           # same force either way

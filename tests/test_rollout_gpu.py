@@ -477,3 +477,52 @@ def test_acrobot_replay_is_bit_exact(N, T, hidden, rollout_impl):
     np.testing.assert_allclose(buf.log_probs.cpu().numpy().reshape(-1), lp.numpy(), **TOL)
     np.testing.assert_allclose(buf.values.cpu().numpy().reshape(-1), v.numpy().reshape(-1), **TOL)
     np.testing.assert_allclose(buf.next_value.cpu().numpy(), nv.numpy(), **TOL)
+
+
+@pytest.mark.parametrize("wrappers,hidden", [(True, 64), (False, 64), (True, 32)])
+def test_mountaincar_continuous_replay_is_bit_exact(wrappers, hidden, rollout_impl):
+    """MountainCarContinuous-v0 ((f) rank 4): float32 state / float64 arithmetic, ClipAction(-1, 1), the continuous wrapper
+    stack with two observation dims and the 999-step TimeLimit (10-bit episode lengths in the log), bit for bit."""
+    N, T = 40, 1100
+    pol, named = random_policy(2, 1, hidden, 2, True, seed=14)
+    desc = kernels.policy_desc(2, 1, hidden, 2, True)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    seeds = list(range(50, 50 + N))
+    rng = np.random.default_rng(3)
+    # rock with the velocity (plus noise, some of it outside [-1, 1]) so that some episodes reach the flag
+    actions = np.zeros((T, N, 1), np.float32)
+    cv = E.CVecEnv(E.MOUNTAINCAR_CONT, N, wrappers=wrappers, trig=E.TRIG_DET)
+    cv.reset(seeds)
+    for t in range(T):
+        vel = cv.phys()[:, 1]
+        a = np.where(vel >= 0, 1.0, -1.0) * (np.arange(N) % 2) + rng.normal(0, 0.8, N)
+        actions[t, :, 0] = a.astype(np.float32)
+        cv.step(actions[t])
+    cv, obs0, obs, rew, done, last_obs, last_done, episodes = _oracle_replay(E.MOUNTAINCAR_CONT, N, wrappers, seeds, actions, T)
+    assert done.any() and any(e[3] == 999 for e in episodes)
+    env = denv.DeviceVecEnv("MountainCarContinuous-v0", N, wrappers=wrappers, log_capacity=N * 64)
+    o, _ = env.reset(seeds)
+    assert np.array_equal(o.cpu().numpy(), obs0)
+    buf = kernels.RolloutBuffers(T, N, 2, (1,), "cuda")
+    kernels.rollout(env, desc, flat, buf, seed=1, step0=0, actions_in=torch.from_numpy(actions).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.states.cpu().numpy(), obs)
+    assert np.array_equal(buf.rewards.cpu().numpy(), rew)
+    assert np.array_equal(buf.terminals.cpu().numpy(), done)
+    assert np.array_equal(env.next_obs.cpu().numpy(), last_obs)
+    assert np.array_equal(env.phys.cpu().numpy().T, cv.phys())
+    if wrappers:
+        assert np.array_equal(env.norm.cpu().numpy().T, cv.norm_stats())
+    got = env.drain_episodes()
+    want = sorted(episodes, key=lambda r: (r[0], r[1]))
+    assert [(g[0], g[1], g[3]) for g in got] == [(e[0], e[1], e[3]) for e in want]
+    np.testing.assert_array_equal([g[2] for g in got], [e[2] for e in want])
+    ft, fenv, fret, flen = env.first_finished_episodes()
+    first = {}
+    for (t, i, r, l) in want:
+        first.setdefault(t, (i, r, l))
+    assert [(int(e), float(r), int(l)) for e, r, l in zip(fenv, fret, flen)] == [first[t] for t in sorted(first)]
+    with torch.no_grad():
+        _, lp, _, v = pol.evaluate(torch.from_numpy(obs.reshape(-1, 2)), torch.from_numpy(actions.reshape(-1, 1)))
+    np.testing.assert_allclose(buf.log_probs.cpu().numpy().reshape(-1), lp.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(buf.values.cpu().numpy().reshape(-1), v.numpy().reshape(-1), rtol=2e-5, atol=5e-6)

@@ -115,3 +115,17 @@ def test_acrobot_runs_through_the_drop_in_api():
     assert len(rets) > 20 and np.isfinite(list(agent.last_stats.values())).all()
     k = max(5, len(rets) // 5)
     assert np.mean(lens[-k:]) < 0.6 * np.mean(lens[:k]), (np.mean(lens[:k]), np.mean(lens[-k:]))
+
+
+def test_mountaincar_continuous_runs_through_the_drop_in_api():
+    """--gym_id MountainCarContinuous-v0 --continuous True: wrapper stack with two observation dims, Normal policy, packed
+    records with obs 2 / one action column; statistics stay finite and episodes are logged (999-step limit)."""
+    from aur_ppo_b200.ppo import ppo
+    torch.manual_seed(1)
+    p = _params(gym_id="MountainCarContinuous-v0", continuous=True, num_envs=64, num_steps=256, num_minibatches=8,
+                num_update_epochs=4, total_timesteps=64 * 256 * 8, learning_rate=3e-4, entropy_coeff=0.0)
+    agent = ppo(p)
+    assert agent.buffer.actions.shape == (256, 64, 1) and agent.buffer.states.shape == (256, 64, 2)
+    rets, lens, xs = agent.train()
+    assert len(rets) > 0 and all(0 < l <= 999 for l in lens)
+    assert np.isfinite(list(agent.last_stats.values())).all()
