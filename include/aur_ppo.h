@@ -83,10 +83,12 @@ int aur_gae_kernel_kind(int32_t T, int64_t N, const float* rewards, const float*
  *   actor_logstd[act]                       (continuous only)
  * every W row-major [out,in] exactly as torch.nn.Linear.weight. */
 typedef struct {
-  int32_t obs_dim;     /* 4 CartPole, 3 Pendulum (<= 4 compiled) */
-  int32_t act_dim;     /* number of discrete actions, or action dimensions if continuous */
-  int32_t hidden_dim;  /* 64 compiled */
-  int32_t num_layers;  /* number of hidden layers (the reference's num_layers), >= 1 */
+  int32_t obs_dim;     /* 1..8 (4 CartPole, 3 Pendulum, 6 Acrobot); widths <= 4 with 64 hidden units run the specialised kernels */
+  int32_t act_dim;     /* number of discrete actions, or action dimensions if continuous; 1..8 */
+  int32_t hidden_dim;  /* multiples of 4 in 4..256; 64 (the reference default) runs the register / tcgen05 kernels,
+                          other widths the runtime-width forward and the shape-generic update kernel */
+  int32_t num_layers;  /* number of hidden layers (the reference's num_layers), 1..16; the update keeps all layers of a
+                          sample tile in shared memory, which bounds hidden_dim * num_layers (AUR_ERR_UNSUPPORTED beyond) */
   int32_t continuous;  /* 0 Categorical, 1 diagonal Normal with state-independent std */
 } aur_policy_desc;
 
@@ -224,7 +226,7 @@ int aur_dp_free(void* area);
 int aur_dp_status(const void* area, void* stream);   /* 0 ok, 1 = a kernel timed out waiting for a peer */
 
 typedef struct {
-  aur_policy_desc policy;    /* num_layers == 2 compiled */
+  aur_policy_desc policy;
   int32_t norm_adv;          /* ppo.py:238 */
   int32_t clip_vloss;        /* ppo.py:250; 0 reproduces the reference's b_values quirk (ppo.py:261) */
   int32_t _pad;
@@ -282,9 +284,11 @@ int aur_ppo_adv_moments_dp(int64_t m, const int32_t* idx, int64_t idx_offset, co
 
 int aur_ppo_update_grad(const aur_update_args* args, void* stream);
 
-/* Kernel behind aur_ppo_update_grad: 1 = tcgen05 (bf16 two-term split operands, fp32 TMEM accumulators; the
- * default), 0 = SIMT fp32 (independent implementation kept as a cross-check).  Both are CUDA; there is no
- * CPU path.  The environment variable AUR_UPDATE_IMPL=simt|tc sets the initial choice. */
+/* Kernel behind aur_ppo_update_grad for the 64 x 2 shape (widths <= 4): 1 = tcgen05 (bf16 two-term split operands,
+ * fp32 TMEM accumulators; the default), 2 = the same with four threads per sample, 0 = SIMT fp32 (independent
+ * implementation kept as a cross-check), 3 = the shape-generic SIMT kernel (update_generic.cu).  Every other
+ * shape always runs kernel 3.  All are CUDA; there is no CPU path.  AUR_UPDATE_IMPL=simt|tc|tc4|generic sets the
+ * initial choice. */
 int aur_ppo_update_set_impl(int impl);
 int aur_ppo_update_get_impl(void);
 
