@@ -440,10 +440,15 @@ __global__ void grad_reduce_kernel(const float* __restrict__ partials, int ncta,
                                    unsigned int* __restrict__ ticket) {
   const int64_t nA = net_param_count(obs_dim, hidden, nl, act_dim), nC = net_param_count(obs_dim, hidden, nl, 1);
   const int64_t P = nA + nC + (continuous ? act_dim : 0);
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P + AUR_NUM_STATS) {
+  // four lanes per output: lane q sums its quarter of the CTA partials in CTA order (fp64), the quarters are combined as
+  // (q0 + q1) + (q2 + q3) - a fixed order, so the result is bit-reproducible and the same on every rank
+  const int64_t tg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = tg >> 2;
+  const int q = (int)(tg & 3);
+  const bool live = i < P + AUR_NUM_STATS;
+  double s = 0.0;
+  if (live) {
     int net; int64_t off;
-    float v = 0.0f;
     bool zero = false;
     if (i < nA) { net = 0; off = i; }
     else if (i < nA + nC) { net = 1; off = i - nA; }
@@ -456,10 +461,23 @@ __global__ void grad_reduce_kernel(const float* __restrict__ partials, int ncta,
     }
     if (!zero) {
       const float* p = partials + (size_t)net * ncta * pstride + off;
-      double s = 0.0;
-      for (int c = 0; c < ncta; ++c) s += (double)p[(size_t)c * pstride];
-      v = (float)s;
+      const int chunk = (ncta + 3) >> 2;
+      int c = q * chunk;
+      const int c1 = min(ncta, c + chunk);
+      for (; c + 8 <= c1; c += 8) {                     // 8 loads in flight
+        float v8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v8[k] = __ldcg(p + (size_t)(c + k) * pstride);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += (double)v8[k];
+      }
+      for (; c < c1; ++c) s += (double)__ldcg(p + (size_t)c * pstride);
     }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);              // q0 + q1 | q2 + q3 (IEEE addition is commutative: both lanes agree)
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  if (live && q == 0) {
+    const float v = (float)s;
     grads_out[i] = v;
     if (dp.world > 1) {                                  // push this rank's sums into every rank's exchange area
       const size_t slot_off = DP_OFF_GRAD + ((size_t)(dp.seq & 1u) * DP_MAX + dp.rank) * dp_grad_stride(P) * sizeof(float);
@@ -728,7 +746,7 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
   const int64_t P = policy_param_count(u.policy);
   const int total = (int)(P + AUR_NUM_STATS);
   unsigned int* ticket2 = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(u.workspace + ws_partials_floats()) + 2 * MOM_CTAS) + 1;
-  grad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(partials, gx, u.policy.obs_dim, u.policy.act_dim, u.policy.continuous,
+  grad_reduce_kernel<<<(4 * total + 255) / 256, 256, 0, s>>>(partials, gx, u.policy.obs_dim, u.policy.act_dim, u.policy.continuous,
                                                         u.policy.hidden_dim, u.policy.num_layers, pstride, u.grads_out, d.dp,
                                                         ticket2);
   AUR_LAUNCH_OK("grad_reduce_kernel");
