@@ -78,6 +78,15 @@ class EquivHeadArgs(ctypes.Structure):
                 ("stats", c_void_p), ("value_out", c_void_p), ("logp_out", c_void_p)]
 
 
+class PlainHeadArgs(ctypes.Structure):
+    _fields_ = [("B", c_int32), ("clip_vloss", c_int32), ("m_total", c_int64), ("a_out", c_void_p), ("a_bias", c_void_p),
+                ("actor_logstd", c_void_p), ("c_pre", c_void_p), ("c_bias1", c_void_p), ("c_w2", c_void_p), ("c_b2", c_void_p),
+                ("action", c_void_p), ("oldlp", c_void_p), ("adv", c_void_p), ("ret", c_void_p), ("vold", c_void_p),
+                ("adv_moments", c_void_p), ("clip_coeff", ctypes.c_float), ("entropy_coeff", ctypes.c_float),
+                ("value_coeff", ctypes.c_float), ("_pad", ctypes.c_float), ("d_a_out", c_void_p), ("d_c_h", c_void_p),
+                ("d_head", c_void_p), ("stats", c_void_p), ("value_out", c_void_p), ("logp_out", c_void_p)]
+
+
 class AurError(RuntimeError):
     pass
 
@@ -198,6 +207,11 @@ def lib() -> ctypes.CDLL:
     L.aur_equiv_head_eval.restype = c_int
     L.aur_equiv_head_eval.argtypes = [c_int32] + [c_void_p] * 7 + [c_uint64, c_uint64, ctypes.POINTER(ctypes.c_float)] + \
         [c_void_p] * 8
+    L.aur_plain_head_eval.restype = c_int
+    L.aur_plain_head_eval.argtypes = [c_int32] + [c_void_p] * 8 + [c_uint64, c_uint64, ctypes.POINTER(ctypes.c_float)] + \
+        [c_void_p] * 8
+    L.aur_plain_head_loss.restype = c_int
+    L.aur_plain_head_loss.argtypes = [ctypes.POINTER(PlainHeadArgs), c_void_p]
     L.aur_sumsq_f32.restype = c_int
     L.aur_sumsq_f32.argtypes = [c_int64, c_void_p, c_void_p, c_void_p]
     L.aur_adam_flat.restype = c_int

@@ -537,6 +537,9 @@ struct HeadEvalDev {
   unsigned long long seed, stream_id;
   float lo[5], hi[5];      // action ranges in the order p, dx, dy, dz, dtheta
   float *unscaled_out, *scaled_out, *logp_out, *ent_out, *value_out, *mean_out, *logstd_out;
+  // plain CNN heads (src/nets/base_cnns.py:57-84): a_out cols 0..4 = mean_linear output, log_std = actor_logstd parameter,
+  // critic = Linear(128,128)-ReLU-Linear(128,1) on c_pre [B,128] (no group pooling)
+  const float* plain_logstd;   // [5] or NULL (equivariant heads)
 };
 __global__ void __launch_bounds__(256) head_eval_kernel(HeadEvalDev a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -548,8 +551,12 @@ __global__ void __launch_bounds__(256) head_eval_kernel(HeadEvalDev a) {
       for (int f = 0; f < 4; ++f) {
         const int fld = lane + 32 * f;
         float best = 0.0f;
+        if (a.plain_logstd) {
+          best = fmaxf(a.c_pre[(size_t)b * 128 + fld] + a.c_bias1[fld], 0.0f);
+        } else {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) best = fmaxf(best, fmaxf(a.c_pre[(size_t)b * 512 + fld * 4 + r] + a.c_bias1[fld * 4 + r], 0.0f));
+          for (int r = 0; r < 4; ++r) best = fmaxf(best, fmaxf(a.c_pre[(size_t)b * 512 + fld * 4 + r] + a.c_bias1[fld * 4 + r], 0.0f));
+        }
         vpart = fmaf(best, a.c_w2[fld], vpart);
       }
       const float value = warp_sum(vpart) + a.c_b2[0];
@@ -558,8 +565,9 @@ __global__ void __launch_bounds__(256) head_eval_kernel(HeadEvalDev a) {
     if (a.a_out && lane == 0) {
       float o10[10];
 #pragma unroll
-      for (int k = 0; k < 10; ++k) o10[k] = a.a_out[(size_t)b * 16 + k] + a.a_bias[k];
-      const int mean_src[5] = {2, 0, 1, 3, 4};
+      for (int k = 0; k < 10; ++k) o10[k] = a.a_out[(size_t)b * 16 + k] + (a.plain_logstd && k >= 5 ? 0.0f : a.a_bias[k]);
+      const int mean_src_e[5] = {2, 0, 1, 3, 4}, mean_src_p[5] = {0, 1, 2, 3, 4};
+      const int* mean_src = a.plain_logstd ? mean_src_p : mean_src_e;
       const float LOG_SQRT_2PI = 0.91893853320467267f;
       float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (!a.action_in) {
@@ -577,7 +585,7 @@ __global__ void __launch_bounds__(256) head_eval_kernel(HeadEvalDev a) {
 #pragma unroll
       for (int d = 0; d < 5; ++d) {
         const float mu = o10[mean_src[d]];
-        const float ls = fminf(fmaxf(o10[5 + d], -20.0f), 2.0f);
+        const float ls = a.plain_logstd ? a.plain_logstd[d] : fminf(fmaxf(o10[5 + d], -20.0f), 2.0f);
         const float sd = expf(ls), var = sd * sd;
         const float x = a.action_in ? a.action_in[(size_t)b * 5 + d] : __fadd_rn(mu, __fmul_rn(sd, z[d]));
         const float diff = x - mu, lsc = logf(sd);
@@ -593,6 +601,121 @@ __global__ void __launch_bounds__(256) head_eval_kernel(HeadEvalDev a) {
       a.logp_out[b] = logp;
       a.ent_out[b] = ent;
     }
+  }
+}
+
+// ---- plain CNN heads + loss (robot_actor_critic, equivariant = False): base_actor.mean_linear + actor_logstd,
+// base_critic.critic = Linear(128,128)-ReLU-Linear(128,1) (src/nets/base_cnns.py:57-84, src/models/robot_actor_critic.py:44-51),
+// same PPO loss seeds as head_loss_kernel (src/robot_ppo.py:345-398).  One warp per sample.
+struct PlainHeadDev {
+  int B;
+  const float* a_out;      // [B,16] mean_linear output before bias (cols 0..4 used)
+  const float* a_bias;     // [5]
+  const float* logstd;     // [5] actor_logstd
+  const float* c_pre;      // [B,128] critic.0 output before bias
+  const float* c_bias1;    // [128]
+  const float* c_w2;       // [128]
+  const float* c_b2;       // [1]
+  const float *action, *oldlp, *adv, *ret, *vold;
+  const double* moments;
+  float clip, clip_lo, clip_hi, ent_c, vf_c, inv_m;
+  int clip_vloss;
+  __nv_bfloat16* d_a_out;  // [B,16]
+  __nv_bfloat16* d_c_h;    // [B,128]
+  float* d_head;           // [5 + 5 + 128 + 1 + 128]: d a_bias | d logstd | d c_w2 | d c_b2 | d c_bias1
+  float* stats;
+  float* value_out;
+  float* logp_out;
+};
+__global__ void __launch_bounds__(256) plain_head_loss_kernel(PlainHeadDev a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float adv_mean = 0.0f, adv_den = 1.0f;
+  if (a.moments) {
+    const double n = a.moments[2], s = a.moments[0], ss = a.moments[1];
+    const double mean = s / n;
+    double var = (ss - s * mean) / (n - 1.0);
+    if (var < 0.0) var = 0.0;
+    adv_mean = (float)mean; adv_den = (float)sqrt(var) + 1e-8f;
+  }
+  float st[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float dmu_acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, dls_acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float db2 = 0.0f, dw2[4] = {0.f, 0.f, 0.f, 0.f}, db1[4] = {0.f, 0.f, 0.f, 0.f};
+  const float LOG_SQRT_2PI = 0.91893853320467267f;
+  for (int b = warp; b < a.B; b += nwarps) {
+    float h[4], vpart = 0.0f;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int c = lane + 32 * f;
+      h[f] = fmaxf(a.c_pre[(size_t)b * 128 + c] + a.c_bias1[c], 0.0f);
+      vpart = fmaf(h[f], a.c_w2[c], vpart);
+    }
+    const float value = warp_sum(vpart) + a.c_b2[0];
+    float logp = 0.0f, ent = 0.0f, dmean[5], dls[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      const float mu = a.a_out[(size_t)b * 16 + d] + a.a_bias[d];
+      const float sd = expf(a.logstd[d]), var = sd * sd, lsc = logf(sd);
+      const float diff = a.action[(size_t)b * 5 + d] - mu;
+      logp += -(diff * diff) / (2.0f * var) - lsc - LOG_SQRT_2PI;
+      ent += 0.5f + LOG_SQRT_2PI + lsc;
+      dmean[d] = diff / var;
+      dls[d] = diff * diff / var - 1.0f;
+    }
+    const float logr = logp - a.oldlp[b];
+    const float ratio = expf(logr);
+    const float advn = a.moments ? (a.adv[b] - adv_mean) / adv_den : a.adv[b];
+    const float l1 = -advn * ratio, l2 = -advn * fminf(fmaxf(ratio, a.clip_lo), a.clip_hi);
+    const float w1 = l1 > l2 ? 1.0f : (l1 == l2 ? 0.5f : 0.0f);
+    const float inr = (ratio >= a.clip_lo && ratio <= a.clip_hi) ? 1.0f : 0.0f;
+    const float g_logp = -advn * (w1 + (1.0f - w1) * inr) * ratio * a.inv_m;
+    const float g_H = -a.ent_c * a.inv_m;
+    const float R = a.ret[b], vold = a.vold[b];
+    float dv, vl;
+    if (a.clip_vloss) {
+      const float du = value - R, vu = du * du;
+      const float dd = value - vold, vc = vold + fminf(fmaxf(dd, -a.clip), a.clip);
+      const float dc = vc - R, lc = dc * dc;
+      const float ww = vu > lc ? 1.0f : (vu == lc ? 0.5f : 0.0f);
+      const float ir = (dd >= -a.clip && dd <= a.clip) ? 1.0f : 0.0f;
+      dv = (ww * du + (1.0f - ww) * dc * ir) * a.vf_c * a.inv_m;
+      vl = 0.5f * fmaxf(vu, lc);
+    } else {
+      const float du = value - R;
+      dv = du * a.vf_c * a.inv_m;
+      vl = 0.5f * du * du;
+    }
+    if (lane == 0) {
+      st[0] += fmaxf(l1, l2); st[1] += vl * a.vf_c; st[2] += ent; st[3] += -logr; st[4] += (ratio - 1.0f) - logr;
+      st[5] += fabsf(ratio - 1.0f) > a.clip ? 1.0f : 0.0f;
+      if (a.value_out) a.value_out[b] = value;
+      if (a.logp_out) a.logp_out[b] = logp;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a.d_a_out[(size_t)b * 16 + k] = __float2bfloat16(k < 5 ? g_logp * dmean[k < 5 ? k : 0] : 0.0f);
+#pragma unroll
+      for (int d = 0; d < 5; ++d) { dmu_acc[d] += g_logp * dmean[d]; dls_acc[d] += g_logp * dls[d] + g_H; }
+      db2 += dv;
+    }
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int c = lane + 32 * f;
+      const float g = h[f] > 0.0f ? dv * a.c_w2[c] : 0.0f;
+      a.d_c_h[(size_t)b * 128 + c] = __float2bfloat16(g);
+      dw2[f] += dv * h[f];
+      db1[f] += g;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) atomicAdd(a.stats + k, st[k]);
+#pragma unroll
+    for (int d = 0; d < 5; ++d) { atomicAdd(a.d_head + d, dmu_acc[d]); atomicAdd(a.d_head + 5 + d, dls_acc[d]); }
+    atomicAdd(a.d_head + 10 + 128, db2);
+  }
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    atomicAdd(a.d_head + 10 + lane + 32 * f, dw2[f]);
+    atomicAdd(a.d_head + 10 + 128 + 1 + lane + 32 * f, db1[f]);
   }
 }
 
@@ -768,10 +891,32 @@ extern "C" int aur_equiv_head_loss(const aur_equiv_head_args* h, void* stream) {
   return 0;
 }
 
+static int head_eval_impl(int32_t B, const float* a_out, const float* a_bias, const float* c_pre, const float* c_bias1,
+                          const float* c_w2, const float* c_b2, const float* action_in, uint64_t seed, uint64_t stream_id,
+                          const float* ranges_lo_hi, float* unscaled_out, float* scaled_out, float* logp_out,
+                          float* entropy_out, float* value_out, float* mean_out, float* logstd_out, const float* plain_logstd,
+                          void* stream);
 extern "C" int aur_equiv_head_eval(int32_t B, const float* a_out, const float* a_bias, const float* c_pre, const float* c_bias1,
                                    const float* c_w2, const float* c_b2, const float* action_in, uint64_t seed, uint64_t stream_id,
                                    const float* ranges_lo_hi, float* unscaled_out, float* scaled_out, float* logp_out,
                                    float* entropy_out, float* value_out, float* mean_out, float* logstd_out, void* stream) {
+  return head_eval_impl(B, a_out, a_bias, c_pre, c_bias1, c_w2, c_b2, action_in, seed, stream_id, ranges_lo_hi, unscaled_out,
+                        scaled_out, logp_out, entropy_out, value_out, mean_out, logstd_out, nullptr, stream);
+}
+extern "C" int aur_plain_head_eval(int32_t B, const float* a_out, const float* a_bias, const float* actor_logstd, const float* c_pre,
+                                   const float* c_bias1, const float* c_w2, const float* c_b2, const float* action_in, uint64_t seed,
+                                   uint64_t stream_id, const float* ranges_lo_hi, float* unscaled_out, float* scaled_out,
+                                   float* logp_out, float* entropy_out, float* value_out, float* mean_out, float* logstd_out,
+                                   void* stream) {
+  if (!actor_logstd) { set_error("aur_plain_head_eval: actor_logstd is required"); return AUR_ERR_ARG; }
+  return head_eval_impl(B, a_out, a_bias, c_pre, c_bias1, c_w2, c_b2, action_in, seed, stream_id, ranges_lo_hi, unscaled_out,
+                        scaled_out, logp_out, entropy_out, value_out, mean_out, logstd_out, actor_logstd, stream);
+}
+static int head_eval_impl(int32_t B, const float* a_out, const float* a_bias, const float* c_pre, const float* c_bias1,
+                          const float* c_w2, const float* c_b2, const float* action_in, uint64_t seed, uint64_t stream_id,
+                          const float* ranges_lo_hi, float* unscaled_out, float* scaled_out, float* logp_out,
+                          float* entropy_out, float* value_out, float* mean_out, float* logstd_out, const float* plain_logstd,
+                          void* stream) {
   if (B <= 0 || (!a_out && !c_pre)) { set_error("aur_equiv_head_eval: bad arguments"); return AUR_ERR_ARG; }
   if (a_out && (!a_bias || !ranges_lo_hi || !unscaled_out || !scaled_out || !logp_out || !entropy_out)) {
     set_error("aur_equiv_head_eval: actor head needs a_bias, ranges and the four outputs"); return AUR_ERR_ARG;
@@ -784,9 +929,28 @@ extern "C" int aur_equiv_head_eval(int32_t B, const float* a_out, const float* a
   d.action_in = action_in; d.seed = seed; d.stream_id = stream_id;
   for (int k = 0; k < 5; ++k) { d.lo[k] = a_out ? ranges_lo_hi[2 * k] : 0.f; d.hi[k] = a_out ? ranges_lo_hi[2 * k + 1] : 0.f; }
   d.unscaled_out = unscaled_out; d.scaled_out = scaled_out; d.logp_out = logp_out; d.ent_out = entropy_out; d.value_out = value_out;
-  d.mean_out = mean_out; d.logstd_out = logstd_out;
+  d.mean_out = mean_out; d.logstd_out = logstd_out; d.plain_logstd = plain_logstd;
   head_eval_kernel<<<grid_for((long long)B * 32, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(d);
   AUR_LAUNCH_OK("head_eval_kernel");
+  return 0;
+}
+
+extern "C" int aur_plain_head_loss(const aur_plain_head_args* h, void* stream) {
+  if (!h || h->B <= 0 || !h->a_out || !h->a_bias || !h->actor_logstd || !h->c_pre || !h->c_bias1 || !h->c_w2 || !h->c_b2 ||
+      !h->action || !h->oldlp || !h->adv || !h->ret || !h->vold || !h->d_a_out || !h->d_c_h || !h->d_head || !h->stats ||
+      h->m_total <= 0) {
+    set_error("aur_plain_head_loss: bad arguments"); return AUR_ERR_ARG;
+  }
+  PlainHeadDev d;
+  d.B = h->B; d.a_out = h->a_out; d.a_bias = h->a_bias; d.logstd = h->actor_logstd; d.c_pre = h->c_pre; d.c_bias1 = h->c_bias1;
+  d.c_w2 = h->c_w2; d.c_b2 = h->c_b2;
+  d.action = h->action; d.oldlp = h->oldlp; d.adv = h->adv; d.ret = h->ret; d.vold = h->vold; d.moments = h->adv_moments;
+  d.clip = h->clip_coeff; d.clip_lo = (float)(1.0 - (double)h->clip_coeff); d.clip_hi = (float)(1.0 + (double)h->clip_coeff);
+  d.ent_c = h->entropy_coeff; d.vf_c = h->value_coeff; d.inv_m = (float)(1.0 / (double)h->m_total); d.clip_vloss = h->clip_vloss;
+  d.d_a_out = (__nv_bfloat16*)h->d_a_out; d.d_c_h = (__nv_bfloat16*)h->d_c_h; d.d_head = h->d_head; d.stats = h->stats;
+  d.value_out = h->value_out; d.logp_out = h->logp_out;
+  plain_head_loss_kernel<<<grid_for((long long)h->B * 32, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(d);
+  AUR_LAUNCH_OK("plain_head_loss_kernel");
   return 0;
 }
 

@@ -57,18 +57,23 @@ def init_params(seed: int = 0, device="cuda", scale: float = 1.0) -> Dict[str, t
 
 
 class _Enc:
-    """Activation / gradient buffers of one encoder for a fixed batch size."""
+    """Activation / gradient buffers of one encoder for a fixed batch size; ch = channels of the six stored activations
+    (NHWC bf16, halo where the next layer pads), feat = encoder output width."""
 
-    def __init__(self, B: int, dev):
+    def __init__(self, B: int, dev, ch=(64, 128, 256, 512, 1024, 512), feat: int = 512):
         bf = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
         u8 = lambda *s: torch.zeros(*s, dtype=torch.uint8, device=dev)
-        self.a = [bf(B, 66, 66, 64), bf(B, 34, 34, 128), bf(B, 18, 18, 256), bf(B, 10, 10, 512), bf(B, 8, 8, 1024),
-                  bf(B, 3, 3, 512)]
-        self.arg = [u8(B, 64, 64, 64), u8(B, 32, 32, 128), u8(B, 16, 16, 256), u8(B, 8, 8, 512), None, u8(B, 3, 3, 512)]
-        self.feat = bf(B, 512)
+        self.a = [bf(B, 66, 66, ch[0]), bf(B, 34, 34, ch[1]), bf(B, 18, 18, ch[2]), bf(B, 10, 10, ch[3]), bf(B, 8, 8, ch[4]),
+                  bf(B, 3, 3, ch[5])]
+        self.arg = [u8(B, 64, 64, ch[0]), u8(B, 32, 32, ch[1]), u8(B, 16, 16, ch[2]), u8(B, 8, 8, ch[3]), None, u8(B, 3, 3, ch[5])]
+        self.feat = bf(B, feat)
 
 
 class EquivActorCritic:
+    CH = (64, 128, 256, 512, 1024, 512)      # channels of the stored activations a[0..5]
+    FEAT = 512                               # encoder output width
+    D_HEAD = 651
+
     def __init__(self, params: Dict[str, torch.Tensor], batch: int, lr: float = 3e-4, eps: float = 1e-5,
                  betas=(0.9, 0.999)):
         if batch % 8:
@@ -79,13 +84,13 @@ class EquivActorCritic:
         if self.dev.type != "cuda":
             raise _lib.AurError("EquivActorCritic needs CUDA parameters (no CPU fallback)")
         self.B = batch
-        self.enc = {"actor": _Enc(batch, self.dev), "critic": _Enc(batch, self.dev)}
+        self.enc = {"actor": _Enc(batch, self.dev, self.CH, self.FEAT), "critic": _Enc(batch, self.dev, self.CH, self.FEAT)}
         self.grads = {k: torch.zeros_like(v) for k, v in params.items()}
         self.m1 = {k: torch.zeros_like(v) for k, v in params.items()}
         self.m2 = {k: torch.zeros_like(v) for k, v in params.items()}
         self.lr, self.eps, self.betas, self.step_count = lr, eps, betas, 0
         self.stats = torch.zeros(8, device=self.dev)
-        self.d_head = torch.zeros(651, device=self.dev)
+        self.d_head = torch.zeros(self.D_HEAD, device=self.dev)
         self.moments = torch.zeros(3, dtype=torch.float64, device=self.dev)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.ws = torch.zeros(1 << 20, device=self.dev)
@@ -125,17 +130,21 @@ class EquivActorCritic:
         self._w = w
 
     # ------------------------------------------------------------------ forward
+    def _layer0_params(self, net: str):
+        return self.p[f"{net}.enc0.psi"], self.p[f"{net}.enc0.bias"]
+
     def _encoder_forward(self, net: str, state, obs):
         e, w = self.enc[net], self._w
-        equiv_conv0(obs, state, self.p[f"{net}.enc0.psi"], self.p[f"{net}.enc0.bias"], e.a[0], e.arg[0])
+        psi0, bias0 = self._layer0_params(net)
+        equiv_conv0(obs, state, psi0, bias0, e.a[0], e.arg[0])
         for l, (epi, off) in zip(range(1, 6), [(2, 1), (2, 1), (2, 1), (1, 0), (2, 0)]):
             wm, _, b = w[f"{net}.{l}"]
             conv3x3_bf16(e.a[l - 1], wm, b, epi, e.a[l], off, e.arg[l])
         wm6, _, b6 = w[f"{net}.6"]
-        pre = tc_gemm_bf16(e.a[5].reshape(self.B, 4608), wm6)
+        pre = tc_gemm_bf16(e.a[5].reshape(self.B, 9 * self.CH[5]), wm6)
         L = _lib.lib()
         with torch.cuda.device(self.dev):
-            _chk(L.aur_bias_relu_bf16(self.B, 512, pre.data_ptr(), b6.data_ptr(), e.feat.data_ptr(), _stream()), "aur_bias_relu_bf16")
+            _chk(L.aur_bias_relu_bf16(self.B, self.FEAT, pre.data_ptr(), b6.data_ptr(), e.feat.data_ptr(), _stream()), "aur_bias_relu_bf16")
 
     def forward(self, state: torch.Tensor, obs: torch.Tensor):
         """Encoders + head GEMMs; returns (actor head output [B,16] fp32, critic head-1 pre-activation [B,512] fp32)."""
@@ -170,10 +179,26 @@ class EquivActorCritic:
         with torch.cuda.device(self.dev):
             _chk(L.aur_wgrad3x3_bf16(Cout, Cin, Q, dy_buf.data_ptr(), x_buf.data_ptr(), base_off, Wb, dw.data_ptr(), 0, _stream()),
                  "aur_wgrad3x3_bf16")
-            _chk(L.aur_equiv_project_regular(dw.data_ptr(), Cout // 4, Cin // 4, self.grads[f"{net}.enc{l}.psi"].data_ptr(), _stream()),
-                 "aur_equiv_project_regular")
-            _chk(L.aur_colsum_bf16(Q, Cout, dy_buf.data_ptr(), 4, self.grads[f"{net}.enc{l}.bias"].data_ptr(), _stream()),
+        self._store_wgrad(net, l, dw, Cout, Cin)
+        self._store_bgrad(net, l, dy_buf.reshape(Q, Cout), Q, Cout)
+
+    # dense gradient of a layer's contraction matrix [Cout, 9, Cin] (layer 6: [Cout, 9 * Cin]) -> the free parameters
+    def _store_wgrad(self, net: str, l: int, dw: torch.Tensor, Cout: int, Cin: int):
+        with torch.cuda.device(self.dev):
+            _chk(_lib.lib().aur_equiv_project_regular(dw.data_ptr(), Cout // 4, Cin // 4, self.grads[f"{net}.enc{l}.psi"].data_ptr(),
+                                                      _stream()), "aur_equiv_project_regular")
+
+    def _store_bgrad(self, net: str, l: int, dy2d: torch.Tensor, Q: int, Cout: int):
+        with torch.cuda.device(self.dev):
+            _chk(_lib.lib().aur_colsum_bf16(Q, Cout, dy2d.data_ptr(), 4, self.grads[f"{net}.enc{l}.bias"].data_ptr(), _stream()),
                  "aur_colsum_bf16")
+
+    def _layer0_wgrad(self, net: str, state, obs, dprev, e):
+        with torch.cuda.device(self.dev):
+            _chk(_lib.lib().aur_equiv_conv0_wgrad(obs.data_ptr(), state.data_ptr(), dprev.data_ptr(), e.a[0].data_ptr(),
+                                                  e.arg[0].data_ptr(), self.B, self.ws.data_ptr(),
+                                                  self.grads[f"{net}.enc0.psi"].data_ptr(),
+                                                  self.grads[f"{net}.enc0.bias"].data_ptr(), _stream()), "aur_equiv_conv0_wgrad")
 
     def _unpool(self, dpool, act, aoff, arg, C, Hp, dHb, doff):
         out = torch.zeros(self.B, dHb, dHb, C, dtype=torch.bfloat16, device=self.dev)
@@ -183,33 +208,30 @@ class EquivActorCritic:
         return out
 
     def _encoder_backward(self, net: str, state, obs, dfeat: torch.Tensor):
-        """dfeat: fp32 [B,512] gradient wrt the encoder output (post-ReLU features)."""
-        L = _lib.lib()
-        e, w, B = self.enc[net], self._w, self.B
+        """dfeat: fp32 [B, FEAT] gradient wrt the encoder output (post-ReLU features)."""
+        e, w, B, CH = self.enc[net], self._w, self.B, self.CH
         dz6 = self._cast(dfeat, e.feat)                                         # through the last ReLU
         wm6, wm6t, _ = w[f"{net}.6"]
-        # layer 6 (dense 3x3 -> 1x1): weight gradient [512,4608] = dz6^T a6 ; data gradient = dz6 W6
+        # layer 6 (dense 3x3 -> 1x1): weight gradient [FEAT, 9 CH5] = dz6^T a6 ; data gradient = dz6 W6
         dz6_cm = self._t(dz6)
-        dW6 = tc_gemm_bf16(dz6_cm, self._t(e.a[5].reshape(B, 4608)))
-        with torch.cuda.device(self.dev):
-            _chk(L.aur_equiv_project_regular(dW6.data_ptr(), 128, 128, self.grads[f"{net}.enc6.psi"].data_ptr(), _stream()),
-                 "aur_equiv_project_regular")
-            _chk(L.aur_colsum_bf16(B, 512, dz6.data_ptr(), 4, self.grads[f"{net}.enc6.bias"].data_ptr(), _stream()),
-                 "aur_colsum_bf16")
-        da6 = self._cast(tc_gemm_bf16(dz6, wm6t), None).reshape(B, 3, 3, 512)
+        dW6 = tc_gemm_bf16(dz6_cm, self._t(e.a[5].reshape(B, 9 * CH[5])))
+        self._store_wgrad(net, 6, dW6, self.FEAT, CH[5])
+        self._store_bgrad(net, 6, dz6, B, self.FEAT)
+        da6 = self._cast(tc_gemm_bf16(dz6, wm6t), None).reshape(B, 3, 3, CH[5])
         # layer 5 (pad 0, pooled): un-pool into a 2-halo buffer (backward-data) and into the input geometry (weights)
-        dy5_d = self._unpool(da6, e.a[5], 0, e.arg[5], 512, 3, 10, 2)
-        dy5_w = self._unpool(da6, e.a[5], 0, e.arg[5], 512, 3, 8, 0)
+        dy5_d = self._unpool(da6, e.a[5], 0, e.arg[5], CH[5], 3, 10, 2)
+        dy5_w = self._unpool(da6, e.a[5], 0, e.arg[5], CH[5], 3, 8, 0)
         self._wgrad(net, 5, dy5_w, e.a[4], 0)
-        dy4 = torch.zeros(B, 10, 10, 1024, dtype=torch.bfloat16, device=self.dev)
+        dy4 = torch.zeros(B, 10, 10, CH[4], dtype=torch.bfloat16, device=self.dev)
         conv3x3_bf16(dy5_d, w[f"{net}.5"][1], None, 3, dy4, 1, None, relu_ref=e.a[4], ref_off=0)   # x ReLU mask of layer 4
         # layer 4 (pad 1, ReLU only)
         self._wgrad(net, 4, dy4, e.a[3], -(10 + 1))
-        da4 = torch.empty(B, 8, 8, 512, dtype=torch.bfloat16, device=self.dev)
+        da4 = torch.empty(B, 8, 8, CH[3], dtype=torch.bfloat16, device=self.dev)
         conv3x3_bf16(dy4, w[f"{net}.4"][1], None, 0, da4, 0)
         # layers 3, 2, 1 (pad 1, pooled)
         dprev = da4
-        for l, Hp, C in ((3, 8, 512), (2, 16, 256), (1, 32, 128)):
+        for l, Hp in ((3, 8), (2, 16), (1, 32)):
+            C = CH[l]
             Hb = 2 * Hp + 2
             dy = self._unpool(dprev, e.a[l], 1, e.arg[l], C, Hp, Hb, 1)
             self._wgrad(net, l, dy, e.a[l - 1], -(Hb + 1))
@@ -217,10 +239,7 @@ class EquivActorCritic:
             dprev = torch.empty(B, 2 * Hp, 2 * Hp, Cin, dtype=torch.bfloat16, device=self.dev)
             conv3x3_bf16(dy, w[f"{net}.{l}"][1], None, 0, dprev, 0)
         # layer 0 (direct)
-        with torch.cuda.device(self.dev):
-            _chk(L.aur_equiv_conv0_wgrad(obs.data_ptr(), state.data_ptr(), dprev.data_ptr(), e.a[0].data_ptr(), e.arg[0].data_ptr(),
-                                         B, self.ws.data_ptr(), self.grads[f"{net}.enc0.psi"].data_ptr(),
-                                         self.grads[f"{net}.enc0.bias"].data_ptr(), _stream()), "aur_equiv_conv0_wgrad")
+        self._layer0_wgrad(net, state, obs, dprev, e)
 
     # ------------------------------------------------------------------- update
     def loss_and_grads(self, state, obs, action, oldlp, adv, ret, vold, clip_coeff=0.2, entropy_coeff=0.01,

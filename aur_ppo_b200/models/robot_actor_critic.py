@@ -10,8 +10,9 @@ encoders and head GEMMs on tcgen05 and decodes the heads in `head_eval_kernel` (
 summed log-prob / entropy, action scaling).  No autograd graph is built and there is no CPU path: gradients come
 from `engine(batch).loss_and_grads(...)`.
 
-`equivariant=False` (the plain `base_encoder` CNN, src/nets/base_cnns.py:20-84) is SURVEY.md §8(f) rank 3 and not
-built: the constructor raises instead of falling back.
+`equivariant=False` selects the plain `base_actor` / `base_critic` CNNs (src/nets/base_cnns.py:20-84, SURVEY.md §8(f)
+rank 3) on the same kernels through `aur_ppo_b200/plain_cnn.py::PlainActorCritic`; its parameters carry the reference
+modules' own state_dict names, see `reference_state_dicts()`.
 """
 from __future__ import annotations
 
@@ -23,6 +24,7 @@ import torch
 from torch import nn
 
 from .. import _lib
+from .. import plain_cnn
 from ..equiv import ENC_FIELDS, N_ACT, EquivActorCritic, init_params
 from ..kernels import _ptr, _stream, tc_gemm_bf16
 
@@ -34,8 +36,8 @@ class _PsiNet(nn.Module):
         super().__init__()
         self._keys = []
         for k, v in params.items():
-            if k.startswith(net + "."):
-                name = k[len(net) + 1:].replace(".", "_")
+            if k.startswith(net + ".") or (net == "actor" and k == "actor_logstd"):
+                name = k.replace(".", "_") if k == "actor_logstd" else k[len(net) + 1:].replace(".", "_")
                 self.register_parameter(name, nn.Parameter(v, requires_grad=False))
                 self._keys.append((k, name))
 
@@ -46,8 +48,6 @@ class _PsiNet(nn.Module):
 class robot_actor_critic(nn.Module):
     def __init__(self, device, equivariant: bool, dx=0.02, dy=0.02, dz=0.02, dr=np.pi / 8, n_a=5, tau=0.001, seed: int = 0) -> None:
         super().__init__()
-        if not equivariant:
-            raise _lib.AurError("robot_actor_critic(equivariant=False): the plain CNN actor-critic is not built (no fallback)")
         if n_a != N_ACT:
             raise _lib.AurError("robot_actor_critic: the equivariant actor head has 5 action dims (equiv.py:70-80)")
         self.device = torch.device(device)
@@ -61,7 +61,7 @@ class robot_actor_critic(nn.Module):
         self.dz_range = torch.tensor([-dz, dz])
         self.n_a = n_a
         self.equivariant = equivariant
-        p = init_params(seed, self.device)
+        p = init_params(seed, self.device) if equivariant else plain_cnn.init_params(seed, self.device)
         self.actor = _PsiNet("actor", p)
         self.critic = _PsiNet("critic", p)
         self._engines: Dict[int, EquivActorCritic] = {}
@@ -84,7 +84,8 @@ class robot_actor_critic(nn.Module):
     def engine(self, batch: int, **kw) -> EquivActorCritic:
         """The update engine for minibatches of `batch` samples, sharing this module's parameter storage."""
         if batch not in self._engines:
-            self._engines[batch] = EquivActorCritic(self.tensors(), batch, **kw)
+            cls = EquivActorCritic if self.equivariant else plain_cnn.PlainActorCritic
+            self._engines[batch] = cls(self.tensors(), batch, **kw)
         return self._engines[batch]
 
     def _run(self, state, obs, action, want_actor: bool, want_critic: bool):
@@ -110,21 +111,29 @@ class robot_actor_critic(nn.Module):
         dev = self.device
         f = lambda *s: torch.empty(*s, device=dev)
         out = dict(unscaled=f(Bp, 5), scaled=f(Bp, 5), logp=f(Bp), ent=f(Bp), value=f(Bp), mean=f(Bp, 5), logstd=f(Bp, 5))
-        a_bias = torch.cat([torch.zeros(2, device=dev), e.p["actor.head.bias_triv"]]).contiguous()
         act_d = None
         if action is not None:
             act_d = action.to(dev, torch.float32).reshape(B, 5)
             if Bp != B:
                 act_d = torch.cat([act_d, act_d.new_zeros(Bp - B, 5)])
             act_d = act_d.contiguous()
-        w2 = e.p["critic.head2.w"].reshape(-1).contiguous()
         self._calls += 1
+        outs = (out["unscaled"].data_ptr(), out["scaled"].data_ptr(), out["logp"].data_ptr(), out["ent"].data_ptr(),
+                out["value"].data_ptr(), out["mean"].data_ptr(), out["logstd"].data_ptr())
         with torch.cuda.device(dev):
-            rc = _lib.lib().aur_equiv_head_eval(
-                Bp, _ptr(a_out), a_bias.data_ptr(), _ptr(c_pre), e._w["critic.head1"][2].data_ptr(), w2.data_ptr(),
-                e.p["critic.head2.bias"].data_ptr(), _ptr(act_d), self.seed & 0xFFFFFFFFFFFFFFFF, self._calls, self._ranges,
-                out["unscaled"].data_ptr(), out["scaled"].data_ptr(), out["logp"].data_ptr(), out["ent"].data_ptr(),
-                out["value"].data_ptr(), out["mean"].data_ptr(), out["logstd"].data_ptr(), _stream())
+            if self.equivariant:
+                a_bias = torch.cat([torch.zeros(2, device=dev), e.p["actor.head.bias_triv"]]).contiguous()
+                w2 = e.p["critic.head2.w"].reshape(-1).contiguous()
+                rc = _lib.lib().aur_equiv_head_eval(
+                    Bp, _ptr(a_out), a_bias.data_ptr(), _ptr(c_pre), e._w["critic.head1"][2].data_ptr(), w2.data_ptr(),
+                    e.p["critic.head2.bias"].data_ptr(), _ptr(act_d), self.seed & 0xFFFFFFFFFFFFFFFF, self._calls, self._ranges,
+                    *outs, _stream())
+            else:
+                w2 = e.p["critic.critic.2.weight"].reshape(-1).contiguous()
+                rc = _lib.lib().aur_plain_head_eval(
+                    Bp, _ptr(a_out), e.p["actor.mean_linear.bias"].data_ptr(), e.p["actor_logstd"].data_ptr(), _ptr(c_pre),
+                    e._w["critic.head1"][2].data_ptr(), w2.data_ptr(), e.p["critic.critic.2.bias"].data_ptr(), _ptr(act_d),
+                    self.seed & 0xFFFFFFFFFFFFFFFF, self._calls, self._ranges, *outs, _stream())
         _lib.check(rc, "aur_equiv_head_eval")
         return {k: v[:B] for k, v in out.items()}
 
@@ -165,3 +174,22 @@ class robot_actor_critic(nn.Module):
     def load_checkpoint_dict(self, d: dict) -> None:
         self.actor.load_state_dict(d["actor_state"])
         self.critic.load_state_dict(d["critic_state"])
+
+    # plain CNN only: the reference modules' own state_dicts (base_actor / base_critic keys, robot_actor_critic.actor_logstd)
+    def reference_state_dicts(self) -> dict:
+        if self.equivariant:
+            raise _lib.AurError("reference_state_dicts: e2cnn checkpoints are not interchangeable (DESIGN.md section 5)")
+        t = self.tensors()
+        return {"actor_state": {k[len("actor."):]: v.detach().clone() for k, v in t.items() if k.startswith("actor.")},
+                "critic_state": {k[len("critic."):]: v.detach().clone() for k, v in t.items() if k.startswith("critic.")},
+                "actor_logstd": t["actor_logstd"].detach().clone()}
+
+    def load_reference_state_dicts(self, d: dict) -> None:
+        t = self.tensors()
+        with torch.no_grad():
+            for k, v in d["actor_state"].items():
+                t["actor." + k].copy_(v)
+            for k, v in d["critic_state"].items():
+                t["critic." + k].copy_(v)
+            if "actor_logstd" in d:
+                t["actor_logstd"].copy_(d["actor_logstd"])

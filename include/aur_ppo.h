@@ -421,6 +421,43 @@ int aur_equiv_head_eval(int32_t B, const float* a_out, const float* a_bias, cons
                         const float* ranges_lo_hi, float* unscaled_out, float* scaled_out, float* logp_out,
                         float* entropy_out, float* value_out, float* mean_out, float* logstd_out, void* stream);
 
+/* The same for the plain CNN heads of robot_actor_critic(equivariant=False) (src/models/robot_actor_critic.py:41-51,
+ * src/nets/base_cnns.py:57-84): a_out cols 0..4 = base_actor.mean_linear output before bias, log_std = the actor_logstd
+ * parameter [5], critic = Linear(128,128)-ReLU-Linear(128,1) on c_pre [B,128]. */
+int aur_plain_head_eval(int32_t B, const float* a_out, const float* a_bias, const float* actor_logstd, const float* c_pre,
+                        const float* c_bias1, const float* c_w2, const float* c_b2, const float* action_in, uint64_t seed,
+                        uint64_t stream_id, const float* ranges_lo_hi, float* unscaled_out, float* scaled_out, float* logp_out,
+                        float* entropy_out, float* value_out, float* mean_out, float* logstd_out, void* stream);
+
+/* Heads + PPO loss of the plain CNN update (robot_ppo.update, src/robot_ppo.py:345-398, on the non-equivariant model):
+ * gradients wrt the two head GEMM outputs (bf16) and the small head parameters. */
+typedef struct {
+  int32_t B;
+  int32_t clip_vloss;
+  int64_t m_total;
+  const float* a_out;        /* [B,16] mean_linear output before bias (5 used) */
+  const float* a_bias;       /* [5] */
+  const float* actor_logstd; /* [5] */
+  const float* c_pre;        /* [B,128] critic.0 output before bias */
+  const float* c_bias1;      /* [128] */
+  const float* c_w2;         /* [128] */
+  const float* c_b2;         /* [1] */
+  const float* action;       /* [B,5] */
+  const float* oldlp;
+  const float* adv;
+  const float* ret;
+  const float* vold;
+  const double* adv_moments; /* [3] or NULL */
+  float clip_coeff, entropy_coeff, value_coeff, _pad;
+  void* d_a_out;             /* [B,16] bf16 out */
+  void* d_c_h;               /* [B,128] bf16 out */
+  float* d_head;             /* [267] accumulated: a_bias 5 | actor_logstd 5 | c_w2 128 | c_b2 1 | c_bias1 128 */
+  float* stats;              /* [8] accumulated sums */
+  float* value_out;          /* [B] or NULL */
+  float* logp_out;           /* [B] or NULL */
+} aur_plain_head_args;
+int aur_plain_head_loss(const aur_plain_head_args* args, void* stream);
+
 int aur_sumsq_f32(int64_t n, const float* g, double* out_accum, void* stream);
 /* torch.optim.Adam math on a flat buffer; clip_sumsq (nullable) = device sum of squares of the clipped group */
 int aur_adam_flat(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, double lr, double beta1,

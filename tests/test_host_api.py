@@ -131,11 +131,10 @@ def test_ppo_class_fails_loudly_without_cuda():
         ppo(p)
 
 
-def test_robot_actor_critic_refuses_unbuilt_paths():
-    """No CPU path and no plain-CNN fallback behind the robot_actor_critic facade."""
+def test_robot_actor_critic_refuses_cpu():
+    """No CPU path behind the robot_actor_critic facade (either model family)."""
     from aur_ppo_b200 import _lib
     from aur_ppo_b200.models import robot_actor_critic
-    with pytest.raises(_lib.AurError):
-        robot_actor_critic("cpu", True)
-    with pytest.raises(_lib.AurError):
-        robot_actor_critic("cuda", False)
+    for equivariant in (True, False):
+        with pytest.raises(_lib.AurError):
+            robot_actor_critic("cpu", equivariant)
