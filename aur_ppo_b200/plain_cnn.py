@@ -117,7 +117,7 @@ class PlainActorCritic(EquivActorCritic):
         self.grads[conv_key(net, l, "weight")].copy_(g)
 
     def _store_bgrad(self, net: str, l: int, dy2d: torch.Tensor, Q: int, Cout: int):
-        out = torch.empty(Cout, device=self.dev)
+        out = torch.zeros(Cout, device=self.dev)           # the kernel accumulates
         with torch.cuda.device(self.dev):
             _chk(_lib.lib().aur_colsum_bf16(Q, Cout, dy2d.data_ptr(), 1, out.data_ptr(), _stream()), "aur_colsum_bf16")
         self.grads[conv_key(net, l, "bias")].copy_(out[:REAL[l]])
