@@ -347,24 +347,28 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_equiv(args):
+def run_equiv(args, plain: bool = False):
     """BASELINE configs[3]: equivariant actor-critic update on synthetic close_loop_block_picking-shaped
     observations (1x128x128 heightmap + gripper state), minibatch 4096.  One step = one full update
-    (two encoders forward + loss + backward + clip + Adam)."""
+    (two encoders forward + loss + backward + clip + Adam).  plain=True: the sibling non-equivariant CNN
+    (robot_actor_critic equivariant=False) on the same inputs."""
     import torch
-    from aur_ppo_b200 import _lib, equiv
+    from aur_ppo_b200 import _lib, equiv, plain_cnn
     B = 4096
     torch.cuda.set_device(0)
-    params = equiv.init_params(seed=0)
-    for k in ("actor.head.psi_triv", "actor.head.psi_irrep", "critic.head2.w"):
-        params[k].mul_(0.1)
+    if plain:
+        params = plain_cnn.init_params(seed=0)
+    else:
+        params = equiv.init_params(seed=0)
+        for k in ("actor.head.psi_triv", "actor.head.psi_irrep", "critic.head2.w"):
+            params[k].mul_(0.1)
     g = torch.Generator(device="cuda").manual_seed(0)
     obs = torch.rand(B, 1, 128, 128, generator=g, device="cuda") * 0.32
     state = (torch.rand(B, generator=g, device="cuda") > 0.5).float()
     action = torch.randn(B, 5, generator=g, device="cuda")
     adv, ret, vold = (torch.randn(B, generator=g, device="cuda") for _ in range(3))
     oldlp = torch.full((B,), -7.0, device="cuda")
-    model = equiv.EquivActorCritic(params, B)
+    model = plain_cnn.PlainActorCritic(params, B) if plain else equiv.EquivActorCritic(params, B)
     for _ in range(args.warmup):
         model.update(state, obs, action, oldlp, adv, ret, vold)
     torch.cuda.synchronize()
@@ -396,7 +400,12 @@ def run_equiv(args):
     torch.cuda.synchronize()
     e2e_ms = e0.elapsed_time(e1) / args.steps
     h2d = sum(t.numel() * t.element_size() for t in host)
-    flops = 3 * 2 * 2.80e9 * B
+    # forward FLOPs per encoder and sample: equivariant 2.80e9; plain CNN 2 * 9 * sum(cin * cout * H * W)
+    # = 9.4 + 4 x 37.7 + 42.5 + 0.6 MFLOP = 2.034e8 (real channels; the padded contractions issue ~2.2x that in layers 0-2)
+    flops = 3 * 2 * (2.034e8 if plain else 2.80e9) * B
+    cpu_baseline = None
+    if plain and not args.no_cpu_baseline:
+        cpu_baseline = cnn_cpu_baseline()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -407,16 +416,53 @@ def run_equiv(args):
     line = {"metric": "update_samples_per_s", "value": B / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 operands / fp32 accumulate (tcgen05), fp32 parameters and Adam", "data": "synthetic",
-            "config": {"workload": "equivariant actor-critic update, minibatch 4096, obs 1x128x128 + gripper state "
-                                   "(BASELINE configs[3])", "l2": "activations 25 GB per step >> L2"},
+            "config": {"workload": ("plain CNN actor-critic update (robot_actor_critic equivariant=False), minibatch 4096, obs "
+                                    "1x128x128 + gripper state (sibling of BASELINE configs[3])") if plain else
+                                   ("equivariant actor-critic update, minibatch 4096, obs 1x128x128 + gripper state "
+                                    "(BASELINE configs[3])"),
+                       "l2": "activations >> L2 per step"},
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
-                         "kernel": "conv_igemm_kernel + wgrad3x3_kernel (whole update, 68.8 TFLOP algorithmic)",
-                         "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "fallback"},
-            "cpu_baseline": None,
+                         "kernel": "conv_igemm_kernel + wgrad3x3_kernel (whole update, %.1f TFLOP algorithmic)" % (flops / 1e12),
+                         "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "note": ("channels 16 / 32 are padded to the 64-wide K chunk and layer 0 runs 4 rotated copies: the "
+                                  "narrow layers are HBM / epilogue bound, see DESIGN.md section 4.8") if plain else None},
+            "cpu_baseline": cpu_baseline,
             "e2e": {"value": B / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                     "ms_per_step": e2e_ms},
             "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line))
+
+
+def cnn_cpu_baseline():
+    """The reference's CPU path for the plain CNN update restated (oracle/cnn_ref.py = base_actor / base_critic forward,
+    robot_ppo.update loss, autograd backward, actor-only clip, torch Adam) on the host cores, bounded sample."""
+    import time
+    import torch
+    from oracle import cnn_ref as C
+    B = 32
+    p = {k: v.clone().requires_grad_(True) for k, v in C.formula_params(C.param_shapes(), seed=0).items()}
+    opt = torch.optim.Adam(list(p.values()), lr=3e-4, eps=1e-5)
+    g = torch.Generator().manual_seed(0)
+    obs = torch.rand(B, 1, 128, 128, generator=g) * 0.32
+    state = (torch.rand(B, generator=g) > 0.5).float()
+    action = torch.randn(B, 5, generator=g)
+    adv, ret, vold = (torch.randn(B, generator=g) for _ in range(3))
+    oldlp = torch.full((B,), -7.0)
+
+    def step():
+        opt.zero_grad()
+        loss, _ = C.update_loss(p, state, obs, action, oldlp, adv, ret, vold)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([v for k, v in p.items() if k.startswith("actor.")], 0.5)
+        opt.step()
+    step()
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or time.perf_counter() - t0 < 10.0:
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * B / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle port (torch CPU conv2d + autograd + Adam), minibatch {B} x {n} updates"}
 
 
 def main():
@@ -426,15 +472,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
-    ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "equiv"],
-                    help="ppo = BASELINE configs[1] (default, the headline line); equiv = configs[3]")
+    ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "equiv", "cnn"],
+                    help="ppo = BASELINE configs[1] (default, the headline line); equiv = configs[3]; cnn = its plain-CNN sibling")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "equiv":
-        run_equiv(args)
+    elif args.workload in ("equiv", "cnn"):
+        run_equiv(args, plain=args.workload == "cnn")
     else:
         run_ours(args)
 
