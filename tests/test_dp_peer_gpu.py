@@ -19,7 +19,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, cont, out_dir):
+def _worker(rank, world, port, cont, out_dir, shape=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     dev = rank % torch.cuda.device_count()
@@ -27,8 +27,11 @@ def _worker(rank, world, port, cont, out_dir):
     from aur_ppo_b200 import kernels, parallel
     from tests.helpers import flat_from_named, random_policy
     obs_dim, act_dim = (3, 1) if cont else (4, 2)
-    _, named = random_policy(obs_dim, act_dim, 64, 2, cont, seed=4)
-    desc = kernels.policy_desc(obs_dim, act_dim, 64, 2, cont)
+    hidden, layers = 64, 2
+    if shape is not None:                                   # a shape of the generic kernel (update_generic.cu)
+        obs_dim, act_dim, hidden, layers = shape
+    _, named = random_policy(obs_dim, act_dim, hidden, layers, cont, seed=4)
+    desc = kernels.policy_desc(obs_dim, act_dim, hidden, layers, cont)
     flat0 = torch.from_numpy(flat_from_named(named)).cuda()
     B, m = 6000, 4096                                       # the global minibatch: m of B rows, same on every rank
     g = torch.Generator().manual_seed(12)
@@ -64,10 +67,10 @@ def _worker(rank, world, port, cont, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cont", [False, True])
-def test_peer_exchange_matches_single_gpu(tmp_path, cont):
+@pytest.mark.parametrize("cont,shape", [(False, None), (True, None), (False, (6, 3, 32, 3)), (True, (5, 2, 128, 2))])
+def test_peer_exchange_matches_single_gpu(tmp_path, cont, shape):
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), cont, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), cont, str(tmp_path), shape), nprocs=world, join=True)
     r0, r1, one = [np.load(tmp_path / f) for f in ("rank0.npz", "rank1.npz", "single.npz")]
     # every rank ends with bit-identical parameters and statistics (same sums in the same order)
     np.testing.assert_array_equal(r0["params"], r1["params"])
