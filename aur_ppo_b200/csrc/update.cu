@@ -506,7 +506,19 @@ __global__ void __launch_bounds__(256) adv_moments_kernel(long long m, const int
   __shared__ double sh[2][8];
   __shared__ bool last;
   double s = 0.0, ss = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < m; i += 4 * stride) {            // four independent gathers in flight, summed in index order
+    float v4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long row = idx ? (long long)__ldg(idx + i + k * stride) : idx_offset + i + k * stride;
+      v4[k] = __ldg(adv + row);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const double v = (double)v4[k]; s += v; ss += v * v; }
+  }
+  for (; i < m; i += stride) {
     const long long row = idx ? (long long)idx[i] : idx_offset + i;
     const double v = (double)__ldg(adv + row);
     s += v; ss += v * v;
@@ -522,13 +534,21 @@ __global__ void __launch_bounds__(256) adv_moments_kernel(long long m, const int
     last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last) {                                            // block-uniform: the whole last CTA finalises, in a fixed order
     __threadfence();
     double a = 0.0, b = 0.0;
-    for (unsigned c = 0; c < gridDim.x; ++c) { a += partial[2 * c]; b += partial[2 * c + 1]; }   // fixed order
-    out[0] = a; out[1] = b; out[2] = (double)m;
-    sh[0][0] = a; sh[1][0] = b;
-    *ticket = 0u;
+    for (unsigned c = threadIdx.x; c < gridDim.x; c += blockDim.x) { a += __ldcg(partial + 2 * c); b += __ldcg(partial + 2 * c + 1); }
+    a = warp_sum(a); b = warp_sum(b);
+    __syncthreads();                                     // sh[][] of the first phase has been consumed by thread 0
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      a = 0.0; b = 0.0;
+      for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
+      out[0] = a; out[1] = b; out[2] = (double)m;
+      sh[0][0] = a; sh[1][0] = b;
+      *ticket = 0u;
+    }
   }
   if (dp.world > 1 && last) {                            // push the local moments to every rank, then release the flags
     __syncthreads();

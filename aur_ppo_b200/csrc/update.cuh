@@ -14,7 +14,7 @@ constexpr int UPD_SW = 4800;           // smem floats reserved for one net (padd
 constexpr int UPD_WD = 2 * UPD_H * UPD_H;   // a 64x64 matrix with every entry duplicated: [k][n][2]
 constexpr int UPD_SMEM_FLOATS = UPD_SW + 2 * UPD_WD + UPD_H + 2 * UPD_H * UPD_LD + 2 * 4 * UPD_LD + 4 * UPD_H;
 constexpr size_t UPD_SMEM = sizeof(float) * UPD_SMEM_FLOATS;
-constexpr int MOM_CTAS = 148;
+constexpr int MOM_CTAS = 148 * 8;      // advantage-moment CTAs: the gather is latency-bound, eight CTAs per SM keep ~64 loads in flight per SM x 8
 
 // ---- data-parallel exchange over peer memory (dp.cu): every rank owns one exchange area that all ranks of the
 // node map (CUDA IPC).  Producers PUSH their values into every peer's area over NVLink and then release a
