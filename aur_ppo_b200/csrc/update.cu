@@ -476,12 +476,18 @@ __global__ void grad_reduce_kernel(const float* __restrict__ partials, int ncta,
   }
   s += __shfl_xor_sync(0xffffffffu, s, 1);              // q0 + q1 | q2 + q3 (IEEE addition is commutative: both lanes agree)
   s += __shfl_xor_sync(0xffffffffu, s, 2);
-  if (live && q == 0) {
-    const float v = (float)s;
-    grads_out[i] = v;
-    if (dp.world > 1) {                                  // push this rank's sums into every rank's exchange area
-      const size_t slot_off = DP_OFF_GRAD + ((size_t)(dp.seq & 1u) * DP_MAX + dp.rank) * dp_grad_stride(P) * sizeof(float);
-      for (int r = 0; r < dp.world; ++r) reinterpret_cast<float*>(dp.peer[r] + slot_off)[i] = v;
+  __shared__ float sv[64];                              // the block's 64 outputs, so that the stores below are coalesced
+  if (q == 0) sv[threadIdx.x >> 2] = (float)s;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int64_t o = (int64_t)blockIdx.x * 64 + threadIdx.x;
+    if (o < P + AUR_NUM_STATS) {
+      const float v = sv[threadIdx.x];
+      grads_out[o] = v;
+      if (dp.world > 1) {                                // push this rank's sums into every rank's exchange area
+        const size_t slot_off = DP_OFF_GRAD + ((size_t)(dp.seq & 1u) * DP_MAX + dp.rank) * dp_grad_stride(P) * sizeof(float);
+        for (int r = 0; r < dp.world; ++r) reinterpret_cast<float*>(dp.peer[r] + slot_off)[o] = v;
+      }
     }
   }
   if (dp.world > 1) {                                    // the last block to finish releases the flags
