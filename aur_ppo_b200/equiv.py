@@ -98,6 +98,7 @@ class EquivActorCritic:
         self.logp = torch.zeros(batch, device=self.dev)
         self._idx11 = None
         self._w = {}
+        self._zcache = {}
 
     # ------------------------------------------------------------------ weights
     def _expand(self):
@@ -200,8 +201,20 @@ class EquivActorCritic:
                                                   self.grads[f"{net}.enc0.psi"].data_ptr(),
                                                   self.grads[f"{net}.enc0.bias"].data_ptr(), _stream()), "aur_equiv_conv0_wgrad")
 
-    def _unpool(self, dpool, act, aoff, arg, C, Hp, dHb, doff):
-        out = torch.zeros(self.B, dHb, dHb, C, dtype=torch.bfloat16, device=self.dev)
+    def _halo_zeros(self, tag: str, *shape) -> torch.Tensor:
+        """bf16 buffer whose halo must be zero and whose interior is fully overwritten by the kernel that fills it (un-pool,
+        masked backward-data): allocated and zeroed ONCE per shape - the halo is never written, so it stays zero, and a
+        per-call torch.zeros of these buffers was 19 GB of fill traffic per 4096-sample update.  Shared by the two nets
+        (their backward passes run one after the other on one stream)."""
+        key = (tag,) + shape                        # one buffer per role: two live buffers may share a shape
+        t = self._zcache.get(key)
+        if t is None:
+            t = torch.zeros(*shape, dtype=torch.bfloat16, device=self.dev)
+            self._zcache[key] = t
+        return t
+
+    def _unpool(self, dpool, act, aoff, arg, C, Hp, dHb, doff, tag: str):
+        out = self._halo_zeros(tag, self.B, dHb, dHb, C)
         with torch.cuda.device(self.dev):
             _chk(_lib.lib().aur_unpool_relu_bwd(self.B, Hp, Hp, C, dpool.data_ptr(), act.data_ptr(), act.shape[1], act.shape[2],
                                                 aoff, arg.data_ptr(), out.data_ptr(), dHb, dHb, doff, _stream()), "aur_unpool_relu_bwd")
@@ -219,10 +232,10 @@ class EquivActorCritic:
         self._store_bgrad(net, 6, dz6, B, self.FEAT)
         da6 = self._cast(tc_gemm_bf16(dz6, wm6t), None).reshape(B, 3, 3, CH[5])
         # layer 5 (pad 0, pooled): un-pool into a 2-halo buffer (backward-data) and into the input geometry (weights)
-        dy5_d = self._unpool(da6, e.a[5], 0, e.arg[5], CH[5], 3, 10, 2)
-        dy5_w = self._unpool(da6, e.a[5], 0, e.arg[5], CH[5], 3, 8, 0)
+        dy5_d = self._unpool(da6, e.a[5], 0, e.arg[5], CH[5], 3, 10, 2, "dy5_d")
+        dy5_w = self._unpool(da6, e.a[5], 0, e.arg[5], CH[5], 3, 8, 0, "dy5_w")
         self._wgrad(net, 5, dy5_w, e.a[4], 0)
-        dy4 = torch.zeros(B, 10, 10, CH[4], dtype=torch.bfloat16, device=self.dev)
+        dy4 = self._halo_zeros("dy4", B, 10, 10, CH[4])
         conv3x3_bf16(dy5_d, w[f"{net}.5"][1], None, 3, dy4, 1, None, relu_ref=e.a[4], ref_off=0)   # x ReLU mask of layer 4
         # layer 4 (pad 1, ReLU only)
         self._wgrad(net, 4, dy4, e.a[3], -(10 + 1))
@@ -233,7 +246,7 @@ class EquivActorCritic:
         for l, Hp in ((3, 8), (2, 16), (1, 32)):
             C = CH[l]
             Hb = 2 * Hp + 2
-            dy = self._unpool(dprev, e.a[l], 1, e.arg[l], C, Hp, Hb, 1)
+            dy = self._unpool(dprev, e.a[l], 1, e.arg[l], C, Hp, Hb, 1, f"dy{l}")
             self._wgrad(net, l, dy, e.a[l - 1], -(Hb + 1))
             Cin = e.a[l - 1].shape[3]
             dprev = torch.empty(B, 2 * Hp, 2 * Hp, Cin, dtype=torch.bfloat16, device=self.dev)
