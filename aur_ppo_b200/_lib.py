@@ -187,6 +187,9 @@ def lib() -> ctypes.CDLL:
     L.aur_equiv_conv0.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
     L.aur_wgrad3x3_bf16.restype = c_int
     L.aur_wgrad3x3_bf16.argtypes = [c_int32, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]
+    L.aur_unpool_relu_bwd_colsum.restype = c_int
+    L.aur_unpool_relu_bwd_colsum.argtypes = [c_int32] * 4 + [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                             c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     L.aur_unpool_relu_bwd.restype = c_int
     L.aur_unpool_relu_bwd.argtypes = [c_int32] * 4 + [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                                       c_int32, c_int32, c_int32, c_void_p]

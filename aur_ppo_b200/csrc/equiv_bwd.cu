@@ -127,10 +127,15 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---- max-pool(2) + ReLU backward: one thread per pooled pixel x 8 channels ------------------
+// colsum (nullable): the bias gradient of the layer, out[c / group] += sum over all written positions of dy[.., c] - what
+// colsum_bf16_kernel would compute from dy, taken here from registers instead of re-reading the buffer.  The grid is a
+// multiple of C / 8 threads (C / 8 divides 256), so a thread keeps one channel group for its whole grid-stride loop.
 __global__ void unpool_relu_bwd_kernel(int B, int Hp, int Wp, int C, const __nv_bfloat16* __restrict__ dpool,
                                        const __nv_bfloat16* __restrict__ act, int aHb, int aWb, int aoff,
                                        const unsigned char* __restrict__ arg, __nv_bfloat16* __restrict__ dy, int dHb, int dWb,
-                                       int doff) {
+                                       int doff, int group, float* __restrict__ colsum) {
+  __shared__ float sacc[1024];
+  float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int cg = C >> 3;
   const long long total = (long long)B * Hp * Wp * cg;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -152,12 +157,23 @@ __global__ void unpool_relu_bwd_kernel(int B, int Hp, int Wp, int C, const __nv_
       const bool pos = (as[i] & 0x7FFFu) != 0 && !(as[i] & 0x8000u);
 #pragma unroll
       for (int w = 0; w < 4; ++w) o[w][i] = (pos && ab[i] == w) ? gs[i] : (unsigned short)0;
+      if (pos && ab[i] < 4) bsum[i] += __uint_as_float((unsigned int)gs[i] << 16);
     }
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const int y = 2 * py + (w >> 1) + doff, x = 2 * px + (w & 1) + doff;
       *reinterpret_cast<uint4*>(dy + (((size_t)b * dHb + y) * dWb + x) * C + c8 * 8) = *reinterpret_cast<const uint4*>(o[w]);
     }
+  }
+  if (colsum) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.0f;
+    __syncthreads();
+    const int c8 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % cg);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (bsum[i] != 0.0f) atomicAdd(&sacc[c8 * 8 + i], bsum[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x)
+      if (sacc[i] != 0.0f) atomicAdd(colsum + i / group, sacc[i]);
   }
 }
 
@@ -799,15 +815,24 @@ extern "C" int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const voi
   return 0;
 }
 
+extern "C" int aur_unpool_relu_bwd_colsum(int32_t B, int32_t Hp, int32_t Wp, int32_t C, const void* dpool, const void* act,
+                                          int32_t aHb, int32_t aWb, int32_t aoff, const uint8_t* arg, void* dy, int32_t dHb,
+                                          int32_t dWb, int32_t doff, int32_t group, float* colsum_out, void* stream) {
+  if (B <= 0 || C % 8 != 0 || !dpool || !act || !arg || !dy) { set_error("aur_unpool_relu_bwd: bad arguments"); return AUR_ERR_ARG; }
+  if (colsum_out && (group <= 0 || C > 1024 || 256 % (C / 8) != 0)) {
+    set_error("aur_unpool_relu_bwd_colsum: needs C / 8 dividing 256, C <= 1024 and group >= 1"); return AUR_ERR_ARG;
+  }
+  const long long total = (long long)B * Hp * Wp * (C / 8);
+  unpool_relu_bwd_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+      B, Hp, Wp, C, (const __nv_bfloat16*)dpool, (const __nv_bfloat16*)act, aHb, aWb, aoff, arg, (__nv_bfloat16*)dy, dHb, dWb, doff,
+      group, colsum_out);
+  AUR_LAUNCH_OK("unpool_relu_bwd_kernel");
+  return 0;
+}
 extern "C" int aur_unpool_relu_bwd(int32_t B, int32_t Hp, int32_t Wp, int32_t C, const void* dpool, const void* act,
                                    int32_t aHb, int32_t aWb, int32_t aoff, const uint8_t* arg, void* dy, int32_t dHb,
                                    int32_t dWb, int32_t doff, void* stream) {
-  if (B <= 0 || C % 8 != 0 || !dpool || !act || !arg || !dy) { set_error("aur_unpool_relu_bwd: bad arguments"); return AUR_ERR_ARG; }
-  const long long total = (long long)B * Hp * Wp * (C / 8);
-  unpool_relu_bwd_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
-      B, Hp, Wp, C, (const __nv_bfloat16*)dpool, (const __nv_bfloat16*)act, aHb, aWb, aoff, arg, (__nv_bfloat16*)dy, dHb, dWb, doff);
-  AUR_LAUNCH_OK("unpool_relu_bwd_kernel");
-  return 0;
+  return aur_unpool_relu_bwd_colsum(B, Hp, Wp, C, dpool, act, aHb, aWb, aoff, arg, dy, dHb, dWb, doff, 1, nullptr, stream);
 }
 
 extern "C" int aur_transpose_bf16(int64_t R, int32_t C, const void* in, void* out, void* stream) {

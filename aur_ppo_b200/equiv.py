@@ -170,7 +170,7 @@ class EquivActorCritic:
             _chk(_lib.lib().aur_relu_mask_bf16(g.numel(), g.data_ptr(), _ptr(ref), out.data_ptr(), _stream()), "aur_relu_mask_bf16")
         return out
 
-    def _wgrad(self, net: str, l: int, dy_buf: torch.Tensor, x_buf: torch.Tensor, base_off: int):
+    def _wgrad(self, net: str, l: int, dy_buf: torch.Tensor, x_buf: torch.Tensor, base_off: int, bias_done: bool = False):
         """dpsi_l, dbias_l from the haloed output-gradient buffer and the layer's input buffer."""
         L = _lib.lib()
         B, Hb, Wb, Cin = x_buf.shape
@@ -181,7 +181,8 @@ class EquivActorCritic:
             _chk(L.aur_wgrad3x3_bf16(Cout, Cin, Q, dy_buf.data_ptr(), x_buf.data_ptr(), base_off, Wb, dw.data_ptr(), 0, _stream()),
                  "aur_wgrad3x3_bf16")
         self._store_wgrad(net, l, dw, Cout, Cin)
-        self._store_bgrad(net, l, dy_buf.reshape(Q, Cout), Q, Cout)
+        if not bias_done:
+            self._store_bgrad(net, l, dy_buf.reshape(Q, Cout), Q, Cout)
 
     # dense gradient of a layer's contraction matrix [Cout, 9, Cin] (layer 6: [Cout, 9 * Cin]) -> the free parameters
     def _store_wgrad(self, net: str, l: int, dw: torch.Tensor, Cout: int, Cin: int):
@@ -213,12 +214,24 @@ class EquivActorCritic:
             self._zcache[key] = t
         return t
 
-    def _unpool(self, dpool, act, aoff, arg, C, Hp, dHb, doff, tag: str):
+    def _unpool(self, dpool, act, aoff, arg, C, Hp, dHb, doff, tag: str, bias=None):
+        """bias = (net, l): also accumulate that layer's bias gradient from the values written (no second pass over dy)."""
         out = self._halo_zeros(tag, self.B, dHb, dHb, C)
+        acc, group = self._bgrad_begin(bias[0], bias[1], C) if bias is not None else (None, 1)
         with torch.cuda.device(self.dev):
-            _chk(_lib.lib().aur_unpool_relu_bwd(self.B, Hp, Hp, C, dpool.data_ptr(), act.data_ptr(), act.shape[1], act.shape[2],
-                                                aoff, arg.data_ptr(), out.data_ptr(), dHb, dHb, doff, _stream()), "aur_unpool_relu_bwd")
+            _chk(_lib.lib().aur_unpool_relu_bwd_colsum(self.B, Hp, Hp, C, dpool.data_ptr(), act.data_ptr(), act.shape[1], act.shape[2],
+                                                       aoff, arg.data_ptr(), out.data_ptr(), dHb, dHb, doff, group, _ptr(acc), _stream()),
+                 "aur_unpool_relu_bwd_colsum")
+        if bias is not None:
+            self._bgrad_end(bias[0], bias[1], acc)
         return out
+
+    # where a fused bias-gradient accumulation lands: (fp32 accumulator [C / group], group); _bgrad_end finalises it
+    def _bgrad_begin(self, net: str, l: int, C: int):
+        return self.grads[f"{net}.enc{l}.bias"], 4
+
+    def _bgrad_end(self, net: str, l: int, acc: torch.Tensor):
+        pass
 
     def _encoder_backward(self, net: str, state, obs, dfeat: torch.Tensor):
         """dfeat: fp32 [B, FEAT] gradient wrt the encoder output (post-ReLU features)."""
@@ -233,8 +246,8 @@ class EquivActorCritic:
         da6 = self._cast(tc_gemm_bf16(dz6, wm6t), None).reshape(B, 3, 3, CH[5])
         # layer 5 (pad 0, pooled): un-pool into a 2-halo buffer (backward-data) and into the input geometry (weights)
         dy5_d = self._unpool(da6, e.a[5], 0, e.arg[5], CH[5], 3, 10, 2, "dy5_d")
-        dy5_w = self._unpool(da6, e.a[5], 0, e.arg[5], CH[5], 3, 8, 0, "dy5_w")
-        self._wgrad(net, 5, dy5_w, e.a[4], 0)
+        dy5_w = self._unpool(da6, e.a[5], 0, e.arg[5], CH[5], 3, 8, 0, "dy5_w", bias=(net, 5))
+        self._wgrad(net, 5, dy5_w, e.a[4], 0, bias_done=True)
         dy4 = self._halo_zeros("dy4", B, 10, 10, CH[4])
         conv3x3_bf16(dy5_d, w[f"{net}.5"][1], None, 3, dy4, 1, None, relu_ref=e.a[4], ref_off=0)   # x ReLU mask of layer 4
         # layer 4 (pad 1, ReLU only)
@@ -246,8 +259,8 @@ class EquivActorCritic:
         for l, Hp in ((3, 8), (2, 16), (1, 32)):
             C = CH[l]
             Hb = 2 * Hp + 2
-            dy = self._unpool(dprev, e.a[l], 1, e.arg[l], C, Hp, Hb, 1, f"dy{l}")
-            self._wgrad(net, l, dy, e.a[l - 1], -(Hb + 1))
+            dy = self._unpool(dprev, e.a[l], 1, e.arg[l], C, Hp, Hb, 1, f"dy{l}", bias=(net, l))
+            self._wgrad(net, l, dy, e.a[l - 1], -(Hb + 1), bias_done=True)
             Cin = e.a[l - 1].shape[3]
             dprev = torch.empty(B, 2 * Hp, 2 * Hp, Cin, dtype=torch.bfloat16, device=self.dev)
             conv3x3_bf16(dy, w[f"{net}.{l}"][1], None, 0, dprev, 0)

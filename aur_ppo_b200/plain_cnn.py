@@ -122,6 +122,12 @@ class PlainActorCritic(EquivActorCritic):
             _chk(_lib.lib().aur_colsum_bf16(Q, Cout, dy2d.data_ptr(), 1, out.data_ptr(), _stream()), "aur_colsum_bf16")
         self.grads[conv_key(net, l, "bias")].copy_(out[:REAL[l]])
 
+    def _bgrad_begin(self, net: str, l: int, C: int):
+        return torch.zeros(C, device=self.dev), 1
+
+    def _bgrad_end(self, net: str, l: int, acc: torch.Tensor):
+        self.grads[conv_key(net, l, "bias")].copy_(acc[:REAL[l]])
+
     def _layer0_wgrad(self, net: str, state, obs, dprev, e):
         with torch.cuda.device(self.dev):
             _chk(_lib.lib().aur_equiv_conv0_wgrad(obs.data_ptr(), state.data_ptr(), dprev.data_ptr(), e.a[0].data_ptr(),

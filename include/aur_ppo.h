@@ -366,6 +366,12 @@ int aur_unpool_relu_bwd(int32_t B, int32_t Hp, int32_t Wp, int32_t C, const void
                         int32_t aWb, int32_t aoff, const uint8_t* arg, void* dy, int32_t dHb, int32_t dWb, int32_t doff,
                         void* stream);
 
+/* The same, also accumulating the layer's bias gradient from the values it writes: colsum_out[c / group] += sum of dy[.., c]
+ * (what aur_colsum_bf16 would compute by re-reading dy).  colsum_out NULL: plain un-pool.  Needs C / 8 dividing 256. */
+int aur_unpool_relu_bwd_colsum(int32_t B, int32_t Hp, int32_t Wp, int32_t C, const void* dpool, const void* act, int32_t aHb,
+                               int32_t aWb, int32_t aoff, const uint8_t* arg, void* dy, int32_t dHb, int32_t dWb, int32_t doff,
+                               int32_t group, float* colsum_out, void* stream);
+
 int aur_transpose_bf16(int64_t R, int32_t C, const void* in, void* out, void* stream);   /* [R][C] -> [C][R] */
 
 /* adjoint of aur_equiv_expand_regular: dpsi [Fo,Fi,4,3,3] += projection of dwmat [Fo*4][9][Fi*4] */
