@@ -379,7 +379,7 @@ static int check_policy(const aur_policy_desc& p, const char* who, int io_max) {
 // block down to 64 threads first; else read them from global memory.  Returns the smem bytes, sets block / in_smem.
 static size_t dyn_launch_shape(const aur_policy_desc& p, int& block, int& in_smem) {
   const size_t pf = (size_t)dyn_policy_smem_floats(p.obs_dim, p.hidden_dim, p.num_layers, p.act_dim);
-  const size_t limit = 200 * 1024;
+  const size_t limit = 226 * 1024;      // 227 KB is the per-CTA maximum on sm_100; 64 hidden-128 columns + both nets need 204 KB
   for (int b = block; b >= 64; b -= 32) {
     const size_t need = (pf + (size_t)2 * p.hidden_dim * b) * sizeof(float);
     if (need <= limit) { block = b; in_smem = 1; return need; }
