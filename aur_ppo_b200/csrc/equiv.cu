@@ -15,6 +15,8 @@
 //        layer's haloed buffer, 2-bit arg-max per pooled element for the backward pass.
 // The same kernel computes backward-data (input = haloed output gradient, weights = transposed,
 // tap-flipped filter, linear epilogue).
+#include <stdlib.h>
+
 #include "tc.cuh"
 
 namespace aur {
@@ -47,19 +49,31 @@ struct ConvDev {
 // across items and the accumulator is double-buffered in TMEM (2 x 128 columns), so the epilogue of item i (TMEM ->
 // bias / ReLU / pool -> bf16 stores) overlaps the TMA + MMA main loop of item i+1.
 constexpr int CV_THREADS = 384;   // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 epilogue (two per TMEM lane quarter)
-template <int CV_BN>
+// SWAP (pooled layers with shallow K, BN = 128): the operand roles are exchanged - D[m = output channel][n = pixel] - so a
+// TMEM lane is a channel and a thread's 32 accumulator columns are 32 pixels = eight complete 2x2 pool windows.  Bias is
+// one register, ReLU + max-pool + arg-max are register compares (no shuffles, no per-element bias loads): ~3 instructions
+// per element instead of ~12, which is what bounded the pooled layers 1-2 (20 / 39 % tensor-pipe activity).
+// RESB (Cin = 64, Cout <= 128: the pooled layer 1): the whole weight matrix (9 taps x 128 x 64 bf16 = 144 KB) is loaded
+// into shared memory once per CTA instead of once per pixel tile - at 9 K-steps per tile half of the L2 -> SM traffic
+// was the same weights over and over (9.2 GB of L2 reads per launch, 11.6 TB/s: the layer was L2-bandwidth bound).
+constexpr int CV_RESB_STAGES = 4;
+constexpr size_t CV_RESB_SMEM = (size_t)CV_RESB_STAGES * CV_A_BYTES + 9 * (128 * CV_BK * 2) + 1024 + 256;
+template <int CV_BN, bool SWAP = false, bool RESB = false>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvDev a) {
+  static_assert(!SWAP || CV_BN == 128, "the swapped epilogue is built for 128 x 128 accumulators");
+  static_assert(!RESB || SWAP, "resident weights come with the channel-major kernel");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
-  constexpr int CV_STAGES = CvCfg<CV_BN>::STAGES, CV_B_BYTES = CvCfg<CV_BN>::B_BYTES;
+  constexpr int CV_STAGES = RESB ? CV_RESB_STAGES : CvCfg<CV_BN>::STAGES, CV_B_BYTES = CvCfg<CV_BN>::B_BYTES;
   unsigned char* sA = smem;
-  unsigned char* sB = smem + CV_STAGES * CV_A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + CV_STAGES * CV_B_BYTES);
+  unsigned char* sB = smem + CV_STAGES * CV_A_BYTES;       // RESB: nine resident tap blocks instead of a ring
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (RESB ? 9 : CV_STAGES) * CV_B_BYTES);
   uint64_t* empty = full + CV_STAGES;
   uint64_t* tmem_full = empty + CV_STAGES;       // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* bres = tmem_empty + 2;               // RESB: the resident weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cchunks = a.Cin / CV_BK;
@@ -77,6 +91,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < CV_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+    mbar_init(bres, 1);
     mbar_fence_init();
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
@@ -90,6 +105,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     // ===== TMA producer: per item, K loop over (tap, channel chunk); the ring index runs across items =====
     uint32_t kg = 0;
+    if constexpr (RESB) {
+      if (blockIdx.x < items) {
+        mbar_arrive_expect_tx(bres, 9 * CV_B_BYTES);
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(sB + tap * CV_B_BYTES, &tmB, tap * a.Cin, 0, bres);
+      }
+    }
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
       int b0, y0, x0, n0;
       decode(item, b0, y0, x0, n0);
@@ -99,9 +120,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int s = kg % CV_STAGES;
           const uint32_t ph = (kg / CV_STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], CV_A_BYTES + CV_B_BYTES);
+          mbar_arrive_expect_tx(&full[s], RESB ? CV_A_BYTES : CV_A_BYTES + CV_B_BYTES);
           tma_load_4d(sA + s * CV_A_BYTES, &tmA, cc * CV_BK, x0 + dx, y0 + dy, b0, &full[s]);
-          tma_load_2d(sB + s * CV_B_BYTES, &tmB, tap * a.Cin + cc * CV_BK, n0, &full[s]);
+          if constexpr (!RESB) tma_load_2d(sB + s * CV_B_BYTES, &tmB, tap * a.Cin + cc * CV_BK, n0, &full[s]);
         }
       }
     }
@@ -109,6 +130,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===== MMA issuer: accumulator (it & 1) once the epilogue has drained its previous use =====
     constexpr uint32_t idesc = instr_desc(FMT_BF16, CV_BM, CV_BN, 0, 0);
     uint32_t kg = 0, it = 0;
+    if constexpr (RESB) {
+      if (blockIdx.x < items) { mbar_wait(bres, 0u); fence_after_sync(); }
+    }
     for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
       mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
@@ -118,13 +142,67 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t ph = (kg / CV_STAGES) & 1u;
         mbar_wait(&full[s], ph);
         fence_after_sync();
-        const uint64_t ad = smem_desc_k_sw128(sA + s * CV_A_BYTES), bd = smem_desc_k_sw128(sB + s * CV_B_BYTES);
+        const uint64_t ad = smem_desc_k_sw128(sA + s * CV_A_BYTES), bd = smem_desc_k_sw128(sB + (RESB ? kb : s) * CV_B_BYTES);
 #pragma unroll
-        for (int k = 0; k < CV_BK / 16; ++k)
-          mma_f16(tmem_d + acc * CV_BN, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+        for (int k = 0; k < CV_BK / 16; ++k) {
+          if constexpr (SWAP) mma_f16(tmem_d + acc * CV_BN, bd + (uint64_t)(2 * k), ad + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          else mma_f16(tmem_d + acc * CV_BN, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+        }
         mma_commit(&empty[s]);
       }
       mma_commit(&tmem_full[acc]);
+    }
+  } else if (SWAP && warp >= 4) {
+    // ===== swapped epilogue: lane = output channel, columns = the tile's 128 pixels; bias + ReLU + 2x2 max-pool in registers =====
+    const int q = (warp - 4) & 3, phalf = (warp - 4) >> 2;     // TMEM lane quarter (32 channels), half of the pixel columns
+    uint32_t it = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      int b0, y0, x0, n0;
+      decode(item, b0, y0, x0, n0);
+      const uint32_t acc = it & 1u;
+      const int ch = n0 + 32 * q + lane;
+      const bool ch_ok = ch < a.Cout;
+      const float bias = (a.bias && ch_ok) ? __ldg(a.bias + ch) : 0.0f;
+      const int Hp = a.Ho >> 1, Wp = a.Wo >> 1;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
+      fence_after_sync();
+#pragma unroll 1
+      for (int c = 64 * phalf; c < 64 * (phalf + 1); c += 32) {
+        float v[32];
+        tmem_ld32(tmem_d + acc * CV_BN + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+        if (c + 32 == 64 * (phalf + 1)) {                 // last read of this accumulator: hand it back to the MMA warp
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if (!ch_ok) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias, 0.0f);
+        // pixel column p = (img * TH + yy) * TW + xx; 32 columns are 2 rows x 16 (TW = 16) or 4 rows x 8 (TW = 8)
+        auto emit = [&](int img, int yy, int xx, float v0, float v1, float v2, float v3) {
+          const int b = b0 + img, y = y0 + yy, x = x0 + xx;
+          if (b >= a.B || y >= a.Ho || x >= a.Wo) return;
+          float m = v0; unsigned int w = 0u;               // first maximum in (y, x) scan order wins ties (torch)
+          if (v1 > m) { m = v1; w = 1u; }
+          if (v2 > m) { m = v2; w = 2u; }
+          if (v3 > m) { m = v3; w = 3u; }
+          const size_t pix = ((size_t)b * a.oHb + (y >> 1) + a.ooff) * a.oWb + (x >> 1) + a.ooff;
+          a.out[pix * a.Cout + ch] = __float2bfloat16_rn(m);
+          if (a.pool_arg) a.pool_arg[(((size_t)b * Hp + (y >> 1)) * Wp + (x >> 1)) * a.Cout + ch] = (unsigned char)w;
+        };
+        if (a.TW == 16) {
+          const int yy = c >> 4;                          // rows yy, yy + 1 of image 0
+#pragma unroll
+          for (int k = 0; k < 8; ++k) emit(0, yy, 2 * k, v[2 * k], v[2 * k + 1], v[16 + 2 * k], v[16 + 2 * k + 1]);
+        } else {
+          const int img = c >> 6, yy = (c & 63) >> 3;     // rows yy .. yy + 3 of image img
+#pragma unroll
+          for (int rp = 0; rp < 2; ++rp)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              emit(img, yy + 2 * rp, 2 * k, v[16 * rp + 2 * k], v[16 * rp + 2 * k + 1], v[16 * rp + 8 + 2 * k], v[16 * rp + 8 + 2 * k + 1]);
+        }
+      }
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> (bias, ReLU, pool) -> bf16 NHWC =====
@@ -390,6 +468,13 @@ extern "C" int aur_equiv_conv0(const float* obs, const float* state, const float
   return 0;
 }
 
+// AUR_CONV_SWAP=0 keeps the pixel-major epilogue everywhere (A/B comparison)
+static bool conv_swap_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AUR_CONV_SWAP"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   using namespace aur;
   using namespace aur::tc;
@@ -418,7 +503,10 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   const uint32_t bA[4] = {CV_BK, (uint32_t)d.TW, (uint32_t)d.TH, (uint32_t)d.NIMG};
   const uint64_t dB[2] = {(uint64_t)9 * c.Cin, (uint64_t)c.Cout};
   const uint64_t sB[1] = {(uint64_t)9 * c.Cin * 2};
-  const bool wide = c.Cout % 256 == 0;
+  // pooled layers with a shallow contraction (K = 9 x 64 / 9 x 128) are epilogue-bound: channel-major accumulator there
+  const bool swap = c.epilogue == 2 && c.Cin == 64 && conv_swap_enabled();       // Cin 128 (layer 2) is faster on 256-wide tiles
+  const bool resb = swap && c.Cout <= 128;
+  const bool wide = !swap && c.Cout % 256 == 0;
   const int BN = wide ? 256 : 128;
   const uint32_t bB[2] = {CV_BK, (uint32_t)BN};
   int rc;
@@ -428,13 +516,17 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   if (!attr) {
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<128>::SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<256>::SMEM));
+    AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<128>::SMEM));
+    AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_RESB_SMEM));
     attr = true;
   }
   d.pix_tiles = (int)(img_groups * d.tiles_y * d.tiles_x);
   d.n_tiles = (c.Cout + BN - 1) / BN;
   const long long items = (long long)d.pix_tiles * d.n_tiles;
   const unsigned grid = (unsigned)(items < sm_count() ? items : sm_count());
-  if (wide) conv_igemm_kernel<256><<<grid, CV_THREADS, CvCfg<256>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
+  if (resb) conv_igemm_kernel<128, true, true><<<grid, CV_THREADS, CV_RESB_SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
+  else if (swap) conv_igemm_kernel<128, true><<<grid, CV_THREADS, CvCfg<128>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
+  else if (wide) conv_igemm_kernel<256><<<grid, CV_THREADS, CvCfg<256>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
   else conv_igemm_kernel<128><<<grid, CV_THREADS, CvCfg<128>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
   AUR_LAUNCH_OK("conv_igemm_kernel");
   return 0;

@@ -25,7 +25,11 @@ def test_expand_matches_oracle_expansion():
 
 
 @pytest.mark.parametrize("B,H,Fi,Fo,pad,pool", [(3, 16, 16, 32, 1, True), (2, 64, 16, 32, 1, True), (5, 8, 32, 64, 1, False),
-                                                (4, 8, 64, 32, 0, True), (2, 32, 32, 16, 1, False)])
+                                                (4, 8, 64, 32, 0, True), (2, 32, 32, 16, 1, False),
+                                                # channel-major pooled epilogue (Cin <= 128): 8-wide tiles with two images,
+                                                # ragged image count, two channel blocks, a 64-channel block, odd tile grid
+                                                (5, 8, 16, 32, 1, True), (3, 8, 32, 16, 1, True), (2, 16, 32, 64, 1, True),
+                                                (3, 24, 16, 16, 1, True), (1, 32, 32, 48, 1, True)])
 def test_conv_layer_matches_conv2d(B, H, Fi, Fo, pad, pool):
     g = torch.Generator().manual_seed(B * 100 + H)
     Cin, Cout = Fi * 4, Fo * 4
