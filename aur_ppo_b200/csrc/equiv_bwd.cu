@@ -54,6 +54,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   long long kb_hi = kb_lo + per;
   if (kb_hi > nkb_total) kb_hi = nkb_total;
   const int nkb = kb_hi > kb_lo ? (int)(kb_hi - kb_lo) : 0;
+  const bool c64 = Cin <= 64;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -75,14 +76,18 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t ph = (i / WG_STAGES) & 1u;
         const long long k0 = (kb_lo + i) * WG_BK;
         mbar_wait(&empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[s], WG_A_BYTES + WG_TAPS * WG_B_BYTES);
+        mbar_arrive_expect_tx(&full[s], WG_A_BYTES + WG_TAPS * (c64 ? WG_B_BYTES / 2 : WG_B_BYTES));
         unsigned char* a = sA + s * WG_A_BYTES;
         tma_load_2d(a, &tmA, m0, (int)k0, &full[s]);
         tma_load_2d(a + 8192, &tmA, m0 + 64, (int)k0, &full[s]);
         for (int dx = 0; dx < WG_TAPS; ++dx) {
-          unsigned char* b = sB + (s * WG_TAPS + dx) * WG_B_BYTES;
-          tma_load_2d(b, &tmB, n0, (int)(k0 + off + dx), &full[s]);
-          tma_load_2d(b + 8192, &tmB, n0 + 64, (int)(k0 + off + dx), &full[s]);
+          if (c64) {            // one 64-channel box per tap, the three taps 8192 B apart: ONE N = 192 operand
+            tma_load_2d(sB + s * WG_TAPS * WG_B_BYTES + dx * 8192, &tmB, 0, (int)(k0 + off + dx), &full[s]);
+          } else {
+            unsigned char* b = sB + (s * WG_TAPS + dx) * WG_B_BYTES;
+            tma_load_2d(b, &tmB, n0, (int)(k0 + off + dx), &full[s]);
+            tma_load_2d(b + 8192, &tmB, n0 + 64, (int)(k0 + off + dx), &full[s]);
+          }
         }
       }
     } else if (warp == 1 && lane == 0) {
@@ -93,6 +98,18 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&full[s], ph);
         fence_after_sync();
         const uint64_t ad = smem_desc_mn_sw128(sA + s * WG_A_BYTES, 8192, 1024);
+        if (c64) {
+          // Cin <= 64: the three taps' input tiles are three 64-channel groups of one MN-major operand (LBO = 8192 B), so
+          // one N = 192 MMA per 16 pixel rows replaces three N = 128 ones (half of whose columns were zero padding) and
+          // the gradient tile is read from shared memory once instead of three times
+          constexpr uint32_t idesc192 = instr_desc(FMT_BF16, WG_BM, 192, 1, 1);
+          const uint64_t bd = smem_desc_mn_sw128(sB + s * WG_TAPS * WG_B_BYTES, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < WG_BK / 16; ++k)
+            mma_f16(tmem_d, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc192, (i | k) != 0);
+          mma_commit(&empty[s]);
+          continue;
+        }
         for (int dx = 0; dx < WG_TAPS; ++dx) {
           const uint64_t bd = smem_desc_mn_sw128(sB + (s * WG_TAPS + dx) * WG_B_BYTES, 8192, 1024);
 #pragma unroll
@@ -107,9 +124,10 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tmem_full, 0);
       fence_after_sync();
       const int co = m0 + 32 * q + lane;
+      const int ncol = c64 ? 64 : WG_BN;                // accumulator columns per tap
 #pragma unroll 1
-      for (int cc = 0; cc < WG_TAPS * WG_BN; cc += 32) {
-        const int dx = cc / WG_BN, c = cc - dx * WG_BN, tap = dy * 3 + dx;
+      for (int cc = 0; cc < WG_TAPS * ncol; cc += 32) {
+        const int dx = cc / ncol, c = cc - dx * ncol, tap = dy * 3 + dx;
         float v[32];
         tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)cc, v);
         if (co < Cout) {
