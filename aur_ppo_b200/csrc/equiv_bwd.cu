@@ -110,11 +110,17 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mma_commit(&empty[s]);
           continue;
         }
-        for (int dx = 0; dx < WG_TAPS; ++dx) {
-          const uint64_t bd = smem_desc_mn_sw128(sB + (s * WG_TAPS + dx) * WG_B_BYTES, 8192, 1024);
+        {
+          // taps dx = 0, 1 are adjacent in the stage (four 64-channel groups, 8192 B apart): one N = 256 MMA feeds both
+          // accumulators from a single read of the gradient tile; tap 2 follows as N = 128
+          constexpr uint32_t idesc256 = instr_desc(FMT_BF16, WG_BM, 256, 1, 1);
+          const uint64_t bd01 = smem_desc_mn_sw128(sB + (s * WG_TAPS) * WG_B_BYTES, 8192, 1024);
+          const uint64_t bd2 = smem_desc_mn_sw128(sB + (s * WG_TAPS + 2) * WG_B_BYTES, 8192, 1024);
 #pragma unroll
-          for (int k = 0; k < WG_BK / 16; ++k)      // 16 pixel rows per MMA = 2048 B = 128 x 16 B
-            mma_f16(tmem_d + dx * WG_BN, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (i | k) != 0);
+          for (int k = 0; k < WG_BK / 16; ++k) {    // 16 pixel rows per MMA = 2048 B = 128 x 16 B
+            mma_f16(tmem_d, ad + (uint64_t)(128 * k), bd01 + (uint64_t)(128 * k), idesc256, (i | k) != 0);
+            mma_f16(tmem_d + 2 * WG_BN, ad + (uint64_t)(128 * k), bd2 + (uint64_t)(128 * k), idesc, (i | k) != 0);
+          }
         }
         mma_commit(&empty[s]);
       }
