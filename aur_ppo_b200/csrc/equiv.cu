@@ -27,7 +27,7 @@ namespace tc {
 constexpr int CV_BM = 128, CV_BK = 64;
 constexpr int CV_A_BYTES = CV_BM * CV_BK * 2;
 template <int BN> struct CvCfg {
-  static constexpr int STAGES = BN == 128 ? 6 : 4;
+  static constexpr int STAGES = BN == 64 ? 8 : (BN == 128 ? 6 : 4);      // 192 KB of operand stages in every shape
   static constexpr int B_BYTES = BN * CV_BK * 2;
   static constexpr size_t SMEM = (size_t)STAGES * (CV_A_BYTES + B_BYTES) + 1024 + 256;
 };
@@ -507,7 +507,8 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   const bool swap = c.epilogue == 2 && c.Cin == 64 && conv_swap_enabled();       // Cin 128 (layer 2) is faster on 256-wide tiles
   const bool resb = swap && c.Cout <= 128;
   const bool wide = !swap && c.Cout % 256 == 0;
-  const int BN = wide ? 256 : 128;
+  const bool narrow = !swap && c.Cout <= 64;     // e.g. the backward-data convolution into the 64-channel layer-0 output: N = 64 MMAs
+  const int BN = wide ? 256 : (narrow ? 64 : 128);
   const uint32_t bB[2] = {CV_BK, (uint32_t)BN};
   int rc;
   if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, c.in, dA, sA, bA))) return rc;
@@ -516,6 +517,7 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   if (!attr) {
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<128>::SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<256>::SMEM));
+    AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<64>::SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<128>::SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_RESB_SMEM));
     attr = true;
@@ -527,6 +529,7 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   if (resb) conv_igemm_kernel<128, true, true><<<grid, CV_THREADS, CV_RESB_SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
   else if (swap) conv_igemm_kernel<128, true><<<grid, CV_THREADS, CvCfg<128>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
   else if (wide) conv_igemm_kernel<256><<<grid, CV_THREADS, CvCfg<256>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
+  else if (narrow) conv_igemm_kernel<64><<<grid, CV_THREADS, CvCfg<64>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
   else conv_igemm_kernel<128><<<grid, CV_THREADS, CvCfg<128>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
   AUR_LAUNCH_OK("conv_igemm_kernel");
   return 0;
