@@ -210,6 +210,10 @@ def lib() -> ctypes.CDLL:
     L.aur_equiv_head_eval.restype = c_int
     L.aur_equiv_head_eval.argtypes = [c_int32] + [c_void_p] * 7 + [c_uint64, c_uint64, ctypes.POINTER(ctypes.c_float)] + \
         [c_void_p] * 8
+    L.aur_plain_conv0.restype = c_int
+    L.aur_plain_conv0.argtypes = [c_void_p] * 4 + [c_int32, c_void_p, c_void_p, c_void_p]
+    L.aur_plain_conv0_wgrad.restype = c_int
+    L.aur_plain_conv0_wgrad.argtypes = [c_void_p] * 5 + [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
     L.aur_plain_head_eval.restype = c_int
     L.aur_plain_head_eval.argtypes = [c_int32] + [c_void_p] * 8 + [c_uint64, c_uint64, ctypes.POINTER(ctypes.c_float)] + \
         [c_void_p] * 8

@@ -22,6 +22,9 @@ constexpr int C0O_B = C0O_A + 4 * C0_A_BYTES;           // [w 4][hi, mid]
 constexpr int C0O_BAR = C0O_B + 8 * C0_B_BYTES;
 constexpr size_t C0_SMEM = C0O_BAR + 64 + 1024;
 
+// PLAIN: only channels 0..15 of the 64-channel layer-0 buffers carry data (aur_plain_conv0), so only the first two channel
+// octets are read; rows 0..15 of the result are the plain filter gradients.
+template <bool PLAIN>
 __global__ void __launch_bounds__(256, 3)
 conv0_wgrad_tc_kernel(const float* __restrict__ obs, const float* __restrict__ state, const __nv_bfloat16* __restrict__ da1,
                       const __nv_bfloat16* __restrict__ a1 /*[B,66,66,64]*/, const unsigned char* __restrict__ arg, int B,
@@ -94,7 +97,7 @@ conv0_wgrad_tc_kernel(const float* __restrict__ obs, const float* __restrict__ s
       const long long pix = pix0 + p;
       uint4 gq = make_uint4(0u, 0u, 0u, 0u), aq = gq;
       uint2 wq = make_uint2(0u, 0u);
-      if (pix < npix) {
+      if (pix < npix && (!PLAIN || c < 2)) {
         const int px = (int)(pix & 63), py = (int)((pix >> 6) & 63), b = (int)(pix >> 12);
         gq = __ldcs(reinterpret_cast<const uint4*>(da1 + (size_t)pix * 64 + c * 8));
         aq = __ldcs(reinterpret_cast<const uint4*>(a1 + (((size_t)b * 66 + py + 1) * 66 + px + 1) * 64 + c * 8));
@@ -151,18 +154,24 @@ conv0_wgrad_tc_kernel(const float* __restrict__ obs, const float* __restrict__ s
 }
 
 int launch_conv0_wgrad_tc(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg, int B,
-                          float* dw0, float* dbias_ch, cudaStream_t s) {
+                          float* dw0, float* dbias_ch, cudaStream_t s, bool plain) {
   static bool attr = false;
   if (!attr) {
-    AUR_CUDA_OK(cudaFuncSetAttribute(conv0_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C0_SMEM));
-    AUR_CUDA_OK(cudaFuncSetAttribute(conv0_wgrad_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    AUR_CUDA_OK(cudaFuncSetAttribute(conv0_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C0_SMEM));
+    AUR_CUDA_OK(cudaFuncSetAttribute(conv0_wgrad_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    AUR_CUDA_OK(cudaFuncSetAttribute(conv0_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C0_SMEM));
+    AUR_CUDA_OK(cudaFuncSetAttribute(conv0_wgrad_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   const long long nblk = ((long long)B * 4096 + C0_PIX - 1) / C0_PIX;
   long long grid = 3LL * sm_count();
   if (grid > nblk) grid = nblk;
-  conv0_wgrad_tc_kernel<<<(unsigned)grid, 256, C0_SMEM, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg, B,
-                                                             dw0, dbias_ch);
+  if (plain)
+    conv0_wgrad_tc_kernel<true><<<(unsigned)grid, 256, C0_SMEM, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg,
+                                                                     B, dw0, dbias_ch);
+  else
+    conv0_wgrad_tc_kernel<false><<<(unsigned)grid, 256, C0_SMEM, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg,
+                                                                      B, dw0, dbias_ch);
   AUR_LAUNCH_OK("conv0_wgrad_tc_kernel");
   return 0;
 }

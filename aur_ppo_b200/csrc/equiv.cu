@@ -346,6 +346,9 @@ __global__ void expand_bias_kernel(const float* __restrict__ bias_f, int F, floa
 // 2x2 max pool.  K = 18 is far too small for the tensor pipe (and the layer is 1.3 % of the FLOPs):
 // direct convolution, one thread per pooled pixel x 16 output channels, weights in shared memory.
 // obs [B,1,128,128] fp32, state [B] fp32, psi [16,2,3,3], bias [16] -> out [B,66,66,64] bf16 interior.
+// PLAIN (base_encoder layer 0, src/nets/base_cnns.py:25): the 16 filters are used as they are and land in channels 0..15 of
+// the 64-channel buffer (the other 48 stay zero from allocation), one 16-channel group per pooled pixel instead of four.
+template <bool PLAIN>
 __global__ void __launch_bounds__(256)
 conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ state, const float* __restrict__ psi,
                     const float* __restrict__ bias_f, int B, __nv_bfloat16* __restrict__ out, unsigned char* __restrict__ pool_arg) {
@@ -357,22 +360,27 @@ conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ sta
     float v = 0.0f;
     if (rem < 18) {
       const int ci = rem / 9, tap = rem - ci * 9;
-      const int o = co >> 2, r = co & 3, y = tap / 3, x = tap - 3 * y;
-      int ys, xs;
-      rot_src(r, y, x, ys, xs);
-      v = psi[((o * 2 + ci) * 3 + ys) * 3 + xs];
+      if (PLAIN) {
+        v = co < 16 ? psi[(co * 2 + ci) * 9 + tap] : 0.0f;
+      } else {
+        const int o = co >> 2, r = co & 3, y = tap / 3, x = tap - 3 * y;
+        int ys, xs;
+        rot_src(r, y, x, ys, xs);
+        v = psi[((o * 2 + ci) * 3 + ys) * 3 + xs];
+      }
     } else if (rem == 18) {
-      v = bias_f[co >> 2];
+      v = PLAIN ? (co < 16 ? bias_f[co] : 0.0f) : bias_f[co >> 2];
     }
     sW[co >> 1][rem][co & 1] = v;
   }
   __syncthreads();
-  const long long total = (long long)B * 64 * 64 * 4;       // pooled pixels x 4 channel groups of 16
+  const long long total = (long long)B * 64 * 64 * (PLAIN ? 1 : 4);       // pooled pixels x channel groups of 16
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     // px fastest, then the channel group: a warp shares its weights (broadcast loads) and reads adjacent pixels
     long long rr = e;
     const int px = (int)(rr & 63); rr >>= 6;
-    const int cg = (int)(rr & 3); rr >>= 2;
+    int cg = 0;
+    if (!PLAIN) { cg = (int)(rr & 3); rr >>= 2; }
     const int py = (int)(rr & 63); rr >>= 6;
     const int b = (int)rr;
     const float st = state[b];
@@ -463,8 +471,21 @@ extern "C" int aur_equiv_conv0(const float* obs, const float* state, const float
   const long long total = (long long)B * 64 * 64 * 4;
   long long grid = (total + 255) / 256;
   if (grid > 148 * 32) grid = 148 * 32;
-  conv0_direct_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, state, psi, bias_f, B, (__nv_bfloat16*)out, pool_arg);
+  conv0_direct_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, state, psi, bias_f, B, (__nv_bfloat16*)out, pool_arg);
   AUR_LAUNCH_OK("conv0_direct_kernel");
+  return 0;
+}
+
+extern "C" int aur_plain_conv0(const float* obs, const float* state, const float* weight, const float* bias, int32_t B,
+                               void* out, uint8_t* pool_arg, void* stream) {
+  using namespace aur;
+  using namespace aur::tc;
+  if (!obs || !state || !weight || !bias || !out || B <= 0) { set_error("aur_plain_conv0: bad arguments"); return AUR_ERR_ARG; }
+  const long long total = (long long)B * 64 * 64;
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  conv0_direct_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, state, weight, bias, B, (__nv_bfloat16*)out, pool_arg);
+  AUR_LAUNCH_OK("conv0_direct_kernel<plain>");
   return 0;
 }
 

@@ -17,7 +17,7 @@ namespace aur {
 namespace tc {
 
 int launch_conv0_wgrad_tc(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg, int B,
-                          float* dw0, float* dbias_ch, cudaStream_t s);
+                          float* dw0, float* dbias_ch, cudaStream_t s, bool plain = false);
 
 constexpr int WG_BM = 128, WG_BN = 128, WG_BK = 64, WG_STAGES = 3, WG_TAPS = 3;
 constexpr int WG_A_BYTES = WG_BM * WG_BK * 2, WG_B_BYTES = WG_BN * WG_BK * 2;
@@ -882,6 +882,23 @@ extern "C" int aur_colsum_bf16(int64_t Q, int32_t C, const void* in, int32_t gro
   if (grid > 148 * 8) grid = 148 * 8;
   colsum_bf16_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((long long)Q, C, (const __nv_bfloat16*)in, group, out);
   AUR_LAUNCH_OK("colsum_bf16_kernel");
+  return 0;
+}
+
+// layer-0 weight gradient of the plain CNN (channels 0..15 of the 64-channel buffers): rows 0..15 of the tensor-core result
+// ARE the filter gradients [16][2][3][3], entries 0..15 of the column of ones the bias gradients
+extern "C" int aur_plain_conv0_wgrad(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg,
+                                     int32_t B, float* scratch /*[64*18 + 64], zeroed by this call*/, float* dweight, float* dbias,
+                                     void* stream) {
+  if (!obs || !state || !da1 || !a1 || !arg || !scratch || !dweight || !dbias || B <= 0) {
+    set_error("aur_plain_conv0_wgrad: bad arguments"); return AUR_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  AUR_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(float) * (64 * 18 + 64), s));
+  int rc = aur::tc::launch_conv0_wgrad_tc(obs, state, da1, a1, arg, B, scratch, scratch + 64 * 18, s, true);
+  if (rc) return rc;
+  AUR_CUDA_OK(cudaMemcpyAsync(dweight, scratch, sizeof(float) * 16 * 18, cudaMemcpyDeviceToDevice, s));
+  AUR_CUDA_OK(cudaMemcpyAsync(dbias, scratch + 64 * 18, sizeof(float) * 16, cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 

@@ -134,10 +134,13 @@ class EquivActorCritic:
     def _layer0_params(self, net: str):
         return self.p[f"{net}.enc0.psi"], self.p[f"{net}.enc0.bias"]
 
-    def _encoder_forward(self, net: str, state, obs):
-        e, w = self.enc[net], self._w
+    def _conv0(self, net: str, state, obs, e):
         psi0, bias0 = self._layer0_params(net)
         equiv_conv0(obs, state, psi0, bias0, e.a[0], e.arg[0])
+
+    def _encoder_forward(self, net: str, state, obs):
+        e, w = self.enc[net], self._w
+        self._conv0(net, state, obs, e)
         for l, (epi, off) in zip(range(1, 6), [(2, 1), (2, 1), (2, 1), (1, 0), (2, 0)]):
             wm, _, b = w[f"{net}.{l}"]
             conv3x3_bf16(e.a[l - 1], wm, b, epi, e.a[l], off, e.arg[l])

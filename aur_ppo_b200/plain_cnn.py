@@ -8,10 +8,9 @@ after layers 0-3 and 5) with channels 2 -> 16 -> 32 -> 64 -> 128 -> 256 -> 256 -
 kernels (`EquivActorCritic`'s forward / backward machinery, csrc/equiv*.cu) with channel counts padded up to the
 64-channel K chunk of the implicit-GEMM convolution:
 
-* layer 0 goes through the direct equivariant kernel with the 16 plain filters passed as its 16 "fields": the kernel
-  emits 4 rotated copies per filter, copy 0 is the plain filter; layer 1's contraction matrix has zero columns for the
-  three rotated copies, so they contribute nothing forward and receive an exactly zero gradient backward, and the
-  kernel's projected filter gradient is therefore the plain one;
+* layer 0 runs the direct layer-0 kernels in their PLAIN instantiation (`aur_plain_conv0`, `aur_plain_conv0_wgrad`): the
+  16 filters land in channels 0..15 of the 64-channel buffer the 64-wide contraction of layer 1 reads, the other 48
+  channels stay zero (a first version passed the filters as 16 equivariant "fields" and paid 4x the layer-0 work);
 * layers 1-2 (16 -> 32 -> 64 real channels) run as 64 -> 64 contractions with zero padding;
 * layer 6 (3x3 valid -> 1x1) and the heads are dense GEMMs on tcgen05 (`aur_tc_gemm_bf16`).
 
@@ -76,7 +75,7 @@ class PlainActorCritic(EquivActorCritic):
         super().__init__(params, batch, lr, eps, betas)
         dev = self.dev
         # input-channel positions of each layer's real channels inside the padded activation feeding it
-        self._in_pos = [None, torch.arange(16, device=dev) * 4] + [torch.arange(REAL[l - 1], device=dev) for l in range(2, 7)]
+        self._in_pos = [None] + [torch.arange(REAL[l - 1], device=dev) for l in range(1, 7)]
 
     # ------------------------------------------------------------------ weights
     def _layer0_params(self, net: str):
@@ -128,12 +127,18 @@ class PlainActorCritic(EquivActorCritic):
     def _bgrad_end(self, net: str, l: int, acc: torch.Tensor):
         self.grads[conv_key(net, l, "bias")].copy_(acc[:REAL[l]])
 
+    def _conv0(self, net: str, state, obs, e):
+        W0, b0 = self._layer0_params(net)
+        with torch.cuda.device(self.dev):
+            _chk(_lib.lib().aur_plain_conv0(obs.data_ptr(), state.data_ptr(), W0.data_ptr(), b0.data_ptr(), self.B, e.a[0].data_ptr(),
+                                            e.arg[0].data_ptr(), _stream()), "aur_plain_conv0")
+
     def _layer0_wgrad(self, net: str, state, obs, dprev, e):
         with torch.cuda.device(self.dev):
-            _chk(_lib.lib().aur_equiv_conv0_wgrad(obs.data_ptr(), state.data_ptr(), dprev.data_ptr(), e.a[0].data_ptr(),
+            _chk(_lib.lib().aur_plain_conv0_wgrad(obs.data_ptr(), state.data_ptr(), dprev.data_ptr(), e.a[0].data_ptr(),
                                                   e.arg[0].data_ptr(), self.B, self.ws.data_ptr(),
                                                   self.grads[conv_key(net, 0, "weight")].data_ptr(),
-                                                  self.grads[conv_key(net, 0, "bias")].data_ptr(), _stream()), "aur_equiv_conv0_wgrad")
+                                                  self.grads[conv_key(net, 0, "bias")].data_ptr(), _stream()), "aur_plain_conv0_wgrad")
 
     # ------------------------------------------------------------------- update
     def loss_and_grads(self, state, obs, action, oldlp, adv, ret, vold, clip_coeff=0.2, entropy_coeff=0.01,

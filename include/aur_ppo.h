@@ -416,6 +416,15 @@ typedef struct {
 } aur_equiv_head_args;
 int aur_equiv_head_loss(const aur_equiv_head_args* args, void* stream);
 
+/* Layer 0 of the plain CNN (base_encoder's first Conv2d(2,16) + ReLU + MaxPool, src/nets/base_cnns.py:25-27) and its weight
+ * gradient: the 16 output channels live in channels 0..15 of the same [B,66,66,64] bf16 buffer / [B,64,64,64] arg-max
+ * buffer the equivariant layer 0 uses (the other 48 channels must be zero: allocate the buffers zeroed).
+ * weight [16,2,3,3], bias [16]; scratch >= 64*18+64 floats. */
+int aur_plain_conv0(const float* obs, const float* state, const float* weight, const float* bias, int32_t B, void* out,
+                    uint8_t* pool_arg, void* stream);
+int aur_plain_conv0_wgrad(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg, int32_t B,
+                          float* scratch, float* dweight, float* dbias, void* stream);
+
 /* Heads at inference: robot_actor_critic.evaluate / value (src/models/robot_actor_critic.py:57-60,104-131) on the
  * head GEMM outputs.  Actor part (a_out non-NULL): Normal(mean, exp(clamp(log_std))) log-prob and entropy summed
  * over the 5 dims, action = action_in or mean + std * N(0,1) from Philox(seed; row, stream_id), and decodeActions
