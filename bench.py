@@ -386,15 +386,34 @@ def run_equiv(args, plain: bool = False):
     clocks = sampler.finish()
     ms = t0.elapsed_time(t1) / args.steps
     # e2e: observations, states, actions and targets uploaded from pinned host memory every step, stats read back
+    # Two device buffer sets and a copy stream: the upload of step i+1 (269 MB of observations) runs while step i computes;
+    # every step's inputs still cross PCIe inside the timed region and every step's statistics are read back.
     host = [t.cpu().pin_memory() for t in (obs, state, action, oldlp, adv, ret, vold)]
-    dev = [torch.empty_like(t) for t in (obs, state, action, oldlp, adv, ret, vold)]
+    dev = [[torch.empty_like(t) for t in (obs, state, action, oldlp, adv, ret, vold)] for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream()
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[i & 1])
+            for d, h in zip(dev[i & 1], host):
+                d.copy_(h, non_blocking=True)
+            ready[i & 1].record(copy_stream)
+    for ev in free:
+        ev.record(main)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        for d, h in zip(dev, host):
-            d.copy_(h, non_blocking=True)
-        st = model.update(dev[1], dev[0], dev[2], dev[3], dev[4], dev[5], dev[6])
+    upload(0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            upload(i + 1)
+        main.wait_event(ready[i & 1])
+        dv = dev[i & 1]
+        st = model.update(dv[1], dv[0], dv[2], dv[3], dv[4], dv[5], dv[6])
+        free[i & 1].record(main)
         st_host = st.cpu()
     e1.record()
     torch.cuda.synchronize()
