@@ -277,3 +277,29 @@ def test_robot_actor_critic_facade_matches_oracle_evaluate():
     assert e.p["actor.enc3.psi"].data_ptr() == m.actor.enc3_psi.data_ptr()
     d = m.checkpoint_dict()
     assert set(d) == {"actor_state", "critic_state", "optimizer_state"} and "enc0_psi" in d["actor_state"]
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout", [(3, 16, 64, 128), (2, 32, 64, 64), (4, 8, 128, 256), (2, 16, 256, 128), (5, 8, 64, 200)])
+def test_wgrad3x3_matches_autograd(B, H, Cin, Cout):
+    """`aur_wgrad3x3_bf16` on its own (pad-1 geometry): dW[co][tap][ci] against torch's convolution weight gradient of the same
+    bf16 operands.  Covers the tap-merged MMA shapes: Cin = 64 -> one N = 192 MMA per filter row, wider inputs -> N = 256 +
+    N = 128, several Cout / Cin tiles and a ragged Cout."""
+    from aur_ppo_b200 import _lib
+    from aur_ppo_b200.kernels import _stream
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn(B, Cin, H, H, generator=g).bfloat16()
+    dy = (torch.randn(B, Cout, H, H, generator=g) * 0.1).bfloat16()
+    Hb = H + 2
+    xb = torch.zeros(B, Hb, Hb, Cin, dtype=torch.bfloat16, device="cuda")
+    xb[:, 1:1 + H, 1:1 + H, :] = x.permute(0, 2, 3, 1).cuda()
+    dyb = torch.zeros(B, Hb, Hb, Cout, dtype=torch.bfloat16, device="cuda")
+    dyb[:, 1:1 + H, 1:1 + H, :] = dy.permute(0, 2, 3, 1).cuda()
+    dw = torch.zeros(Cout, 9, Cin, device="cuda")
+    rc = _lib.lib().aur_wgrad3x3_bf16(Cout, Cin, B * Hb * Hb, dyb.data_ptr(), xb.data_ptr(), -(Hb + 1), Hb, dw.data_ptr(), 0, _stream())
+    _lib.check(rc, "aur_wgrad3x3_bf16")
+    W = torch.zeros(Cout, Cin, 3, 3, requires_grad=True)
+    F.conv2d(x.float(), W, padding=1).backward(dy.float())
+    want = W.grad.permute(0, 2, 3, 1).reshape(Cout, 9, Cin)
+    got = dw.cpu()
+    assert _rel(got, want) < 2e-3, _rel(got, want)
+    torch.testing.assert_close(got, want, rtol=1e-2, atol=2e-3 * float(want.abs().max()))
