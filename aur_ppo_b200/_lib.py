@@ -131,6 +131,9 @@ def lib() -> ctypes.CDLL:
     L.aur_policy_evaluate.restype = c_int
     L.aur_policy_evaluate.argtypes = [ctypes.POINTER(PolicyDesc), c_void_p, c_int64, c_void_p, c_void_p, c_uint64,
                                       c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.aur_policy_act.restype = c_int
+    L.aur_policy_act.argtypes = [ctypes.POINTER(PolicyDesc), c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_uint64,
+                                 c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.aur_env_reset.restype = c_int
     L.aur_env_reset.argtypes = [c_int32, c_int64, c_int32, ctypes.POINTER(EnvState), c_void_p, c_void_p, c_void_p]
     L.aur_rollout.restype = c_int

@@ -1,6 +1,9 @@
 // Host-side plumbing shared by every entry point of libaurppo.so.
 #include <stdarg.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace aur {
@@ -29,6 +32,34 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+
+namespace {
+struct TicketSlot { int dev; cudaStream_t s; unsigned int* p; };
+std::mutex g_ticket_mu;
+std::vector<TicketSlot> g_tickets;
+}  // namespace
+
+unsigned int* stream_tickets(cudaStream_t s) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error("stream_tickets: no current device"); return nullptr; }
+  std::lock_guard<std::mutex> lk(g_ticket_mu);
+  for (const TicketSlot& t : g_tickets)
+    if (t.dev == dev && t.s == s) return t.p;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+    set_error("stream_tickets: first use of a stream inside a graph capture (run one eager call on it first)");
+    return nullptr;
+  }
+  unsigned int* p = nullptr;
+  if (cudaMalloc(&p, 64) != cudaSuccess || cudaMemset(p, 0, 64) != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("stream_tickets: cudaMalloc failed");
+    return nullptr;
+  }
+  g_tickets.push_back({dev, s, p});
+  return p;
 }
 
 }  // namespace aur

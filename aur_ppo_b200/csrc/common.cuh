@@ -32,6 +32,24 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int sm_count();
 
+// "do this once per device": function attributes (dynamic shared memory limits) are per device, a process-wide
+// flag would leave every device but the first one without them.
+struct DeviceOnce {
+  uint64_t mask = 0;
+  int dev = -1;
+  bool first() {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { dev = -1; return true; }
+    return !((mask >> dev) & 1ull);
+  }
+  void done() { if (dev >= 0) mask |= 1ull << dev; }
+};
+
+// Last-CTA ticket counters owned by the LIBRARY (zeroed at allocation, reset by the kernel that used them), one
+// block of 16 words per (device, stream): kernels of one stream run in order, so they can share a block; a
+// caller-provided workspace would have to be zero-initialised by contract (it is not part of the ABI contract).
+// Returns nullptr on failure (error text set).
+unsigned int* stream_tickets(cudaStream_t s);
+
 // ---- mbarrier / bulk-async (TMA 1-D) PTX wrappers -----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

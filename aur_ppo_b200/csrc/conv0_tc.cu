@@ -155,13 +155,13 @@ conv0_wgrad_tc_kernel(const float* __restrict__ obs, const float* __restrict__ s
 
 int launch_conv0_wgrad_tc(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg, int B,
                           float* dw0, float* dbias_ch, cudaStream_t s, bool plain) {
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     AUR_CUDA_OK(cudaFuncSetAttribute(conv0_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C0_SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv0_wgrad_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv0_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C0_SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv0_wgrad_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr = true;
+    attr.done();
   }
   const long long nblk = ((long long)B * 4096 + C0_PIX - 1) / C0_PIX;
   long long grid = 3LL * sm_count();

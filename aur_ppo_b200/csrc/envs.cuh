@@ -311,6 +311,7 @@ struct RolloutDev {
   long long N;
   int T, wrappers;
   int obs_dim, act_dim, nl, continuous;
+  int greedy;                 // policy_evaluate kernels only: 1 = arg-max action / the Normal mean instead of a sample (test.py-style evaluation)
   int hid, dyn_smem;          // runtime-width path (hidden_dim != 64): hidden units, 1 = both nets are copied to shared memory
   const float* params;
   aur_env_state env;

@@ -534,14 +534,14 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   int rc;
   if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, c.in, dA, sA, bA))) return rc;
   if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.wmat, dB, sB, bB))) return rc;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<128>::SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<256>::SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<64>::SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<128>::SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_RESB_SMEM));
-    attr = true;
+    attr.done();
   }
   d.pix_tiles = (int)(img_groups * d.tiles_y * d.tiles_x);
   d.n_tiles = (c.Cout + BN - 1) / BN;

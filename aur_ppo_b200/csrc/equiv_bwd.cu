@@ -820,10 +820,10 @@ extern "C" int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const voi
   int rc;
   if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dy, dA, stA, bx))) return rc;
   if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dB, stB, bx))) return rc;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     AUR_CUDA_OK(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
-    attr = true;
+    attr.done();
   }
   const int mt = (Cout + WG_BM - 1) / WG_BM, nt = (Cin + WG_BN - 1) / WG_BN;
   if (split_k < 1) {

@@ -193,10 +193,10 @@ static int launch_gae_bulk(int32_t T, int64_t N, const float* rewards, const flo
                            const float* next_value, const float* next_done, float g32, float gl32, int use_gae,
                            float* adv_out, float* ret_out, cudaStream_t st) {
   constexpr size_t smem = sizeof(float) * STAGES * 3 * TT * W + 2 * STAGES * sizeof(uint64_t);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     AUR_CUDA_OK(cudaFuncSetAttribute(gae_bulk_kernel<W, TT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set.done();
   }
   const long long ntiles = (N + W - 1) / W;
   int per_sm = (int)(220 * 1024 / (smem + 1024));

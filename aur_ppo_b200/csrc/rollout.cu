@@ -259,9 +259,12 @@ __global__ void __launch_bounds__(256, 1) policy_evaluate_kernel(RolloutDev a, l
     const uint64_t gid = row0 + (uint64_t)b;
     if (!a.continuous) {
       int action = 0;
-      const bool sample = a.actions_in == nullptr;
+      const bool sample = a.actions_in == nullptr && !a.greedy;
       float u = 0.0f;
-      if (sample) {
+      if (a.greedy) {                                       // first maximum, like torch.argmax
+        const auto& lg = head[0];
+        for (int k = 1; k < a.act_dim; ++k) if (lg[k] > lg[action]) action = k;
+      } else if (sample) {
         const Philox r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32),
                                        (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
         u = u01_24(r.c[0]);
@@ -272,7 +275,9 @@ __global__ void __launch_bounds__(256, 1) policy_evaluate_kernel(RolloutDev a, l
       if (act_out) act_out[b] = (float)action;
     } else {
       float act[POL_OUT_MAX] = {0.f, 0.f, 0.f, 0.f};
-      if (a.actions_in == nullptr) {
+      if (a.greedy) {
+        for (int k = 0; k < POL_OUT_MAX; ++k) act[k] = head[0][k];
+      } else if (a.actions_in == nullptr) {
         const Philox r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32),
                                        (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
         float z[POL_OUT_MAX];
@@ -315,9 +320,12 @@ __global__ void __launch_bounds__(128, 1) policy_evaluate_dyn_kernel(RolloutDev 
     const uint64_t gid = row0 + (uint64_t)b;
     if (!a.continuous) {
       int action = 0;
-      const bool sample = a.actions_in == nullptr;
+      const bool sample = a.actions_in == nullptr && !a.greedy;
       float u = 0.0f;
-      if (sample) {
+      if (a.greedy) {                                       // first maximum, like torch.argmax
+        const auto& lg = head;
+        for (int k = 1; k < a.act_dim; ++k) if (lg[k] > lg[action]) action = k;
+      } else if (sample) {
         const Philox r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32),
                                        (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
         u = u01_24(r.c[0]);
@@ -330,7 +338,10 @@ __global__ void __launch_bounds__(128, 1) policy_evaluate_dyn_kernel(RolloutDev 
       float act[DYN_IO];
 #pragma unroll
       for (int k = 0; k < DYN_IO; ++k) act[k] = 0.0f;
-      if (a.actions_in == nullptr) {
+      if (a.greedy) {
+#pragma unroll
+        for (int k = 0; k < DYN_IO; ++k) act[k] = k < a.act_dim ? head[k] : 0.0f;
+      } else if (a.actions_in == nullptr) {
         // dims 0..3 from the Philox block the 4-wide kernels use, dims 4..7 from a second block (counter word 3 ^ 1 << 24)
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
@@ -558,15 +569,22 @@ extern "C" int aur_policy_evaluate(const aur_policy_desc* desc, const float* par
                                    const float* actions_in, uint64_t seed, uint64_t row0, uint64_t step,
                                    float* actions_out, float* logp_out, float* entropy_out, float* value_out,
                                    void* stream) {
+  return aur_policy_act(desc, params, B, obs, actions_in, 0, seed, row0, step, actions_out, logp_out, entropy_out, value_out, stream);
+}
+
+extern "C" int aur_policy_act(const aur_policy_desc* desc, const float* params, int64_t B, const float* obs,
+                              const float* actions_in, int32_t greedy, uint64_t seed, uint64_t row0, uint64_t step,
+                              float* actions_out, float* logp_out, float* entropy_out, float* value_out, void* stream) {
   using namespace aur;
   if (!desc || !params || B < 0 || (B > 0 && !obs)) { set_error("aur_policy_evaluate: bad arguments"); return AUR_ERR_ARG; }
+  if (greedy && actions_in) { set_error("aur_policy_act: greedy and actions_in are mutually exclusive"); return AUR_ERR_ARG; }
   if (B == 0) return 0;
   int rc = check_policy(*desc, "aur_policy_evaluate", DYN_IO);
   if (rc) return rc;
   RolloutDev d{};
   d.obs_dim = desc->obs_dim; d.act_dim = desc->act_dim; d.nl = desc->num_layers; d.continuous = desc->continuous;
   d.hid = desc->hidden_dim; d.dyn_smem = 0;
-  d.params = params; d.actions_in = actions_in; d.seed = seed;
+  d.params = params; d.actions_in = actions_in; d.seed = seed; d.greedy = greedy ? 1 : 0;
   if (!is_compiled_width(*desc)) {
     if (((uintptr_t)params & 15) != 0) { set_error("aur_policy_evaluate: params must be 16-byte aligned"); return AUR_ERR_ARG; }
     int block = 128;

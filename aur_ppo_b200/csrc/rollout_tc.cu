@@ -269,11 +269,11 @@ static int rollout_tc_attrs() {
 }
 
 int launch_rollout_tc(const RolloutDev& d, int env_kind, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     int rc;
     if ((rc = rollout_tc_attrs<CartPole>()) || (rc = rollout_tc_attrs<Pendulum>()) || (rc = rollout_tc_attrs<MountainCar>())) return rc;
-    attr = true;
+    attr.done();
   }
   const unsigned grid = (unsigned)((d.N + RT_S - 1) / RT_S);
   if (env_kind == AUR_ENV_PENDULUM) rollout_tc_kernel<Pendulum><<<grid, RT_S, RT_SMEM, s>>>(d);

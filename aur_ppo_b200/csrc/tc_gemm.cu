@@ -129,10 +129,10 @@ extern "C" int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, 
   int rc;
   if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, dA, st, boxA))) return rc;
   if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, dB, st, boxB))) return rc;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     AUR_CUDA_OK(cudaFuncSetAttribute(tc_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    attr = true;
+    attr.done();
   }
   dim3 grid((unsigned)((M + GEMM_BM - 1) / GEMM_BM), (unsigned)((N + GEMM_BN - 1) / GEMM_BN));
   tc_gemm_bf16_kernel<<<grid, 256, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, C, (int)M, (int)N, (int)K, (int)N);

@@ -706,7 +706,8 @@ extern "C" int aur_ppo_adv_moments_dp(int64_t m, const int32_t* idx, int64_t idx
   { int rc = make_dp(dp, seq, dpd, "aur_ppo_adv_moments_dp"); if (rc) return rc; }
   if (m <= 0 || !advantages || !moments_out || !workspace) { set_error("aur_ppo_adv_moments: bad arguments"); return AUR_ERR_ARG; }
   double* partial = reinterpret_cast<double*>(workspace + ws_partials_floats());
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + 2 * MOM_CTAS);
+  unsigned int* ticket = stream_tickets((cudaStream_t)stream);      // library-owned: the workspace need not be zeroed
+  if (!ticket) return AUR_ERR_ARG;
   long long grid = (m + 255) / 256;
   if (grid > MOM_CTAS) grid = MOM_CTAS;
   adv_moments_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((long long)m, idx, (long long)idx_offset, advantages,
@@ -746,10 +747,10 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
   if ((u.rec_actor != nullptr) != (u.rec_critic != nullptr)) { set_error("aur_ppo_update_grad: give both record arrays or neither"); return AUR_ERR_ARG; }
   if (u.rec_actor && u.policy.continuous && u.policy.act_dim > 2) { set_error("aur_ppo_update_grad: records hold at most 2 action dims"); return AUR_ERR_ARG; }
   d.rec_actor = reinterpret_cast<const float4*>(u.rec_actor); d.rec_critic = reinterpret_cast<const float4*>(u.rec_critic);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     AUR_CUDA_OK(cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
-    attr_set = true;
+    attr_set.done();
   }
   cudaStream_t s = (cudaStream_t)stream;
   const int impl = is_headline_shape(u.policy) ? update_impl() : 3;
@@ -771,7 +772,9 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
   }
   const int64_t P = policy_param_count(u.policy);
   const int total = (int)(P + AUR_NUM_STATS);
-  unsigned int* ticket2 = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(u.workspace + ws_partials_floats()) + 2 * MOM_CTAS) + 1;
+  unsigned int* ticket2 = stream_tickets(s);
+  if (!ticket2) return AUR_ERR_ARG;
+  ticket2 += 1;
   grad_reduce_kernel<<<(4 * total + 255) / 256, 256, 0, s>>>(partials, gx, u.policy.obs_dim, u.policy.act_dim, u.policy.continuous,
                                                         u.policy.hidden_dim, u.policy.num_layers, pstride, u.grads_out, d.dp,
                                                         ticket2);

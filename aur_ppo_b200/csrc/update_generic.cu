@@ -496,14 +496,10 @@ int launch_ppo_grad_generic(const UpdDev& d, const aur_policy_desc& p, float* ws
       d.params, p.obs_dim, g.H, g.NL, p.act_dim, ws);
   AUR_LAUNCH_OK("stage_params_kernel");
   const size_t smem = gen_smem_bytes(g.H, g.NL, g.S);
-  static size_t attr[3] = {0, 0, 0};
   const int ts = g.S / 32;
   void (*kern)(GenDev) = ts == 4 ? ppo_grad_generic_kernel<4> : ts == 2 ? ppo_grad_generic_kernel<2> : ppo_grad_generic_kernel<1>;
-  const int slot = ts == 4 ? 2 : ts == 2 ? 1 : 0;
-  if (attr[slot] < smem) {
-    AUR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[slot] = smem;
-  }
+  // per device and per shape: set on every launch (a host-side table update, no device work)
+  AUR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<dim3(gx, 2), GEN_THREADS, smem, s>>>(g);
   AUR_LAUNCH_OK("ppo_grad_generic_kernel");
   *gx_out = gx;

@@ -724,11 +724,11 @@ static int tc_attrs() {
 
 // gx = CTAs per net (partials are [2][gx][UPD_PSTRIDE]); the grid is 2 * gx.  tps = threads per sample (2 or 4).
 int launch_ppo_grad_tc(const UpdDev& d, int gx, int tps, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     int rc;
     if ((rc = tc_attrs<2>()) || (rc = tc_attrs<4>())) return rc;
-    attr = true;
+    attr.done();
   }
   if (tps == 4) ppo_grad_tc_kernel<4><<<2 * gx, 512, T2_SMEM, s>>>(d);
   else ppo_grad_tc_kernel<2><<<2 * gx, 256, T2_SMEM, s>>>(d);

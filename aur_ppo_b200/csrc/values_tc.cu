@@ -146,11 +146,11 @@ __global__ void __launch_bounds__(VT_THREADS, 3) critic_values_tc_kernel(const f
 // first parameter inside the flat buffer
 int launch_critic_values_tc(const float* critic, int obs_dim, const float* obs, long long M, float* out, cudaStream_t s) {
   if (M <= 0) return 0;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     AUR_CUDA_OK(cudaFuncSetAttribute(critic_values_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(critic_values_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr = true;
+    attr.done();
   }
   const long long ntiles = (M + VT_S - 1) / VT_S;
   long long grid = 3LL * sm_count();

@@ -75,7 +75,10 @@ class EquivActorCritic:
     D_HEAD = 651
 
     def __init__(self, params: Dict[str, torch.Tensor], batch: int, lr: float = 3e-4, eps: float = 1e-5,
-                 betas=(0.9, 0.999)):
+                 betas=(0.9, 0.999), split: bool = False):
+        self.split = bool(split)
+        if self.split:
+            raise _lib.AurError("split-precision mode is not built yet")
         if batch % 8:
             raise _lib.AurError("batch must be a multiple of 8 (16-byte rows for the TMA weight-gradient maps)")
         _lib.lib()

@@ -63,8 +63,9 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def policy_evaluate(desc: _lib.PolicyDesc, params: torch.Tensor, obs: torch.Tensor,
-                    actions: Optional[torch.Tensor] = None, seed: int = 0, row0: int = 0, step: int = 0):
-    """(action, log_prob, entropy, value[B]) of actor_critic.evaluate (models/actor_critic.py:34-51), no grad."""
+                    actions: Optional[torch.Tensor] = None, seed: int = 0, row0: int = 0, step: int = 0, greedy: bool = False):
+    """(action, log_prob, entropy, value[B]) of actor_critic.evaluate (models/actor_critic.py:34-51), no grad.
+    greedy: arg-max action / Normal mean instead of a sample (checkpoint evaluation)."""
     import ctypes
     params, obs = _f32c(params, "params"), _f32c(obs, "obs")
     B = obs.shape[0]
@@ -74,10 +75,10 @@ def policy_evaluate(desc: _lib.PolicyDesc, params: torch.Tensor, obs: torch.Tens
     act = torch.empty((B, A) if desc.continuous else (B,), device=obs.device, dtype=torch.float32)
     logp, ent, val = (torch.empty(B, device=obs.device, dtype=torch.float32) for _ in range(3))
     with torch.cuda.device(obs.device):
-        rc = _lib.lib().aur_policy_evaluate(ctypes.byref(desc), params.data_ptr(), B, obs.data_ptr(), _ptr(actions),
-                                            seed, row0, step, act.data_ptr(), logp.data_ptr(), ent.data_ptr(),
-                                            val.data_ptr(), _stream())
-    _lib.check(rc, "aur_policy_evaluate")
+        rc = _lib.lib().aur_policy_act(ctypes.byref(desc), params.data_ptr(), B, obs.data_ptr(), _ptr(actions),
+                                       int(bool(greedy)), seed, row0, step, act.data_ptr(), logp.data_ptr(), ent.data_ptr(),
+                                       val.data_ptr(), _stream())
+    _lib.check(rc, "aur_policy_act")
     return act, logp, ent, val
 
 
@@ -254,19 +255,23 @@ class Updater:
         self._m_total, self._ent_c, self._vf_c = m_total, float(entropy_coeff), float(value_coeff)
         return self.grads
 
-    def apply(self, lr: float, max_grad_norm: float = 0.5) -> torch.Tensor:
-        """Phase 3: clip_grad_norm_ + Adam in place on the flat parameters; returns the stats tensor (device)."""
+    def apply(self, lr: float, max_grad_norm: float = 0.5, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Phase 3: clip_grad_norm_ + Adam in place on the flat parameters; returns the stats tensor (device).
+        stats_out: optional fp32 [NUM_STATS] row the kernel writes instead of self.stats (no extra copy kernel)."""
         import ctypes
         self.step_count += 1
+        stats = self.stats if stats_out is None else _f32c(stats_out, "stats_out")
+        if stats.numel() < NUM_STATS:
+            raise _lib.AurError(f"stats_out needs {NUM_STATS} elements")
         with torch.cuda.device(self.params.device):
             dp = ctypes.addressof(self.exchange.ctx) if self.exchange is not None else None
             rc = _lib.lib().aur_ppo_update_apply_dp(ctypes.byref(self.desc), self.params.data_ptr(), self.grads.data_ptr(),
                                                     self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), float(lr),
                                                     self.betas[0], self.betas[1], self.eps, self.step_count,
                                                     float(max_grad_norm), self._m_total, self._ent_c, self._vf_c,
-                                                    self.stats.data_ptr(), dp, getattr(self, "_seq", 0) if dp else 0, _stream())
+                                                    stats.data_ptr(), dp, getattr(self, "_seq", 0) if dp else 0, _stream())
         _lib.check(rc, "aur_ppo_update_apply")
-        return self.stats
+        return stats
 
     def step(self, *args, lr: float, max_grad_norm: float = 0.5, **kw) -> torch.Tensor:
         self.grad(*args, **kw)

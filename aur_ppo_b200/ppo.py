@@ -13,9 +13,10 @@ return value, same TensorBoard tags and checkpoint file.  What differs is where 
   np.random.shuffle + index H2D per epoch     keyed bijection written by shuffle_kernel (no sort)
 
 There is no CPU path: without a CUDA device or without libaurppo.so the constructor raises.
-Under torch.distributed (NCCL) each rank owns num_envs / world_size env columns; the only
-exchange is one all_reduce of the packed [grads | stats] buffer (and of three fp64 advantage
-moments) per minibatch.
+Under torch.distributed each rank owns num_envs / world_size env columns; the only exchange is
+the packed [grads | stats] buffer (and three fp64 advantage moments) per minibatch, summed by the
+update kernels themselves over NVLink peer memory (parallel.PeerExchange; AUR_DP_EXCHANGE=nccl
+selects two library all_reduce calls instead).
 """
 from __future__ import annotations
 
@@ -66,8 +67,8 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(list(params), dict(lr=lr, eps=eps, betas=betas, weight_decay=0, amsgrad=False))
         self.updater = updater
 
-    def step(self, closure=None, max_grad_norm: float = 0.5):
-        return self.updater.apply(self.param_groups[0]["lr"], max_grad_norm)
+    def step(self, closure=None, max_grad_norm: float = 0.5, stats_out=None):
+        return self.updater.apply(self.param_groups[0]["lr"], max_grad_norm, stats_out=stats_out)
 
     def zero_grad(self, set_to_none: bool = True):
         pass   # the gradient buffer is overwritten by every aur_ppo_update_grad call
@@ -172,22 +173,27 @@ class ppo:
         self._records = kernels.pack_records(b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values,
                                              out=self._records)
 
-    def update_minibatch(self, flat_bufs, mb_inds: torch.Tensor) -> torch.Tensor:
-        """ppo.py:220-269 for one minibatch of local row indices -> device stats tensor."""
+    def update_minibatch(self, flat_bufs, mb_inds: torch.Tensor, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """ppo.py:220-269 for one minibatch of local row indices -> device stats tensor (written to stats_out if given)."""
         b_obs, b_logprobs, b_actions, b_advantages, b_returns, b_values = flat_bufs
         self.updater.grad(b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values, mb_inds,
                           m_total=mb_inds.numel() * self.world_size, clip_coeff=self.clip_coeff,
                           entropy_coeff=self.entropy_coeff, value_coeff=self.value_coeff, norm_adv=bool(self.norm_adv),
                           clip_vloss=bool(self.clip_vloss), records=self._records)
-        return self.optimizer.step(max_grad_norm=self.max_grad_norm)
+        return self.optimizer.step(max_grad_norm=self.max_grad_norm, stats_out=stats_out)
 
-    def run_update(self, update: int) -> Dict[str, torch.Tensor]:
-        """One full iteration of the outer loop (ppo.py:192-273) without logging; returns device tensors."""
+    def run_update(self, update: int, events=None) -> Dict[str, torch.Tensor]:
+        """One full iteration of the outer loop (ppo.py:192-273) without logging; returns device tensors.
+        events: optional 4 CUDA events recorded at the phase boundaries (start, rollout done, GAE done, update done)."""
+        rec = (lambda i: events[i].record()) if events is not None else (lambda i: None)
         if self.anneal_lr:
             frac = 1.0 - (update - 1.0) / self.num_updates
             self.optimizer.param_groups[0]["lr"] = frac * self.learning_rate
+        rec(0)
         self.rollout()
+        rec(1)
         returns, advantages = self.advantages()
+        rec(2)
         flat_bufs = self.buffer.flatten(returns, advantages)
         self.pack(flat_bufs)
         n_mb = 0
@@ -198,11 +204,12 @@ class ppo:
             self._shuffle_count += 1
             for start in range(0, self.local_batch, self.local_minibatch):
                 mb = b_inds[start:start + self.local_minibatch]
-                stats_rows[n_mb].copy_(self.update_minibatch(flat_bufs, mb))
+                self.update_minibatch(flat_bufs, mb, stats_out=stats_rows[n_mb])
                 n_mb += 1
             if self.target_kl is not None:
                 if stats_rows[n_mb - 1, 4].item() > self.target_kl:
                     break
+        rec(3)
         return dict(stats=stats_rows[:n_mb], b_values=flat_bufs[5], b_returns=flat_bufs[4])
 
     # --------------------------------------------------------------------------- train

@@ -1,13 +1,19 @@
 #!/usr/bin/env python
-"""Headline benchmark: one PPO iteration (fused rollout -> GAE -> minibatch updates) per step.
+"""Benchmarks of the PPO hot path, one JSON line per run.
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+  python bench.py --gpus N --steps K --warmup W                  # headline: BASELINE configs[1]
+  python bench.py --workload pendulum|scale1m|equiv|cnn ...      # configs[2], configs[4], configs[3], its plain-CNN sibling
+  python bench.py --impl reference [--workload ...] ...          # the reference's CPU path (oracle port), bounded sample
 
-Workload (BASELINE.json configs[1]): CartPole-v1 PPO, num_envs = 65536 PER GPU (weak scaling),
-T = 128, num_minibatches = 4, update_epochs = 4, 2-layer 64-wide MLP, synthetic = the env itself
-(seeds 0..N-1, reference-initialised weights).  A step = T*num_envs env steps, one GAE pass and
-epochs*num_minibatches fused updates.  Prints ONE JSON line (see the contract in the task brief).
+Workloads (sizes per BASELINE.json):
+  ppo       CartPole-v1, 65536 envs PER GPU (weak scaling), T = 128, 4 minibatches x 4 epochs           configs[1]
+  pendulum  Pendulum-v1 + the 5 wrappers, 65536 envs PER GPU, T = 256, the reference's continuous
+            override (run_ppo.py:44-51): 32 minibatches x 10 epochs, lr 3e-4, entropy 0                  configs[2]
+  scale1m   CartPole-v1, 1,048,576 envs IN TOTAL sharded over the GPUs (strong scaling), T = 128,
+            plus a GAE sweep T = 128..2048 on 131072 columns per GPU                                      configs[4]
+  equiv     equivariant actor-critic update, minibatch 4096 (--precision split|bf16)                      configs[3]
+A step = one PPO iteration: T * num_envs env steps (fused rollout), one GAE pass and
+epochs * num_minibatches fused updates.
 """
 from __future__ import annotations
 
@@ -21,31 +27,57 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NUM_ENVS_PER_GPU = 65536
-T = 128
-NUM_MINIBATCHES = 4
-EPOCHS = 4
 METRIC = "env_steps_per_s"
 UNIT = "env-steps/s"
-FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 148 SMs x 128 FMA lanes x 2 flop x max SM clock (no measured figure)
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # nominal: 148 SMs x 128 FMA lanes x 2 flop x max SM clock (context, not a measured roofline)
+CPU_SAMPLE_ENVS = {"ppo": 1024, "pendulum": 256, "scale1m": 1024}   # the CPU arm steps a bounded sample of the workload (see reference_arm_note)
+
+WORKLOADS = {
+    "ppo": dict(gym_id="CartPole-v1", continuous=False, T=128, nm=4, epochs=4, envs_per_gpu=65536, total_envs=None,
+                lr=2.5e-4, ent=0.01, obs=4, act=2, baseline="BASELINE configs[1]", scaling="weak"),
+    "pendulum": dict(gym_id="Pendulum-v1", continuous=True, T=256, nm=32, epochs=10, envs_per_gpu=65536, total_envs=None,
+                     lr=3e-4, ent=0.0, obs=3, act=1, baseline="BASELINE configs[2]", scaling="weak"),
+    "scale1m": dict(gym_id="CartPole-v1", continuous=False, T=128, nm=4, epochs=4, envs_per_gpu=None, total_envs=1048576,
+                    lr=2.5e-4, ent=0.01, obs=4, act=2, baseline="BASELINE configs[4]", scaling="strong"),
+}
+GAE_SWEEP_T = (128, 256, 512, 1024, 2048)
+GAE_SWEEP_COLS = 131072                              # config E at 8 GPUs: 1M / 8 columns per GPU
 
 
-def workload_config(n_gpus):
-    return {"workload": "CartPole-v1 PPO iteration: fused rollout + GAE + update (BASELINE configs[1])",
-            "num_envs_per_gpu": NUM_ENVS_PER_GPU, "num_envs": NUM_ENVS_PER_GPU * n_gpus, "num_steps": T,
-            "num_minibatches": NUM_MINIBATCHES, "update_epochs": EPOCHS, "hidden_dim": 64, "num_layers": 2,
+def num_envs_for(w, n_gpus):
+    return w["total_envs"] if w["total_envs"] else w["envs_per_gpu"] * n_gpus
+
+
+def mlp_flops_fwd(w, hidden=64):
+    """fp32 FLOPs of one actor + critic forward per sample (2 x multiply-adds)."""
+    o, a = w["obs"], w["act"]
+    return 2 * (o * hidden + hidden * hidden + hidden * a) + 2 * (o * hidden + hidden * hidden + hidden)
+
+
+def workload_config(name, n_gpus):
+    w = WORKLOADS[name]
+    n_envs = num_envs_for(w, n_gpus)
+    return {"workload": f"{w['gym_id']} PPO iteration: fused rollout + GAE + update ({w['baseline']})",
+            "name": name, "num_envs_per_gpu": n_envs // n_gpus, "num_envs": n_envs, "num_steps": w["T"],
+            "num_minibatches": w["nm"], "update_epochs": w["epochs"], "hidden_dim": 64, "num_layers": 2,
+            "continuous": w["continuous"], "wrappers": w["continuous"],
             "parallelism": f"dp{n_gpus} (env columns sharded; per minibatch one packed [grads|stats] exchange done by the "
                            f"update kernels over NVLink peer memory, AUR_DP_EXCHANGE=nccl selects a library all-reduce)",
-            "l2": "working set 370 MB per iteration > 126 MB L2 (no explicit flush needed)"}
+            "l2": "working set per iteration >> 126 MB L2 (no explicit flush needed); the GAE sweep flushes L2 between launches",
+            "reference_arm_note": f"the CPU arm (--impl reference and cpu_baseline) steps a BOUNDED SAMPLE of this workload: "
+                                  f"num_envs={CPU_SAMPLE_ENVS[name]} x T={w['T']}, same minibatch count and epochs (a serial Python env "
+                                  f"loop is ~flat in env-steps/s over num_envs; see cpu_points for num_envs 4 and 1024)"}
 
 
-def params(num_envs, total_iters):
-    return {'gym_id': 'CartPole-v1', 'seed': 1.0, 'num_steps': T, 'gae': True,
-            'total_timesteps': num_envs * T * max(total_iters, 1), 'anneal_lr': True, 'gae_lambda': 0.95,
-            'num_update_epochs': EPOCHS, 'num_envs': num_envs, 'num_minibatches': NUM_MINIBATCHES, 'entropy_coeff': 0.01,
+def params(name, n_gpus, total_iters):
+    w = WORKLOADS[name]
+    n = num_envs_for(w, n_gpus)
+    return {'gym_id': w["gym_id"], 'seed': 1.0, 'num_steps': w["T"], 'gae': True,
+            'total_timesteps': n * w["T"] * max(total_iters, 1), 'anneal_lr': True, 'gae_lambda': 0.95,
+            'num_update_epochs': w["epochs"], 'num_envs': n, 'num_minibatches': w["nm"], 'entropy_coeff': w["ent"],
             'value_coeff': 0.5, 'clip_coeff': 0.2, 'clip_vloss': True, 'max_grad_norm': 0.5, 'target_kl': None,
-            'norm_adv': True, 'capture_video': False, 'hidden_dim': 64, 'continuous': False, 'learning_rate': 2.5e-4,
-            'exp_name': 'bench', 'num_layers': 2, 'dropout': 0.0, 'gamma': 0.99, 'track': False,
+            'norm_adv': True, 'capture_video': False, 'hidden_dim': 64, 'continuous': w["continuous"],
+            'learning_rate': w["lr"], 'exp_name': 'bench', 'num_layers': 2, 'dropout': 0.0, 'gamma': 0.99, 'track': False,
             'tensorboard': False, 'save': False}
 
 
@@ -94,26 +126,42 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------- reference arm (CPU)
-def cpu_reference_iteration(num_envs, iters, warmup, seed=1):
+def host_threads():
+    """All the host threads torch may use, set explicitly (torchrun exports OMP_NUM_THREADS=1)."""
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(max(n, 1))
+    return torch.get_num_threads()
+
+
+def cpu_reference_iteration(name, num_envs, iters, warmup, seed=1):
     """The reference's CPU path restated (oracle/): gym-style SyncVectorEnv of per-env Python objects
-    stepped serially, reference actor_critic math on torch CPU, run_gae loop, update loop with Adam.
+    stepped serially (with the continuous wrapper stack of ppo.py:92-97 when the workload has it), reference
+    actor_critic math on torch CPU, run_gae loop, update loop with Adam.
     Returns (seconds per iteration, env steps per iteration)."""
     import numpy as np
     import torch
     from oracle import gym_restated as G
     from oracle import ppo_ref as R
     from tests.helpers import random_policy
+    w = WORKLOADS[name]
+    T, cont, O = w["T"], w["continuous"], w["obs"]
     torch.manual_seed(seed)
     np.random.seed(seed)
-    pol, _ = random_policy(4, 2, 64, 2, False, seed=seed)
-    opt = R.RefAdam(pol.tensors(), lr=2.5e-4, eps=1e-5)
-    envs = G.SyncVectorEnv([G.make_env("CartPole-v1", False) for _ in range(num_envs)], 4)
+    pol, _ = random_policy(O, w["act"], 64, 2, cont, seed=seed)
+    opt = R.RefAdam(pol.tensors(), lr=w["lr"], eps=1e-5)
+    envs = G.SyncVectorEnv([G.make_env(w["gym_id"], cont) for _ in range(num_envs)], O)
     next_obs = torch.from_numpy(envs.reset(seed=list(range(num_envs)))[0])
     next_done = torch.zeros(num_envs)
     N = num_envs
-    obs = torch.zeros(T, N, 4); actions = torch.zeros(T, N); logps = torch.zeros(T, N)
-    rewards = torch.zeros(T, N); dones = torch.zeros(T, N); values = torch.zeros(T, N)
-    batch, mb = N * T, N * T // NUM_MINIBATCHES
+    obs = torch.zeros(T, N, O); actions = torch.zeros(T, N, w["act"]) if cont else torch.zeros(T, N)
+    logps = torch.zeros(T, N); rewards = torch.zeros(T, N); dones = torch.zeros(T, N); values = torch.zeros(T, N)
+    batch = N * T
+    mb = max(batch // w["nm"], 1)
     times = []
     for it in range(warmup + iters):
         t0 = time.perf_counter()
@@ -127,43 +175,116 @@ def cpu_reference_iteration(num_envs, iters, warmup, seed=1):
             next_obs, next_done = torch.from_numpy(o), torch.from_numpy(term.astype(np.float32))
         with torch.no_grad():                                # ppo.py:159-166
             ret, adv = R.gae(rewards, values, dones, pol.value(next_obs), next_done, 0.99, 0.95)
-        b = (obs.reshape(-1, 4), actions.reshape(-1), logps.reshape(-1), adv.reshape(-1), ret.reshape(-1), values.reshape(-1))
+        b = (obs.reshape(-1, O), actions.reshape(-1, w["act"]) if cont else actions.reshape(-1), logps.reshape(-1),
+             adv.reshape(-1), ret.reshape(-1), values.reshape(-1))
         inds = np.arange(batch)
-        for ep in range(EPOCHS):                             # ppo.py:215-269
+        for ep in range(w["epochs"]):                        # ppo.py:215-269
             np.random.shuffle(inds)
             for s in range(0, batch, mb):
                 mi = torch.from_numpy(inds[s:s + mb])
-                R.ppo_update_step(pol, opt, b[0][mi], b[1][mi], b[2][mi], b[3][mi], b[4][mi], b[5][mi])
+                R.ppo_update_step(pol, opt, b[0][mi], b[1][mi], b[2][mi], b[3][mi], b[4][mi], b[5][mi], ent_c=w["ent"])
         times.append(time.perf_counter() - t0)
     times = times[warmup:]
     return sum(times) / len(times), N * T
+
+
+def cpu_sample_text(name, n, iters):
+    w = WORKLOADS[name]
+    return (f"oracle port of the reference CPU path (gym-style SyncVectorEnv of Python env objects"
+            f"{' + ClipAction/NormalizeObservation/NormalizeReward wrappers' if w['continuous'] else ''} + torch CPU), "
+            f"{w['gym_id']} num_envs={n} x T={w['T']}, {w['epochs']} epochs x {w['nm']} minibatches per step, {iters} timed "
+            f"iterations; gym itself is not installed, so this is oracle/gym_restated.py + oracle/ppo_ref.py")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    sample_envs = 256
-    sec, steps = cpu_reference_iteration(sample_envs, args.steps, args.warmup)
+    if args.workload in ("equiv", "cnn"):
+        return run_reference_cnn(args)
+    name = args.workload
+    w = WORKLOADS[name]
+    cores = host_threads()
+    n = CPU_SAMPLE_ENVS[name]
+    sec, steps = cpu_reference_iteration(name, n, args.steps, args.warmup)
     v = steps / sec
-    sample = (f"oracle port of the reference CPU path (gym-style SyncVectorEnv of Python env objects + torch CPU), "
-              f"CartPole-v1 num_envs={sample_envs} x T={T}, {EPOCHS} epochs x {NUM_MINIBATCHES} minibatches per step; "
-              f"gym itself is not installed, so this is oracle/gym_restated.py + oracle/ppo_ref.py")
+    # the reference's own CPU-runnable case (configs[0], num_envs = 4) and one scaled point
+    points = []
+    if name == "ppo":
+        for pn, it in ((4, 8), (n, 0)):
+            if it:
+                ps, pst = cpu_reference_iteration(name, pn, it, 2)
+                points.append({"num_envs": pn, "value": pst / ps, "unit": UNIT, "ms_per_iteration": ps * 1e3})
+            else:
+                points.append({"num_envs": pn, "value": v, "unit": UNIT, "ms_per_iteration": sec * 1e3})
+    sample = cpu_sample_text(name, n, args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "f32 (MLP) / f64 (env state)", "data": "synthetic",
-            "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "config": workload_config(name, args.gpus),
+            "sampled": {"num_envs": n, "num_steps": w["T"], "env_steps_per_step": steps,
+                        "note": "value = env-steps of the SAMPLE / its time; one CPU process whatever --gpus says"},
+            "cpu_points": points,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
+def run_reference_cnn(args):
+    """--impl reference for configs[3] / its sibling: the torch-CPU port of the update on a bounded minibatch."""
+    plain = args.workload == "cnn"
+    cores = host_threads()
+    cb = cnn_cpu_baseline(plain, min_seconds=5.0 * max(args.steps, 1) / 10.0 + 5.0)
+    line = {"impl": "reference", "metric": "update_samples_per_s", "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 4096 / cb["value"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": equiv_config(plain),
+            "cpu_baseline": dict(cb, cores=cores),
+            "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------ own arm
+def gae_sweep(torch, kernels, dev, cols, hbm_peak):
+    """GAE-only launches on synthetic [T, cols] inputs, L2 flushed before every launch,
+    CUDA events around each launch -> one rooflines[] entry per T."""
+    out = []
+    g = torch.Generator(device=dev).manual_seed(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for T in GAE_SWEEP_T:
+        rew = torch.rand(T, cols, generator=g, device=dev)
+        val = torch.randn(T, cols, generator=g, device=dev)
+        term = (torch.rand(T, cols, generator=g, device=dev) < 1.0 / 200).float()
+        nv = torch.randn(cols, generator=g, device=dev)
+        nd = torch.zeros(cols, device=dev)
+        ret, adv = torch.empty_like(rew), torch.empty_like(rew)
+        ts = []
+        for i in range(3 + 10):
+            flush.fill_(i & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            kernels.gae(rew, val, term, nv, nd, 0.99, 0.95, True, out=(ret, adv))
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        ms = ts[len(ts) // 2]
+        nbytes = 20 * T * cols + 8 * cols
+        gbps = nbytes / (ms * 1e-3) / 1e9
+        out.append({"kernel": f"gae_bulk_kernel [T={T}, N={cols}] (cold L2)", "bound": "hbm", "achieved": gbps, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": gbps / hbm_peak, "traffic": None, "algorithmic_bytes": nbytes, "ms": ms})
+        del rew, val, term, ret, adv
+    return out
+
+
 def run_ours(args):
+    import math
     import torch
     import torch.distributed as dist
     from aur_ppo_b200 import _lib, kernels
+    name = args.workload
+    w = WORKLOADS[name]
+    T, EPOCHS, NM = w["T"], w["epochs"], w["nm"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -175,9 +296,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     from aur_ppo_b200.ppo import ppo
     n_gpus = world
-    agent = ppo(params(NUM_ENVS_PER_GPU * n_gpus, args.steps + args.warmup))
-    import math
-    agent._stats_rows = torch.zeros(EPOCHS * math.ceil(agent.local_batch / agent.local_minibatch), 16, device=agent.device)
+    agent = ppo(params(name, n_gpus, args.steps + args.warmup))
+    n_mb_iter = EPOCHS * math.ceil(agent.local_batch / agent.local_minibatch)
+    agent._stats_rows = torch.zeros(n_mb_iter, 16, device=agent.device)
     id0 = agent.rank * agent.local_envs
     agent.envs.reset(seed=list(range(id0, id0 + agent.local_envs)))
     L = _lib.lib()
@@ -201,22 +322,7 @@ def run_ours(args):
     start.record()
     for k in range(args.steps):
         upd += 1
-        if agent.anneal_lr:
-            agent.optimizer.param_groups[0]["lr"] = (1.0 - (upd - 1.0) / agent.num_updates) * agent.learning_rate
-        ev[k][0].record()
-        agent.rollout()
-        ev[k][1].record()
-        returns, advantages = agent.advantages()
-        ev[k][2].record()
-        flat_bufs = agent.buffer.flatten(returns, advantages)
-        agent.pack(flat_bufs)
-        for ep in range(EPOCHS):
-            b_inds = kernels.shuffle_indices(agent.local_batch, seed=agent.shuffle_seed, stream_id=agent._shuffle_count,
-                                             out=agent._b_inds)
-            agent._shuffle_count += 1
-            for s in range(0, agent.local_batch, agent.local_minibatch):
-                agent.update_minibatch(flat_bufs, b_inds[s:s + agent.local_minibatch])
-        ev[k][3].record()
+        agent.run_update(upd, events=ev[k])
     end.record()
     barrier()
     launches = int(L.aur_launch_count())
@@ -230,7 +336,8 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_total, t_roll, t_gae, t_upd = [float(x) for x in tt.cpu()]
     ms_per_step = ms_total / args.steps
-    steps_per_iter = NUM_ENVS_PER_GPU * n_gpus * T
+    local_envs = agent.local_envs
+    steps_per_iter = local_envs * n_gpus * T
     value = steps_per_iter / (ms_per_step * 1e-3)
 
     # ---- e2e through the public API with host buffers: every step uploads the policy parameters and
@@ -264,13 +371,14 @@ def run_ours(args):
     d2h_bytes = P * 4 + h_stats.numel() * 4 + d2h // args.steps
 
     exchange_kind = "in-kernel all-reduce over NVLink peer memory" if agent.exchange is not None else ("nccl all_reduce" if world > 1 else "none")
+    wait_stats = agent.exchange.wait_stats() if agent.exchange is not None and hasattr(agent.exchange, "wait_stats") else None
     if agent.exchange is not None and agent.exchange.status() != 0:
         raise SystemExit("data-parallel exchange: a kernel timed out waiting for a peer rank")
+    m = agent.local_minibatch
+    dev = agent.device
     agent.close()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    del agent
+    torch.cuda.empty_cache()
 
     peaks = {}
     try:
@@ -278,65 +386,78 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    sweep = []
+    if name == "scale1m":                                             # every rank runs it (same work), rank 0 reports
+        sweep = gae_sweep(torch, kernels, dev, GAE_SWEEP_COLS, hbm_peak)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     tensor_peak = next((float(peaks[k]) for k in ("bf16_tflops_sustained", "bf16_dense_tflops_sustained", "bf16_tflops")
                         if k in peaks), 1414.7)
-    m = agent.local_minibatch
-    n_mb = EPOCHS * NUM_MINIBATCHES
+    n_mb = n_mb_iter
+    fwd = float(mlp_flops_fwd(w))
+    upd_flops = 3.0 * fwd
     upd_samples_per_s = n_mb * m * n_gpus / (t_upd * 1e-3)
     roll_steps_per_s = steps_per_iter / (t_roll * 1e-3)
-    gae_bytes = 20 * T * NUM_ENVS_PER_GPU + 8 * NUM_ENVS_PER_GPU
+    gae_bytes = 20 * T * local_envs + 8 * local_envs
     gae_gbps = gae_bytes / (t_gae * 1e-3) / 1e9
     upd_gbps = 40.0 * m / (t_upd / n_mb * 1e-3) / 1e9
-    upd_tflops = 53400.0 * m / (t_upd / n_mb * 1e-3) / 1e12
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-    except Exception:
-        traffic = {}
+    upd_tflops = upd_flops * m / (t_upd / n_mb * 1e-3) / 1e12
+    # DRAM bytes per launch from the committed `ncu --set full` capture of THIS round's binary (profiles/r2_traffic.json,
+    # config-B shapes); null when the workload's shapes differ from the captured ones
+    traffic, traffic_src = {}, None
+    if name == "ppo":
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch", {}), tj.get("source")
+        except Exception:
+            traffic = {}
+    roll_bytes = 36.0 * local_envs * T
     rooflines = [
         {"kernel": "gae_bulk_kernel", "bound": "hbm", "achieved": gae_gbps, "peak": hbm_peak, "unit": "GB/s",
          "frac": gae_gbps / hbm_peak, "traffic": traffic.get("gae_bulk_kernel"), "algorithmic_bytes": gae_bytes,
-         "ms": t_gae},
-        {"kernel": "rollout_tc_kernel + critic_values_tc_kernel", "bound": "hbm", "achieved": 36.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e9,
-         "peak": hbm_peak, "unit": "GB/s", "frac": 36.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e9 / hbm_peak,
+         "ms": t_gae, "note": "inside the iteration: inputs were just written by the rollout (partly L2-resident)"},
+        {"kernel": "rollout_tc_kernel + critic_values_tc_kernel", "bound": "hbm", "achieved": roll_bytes / (t_roll * 1e-3) / 1e9,
+         "peak": hbm_peak, "unit": "GB/s", "frac": roll_bytes / (t_roll * 1e-3) / 1e9 / hbm_peak,
          "traffic": (traffic.get("rollout_tc_kernel", 0) + traffic.get("critic_values_tc_kernel", 0)) or None, "ms": t_roll,
-         "fp32_tflops": 17792.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e12,
-         "fp32_frac_of_nominal": 17792.0 * NUM_ENVS_PER_GPU * T / (t_roll * 1e-3) / 1e12 / FP32_PEAK_TFLOPS},
+         "fp32_tflops": fwd * local_envs * T / (t_roll * 1e-3) / 1e12,
+         "fp32_frac_of_nominal": fwd * local_envs * T / (t_roll * 1e-3) / 1e12 / FP32_PEAK_TFLOPS},
         {"kernel": "ppo_grad_tc_kernel (+shuffle, moments, reduce, adam)", "bound": "tensor", "achieved": upd_tflops,
          "peak": tensor_peak, "unit": "TFLOP/s", "frac": upd_tflops / tensor_peak, "traffic": traffic.get("ppo_grad_tc_kernel"),
-         "ms": t_upd / n_mb, "algorithmic_flops": 53400.0 * m, "algorithmic_bytes": 40.0 * m,
-         "issued_bf16_tflops": 25165.8e3 * (m / 128.0) / (t_upd / n_mb * 1e-3) / 1e12,
+         "ms": t_upd / n_mb, "algorithmic_flops": upd_flops * m, "algorithmic_bytes": 40.0 * m,
          "hbm_GBps": upd_gbps, "hbm_frac": upd_gbps / hbm_peak,
          "fp32_equiv_frac_of_nominal_fp32": upd_tflops / FP32_PEAK_TFLOPS,
-         "note": "1335 FLOP per gathered byte: compute side of the roofline.  The 64x64 contractions run on tcgen05 as "
-                 "bf16 two-term splits (2-3 products each, issued_bf16_tflops counts them); achieved = ALGORITHMIC "
-                 "53.4 kFLOP per sample / time against the measured dense bf16 peak.  ncu: the kernel is issue-bound on "
-                 "the per-sample SIMT work (operand splitting, tanh, loss), see profiles/"},
-    ]
-    dominant = max(rooflines, key=lambda r: r["ms"] * (n_mb if r["kernel"].startswith("ppo_grad") else 1))
+         "note": "compute side of the roofline (>1000 FLOP per gathered byte).  The 64x64 contractions run on tcgen05 as "
+                 "bf16 two-term splits; achieved = ALGORITHMIC fwd+bwd FLOP per sample / time against the measured dense "
+                 "bf16 peak.  ncu: the kernel is issue-bound on the per-sample SIMT work, see profiles/"},
+    ] + sweep
+    dominant = max(rooflines[:3], key=lambda r: r["ms"] * (n_mb if r["kernel"].startswith("ppo_grad") else 1))
     roofline = {k: dominant[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
     roofline["kernel"] = dominant["kernel"]
     roofline["peak_source"] = peak_src
-    for k in ("fp32_tflops", "fp32_frac_of_nominal", "issued_bf16_tflops", "hbm_GBps", "hbm_frac", "note"):
+    roofline["traffic_source"] = traffic_src
+    for k in ("fp32_tflops", "fp32_frac_of_nominal", "hbm_GBps", "hbm_frac", "note"):
         if k in dominant:
             roofline[k] = dominant[k]
 
     cpu_baseline = None
     if n_gpus == 1 and not args.no_cpu_baseline:
-        import torch as _t
-        sample_envs = 256
-        sec, steps = cpu_reference_iteration(sample_envs, 4, 1)
-        cpu_baseline = {"value": steps / sec, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
-                        "sample": f"oracle port (gym-style SyncVectorEnv of Python env objects + torch CPU), CartPole-v1 "
-                                  f"num_envs={sample_envs} x T={T}, {EPOCHS}x{NUM_MINIBATCHES} minibatch updates, 4 iterations"}
+        cores = host_threads()
+        iters = 4 if name != "pendulum" else 2
+        sec, steps = cpu_reference_iteration(name, CPU_SAMPLE_ENVS[name], iters, 1)
+        cpu_baseline = {"value": steps / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": cpu_sample_text(name, CPU_SAMPLE_ENVS[name], iters)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (MLP, GAE, Adam) / f64 (env state)", "data": "synthetic", "config": workload_config(n_gpus),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+            "dtype": "f32 (MLP, GAE, Adam) / f64 (env state)", "data": "synthetic", "config": workload_config(name, n_gpus),
             "rollout_env_steps_per_s": roll_steps_per_s, "update_samples_per_s": upd_samples_per_s,
             "gae_GBps": gae_gbps, "gae_frac_of_hbm_peak": gae_gbps / hbm_peak,
             "phase_ms": {"rollout": t_roll, "gae": t_gae, "update": t_upd},
             "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu_baseline, "dp_exchange": exchange_kind,
+            "dp_wait": wait_stats,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms,
                     "what": "per step: H2D policy parameters from pinned memory -> ppo.run_update() -> D2H updated "
@@ -345,6 +466,16 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def equiv_config(plain):
+    return {"workload": ("plain CNN actor-critic update (robot_actor_critic equivariant=False), minibatch 4096, obs "
+                         "1x128x128 + gripper state (sibling of BASELINE configs[3])") if plain else
+                        ("equivariant actor-critic update, minibatch 4096, obs 1x128x128 + gripper state "
+                         "(BASELINE configs[3])"),
+            "l2": "activations >> L2 per step",
+            "reference_arm_note": "the CPU arm (--impl reference and cpu_baseline) runs the torch-CPU port of the same update "
+                                  "on a BOUNDED minibatch (32 for the plain CNN, 8 for the equivariant model)"}
 
 
 def run_equiv(args, plain: bool = False):
@@ -356,6 +487,7 @@ def run_equiv(args, plain: bool = False):
     from aur_ppo_b200 import _lib, equiv, plain_cnn
     B = 4096
     torch.cuda.set_device(0)
+    split = args.precision == "split"
     if plain:
         params = plain_cnn.init_params(seed=0)
     else:
@@ -368,7 +500,7 @@ def run_equiv(args, plain: bool = False):
     action = torch.randn(B, 5, generator=g, device="cuda")
     adv, ret, vold = (torch.randn(B, generator=g, device="cuda") for _ in range(3))
     oldlp = torch.full((B,), -7.0, device="cuda")
-    model = plain_cnn.PlainActorCritic(params, B) if plain else equiv.EquivActorCritic(params, B)
+    model = plain_cnn.PlainActorCritic(params, B, split=split) if plain else equiv.EquivActorCritic(params, B, split=split)
     for _ in range(args.warmup):
         model.update(state, obs, action, oldlp, adv, ret, vold)
     torch.cuda.synchronize()
@@ -423,8 +555,9 @@ def run_equiv(args, plain: bool = False):
     # = 9.4 + 4 x 37.7 + 42.5 + 0.6 MFLOP = 2.034e8 (real channels; the padded contractions issue ~2.2x that in layers 0-2)
     flops = 3 * 2 * (2.034e8 if plain else 2.80e9) * B
     cpu_baseline = None
-    if plain and not args.no_cpu_baseline:
-        cpu_baseline = cnn_cpu_baseline()
+    if not args.no_cpu_baseline:
+        cores = host_threads()
+        cpu_baseline = dict(cnn_cpu_baseline(plain), cores=cores)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -434,13 +567,14 @@ def run_equiv(args, plain: bool = False):
     tf = flops / (ms * 1e-3) / 1e12
     line = {"metric": "update_samples_per_s", "value": B / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 operands / fp32 accumulate (tcgen05), fp32 parameters and Adam", "data": "synthetic",
-            "config": {"workload": ("plain CNN actor-critic update (robot_actor_critic equivariant=False), minibatch 4096, obs "
-                                    "1x128x128 + gripper state (sibling of BASELINE configs[3])") if plain else
-                                   ("equivariant actor-critic update, minibatch 4096, obs 1x128x128 + gripper state "
-                                    "(BASELINE configs[3])"),
-                       "l2": "activations >> L2 per step"},
+            "dtype": ("bf16x2 split operands (hi + mid planes, 3 products) / fp32 accumulate (tcgen05): fp32-class "
+                      "arithmetic (north_star's 1e-4 gradient bar), fp32 parameters and Adam") if split else
+                     ("bf16 operands / fp32 accumulate (tcgen05), fp32 parameters and Adam: BELOW the reference's fp32 "
+                      "precision (fast mode)"),
+            "data": "synthetic", "precision": args.precision,
+            "config": dict(equiv_config(plain), precision=args.precision),
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+                         "issued_tflops": tf * (3.0 if split else 1.0),
                          "kernel": "conv_igemm_kernel + wgrad3x3_kernel (whole update, %.1f TFLOP algorithmic)" % (flops / 1e12),
                          "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "note": ("channels 16 / 32 are padded to the 64-wide K chunk and layer 0 runs 4 rotated copies: the "
@@ -452,14 +586,19 @@ def run_equiv(args, plain: bool = False):
     print(json.dumps(line))
 
 
-def cnn_cpu_baseline():
-    """The reference's CPU path for the plain CNN update restated (oracle/cnn_ref.py = base_actor / base_critic forward,
-    robot_ppo.update loss, autograd backward, actor-only clip, torch Adam) on the host cores, bounded sample."""
-    import time
+def cnn_cpu_baseline(plain=True, min_seconds=10.0):
+    """The reference's CPU path for the CNN update restated (oracle/cnn_ref.py = base_actor / base_critic forward,
+    oracle/equiv_ref.py = the restated equivariant model; robot_ppo.update loss, autograd backward, actor-only clip,
+    torch Adam) on the host cores, bounded sample."""
     import torch
-    from oracle import cnn_ref as C
-    B = 32
-    p = {k: v.clone().requires_grad_(True) for k, v in C.formula_params(C.param_shapes(), seed=0).items()}
+    if plain:
+        from oracle import cnn_ref as C
+        B = 32
+        p = {k: v.clone().requires_grad_(True) for k, v in C.formula_params(C.param_shapes(), seed=0).items()}
+    else:
+        from oracle import equiv_ref as C
+        B = 8
+        p = {k: v.clone().requires_grad_(True) for k, v in C.init_params(seed=0).items()}
     opt = torch.optim.Adam(list(p.values()), lr=3e-4, eps=1e-5)
     g = torch.Generator().manual_seed(0)
     obs = torch.rand(B, 1, 128, 128, generator=g) * 0.32
@@ -476,12 +615,12 @@ def cnn_cpu_baseline():
         opt.step()
     step()
     n, t0 = 0, time.perf_counter()
-    while n < 3 or time.perf_counter() - t0 < 10.0:
+    while n < 3 or time.perf_counter() - t0 < min_seconds:
         step()
         n += 1
     dt = time.perf_counter() - t0
     return {"value": n * B / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"oracle port (torch CPU conv2d + autograd + Adam), minibatch {B} x {n} updates"}
+            "sample": f"oracle port (torch CPU conv2d + autograd + Adam, fp32), minibatch {B} x {n} updates"}
 
 
 def main():
@@ -491,8 +630,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
-    ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "equiv", "cnn"],
-                    help="ppo = BASELINE configs[1] (default, the headline line); equiv = configs[3]; cnn = its plain-CNN sibling")
+    ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "pendulum", "scale1m", "equiv", "cnn"],
+                    help="ppo = BASELINE configs[1] (default, the headline line); pendulum = configs[2]; scale1m = configs[4] "
+                         "(1M envs over the GPUs + GAE sweep); equiv = configs[3]; cnn = its plain-CNN sibling")
+    ap.add_argument("--precision", type=str, default="split", choices=["split", "bf16"],
+                    help="equiv / cnn: split = bf16 hi+mid operand planes, fp32-class results (default); bf16 = single-plane fast mode")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

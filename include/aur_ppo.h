@@ -103,6 +103,13 @@ int aur_policy_evaluate(const aur_policy_desc* desc, const float* params, int64_
                         const float* actions_in, uint64_t seed, uint64_t row0, uint64_t step, float* actions_out,
                         float* logp_out, float* entropy_out, float* value_out, void* stream);
 
+/* The same with a `greedy` switch for checkpoint evaluation (src/test.py:17-61 plays a saved policy; its
+ * `agent.act(state)` samples, greedy != 0 takes torch.argmax of the logits / the Normal mean instead).
+ * greedy and actions_in are mutually exclusive. */
+int aur_policy_act(const aur_policy_desc* desc, const float* params, int64_t B, const float* obs,
+                   const float* actions_in, int32_t greedy, uint64_t seed, uint64_t row0, uint64_t step,
+                   float* actions_out, float* logp_out, float* entropy_out, float* value_out, void* stream);
+
 /* ---------------------------------------------------------------- envs ----
  * Device-resident vector env: replaces gym.vector.SyncVectorEnv over the
  * make_env thunks (src/ppo.py:66-68,85-99): gym CartPole-v1 / Pendulum-v1

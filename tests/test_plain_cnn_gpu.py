@@ -72,6 +72,7 @@ def test_plain_update_gradients_match_oracle_autograd():
     loose = {k for k in cpu if k.startswith("actor.conv.conv.") and not k.startswith("actor.conv.conv.17.")}
     bad = {k: v for k, v in worst.items()
            if not ((v[0] < 0.2 and v[1] > 0.985) if k in loose else (v[0] < 5e-2 and v[1] > 0.998))}
+    assert not bad, bad
     # one Adam step with the actor-only clip (robot_ppo.py:401-402) against torch.optim.Adam on the checker's gradients
     actor_keys = [k for k in cpu if k.startswith("actor.")]
     ref_p = {k: v.detach().clone() for k, v in cpu.items()}
