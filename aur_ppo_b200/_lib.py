@@ -131,6 +131,9 @@ def lib() -> ctypes.CDLL:
     L.aur_policy_evaluate.restype = c_int
     L.aur_policy_evaluate.argtypes = [ctypes.POINTER(PolicyDesc), c_void_p, c_int64, c_void_p, c_void_p, c_uint64,
                                       c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.aur_tc_set_precision.restype = c_int
+    L.aur_tc_set_precision.argtypes = [c_int]
+    L.aur_tc_get_precision.restype = c_int
     L.aur_policy_act.restype = c_int
     L.aur_policy_act.argtypes = [ctypes.POINTER(PolicyDesc), c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_uint64,
                                  c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

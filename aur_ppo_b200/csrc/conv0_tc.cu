@@ -28,7 +28,7 @@ template <bool PLAIN>
 __global__ void __launch_bounds__(256, 3)
 conv0_wgrad_tc_kernel(const float* __restrict__ obs, const float* __restrict__ state, const __nv_bfloat16* __restrict__ da1,
                       const __nv_bfloat16* __restrict__ a1 /*[B,66,66,64]*/, const unsigned char* __restrict__ arg, int B,
-                      float* __restrict__ dw0 /*[64][2][9]*/, float* __restrict__ dbias_ch /*[64]*/) {
+                      float* __restrict__ dw0 /*[64][2][9]*/, float* __restrict__ dbias_ch /*[64]*/, int parts) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = base + C0O_A;
@@ -128,7 +128,7 @@ conv0_wgrad_tc_kernel(const float* __restrict__ obs, const float* __restrict__ s
       fence_after_sync();
       for (int w = 0; w < 4; ++w) {
         const uint64_t ad = smem_desc_mn_sw128(sA + w * C0_A_BYTES, C0_A_BYTES, 1024);
-        for (int part = 0; part < 2; ++part) {
+        for (int part = 0; part < parts; ++part) {         // parts = 1: the hi views only (second pass over the gradient's mid plane)
           const uint64_t bd = smem_desc_k_sw128(sB + (2 * w + part) * C0_B_BYTES);
           for (int k = 0; k < C0_PIX / 16; ++k)
             mma_f16(tm_d, ad + (uint64_t)(128 * k), bd + (uint64_t)(2 * k), IDESC, (it | (uint32_t)(w | part | k)) != 0u);
@@ -154,7 +154,7 @@ conv0_wgrad_tc_kernel(const float* __restrict__ obs, const float* __restrict__ s
 }
 
 int launch_conv0_wgrad_tc(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg, int B,
-                          float* dw0, float* dbias_ch, cudaStream_t s, bool plain) {
+                          float* dw0, float* dbias_ch, cudaStream_t s, bool plain, int parts) {
   static DeviceOnce attr;
   if (attr.first()) {
     AUR_CUDA_OK(cudaFuncSetAttribute(conv0_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C0_SMEM));
@@ -168,10 +168,10 @@ int launch_conv0_wgrad_tc(const float* obs, const float* state, const void* da1,
   if (grid > nblk) grid = nblk;
   if (plain)
     conv0_wgrad_tc_kernel<true><<<(unsigned)grid, 256, C0_SMEM, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg,
-                                                                     B, dw0, dbias_ch);
+                                                                     B, dw0, dbias_ch, parts);
   else
     conv0_wgrad_tc_kernel<false><<<(unsigned)grid, 256, C0_SMEM, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg,
-                                                                      B, dw0, dbias_ch);
+                                                                      B, dw0, dbias_ch, parts);
   AUR_LAUNCH_OK("conv0_wgrad_tc_kernel");
   return 0;
 }

@@ -38,8 +38,10 @@ struct ConvDev {
   int pix_tiles, n_tiles;                  // work items: pix_tiles x n_tiles (output-channel blocks), walked by a persistent grid
   int epi;                                 // 0 linear, 1 bias+ReLU, 2 bias+ReLU+maxpool2
   int oHb, oWb, ooff;                      // output buffer geometry
+  int nterm;                               // K-step terms per (tap, channel chunk): 1 = bf16, 3 = split planes (hi,hi), (hi,mid), (mid,hi)
   const float* bias;
   __nv_bfloat16* out;
+  __nv_bfloat16* out_mid;                  // split: mid plane of the output (same geometry), else NULL
   unsigned char* pool_arg;
   const __nv_bfloat16* relu_ref;           // epi 3: out = acc * (relu_ref > 0), relu_ref buffer [B,rHb,rWb,Cout] at +roff
   int rHb, rWb, roff;
@@ -77,7 +79,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cchunks = a.Cin / CV_BK;
-  const int nkb = 9 * cchunks;
+  const int nkb = 9 * cchunks * a.nterm;
   const long long items = (long long)a.pix_tiles * a.n_tiles;
   // item -> (pixel tile, channel block): channel blocks of one pixel tile are adjacent, so the CTAs of a wave share A
   auto decode = [&](long long item, int& b0, int& y0, int& x0, int& n0) {
@@ -108,7 +110,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if constexpr (RESB) {
       if (blockIdx.x < items) {
         mbar_arrive_expect_tx(bres, 9 * CV_B_BYTES);
-        for (int tap = 0; tap < 9; ++tap) tma_load_2d(sB + tap * CV_B_BYTES, &tmB, tap * a.Cin, 0, bres);
+        for (int tap = 0; tap < 9; ++tap) tma_load_3d(sB + tap * CV_B_BYTES, &tmB, tap * a.Cin, 0, 0, bres);
       }
     }
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
@@ -116,13 +118,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       decode(item, b0, y0, x0, n0);
       for (int tap = 0; tap < 9; ++tap) {
         const int dy = tap / 3, dx = tap - 3 * dy;
-        for (int cc = 0; cc < cchunks; ++cc, ++kg) {
-          const int s = kg % CV_STAGES;
-          const uint32_t ph = (kg / CV_STAGES) & 1u;
-          mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], RESB ? CV_A_BYTES : CV_A_BYTES + CV_B_BYTES);
-          tma_load_4d(sA + s * CV_A_BYTES, &tmA, cc * CV_BK, x0 + dx, y0 + dy, b0, &full[s]);
-          if constexpr (!RESB) tma_load_2d(sB + s * CV_B_BYTES, &tmB, tap * a.Cin + cc * CV_BK, n0, &full[s]);
+        for (int cc = 0; cc < cchunks; ++cc) {
+          for (int term = 0; term < a.nterm; ++term, ++kg) {
+            const int s = kg % CV_STAGES;
+            const uint32_t ph = (kg / CV_STAGES) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&full[s], RESB ? CV_A_BYTES : CV_A_BYTES + CV_B_BYTES);
+            tma_load_5d(sA + s * CV_A_BYTES, &tmA, cc * CV_BK, x0 + dx, y0 + dy, b0, term_plane_a(term), &full[s]);
+            if constexpr (!RESB) tma_load_3d(sB + s * CV_B_BYTES, &tmB, tap * a.Cin + cc * CV_BK, n0, term_plane_b(term), &full[s]);
+          }
         }
       }
     }
@@ -256,15 +260,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (valid && w == 0) {
           const size_t pix = ((size_t)b * a.oHb + (y >> 1) + a.ooff) * a.oWb + (x >> 1) + a.ooff;
           __nv_bfloat16* dst = a.out + pix * a.Cout + ch;
+          __nv_bfloat16* dmid = a.out_mid ? a.out_mid + pix * a.Cout + ch : nullptr;
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[i], v[i + 1]), t1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), t3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-            pk.x = *reinterpret_cast<unsigned int*>(&t0); pk.y = *reinterpret_cast<unsigned int*>(&t1);
-            pk.z = *reinterpret_cast<unsigned int*>(&t2); pk.w = *reinterpret_cast<unsigned int*>(&t3);
-            *reinterpret_cast<uint4*>(dst + i) = pk;
-          }
+          for (int i = 0; i < 32; i += 8) store8_planes(dst + i, dmid ? dmid + i : nullptr, v + i);
           if (a.pool_arg) {
             const size_t ppix = ((size_t)b * (a.Ho >> 1) + (y >> 1)) * (a.Wo >> 1) + (x >> 1);
             uint4* ad = reinterpret_cast<uint4*>(a.pool_arg + ppix * a.Cout + ch);
@@ -275,6 +273,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } else if (valid) {
         const size_t pix = ((size_t)b * a.oHb + y + a.ooff) * a.oWb + x + a.ooff;
         __nv_bfloat16* dst = a.out + pix * a.Cout + ch;
+        __nv_bfloat16* dmid = a.out_mid ? a.out_mid + pix * a.Cout + ch : nullptr;
         if (a.epi == 3) {
           const __nv_bfloat16* ref = a.relu_ref + (((size_t)b * a.rHb + y + a.roff) * a.rWb + x + a.roff) * a.Cout + ch;
 #pragma unroll
@@ -290,14 +289,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 pk;
-          __nv_bfloat162 t0 = __floats2bfloat162_rn(v[i], v[i + 1]), t1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-          __nv_bfloat162 t2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), t3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-          pk.x = *reinterpret_cast<unsigned int*>(&t0); pk.y = *reinterpret_cast<unsigned int*>(&t1);
-          pk.z = *reinterpret_cast<unsigned int*>(&t2); pk.w = *reinterpret_cast<unsigned int*>(&t3);
-          *reinterpret_cast<uint4*>(dst + i) = pk;
-        }
+        for (int i = 0; i < 32; i += 8) store8_planes(dst + i, dmid ? dmid + i : nullptr, v + i);
       }
     }
     }   // items
@@ -319,7 +311,7 @@ __device__ __forceinline__ void rot_src(int r, int y, int x, int& ys, int& xs) {
   }
 }
 __global__ void expand_reg_reg_kernel(const float* __restrict__ psi, int Fo, int Fi, __nv_bfloat16* __restrict__ wmat,
-                                      __nv_bfloat16* __restrict__ wt) {
+                                      __nv_bfloat16* __restrict__ wt, int planes) {
   const int Cout = Fo * 4, Cin = Fi * 4;
   const long long total = (long long)Cout * 9 * Cin;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -332,9 +324,15 @@ __global__ void expand_reg_reg_kernel(const float* __restrict__ psi, int Fo, int
     int ys, xs;
     rot_src(r, y, x, ys, xs);
     const float w = psi[((((size_t)o * Fi + i) * 4 + ((s - r) & 3)) * 3 + ys) * 3 + xs];
-    const __nv_bfloat16 wb = __float2bfloat16(w);
+    __nv_bfloat16 wb, wm;
+    split_bf16(w, wb, wm);
     wmat[e] = wb;
-    if (wt) wt[((size_t)ci * 9 + (8 - tap)) * Cout + co] = wb;
+    const size_t te = ((size_t)ci * 9 + (8 - tap)) * Cout + co;
+    if (wt) wt[te] = wb;
+    if (planes == 2) {                     // mid planes behind the hi planes
+      wmat[total + e] = wm;
+      if (wt) wt[total + te] = wm;
+    }
   }
 }
 __global__ void expand_bias_kernel(const float* __restrict__ bias_f, int F, float* __restrict__ bias_ch) {
@@ -351,7 +349,8 @@ __global__ void expand_bias_kernel(const float* __restrict__ bias_f, int F, floa
 template <bool PLAIN>
 __global__ void __launch_bounds__(256)
 conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ state, const float* __restrict__ psi,
-                    const float* __restrict__ bias_f, int B, __nv_bfloat16* __restrict__ out, unsigned char* __restrict__ pool_arg) {
+                    const float* __restrict__ bias_f, int B, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_mid,
+                    unsigned char* __restrict__ pool_arg) {
   // weights of a PAIR of output channels interleaved: [pair][18 taps + bias + pad][2], read as ten warp-uniform
   // LDS.128 and fed to FFMA2 (the two halves are the two channels)
   __shared__ __align__(16) float sW[32][20][2];
@@ -396,7 +395,7 @@ conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ sta
         p0[i][j] = in ? __ldg(img + yy * 128 + xx) : 0.0f;
         p1[i][j] = in ? st : 0.0f;
       }
-    unsigned int packed[8];
+    unsigned int packed[8], packed_mid[8];
     unsigned int argp[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int cp = 0; cp < 8; ++cp) {
@@ -425,9 +424,11 @@ conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ sta
           if (w == 0 || acc.x > best.x) { best.x = acc.x; bw0 = w; }
           if (w == 0 || acc.y > best.y) { best.y = acc.y; bw1 = w; }
         }
-      const unsigned int b0 = (unsigned int)__bfloat16_as_ushort(__float2bfloat16(best.x));
-      const unsigned int b1 = (unsigned int)__bfloat16_as_ushort(__float2bfloat16(best.y));
-      packed[cp] = b0 | (b1 << 16);
+      __nv_bfloat16 h0, m0, h1, m1;
+      split_bf16(best.x, h0, m0);
+      split_bf16(best.y, h1, m1);
+      packed[cp] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
+      packed_mid[cp] = (unsigned int)__bfloat16_as_ushort(m0) | ((unsigned int)__bfloat16_as_ushort(m1) << 16);
       const int c = 2 * cp;
       if ((c & 3) == 0) argp[c >> 2] = 0u;
       argp[c >> 2] |= ((unsigned int)bw0 << (8 * (c & 3))) | ((unsigned int)bw1 << (8 * ((c + 1) & 3)));
@@ -436,6 +437,11 @@ conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ sta
     uint4* dst = reinterpret_cast<uint4*>(out + pix * 64 + cg * 16);
     dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    if (out_mid) {
+      uint4* dm = reinterpret_cast<uint4*>(out_mid + pix * 64 + cg * 16);
+      dm[0] = make_uint4(packed_mid[0], packed_mid[1], packed_mid[2], packed_mid[3]);
+      dm[1] = make_uint4(packed_mid[4], packed_mid[5], packed_mid[6], packed_mid[7]);
+    }
     if (pool_arg) {
       const size_t ppix = ((size_t)b * 64 + py) * 64 + px;
       *reinterpret_cast<uint4*>(pool_arg + ppix * 64 + cg * 16) = make_uint4(argp[0], argp[1], argp[2], argp[3]);
@@ -454,7 +460,7 @@ extern "C" int aur_equiv_expand_regular(const float* psi, int32_t Fo, int32_t Fi
   const long long total = (long long)Fo * 4 * 9 * Fi * 4;
   long long grid = (total + 255) / 256;
   if (grid > 148 * 16) grid = 148 * 16;
-  expand_reg_reg_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(psi, Fo, Fi, (__nv_bfloat16*)wmat, (__nv_bfloat16*)wt);
+  expand_reg_reg_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(psi, Fo, Fi, (__nv_bfloat16*)wmat, (__nv_bfloat16*)wt, tc_planes());
   AUR_LAUNCH_OK("expand_reg_reg_kernel");
   if (bias_f && bias_ch) {
     expand_bias_kernel<<<(Fo * 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(bias_f, Fo, bias_ch);
@@ -471,7 +477,8 @@ extern "C" int aur_equiv_conv0(const float* obs, const float* state, const float
   const long long total = (long long)B * 64 * 64 * 4;
   long long grid = (total + 255) / 256;
   if (grid > 148 * 32) grid = 148 * 32;
-  conv0_direct_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, state, psi, bias_f, B, (__nv_bfloat16*)out, pool_arg);
+  __nv_bfloat16* out_mid = tc_planes() == 2 ? (__nv_bfloat16*)out + (size_t)B * 66 * 66 * 64 : nullptr;
+  conv0_direct_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, state, psi, bias_f, B, (__nv_bfloat16*)out, out_mid, pool_arg);
   AUR_LAUNCH_OK("conv0_direct_kernel");
   return 0;
 }
@@ -484,7 +491,8 @@ extern "C" int aur_plain_conv0(const float* obs, const float* state, const float
   const long long total = (long long)B * 64 * 64;
   long long grid = (total + 255) / 256;
   if (grid > 148 * 32) grid = 148 * 32;
-  conv0_direct_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, state, weight, bias, B, (__nv_bfloat16*)out, pool_arg);
+  __nv_bfloat16* out_mid = tc_planes() == 2 ? (__nv_bfloat16*)out + (size_t)B * 66 * 66 * 64 : nullptr;
+  conv0_direct_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, state, weight, bias, B, (__nv_bfloat16*)out, out_mid, pool_arg);
   AUR_LAUNCH_OK("conv0_direct_kernel<plain>");
   return 0;
 }
@@ -508,6 +516,9 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   ConvDev d;
   d.B = c.B; d.Hb = c.Hb; d.Wb = c.Wb; d.Ho = c.Hb - 2; d.Wo = c.Wb - 2; d.Cin = c.Cin; d.Cout = c.Cout;
   d.epi = c.epilogue; d.oHb = c.out_Hb; d.oWb = c.out_Wb; d.ooff = c.out_off; d.bias = c.bias;
+  const int P = tc_planes();
+  d.nterm = P == 2 ? 3 : 1;
+  d.out_mid = P == 2 ? (__nv_bfloat16*)c.out + (size_t)c.B * c.out_Hb * c.out_Wb * c.Cout : nullptr;
   d.out = (__nv_bfloat16*)c.out; d.pool_arg = c.pool_arg; d.relu_ref = (const __nv_bfloat16*)c.relu_ref; d.rHb = c.ref_Hb; d.rWb = c.ref_Wb; d.roff = c.ref_off;
   if (c.epilogue == 3 && !c.relu_ref) { set_error("aur_conv3x3_bf16: epilogue 3 needs relu_ref"); return AUR_ERR_ARG; }
   if (c.epilogue == 2 && ((d.Ho | d.Wo) & 1)) { set_error("aur_conv3x3_bf16: pooling needs even output size"); return AUR_ERR_ARG; }
@@ -519,21 +530,24 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   d.tiles_y = (d.Ho + d.TH - 1) / d.TH;
   const long long img_groups = (c.B + d.NIMG - 1) / d.NIMG;
   CUtensorMap tmA, tmB;
-  const uint64_t dA[4] = {(uint64_t)c.Cin, (uint64_t)c.Wb, (uint64_t)c.Hb, (uint64_t)c.B};
-  const uint64_t sA[3] = {(uint64_t)c.Cin * 2, (uint64_t)c.Wb * c.Cin * 2, (uint64_t)c.Hb * c.Wb * c.Cin * 2};
-  const uint32_t bA[4] = {CV_BK, (uint32_t)d.TW, (uint32_t)d.TH, (uint32_t)d.NIMG};
-  const uint64_t dB[2] = {(uint64_t)9 * c.Cin, (uint64_t)c.Cout};
-  const uint64_t sB[1] = {(uint64_t)9 * c.Cin * 2};
+  // planes (hi / mid stacks) are the outermost tensor-map dimension of both operands
+  const uint64_t dA[5] = {(uint64_t)c.Cin, (uint64_t)c.Wb, (uint64_t)c.Hb, (uint64_t)c.B, (uint64_t)P};
+  const uint64_t sA[4] = {(uint64_t)c.Cin * 2, (uint64_t)c.Wb * c.Cin * 2, (uint64_t)c.Hb * c.Wb * c.Cin * 2,
+                          (uint64_t)c.B * c.Hb * c.Wb * c.Cin * 2};
+  const uint32_t bA[5] = {CV_BK, (uint32_t)d.TW, (uint32_t)d.TH, (uint32_t)d.NIMG, 1};
+  const uint64_t dB[3] = {(uint64_t)9 * c.Cin, (uint64_t)c.Cout, (uint64_t)P};
+  const uint64_t sB[2] = {(uint64_t)9 * c.Cin * 2, (uint64_t)9 * c.Cin * c.Cout * 2};
   // pooled layers with a shallow contraction (K = 9 x 64 / 9 x 128) are epilogue-bound: channel-major accumulator there
-  const bool swap = c.epilogue == 2 && c.Cin == 64 && conv_swap_enabled();       // Cin 128 (layer 2) is faster on 256-wide tiles
+  // (split planes: the pixel-major kernels only - the resident-weight variant has no room for two weight planes)
+  const bool swap = c.epilogue == 2 && c.Cin == 64 && P == 1 && conv_swap_enabled();       // Cin 128 (layer 2) is faster on 256-wide tiles
   const bool resb = swap && c.Cout <= 128;
   const bool wide = !swap && c.Cout % 256 == 0;
   const bool narrow = !swap && c.Cout <= 64;     // e.g. the backward-data convolution into the 64-channel layer-0 output: N = 64 MMAs
   const int BN = wide ? 256 : (narrow ? 64 : 128);
-  const uint32_t bB[2] = {CV_BK, (uint32_t)BN};
+  const uint32_t bB[3] = {CV_BK, (uint32_t)BN, 1};
   int rc;
-  if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, c.in, dA, sA, bA))) return rc;
-  if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.wmat, dB, sB, bB))) return rc;
+  if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, c.in, dA, sA, bA))) return rc;
+  if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.wmat, dB, sB, bB))) return rc;
   static DeviceOnce attr;
   if (attr.first()) {
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<128>::SMEM));

@@ -17,7 +17,7 @@ namespace aur {
 namespace tc {
 
 int launch_conv0_wgrad_tc(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg, int B,
-                          float* dw0, float* dbias_ch, cudaStream_t s, bool plain = false);
+                          float* dw0, float* dbias_ch, cudaStream_t s, bool plain = false, int parts = 2);
 
 constexpr int WG_BM = 128, WG_BN = 128, WG_BK = 64, WG_STAGES = 3, WG_TAPS = 3;
 constexpr int WG_A_BYTES = WG_BM * WG_BK * 2, WG_B_BYTES = WG_BN * WG_BK * 2;
@@ -33,7 +33,7 @@ constexpr size_t WG_SMEM = (size_t)WG_STAGES * (WG_A_BYTES + WG_TAPS * WG_B_BYTE
 // (row) coordinate of the input map, which TMA takes at element granularity.
 __global__ void __launch_bounds__(256, 1)
 wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Cout, int Cin,
-                long long Q, int base_off, int Wb, int n_tiles, float* __restrict__ dwmat) {
+                long long Q, int base_off, int Wb, int n_tiles, float* __restrict__ dwmat, int nterm) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   unsigned char* sA = smem;
@@ -53,7 +53,8 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const long long kb_lo = (long long)blockIdx.z * per;
   long long kb_hi = kb_lo + per;
   if (kb_hi > nkb_total) kb_hi = nkb_total;
-  const int nkb = kb_hi > kb_lo ? (int)(kb_hi - kb_lo) : 0;
+  // split operand planes: the (hi,hi), (hi,mid), (mid,hi) products are extra K steps over the same pixel block
+  const int nkb = (kb_hi > kb_lo ? (int)(kb_hi - kb_lo) : 0) * nterm;
   const bool c64 = Cin <= 64;
 
   if (threadIdx.x == 0) {
@@ -74,19 +75,20 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int i = 0; i < nkb; ++i) {
         const int s = i % WG_STAGES;
         const uint32_t ph = (i / WG_STAGES) & 1u;
-        const long long k0 = (kb_lo + i) * WG_BK;
+        const int term = i % nterm, pa = term_plane_a(term), pb = term_plane_b(term);
+        const long long k0 = (kb_lo + i / nterm) * WG_BK;
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&full[s], WG_A_BYTES + WG_TAPS * (c64 ? WG_B_BYTES / 2 : WG_B_BYTES));
         unsigned char* a = sA + s * WG_A_BYTES;
-        tma_load_2d(a, &tmA, m0, (int)k0, &full[s]);
-        tma_load_2d(a + 8192, &tmA, m0 + 64, (int)k0, &full[s]);
+        tma_load_3d(a, &tmA, m0, (int)k0, pa, &full[s]);
+        tma_load_3d(a + 8192, &tmA, m0 + 64, (int)k0, pa, &full[s]);
         for (int dx = 0; dx < WG_TAPS; ++dx) {
           if (c64) {            // one 64-channel box per tap, the three taps 8192 B apart: ONE N = 192 operand
-            tma_load_2d(sB + s * WG_TAPS * WG_B_BYTES + dx * 8192, &tmB, 0, (int)(k0 + off + dx), &full[s]);
+            tma_load_3d(sB + s * WG_TAPS * WG_B_BYTES + dx * 8192, &tmB, 0, (int)(k0 + off + dx), pb, &full[s]);
           } else {
             unsigned char* b = sB + (s * WG_TAPS + dx) * WG_B_BYTES;
-            tma_load_2d(b, &tmB, n0, (int)(k0 + off + dx), &full[s]);
-            tma_load_2d(b + 8192, &tmB, n0 + 64, (int)(k0 + off + dx), &full[s]);
+            tma_load_3d(b, &tmB, n0, (int)(k0 + off + dx), pb, &full[s]);
+            tma_load_3d(b + 8192, &tmB, n0 + 64, (int)(k0 + off + dx), pb, &full[s]);
           }
         }
       }
@@ -154,9 +156,13 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // colsum (nullable): the bias gradient of the layer, out[c / group] += sum over all written positions of dy[.., c] - what
 // colsum_bf16_kernel would compute from dy, taken here from registers instead of re-reading the buffer.  The grid is a
 // multiple of C / 8 threads (C / 8 divides 256), so a thread keeps one channel group for its whole grid-stride loop.
+// dpool_mid / dy_mid (nullable): the mid planes of the split representation, routed exactly like the hi plane (the ReLU mask
+// reads the hi plane of `act`: hi > 0 <=> value > 0).
 __global__ void unpool_relu_bwd_kernel(int B, int Hp, int Wp, int C, const __nv_bfloat16* __restrict__ dpool,
+                                       const __nv_bfloat16* __restrict__ dpool_mid,
                                        const __nv_bfloat16* __restrict__ act, int aHb, int aWb, int aoff,
-                                       const unsigned char* __restrict__ arg, __nv_bfloat16* __restrict__ dy, int dHb, int dWb,
+                                       const unsigned char* __restrict__ arg, __nv_bfloat16* __restrict__ dy,
+                                       __nv_bfloat16* __restrict__ dy_mid, int dHb, int dWb,
                                        int doff, int group, float* __restrict__ colsum) {
   __shared__ float sacc[1024];
   float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -170,23 +176,31 @@ __global__ void unpool_relu_bwd_kernel(int B, int Hp, int Wp, int C, const __nv_
     const int b = (int)r;
     const size_t pp = (((size_t)b * Hp + py) * Wp + px) * C + c8 * 8;
     const uint4 g = *reinterpret_cast<const uint4*>(dpool + pp);
+    uint4 gm = make_uint4(0u, 0u, 0u, 0u);
+    if (dpool_mid) gm = *reinterpret_cast<const uint4*>(dpool_mid + pp);
     const uint4 av = *reinterpret_cast<const uint4*>(act + (((size_t)b * aHb + py + aoff) * aWb + px + aoff) * C + c8 * 8);
     const uint2 ar = *reinterpret_cast<const uint2*>(arg + pp);
     const unsigned short* gs = reinterpret_cast<const unsigned short*>(&g);
+    const unsigned short* gms = reinterpret_cast<const unsigned short*>(&gm);
     const unsigned short* as = reinterpret_cast<const unsigned short*>(&av);
     const unsigned char* ab = reinterpret_cast<const unsigned char*>(&ar);
-    unsigned short o[4][8];
+    unsigned short o[4][8], om[4][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const bool pos = (as[i] & 0x7FFFu) != 0 && !(as[i] & 0x8000u);
 #pragma unroll
-      for (int w = 0; w < 4; ++w) o[w][i] = (pos && ab[i] == w) ? gs[i] : (unsigned short)0;
-      if (pos && ab[i] < 4) bsum[i] += __uint_as_float((unsigned int)gs[i] << 16);
+      for (int w = 0; w < 4; ++w) {
+        o[w][i] = (pos && ab[i] == w) ? gs[i] : (unsigned short)0;
+        om[w][i] = (pos && ab[i] == w) ? gms[i] : (unsigned short)0;
+      }
+      if (pos && ab[i] < 4) bsum[i] += __uint_as_float((unsigned int)gs[i] << 16) + __uint_as_float((unsigned int)gms[i] << 16);
     }
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const int y = 2 * py + (w >> 1) + doff, x = 2 * px + (w & 1) + doff;
-      *reinterpret_cast<uint4*>(dy + (((size_t)b * dHb + y) * dWb + x) * C + c8 * 8) = *reinterpret_cast<const uint4*>(o[w]);
+      const size_t di = (((size_t)b * dHb + y) * dWb + x) * C + c8 * 8;
+      *reinterpret_cast<uint4*>(dy + di) = *reinterpret_cast<const uint4*>(o[w]);
+      if (dy_mid) *reinterpret_cast<uint4*>(dy_mid + di) = *reinterpret_cast<const uint4*>(om[w]);
     }
   }
   if (colsum) {
@@ -305,6 +319,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(long long Q, int C, co
 constexpr int C0W_PIX = 32;               // pooled pixels staged per barrier pair
 __global__ void __launch_bounds__(256)
 conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ state, const __nv_bfloat16* __restrict__ da1,
+                   const __nv_bfloat16* __restrict__ da1_mid /*nullable*/,
                    const __nv_bfloat16* __restrict__ a1 /*[B,66,66,64]*/, const unsigned char* __restrict__ arg, int B,
                    float* __restrict__ dw0 /*[64][2][9] expanded-channel gradient*/, float* __restrict__ dbias_ch /*[64]*/) {
   __shared__ __align__(16) float patch[C0W_PIX][2][4][4];
@@ -334,10 +349,11 @@ conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ stat
     __syncthreads();
     // this thread's channel over 8 of the staged pixels; the three per-pixel loads of all 8 are issued up front
     // raw loads first (nothing consumes them inside this loop, so all 24 are in flight together), conversions after
-    unsigned short ar[C0W_PIX / 4], gr[C0W_PIX / 4];
+    unsigned short ar[C0W_PIX / 4], gr[C0W_PIX / 4], gmr[C0W_PIX / 4];
     unsigned char wr[C0W_PIX / 4];
     const unsigned short* a1u = reinterpret_cast<const unsigned short*>(a1);
     const unsigned short* da1u = reinterpret_cast<const unsigned short*>(da1);
+    const unsigned short* da1mu = reinterpret_cast<const unsigned short*>(da1_mid);
 #pragma unroll
     for (int k = 0; k < C0W_PIX / 4; ++k) {
       long long pix = base + sub + 4 * k;
@@ -346,6 +362,7 @@ conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ stat
       const int px = (int)(pix & 63), py = (int)((pix >> 6) & 63), b = (int)(pix >> 12);
       ar[k] = __ldg(a1u + (((size_t)b * 66 + py + 1) * 66 + px + 1) * 64 + co);
       gr[k] = __ldg(da1u + (size_t)pix * 64 + co);
+      gmr[k] = da1mu ? __ldg(da1mu + (size_t)pix * 64 + co) : (unsigned short)0;
       wr[k] = __ldg(arg + (size_t)pix * 64 + co);
       if (!ok) ar[k] = 0;
     }
@@ -354,7 +371,7 @@ conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ stat
 #pragma unroll
     for (int k = 0; k < C0W_PIX / 4; ++k) {
       av[k] = __uint_as_float((unsigned int)ar[k] << 16);
-      gv[k] = __uint_as_float((unsigned int)gr[k] << 16);
+      gv[k] = __uint_as_float((unsigned int)gr[k] << 16) + __uint_as_float((unsigned int)gmr[k] << 16);
       wv[k] = wr[k];
     }
 #pragma unroll
@@ -405,20 +422,34 @@ __global__ void project_conv0_kernel(const float* __restrict__ dw0, const float*
 
 // ---- elementwise helpers ---------------------------------------------------------------------------
 // out_bf16[r][c] = relu(in_f32[r][c] + bias[c])
+// (every helper: out_mid nullable = mid plane of the split representation)
 __global__ void bias_relu_kernel(long long n, int C, const float* __restrict__ in, const float* __restrict__ bias,
-                                 __nv_bfloat16* __restrict__ out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16(fmaxf(in[i] + bias[(int)(i % C)], 0.0f));
+                                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_mid) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    __nv_bfloat16 h, m;
+    split_bf16(fmaxf(in[i] + bias[(int)(i % C)], 0.0f), h, m);
+    out[i] = h;
+    if (out_mid) out_mid[i] = m;
+  }
 }
 // out_bf16 = g_f32 * (ref_bf16 > 0)
 __global__ void relu_mask_kernel(long long n, const float* __restrict__ g, const __nv_bfloat16* __restrict__ ref,
-                                 __nv_bfloat16* __restrict__ out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16(__bfloat162float(ref[i]) > 0.0f ? g[i] : 0.0f);
+                                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_mid) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    __nv_bfloat16 h, m;
+    split_bf16(__bfloat162float(ref[i]) > 0.0f ? g[i] : 0.0f, h, m);
+    out[i] = h;
+    if (out_mid) out_mid[i] = m;
+  }
 }
-__global__ void f32_to_bf16_kernel(long long n, const float* __restrict__ in, __nv_bfloat16* __restrict__ out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16(in[i]);
+__global__ void f32_to_bf16_kernel(long long n, const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                   __nv_bfloat16* __restrict__ out_mid) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    __nv_bfloat16 h, m;
+    split_bf16(in[i], h, m);
+    out[i] = h;
+    if (out_mid) out_mid[i] = m;
+  }
 }
 
 // ---- heads + loss: one warp per sample --------------------------------------------------------------
@@ -436,6 +467,7 @@ struct HeadLossDev {
   int clip_vloss;
   __nv_bfloat16* d_a_out;  // [B,16] gradient wrt actor head output (bf16, zero padded)
   __nv_bfloat16* d_c_h;    // [B,512] gradient wrt critic head-1 pre-activation
+  __nv_bfloat16 *d_a_out_mid, *d_c_h_mid;   // split: mid planes, else NULL
   float* d_head;           // [10 + 128 + 1 + 512]: d a_bias | d c_w2 | d c_b2 | d c_bias1(per channel)
   float* stats;            // [8] sums: policy loss, value loss (x vf_c as the reference), entropy, -logr, r-1-logr, clip
   float* value_out;        // [B]
@@ -539,7 +571,12 @@ __global__ void __launch_bounds__(256) head_loss_kernel(HeadLossDev a) {
         d10[5 + d] = g_logp * dls[d] + g_H * o10[5 + d];
       }
 #pragma unroll
-      for (int k = 0; k < 16; ++k) a.d_a_out[(size_t)b * 16 + k] = __float2bfloat16(k < 10 ? d10[k] : 0.0f);
+      for (int k = 0; k < 16; ++k) {
+        __nv_bfloat16 h, m;
+        split_bf16(k < 10 ? d10[k] : 0.0f, h, m);
+        a.d_a_out[(size_t)b * 16 + k] = h;
+        if (a.d_a_out_mid) a.d_a_out_mid[(size_t)b * 16 + k] = m;
+      }
 #pragma unroll
       for (int k = 0; k < 10; ++k) dbias_a[k] += d10[k];
       db2 += dv;
@@ -553,7 +590,10 @@ __global__ void __launch_bounds__(256) head_loss_kernel(HeadLossDev a) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const float g = (r == field_arg[f] && hv[f * 4 + r] > 0.0f) ? gp : 0.0f;
-        a.d_c_h[(size_t)b * 512 + fld * 4 + r] = __float2bfloat16(g);
+        __nv_bfloat16 gh, gm;
+        split_bf16(g, gh, gm);
+        a.d_c_h[(size_t)b * 512 + fld * 4 + r] = gh;
+        if (a.d_c_h_mid) a.d_c_h_mid[(size_t)b * 512 + fld * 4 + r] = gm;
         if (g != 0.0f) atomicAdd(a.d_head + 10 + 128 + 1 + fld * 4 + r, g);   // d c_bias1 (per channel)
       }
     }
@@ -662,6 +702,7 @@ struct PlainHeadDev {
   int clip_vloss;
   __nv_bfloat16* d_a_out;  // [B,16]
   __nv_bfloat16* d_c_h;    // [B,128]
+  __nv_bfloat16 *d_a_out_mid, *d_c_h_mid;   // split: mid planes, else NULL
   float* d_head;           // [5 + 5 + 128 + 1 + 128]: d a_bias | d logstd | d c_w2 | d c_b2 | d c_bias1
   float* stats;
   float* value_out;
@@ -731,7 +772,12 @@ __global__ void __launch_bounds__(256) plain_head_loss_kernel(PlainHeadDev a) {
       if (a.value_out) a.value_out[b] = value;
       if (a.logp_out) a.logp_out[b] = logp;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) a.d_a_out[(size_t)b * 16 + k] = __float2bfloat16(k < 5 ? g_logp * dmean[k < 5 ? k : 0] : 0.0f);
+      for (int k = 0; k < 16; ++k) {
+        __nv_bfloat16 h, m;
+        split_bf16(k < 5 ? g_logp * dmean[k < 5 ? k : 0] : 0.0f, h, m);
+        a.d_a_out[(size_t)b * 16 + k] = h;
+        if (a.d_a_out_mid) a.d_a_out_mid[(size_t)b * 16 + k] = m;
+      }
 #pragma unroll
       for (int d = 0; d < 5; ++d) { dmu_acc[d] += g_logp * dmean[d]; dls_acc[d] += g_logp * dls[d] + g_H; }
       db2 += dv;
@@ -740,7 +786,10 @@ __global__ void __launch_bounds__(256) plain_head_loss_kernel(PlainHeadDev a) {
     for (int f = 0; f < 4; ++f) {
       const int c = lane + 32 * f;
       const float g = h[f] > 0.0f ? dv * a.c_w2[c] : 0.0f;
-      a.d_c_h[(size_t)b * 128 + c] = __float2bfloat16(g);
+      __nv_bfloat16 gh, gm;
+      split_bf16(g, gh, gm);
+      a.d_c_h[(size_t)b * 128 + c] = gh;
+      if (a.d_c_h_mid) a.d_c_h_mid[(size_t)b * 128 + c] = gm;
       dw2[f] += dv * h[f];
       db1[f] += g;
     }
@@ -814,12 +863,13 @@ extern "C" int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const voi
     set_error("aur_wgrad3x3_bf16: bad arguments (channel counts must be multiples of 8)"); return AUR_ERR_ARG;
   }
   CUtensorMap tmA, tmB;
-  const uint64_t dA[2] = {(uint64_t)Cout, (uint64_t)Q}, dB[2] = {(uint64_t)Cin, (uint64_t)Q};
-  const uint64_t stA[1] = {(uint64_t)Cout * 2}, stB[1] = {(uint64_t)Cin * 2};
-  const uint32_t bx[2] = {64, WG_BK};
+  const int P = tc_planes();
+  const uint64_t dA[3] = {(uint64_t)Cout, (uint64_t)Q, (uint64_t)P}, dB[3] = {(uint64_t)Cin, (uint64_t)Q, (uint64_t)P};
+  const uint64_t stA[2] = {(uint64_t)Cout * 2, (uint64_t)Cout * Q * 2}, stB[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * Q * 2};
+  const uint32_t bx[3] = {64, WG_BK, 1};
   int rc;
-  if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dy, dA, stA, bx))) return rc;
-  if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dB, stB, bx))) return rc;
+  if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dy, dA, stA, bx))) return rc;
+  if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, x, dB, stB, bx))) return rc;
   static DeviceOnce attr;
   if (attr.first()) {
     AUR_CUDA_OK(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
@@ -834,7 +884,7 @@ extern "C" int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const voi
     if (split_k < 1) split_k = 1;
   }
   dim3 grid((unsigned)(mt * nt), 3, (unsigned)split_k);
-  wgrad3x3_kernel<<<grid, 256, WG_SMEM, (cudaStream_t)stream>>>(tmA, tmB, Cout, Cin, (long long)Q, base_off, Wb, nt, dwmat);
+  wgrad3x3_kernel<<<grid, 256, WG_SMEM, (cudaStream_t)stream>>>(tmA, tmB, Cout, Cin, (long long)Q, base_off, Wb, nt, dwmat, P == 2 ? 3 : 1);
   AUR_LAUNCH_OK("wgrad3x3_kernel");
   return 0;
 }
@@ -847,9 +897,12 @@ extern "C" int aur_unpool_relu_bwd_colsum(int32_t B, int32_t Hp, int32_t Wp, int
     set_error("aur_unpool_relu_bwd_colsum: needs C / 8 dividing 256, C <= 1024 and group >= 1"); return AUR_ERR_ARG;
   }
   const long long total = (long long)B * Hp * Wp * (C / 8);
+  const bool split = tc_planes() == 2;
+  const __nv_bfloat16* dpool_mid = split ? (const __nv_bfloat16*)dpool + (size_t)B * Hp * Wp * C : nullptr;
+  __nv_bfloat16* dy_mid = split ? (__nv_bfloat16*)dy + (size_t)B * dHb * dWb * C : nullptr;
   unpool_relu_bwd_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
-      B, Hp, Wp, C, (const __nv_bfloat16*)dpool, (const __nv_bfloat16*)act, aHb, aWb, aoff, arg, (__nv_bfloat16*)dy, dHb, dWb, doff,
-      group, colsum_out);
+      B, Hp, Wp, C, (const __nv_bfloat16*)dpool, dpool_mid, (const __nv_bfloat16*)act, aHb, aWb, aoff, arg, (__nv_bfloat16*)dy,
+      dy_mid, dHb, dWb, doff, group, colsum_out);
   AUR_LAUNCH_OK("unpool_relu_bwd_kernel");
   return 0;
 }
@@ -897,6 +950,11 @@ extern "C" int aur_plain_conv0_wgrad(const float* obs, const float* state, const
   AUR_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(float) * (64 * 18 + 64), s));
   int rc = aur::tc::launch_conv0_wgrad_tc(obs, state, da1, a1, arg, B, scratch, scratch + 64 * 18, s, true);
   if (rc) return rc;
+  if (tc_planes() == 2) {       // mid plane of the gradient against the hi part of the input views (mid x mid is dropped)
+    rc = aur::tc::launch_conv0_wgrad_tc(obs, state, (const __nv_bfloat16*)da1 + (size_t)B * 64 * 64 * 64, a1, arg, B, scratch,
+                                         scratch + 64 * 18, s, true, 1);
+    if (rc) return rc;
+  }
   AUR_CUDA_OK(cudaMemcpyAsync(dweight, scratch, sizeof(float) * 16 * 18, cudaMemcpyDeviceToDevice, s));
   AUR_CUDA_OK(cudaMemcpyAsync(dbias, scratch + 64 * 18, sizeof(float) * 16, cudaMemcpyDeviceToDevice, s));
   return 0;
@@ -913,12 +971,18 @@ extern "C" int aur_equiv_conv0_wgrad(const float* obs, const float* state, const
   static int simt = -1;                              // AUR_CONV0_WGRAD=simt keeps the fp32 SIMT kernel (cross-check)
   if (simt < 0) { const char* e = getenv("AUR_CONV0_WGRAD"); simt = (e && e[0] == 's') ? 1 : 0; }
   if (simt) {
-    conv0_wgrad_kernel<<<148 * 8, 256, 0, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg, B, scratch,
-                                              scratch + 64 * 18);
+    conv0_wgrad_kernel<<<148 * 8, 256, 0, s>>>(obs, state, (const __nv_bfloat16*)da1,
+                                              tc_planes() == 2 ? (const __nv_bfloat16*)da1 + (size_t)B * 64 * 64 * 64 : nullptr,
+                                              (const __nv_bfloat16*)a1, arg, B, scratch, scratch + 64 * 18);
     AUR_LAUNCH_OK("conv0_wgrad_kernel");
   } else {
     int rc = aur::tc::launch_conv0_wgrad_tc(obs, state, da1, a1, arg, B, scratch, scratch + 64 * 18, s);
     if (rc) return rc;
+    if (tc_planes() == 2) {
+      rc = aur::tc::launch_conv0_wgrad_tc(obs, state, (const __nv_bfloat16*)da1 + (size_t)B * 64 * 64 * 64, a1, arg, B, scratch,
+                                           scratch + 64 * 18, s, false, 1);
+      if (rc) return rc;
+    }
   }
   project_conv0_kernel<<<(64 * 18 + 255) / 256, 256, 0, s>>>(scratch, scratch + 64 * 18, dpsi, dbias_f);
   AUR_LAUNCH_OK("project_conv0_kernel");
@@ -927,14 +991,16 @@ extern "C" int aur_equiv_conv0_wgrad(const float* obs, const float* state, const
 
 extern "C" int aur_bias_relu_bf16(int64_t rows, int32_t C, const float* in, const float* bias, void* out, void* stream) {
   if (rows <= 0 || C <= 0 || !in || !bias || !out) { set_error("aur_bias_relu_bf16: bad arguments"); return AUR_ERR_ARG; }
-  bias_relu_kernel<<<grid_for(rows * C), 256, 0, (cudaStream_t)stream>>>(rows * C, C, in, bias, (__nv_bfloat16*)out);
+  __nv_bfloat16* om = tc_planes() == 2 ? (__nv_bfloat16*)out + rows * C : nullptr;
+  bias_relu_kernel<<<grid_for(rows * C), 256, 0, (cudaStream_t)stream>>>(rows * C, C, in, bias, (__nv_bfloat16*)out, om);
   AUR_LAUNCH_OK("bias_relu_kernel");
   return 0;
 }
 extern "C" int aur_relu_mask_bf16(int64_t n, const float* g, const void* ref, void* out, void* stream) {
   if (n <= 0 || !g || !out) { set_error("aur_relu_mask_bf16: bad arguments"); return AUR_ERR_ARG; }
-  if (ref) relu_mask_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, g, (const __nv_bfloat16*)ref, (__nv_bfloat16*)out);
-  else f32_to_bf16_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, g, (__nv_bfloat16*)out);
+  __nv_bfloat16* om = tc_planes() == 2 ? (__nv_bfloat16*)out + n : nullptr;
+  if (ref) relu_mask_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, g, (const __nv_bfloat16*)ref, (__nv_bfloat16*)out, om);
+  else f32_to_bf16_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, g, (__nv_bfloat16*)out, om);
   AUR_LAUNCH_OK("relu_mask_kernel");
   return 0;
 }
@@ -950,6 +1016,8 @@ extern "C" int aur_equiv_head_loss(const aur_equiv_head_args* h, void* stream) {
   d.clip = h->clip_coeff; d.clip_lo = (float)(1.0 - (double)h->clip_coeff); d.clip_hi = (float)(1.0 + (double)h->clip_coeff);
   d.ent_c = h->entropy_coeff; d.vf_c = h->value_coeff; d.inv_m = (float)(1.0 / (double)h->m_total); d.clip_vloss = h->clip_vloss;
   d.d_a_out = (__nv_bfloat16*)h->d_a_out; d.d_c_h = (__nv_bfloat16*)h->d_c_h; d.d_head = h->d_head; d.stats = h->stats;
+  d.d_a_out_mid = tc_planes() == 2 ? d.d_a_out + (size_t)h->B * 16 : nullptr;
+  d.d_c_h_mid = tc_planes() == 2 ? d.d_c_h + (size_t)h->B * 512 : nullptr;
   d.value_out = h->value_out; d.logp_out = h->logp_out;
   const unsigned grid = grid_for((long long)h->B * 32, 256, 148 * 4);
   head_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d);
@@ -1014,6 +1082,8 @@ extern "C" int aur_plain_head_loss(const aur_plain_head_args* h, void* stream) {
   d.clip = h->clip_coeff; d.clip_lo = (float)(1.0 - (double)h->clip_coeff); d.clip_hi = (float)(1.0 + (double)h->clip_coeff);
   d.ent_c = h->entropy_coeff; d.vf_c = h->value_coeff; d.inv_m = (float)(1.0 / (double)h->m_total); d.clip_vloss = h->clip_vloss;
   d.d_a_out = (__nv_bfloat16*)h->d_a_out; d.d_c_h = (__nv_bfloat16*)h->d_c_h; d.d_head = h->d_head; d.stats = h->stats;
+  d.d_a_out_mid = tc_planes() == 2 ? d.d_a_out + (size_t)h->B * 16 : nullptr;
+  d.d_c_h_mid = tc_planes() == 2 ? d.d_c_h + (size_t)h->B * 128 : nullptr;
   d.value_out = h->value_out; d.logp_out = h->logp_out;
   plain_head_loss_kernel<<<grid_for((long long)h->B * 32, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(d);
   AUR_LAUNCH_OK("plain_head_loss_kernel");

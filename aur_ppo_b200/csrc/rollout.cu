@@ -410,6 +410,12 @@ static size_t policy_smem_bytes(const aur_policy_desc& p, int threads, bool need
   return f * sizeof(float);
 }
 
+// the 64-wide kernels keep BOTH nets in shared memory (register-resident activations): deep policies (e.g. the reference's
+// shipped 10-layer checkpoint, 328 KB of weights) take the runtime-shape path, which can read the weights from global / L1
+static bool fits_compiled_kernel(const aur_policy_desc& p) {
+  return is_compiled_width(p) && policy_smem_bytes(p, 256, p.num_layers >= 3) <= (size_t)227 * 1024;
+}
+
 template <class K>
 static int launch_cfg(K kernel, size_t smem) {
   if (smem > 227 * 1024) { set_error("policy does not fit shared memory (%zu B); no fallback", smem); return AUR_ERR_UNSUPPORTED; }
@@ -506,7 +512,7 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
   RolloutDev d = to_dev(a);
   cudaStream_t s = (cudaStream_t)stream;
   const int sms = sm_count();
-  if (!is_compiled_width(a.policy)) {
+  if (!fits_compiled_kernel(a.policy)) {
     // runtime-width policy: one env per thread, both nets in the sequential kernel
     if (((uintptr_t)a.params & 15) != 0) { set_error("aur_rollout: params must be 16-byte aligned"); return AUR_ERR_ARG; }
     int block = round_up((int)((a.N + sms - 1) / sms < 256 ? (a.N + sms - 1) / sms : 256), 32);
@@ -585,7 +591,7 @@ extern "C" int aur_policy_act(const aur_policy_desc* desc, const float* params, 
   d.obs_dim = desc->obs_dim; d.act_dim = desc->act_dim; d.nl = desc->num_layers; d.continuous = desc->continuous;
   d.hid = desc->hidden_dim; d.dyn_smem = 0;
   d.params = params; d.actions_in = actions_in; d.seed = seed; d.greedy = greedy ? 1 : 0;
-  if (!is_compiled_width(*desc)) {
+  if (!fits_compiled_kernel(*desc)) {
     if (((uintptr_t)params & 15) != 0) { set_error("aur_policy_evaluate: params must be 16-byte aligned"); return AUR_ERR_ARG; }
     int block = 128;
     const size_t smem = dyn_launch_shape(*desc, block, d.dyn_smem);

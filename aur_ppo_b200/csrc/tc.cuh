@@ -158,6 +158,20 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -171,6 +185,41 @@ EncodeTiledFn encode_tiled_fn();
 // 128-B swizzle (box[0] * elem_bytes must be 128).
 int make_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box);
+
+
+// ---- operand precision of the row-X tensor-core entry points (aur_tc_set_precision) -------------------------------
+// 1 plane : bf16 operands (fast mode, below the reference's fp32 arithmetic).
+// 2 planes: every bf16 tensor is a stack [2][...] of a HI plane bf16(v) and a MID plane bf16(v - hi), |v - hi - mid| <=
+//           2^-17 |v|; contractions issue hi*hi + hi*mid + mid*hi with fp32 accumulation in TMEM (the mid*mid term,
+//           <= 2^-16 of the product, is dropped): fp32-class results on the bf16 tensor pipe at 3x the MMA work.
+//           The planes are walked as extra K steps of the same pipelines: plane index = outermost TMA coordinate.
+int tc_planes();
+// K-step term -> (plane of the first operand, plane of the second operand): (hi,hi), (hi,mid), (mid,hi)
+__host__ __device__ __forceinline__ int term_plane_a(int term) { return term == 2 ? 1 : 0; }
+__host__ __device__ __forceinline__ int term_plane_b(int term) { return term == 1 ? 1 : 0; }
+#ifdef __CUDACC__
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& mid) {
+  hi = __float2bfloat16_rn(v);
+  mid = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+// 8 consecutive values -> one 16-byte store of the hi plane and, if mid != NULL, one of the mid plane
+__device__ __forceinline__ void store8_planes(__nv_bfloat16* hi, __nv_bfloat16* mid, const float* v) {
+  uint4 ph, pm;
+  unsigned int* h = reinterpret_cast<unsigned int*>(&ph);
+  unsigned int* m = reinterpret_cast<unsigned int*>(&pm);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    h[j] = *reinterpret_cast<const unsigned int*>(&t);
+    if (mid) {
+      const __nv_bfloat162 r = __floats2bfloat162_rn(v[2 * j] - __low2float(t), v[2 * j + 1] - __high2float(t));
+      m[j] = *reinterpret_cast<const unsigned int*>(&r);
+    }
+  }
+  *reinterpret_cast<uint4*>(hi) = ph;
+  if (mid) *reinterpret_cast<uint4*>(mid) = pm;
+}
+#endif
 
 }  // namespace tc
 }  // namespace aur

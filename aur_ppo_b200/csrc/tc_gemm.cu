@@ -33,13 +33,16 @@ int make_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const vo
   return 0;
 }
 
+static thread_local int g_tc_planes = 1;
+int tc_planes() { return g_tc_planes; }
+
 constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 64, GEMM_STAGES = 4;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2, GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;
 constexpr size_t GEMM_SMEM = (size_t)GEMM_STAGES * (GEMM_A_BYTES + GEMM_B_BYTES) + 1024 + 256;
 
 __global__ void __launch_bounds__(256, 1)
 tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
-                    int M, int N, int K, int ldc) {
+                    int M, int N, int K, int ldc, int nterm) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   unsigned char* sA = smem;
@@ -51,7 +54,7 @@ tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * GEMM_BN;
-  const int nkb = (K + GEMM_BK - 1) / GEMM_BK;
+  const int nkb = ((K + GEMM_BK - 1) / GEMM_BK) * nterm;     // split operands: the (hi,hi), (hi,mid), (mid,hi) products are extra K steps
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -72,8 +75,9 @@ tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t ph = (kb / GEMM_STAGES) & 1u;
       mbar_wait(&empty[s], ph ^ 1u);
       mbar_arrive_expect_tx(&full[s], GEMM_A_BYTES + GEMM_B_BYTES);
-      tma_load_2d(sA + s * GEMM_A_BYTES, &tmA, kb * GEMM_BK, m0, &full[s]);
-      tma_load_2d(sB + s * GEMM_B_BYTES, &tmB, kb * GEMM_BK, n0, &full[s]);
+      const int kk = kb / nterm, term = kb - kk * nterm;
+      tma_load_3d(sA + s * GEMM_A_BYTES, &tmA, kk * GEMM_BK, m0, term_plane_a(term), &full[s]);
+      tma_load_3d(sB + s * GEMM_B_BYTES, &tmB, kk * GEMM_BK, n0, term_plane_b(term), &full[s]);
     }
   } else if (warp == 1 && lane == 0) {
     constexpr uint32_t idesc = instr_desc(FMT_BF16, GEMM_BM, GEMM_BN, 0, 0);
@@ -117,25 +121,34 @@ tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }  // namespace tc
 }  // namespace aur
 
+extern "C" int aur_tc_set_precision(int planes) {
+  if (planes != 1 && planes != 2) { aur::set_error("aur_tc_set_precision: planes must be 1 (bf16) or 2 (bf16 hi + mid split)"); return AUR_ERR_ARG; }
+  const int prev = aur::tc::g_tc_planes;
+  aur::tc::g_tc_planes = planes;
+  return prev;
+}
+extern "C" int aur_tc_get_precision(void) { return aur::tc::g_tc_planes; }
+
 extern "C" int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, const void* B, float* C, void* stream) {
   using namespace aur;
   using namespace aur::tc;
+  const int P = tc_planes();
   if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) { set_error("aur_tc_gemm_bf16: bad arguments"); return AUR_ERR_ARG; }
   if (K % 8 != 0) { set_error("aur_tc_gemm_bf16: K must be a multiple of 8 (16-byte row pitch for TMA)"); return AUR_ERR_UNSUPPORTED; }
   CUtensorMap tmA, tmB;
-  const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, dB[2] = {(uint64_t)K, (uint64_t)N};
-  const uint64_t st[1] = {(uint64_t)K * 2};
-  const uint32_t boxA[2] = {GEMM_BK, GEMM_BM}, boxB[2] = {GEMM_BK, GEMM_BN};
+  const uint64_t dA[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)P}, dB[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)P};
+  const uint64_t stA[2] = {(uint64_t)K * 2, (uint64_t)K * M * 2}, stB[2] = {(uint64_t)K * 2, (uint64_t)K * N * 2};
+  const uint32_t boxA[3] = {GEMM_BK, GEMM_BM, 1}, boxB[3] = {GEMM_BK, GEMM_BN, 1};
   int rc;
-  if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, dA, st, boxA))) return rc;
-  if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, dB, st, boxB))) return rc;
+  if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, A, dA, stA, boxA))) return rc;
+  if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, B, dB, stB, boxB))) return rc;
   static DeviceOnce attr;
   if (attr.first()) {
     AUR_CUDA_OK(cudaFuncSetAttribute(tc_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     attr.done();
   }
   dim3 grid((unsigned)((M + GEMM_BM - 1) / GEMM_BM), (unsigned)((N + GEMM_BN - 1) / GEMM_BN));
-  tc_gemm_bf16_kernel<<<grid, 256, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, C, (int)M, (int)N, (int)K, (int)N);
+  tc_gemm_bf16_kernel<<<grid, 256, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, C, (int)M, (int)N, (int)K, (int)N, P == 2 ? 3 : 1);
   AUR_LAUNCH_OK("tc_gemm_bf16_kernel");
   return 0;
 }

@@ -6,7 +6,14 @@ over actor + critic, eps=1e-5).
 
 Every convolution / dense contraction runs on tcgen05 tensor cores through the C ABI
 (aur_conv3x3_bf16, aur_wgrad3x3_bf16, aur_tc_gemm_bf16); activations are bf16 NHWC with explicit
-halos, accumulation is fp32, parameters / gradients / Adam moments are fp32.  The free parameters are
+halos, accumulation is fp32, parameters / gradients / Adam moments are fp32.
+
+Two operand precisions (aur_tc_set_precision):
+  split=True   every bf16 tensor is a stack of a hi and a mid plane (v = hi + mid to 2^-17) and every contraction
+               issues hi*hi + hi*mid + mid*hi: fp32-class arithmetic like the reference's (equiv.py / robot_ppo.py
+               compute in fp32), gradients within north_star's 1e-4 of an fp32 / fp64 autograd on identical routing;
+  split=False  single-plane bf16 operands: the fast mode, below the reference's precision (1e-2 class).
+Internally every bf16 buffer carries a leading plane dimension P (1 or 2).  The free parameters are
 the p4 group-convolution filters psi (see oracle/equiv_ref.py for the restated architecture and why
 weights are not interchangeable with e2cnn checkpoints).  No CPU path.
 
@@ -22,7 +29,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import _lib
-from .kernels import _ptr, _stream, conv3x3_bf16, equiv_conv0, equiv_expand_regular, tc_gemm_bf16
+from .kernels import _ptr, _stream, adv_moments, conv3x3_bf16, equiv_conv0, equiv_expand_regular, tc_gemm_bf16, tc_precision
 
 ENC_FIELDS = [16, 32, 64, 128, 256, 128, 128]
 N_ACT = 5
@@ -60,8 +67,8 @@ class _Enc:
     """Activation / gradient buffers of one encoder for a fixed batch size; ch = channels of the six stored activations
     (NHWC bf16, halo where the next layer pads), feat = encoder output width."""
 
-    def __init__(self, B: int, dev, ch=(64, 128, 256, 512, 1024, 512), feat: int = 512):
-        bf = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
+    def __init__(self, B: int, dev, ch=(64, 128, 256, 512, 1024, 512), feat: int = 512, planes: int = 1):
+        bf = lambda *s: torch.zeros(planes, *s, dtype=torch.bfloat16, device=dev)
         u8 = lambda *s: torch.zeros(*s, dtype=torch.uint8, device=dev)
         self.a = [bf(B, 66, 66, ch[0]), bf(B, 34, 34, ch[1]), bf(B, 18, 18, ch[2]), bf(B, 10, 10, ch[3]), bf(B, 8, 8, ch[4]),
                   bf(B, 3, 3, ch[5])]
@@ -77,8 +84,7 @@ class EquivActorCritic:
     def __init__(self, params: Dict[str, torch.Tensor], batch: int, lr: float = 3e-4, eps: float = 1e-5,
                  betas=(0.9, 0.999), split: bool = False):
         self.split = bool(split)
-        if self.split:
-            raise _lib.AurError("split-precision mode is not built yet")
+        self.P = 2 if self.split else 1
         if batch % 8:
             raise _lib.AurError("batch must be a multiple of 8 (16-byte rows for the TMA weight-gradient maps)")
         _lib.lib()
@@ -87,7 +93,8 @@ class EquivActorCritic:
         if self.dev.type != "cuda":
             raise _lib.AurError("EquivActorCritic needs CUDA parameters (no CPU fallback)")
         self.B = batch
-        self.enc = {"actor": _Enc(batch, self.dev, self.CH, self.FEAT), "critic": _Enc(batch, self.dev, self.CH, self.FEAT)}
+        self.enc = {"actor": _Enc(batch, self.dev, self.CH, self.FEAT, self.P),
+                    "critic": _Enc(batch, self.dev, self.CH, self.FEAT, self.P)}
         self.grads = {k: torch.zeros_like(v) for k, v in params.items()}
         self.m1 = {k: torch.zeros_like(v) for k, v in params.items()}
         self.m2 = {k: torch.zeros_like(v) for k, v in params.items()}
@@ -97,11 +104,26 @@ class EquivActorCritic:
         self.moments = torch.zeros(3, dtype=torch.float64, device=self.dev)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.ws = torch.zeros(1 << 20, device=self.dev)
+        desc = _lib.PolicyDesc(4, 2, 64, 2, 0)                  # only sizes the advantage-moment workspace
+        self._mom_ws = torch.zeros((int(_lib.lib().aur_ppo_update_workspace_bytes(ctypes.byref(desc))) + 3) // 4, device=self.dev)
+        self._cs = (torch.tensor([1.0, 0.0, -1.0, 0.0], device=self.dev), torch.tensor([0.0, 1.0, 0.0, -1.0], device=self.dev))
+        self._a_bias = torch.zeros(10, device=self.dev)
         self.value = torch.zeros(batch, device=self.dev)
         self.logp = torch.zeros(batch, device=self.dev)
         self._idx11 = None
         self._w = {}
         self._zcache = {}
+
+    # ------------------------------------------------------------------- planes
+    def _bf(self, x: torch.Tensor) -> torch.Tensor:
+        """fp32 -> [P, ...] bf16 planes (tiny host-side tensors only: head filters)."""
+        hi = x.bfloat16()
+        if self.P == 1:
+            return hi.unsqueeze(0).contiguous()
+        return torch.stack([hi, (x - hi.float()).bfloat16()]).contiguous()
+
+    def _empty(self, *shape) -> torch.Tensor:
+        return torch.empty(self.P, *shape, dtype=torch.bfloat16, device=self.dev)
 
     # ------------------------------------------------------------------ weights
     def _expand(self):
@@ -110,26 +132,26 @@ class EquivActorCritic:
         for net in ("actor", "critic"):
             for l in range(1, 6):
                 wm, wt, b = equiv_expand_regular(self.p[f"{net}.enc{l}.psi"], self.p[f"{net}.enc{l}.bias"], want_wt=True)
-                w[f"{net}.{l}"] = (wm, wt, b)
+                w[f"{net}.{l}"] = (wm.reshape(self.P, *wm.shape[-3:]), wt.reshape(self.P, *wt.shape[-3:]), b)
             wm, _, b = equiv_expand_regular(self.p[f"{net}.enc6.psi"], self.p[f"{net}.enc6.bias"])
-            wm = wm.reshape(512, 4608)
-            w[f"{net}.6"] = (wm, wm.t().contiguous(), b)
+            wm = wm.reshape(self.P, 512, 4608)
+            w[f"{net}.6"] = (wm, wm.transpose(1, 2).contiguous(), b)
         # heads (tiny, torch plumbing): actor [16,512] (10 used), critic head-1 [512,512]
         pi, pt = self.p["actor.head.psi_irrep"], self.p["actor.head.psi_triv"]
-        c = torch.tensor([1.0, 0.0, -1.0, 0.0], device=self.dev); s = torch.tensor([0.0, 1.0, 0.0, -1.0], device=self.dev)
+        c, s = self._cs
         a_, b_ = pi[:, 0:1], pi[:, 1:2]
         Wa = torch.zeros(16, 512, device=self.dev)
         Wa[0] = (c * a_ - s * b_).reshape(-1)
         Wa[1] = (s * a_ + c * b_).reshape(-1)
         Wa[2:10] = pt.unsqueeze(-1).expand(-1, -1, 4).reshape(8, 512)
-        w["actor.head"] = (Wa.bfloat16().contiguous(), Wa.t().contiguous().bfloat16().contiguous())
+        w["actor.head"] = (self._bf(Wa), self._bf(Wa.t().contiguous()))
         psi1 = self.p["critic.head1.psi"].reshape(128, 128, 4)
         if self._idx11 is None:
             o = torch.arange(128, device=self.dev).view(128, 1, 1, 1); r = torch.arange(4, device=self.dev).view(1, 4, 1, 1)
             i = torch.arange(128, device=self.dev).view(1, 1, 128, 1); s_ = torch.arange(4, device=self.dev).view(1, 1, 1, 4)
             self._idx11 = ((o * 128 + i) * 4 + ((s_ - r) % 4)).reshape(512, 512)
         W1 = psi1.reshape(-1)[self._idx11]
-        w["critic.head1"] = (W1.bfloat16().contiguous(), W1.t().contiguous().bfloat16().contiguous(),
+        w["critic.head1"] = (self._bf(W1), self._bf(W1.t().contiguous()),
                              self.p["critic.head1.bias"].repeat_interleave(4).contiguous())
         self._w = w
 
@@ -148,13 +170,17 @@ class EquivActorCritic:
             wm, _, b = w[f"{net}.{l}"]
             conv3x3_bf16(e.a[l - 1], wm, b, epi, e.a[l], off, e.arg[l])
         wm6, _, b6 = w[f"{net}.6"]
-        pre = tc_gemm_bf16(e.a[5].reshape(self.B, 9 * self.CH[5]), wm6)
+        pre = tc_gemm_bf16(e.a[5].reshape(self.P, self.B, 9 * self.CH[5]), wm6)
         L = _lib.lib()
         with torch.cuda.device(self.dev):
             _chk(L.aur_bias_relu_bf16(self.B, self.FEAT, pre.data_ptr(), b6.data_ptr(), e.feat.data_ptr(), _stream()), "aur_bias_relu_bf16")
 
     def forward(self, state: torch.Tensor, obs: torch.Tensor):
         """Encoders + head GEMMs; returns (actor head output [B,16] fp32, critic head-1 pre-activation [B,512] fp32)."""
+        with tc_precision(self.P):
+            return self._forward(state, obs)
+
+    def _forward(self, state: torch.Tensor, obs: torch.Tensor):
         self._expand()
         self._encoder_forward("actor", state, obs)
         self._encoder_forward("critic", state, obs)
@@ -163,15 +189,18 @@ class EquivActorCritic:
         return a_out, c_pre
 
     # ----------------------------------------------------------------- backward
-    def _t(self, x2d: torch.Tensor) -> torch.Tensor:
-        R, C = x2d.shape
-        out = torch.empty(C, R, dtype=torch.bfloat16, device=self.dev)
+    def _t(self, x: torch.Tensor) -> torch.Tensor:
+        """[P,R,C] -> [P,C,R], plane by plane."""
+        P, R, C = x.shape
+        out = torch.empty(P, C, R, dtype=torch.bfloat16, device=self.dev)
         with torch.cuda.device(self.dev):
-            _chk(_lib.lib().aur_transpose_bf16(R, C, x2d.data_ptr(), out.data_ptr(), _stream()), "aur_transpose_bf16")
+            for pl in range(P):
+                _chk(_lib.lib().aur_transpose_bf16(R, C, x[pl].data_ptr(), out[pl].data_ptr(), _stream()), "aur_transpose_bf16")
         return out
 
     def _cast(self, g: torch.Tensor, ref: Optional[torch.Tensor]) -> torch.Tensor:
-        out = torch.empty(g.shape, dtype=torch.bfloat16, device=self.dev)
+        """fp32 [..] -> [P, ..] bf16 planes, masked by ref > 0 (ref: [P, ..] planes, the hi plane decides)."""
+        out = self._empty(*g.shape)
         with torch.cuda.device(self.dev):
             _chk(_lib.lib().aur_relu_mask_bf16(g.numel(), g.data_ptr(), _ptr(ref), out.data_ptr(), _stream()), "aur_relu_mask_bf16")
         return out
@@ -179,8 +208,8 @@ class EquivActorCritic:
     def _wgrad(self, net: str, l: int, dy_buf: torch.Tensor, x_buf: torch.Tensor, base_off: int, bias_done: bool = False):
         """dpsi_l, dbias_l from the haloed output-gradient buffer and the layer's input buffer."""
         L = _lib.lib()
-        B, Hb, Wb, Cin = x_buf.shape
-        Cout = dy_buf.shape[3]
+        B, Hb, Wb, Cin = x_buf.shape[-4:]
+        Cout = dy_buf.shape[-1]
         Q = B * Hb * Wb
         dw = torch.zeros(Cout, 9, Cin, device=self.dev)
         with torch.cuda.device(self.dev):
@@ -188,7 +217,7 @@ class EquivActorCritic:
                  "aur_wgrad3x3_bf16")
         self._store_wgrad(net, l, dw, Cout, Cin)
         if not bias_done:
-            self._store_bgrad(net, l, dy_buf.reshape(Q, Cout), Q, Cout)
+            self._store_bgrad(net, l, dy_buf.reshape(self.P, Q, Cout), Q, Cout)
 
     # dense gradient of a layer's contraction matrix [Cout, 9, Cin] (layer 6: [Cout, 9 * Cin]) -> the free parameters
     def _store_wgrad(self, net: str, l: int, dw: torch.Tensor, Cout: int, Cin: int):
@@ -198,8 +227,9 @@ class EquivActorCritic:
 
     def _store_bgrad(self, net: str, l: int, dy2d: torch.Tensor, Q: int, Cout: int):
         with torch.cuda.device(self.dev):
-            _chk(_lib.lib().aur_colsum_bf16(Q, Cout, dy2d.data_ptr(), 4, self.grads[f"{net}.enc{l}.bias"].data_ptr(), _stream()),
-                 "aur_colsum_bf16")
+            for pl in range(self.P):                       # the kernel accumulates: hi + mid
+                _chk(_lib.lib().aur_colsum_bf16(Q, Cout, dy2d[pl].data_ptr(), 4, self.grads[f"{net}.enc{l}.bias"].data_ptr(),
+                                                _stream()), "aur_colsum_bf16")
 
     def _layer0_wgrad(self, net: str, state, obs, dprev, e):
         with torch.cuda.device(self.dev):
@@ -216,7 +246,7 @@ class EquivActorCritic:
         key = (tag,) + shape                        # one buffer per role: two live buffers may share a shape
         t = self._zcache.get(key)
         if t is None:
-            t = torch.zeros(*shape, dtype=torch.bfloat16, device=self.dev)
+            t = torch.zeros(self.P, *shape, dtype=torch.bfloat16, device=self.dev)
             self._zcache[key] = t
         return t
 
@@ -225,7 +255,7 @@ class EquivActorCritic:
         out = self._halo_zeros(tag, self.B, dHb, dHb, C)
         acc, group = self._bgrad_begin(bias[0], bias[1], C) if bias is not None else (None, 1)
         with torch.cuda.device(self.dev):
-            _chk(_lib.lib().aur_unpool_relu_bwd_colsum(self.B, Hp, Hp, C, dpool.data_ptr(), act.data_ptr(), act.shape[1], act.shape[2],
+            _chk(_lib.lib().aur_unpool_relu_bwd_colsum(self.B, Hp, Hp, C, dpool.data_ptr(), act.data_ptr(), act.shape[-3], act.shape[-2],
                                                        aoff, arg.data_ptr(), out.data_ptr(), dHb, dHb, doff, group, _ptr(acc), _stream()),
                  "aur_unpool_relu_bwd_colsum")
         if bias is not None:
@@ -246,10 +276,10 @@ class EquivActorCritic:
         wm6, wm6t, _ = w[f"{net}.6"]
         # layer 6 (dense 3x3 -> 1x1): weight gradient [FEAT, 9 CH5] = dz6^T a6 ; data gradient = dz6 W6
         dz6_cm = self._t(dz6)
-        dW6 = tc_gemm_bf16(dz6_cm, self._t(e.a[5].reshape(B, 9 * CH[5])))
+        dW6 = tc_gemm_bf16(dz6_cm, self._t(e.a[5].reshape(self.P, B, 9 * CH[5])))
         self._store_wgrad(net, 6, dW6, self.FEAT, CH[5])
         self._store_bgrad(net, 6, dz6, B, self.FEAT)
-        da6 = self._cast(tc_gemm_bf16(dz6, wm6t), None).reshape(B, 3, 3, CH[5])
+        da6 = self._cast(tc_gemm_bf16(dz6, wm6t), None).reshape(self.P, B, 3, 3, CH[5])
         # layer 5 (pad 0, pooled): un-pool into a 2-halo buffer (backward-data) and into the input geometry (weights)
         dy5_d = self._unpool(da6, e.a[5], 0, e.arg[5], CH[5], 3, 10, 2, "dy5_d")
         dy5_w = self._unpool(da6, e.a[5], 0, e.arg[5], CH[5], 3, 8, 0, "dy5_w", bias=(net, 5))
@@ -258,7 +288,7 @@ class EquivActorCritic:
         conv3x3_bf16(dy5_d, w[f"{net}.5"][1], None, 3, dy4, 1, None, relu_ref=e.a[4], ref_off=0)   # x ReLU mask of layer 4
         # layer 4 (pad 1, ReLU only)
         self._wgrad(net, 4, dy4, e.a[3], -(10 + 1))
-        da4 = torch.empty(B, 8, 8, CH[3], dtype=torch.bfloat16, device=self.dev)
+        da4 = self._empty(B, 8, 8, CH[3])
         conv3x3_bf16(dy4, w[f"{net}.4"][1], None, 0, da4, 0)
         # layers 3, 2, 1 (pad 1, pooled)
         dprev = da4
@@ -267,8 +297,8 @@ class EquivActorCritic:
             Hb = 2 * Hp + 2
             dy = self._unpool(dprev, e.a[l], 1, e.arg[l], C, Hp, Hb, 1, f"dy{l}", bias=(net, l))
             self._wgrad(net, l, dy, e.a[l - 1], -(Hb + 1), bias_done=True)
-            Cin = e.a[l - 1].shape[3]
-            dprev = torch.empty(B, 2 * Hp, 2 * Hp, Cin, dtype=torch.bfloat16, device=self.dev)
+            Cin = e.a[l - 1].shape[-1]
+            dprev = self._empty(B, 2 * Hp, 2 * Hp, Cin)
             conv3x3_bf16(dy, w[f"{net}.{l}"][1], None, 0, dprev, 0)
         # layer 0 (direct)
         self._layer0_wgrad(net, state, obs, dprev, e)
@@ -277,18 +307,24 @@ class EquivActorCritic:
     def loss_and_grads(self, state, obs, action, oldlp, adv, ret, vold, clip_coeff=0.2, entropy_coeff=0.01,
                        value_coeff=0.5, norm_adv=True, clip_vloss=True) -> torch.Tensor:
         """Forward + loss + full backward; gradients land in self.grads.  Returns the stats tensor (means)."""
+        with tc_precision(self.P):
+            return self._loss_and_grads(state, obs, action, oldlp, adv, ret, vold, clip_coeff, entropy_coeff, value_coeff,
+                                        norm_adv, clip_vloss)
+
+    def _loss_and_grads(self, state, obs, action, oldlp, adv, ret, vold, clip_coeff, entropy_coeff, value_coeff, norm_adv,
+                        clip_vloss) -> torch.Tensor:
         L = _lib.lib()
         B = self.B
         for g in self.grads.values():
             g.zero_()
         self.stats.zero_(); self.d_head.zero_()
-        a_out, c_pre = self.forward(state, obs)
+        a_out, c_pre = self._forward(state, obs)
         if norm_adv:
-            a64 = adv.double()
-            self.moments.copy_(torch.stack([a64.sum(), (a64 * a64).sum(), torch.tensor(float(B), dtype=torch.float64, device=self.dev)]))
-        d_a_out = torch.empty(B, 16, dtype=torch.bfloat16, device=self.dev)
-        d_c_h = torch.empty(B, 512, dtype=torch.bfloat16, device=self.dev)
-        a_bias = torch.cat([torch.zeros(2, device=self.dev), self.p["actor.head.bias_triv"]]).contiguous()
+            adv_moments(adv, self.moments, self._mom_ws)
+        d_a_out = self._empty(B, 16)
+        d_c_h = self._empty(B, 512)
+        a_bias = self._a_bias
+        a_bias[2:10].copy_(self.p["actor.head.bias_triv"])
         h = _lib.EquivHeadArgs()
         h.B, h.clip_vloss, h.m_total = B, int(bool(clip_vloss)), B
         h.a_out, h.a_bias, h.c_pre = a_out.data_ptr(), a_bias.data_ptr(), c_pre.data_ptr()
@@ -306,7 +342,7 @@ class EquivActorCritic:
         # ---- head parameter gradients (contractions on tensor cores, projection = tiny torch plumbing)
         fa, fc = self.enc["actor"].feat, self.enc["critic"].feat
         dWa = tc_gemm_bf16(self._t(d_a_out), self._t(fa))                       # [16,512]
-        c = torch.tensor([1.0, 0.0, -1.0, 0.0], device=self.dev); s = torch.tensor([0.0, 1.0, 0.0, -1.0], device=self.dev)
+        c, s = self._cs
         g0, g1 = dWa[0].reshape(128, 4), dWa[1].reshape(128, 4)
         self.grads["actor.head.psi_irrep"].copy_(torch.stack([(c * g0 + s * g1).sum(1), (-s * g0 + c * g1).sum(1)], 1))
         self.grads["actor.head.psi_triv"].copy_(dWa[2:10].reshape(8, 128, 4).sum(2))

@@ -279,12 +279,59 @@ class Updater:
 
 
 # ----------------------------------------------------------------------- tensor cores
+class tc_precision:
+    """`with tc_precision(2):` runs the row-X entry points on split operands (aur_tc_set_precision): every bf16 tensor is
+    then a stack [2, ...] of a hi and a mid plane.  Restores the previous mode on exit."""
+
+    def __init__(self, planes: int):
+        self.planes, self.prev = int(planes), None
+
+    def __enter__(self):
+        self.prev = _lib.lib().aur_tc_set_precision(self.planes)
+        if self.prev < 0:
+            _lib.check(self.prev, "aur_tc_set_precision")
+        return self
+
+    def __exit__(self, *exc):
+        _lib.lib().aur_tc_set_precision(self.prev)
+        return False
+
+
+def tc_planes() -> int:
+    return int(_lib.lib().aur_tc_get_precision())
+
+
+def split_planes(x: torch.Tensor) -> torch.Tensor:
+    """fp32 tensor -> [2, ...] bf16 (hi = bf16(x), mid = bf16(x - hi)); the layout split-precision entry points take."""
+    hi = x.bfloat16()
+    return torch.stack([hi, (x - hi.float()).bfloat16()]).contiguous()
+
+
+def join_planes(x: torch.Tensor) -> torch.Tensor:
+    """[P, ...] bf16 planes -> fp32 value (sum of the planes)."""
+    return x.float().sum(0)
+
+
+def _check_planes(t: torch.Tensor, base_dims: int, name: str) -> int:
+    """Plane count of a bf16 tensor argument: `base_dims` dims = one plane, one more leading dim = a plane stack."""
+    if t.dtype != torch.bfloat16 or not t.is_cuda or not t.is_contiguous():
+        raise _lib.AurError(f"{name} must be a contiguous CUDA bf16 tensor")
+    P = 1 if t.dim() == base_dims else (t.shape[0] if t.dim() == base_dims + 1 else -1)
+    if P != tc_planes():
+        raise _lib.AurError(f"{name}: {tuple(t.shape)} does not match the current tensor-core precision ({tc_planes()} plane(s))")
+    return P
+
+
+def _planes_shape(P: int, *shape):
+    return (P,) + tuple(shape) if P == 2 else tuple(shape)
+
+
 def tc_gemm_bf16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """a [M,K] bf16, b [N,K] bf16 -> a @ b.T as fp32 [M,N] (tcgen05, fp32 accumulate)."""
-    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or not a.is_cuda or not a.is_contiguous() or not b.is_contiguous():
-        raise _lib.AurError("tc_gemm_bf16 needs contiguous CUDA bf16 operands")
-    M, K = a.shape
-    N = b.shape[0]
+    """a [M,K] bf16, b [N,K] bf16 (or [2,M,K] / [2,N,K] plane stacks in split mode) -> a @ b.T as fp32 [M,N]
+    (tcgen05, fp32 accumulate)."""
+    _check_planes(a, 2, "a"), _check_planes(b, 2, "b")
+    M, K = a.shape[-2:]
+    N = b.shape[-2]
     c = torch.empty(M, N, dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         rc = _lib.lib().aur_tc_gemm_bf16(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), _stream())
@@ -293,11 +340,13 @@ def tc_gemm_bf16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 def equiv_expand_regular(psi: torch.Tensor, bias_f: Optional[torch.Tensor] = None, want_wt: bool = False):
-    """psi [Fo,Fi,4,3,3] fp32 -> (wmat [Fo*4, 9, Fi*4] bf16, wt [Fi*4, 9, Fo*4] bf16 | None, bias [Fo*4] | None)."""
+    """psi [Fo,Fi,4,3,3] fp32 -> (wmat [Fo*4, 9, Fi*4] bf16, wt [Fi*4, 9, Fo*4] bf16 | None, bias [Fo*4] | None);
+    split mode: wmat / wt are [2, ...] plane stacks."""
     psi = _f32c(psi, "psi")
     Fo, Fi = psi.shape[0], psi.shape[1]
-    wmat = torch.empty(Fo * 4, 9, Fi * 4, dtype=torch.bfloat16, device=psi.device)
-    wt = torch.empty(Fi * 4, 9, Fo * 4, dtype=torch.bfloat16, device=psi.device) if want_wt else None
+    P = tc_planes()
+    wmat = torch.empty(_planes_shape(P, Fo * 4, 9, Fi * 4), dtype=torch.bfloat16, device=psi.device)
+    wt = torch.empty(_planes_shape(P, Fi * 4, 9, Fo * 4), dtype=torch.bfloat16, device=psi.device) if want_wt else None
     bias = torch.empty(Fo * 4, dtype=torch.float32, device=psi.device) if bias_f is not None else None
     with torch.cuda.device(psi.device):
         rc = _lib.lib().aur_equiv_expand_regular(psi.data_ptr(), Fo, Fi, _ptr(bias_f), wmat.data_ptr(), _ptr(wt),
@@ -309,13 +358,15 @@ def equiv_expand_regular(psi: torch.Tensor, bias_f: Optional[torch.Tensor] = Non
 def conv3x3_bf16(inp: torch.Tensor, wmat: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int,
                  out: torch.Tensor, out_off: int, pool_arg: Optional[torch.Tensor] = None,
                  relu_ref: Optional[torch.Tensor] = None, ref_off: int = 0) -> torch.Tensor:
-    """inp [B,Hb,Wb,Cin] bf16 (halo included) -> valid 3x3 conv (+bias/ReLU/pool) into out[:, off:, off:, :]."""
+    """inp [B,Hb,Wb,Cin] bf16 (halo included) -> valid 3x3 conv (+bias/ReLU/pool) into out[:, off:, off:, :].
+    Split mode: inp / wmat / out (and relu_ref) are [2, ...] plane stacks."""
     import ctypes
-    B, Hb, Wb, Cin = inp.shape
-    Cout = wmat.shape[0]
-    a = _lib.ConvArgs(B, Hb, Wb, Cin, Cout, epilogue, out.shape[1], out.shape[2], out_off, 0, inp.data_ptr(),
+    _check_planes(inp, 4, "inp"), _check_planes(wmat, 3, "wmat"), _check_planes(out, 4, "out")
+    B, Hb, Wb, Cin = inp.shape[-4:]
+    Cout = wmat.shape[-3]
+    a = _lib.ConvArgs(B, Hb, Wb, Cin, Cout, epilogue, out.shape[-3], out.shape[-2], out_off, 0, inp.data_ptr(),
                       wmat.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(pool_arg), _ptr(relu_ref),
-                      relu_ref.shape[1] if relu_ref is not None else 0, relu_ref.shape[2] if relu_ref is not None else 0,
+                      relu_ref.shape[-3] if relu_ref is not None else 0, relu_ref.shape[-2] if relu_ref is not None else 0,
                       ref_off, 0)
     with torch.cuda.device(inp.device):
         rc = _lib.lib().aur_conv3x3_bf16(ctypes.byref(a), _stream())
@@ -326,9 +377,19 @@ def conv3x3_bf16(inp: torch.Tensor, wmat: torch.Tensor, bias: Optional[torch.Ten
 def equiv_conv0(obs: torch.Tensor, state: torch.Tensor, psi: torch.Tensor, bias_f: torch.Tensor, out: torch.Tensor,
                 pool_arg: Optional[torch.Tensor] = None) -> torch.Tensor:
     B = obs.shape[0]
+    _check_planes(out, 4, "out")
     with torch.cuda.device(obs.device):
         rc = _lib.lib().aur_equiv_conv0(_f32c(obs, "obs").data_ptr(), _f32c(state, "state").data_ptr(),
                                         _f32c(psi, "psi").data_ptr(), _f32c(bias_f, "bias").data_ptr(), B, out.data_ptr(),
                                         _ptr(pool_arg), _stream())
     _lib.check(rc, "aur_equiv_conv0")
+    return out
+
+
+def adv_moments(adv: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor) -> torch.Tensor:
+    """(sum, sum of squares, count) of `adv` in fp64 -> out [3] (aur_ppo_adv_moments over the whole array)."""
+    with torch.cuda.device(adv.device):
+        rc = _lib.lib().aur_ppo_adv_moments(adv.numel(), None, 0, _f32c(adv, "adv").data_ptr(), out.data_ptr(),
+                                            workspace.data_ptr(), _stream())
+    _lib.check(rc, "aur_ppo_adv_moments")
     return out

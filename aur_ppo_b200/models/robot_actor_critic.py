@@ -26,7 +26,7 @@ from torch import nn
 from .. import _lib
 from .. import plain_cnn
 from ..equiv import ENC_FIELDS, N_ACT, EquivActorCritic, init_params
-from ..kernels import _ptr, _stream, tc_gemm_bf16
+from ..kernels import _ptr, _stream, tc_gemm_bf16, tc_precision
 
 
 class _PsiNet(nn.Module):
@@ -100,14 +100,15 @@ class robot_actor_critic(nn.Module):
             st_d = torch.cat([st_d, st_d.new_zeros(Bp - B)])
         obs_d, st_d = obs_d.contiguous(), st_d.contiguous()
         e = self.engine(Bp)
-        e._expand()
         a_out = c_pre = None
-        if want_actor:
-            e._encoder_forward("actor", st_d, obs_d)
-            a_out = tc_gemm_bf16(e.enc["actor"].feat, e._w["actor.head"][0])
-        if want_critic:
-            e._encoder_forward("critic", st_d, obs_d)
-            c_pre = tc_gemm_bf16(e.enc["critic"].feat, e._w["critic.head1"][0])
+        with tc_precision(e.P):
+            e._expand()
+            if want_actor:
+                e._encoder_forward("actor", st_d, obs_d)
+                a_out = tc_gemm_bf16(e.enc["actor"].feat, e._w["actor.head"][0])
+            if want_critic:
+                e._encoder_forward("critic", st_d, obs_d)
+                c_pre = tc_gemm_bf16(e.enc["critic"].feat, e._w["critic.head1"][0])
         dev = self.device
         f = lambda *s: torch.empty(*s, device=dev)
         out = dict(unscaled=f(Bp, 5), scaled=f(Bp, 5), logp=f(Bp), ent=f(Bp), value=f(Bp), mean=f(Bp, 5), logstd=f(Bp, 5))

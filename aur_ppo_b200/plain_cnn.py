@@ -29,7 +29,7 @@ import torch
 
 from . import _lib
 from .equiv import EquivActorCritic, N_ACT, _chk
-from .kernels import _stream, tc_gemm_bf16
+from .kernels import _stream, adv_moments, tc_gemm_bf16, tc_precision
 
 CONV_IDX = [0, 3, 6, 9, 12, 14, 17]                 # positions of the Conv2d layers in base_encoder.conv
 REAL = [16, 32, 64, 128, 256, 256, 128]             # real output channels of the seven convolutions
@@ -91,20 +91,19 @@ class PlainActorCritic(EquivActorCritic):
                 Cin, Cout = self.CH[l - 1], self.CH[l]
                 dense = torch.zeros(Cout, Cin, 3, 3, device=self.dev)
                 dense[:co, self._in_pos[l]] = W
-                wm = dense.permute(0, 2, 3, 1).reshape(Cout, 9, Cin).bfloat16().contiguous()
-                wt = torch.flip(dense, dims=(2, 3)).permute(1, 2, 3, 0).reshape(Cin, 9, Cout).bfloat16().contiguous()
+                wm = self._bf(dense.permute(0, 2, 3, 1).reshape(Cout, 9, Cin))
+                wt = self._bf(torch.flip(dense, dims=(2, 3)).permute(1, 2, 3, 0).reshape(Cin, 9, Cout))
                 bias = torch.zeros(Cout, device=self.dev)
                 bias[:co] = b
                 w[f"{net}.{l}"] = (wm, wt, bias)
             W6, b6 = self.p[conv_key(net, 6, "weight")], self.p[conv_key(net, 6, "bias")]
-            wm6 = W6.permute(0, 2, 3, 1).reshape(128, 9 * 256).bfloat16().contiguous()
-            w[f"{net}.6"] = (wm6, wm6.t().contiguous(), b6.contiguous())
+            wm6 = self._bf(W6.permute(0, 2, 3, 1).reshape(128, 9 * 256))
+            w[f"{net}.6"] = (wm6, wm6.transpose(1, 2).contiguous(), b6.contiguous())
         Wa = torch.zeros(16, 128, device=self.dev)
         Wa[:N_ACT] = self.p["actor.mean_linear.weight"]
-        w["actor.head"] = (Wa.bfloat16().contiguous(), Wa.t().contiguous().bfloat16().contiguous())
+        w["actor.head"] = (self._bf(Wa), self._bf(Wa.t().contiguous()))
         W1 = self.p["critic.critic.0.weight"]
-        w["critic.head1"] = (W1.bfloat16().contiguous(), W1.t().contiguous().bfloat16().contiguous(),
-                             self.p["critic.critic.0.bias"].contiguous())
+        w["critic.head1"] = (self._bf(W1), self._bf(W1.t().contiguous()), self.p["critic.critic.0.bias"].contiguous())
         self._w = w
 
     # ---------------------------------------------------------------- gradients
@@ -119,7 +118,8 @@ class PlainActorCritic(EquivActorCritic):
     def _store_bgrad(self, net: str, l: int, dy2d: torch.Tensor, Q: int, Cout: int):
         out = torch.zeros(Cout, device=self.dev)           # the kernel accumulates
         with torch.cuda.device(self.dev):
-            _chk(_lib.lib().aur_colsum_bf16(Q, Cout, dy2d.data_ptr(), 1, out.data_ptr(), _stream()), "aur_colsum_bf16")
+            for pl in range(self.P):
+                _chk(_lib.lib().aur_colsum_bf16(Q, Cout, dy2d[pl].data_ptr(), 1, out.data_ptr(), _stream()), "aur_colsum_bf16")
         self.grads[conv_key(net, l, "bias")].copy_(out[:REAL[l]])
 
     def _bgrad_begin(self, net: str, l: int, C: int):
@@ -142,19 +142,18 @@ class PlainActorCritic(EquivActorCritic):
                                                   self.grads[conv_key(net, 0, "bias")].data_ptr(), _stream()), "aur_plain_conv0_wgrad")
 
     # ------------------------------------------------------------------- update
-    def loss_and_grads(self, state, obs, action, oldlp, adv, ret, vold, clip_coeff=0.2, entropy_coeff=0.01,
-                       value_coeff=0.5, norm_adv=True, clip_vloss=True) -> torch.Tensor:
+    def _loss_and_grads(self, state, obs, action, oldlp, adv, ret, vold, clip_coeff, entropy_coeff, value_coeff, norm_adv,
+                        clip_vloss) -> torch.Tensor:
         L = _lib.lib()
         B = self.B
         for g in self.grads.values():
             g.zero_()
         self.stats.zero_(); self.d_head.zero_()
-        a_out, c_pre = self.forward(state, obs)
+        a_out, c_pre = self._forward(state, obs)
         if norm_adv:
-            a64 = adv.double()
-            self.moments.copy_(torch.stack([a64.sum(), (a64 * a64).sum(), torch.tensor(float(B), dtype=torch.float64, device=self.dev)]))
-        d_a_out = torch.empty(B, 16, dtype=torch.bfloat16, device=self.dev)
-        d_c_h = torch.empty(B, 128, dtype=torch.bfloat16, device=self.dev)
+            adv_moments(adv, self.moments, self._mom_ws)
+        d_a_out = self._empty(B, 16)
+        d_c_h = self._empty(B, 128)
         h = _lib.PlainHeadArgs()
         h.B, h.clip_vloss, h.m_total = B, int(bool(clip_vloss)), B
         h.a_out, h.a_bias, h.actor_logstd = a_out.data_ptr(), self.p["actor.mean_linear.bias"].data_ptr(), self.p["actor_logstd"].data_ptr()

@@ -328,6 +328,19 @@ int aur_squashed_gaussian_sample(int64_t B, int32_t A, const float* mean, const 
  * K must be a multiple of 8. */
 int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, const void* B, float* C, void* stream);
 
+/* Operand precision of every row-X entry point below (and of aur_tc_gemm_bf16), per calling thread, like a BLAS math mode:
+ *   planes = 1  bf16 operands, fp32 accumulation: the fast mode, BELOW the reference's fp32 arithmetic
+ *               (src/nets/equiv.py:12-157 and src/robot_ppo.py:329-408 compute in fp32);
+ *   planes = 2  every bf16 tensor argument (activations, gradients, expanded filters; inputs and outputs alike) is a stack
+ *               [2][...] of two planes of the documented shape: hi = bf16(v), mid = bf16(v - hi), so v = hi + mid to
+ *               2^-17 relative.  Contractions issue hi*hi + hi*mid + mid*hi on the tensor cores with fp32 accumulation
+ *               (three K passes of the same pipelines): fp32-class results, north_star's 1e-4 gradient bar, 3x the MMA work.
+ *               ReLU / max-pool decisions are taken on the fp32 accumulators; masks read the hi plane (hi > 0 <=> v > 0).
+ * fp32 arguments (parameters, biases, gradients of parameters, GEMM outputs) are unaffected.  Returns the previous value,
+ * or AUR_ERR_ARG.  Default 1. */
+int aur_tc_set_precision(int planes);
+int aur_tc_get_precision(void);
+
 /* -------------------------------------------- equivariant encoder (row X) ----
  * The C4-equivariant convolutions of EquivariantEncoder128 (src/nets/equiv.py:12-62), which the
  * reference runs as e2cnn R2Conv -> cuDNN.  Activations are NHWC bf16 buffers that INCLUDE their

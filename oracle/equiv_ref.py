@@ -106,18 +106,49 @@ def bf16_ste(x: torch.Tensor) -> torch.Tensor:
     return x + (x.bfloat16().float() - x).detach()
 
 
-def encoder_forward(p: Dict[str, torch.Tensor], net: str, x: torch.Tensor, collect: List = None, quant: bool = False) -> torch.Tensor:
+def _windows(z: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] -> [B,C,H/2,W/2,4] with the 2x2 window flattened as w = wy * 2 + wx."""
+    B, C, H, W = z.shape
+    return z.reshape(B, C, H // 2, 2, W // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, C, H // 2, W // 2, 4)
+
+
+def encoder_forward(p: Dict[str, torch.Tensor], net: str, x: torch.Tensor, collect: List = None, quant: bool = False,
+                    route: List = None, route_out: List = None) -> torch.Tensor:
     """x [B,2,128,128] -> [B,512] (regular fields at 1x1).
 
     quant=True mirrors WHERE the CUDA path stores bf16 (expanded weights of layers 1-6, every stored
     activation) so that the discrete routing decisions (max-pool / GroupPooling arg-max, ReLU masks)
-    of the two paths coincide; the arithmetic stays fp32."""
+    of the two paths coincide; the arithmetic stays fp32.
+
+    route: per layer a dict(arg=[B,C,Hp,Wp] window index or None, pos=[B,C,Hp,Wp] bool): FORCES the discrete
+    decisions (which window element a max-pool takes, which outputs the ReLU keeps) instead of taking them
+    from this pass's own values -- with routing fixed the network is a linear map, so two implementations
+    that agree on the routing must agree on every gradient to rounding.  route_out: filled with this
+    pass's own routing in the same format (to count decisions that differ)."""
     for l in range(len(ENC_FIELDS)):
         psi = p[f"{net}.enc{l}.psi"]
         W = expand_trivial_to_regular(psi) if l == 0 else expand_regular_to_regular(psi)
         if quant and l > 0:
             W = bf16_ste(W)
         x = F.conv2d(x, W, expand_bias_regular(p[f"{net}.enc{l}.bias"]), padding=ENC_PAD[l])
+        if route_out is not None:
+            with torch.no_grad():
+                if ENC_POOL[l]:
+                    zw = _windows(x)
+                    m, a = zw.max(-1)
+                    # first maximum in scan order (torch's max_pool2d backward); .max returns an arbitrary one on exact ties
+                    a = (zw == m.unsqueeze(-1)).float().argmax(-1)
+                    route_out.append(dict(arg=a, pos=m > 0, margin=m))
+                else:
+                    route_out.append(dict(arg=None, pos=x > 0, margin=x.detach()))
+        if route is not None:
+            r = route[l]
+            if ENC_POOL[l]:
+                x = _windows(x).gather(-1, r["arg"].unsqueeze(-1)).squeeze(-1)
+            x = x * r["pos"].to(x.dtype)
+            if collect is not None:
+                collect.append(x)
+            continue
         x = F.relu(x)
         if ENC_POOL[l]:
             x = F.max_pool2d(x, 2)
@@ -128,13 +159,14 @@ def encoder_forward(p: Dict[str, torch.Tensor], net: str, x: torch.Tensor, colle
     return x.reshape(x.shape[0], -1)
 
 
-def actor_forward(p, cat_obs, collect=None, quant=False):
+def actor_forward(p, cat_obs, collect=None, quant=False, route=None, route_out=None):
     """EquivariantActor.forward (equiv.py:82-91) -> (mean [B,5], log_std [B,5])."""
-    feat = encoder_forward(p, "actor", cat_obs, collect, quant)
+    feat = encoder_forward(p, "actor", cat_obs, collect, quant, route=route["actor"] if route else None,
+                           route_out=route_out["actor"] if route_out is not None else None)
     W = torch.cat([expand_regular_to_irrep1(p["actor.head.psi_irrep"]), expand_regular_to_trivial(p["actor.head.psi_triv"])], 0)
     if quant:
         W = bf16_ste(W)
-    bias = torch.cat([torch.zeros(2), p["actor.head.bias_triv"]])
+    bias = torch.cat([torch.zeros(2, dtype=feat.dtype), p["actor.head.bias_triv"]])
     out = feat @ W.T + bias                                        # [B,10]
     dxy, inv_act = out[:, 0:2], out[:, 2:N_ACT]
     mean = torch.cat((inv_act[:, 0:1], dxy, inv_act[:, 1:]), dim=1)
@@ -142,13 +174,24 @@ def actor_forward(p, cat_obs, collect=None, quant=False):
     return mean, log_std
 
 
-def critic_forward(p, cat_obs, collect=None, quant=False):
+def critic_forward(p, cat_obs, collect=None, quant=False, route=None, route_out=None):
     """EquivariantCritic.forward (equiv.py:153-157) -> value [B]."""
-    feat = encoder_forward(p, "critic", cat_obs, collect, quant)
+    feat = encoder_forward(p, "critic", cat_obs, collect, quant, route=route["critic"] if route else None,
+                           route_out=route_out["critic"] if route_out is not None else None)
     W1 = expand_regular_to_regular(p["critic.head1.psi"]).reshape(feat.shape[1], feat.shape[1])
     if quant:
         W1 = bf16_ste(W1)
-    h = F.relu(feat @ W1.T + expand_bias_regular(p["critic.head1.bias"]))
+    hpre = feat @ W1.T + expand_bias_regular(p["critic.head1.bias"])
+    if route_out is not None:
+        with torch.no_grad():
+            hw = hpre.reshape(hpre.shape[0], -1, 4)
+            m = hw.max(-1).values
+            route_out["group"] = dict(arg=(hw == m.unsqueeze(-1)).float().argmax(-1), pos=m > 0, margin=m)
+    if route is not None:
+        g = route["group"]
+        pooled = hpre.reshape(hpre.shape[0], -1, 4).gather(-1, g["arg"].unsqueeze(-1)).squeeze(-1) * g["pos"].to(hpre.dtype)
+        return (pooled @ p["critic.head2.w"].T + p["critic.head2.bias"]).reshape(-1)
+    h = F.relu(hpre)
     pooled = h.reshape(h.shape[0], -1, 4).max(dim=2).values        # GroupPooling: max over the group channels
     return (pooled @ p["critic.head2.w"].T + p["critic.head2.bias"]).reshape(-1)
 
@@ -159,21 +202,21 @@ def cat_obs(state: torch.Tensor, obs: torch.Tensor) -> torch.Tensor:
     return torch.cat([obs, tile], dim=1)
 
 
-def evaluate(p, state, obs, action, quant=False):
+def evaluate(p, state, obs, action, quant=False, route=None, route_out=None):
     """robot_actor_critic.evaluate with `action` given -> (log_prob [B], entropy [B], value [B])."""
     x = cat_obs(state, obs)
-    mean, log_std = actor_forward(p, x, quant=quant)
+    mean, log_std = actor_forward(p, x, quant=quant, route=route, route_out=route_out)
     std = torch.exp(log_std)
     var = std ** 2
     log_prob = -((action - mean) ** 2) / (2 * var) - std.log() - math.log(math.sqrt(2 * math.pi))
     entropy = 0.5 + 0.5 * math.log(2 * math.pi) + std.log()
-    return log_prob.sum(1), entropy.sum(1), critic_forward(p, x, quant=quant)
+    return log_prob.sum(1), entropy.sum(1), critic_forward(p, x, quant=quant, route=route, route_out=route_out)
 
 
 def update_loss(p, state, obs, action, oldlp, adv, ret, vold, true_action=None, clip_coeff=0.2, ent_c=0.01, vf_c=0.5,
-                norm_adv=True, clip_vloss=True, expert_weight=0.0, quant=False):
+                norm_adv=True, clip_vloss=True, expert_weight=0.0, quant=False, route=None, route_out=None):
     """Loss of robot_ppo.update (robot_ppo.py:345-398)."""
-    newlogprob, entropy, newvalue = evaluate(p, state, obs, action, quant=quant)
+    newlogprob, entropy, newvalue = evaluate(p, state, obs, action, quant=quant, route=route, route_out=route_out)
     log_ratio = newlogprob - oldlp
     ratio = log_ratio.exp()
     mb_adv = adv
