@@ -74,12 +74,35 @@ def cat_obs(state: torch.Tensor, obs: torch.Tensor) -> torch.Tensor:
     return torch.cat([obs, tile], dim=1)
 
 
-def encoder_forward(p, net: str, x: torch.Tensor, quant: bool = False) -> torch.Tensor:
+def _windows(z: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] -> [B,C,H/2,W/2,4] with the 2x2 window flattened as w = wy * 2 + wx."""
+    B, C, H, W = z.shape
+    return z.reshape(B, C, H // 2, 2, W // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, C, H // 2, W // 2, 4)
+
+
+def encoder_forward(p, net: str, x: torch.Tensor, quant: bool = False, route=None, route_out=None) -> torch.Tensor:
+    """route / route_out: forced / recorded discrete decisions per layer (max-pool arg-max, ReLU mask), see
+    oracle/equiv_ref.py::encoder_forward."""
     for l in range(7):
         W, b = p[f"{net}.conv.conv.{CONV_IDX[l]}.weight"], p[f"{net}.conv.conv.{CONV_IDX[l]}.bias"]
         if quant and l > 0:
             W = bf16_ste(W)
-        x = F.relu(F.conv2d(x, W, b, padding=PADS[l]))
+        x = F.conv2d(x, W, b, padding=PADS[l])
+        if route_out is not None:
+            with torch.no_grad():
+                if POOL[l]:
+                    zw = _windows(x)
+                    m = zw.max(-1).values
+                    route_out.append(dict(arg=(zw == m.unsqueeze(-1)).float().argmax(-1), pos=m > 0))
+                else:
+                    route_out.append(dict(arg=None, pos=x > 0))
+        if route is not None:
+            r = route[l]
+            if POOL[l]:
+                x = _windows(x).gather(-1, r["arg"].unsqueeze(-1)).squeeze(-1)
+            x = x * r["pos"].to(x.dtype)
+            continue
+        x = F.relu(x)
         if POOL[l]:
             x = F.max_pool2d(x, 2)
         if quant:
@@ -87,26 +110,30 @@ def encoder_forward(p, net: str, x: torch.Tensor, quant: bool = False) -> torch.
     return x.reshape(x.shape[0], -1)
 
 
-def evaluate(p, state, obs, action, quant: bool = False):
+def evaluate(p, state, obs, action, quant: bool = False, route=None, route_out=None):
     """robot_actor_critic.evaluate (equivariant=False) with `action` given -> (log_prob [B], entropy [B], value [B])."""
     x = cat_obs(state, obs)
     q = bf16_ste if quant else (lambda t: t)
-    fa, fc = encoder_forward(p, "actor", x, quant), encoder_forward(p, "critic", x, quant)
+    fa = encoder_forward(p, "actor", x, quant, route["actor"] if route else None, route_out["actor"] if route_out is not None else None)
+    fc = encoder_forward(p, "critic", x, quant, route["critic"] if route else None, route_out["critic"] if route_out is not None else None)
     mean = fa @ q(p["actor.mean_linear.weight"]).T + p["actor.mean_linear.bias"]
     log_std = p["actor_logstd"].expand_as(mean)
     std = torch.exp(log_std)
     var = std ** 2
     log_prob = -((action - mean) ** 2) / (2 * var) - std.log() - math.log(math.sqrt(2 * math.pi))
     entropy = 0.5 + 0.5 * math.log(2 * math.pi) + std.log()
-    h = F.relu(fc @ q(p["critic.critic.0.weight"]).T + p["critic.critic.0.bias"])
+    hpre = fc @ q(p["critic.critic.0.weight"]).T + p["critic.critic.0.bias"]
+    if route_out is not None:
+        route_out["group"] = dict(arg=None, pos=hpre.detach() > 0)
+    h = hpre * route["group"]["pos"].to(hpre.dtype) if route is not None else F.relu(hpre)
     value = (h @ p["critic.critic.2.weight"].T + p["critic.critic.2.bias"]).reshape(-1)
     return log_prob.sum(1), entropy.sum(1), value
 
 
 def update_loss(p, state, obs, action, oldlp, adv, ret, vold, clip_coeff=0.2, ent_c=0.01, vf_c=0.5, norm_adv=True,
-                clip_vloss=True, quant: bool = False):
+                clip_vloss=True, quant: bool = False, route=None, route_out=None):
     """Loss of robot_ppo.update (robot_ppo.py:345-398) without the behaviour-cloning term (constant in the parameters)."""
-    newlogprob, entropy, newvalue = evaluate(p, state, obs, action, quant=quant)
+    newlogprob, entropy, newvalue = evaluate(p, state, obs, action, quant=quant, route=route, route_out=route_out)
     ratio = (newlogprob - oldlp).exp()
     mb_adv = (adv - adv.mean()) / (adv.std() + 1e-8) if norm_adv else adv
     policy_loss = torch.max(-mb_adv * ratio, -mb_adv * torch.clamp(ratio, 1 - clip_coeff, 1 + clip_coeff)).mean()

@@ -11,9 +11,15 @@
  * trig mode 0 = host libm sin/cos (what gym calls); trig mode 1 = the
  * deterministic routine in aur_ppo_b200/csrc/det_sincos.h (the single header
  * the GPU kernels also compile), so that GPU-vs-checker transitions can be
- * compared bit-for-bit.  Build with -ffp-contract=off.
+ * compared bit-for-bit; trig mode 2 = the checker's OWN reference, independent
+ * of the product: libquadmath's 113-bit sinq / cosq rounded once to double,
+ * i.e. the correctly rounded value.  tests/test_oracle_envs.py replays the
+ * GPU parity trajectories in modes 1 and 2 and requires identical bits, so the
+ * bit-exact GPU == checker claim does not rest on the shared header alone.
+ * Build with -ffp-contract=off.
  */
 #include <math.h>
+#include <quadmath.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -42,11 +48,15 @@ static inline int time_limit_of(int kind) { return (kind == 0 || kind == 3) ? 50
 
 static inline void trig(int mode, double x, double* s, double* c) {
   if (mode == 0) { *s = sin(x); *c = cos(x); }
+  else if (mode == 2) { *s = (double)sinq((__float128)x); *c = (double)cosq((__float128)x); }
   else aur_sincos(x, s, c);
 }
 
 void orc_sincos(int64_t n, const double* x, double* s, double* c) {
   for (int64_t i = 0; i < n; ++i) aur_sincos(x[i], &s[i], &c[i]);
+}
+void orc_cr_sincos(int64_t n, const double* x, double* s, double* c) {
+  for (int64_t i = 0; i < n; ++i) { s[i] = (double)sinq((__float128)x[i]); c[i] = (double)cosq((__float128)x[i]); }
 }
 void orc_libm_sincos(int64_t n, const double* x, double* s, double* c) {
   for (int64_t i = 0; i < n; ++i) { s[i] = sin(x[i]); c[i] = cos(x[i]); }

@@ -20,7 +20,7 @@ CARTPOLE, PENDULUM, MOUNTAINCAR, ACROBOT, MOUNTAINCAR_CONT = 0, 1, 2, 3, 4
 OBS_DIM = {CARTPOLE: 4, PENDULUM: 3, MOUNTAINCAR: 2, ACROBOT: 6, MOUNTAINCAR_CONT: 2}
 PHYS_DIM = {CARTPOLE: 4, PENDULUM: 2, MOUNTAINCAR: 2, ACROBOT: 4, MOUNTAINCAR_CONT: 2}
 CONTINUOUS = (PENDULUM, MOUNTAINCAR_CONT)
-TRIG_LIBM, TRIG_DET = 0, 1
+TRIG_LIBM, TRIG_DET, TRIG_CR = 0, 1, 2       # TRIG_CR: libquadmath rounded once to double, independent of the product
 
 
 def build() -> str:
@@ -45,6 +45,7 @@ def lib():
         L.orc_vec_get_norm.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.orc_sincos.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 3
         L.orc_libm_sincos.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 3
+        L.orc_cr_sincos.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 3
         L.orc_pcg64_doubles.argtypes = [ctypes.c_uint64] * 4 + [ctypes.c_int64, ctypes.c_void_p]
         _LIB = L
     return _LIB
@@ -71,6 +72,14 @@ def libm_sincos(x: np.ndarray):
     x = np.ascontiguousarray(x, dtype=np.float64)
     s, c = np.empty_like(x), np.empty_like(x)
     lib().orc_libm_sincos(x.size, x.ctypes.data, s.ctypes.data, c.ctypes.data)
+    return s, c
+
+
+def cr_sincos(x: np.ndarray):
+    """Correctly rounded sin / cos (113-bit libquadmath evaluation rounded once): the checker's independent reference."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib().orc_cr_sincos(x.size, x.ctypes.data, s.ctypes.data, c.ctypes.data)
     return s, c
 
 

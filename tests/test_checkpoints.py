@@ -103,7 +103,7 @@ def test_play_reference_checkpoint_on_device_envs(mode):
     # observations the checker produces; greedy play is deterministic, so the lengths must agree exactly
     if mode == "greedy":
         m = compat.load_policy(os.path.join(CKPT, "actor_critic.pt"))
-        cv = E.CVecEnv(E.CARTPOLE, N, wrappers=False, trig=E.TRIG_DET)
+        cv = E.CVecEnv(E.CARTPOLE, N, wrappers=False, trig=E.TRIG_CR)
         obs, _ = cv.reset(list(range(3, 3 + N)))
         want = np.zeros(N, np.int64)
         done = np.zeros(N, bool)

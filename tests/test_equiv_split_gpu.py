@@ -140,16 +140,18 @@ def test_conv0_split_forward_and_weight_gradient():
     assert _rel(dbias.cpu(), bd.grad) < BAR, _rel(dbias.cpu(), bd.grad)
 
 
-def _device_route(model, B):
-    """The discrete decisions the device took in its last forward, in oracle/equiv_ref.py's `route` format."""
+def _device_route(model, B, real=None):
+    """The discrete decisions the device took in its last forward, in the oracles' `route` format.
+    real: real channel count per layer when the stored activations are channel-padded (plain CNN)."""
     route = {}
     inner = [(1, 65), (1, 33), (1, 17), (1, 9), (0, 8), (0, 3)]
     for net in ("actor", "critic"):
         e, layers = model.enc[net], []
         for l in range(6):
             lo, hi = inner[l]
-            act = e.a[l][0, :, lo:hi, lo:hi, :].permute(0, 3, 1, 2).float().cpu()          # hi plane: > 0 <=> value > 0
-            arg = e.arg[l].permute(0, 3, 1, 2).long().cpu() if e.arg[l] is not None else None
+            C = real[l] if real else e.a[l].shape[-1]
+            act = e.a[l][0, :, lo:hi, lo:hi, :C].permute(0, 3, 1, 2).float().cpu()          # hi plane: > 0 <=> value > 0
+            arg = e.arg[l][..., :C].permute(0, 3, 1, 2).long().cpu() if e.arg[l] is not None else None
             layers.append(dict(arg=arg, pos=act > 0))
         layers.append(dict(arg=None, pos=(e.feat[0].float().cpu() > 0).reshape(B, -1, 1, 1)))
         route[net] = layers
@@ -157,21 +159,24 @@ def _device_route(model, B):
 
 
 def _count_flips(dev_route, own_route):
-    flips, total, near = 0, 0, []
-    for net in ("actor", "critic"):
-        for d, o in zip(dev_route[net], own_route[net]):
-            diff = d["pos"] != o["pos"]
-            if d["arg"] is not None:
-                diff |= d["pos"] & o["pos"] & (d["arg"] != o["arg"])
-            flips += int(diff.sum())
-            total += diff.numel()
-    g_d, g_o = dev_route["group"], own_route["group"]
-    diff = (g_d["pos"] != g_o["pos"]) | (g_d["pos"] & g_o["pos"] & (g_d["arg"] != g_o["arg"]))
-    return flips + int(diff.sum()), total + diff.numel()
+    flips, total = 0, 0
+    items = [(d, o) for net in ("actor", "critic") for d, o in zip(dev_route[net], own_route[net])]
+    items.append((dev_route["group"], own_route["group"]))
+    for d, o in items:
+        diff = d["pos"] != o["pos"]
+        if d["arg"] is not None:
+            diff = diff | (d["pos"] & o["pos"] & (d["arg"] != o["arg"]))
+        flips += int(diff.sum())
+        total += diff.numel()
+    return flips, total
 
 
-@pytest.mark.parametrize("kind", ["equiv", "plain"])
-def test_full_update_split_gradients_match_fp64_autograd(kind):
+@pytest.mark.parametrize("kind,head_scale", [("equiv", 0.02), ("equiv", 0.1), ("plain", 1.0)])
+def test_full_update_split_gradients_match_fp64_autograd(kind, head_scale):
+    """head_scale: factor on the equivariant head filters.  The actor's log_std is a head OUTPUT there (equiv.py:88-90);
+    at 0.1 it reaches -2 (std 0.13) on this input, where d log_prob / d mean = diff / var amplifies any forward error ~50x
+    into the loss seeds of EVERY actor gradient; at 0.02 (|log_std| < 0.5, what a freshly initialised policy has) it does
+    not.  The critic and the plain CNN (state-independent actor_logstd = 0) have no such amplification."""
     from aur_ppo_b200 import equiv, plain_cnn
     B = 8
     g = torch.Generator().manual_seed(1)
@@ -182,16 +187,18 @@ def test_full_update_split_gradients_match_fp64_autograd(kind):
     state = (torch.rand(B, generator=g) > 0.5).float()
     action = torch.randn(B, 5, generator=g)
     adv, ret = torch.randn(B, generator=g), torch.randn(B, generator=g)
+    real = None
     if kind == "equiv":
         O = Q
         params = equiv.init_params(seed=5, scale=1.1)
         for k in ("actor.head.psi_triv", "actor.head.psi_irrep", "critic.head2.w"):
-            params[k].mul_(0.1)
+            params[k].mul_(head_scale)
         make = lambda: equiv.EquivActorCritic(params, B, split=True)
     else:
         from oracle import cnn_ref as O
         params = {k: v.cuda().contiguous() for k, v in O.formula_params(O.param_shapes(), seed=3).items()}
         make = lambda: plain_cnn.PlainActorCritic(params, B, split=True)
+        real = plain_cnn.REAL
     p32 = {k: v.detach().cpu().clone() for k, v in params.items()}
     p64 = {k: v.double().requires_grad_(True) for k, v in p32.items()}
     with torch.no_grad():
@@ -203,53 +210,56 @@ def test_full_update_split_gradients_match_fp64_autograd(kind):
     st = model.loss_and_grads(dev(state), dev(obs), dev(action), dev(oldlp), dev(adv), dev(ret), dev(vold)).cpu()
     args64 = [t.double() for t in (state, obs, action, oldlp, adv, ret, vold)]
 
-    if kind == "plain":
-        # the plain oracle has no forced-routing hook: compare on its own routing (float64) and report
-        loss, st_ref = O.update_loss(p64, *args64)
-        loss.backward()
-        worst = {k: _rel(model.grads[k].cpu(), p64[k].grad) for k in p64}
-        print("plain CNN, split precision vs float64 autograd (own routing): worst", max(worst.values()), worst)
-        assert abs(st[0] - st_ref["policy_loss"]) < BAR * max(1, abs(st_ref["policy_loss"]))
-        assert abs(st[1] - st_ref["value_loss"]) < BAR * max(1, abs(st_ref["value_loss"]))
-        assert abs(st[2] - st_ref["entropy"]) < BAR * max(1, abs(st_ref["entropy"]))
-        assert max(worst.values()) < 2e-2, worst         # flips allowed (see module docstring); typical tensors ~1e-5
-        assert sorted(worst.values())[len(worst) // 2] < BAR, worst
-        return
-
     # ---- (a) identical routing: the device's decisions forced on the float64 oracle
-    route = _device_route(model, B)
+    route = _device_route(model, B, real)
     a_out, c_pre, _, _ = model._last_head
-    hw = (c_pre.cpu() + Q.expand_bias_regular(p32["critic.head1.bias"])).reshape(B, -1, 4)
-    m = hw.max(-1).values
-    route["group"] = dict(arg=(hw == m.unsqueeze(-1)).float().argmax(-1), pos=m > 0)
-    loss, st_ref = Q.update_loss(p64, *args64, route=route)
+    if kind == "equiv":
+        hw = (c_pre.cpu() + Q.expand_bias_regular(p32["critic.head1.bias"])).reshape(B, -1, 4)
+        m = hw.max(-1).values
+        route["group"] = dict(arg=(hw == m.unsqueeze(-1)).float().argmax(-1), pos=m > 0)
+    else:
+        route["group"] = dict(arg=None, pos=(c_pre.cpu() + p32["critic.critic.0.bias"]) > 0)
+    loss, st_ref = O.update_loss(p64, *args64, route=route)
     loss.backward()
+    with torch.no_grad():
+        lp64, _, v64 = O.evaluate(p64, *args64[:3], route=route)
+    d_lp = float((model.logp.cpu().double() - lp64).abs().max())
+    d_v = float((model.value.cpu().double() - v64).abs().max())
     forced = {k: _rel(model.grads[k].cpu(), p64[k].grad) for k in p64}
-    print("split precision vs float64 autograd on identical routing:", {k: f"{v:.1e}" for k, v in forced.items()})
+    worst_a = max(v for k, v in forced.items() if k.startswith("actor"))
+    worst_c = max(v for k, v in forced.items() if k.startswith("critic"))
+    print(f"[{kind} x{head_scale}] split precision vs float64 autograd on identical routing: worst actor {worst_a:.1e}, worst critic "
+          f"{worst_c:.1e}; forward: max |log_prob error| {d_lp:.1e} (|log_prob| ~ {float(lp64.abs().mean()):.1f}), max |value error| {d_v:.1e}")
+    print("   per tensor:", {k: f"{v:.1e}" for k, v in forced.items()})
     assert abs(st[0] - st_ref["policy_loss"]) < BAR * max(1, abs(st_ref["policy_loss"]))
     assert abs(st[1] - st_ref["value_loss"]) < BAR * max(1, abs(st_ref["value_loss"]))
     assert abs(st[2] - st_ref["entropy"]) < BAR * max(1, abs(st_ref["entropy"]))
-    assert max(forced.values()) < BAR, forced
+    assert d_lp < BAR * float(lp64.abs().mean()) and d_v < BAR * max(1.0, float(v64.abs().max()))
+    assert worst_c < BAR, forced
+    assert worst_a < (BAR if head_scale != 0.1 else 1e-3), forced
 
     # ---- (b) the oracle's own routing in float64 and in float32: flips and what they cost
     own64 = {"actor": [], "critic": []}
     q64 = {k: v.detach().clone().requires_grad_(True) for k, v in p64.items()}
-    loss64, _ = Q.update_loss(q64, *args64, route_out=own64)
+    loss64, _ = O.update_loss(q64, *args64, route_out=own64)
     loss64.backward()
     own32 = {"actor": [], "critic": []}
     q32 = {k: v.clone().requires_grad_(True) for k, v in p32.items()}
-    loss32, _ = Q.update_loss(q32, state, obs, action, oldlp, adv, ret, vold, route_out=own32)
+    loss32, _ = O.update_loss(q32, state, obs, action, oldlp, adv, ret, vold, route_out=own32)
     loss32.backward()
     flips_dev, total = _count_flips(route, own64)
     flips_f32, _ = _count_flips(own32, own64)
     free_dev = {k: _rel(model.grads[k].cpu(), q64[k].grad) for k in q64}
     free_f32 = {k: _rel(q32[k].grad, q64[k].grad) for k in q64}
-    print(f"routing decisions differing from float64: device (split) {flips_dev} of {total}, torch fp32 CPU {flips_f32} of {total}")
-    print("own-routing gradient error, device vs fp64: worst %.2e; torch fp32 vs fp64: worst %.2e" %
-          (max(free_dev.values()), max(free_f32.values())))
-    assert flips_dev <= max(200, 50 * max(flips_f32, 1)), (flips_dev, flips_f32)
+    print(f"   routing decisions differing from float64: device (split) {flips_dev} of {total}, torch fp32 on the CPU {flips_f32} of {total}")
+    print("   own-routing gradient error vs float64: device worst %.2e (median %.2e); torch fp32 CPU worst %.2e (median %.2e)" %
+          (max(free_dev.values()), sorted(free_dev.values())[len(free_dev) // 2], max(free_f32.values()),
+           sorted(free_f32.values())[len(free_f32) // 2]))
+    assert flips_dev <= max(400, 100 * max(flips_f32, 1)), (flips_dev, flips_f32)
     assert max(free_dev.values()) < 5e-2, free_dev
 
+    if kind != "equiv":
+        return
     # one Adam step on these gradients (actor-only clip, robot_ppo.py:401-402)
     before = {k: v.clone() for k, v in params.items()}
     model.apply(lr=3e-4, max_grad_norm=0.5)

@@ -97,6 +97,47 @@ def test_det_vs_libm_discrepancy_is_last_bit_only():
     assert np.mean(s != s2) < 0.01 and np.mean(c != c2) < 0.01
 
 
+def test_det_sincos_vs_independent_correctly_rounded_reference():
+    """The product's sin / cos (det_sincos.h) against the checker's OWN reference (libquadmath rounded once = correctly
+    rounded): a census of 2e6 random points per env range; the full 1e8-point census is profiles/r2_sincos_census.md
+    (det: 6e-8 .. 1.4e-6 of the points differ in the last bit; glibc libm: 0.14 .. 0.28 %)."""
+    rng = np.random.default_rng(5)
+    for lo, hi in ((-0.42, 0.42), (-85.0, 85.0), (-6.3, 6.3), (-3.6, 1.8)):
+        x = rng.uniform(lo, hi, 2_000_000)
+        s, c = E.det_sincos(x)
+        s2, c2 = E.cr_sincos(x)
+        s3, c3 = E.libm_sincos(x)
+        det_bad = int((s != s2).sum() + (c != c2).sum())
+        libm_bad = int((s3 != s2).sum() + (c3 != c2).sum())
+        assert det_bad <= 20, (lo, hi, det_bad)                       # <= 5e-6 of 4e6 values
+        assert libm_bad > 50 * max(det_bad, 1), (lo, hi, libm_bad)     # the libm gym calls is the less reproducible one
+        bad = (s != s2) | (c != c2)
+        if bad.any():                                                 # and where it differs it is the neighbouring double
+            assert np.all(np.abs(s[bad] - s2[bad]) <= np.spacing(np.abs(s2[bad])))
+            assert np.all(np.abs(c[bad] - c2[bad]) <= np.spacing(np.abs(c2[bad])))
+
+
+@pytest.mark.parametrize("kind,N,T,wrappers,cont,nact", [(E.CARTPOLE, 1024, 700, False, False, 2), (E.PENDULUM, 256, 600, True, True, 1),
+                                                       (E.PENDULUM, 256, 600, False, True, 1), (E.ACROBOT, 128, 600, False, False, 3),
+                                                       (E.MOUNTAINCAR, 256, 400, False, False, 3),
+                                                       (E.MOUNTAINCAR_CONT, 128, 1100, True, True, 1)])
+def test_checker_trajectories_identical_with_product_and_independent_trig(kind, N, T, wrappers, cont, nact):
+    """The GPU parity tests compare the CUDA kernels (det_sincos.h) with the checker in TRIG_CR mode (libquadmath), i.e.
+    with trigonometry the product does not share.  Here the checker itself runs both ways: every observation, reward,
+    flag and the final fp64 state (incl. the wrappers' running statistics) must be identical bit for bit."""
+    rng = np.random.default_rng(kind * 7 + 1)
+    a = E.CVecEnv(kind, N, wrappers=wrappers, trig=E.TRIG_DET)
+    b = E.CVecEnv(kind, N, wrappers=wrappers, trig=E.TRIG_CR)
+    oa, _ = a.reset(list(range(N))); ob, _ = b.reset(list(range(N)))
+    assert np.array_equal(oa, ob)
+    for t in range(T):
+        act = rng.normal(0, 1, (N, 1)).astype(np.float32) if cont else rng.integers(0, nact, N)
+        ra, rb = a.step(act), b.step(act)
+        for u, v in zip(ra[:4], rb[:4]):
+            assert np.array_equal(u, v), (t,)
+    assert np.array_equal(a.phys(), b.phys())
+
+
 def test_det_and_libm_trajectories_agree_on_float32_observations():
     """Measures what the sincos choice changes at the interface the policy sees."""
     N, T = 64, 600

@@ -61,7 +61,7 @@ def test_unsupported_shapes_fail_loudly():
 
 
 def _oracle_replay(kind, N, wrappers, seeds, actions, T):
-    cv = E.CVecEnv(kind, N, wrappers=wrappers, trig=E.TRIG_DET)
+    cv = E.CVecEnv(kind, N, wrappers=wrappers, trig=E.TRIG_CR)
     obs0, _ = cv.reset(seeds)
     D = cv.obs_dim
     obs = np.zeros((T, N, D), np.float32); rew = np.zeros((T, N), np.float32); done = np.zeros((T, N), np.float32)
@@ -162,7 +162,7 @@ def test_mountaincar_replay_is_bit_exact(N, T):
 def _oracle_replay_adaptive(kind, N, seeds, actions, T):
     """Like _oracle_replay, but even-numbered envs follow the energy-pumping policy (push in the direction of motion):
     `actions` is overwritten in place with what was actually played."""
-    cv = E.CVecEnv(kind, N, wrappers=False, trig=E.TRIG_DET)
+    cv = E.CVecEnv(kind, N, wrappers=False, trig=E.TRIG_CR)
     obs0, _ = cv.reset(seeds)
     D = cv.obs_dim
     obs = np.zeros((T, N, D), np.float32); rew = np.zeros((T, N), np.float32); done = np.zeros((T, N), np.float32)
@@ -316,7 +316,7 @@ def test_full_size_rollout_properties():
     acts = buf.actions.cpu().numpy()
     assert set(np.unique(acts)) <= {0.0, 1.0} and 0.3 < acts.mean() < 0.7
     cols = np.sort(np.random.default_rng(0).choice(N, 96, replace=False))
-    cv = E.CVecEnv(E.CARTPOLE, len(cols), wrappers=False, trig=E.TRIG_DET)
+    cv = E.CVecEnv(E.CARTPOLE, len(cols), wrappers=False, trig=E.TRIG_CR)
     cur, _ = cv.reset([int(c) for c in cols])            # env i is seeded with its global id
     cur_done = np.zeros(len(cols), np.float32)
     states, terminals = buf.states.cpu().numpy(), buf.terminals.cpu().numpy()
@@ -449,7 +449,7 @@ def test_acrobot_replay_is_bit_exact(N, T, hidden, rollout_impl):
     rng = np.random.default_rng(N)
     # torque along the second joint's velocity most of the time, so that episodes actually terminate inside T
     actions = rng.integers(0, 3, (T, N))
-    cv = E.CVecEnv(E.ACROBOT, N, trig=E.TRIG_DET)
+    cv = E.CVecEnv(E.ACROBOT, N, trig=E.TRIG_CR)
     cv.reset(seeds)
     for t in range(T):
         greedy = np.where(cv.phys()[:, 3] > 0, 2, 0)
@@ -491,7 +491,7 @@ def test_mountaincar_continuous_replay_is_bit_exact(wrappers, hidden, rollout_im
     rng = np.random.default_rng(3)
     # rock with the velocity (plus noise, some of it outside [-1, 1]) so that some episodes reach the flag
     actions = np.zeros((T, N, 1), np.float32)
-    cv = E.CVecEnv(E.MOUNTAINCAR_CONT, N, wrappers=wrappers, trig=E.TRIG_DET)
+    cv = E.CVecEnv(E.MOUNTAINCAR_CONT, N, wrappers=wrappers, trig=E.TRIG_CR)
     cv.reset(seeds)
     for t in range(T):
         vel = cv.phys()[:, 1]
