@@ -44,13 +44,13 @@ class RolloutArgs(ctypes.Structure):
 
 
 class UpdateArgs(ctypes.Structure):
-    _fields_ = [("policy", PolicyDesc), ("norm_adv", c_int32), ("clip_vloss", c_int32), ("_pad", c_int32),
+    _fields_ = [("policy", PolicyDesc), ("norm_adv", c_int32), ("clip_vloss", c_int32), ("mom_index", c_int32),
                 ("m_local", c_int64), ("m_total", c_int64), ("idx", c_void_p), ("idx_offset", c_int64),
                 ("obs", c_void_p), ("actions", c_void_p), ("logprobs", c_void_p), ("advantages", c_void_p),
                 ("returns", c_void_p), ("values", c_void_p), ("params", c_void_p),
                 ("clip_coeff", ctypes.c_float), ("entropy_coeff", ctypes.c_float), ("value_coeff", ctypes.c_float),
                 ("_pad2", ctypes.c_float), ("adv_moments", c_void_p), ("workspace", c_void_p), ("grads_out", c_void_p),
-                ("dp", c_void_p), ("dp_seq", ctypes.c_uint32), ("_pad3", ctypes.c_uint32),
+                ("dp", c_void_p), ("dp_seq", ctypes.c_uint32), ("mom_seq", ctypes.c_uint32),
                 ("rec_actor", c_void_p), ("rec_critic", c_void_p)]
 
 
@@ -166,6 +166,9 @@ def lib() -> ctypes.CDLL:
     L.aur_dp_free.argtypes = [c_void_p]
     L.aur_dp_status.restype = c_int
     L.aur_dp_status.argtypes = [c_void_p, c_void_p]
+    L.aur_ppo_adv_moments_multi.restype = c_int
+    L.aur_ppo_adv_moments_multi.argtypes = [c_int32, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            ctypes.c_uint32, c_void_p]
     L.aur_ppo_adv_moments_dp.restype = c_int
     L.aur_ppo_adv_moments_dp.argtypes = [c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint32,
                                          c_void_p]

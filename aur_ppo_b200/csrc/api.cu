@@ -37,6 +37,7 @@ int sm_count() {
 
 namespace {
 struct TicketSlot { int dev; cudaStream_t s; unsigned int* p; };
+constexpr size_t TICKET_BYTES = 4096;   // words 0, 1: single-minibatch moments / gradient reduce; 16 ..: aur_ppo_adv_moments_multi (1 + 512)
 std::mutex g_ticket_mu;
 std::vector<TicketSlot> g_tickets;
 }  // namespace
@@ -53,7 +54,7 @@ unsigned int* stream_tickets(cudaStream_t s) {
     return nullptr;
   }
   unsigned int* p = nullptr;
-  if (cudaMalloc(&p, 64) != cudaSuccess || cudaMemset(p, 0, 64) != cudaSuccess) {
+  if (cudaMalloc(&p, TICKET_BYTES) != cudaSuccess || cudaMemset(p, 0, TICKET_BYTES) != cudaSuccess) {
     (void)cudaGetLastError();
     set_error("stream_tickets: cudaMalloc failed");
     return nullptr;

@@ -45,7 +45,7 @@ struct DeviceOnce {
 };
 
 // Last-CTA ticket counters owned by the LIBRARY (zeroed at allocation, reset by the kernel that used them), one
-// block of 16 words per (device, stream): kernels of one stream run in order, so they can share a block; a
+// block of 1024 words per (device, stream): kernels of one stream run in order, so they can share a block; a
 // caller-provided workspace would have to be zero-initialised by contract (it is not part of the ABI contract).
 // Returns nullptr on failure (error text set).
 unsigned int* stream_tickets(cudaStream_t s);

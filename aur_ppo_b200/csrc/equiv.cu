@@ -38,10 +38,11 @@ struct ConvDev {
   int pix_tiles, n_tiles;                  // work items: pix_tiles x n_tiles (output-channel blocks), walked by a persistent grid
   int epi;                                 // 0 linear, 1 bias+ReLU, 2 bias+ReLU+maxpool2
   int oHb, oWb, ooff;                      // output buffer geometry
-  int nterm;                               // K-step terms per (tap, channel chunk): 1 = bf16, 3 = split planes (hi,hi), (hi,mid), (mid,hi)
+  int nterm;                               // K-step terms per (tap, channel chunk): 1 / 3 / 6 for 1 / 2 / 3 operand planes (tc.cuh)
+  int planes;                              // planes of the output stack
+  size_t out_plane;                        // elements between the output planes
   const float* bias;
   __nv_bfloat16* out;
-  __nv_bfloat16* out_mid;                  // split: mid plane of the output (same geometry), else NULL
   unsigned char* pool_arg;
   const __nv_bfloat16* relu_ref;           // epi 3: out = acc * (relu_ref > 0), relu_ref buffer [B,rHb,rWb,Cout] at +roff
   int rHb, rWb, roff;
@@ -260,9 +261,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (valid && w == 0) {
           const size_t pix = ((size_t)b * a.oHb + (y >> 1) + a.ooff) * a.oWb + (x >> 1) + a.ooff;
           __nv_bfloat16* dst = a.out + pix * a.Cout + ch;
-          __nv_bfloat16* dmid = a.out_mid ? a.out_mid + pix * a.Cout + ch : nullptr;
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) store8_planes(dst + i, dmid ? dmid + i : nullptr, v + i);
+          for (int i = 0; i < 32; i += 8) store8_planes(dst + i, a.out_plane, a.planes, v + i);
           if (a.pool_arg) {
             const size_t ppix = ((size_t)b * (a.Ho >> 1) + (y >> 1)) * (a.Wo >> 1) + (x >> 1);
             uint4* ad = reinterpret_cast<uint4*>(a.pool_arg + ppix * a.Cout + ch);
@@ -273,7 +273,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } else if (valid) {
         const size_t pix = ((size_t)b * a.oHb + y + a.ooff) * a.oWb + x + a.ooff;
         __nv_bfloat16* dst = a.out + pix * a.Cout + ch;
-        __nv_bfloat16* dmid = a.out_mid ? a.out_mid + pix * a.Cout + ch : nullptr;
         if (a.epi == 3) {
           const __nv_bfloat16* ref = a.relu_ref + (((size_t)b * a.rHb + y + a.roff) * a.rWb + x + a.roff) * a.Cout + ch;
 #pragma unroll
@@ -289,7 +288,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) store8_planes(dst + i, dmid ? dmid + i : nullptr, v + i);
+        for (int i = 0; i < 32; i += 8) store8_planes(dst + i, a.out_plane, a.planes, v + i);
       }
     }
     }   // items
@@ -324,15 +323,9 @@ __global__ void expand_reg_reg_kernel(const float* __restrict__ psi, int Fo, int
     int ys, xs;
     rot_src(r, y, x, ys, xs);
     const float w = psi[((((size_t)o * Fi + i) * 4 + ((s - r) & 3)) * 3 + ys) * 3 + xs];
-    __nv_bfloat16 wb, wm;
-    split_bf16(w, wb, wm);
-    wmat[e] = wb;
     const size_t te = ((size_t)ci * 9 + (8 - tap)) * Cout + co;
-    if (wt) wt[te] = wb;
-    if (planes == 2) {                     // mid planes behind the hi planes
-      wmat[total + e] = wm;
-      if (wt) wt[total + te] = wm;
-    }
+    store_planes(wmat + e, (size_t)total, planes, w);          // planes stacked behind each other
+    if (wt) store_planes(wt + te, (size_t)total, planes, w);
   }
 }
 __global__ void expand_bias_kernel(const float* __restrict__ bias_f, int F, float* __restrict__ bias_ch) {
@@ -349,7 +342,7 @@ __global__ void expand_bias_kernel(const float* __restrict__ bias_f, int F, floa
 template <bool PLAIN>
 __global__ void __launch_bounds__(256)
 conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ state, const float* __restrict__ psi,
-                    const float* __restrict__ bias_f, int B, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_mid,
+                    const float* __restrict__ bias_f, int B, __nv_bfloat16* __restrict__ out, int planes,
                     unsigned char* __restrict__ pool_arg) {
   // weights of a PAIR of output channels interleaved: [pair][18 taps + bias + pad][2], read as ten warp-uniform
   // LDS.128 and fed to FFMA2 (the two halves are the two channels)
@@ -395,7 +388,7 @@ conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ sta
         p0[i][j] = in ? __ldg(img + yy * 128 + xx) : 0.0f;
         p1[i][j] = in ? st : 0.0f;
       }
-    unsigned int packed[8], packed_mid[8];
+    float bestv[16];
     unsigned int argp[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int cp = 0; cp < 8; ++cp) {
@@ -424,24 +417,15 @@ conv0_direct_kernel(const float* __restrict__ obs, const float* __restrict__ sta
           if (w == 0 || acc.x > best.x) { best.x = acc.x; bw0 = w; }
           if (w == 0 || acc.y > best.y) { best.y = acc.y; bw1 = w; }
         }
-      __nv_bfloat16 h0, m0, h1, m1;
-      split_bf16(best.x, h0, m0);
-      split_bf16(best.y, h1, m1);
-      packed[cp] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
-      packed_mid[cp] = (unsigned int)__bfloat16_as_ushort(m0) | ((unsigned int)__bfloat16_as_ushort(m1) << 16);
+      bestv[2 * cp] = best.x; bestv[2 * cp + 1] = best.y;
       const int c = 2 * cp;
       if ((c & 3) == 0) argp[c >> 2] = 0u;
       argp[c >> 2] |= ((unsigned int)bw0 << (8 * (c & 3))) | ((unsigned int)bw1 << (8 * ((c + 1) & 3)));
     }
     const size_t pix = ((size_t)b * 66 + py + 1) * 66 + px + 1;
-    uint4* dst = reinterpret_cast<uint4*>(out + pix * 64 + cg * 16);
-    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-    if (out_mid) {
-      uint4* dm = reinterpret_cast<uint4*>(out_mid + pix * 64 + cg * 16);
-      dm[0] = make_uint4(packed_mid[0], packed_mid[1], packed_mid[2], packed_mid[3]);
-      dm[1] = make_uint4(packed_mid[4], packed_mid[5], packed_mid[6], packed_mid[7]);
-    }
+    const size_t plane = (size_t)B * 66 * 66 * 64;
+    store8_planes(out + pix * 64 + cg * 16, plane, planes, bestv);
+    store8_planes(out + pix * 64 + cg * 16 + 8, plane, planes, bestv + 8);
     if (pool_arg) {
       const size_t ppix = ((size_t)b * 64 + py) * 64 + px;
       *reinterpret_cast<uint4*>(pool_arg + ppix * 64 + cg * 16) = make_uint4(argp[0], argp[1], argp[2], argp[3]);
@@ -477,8 +461,7 @@ extern "C" int aur_equiv_conv0(const float* obs, const float* state, const float
   const long long total = (long long)B * 64 * 64 * 4;
   long long grid = (total + 255) / 256;
   if (grid > 148 * 32) grid = 148 * 32;
-  __nv_bfloat16* out_mid = tc_planes() == 2 ? (__nv_bfloat16*)out + (size_t)B * 66 * 66 * 64 : nullptr;
-  conv0_direct_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, state, psi, bias_f, B, (__nv_bfloat16*)out, out_mid, pool_arg);
+  conv0_direct_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, state, psi, bias_f, B, (__nv_bfloat16*)out, tc_planes(), pool_arg);
   AUR_LAUNCH_OK("conv0_direct_kernel");
   return 0;
 }
@@ -491,8 +474,7 @@ extern "C" int aur_plain_conv0(const float* obs, const float* state, const float
   const long long total = (long long)B * 64 * 64;
   long long grid = (total + 255) / 256;
   if (grid > 148 * 32) grid = 148 * 32;
-  __nv_bfloat16* out_mid = tc_planes() == 2 ? (__nv_bfloat16*)out + (size_t)B * 66 * 66 * 64 : nullptr;
-  conv0_direct_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, state, weight, bias, B, (__nv_bfloat16*)out, out_mid, pool_arg);
+  conv0_direct_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, state, weight, bias, B, (__nv_bfloat16*)out, tc_planes(), pool_arg);
   AUR_LAUNCH_OK("conv0_direct_kernel<plain>");
   return 0;
 }
@@ -517,8 +499,9 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   d.B = c.B; d.Hb = c.Hb; d.Wb = c.Wb; d.Ho = c.Hb - 2; d.Wo = c.Wb - 2; d.Cin = c.Cin; d.Cout = c.Cout;
   d.epi = c.epilogue; d.oHb = c.out_Hb; d.oWb = c.out_Wb; d.ooff = c.out_off; d.bias = c.bias;
   const int P = tc_planes();
-  d.nterm = P == 2 ? 3 : 1;
-  d.out_mid = P == 2 ? (__nv_bfloat16*)c.out + (size_t)c.B * c.out_Hb * c.out_Wb * c.Cout : nullptr;
+  d.nterm = tc_terms(P);
+  d.planes = P;
+  d.out_plane = (size_t)c.B * c.out_Hb * c.out_Wb * c.Cout;
   d.out = (__nv_bfloat16*)c.out; d.pool_arg = c.pool_arg; d.relu_ref = (const __nv_bfloat16*)c.relu_ref; d.rHb = c.ref_Hb; d.rWb = c.ref_Wb; d.roff = c.ref_off;
   if (c.epilogue == 3 && !c.relu_ref) { set_error("aur_conv3x3_bf16: epilogue 3 needs relu_ref"); return AUR_ERR_ARG; }
   if (c.epilogue == 2 && ((d.Ho | d.Wo) & 1)) { set_error("aur_conv3x3_bf16: pooling needs even output size"); return AUR_ERR_ARG; }

@@ -156,14 +156,12 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // colsum (nullable): the bias gradient of the layer, out[c / group] += sum over all written positions of dy[.., c] - what
 // colsum_bf16_kernel would compute from dy, taken here from registers instead of re-reading the buffer.  The grid is a
 // multiple of C / 8 threads (C / 8 divides 256), so a thread keeps one channel group for its whole grid-stride loop.
-// dpool_mid / dy_mid (nullable): the mid planes of the split representation, routed exactly like the hi plane (the ReLU mask
-// reads the hi plane of `act`: hi > 0 <=> value > 0).
+// planes: every plane of the gradient stack (dpool -> dy, plane strides dp_plane / dy_plane) is routed exactly alike; the ReLU
+// mask reads the hi plane of `act` (hi > 0 <=> value > 0).
 __global__ void unpool_relu_bwd_kernel(int B, int Hp, int Wp, int C, const __nv_bfloat16* __restrict__ dpool,
-                                       const __nv_bfloat16* __restrict__ dpool_mid,
                                        const __nv_bfloat16* __restrict__ act, int aHb, int aWb, int aoff,
-                                       const unsigned char* __restrict__ arg, __nv_bfloat16* __restrict__ dy,
-                                       __nv_bfloat16* __restrict__ dy_mid, int dHb, int dWb,
-                                       int doff, int group, float* __restrict__ colsum) {
+                                       const unsigned char* __restrict__ arg, __nv_bfloat16* __restrict__ dy, int dHb, int dWb,
+                                       int doff, int group, float* __restrict__ colsum, int planes, size_t dp_plane, size_t dy_plane) {
   __shared__ float sacc[1024];
   float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int cg = C >> 3;
@@ -175,32 +173,26 @@ __global__ void unpool_relu_bwd_kernel(int B, int Hp, int Wp, int C, const __nv_
     const int py = (int)(r % Hp); r /= Hp;
     const int b = (int)r;
     const size_t pp = (((size_t)b * Hp + py) * Wp + px) * C + c8 * 8;
-    const uint4 g = *reinterpret_cast<const uint4*>(dpool + pp);
-    uint4 gm = make_uint4(0u, 0u, 0u, 0u);
-    if (dpool_mid) gm = *reinterpret_cast<const uint4*>(dpool_mid + pp);
     const uint4 av = *reinterpret_cast<const uint4*>(act + (((size_t)b * aHb + py + aoff) * aWb + px + aoff) * C + c8 * 8);
     const uint2 ar = *reinterpret_cast<const uint2*>(arg + pp);
-    const unsigned short* gs = reinterpret_cast<const unsigned short*>(&g);
-    const unsigned short* gms = reinterpret_cast<const unsigned short*>(&gm);
     const unsigned short* as = reinterpret_cast<const unsigned short*>(&av);
     const unsigned char* ab = reinterpret_cast<const unsigned char*>(&ar);
-    unsigned short o[4][8], om[4][8];
+    for (int pl = 0; pl < planes; ++pl) {
+      const uint4 g = *reinterpret_cast<const uint4*>(dpool + pl * dp_plane + pp);
+      const unsigned short* gs = reinterpret_cast<const unsigned short*>(&g);
+      unsigned short o[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const bool pos = (as[i] & 0x7FFFu) != 0 && !(as[i] & 0x8000u);
+      for (int i = 0; i < 8; ++i) {
+        const bool pos = (as[i] & 0x7FFFu) != 0 && !(as[i] & 0x8000u);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) o[w][i] = (pos && ab[i] == w) ? gs[i] : (unsigned short)0;
+        if (pos && ab[i] < 4) bsum[i] += __uint_as_float((unsigned int)gs[i] << 16);
+      }
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
-        o[w][i] = (pos && ab[i] == w) ? gs[i] : (unsigned short)0;
-        om[w][i] = (pos && ab[i] == w) ? gms[i] : (unsigned short)0;
+        const int y = 2 * py + (w >> 1) + doff, x = 2 * px + (w & 1) + doff;
+        *reinterpret_cast<uint4*>(dy + pl * dy_plane + (((size_t)b * dHb + y) * dWb + x) * C + c8 * 8) = *reinterpret_cast<const uint4*>(o[w]);
       }
-      if (pos && ab[i] < 4) bsum[i] += __uint_as_float((unsigned int)gs[i] << 16) + __uint_as_float((unsigned int)gms[i] << 16);
-    }
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const int y = 2 * py + (w >> 1) + doff, x = 2 * px + (w & 1) + doff;
-      const size_t di = (((size_t)b * dHb + y) * dWb + x) * C + c8 * 8;
-      *reinterpret_cast<uint4*>(dy + di) = *reinterpret_cast<const uint4*>(o[w]);
-      if (dy_mid) *reinterpret_cast<uint4*>(dy_mid + di) = *reinterpret_cast<const uint4*>(om[w]);
     }
   }
   if (colsum) {
@@ -319,7 +311,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(long long Q, int C, co
 constexpr int C0W_PIX = 32;               // pooled pixels staged per barrier pair
 __global__ void __launch_bounds__(256)
 conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ state, const __nv_bfloat16* __restrict__ da1,
-                   const __nv_bfloat16* __restrict__ da1_mid /*nullable*/,
+                   int planes /*of da1, stacked B * 64 * 64 * 64 elements apart*/,
                    const __nv_bfloat16* __restrict__ a1 /*[B,66,66,64]*/, const unsigned char* __restrict__ arg, int B,
                    float* __restrict__ dw0 /*[64][2][9] expanded-channel gradient*/, float* __restrict__ dbias_ch /*[64]*/) {
   __shared__ __align__(16) float patch[C0W_PIX][2][4][4];
@@ -349,11 +341,12 @@ conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ stat
     __syncthreads();
     // this thread's channel over 8 of the staged pixels; the three per-pixel loads of all 8 are issued up front
     // raw loads first (nothing consumes them inside this loop, so all 24 are in flight together), conversions after
-    unsigned short ar[C0W_PIX / 4], gr[C0W_PIX / 4], gmr[C0W_PIX / 4];
+    unsigned short ar[C0W_PIX / 4];
+    float gsum[C0W_PIX / 4];
     unsigned char wr[C0W_PIX / 4];
     const unsigned short* a1u = reinterpret_cast<const unsigned short*>(a1);
     const unsigned short* da1u = reinterpret_cast<const unsigned short*>(da1);
-    const unsigned short* da1mu = reinterpret_cast<const unsigned short*>(da1_mid);
+    const size_t gplane = (size_t)B * 64 * 64 * 64;
 #pragma unroll
     for (int k = 0; k < C0W_PIX / 4; ++k) {
       long long pix = base + sub + 4 * k;
@@ -361,8 +354,8 @@ conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ stat
       if (!ok) pix = npix - 1;                         // clamp instead of branching; masked below
       const int px = (int)(pix & 63), py = (int)((pix >> 6) & 63), b = (int)(pix >> 12);
       ar[k] = __ldg(a1u + (((size_t)b * 66 + py + 1) * 66 + px + 1) * 64 + co);
-      gr[k] = __ldg(da1u + (size_t)pix * 64 + co);
-      gmr[k] = da1mu ? __ldg(da1mu + (size_t)pix * 64 + co) : (unsigned short)0;
+      gsum[k] = 0.0f;
+      for (int pl = planes - 1; pl >= 0; --pl) gsum[k] += __uint_as_float((unsigned int)__ldg(da1u + pl * gplane + (size_t)pix * 64 + co) << 16);
       wr[k] = __ldg(arg + (size_t)pix * 64 + co);
       if (!ok) ar[k] = 0;
     }
@@ -371,7 +364,7 @@ conv0_wgrad_kernel(const float* __restrict__ obs, const float* __restrict__ stat
 #pragma unroll
     for (int k = 0; k < C0W_PIX / 4; ++k) {
       av[k] = __uint_as_float((unsigned int)ar[k] << 16);
-      gv[k] = __uint_as_float((unsigned int)gr[k] << 16) + __uint_as_float((unsigned int)gmr[k] << 16);
+      gv[k] = gsum[k];
       wv[k] = wr[k];
     }
 #pragma unroll
@@ -422,34 +415,21 @@ __global__ void project_conv0_kernel(const float* __restrict__ dw0, const float*
 
 // ---- elementwise helpers ---------------------------------------------------------------------------
 // out_bf16[r][c] = relu(in_f32[r][c] + bias[c])
-// (every helper: out_mid nullable = mid plane of the split representation)
+// (every helper: `planes` output planes, stacked n elements apart)
 __global__ void bias_relu_kernel(long long n, int C, const float* __restrict__ in, const float* __restrict__ bias,
-                                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_mid) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    __nv_bfloat16 h, m;
-    split_bf16(fmaxf(in[i] + bias[(int)(i % C)], 0.0f), h, m);
-    out[i] = h;
-    if (out_mid) out_mid[i] = m;
-  }
+                                 __nv_bfloat16* __restrict__ out, int planes) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    store_planes(out + i, (size_t)n, planes, fmaxf(in[i] + bias[(int)(i % C)], 0.0f));
 }
 // out_bf16 = g_f32 * (ref_bf16 > 0)
 __global__ void relu_mask_kernel(long long n, const float* __restrict__ g, const __nv_bfloat16* __restrict__ ref,
-                                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_mid) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    __nv_bfloat16 h, m;
-    split_bf16(__bfloat162float(ref[i]) > 0.0f ? g[i] : 0.0f, h, m);
-    out[i] = h;
-    if (out_mid) out_mid[i] = m;
-  }
+                                 __nv_bfloat16* __restrict__ out, int planes) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    store_planes(out + i, (size_t)n, planes, __bfloat162float(ref[i]) > 0.0f ? g[i] : 0.0f);
 }
-__global__ void f32_to_bf16_kernel(long long n, const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                   __nv_bfloat16* __restrict__ out_mid) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    __nv_bfloat16 h, m;
-    split_bf16(in[i], h, m);
-    out[i] = h;
-    if (out_mid) out_mid[i] = m;
-  }
+__global__ void f32_to_bf16_kernel(long long n, const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int planes) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    store_planes(out + i, (size_t)n, planes, in[i]);
 }
 
 // ---- heads + loss: one warp per sample --------------------------------------------------------------
@@ -467,7 +447,7 @@ struct HeadLossDev {
   int clip_vloss;
   __nv_bfloat16* d_a_out;  // [B,16] gradient wrt actor head output (bf16, zero padded)
   __nv_bfloat16* d_c_h;    // [B,512] gradient wrt critic head-1 pre-activation
-  __nv_bfloat16 *d_a_out_mid, *d_c_h_mid;   // split: mid planes, else NULL
+  int planes;              // planes of d_a_out / d_c_h (stacked B * 16 / B * 512 elements apart)
   float* d_head;           // [10 + 128 + 1 + 512]: d a_bias | d c_w2 | d c_b2 | d c_bias1(per channel)
   float* stats;            // [8] sums: policy loss, value loss (x vf_c as the reference), entropy, -logr, r-1-logr, clip
   float* value_out;        // [B]
@@ -571,12 +551,7 @@ __global__ void __launch_bounds__(256) head_loss_kernel(HeadLossDev a) {
         d10[5 + d] = g_logp * dls[d] + g_H * o10[5 + d];
       }
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        __nv_bfloat16 h, m;
-        split_bf16(k < 10 ? d10[k] : 0.0f, h, m);
-        a.d_a_out[(size_t)b * 16 + k] = h;
-        if (a.d_a_out_mid) a.d_a_out_mid[(size_t)b * 16 + k] = m;
-      }
+      for (int k = 0; k < 16; ++k) store_planes(a.d_a_out + (size_t)b * 16 + k, (size_t)a.B * 16, a.planes, k < 10 ? d10[k] : 0.0f);
 #pragma unroll
       for (int k = 0; k < 10; ++k) dbias_a[k] += d10[k];
       db2 += dv;
@@ -590,10 +565,7 @@ __global__ void __launch_bounds__(256) head_loss_kernel(HeadLossDev a) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const float g = (r == field_arg[f] && hv[f * 4 + r] > 0.0f) ? gp : 0.0f;
-        __nv_bfloat16 gh, gm;
-        split_bf16(g, gh, gm);
-        a.d_c_h[(size_t)b * 512 + fld * 4 + r] = gh;
-        if (a.d_c_h_mid) a.d_c_h_mid[(size_t)b * 512 + fld * 4 + r] = gm;
+        store_planes(a.d_c_h + (size_t)b * 512 + fld * 4 + r, (size_t)a.B * 512, a.planes, g);
         if (g != 0.0f) atomicAdd(a.d_head + 10 + 128 + 1 + fld * 4 + r, g);   // d c_bias1 (per channel)
       }
     }
@@ -702,7 +674,7 @@ struct PlainHeadDev {
   int clip_vloss;
   __nv_bfloat16* d_a_out;  // [B,16]
   __nv_bfloat16* d_c_h;    // [B,128]
-  __nv_bfloat16 *d_a_out_mid, *d_c_h_mid;   // split: mid planes, else NULL
+  int planes;              // planes of d_a_out / d_c_h (stacked B * 16 / B * 128 elements apart)
   float* d_head;           // [5 + 5 + 128 + 1 + 128]: d a_bias | d logstd | d c_w2 | d c_b2 | d c_bias1
   float* stats;
   float* value_out;
@@ -772,12 +744,8 @@ __global__ void __launch_bounds__(256) plain_head_loss_kernel(PlainHeadDev a) {
       if (a.value_out) a.value_out[b] = value;
       if (a.logp_out) a.logp_out[b] = logp;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        __nv_bfloat16 h, m;
-        split_bf16(k < 5 ? g_logp * dmean[k < 5 ? k : 0] : 0.0f, h, m);
-        a.d_a_out[(size_t)b * 16 + k] = h;
-        if (a.d_a_out_mid) a.d_a_out_mid[(size_t)b * 16 + k] = m;
-      }
+      for (int k = 0; k < 16; ++k)
+        store_planes(a.d_a_out + (size_t)b * 16 + k, (size_t)a.B * 16, a.planes, k < 5 ? g_logp * dmean[k < 5 ? k : 0] : 0.0f);
 #pragma unroll
       for (int d = 0; d < 5; ++d) { dmu_acc[d] += g_logp * dmean[d]; dls_acc[d] += g_logp * dls[d] + g_H; }
       db2 += dv;
@@ -786,10 +754,7 @@ __global__ void __launch_bounds__(256) plain_head_loss_kernel(PlainHeadDev a) {
     for (int f = 0; f < 4; ++f) {
       const int c = lane + 32 * f;
       const float g = h[f] > 0.0f ? dv * a.c_w2[c] : 0.0f;
-      __nv_bfloat16 gh, gm;
-      split_bf16(g, gh, gm);
-      a.d_c_h[(size_t)b * 128 + c] = gh;
-      if (a.d_c_h_mid) a.d_c_h_mid[(size_t)b * 128 + c] = gm;
+      store_planes(a.d_c_h + (size_t)b * 128 + c, (size_t)a.B * 128, a.planes, g);
       dw2[f] += dv * h[f];
       db1[f] += g;
     }
@@ -884,7 +849,7 @@ extern "C" int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const voi
     if (split_k < 1) split_k = 1;
   }
   dim3 grid((unsigned)(mt * nt), 3, (unsigned)split_k);
-  wgrad3x3_kernel<<<grid, 256, WG_SMEM, (cudaStream_t)stream>>>(tmA, tmB, Cout, Cin, (long long)Q, base_off, Wb, nt, dwmat, P == 2 ? 3 : 1);
+  wgrad3x3_kernel<<<grid, 256, WG_SMEM, (cudaStream_t)stream>>>(tmA, tmB, Cout, Cin, (long long)Q, base_off, Wb, nt, dwmat, tc_terms(P));
   AUR_LAUNCH_OK("wgrad3x3_kernel");
   return 0;
 }
@@ -897,12 +862,9 @@ extern "C" int aur_unpool_relu_bwd_colsum(int32_t B, int32_t Hp, int32_t Wp, int
     set_error("aur_unpool_relu_bwd_colsum: needs C / 8 dividing 256, C <= 1024 and group >= 1"); return AUR_ERR_ARG;
   }
   const long long total = (long long)B * Hp * Wp * (C / 8);
-  const bool split = tc_planes() == 2;
-  const __nv_bfloat16* dpool_mid = split ? (const __nv_bfloat16*)dpool + (size_t)B * Hp * Wp * C : nullptr;
-  __nv_bfloat16* dy_mid = split ? (__nv_bfloat16*)dy + (size_t)B * dHb * dWb * C : nullptr;
   unpool_relu_bwd_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
-      B, Hp, Wp, C, (const __nv_bfloat16*)dpool, dpool_mid, (const __nv_bfloat16*)act, aHb, aWb, aoff, arg, (__nv_bfloat16*)dy,
-      dy_mid, dHb, dWb, doff, group, colsum_out);
+      B, Hp, Wp, C, (const __nv_bfloat16*)dpool, (const __nv_bfloat16*)act, aHb, aWb, aoff, arg, (__nv_bfloat16*)dy, dHb, dWb, doff,
+      group, colsum_out, tc_planes(), (size_t)B * Hp * Wp * C, (size_t)B * dHb * dWb * C);
   AUR_LAUNCH_OK("unpool_relu_bwd_kernel");
   return 0;
 }
@@ -950,9 +912,11 @@ extern "C" int aur_plain_conv0_wgrad(const float* obs, const float* state, const
   AUR_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(float) * (64 * 18 + 64), s));
   int rc = aur::tc::launch_conv0_wgrad_tc(obs, state, da1, a1, arg, B, scratch, scratch + 64 * 18, s, true);
   if (rc) return rc;
-  if (tc_planes() == 2) {       // mid plane of the gradient against the hi part of the input views (mid x mid is dropped)
-    rc = aur::tc::launch_conv0_wgrad_tc(obs, state, (const __nv_bfloat16*)da1 + (size_t)B * 64 * 64 * 64, a1, arg, B, scratch,
-                                         scratch + 64 * 18, s, true, 1);
+  // further planes of the gradient stack: mid against both parts of the input views (2 planes: hi part only, mid x mid is
+  // dropped there), lo against the hi part
+  for (int pl = 1; pl < tc_planes(); ++pl) {
+    rc = aur::tc::launch_conv0_wgrad_tc(obs, state, (const __nv_bfloat16*)da1 + (size_t)pl * B * 64 * 64 * 64, a1, arg, B, scratch,
+                                         scratch + 64 * 18, s, true, (tc_planes() == 3 && pl == 1) ? 2 : 1);
     if (rc) return rc;
   }
   AUR_CUDA_OK(cudaMemcpyAsync(dweight, scratch, sizeof(float) * 16 * 18, cudaMemcpyDeviceToDevice, s));
@@ -972,15 +936,14 @@ extern "C" int aur_equiv_conv0_wgrad(const float* obs, const float* state, const
   if (simt < 0) { const char* e = getenv("AUR_CONV0_WGRAD"); simt = (e && e[0] == 's') ? 1 : 0; }
   if (simt) {
     conv0_wgrad_kernel<<<148 * 8, 256, 0, s>>>(obs, state, (const __nv_bfloat16*)da1,
-                                              tc_planes() == 2 ? (const __nv_bfloat16*)da1 + (size_t)B * 64 * 64 * 64 : nullptr,
-                                              (const __nv_bfloat16*)a1, arg, B, scratch, scratch + 64 * 18);
+                                              tc_planes(), (const __nv_bfloat16*)a1, arg, B, scratch, scratch + 64 * 18);
     AUR_LAUNCH_OK("conv0_wgrad_kernel");
   } else {
     int rc = aur::tc::launch_conv0_wgrad_tc(obs, state, da1, a1, arg, B, scratch, scratch + 64 * 18, s);
     if (rc) return rc;
-    if (tc_planes() == 2) {
-      rc = aur::tc::launch_conv0_wgrad_tc(obs, state, (const __nv_bfloat16*)da1 + (size_t)B * 64 * 64 * 64, a1, arg, B, scratch,
-                                           scratch + 64 * 18, s, false, 1);
+    for (int pl = 1; pl < tc_planes(); ++pl) {
+      rc = aur::tc::launch_conv0_wgrad_tc(obs, state, (const __nv_bfloat16*)da1 + (size_t)pl * B * 64 * 64 * 64, a1, arg, B, scratch,
+                                           scratch + 64 * 18, s, false, (tc_planes() == 3 && pl == 1) ? 2 : 1);
       if (rc) return rc;
     }
   }
@@ -991,16 +954,14 @@ extern "C" int aur_equiv_conv0_wgrad(const float* obs, const float* state, const
 
 extern "C" int aur_bias_relu_bf16(int64_t rows, int32_t C, const float* in, const float* bias, void* out, void* stream) {
   if (rows <= 0 || C <= 0 || !in || !bias || !out) { set_error("aur_bias_relu_bf16: bad arguments"); return AUR_ERR_ARG; }
-  __nv_bfloat16* om = tc_planes() == 2 ? (__nv_bfloat16*)out + rows * C : nullptr;
-  bias_relu_kernel<<<grid_for(rows * C), 256, 0, (cudaStream_t)stream>>>(rows * C, C, in, bias, (__nv_bfloat16*)out, om);
+  bias_relu_kernel<<<grid_for(rows * C), 256, 0, (cudaStream_t)stream>>>(rows * C, C, in, bias, (__nv_bfloat16*)out, tc_planes());
   AUR_LAUNCH_OK("bias_relu_kernel");
   return 0;
 }
 extern "C" int aur_relu_mask_bf16(int64_t n, const float* g, const void* ref, void* out, void* stream) {
   if (n <= 0 || !g || !out) { set_error("aur_relu_mask_bf16: bad arguments"); return AUR_ERR_ARG; }
-  __nv_bfloat16* om = tc_planes() == 2 ? (__nv_bfloat16*)out + n : nullptr;
-  if (ref) relu_mask_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, g, (const __nv_bfloat16*)ref, (__nv_bfloat16*)out, om);
-  else f32_to_bf16_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, g, (__nv_bfloat16*)out, om);
+  if (ref) relu_mask_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, g, (const __nv_bfloat16*)ref, (__nv_bfloat16*)out, tc_planes());
+  else f32_to_bf16_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, g, (__nv_bfloat16*)out, tc_planes());
   AUR_LAUNCH_OK("relu_mask_kernel");
   return 0;
 }
@@ -1016,8 +977,7 @@ extern "C" int aur_equiv_head_loss(const aur_equiv_head_args* h, void* stream) {
   d.clip = h->clip_coeff; d.clip_lo = (float)(1.0 - (double)h->clip_coeff); d.clip_hi = (float)(1.0 + (double)h->clip_coeff);
   d.ent_c = h->entropy_coeff; d.vf_c = h->value_coeff; d.inv_m = (float)(1.0 / (double)h->m_total); d.clip_vloss = h->clip_vloss;
   d.d_a_out = (__nv_bfloat16*)h->d_a_out; d.d_c_h = (__nv_bfloat16*)h->d_c_h; d.d_head = h->d_head; d.stats = h->stats;
-  d.d_a_out_mid = tc_planes() == 2 ? d.d_a_out + (size_t)h->B * 16 : nullptr;
-  d.d_c_h_mid = tc_planes() == 2 ? d.d_c_h + (size_t)h->B * 512 : nullptr;
+  d.planes = tc_planes();
   d.value_out = h->value_out; d.logp_out = h->logp_out;
   const unsigned grid = grid_for((long long)h->B * 32, 256, 148 * 4);
   head_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d);
@@ -1082,8 +1042,7 @@ extern "C" int aur_plain_head_loss(const aur_plain_head_args* h, void* stream) {
   d.clip = h->clip_coeff; d.clip_lo = (float)(1.0 - (double)h->clip_coeff); d.clip_hi = (float)(1.0 + (double)h->clip_coeff);
   d.ent_c = h->entropy_coeff; d.vf_c = h->value_coeff; d.inv_m = (float)(1.0 / (double)h->m_total); d.clip_vloss = h->clip_vloss;
   d.d_a_out = (__nv_bfloat16*)h->d_a_out; d.d_c_h = (__nv_bfloat16*)h->d_c_h; d.d_head = h->d_head; d.stats = h->stats;
-  d.d_a_out_mid = tc_planes() == 2 ? d.d_a_out + (size_t)h->B * 16 : nullptr;
-  d.d_c_h_mid = tc_planes() == 2 ? d.d_c_h + (size_t)h->B * 128 : nullptr;
+  d.planes = tc_planes();
   d.value_out = h->value_out; d.logp_out = h->logp_out;
   plain_head_loss_kernel<<<grid_for((long long)h->B * 32, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(d);
   AUR_LAUNCH_OK("plain_head_loss_kernel");

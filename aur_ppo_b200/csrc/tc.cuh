@@ -190,34 +190,52 @@ int make_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const vo
 // ---- operand precision of the row-X tensor-core entry points (aur_tc_set_precision) -------------------------------
 // 1 plane : bf16 operands (fast mode, below the reference's fp32 arithmetic).
 // 2 planes: every bf16 tensor is a stack [2][...] of a HI plane bf16(v) and a MID plane bf16(v - hi), |v - hi - mid| <=
-//           2^-17 |v|; contractions issue hi*hi + hi*mid + mid*hi with fp32 accumulation in TMEM (the mid*mid term,
-//           <= 2^-16 of the product, is dropped): fp32-class results on the bf16 tensor pipe at 3x the MMA work.
-//           The planes are walked as extra K steps of the same pipelines: plane index = outermost TMA coordinate.
+//           2^-18 |v|; contractions issue hi*hi + hi*mid + mid*hi with fp32 accumulation in TMEM (3x the MMA work):
+//           ~3e-5 relative through the seven-layer encoders.
+// 3 planes: a third LO plane bf16(v - hi - mid) (3 x 8 = 24 mantissa bits: all of fp32) and six products hi*hi + hi*mid +
+//           mid*hi + mid*mid + hi*lo + lo*hi (everything above 2^-24 of the product): fp32-equivalent, 6x the MMA work.
+// The planes are walked as extra K steps of the same pipelines: plane index = outermost TMA coordinate.
 int tc_planes();
-// K-step term -> (plane of the first operand, plane of the second operand): (hi,hi), (hi,mid), (mid,hi)
-__host__ __device__ __forceinline__ int term_plane_a(int term) { return term == 2 ? 1 : 0; }
-__host__ __device__ __forceinline__ int term_plane_b(int term) { return term == 1 ? 1 : 0; }
+__host__ __device__ __forceinline__ int tc_terms(int planes) { return planes == 1 ? 1 : (planes == 2 ? 3 : 6); }
+// K-step term -> (plane of the first operand, plane of the second): 0 (0,0)  1 (0,1)  2 (1,0)  3 (1,1)  4 (0,2)  5 (2,0)
+__host__ __device__ __forceinline__ int term_plane_a(int t) { return (t == 2 || t == 3) ? 1 : (t == 5 ? 2 : 0); }
+__host__ __device__ __forceinline__ int term_plane_b(int t) { return (t == 1 || t == 3) ? 1 : (t == 4 ? 2 : 0); }
 #ifdef __CUDACC__
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& mid) {
   hi = __float2bfloat16_rn(v);
   mid = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
-// 8 consecutive values -> one 16-byte store of the hi plane and, if mid != NULL, one of the mid plane
-__device__ __forceinline__ void store8_planes(__nv_bfloat16* hi, __nv_bfloat16* mid, const float* v) {
-  uint4 ph, pm;
-  unsigned int* h = reinterpret_cast<unsigned int*>(&ph);
-  unsigned int* m = reinterpret_cast<unsigned int*>(&pm);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    h[j] = *reinterpret_cast<const unsigned int*>(&t);
-    if (mid) {
-      const __nv_bfloat162 r = __floats2bfloat162_rn(v[2 * j] - __low2float(t), v[2 * j + 1] - __high2float(t));
-      m[j] = *reinterpret_cast<const unsigned int*>(&r);
-    }
+// v -> plane p of nplanes planes at dst[p * plane_stride] (successive bf16 roundings of the remainder)
+__device__ __forceinline__ void store_planes(__nv_bfloat16* dst, size_t plane_stride, int nplanes, float v) {
+  for (int p = 0; p < nplanes; ++p) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    dst[(size_t)p * plane_stride] = h;
+    v -= __bfloat162float(h);
   }
-  *reinterpret_cast<uint4*>(hi) = ph;
-  if (mid) *reinterpret_cast<uint4*>(mid) = pm;
+}
+// 8 consecutive values -> one 16-byte store per plane
+__device__ __forceinline__ void store8_planes(__nv_bfloat16* dst, size_t plane_stride, int nplanes, const float* v) {
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = v[i];
+  for (int p = 0; p < nplanes; ++p) {
+    uint4 pk;
+    unsigned int* w = reinterpret_cast<unsigned int*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 t = __floats2bfloat162_rn(r[2 * j], r[2 * j + 1]);
+      w[j] = *reinterpret_cast<const unsigned int*>(&t);
+      r[2 * j] -= __low2float(t);
+      r[2 * j + 1] -= __high2float(t);
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)p * plane_stride) = pk;
+  }
+}
+// sum of the planes of one element
+__device__ __forceinline__ float load_planes(const __nv_bfloat16* src, size_t plane_stride, int nplanes) {
+  float v = 0.0f;
+  for (int p = nplanes - 1; p >= 0; --p) v += __bfloat162float(src[(size_t)p * plane_stride]);
+  return v;
 }
 #endif
 

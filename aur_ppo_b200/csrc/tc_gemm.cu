@@ -122,7 +122,7 @@ tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }  // namespace aur
 
 extern "C" int aur_tc_set_precision(int planes) {
-  if (planes != 1 && planes != 2) { aur::set_error("aur_tc_set_precision: planes must be 1 (bf16) or 2 (bf16 hi + mid split)"); return AUR_ERR_ARG; }
+  if (planes < 1 || planes > 3) { aur::set_error("aur_tc_set_precision: planes must be 1 (bf16), 2 (hi + mid) or 3 (hi + mid + lo)"); return AUR_ERR_ARG; }
   const int prev = aur::tc::g_tc_planes;
   aur::tc::g_tc_planes = planes;
   return prev;
@@ -148,7 +148,7 @@ extern "C" int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, 
     attr.done();
   }
   dim3 grid((unsigned)((M + GEMM_BM - 1) / GEMM_BM), (unsigned)((N + GEMM_BN - 1) / GEMM_BN));
-  tc_gemm_bf16_kernel<<<grid, 256, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, C, (int)M, (int)N, (int)K, (int)N, P == 2 ? 3 : 1);
+  tc_gemm_bf16_kernel<<<grid, 256, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, C, (int)M, (int)N, (int)K, (int)N, tc_terms(P));
   AUR_LAUNCH_OK("tc_gemm_bf16_kernel");
   return 0;
 }

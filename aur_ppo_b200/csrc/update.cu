@@ -568,6 +568,74 @@ __global__ void __launch_bounds__(256) adv_moments_kernel(long long m, const int
   }
 }
 
+// The same for all n_mb minibatches of an iteration at once: grid = (CTAs per minibatch, n_mb).  The last CTA of a minibatch
+// finalises it (fixed order) and, data-parallel, pushes its three moments to every rank; the last minibatch to finish
+// releases the flags - ONE rendezvous per iteration instead of one per minibatch.
+__global__ void __launch_bounds__(256) adv_moments_multi_kernel(long long m, const int32_t* __restrict__ idx, long long idx_stride,
+                                                              const float* __restrict__ adv, double* __restrict__ partial,
+                                                              unsigned int* __restrict__ tickets, double* __restrict__ out, DpDev dp) {
+  __shared__ double sh[2][8];
+  __shared__ bool last, last_of_all;
+  const int y = blockIdx.y;
+  const int32_t* my_idx = idx ? idx + (long long)y * idx_stride : nullptr;
+  const long long row0 = (long long)y * idx_stride;
+  double s = 0.0, ss = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < m; i += 4 * stride) {
+    float v4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long row = my_idx ? (long long)__ldg(my_idx + i + k * stride) : row0 + i + k * stride;
+      v4[k] = __ldg(adv + row);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const double v = (double)v4[k]; s += v; ss += v * v; }
+  }
+  for (; i < m; i += stride) {
+    const long long row = my_idx ? (long long)my_idx[i] : row0 + i;
+    const double v = (double)__ldg(adv + row);
+    s += v; ss += v * v;
+  }
+  s = warp_sum(s); ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  double* part = partial + (size_t)y * gridDim.x * 2;
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
+    part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
+    __threadfence();
+    last = atomicAdd(tickets + 1 + y, 1u) == gridDim.x - 1;
+    last_of_all = false;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (unsigned c = 0; c < gridDim.x; ++c) { a += __ldcg(part + 2 * c); b += __ldcg(part + 2 * c + 1); }
+    out[3 * y] = a; out[3 * y + 1] = b; out[3 * y + 2] = (double)m;
+    tickets[1 + y] = 0u;
+    if (dp.world > 1) {
+      for (int r = 0; r < dp.world; ++r) {
+        double* rm = reinterpret_cast<double*>(dp.peer[r] + DP_OFF_MOMX) + ((size_t)(dp.mom_seq & 1u) * DP_MAX + dp.rank) * DP_MAXMB * 4 +
+                     (size_t)y * 4;
+        rm[0] = a; rm[1] = b; rm[2] = (double)m;
+      }
+      __threadfence_system();
+      last_of_all = atomicAdd(tickets, 1u) == gridDim.y - 1;
+    }
+  }
+  __syncthreads();
+  if (last_of_all) {                                     // every minibatch of this rank has been pushed: release the flags
+    __threadfence_system();
+    if ((int)threadIdx.x < dp.world)
+      st_release_sys(reinterpret_cast<uint32_t*>(dp.peer[threadIdx.x] + DP_OFF_FLAG_MOMX) + dp.rank, dp.mom_seq);
+    if (threadIdx.x == 0) tickets[0] = 0u;
+  }
+}
+
 // clip_grad_norm_ (all parameters, torch semantics) + Adam, one CTA (P ~ 9e3).
 __global__ void __launch_bounds__(1024) adam_kernel(int64_t P, float* __restrict__ params, float* __restrict__ g_in,
                                                    float* __restrict__ m1, float* __restrict__ m2, float lr_over_bc1,
@@ -680,6 +748,7 @@ extern "C" int64_t aur_ppo_update_workspace_bytes(const aur_policy_desc* desc) {
 namespace aur {
 static int make_dp(const aur_dp_ctx* c, uint32_t seq, DpDev& d, const char* who) {
   d.world = 1; d.rank = 0; d.seq = seq;
+  d.mom_seq = 0; d.mom_index = 0;
   for (int r = 0; r < DP_MAX; ++r) d.peer[r] = nullptr;
   if (!c || c->world <= 1) return 0;
   if (c->world > DP_MAX || c->rank < 0 || c->rank >= c->world || seq == 0) {
@@ -716,6 +785,30 @@ extern "C" int aur_ppo_adv_moments_dp(int64_t m, const int32_t* idx, int64_t idx
   return 0;
 }
 
+extern "C" int aur_ppo_adv_moments_multi(int32_t n_mb, int64_t m, const int32_t* idx, int64_t idx_stride, const float* advantages,
+                                         double* moments_out, float* workspace, const aur_dp_ctx* dp, uint32_t mom_seq, void* stream) {
+  using namespace aur;
+  if (n_mb <= 0 || n_mb > DP_MAXMB || m <= 0 || idx_stride < m || !advantages || !moments_out || !workspace) {
+    set_error("aur_ppo_adv_moments_multi: bad arguments (1 <= n_mb <= %d, idx_stride >= m)", DP_MAXMB); return AUR_ERR_ARG;
+  }
+  DpDev dpd;
+  { int rc = make_dp(dp, mom_seq ? mom_seq : 1u, dpd, "aur_ppo_adv_moments_multi"); if (rc) return rc; }
+  if (dpd.world > 1 && mom_seq == 0) { set_error("aur_ppo_adv_moments_multi: data-parallel needs mom_seq >= 1"); return AUR_ERR_ARG; }
+  dpd.mom_seq = mom_seq;
+  // all n_mb x cpm CTAs share the moment-partial region of the workspace (2 x MOM_CTAS doubles)
+  int cpm = MOM_CTAS / n_mb;
+  if (cpm < 1) cpm = 1;
+  const long long need = (m + 255) / 256;
+  if (cpm > need) cpm = (int)need;
+  double* partial = reinterpret_cast<double*>(workspace + ws_partials_floats());
+  unsigned int* tickets = stream_tickets((cudaStream_t)stream);
+  if (!tickets) return AUR_ERR_ARG;
+  adv_moments_multi_kernel<<<dim3((unsigned)cpm, (unsigned)n_mb), 256, 0, (cudaStream_t)stream>>>(
+      (long long)m, idx, (long long)idx_stride, advantages, partial, tickets + 16, moments_out, dpd);
+  AUR_LAUNCH_OK("adv_moments_multi_kernel");
+  return 0;
+}
+
 extern "C" int aur_ppo_update_set_impl(int impl) {
   if (impl < 0 || impl > 3) { aur::set_error("aur_ppo_update_set_impl: impl must be 0 (simt), 1 (tensor core), 2 (tensor core, 4 threads per sample) or 3 (shape-generic)"); return AUR_ERR_ARG; }
   aur::g_update_impl = impl;
@@ -744,6 +837,10 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
   d.ent_c = u.entropy_coeff; d.vf_c = u.value_coeff; d.inv_m = (float)(1.0 / (double)u.m_total);
   d.moments = u.adv_moments; d.partials = u.workspace;
   { int rc2 = make_dp(u.dp, u.dp_seq, d.dp, "aur_ppo_update_grad"); if (rc2) return rc2; }
+  if (u.mom_seq) {
+    if (u.mom_index < 0 || u.mom_index >= DP_MAXMB) { set_error("aur_ppo_update_grad: mom_index %d outside 0..%d", u.mom_index, DP_MAXMB - 1); return AUR_ERR_ARG; }
+    d.dp.mom_seq = u.mom_seq; d.dp.mom_index = u.mom_index;
+  }
   if ((u.rec_actor != nullptr) != (u.rec_critic != nullptr)) { set_error("aur_ppo_update_grad: give both record arrays or neither"); return AUR_ERR_ARG; }
   if (u.rec_actor && u.policy.continuous && u.policy.act_dim > 2) { set_error("aur_ppo_update_grad: records hold at most 2 action dims"); return AUR_ERR_ARG; }
   d.rec_actor = reinterpret_cast<const float4*>(u.rec_actor); d.rec_critic = reinterpret_cast<const float4*>(u.rec_critic);

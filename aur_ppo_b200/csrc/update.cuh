@@ -24,14 +24,20 @@ constexpr int DP_MAX = 16;
 constexpr int DP_OFF_FLAG_MOM = 0;         // u32 [DP_MAX]
 constexpr int DP_OFF_FLAG_GRAD = 64;       // u32 [DP_MAX]
 constexpr int DP_OFF_STATUS = 128;         // u32: 1 = a wait timed out
+constexpr int DP_OFF_FLAG_MOMX = 192;      // u32 [DP_MAX]: iteration counter of the moments exchanged ahead (aur_ppo_adv_moments_multi)
 constexpr int DP_OFF_MOM = 256;            // f64 [2][DP_MAX][4]
-constexpr int DP_OFF_GRAD = DP_OFF_MOM + 2 * DP_MAX * 4 * 8;   // f32 [2][DP_MAX][dp_grad_stride]
+constexpr int DP_MAXMB = AUR_DP_MAX_MINIBATCHES;
+constexpr int DP_OFF_MOMX = DP_OFF_MOM + 2 * DP_MAX * 4 * 8;             // f64 [2][DP_MAX][DP_MAXMB][4]: moments of a whole iteration
+constexpr int DP_OFF_GRAD = DP_OFF_MOMX + 2 * DP_MAX * DP_MAXMB * 4 * 8; // f32 [2][DP_MAX][dp_grad_stride]
 __host__ __device__ inline int dp_grad_stride(int64_t P) { return (int)((P + AUR_NUM_STATS + 63) / 64 * 64); }
 __host__ __device__ inline int64_t dp_area_bytes(int64_t P) { return DP_OFF_GRAD + (int64_t)2 * DP_MAX * dp_grad_stride(P) * 4; }
 struct DpDev {
   int world, rank;                         // world <= 1: not data-parallel
   uint32_t seq;                            // minibatch sequence number (same on every rank), starts at 1
   unsigned char* peer[DP_MAX];             // exchange area of every rank as mapped here; peer[rank] is local
+  // advantage moments exchanged ahead for the whole iteration (aur_ppo_adv_moments_multi): mom_seq != 0 selects them
+  uint32_t mom_seq;
+  int mom_index;
 };
 
 #ifdef __CUDACC__
@@ -78,9 +84,20 @@ struct UpdDev {
 __device__ __forceinline__ void load_adv_moments(const UpdDev& a, double& s, double& ss, double& n) {
   if (a.dp.world > 1) {
     unsigned char* me = a.dp.peer[a.dp.rank];
+    s = 0.0; ss = 0.0; n = 0.0;
+    if (a.dp.mom_seq) {                      // exchanged once for the whole iteration: normally no wait at all here
+      const uint32_t* flags = reinterpret_cast<const uint32_t*>(me + DP_OFF_FLAG_MOMX);
+      const double* rm = reinterpret_cast<const double*>(me + DP_OFF_MOMX) + (size_t)(a.dp.mom_seq & 1u) * DP_MAX * DP_MAXMB * 4 +
+                         (size_t)a.dp.mom_index * 4;
+      for (int r = 0; r < a.dp.world; ++r) {
+        dp_wait_flag(flags + r, a.dp.mom_seq, me);
+        const double* q = rm + (size_t)r * DP_MAXMB * 4;
+        s += __ldcg(q); ss += __ldcg(q + 1); n += __ldcg(q + 2);
+      }
+      return;
+    }
     const uint32_t* flags = reinterpret_cast<const uint32_t*>(me + DP_OFF_FLAG_MOM);
     const double* rm = reinterpret_cast<const double*>(me + DP_OFF_MOM) + (a.dp.seq & 1u) * DP_MAX * 4;
-    s = 0.0; ss = 0.0; n = 0.0;
     for (int r = 0; r < a.dp.world; ++r) {
       dp_wait_flag(flags + r, a.dp.seq, me);
       s += __ldcg(rm + r * 4); ss += __ldcg(rm + r * 4 + 1); n += __ldcg(rm + r * 4 + 2);

@@ -8,12 +8,15 @@ Every convolution / dense contraction runs on tcgen05 tensor cores through the C
 (aur_conv3x3_bf16, aur_wgrad3x3_bf16, aur_tc_gemm_bf16); activations are bf16 NHWC with explicit
 halos, accumulation is fp32, parameters / gradients / Adam moments are fp32.
 
-Two operand precisions (aur_tc_set_precision):
-  split=True   every bf16 tensor is a stack of a hi and a mid plane (v = hi + mid to 2^-17) and every contraction
-               issues hi*hi + hi*mid + mid*hi: fp32-class arithmetic like the reference's (equiv.py / robot_ppo.py
-               compute in fp32), gradients within north_star's 1e-4 of an fp32 / fp64 autograd on identical routing;
-  split=False  single-plane bf16 operands: the fast mode, below the reference's precision (1e-2 class).
-Internally every bf16 buffer carries a leading plane dimension P (1 or 2).  The free parameters are
+Operand precisions (aur_tc_set_precision), `precision=`:
+  "split"  2 planes: every bf16 tensor is a stack hi / mid (v = hi + mid to 2^-18) and every contraction issues hi*hi +
+           hi*mid + mid*hi with fp32 accumulation: the REFERENCE-PRECISION mode (equiv.py / robot_ppo.py compute in fp32, in
+           practice TF32 through cuDNN's default): forward within ~3e-5, gradients within north_star's 1e-4 of float64
+           autograd on identical routing (tests/test_equiv_split_gpu.py); 3x the MMA work;
+  "split3" 3 planes (hi / mid / lo, six products): measured NO more accurate - the tensor core's truncating fp32 accumulator,
+           not operand rounding, sets the error, and six products double the accumulation steps; kept, tested, unused;
+  "bf16"   single-plane bf16 operands: the fast mode, below the reference's precision (1e-2 class).
+Internally every bf16 buffer carries a leading plane dimension P (1, 2 or 3).  The free parameters are
 the p4 group-convolution filters psi (see oracle/equiv_ref.py for the restated architecture and why
 weights are not interchangeable with e2cnn checkpoints).  No CPU path.
 
@@ -32,6 +35,7 @@ from . import _lib
 from .kernels import _ptr, _stream, adv_moments, conv3x3_bf16, equiv_conv0, equiv_expand_regular, tc_gemm_bf16, tc_precision
 
 ENC_FIELDS = [16, 32, 64, 128, 256, 128, 128]
+PRECISIONS = {"bf16": 1, "split": 2, "split3": 3}        # operand planes (aur_tc_set_precision)
 N_ACT = 5
 
 
@@ -82,9 +86,14 @@ class EquivActorCritic:
     D_HEAD = 651
 
     def __init__(self, params: Dict[str, torch.Tensor], batch: int, lr: float = 3e-4, eps: float = 1e-5,
-                 betas=(0.9, 0.999), split: bool = False):
-        self.split = bool(split)
-        self.P = 2 if self.split else 1
+                 betas=(0.9, 0.999), split: bool = False, precision: Optional[str] = None):
+        if precision is None:
+            precision = "split" if split else "bf16"
+        if precision not in PRECISIONS:
+            raise _lib.AurError(f"precision must be one of {sorted(PRECISIONS)}")
+        self.precision = precision
+        self.P = PRECISIONS[precision]
+        self.split = self.P > 1
         if batch % 8:
             raise _lib.AurError("batch must be a multiple of 8 (16-byte rows for the TMA weight-gradient maps)")
         _lib.lib()
@@ -117,10 +126,8 @@ class EquivActorCritic:
     # ------------------------------------------------------------------- planes
     def _bf(self, x: torch.Tensor) -> torch.Tensor:
         """fp32 -> [P, ...] bf16 planes (tiny host-side tensors only: head filters)."""
-        hi = x.bfloat16()
-        if self.P == 1:
-            return hi.unsqueeze(0).contiguous()
-        return torch.stack([hi, (x - hi.float()).bfloat16()]).contiguous()
+        from .kernels import split_planes
+        return split_planes(x, self.P)
 
     def _empty(self, *shape) -> torch.Tensor:
         return torch.empty(self.P, *shape, dtype=torch.bfloat16, device=self.dev)

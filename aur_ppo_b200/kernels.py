@@ -210,11 +210,38 @@ class Updater:
         self.exchange = exchange
         if exchange is not None and allreduce is not None:
             raise _lib.AurError("give either a peer exchange or an allreduce callable, not both")
+        self.moments_all = None          # [n_mb, 3] fp64: moments of every minibatch of the iteration (prepare_moments)
+        self._mom_seq = 0
+
+    MAX_MINIBATCHES = 512                # AUR_DP_MAX_MINIBATCHES
+
+    def prepare_moments(self, b_advantages: torch.Tensor, idx_all: torch.Tensor) -> None:
+        """Advantage moments of ALL the minibatches of an iteration in one launch (and, data-parallel, ONE exchange):
+        idx_all [n_mb, m] int32 = the index lists of every epoch's minibatches.  Afterwards `grad(..., moments_index=j)`
+        normalises minibatch j with entry j instead of computing (and exchanging) its moments itself."""
+        import ctypes
+        if idx_all.dtype != torch.int32 or idx_all.dim() != 2 or not idx_all.is_cuda or not idx_all.is_contiguous():
+            raise _lib.AurError("idx_all must be a contiguous CUDA int32 tensor [n_mb, m]")
+        n_mb, m = idx_all.shape
+        if n_mb > self.MAX_MINIBATCHES:
+            raise _lib.AurError(f"at most {self.MAX_MINIBATCHES} minibatches per prepare_moments call")
+        if self.moments_all is None or self.moments_all.shape[0] != n_mb:
+            self.moments_all = torch.zeros(n_mb, 3, dtype=torch.float64, device=self.params.device)
+        self._mom_seq += 1
+        with torch.cuda.device(self.params.device):
+            dp = ctypes.addressof(self.exchange.ctx) if self.exchange is not None else None
+            rc = _lib.lib().aur_ppo_adv_moments_multi(n_mb, m, idx_all.data_ptr(), m, _f32c(b_advantages, "advantages").data_ptr(),
+                                                      self.moments_all.data_ptr(), self.workspace.data_ptr(), dp, self._mom_seq, _stream())
+            _lib.check(rc, "aur_ppo_adv_moments_multi")
+            if self.allreduce is not None:
+                self.allreduce(self.moments_all)
 
     def grad(self, b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values, idx: Optional[torch.Tensor],
              m_total: Optional[int] = None, idx_offset: int = 0, m_local: Optional[int] = None, clip_coeff=0.2,
-             entropy_coeff=0.01, value_coeff=0.5, norm_adv=True, clip_vloss=True, records=None) -> torch.Tensor:
-        """Phases 1-2 (moments, gather+fwd+loss+bwd+reduce) -> packed [grads | stat sums] on device."""
+             entropy_coeff=0.01, value_coeff=0.5, norm_adv=True, clip_vloss=True, records=None,
+             moments_index: Optional[int] = None) -> torch.Tensor:
+        """Phases 1-2 (moments, gather+fwd+loss+bwd+reduce) -> packed [grads | stat sums] on device.
+        moments_index: use entry j of the last prepare_moments() call instead of computing this minibatch's moments."""
         import ctypes
         L = _lib.lib()
         if idx is not None:
@@ -231,7 +258,10 @@ class Updater:
             st = _stream()
             dp, seq = (ctypes.addressof(self.exchange.ctx), self.exchange.next_seq()) if self.exchange is not None else (None, 0)
             self._seq = seq
-            if norm_adv:
+            ahead = norm_adv and moments_index is not None
+            if ahead and (self.moments_all is None or not 0 <= moments_index < self.moments_all.shape[0]):
+                raise _lib.AurError("moments_index needs a matching prepare_moments() call")
+            if norm_adv and not ahead:
                 _lib.check(L.aur_ppo_adv_moments_dp(m_local, _ptr(idx), idx_offset, b_advantages.data_ptr(),
                                                     self.moments.data_ptr(), self.workspace.data_ptr(), dp, seq, st),
                            "aur_ppo_adv_moments")
@@ -245,6 +275,10 @@ class Updater:
             a.params = self.params.data_ptr()
             a.clip_coeff, a.entropy_coeff, a.value_coeff = float(clip_coeff), float(entropy_coeff), float(value_coeff)
             a.adv_moments = self.moments.data_ptr() if norm_adv else None
+            if ahead:
+                a.adv_moments = self.moments_all.data_ptr() + 24 * moments_index
+                if dp is not None:
+                    a.mom_seq, a.mom_index = self._mom_seq, moments_index
             a.workspace, a.grads_out = self.workspace.data_ptr(), self.grads.data_ptr()
             a.dp, a.dp_seq = dp, seq
             if records is not None:
@@ -280,8 +314,8 @@ class Updater:
 
 # ----------------------------------------------------------------------- tensor cores
 class tc_precision:
-    """`with tc_precision(2):` runs the row-X entry points on split operands (aur_tc_set_precision): every bf16 tensor is
-    then a stack [2, ...] of a hi and a mid plane.  Restores the previous mode on exit."""
+    """`with tc_precision(P):` runs the row-X entry points on P operand planes (aur_tc_set_precision): P = 2 / 3 makes
+    every bf16 tensor a stack [P, ...] of hi / mid (/ lo) planes.  Restores the previous mode on exit."""
 
     def __init__(self, planes: int):
         self.planes, self.prev = int(planes), None
@@ -301,10 +335,15 @@ def tc_planes() -> int:
     return int(_lib.lib().aur_tc_get_precision())
 
 
-def split_planes(x: torch.Tensor) -> torch.Tensor:
-    """fp32 tensor -> [2, ...] bf16 (hi = bf16(x), mid = bf16(x - hi)); the layout split-precision entry points take."""
-    hi = x.bfloat16()
-    return torch.stack([hi, (x - hi.float()).bfloat16()]).contiguous()
+def split_planes(x: torch.Tensor, planes: int = 2) -> torch.Tensor:
+    """fp32 tensor -> [planes, ...] bf16 (hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid)): the layout the
+    multi-plane entry points take."""
+    out, r = [], x.float()
+    for _ in range(planes):
+        h = r.bfloat16()
+        out.append(h)
+        r = r - h.float()
+    return torch.stack(out).contiguous()
 
 
 def join_planes(x: torch.Tensor) -> torch.Tensor:
@@ -323,7 +362,7 @@ def _check_planes(t: torch.Tensor, base_dims: int, name: str) -> int:
 
 
 def _planes_shape(P: int, *shape):
-    return (P,) + tuple(shape) if P == 2 else tuple(shape)
+    return (P,) + tuple(shape) if P > 1 else tuple(shape)
 
 
 def tc_gemm_bf16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

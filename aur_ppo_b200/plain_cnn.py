@@ -72,8 +72,8 @@ class PlainActorCritic(EquivActorCritic):
     D_HEAD = 267
 
     def __init__(self, params: Dict[str, torch.Tensor], batch: int, lr: float = 3e-4, eps: float = 1e-5, betas=(0.9, 0.999),
-                 split: bool = False):
-        super().__init__(params, batch, lr, eps, betas, split=split)
+                 split: bool = False, precision: Optional[str] = None):
+        super().__init__(params, batch, lr, eps, betas, split=split, precision=precision)
         dev = self.dev
         # input-channel positions of each layer's real channels inside the padded activation feeding it
         self._in_pos = [None] + [torch.arange(REAL[l - 1], device=dev) for l in range(1, 7)]

@@ -136,7 +136,8 @@ class ppo:
         # minibatch shuffles: one stream per (rank, epoch) so that ranks draw independent permutations
         self.shuffle_seed = int(params.get("shuffle_seed", self.philox_seed))
         self._shuffle_count = self.rank << 40
-        self._b_inds = torch.empty(self.local_batch, dtype=torch.int32, device=self.device)
+        # the permutations of ALL epochs of an iteration (they do not depend on the parameters): [epochs, local_batch]
+        self._b_inds = torch.empty(max(int(self.num_update_epochs), 1), self.local_batch, dtype=torch.int32, device=self.device)
         self._records = None
         self.total_returns: List[float] = []
         self.total_episode_lengths: List[int] = []
@@ -173,13 +174,15 @@ class ppo:
         self._records = kernels.pack_records(b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values,
                                              out=self._records)
 
-    def update_minibatch(self, flat_bufs, mb_inds: torch.Tensor, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """ppo.py:220-269 for one minibatch of local row indices -> device stats tensor (written to stats_out if given)."""
+    def update_minibatch(self, flat_bufs, mb_inds: torch.Tensor, stats_out: Optional[torch.Tensor] = None,
+                         moments_index: Optional[int] = None) -> torch.Tensor:
+        """ppo.py:220-269 for one minibatch of local row indices -> device stats tensor (written to stats_out if given).
+        moments_index: entry of the iteration's pre-computed advantage moments (run_update), else computed here."""
         b_obs, b_logprobs, b_actions, b_advantages, b_returns, b_values = flat_bufs
         self.updater.grad(b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values, mb_inds,
                           m_total=mb_inds.numel() * self.world_size, clip_coeff=self.clip_coeff,
                           entropy_coeff=self.entropy_coeff, value_coeff=self.value_coeff, norm_adv=bool(self.norm_adv),
-                          clip_vloss=bool(self.clip_vloss), records=self._records)
+                          clip_vloss=bool(self.clip_vloss), records=self._records, moments_index=moments_index)
         return self.optimizer.step(max_grad_norm=self.max_grad_norm, stats_out=stats_out)
 
     def run_update(self, update: int, events=None) -> Dict[str, torch.Tensor]:
@@ -198,13 +201,21 @@ class ppo:
         self.pack(flat_bufs)
         n_mb = 0
         stats_rows = self._stats_rows
+        # np.random.shuffle(b_inds) of every epoch (ppo.py:214-215) up front, then the advantage moments of every minibatch in
+        # ONE launch (data-parallel: one exchange per iteration instead of one per minibatch)
         for ep in range(self.num_update_epochs):
-            b_inds = kernels.shuffle_indices(self.local_batch, seed=self.shuffle_seed, stream_id=self._shuffle_count,
-                                             out=self._b_inds)
+            kernels.shuffle_indices(self.local_batch, seed=self.shuffle_seed, stream_id=self._shuffle_count, out=self._b_inds[ep])
             self._shuffle_count += 1
-            for start in range(0, self.local_batch, self.local_minibatch):
+        per_epoch = self.local_batch // self.local_minibatch
+        ahead = (bool(self.norm_adv) and self.local_batch % self.local_minibatch == 0 and
+                 self.num_update_epochs * per_epoch <= kernels.Updater.MAX_MINIBATCHES)
+        if ahead:
+            self.updater.prepare_moments(flat_bufs[3], self._b_inds.view(-1, self.local_minibatch))
+        for ep in range(self.num_update_epochs):
+            b_inds = self._b_inds[ep]
+            for j, start in enumerate(range(0, self.local_batch, self.local_minibatch)):
                 mb = b_inds[start:start + self.local_minibatch]
-                self.update_minibatch(flat_bufs, mb, stats_out=stats_rows[n_mb])
+                self.update_minibatch(flat_bufs, mb, stats_out=stats_rows[n_mb], moments_index=ep * per_epoch + j if ahead else None)
                 n_mb += 1
             if self.target_kl is not None:
                 if stats_rows[n_mb - 1, 4].item() > self.target_kl:

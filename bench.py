@@ -11,7 +11,7 @@ Workloads (sizes per BASELINE.json):
             override (run_ppo.py:44-51): 32 minibatches x 10 epochs, lr 3e-4, entropy 0                  configs[2]
   scale1m   CartPole-v1, 1,048,576 envs IN TOTAL sharded over the GPUs (strong scaling), T = 128,
             plus a GAE sweep T = 128..2048 on 131072 columns per GPU                                      configs[4]
-  equiv     equivariant actor-critic update, minibatch 4096 (--precision split|bf16)                      configs[3]
+  equiv     equivariant actor-critic update, minibatch 4096 (--precision split|split3|bf16)                      configs[3]
 A step = one PPO iteration: T * num_envs env steps (fused rollout), one GAE pass and
 epochs * num_minibatches fused updates.
 """
@@ -487,7 +487,7 @@ def run_equiv(args, plain: bool = False):
     from aur_ppo_b200 import _lib, equiv, plain_cnn
     B = 4096
     torch.cuda.set_device(0)
-    split = args.precision == "split"
+    split = args.precision != "bf16"
     if plain:
         params = plain_cnn.init_params(seed=0)
     else:
@@ -500,7 +500,7 @@ def run_equiv(args, plain: bool = False):
     action = torch.randn(B, 5, generator=g, device="cuda")
     adv, ret, vold = (torch.randn(B, generator=g, device="cuda") for _ in range(3))
     oldlp = torch.full((B,), -7.0, device="cuda")
-    model = plain_cnn.PlainActorCritic(params, B, split=split) if plain else equiv.EquivActorCritic(params, B, split=split)
+    model = (plain_cnn.PlainActorCritic if plain else equiv.EquivActorCritic)(params, B, precision=args.precision)
     for _ in range(args.warmup):
         model.update(state, obs, action, oldlp, adv, ret, vold)
     torch.cuda.synchronize()
@@ -567,14 +567,17 @@ def run_equiv(args, plain: bool = False):
     tf = flops / (ms * 1e-3) / 1e12
     line = {"metric": "update_samples_per_s", "value": B / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": ("bf16x2 split operands (hi + mid planes, 3 products) / fp32 accumulate (tcgen05): fp32-class "
-                      "arithmetic (north_star's 1e-4 gradient bar), fp32 parameters and Adam") if split else
-                     ("bf16 operands / fp32 accumulate (tcgen05), fp32 parameters and Adam: BELOW the reference's fp32 "
-                      "precision (fast mode)"),
+            "dtype": {"split3": "bf16x3 operand planes (hi + mid + lo), six products, fp32 accumulate in TMEM (tcgen05): measured no "
+                                "more accurate than split (accumulator-limited); fp32 parameters and Adam",
+                      "split": "reference precision: bf16x2 operand planes (hi + mid = 16 mantissa bits), three products, fp32 "
+                               "accumulate in TMEM (tcgen05): forward ~3e-5, gradients within 1e-4 of float64 on identical routing; "
+                               "fp32 parameters and Adam.  (The reference's fp32 convolutions run as TF32 under cuDNN's default.)",
+                      "bf16": "bf16 operands / fp32 accumulate (tcgen05), fp32 parameters and Adam: BELOW the reference's fp32 "
+                              "precision (fast mode)"}[args.precision],
             "data": "synthetic", "precision": args.precision,
             "config": dict(equiv_config(plain), precision=args.precision),
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
-                         "issued_tflops": tf * (3.0 if split else 1.0),
+                         "issued_tflops": tf * {"split3": 6.0, "split": 3.0, "bf16": 1.0}[args.precision],
                          "kernel": "conv_igemm_kernel + wgrad3x3_kernel (whole update, %.1f TFLOP algorithmic)" % (flops / 1e12),
                          "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "note": ("channels 16 / 32 are padded to the 64-wide K chunk and layer 0 runs 4 rotated copies: the "
@@ -633,8 +636,9 @@ def main():
     ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "pendulum", "scale1m", "equiv", "cnn"],
                     help="ppo = BASELINE configs[1] (default, the headline line); pendulum = configs[2]; scale1m = configs[4] "
                          "(1M envs over the GPUs + GAE sweep); equiv = configs[3]; cnn = its plain-CNN sibling")
-    ap.add_argument("--precision", type=str, default="split", choices=["split", "bf16"],
-                    help="equiv / cnn: split = bf16 hi+mid operand planes, fp32-class results (default); bf16 = single-plane fast mode")
+    ap.add_argument("--precision", type=str, default="split", choices=["split", "split3", "bf16"],
+                    help="equiv / cnn: split = two bf16 operand planes, the reference-precision mode (default); split3 = three planes "
+                         "(no more accurate, measured); bf16 = single-plane fast mode, below the reference's precision")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -236,7 +236,7 @@ typedef struct {
   aur_policy_desc policy;
   int32_t norm_adv;          /* ppo.py:238 */
   int32_t clip_vloss;        /* ppo.py:250; 0 reproduces the reference's b_values quirk (ppo.py:261) */
-  int32_t _pad;
+  int32_t mom_index;         /* which entry of an aur_ppo_adv_moments_multi launch this minibatch is (with dp + mom_seq) */
   int64_t m_local;           /* samples of this GPU's share of the minibatch */
   int64_t m_total;           /* samples of the whole minibatch (means divide by this) */
   const int32_t* idx;        /* [m_local] row indices into the flattened buffers, or NULL: idx_offset + i */
@@ -254,7 +254,8 @@ typedef struct {
   float* grads_out;          /* [P + 16] */
   const aur_dp_ctx* dp;      /* NULL: single GPU */
   uint32_t dp_seq;
-  uint32_t _pad3;
+  uint32_t mom_seq;          /* != 0: the advantage moments were exchanged AHEAD by aur_ppo_adv_moments_multi(mom_seq): the
+                                gradient kernel reads entry mom_index of that exchange instead of waiting for a per-minibatch one */
   const float* rec_actor;    /* optional: [B,8] records of aur_ppo_pack_records (both or neither); the kernel then */
   const float* rec_critic;   /* gathers one 32-byte sector per sample and net instead of one per array */
 } aur_update_args;
@@ -288,6 +289,16 @@ int aur_ppo_adv_moments(int64_t m, const int32_t* idx, int64_t idx_offset, const
 
 int aur_ppo_adv_moments_dp(int64_t m, const int32_t* idx, int64_t idx_offset, const float* advantages,
                            double* moments_out, float* workspace, const aur_dp_ctx* dp, uint32_t seq, void* stream);
+
+/* Advantage moments of ALL the minibatches of an iteration in one launch: the permutations of every epoch do not depend
+ * on the parameters, so they (and these moments) can be produced right after GAE.  idx: n_mb consecutive index lists of m
+ * rows each (idx_stride apart).  moments_out [n_mb][3] (sum, sum of squares, count).  Data-parallel: the local moments of
+ * all n_mb minibatches are pushed to every rank once, under the iteration counter mom_seq (1-based, the same on every rank) -
+ * one rendezvous per iteration instead of one per minibatch; aur_update_args.mom_seq / mom_index select an entry.
+ * n_mb <= AUR_DP_MAX_MINIBATCHES.  Replaces `mb_advantages.mean() / .std()` of ppo.py:239 for the whole update loop. */
+#define AUR_DP_MAX_MINIBATCHES 512
+int aur_ppo_adv_moments_multi(int32_t n_mb, int64_t m, const int32_t* idx, int64_t idx_stride, const float* advantages,
+                              double* moments_out, float* workspace, const aur_dp_ctx* dp, uint32_t mom_seq, void* stream);
 
 int aur_ppo_update_grad(const aur_update_args* args, void* stream);
 

@@ -19,7 +19,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, cont, out_dir, shape=None):
+def _worker(rank, world, port, cont, out_dir, shape=None, ahead=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     dev = rank % torch.cuda.device_count()
@@ -47,8 +47,14 @@ def _worker(rank, world, port, cont, out_dir, shape=None):
     share = m // world
     mine = idx[rank * share:(rank + 1) * share].contiguous()
     grads, stats = [], []
+    if ahead:
+        # the advantage moments of all three "minibatches" of the iteration in one launch, exchanged ONCE
+        # (aur_ppo_adv_moments_multi); entry 1 gets a different index list so that a wrong entry would show
+        other = idx.flip(0)[rank * share:(rank + 1) * share].contiguous()
+        up.prepare_moments(adv, torch.stack([mine, other, mine]).contiguous())
     for step in range(3):
-        grads.append(up.grad(*bufs, mine, m_total=m).clone())       # local sums (before the gather)
+        kw = dict(moments_index=2 * (step & 1)) if ahead else {}
+        grads.append(up.grad(*bufs, mine, m_total=m, **kw).clone())  # local sums (before the gather)
         stats.append(up.apply(2.5e-4, 0.5).clone())
         grads.append(up.grads.clone())                                # world sums, written back by the Adam kernel
     torch.cuda.synchronize()
@@ -67,10 +73,13 @@ def _worker(rank, world, port, cont, out_dir, shape=None):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cont,shape", [(False, None), (True, None), (False, (6, 3, 32, 3)), (True, (5, 2, 128, 2))])
-def test_peer_exchange_matches_single_gpu(tmp_path, cont, shape):
+@pytest.mark.parametrize("cont,shape,ahead", [(False, None, False), (True, None, False), (False, (6, 3, 32, 3), False),
+                                              (True, (5, 2, 128, 2), False), (False, None, True), (True, None, True),
+                                              (False, (6, 3, 32, 3), True)])
+def test_peer_exchange_matches_single_gpu(tmp_path, cont, shape, ahead):
+    """ahead=True: the advantage moments travel once per iteration (prepare_moments) instead of once per minibatch."""
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), cont, str(tmp_path), shape), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), cont, str(tmp_path), shape, ahead), nprocs=world, join=True)
     r0, r1, one = [np.load(tmp_path / f) for f in ("rank0.npz", "rank1.npz", "single.npz")]
     # every rank ends with bit-identical parameters and statistics (same sums in the same order)
     np.testing.assert_array_equal(r0["params"], r1["params"])

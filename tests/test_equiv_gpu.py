@@ -95,15 +95,17 @@ def test_conv0_weight_gradient_matches_autograd():
     state = (torch.rand(B, generator=g) > 0.5).float()
     out = torch.zeros(B, 66, 66, 64, dtype=torch.bfloat16, device="cuda")
     arg = torch.zeros(B, 64, 64, 64, dtype=torch.uint8, device="cuda")
-    kernels.equiv_conv0(obs.cuda(), state.cuda(), psi.detach().cuda(), bias.detach().cuda(), out, arg)
+    d_obs, d_state = obs.cuda(), state.cuda()          # kept alive: a temporary's memory may be reused before the kernel reads it
+    kernels.equiv_conv0(d_obs, d_state, psi.detach().cuda(), bias.detach().cuda(), out, arg)
     da1 = (torch.randn(B, 64, 64, 64, generator=g) * 0.1).to(torch.bfloat16)          # upstream gradient, NHWC
+    d_g = da1.cuda()
     x = Q.cat_obs(state, obs)
     y = F.max_pool2d(F.relu(F.conv2d(x, Q.expand_trivial_to_regular(psi), Q.expand_bias_regular(bias), padding=1)), 2)
     y.backward(da1.float().permute(0, 3, 1, 2))
     ws = torch.zeros(64 * 18 + 64, device="cuda")
     dpsi, dbias = torch.zeros(16, 2, 3, 3, device="cuda"), torch.zeros(16, device="cuda")
-    rc = _lib.lib().aur_equiv_conv0_wgrad(obs.cuda().data_ptr(), state.cuda().data_ptr(), da1.cuda().data_ptr(), out.data_ptr(),
-                                          arg.data_ptr(), B, ws.data_ptr(), dpsi.data_ptr(), dbias.data_ptr(), None)
+    rc = _lib.lib().aur_equiv_conv0_wgrad(d_obs.data_ptr(), d_state.data_ptr(), d_g.data_ptr(), out.data_ptr(),
+                                          arg.data_ptr(), B, ws.data_ptr(), dpsi.data_ptr(), dbias.data_ptr(), kernels._stream())
     _lib.check(rc, "aur_equiv_conv0_wgrad")
     torch.cuda.synchronize()
     # the only difference: fp32 vs bf16-stored forward decides a few near-tie arg-max / ReLU routings

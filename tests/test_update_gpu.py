@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from aur_ppo_b200 import kernels
+from aur_ppo_b200 import _lib, kernels
 from oracle import ppo_ref as R
 from tests.helpers import flat_from_named, random_policy
 
@@ -215,3 +215,36 @@ def test_full_size_minibatch_properties():
         np.testing.assert_allclose(out["tc"][P:P + 6].cpu().numpy(), out["simt"][P:P + 6].cpu().numpy(), rtol=1e-4)
     finally:
         L.aur_ppo_update_set_impl(prev)
+
+
+@pytest.mark.parametrize("cont", [False, True])
+def test_moments_of_all_minibatches_in_one_launch(cont):
+    """aur_ppo_adv_moments_multi (what ppo.run_update uses: the moments of every minibatch of an iteration right after the
+    shuffles) against the per-minibatch kernel and against float64 torch; the update that reads entry j is the update that
+    computed its own moments."""
+    from tests.helpers import flat_from_named, random_policy
+    obs_dim, act_dim = (3, 1) if cont else (4, 2)
+    _, named = random_policy(obs_dim, act_dim, 64, 2, cont, seed=9)
+    desc = kernels.policy_desc(obs_dim, act_dim, 64, 2, cont)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    B, n_mb, m = 40000, 7, 5000
+    g = torch.Generator().manual_seed(3)
+    obs = (torch.randn(B, obs_dim, generator=g) * 0.5).cuda()
+    act = (torch.randn(B, act_dim, generator=g) if cont else torch.randint(0, act_dim, (B,), generator=g).float()).cuda()
+    oldlp = (-0.7 + 0.2 * torch.randn(B, generator=g)).cuda(); adv = (torch.randn(B, generator=g) * 3 + 2).cuda()
+    ret = torch.randn(B, generator=g).cuda(); vold = torch.randn(B, generator=g).cuda()
+    idx_all = torch.stack([torch.randperm(B, generator=g)[:m] for _ in range(n_mb)]).to(torch.int32).cuda().contiguous()
+    bufs = (obs, act, oldlp, adv, ret, vold)
+    up = kernels.Updater(desc, flat.clone())
+    up.prepare_moments(adv, idx_all)
+    got = up.moments_all.cpu()
+    for j in range(n_mb):
+        a = adv[idx_all[j].long()].double().cpu()
+        np.testing.assert_allclose(got[j].numpy(), [float(a.sum()), float((a * a).sum()), m], rtol=1e-13)
+    ref = kernels.Updater(desc, flat.clone())
+    for j in (0, 3, 6):
+        g1 = up.grad(*bufs, idx_all[j], moments_index=j).clone()
+        g2 = ref.grad(*bufs, idx_all[j]).clone()
+        assert torch.equal(g1, g2) or float((g1 - g2).abs().max()) <= 1e-7 * float(g2.abs().max())
+    with pytest.raises(_lib.AurError):
+        up.grad(*bufs, idx_all[0], moments_index=n_mb)
