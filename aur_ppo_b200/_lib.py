@@ -166,6 +166,8 @@ def lib() -> ctypes.CDLL:
     L.aur_dp_free.argtypes = [c_void_p]
     L.aur_dp_status.restype = c_int
     L.aur_dp_status.argtypes = [c_void_p, c_void_p]
+    L.aur_dp_wait_stats.restype = c_int
+    L.aur_dp_wait_stats.argtypes = [c_void_p, c_void_p, c_int32, c_void_p]
     L.aur_ppo_adv_moments_multi.restype = c_int
     L.aur_ppo_adv_moments_multi.argtypes = [c_int32, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                             ctypes.c_uint32, c_void_p]

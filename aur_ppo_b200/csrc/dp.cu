@@ -50,6 +50,17 @@ extern "C" int aur_dp_free(void* area) {
   return 0;
 }
 
+// out[4] = {ns spent waiting for gradient flags, number of such waits, ns for moment flags, number}; reset != 0 zeroes them
+extern "C" int aur_dp_wait_stats(void* area, uint64_t* out4, int32_t reset, void* stream) {
+  using namespace aur;
+  if (!area || !out4) { set_error("aur_dp_wait_stats: bad arguments"); return AUR_ERR_ARG; }
+  unsigned char* w = static_cast<unsigned char*>(area) + DP_OFF_WAIT;
+  AUR_CUDA_OK(cudaMemcpyAsync(out4, w, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (reset) AUR_CUDA_OK(cudaMemsetAsync(w, 0, 4 * sizeof(uint64_t), (cudaStream_t)stream));
+  AUR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
 // 0 = healthy, 1 = a kernel gave up waiting for a peer (its results are invalid)
 extern "C" int aur_dp_status(const void* area, void* stream) {
   using namespace aur;

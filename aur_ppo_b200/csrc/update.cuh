@@ -24,6 +24,7 @@ constexpr int DP_MAX = 16;
 constexpr int DP_OFF_FLAG_MOM = 0;         // u32 [DP_MAX]
 constexpr int DP_OFF_FLAG_GRAD = 64;       // u32 [DP_MAX]
 constexpr int DP_OFF_STATUS = 128;         // u32: 1 = a wait timed out
+constexpr int DP_OFF_WAIT = 136;           // u64 [4]: ns spent waiting for peers' gradient flags, number of such waits, the same for moment flags
 constexpr int DP_OFF_FLAG_MOMX = 192;      // u32 [DP_MAX]: iteration counter of the moments exchanged ahead (aur_ppo_adv_moments_multi)
 constexpr int DP_OFF_MOM = 256;            // f64 [2][DP_MAX][4]
 constexpr int DP_MAXMB = AUR_DP_MAX_MINIBATCHES;
@@ -55,13 +56,18 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 // wait until the peer's flag in OUR area reaches seq; gives up after 20 s (status word) instead of hanging the GPU
-__device__ __forceinline__ void dp_wait_flag(const uint32_t* flag, uint32_t seq, unsigned char* my_area) {
+// (which: 0 = gradient flags, 1 = moment flags - the time spent spinning is accumulated per kind in the exchange area, so the
+// skew between ranks is measured, not inferred: aur_dp_wait_stats)
+__device__ __forceinline__ void dp_wait_flag(const uint32_t* flag, uint32_t seq, unsigned char* my_area, int which = 0) {
   if ((int32_t)(ld_acquire_sys(flag) - seq) >= 0) return;
   const uint64_t t0 = global_timer_ns();
   while ((int32_t)(ld_acquire_sys(flag) - seq) < 0) {
     __nanosleep(64);
     if (global_timer_ns() - t0 > 20000000000ull) { *reinterpret_cast<volatile uint32_t*>(my_area + DP_OFF_STATUS) = 1u; break; }
   }
+  unsigned long long* w = reinterpret_cast<unsigned long long*>(my_area + DP_OFF_WAIT) + 2 * which;
+  atomicAdd(w, (unsigned long long)(global_timer_ns() - t0));
+  atomicAdd(w + 1, 1ull);
 }
 #endif
 
@@ -90,7 +96,7 @@ __device__ __forceinline__ void load_adv_moments(const UpdDev& a, double& s, dou
       const double* rm = reinterpret_cast<const double*>(me + DP_OFF_MOMX) + (size_t)(a.dp.mom_seq & 1u) * DP_MAX * DP_MAXMB * 4 +
                          (size_t)a.dp.mom_index * 4;
       for (int r = 0; r < a.dp.world; ++r) {
-        dp_wait_flag(flags + r, a.dp.mom_seq, me);
+        dp_wait_flag(flags + r, a.dp.mom_seq, me, 1);
         const double* q = rm + (size_t)r * DP_MAXMB * 4;
         s += __ldcg(q); ss += __ldcg(q + 1); n += __ldcg(q + 2);
       }
@@ -99,7 +105,7 @@ __device__ __forceinline__ void load_adv_moments(const UpdDev& a, double& s, dou
     const uint32_t* flags = reinterpret_cast<const uint32_t*>(me + DP_OFF_FLAG_MOM);
     const double* rm = reinterpret_cast<const double*>(me + DP_OFF_MOM) + (a.dp.seq & 1u) * DP_MAX * 4;
     for (int r = 0; r < a.dp.world; ++r) {
-      dp_wait_flag(flags + r, a.dp.seq, me);
+      dp_wait_flag(flags + r, a.dp.seq, me, 1);
       s += __ldcg(rm + r * 4); ss += __ldcg(rm + r * 4 + 1); n += __ldcg(rm + r * 4 + 2);
     }
   } else {

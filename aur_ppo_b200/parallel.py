@@ -121,6 +121,14 @@ class PeerExchange:
     def status(self) -> int:
         return int(self._L.aur_dp_status(self.own, None))
 
+    def wait_stats(self, reset: bool = False) -> dict:
+        """Time this rank's kernels spent spinning on peers' flags (measured on the device, globaltimer) since the last reset."""
+        import ctypes
+        from . import _lib
+        out = (ctypes.c_uint64 * 4)()
+        _lib.check(self._L.aur_dp_wait_stats(self.own, out, int(reset), None), "aur_dp_wait_stats")
+        return {"grad_wait_us": out[0] / 1e3, "grad_waits": int(out[1]), "moment_wait_us": out[2] / 1e3, "moment_waits": int(out[3])}
+
     def close(self) -> None:
         if self._L is None:
             return

@@ -318,6 +318,8 @@ def run_ours(args):
     sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     L.aur_launch_count_reset()
+    if agent.exchange is not None:
+        agent.exchange.wait_stats(reset=True)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for k in range(args.steps):
@@ -326,6 +328,18 @@ def run_ours(args):
     end.record()
     barrier()
     launches = int(L.aur_launch_count())
+    wait_stats = None
+    if agent.exchange is not None:                      # device-measured spin time on peers' flags inside the timed region
+        ws_ = agent.exchange.wait_stats()
+        wt = torch.tensor([ws_["grad_wait_us"], ws_["moment_wait_us"]], device=agent.device, dtype=torch.float64)
+        wmax, wmin = wt.clone(), wt.clone()
+        dist.all_reduce(wmax, op=dist.ReduceOp.MAX); dist.all_reduce(wmin, op=dist.ReduceOp.MIN)
+        per = args.steps * n_mb_iter
+        wait_stats = {"rank0": ws_, "grad_wait_us_per_minibatch_max_rank": float(wmax[0]) / per,
+                      "grad_wait_us_per_minibatch_min_rank": float(wmin[0]) / per,
+                      "moment_wait_us_per_iteration_max_rank": float(wmax[1]) / args.steps,
+                      "what": "time the update kernels spent spinning on peers' flags (globaltimer, accumulated in the exchange "
+                              "area); a rank that arrives last waits ~0, the others wait for it"}
     clocks = sampler.finish()
     ms_total = start.elapsed_time(end)
     t_roll = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
@@ -371,7 +385,6 @@ def run_ours(args):
     d2h_bytes = P * 4 + h_stats.numel() * 4 + d2h // args.steps
 
     exchange_kind = "in-kernel all-reduce over NVLink peer memory" if agent.exchange is not None else ("nccl all_reduce" if world > 1 else "none")
-    wait_stats = agent.exchange.wait_stats() if agent.exchange is not None and hasattr(agent.exchange, "wait_stats") else None
     if agent.exchange is not None and agent.exchange.status() != 0:
         raise SystemExit("data-parallel exchange: a kernel timed out waiting for a peer rank")
     m = agent.local_minibatch
