@@ -28,7 +28,7 @@ template <bool PLAIN>
 __global__ void __launch_bounds__(256, 3)
 conv0_wgrad_tc_kernel(const float* __restrict__ obs, const float* __restrict__ state, const __nv_bfloat16* __restrict__ da1,
                       const __nv_bfloat16* __restrict__ a1 /*[B,66,66,64]*/, const unsigned char* __restrict__ arg, int B,
-                      float* __restrict__ dw0 /*[64][2][9]*/, float* __restrict__ dbias_ch /*[64]*/, int parts) {
+                      float* __restrict__ dw0 /*[64][2][9]*/, float* __restrict__ dbias_ch /*[64]*/, int parts, int flush) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = base + C0O_A;
@@ -53,9 +53,22 @@ conv0_wgrad_tc_kernel(const float* __restrict__ obs, const float* __restrict__ s
 
   const long long npix = (long long)B * 64 * 64;
   const long long nblk = (npix + C0_PIX - 1) / C0_PIX;
-  uint32_t it = 0;
-  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++it) {
+  // flush > 0 (multi-plane precisions): the TMEM accumulator is drained into the global fp32 sums every `flush` blocks - the
+  // tensor core's accumulator adds truncate (~2e-8 per MMA step), and a CTA walks hundreds of blocks at minibatch 4096
+  auto drain = [&]() {
+    fence_after_sync();
+    if (tid < 64) {                                     // accumulator row = output channel: warps 0, 1 hold rows 0..63
+      float v[32];
+      tmem_ld32(tm_d + ((uint32_t)(32 * warp) << 16), v);
+#pragma unroll
+      for (int n = 0; n < 18; ++n) atomicAdd(dw0 + tid * 18 + n, v[n]);
+      atomicAdd(dbias_ch + tid, v[18]);
+    }
+  };
+  uint32_t it = 0, since = 0;                           // since: blocks accumulated since the last drain
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++it, ++since) {
     if (it > 0) mbar_wait(bar, (it - 1u) & 1u);          // the previous block's MMAs have read the tiles
+    if (flush > 0 && since == (uint32_t)flush) { drain(); since = 0; }
     const long long pix0 = blk * C0_PIX;
     // ---- B: thread (window w, pixel p) writes the 18 taps of its window's view as hi / mid
     {
@@ -131,7 +144,7 @@ conv0_wgrad_tc_kernel(const float* __restrict__ obs, const float* __restrict__ s
         for (int part = 0; part < parts; ++part) {         // parts = 1: the hi views only (second pass over the gradient's mid plane)
           const uint64_t bd = smem_desc_k_sw128(sB + (2 * w + part) * C0_B_BYTES);
           for (int k = 0; k < C0_PIX / 16; ++k)
-            mma_f16(tm_d, ad + (uint64_t)(128 * k), bd + (uint64_t)(2 * k), IDESC, (it | (uint32_t)(w | part | k)) != 0u);
+            mma_f16(tm_d, ad + (uint64_t)(128 * k), bd + (uint64_t)(2 * k), IDESC, (since | (uint32_t)(w | part | k)) != 0u);
         }
       }
       mma_commit(bar);
@@ -139,14 +152,7 @@ conv0_wgrad_tc_kernel(const float* __restrict__ obs, const float* __restrict__ s
   }
   if (it > 0) {
     mbar_wait(bar, (it - 1u) & 1u);
-    fence_after_sync();
-    if (tid < 64) {                                     // accumulator row = output channel: warps 0, 1 hold rows 0..63
-      float v[32];
-      tmem_ld32(tm_d + ((uint32_t)(32 * warp) << 16), v);
-#pragma unroll
-      for (int n = 0; n < 18; ++n) atomicAdd(dw0 + tid * 18 + n, v[n]);
-      atomicAdd(dbias_ch + tid, v[18]);
-    }
+    drain();
   }
   fence_before_sync();
   __syncthreads();
@@ -155,6 +161,7 @@ conv0_wgrad_tc_kernel(const float* __restrict__ obs, const float* __restrict__ s
 
 int launch_conv0_wgrad_tc(const float* obs, const float* state, const void* da1, const void* a1, const uint8_t* arg, int B,
                           float* dw0, float* dbias_ch, cudaStream_t s, bool plain, int parts) {
+  const int flush = tc_planes() > 1 ? 8 : 0;
   static DeviceOnce attr;
   if (attr.first()) {
     AUR_CUDA_OK(cudaFuncSetAttribute(conv0_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C0_SMEM));
@@ -168,10 +175,10 @@ int launch_conv0_wgrad_tc(const float* obs, const float* state, const void* da1,
   if (grid > nblk) grid = nblk;
   if (plain)
     conv0_wgrad_tc_kernel<true><<<(unsigned)grid, 256, C0_SMEM, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg,
-                                                                     B, dw0, dbias_ch, parts);
+                                                                     B, dw0, dbias_ch, parts, flush);
   else
     conv0_wgrad_tc_kernel<false><<<(unsigned)grid, 256, C0_SMEM, s>>>(obs, state, (const __nv_bfloat16*)da1, (const __nv_bfloat16*)a1, arg,
-                                                                      B, dw0, dbias_ch, parts);
+                                                                      B, dw0, dbias_ch, parts, flush);
   AUR_LAUNCH_OK("conv0_wgrad_tc_kernel");
   return 0;
 }

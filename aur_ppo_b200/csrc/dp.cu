@@ -50,13 +50,14 @@ extern "C" int aur_dp_free(void* area) {
   return 0;
 }
 
-// out[4] = {ns spent waiting for gradient flags, number of such waits, ns for moment flags, number}; reset != 0 zeroes them
-extern "C" int aur_dp_wait_stats(void* area, uint64_t* out4, int32_t reset, void* stream) {
+// out[6] = {spin ns on gradient flags (summed over spinning threads), spins, the same for moment flags, wall ns the Adam kernels
+// waited for the slowest peer, Adam launches}; reset != 0 zeroes them
+extern "C" int aur_dp_wait_stats(void* area, uint64_t* out6, int32_t reset, void* stream) {
   using namespace aur;
-  if (!area || !out4) { set_error("aur_dp_wait_stats: bad arguments"); return AUR_ERR_ARG; }
+  if (!area || !out6) { set_error("aur_dp_wait_stats: bad arguments"); return AUR_ERR_ARG; }
   unsigned char* w = static_cast<unsigned char*>(area) + DP_OFF_WAIT;
-  AUR_CUDA_OK(cudaMemcpyAsync(out4, w, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  if (reset) AUR_CUDA_OK(cudaMemsetAsync(w, 0, 4 * sizeof(uint64_t), (cudaStream_t)stream));
+  AUR_CUDA_OK(cudaMemcpyAsync(out6, w, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (reset) AUR_CUDA_OK(cudaMemsetAsync(w, 0, 6 * sizeof(uint64_t), (cudaStream_t)stream));
   AUR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }

@@ -61,11 +61,19 @@ constexpr int CV_THREADS = 384;   // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM
 // was the same weights over and over (9.2 GB of L2 reads per launch, 11.6 TB/s: the layer was L2-bandwidth bound).
 constexpr int CV_RESB_STAGES = 4;
 constexpr size_t CV_RESB_SMEM = (size_t)CV_RESB_STAGES * CV_A_BYTES + 9 * (128 * CV_BK * 2) + 1024 + 256;
-template <int CV_BN, bool SWAP = false, bool RESB = false>
+// CHUNKED (the multi-plane precisions): the tensor core adds every K = 16 step into its fp32 accumulator with TRUNCATION, so a
+// contraction over thousands of steps drifts by ~3e-8 per step (measured: 1.5e-5 at K = 4608 x 3 products, 5e-5 for layer 5,
+// more than all the operand rounding of the two-plane split).  The MMA warp therefore switches between the two TMEM
+// accumulators every CV_CHUNK stages instead of every work item, and the epilogue warps PROMOTE each finished chunk into fp32
+// registers (round-to-nearest adds, 64 registers per thread at BN = 128); the epilogue proper then runs from the registers.
+// A chunk is 32 MMA steps (~1e-6); draining it (two tcgen05.ld + 64 FADD per thread) hides behind the next chunk's MMAs.
+constexpr int CV_CHUNK = 8;       // stages per promoted chunk
+template <int CV_BN, bool SWAP = false, bool RESB = false, bool CHUNKED = false>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvDev a) {
   static_assert(!SWAP || CV_BN == 128, "the swapped epilogue is built for 128 x 128 accumulators");
   static_assert(!RESB || SWAP, "resident weights come with the channel-major kernel");
+  static_assert(!CHUNKED || (!SWAP && CV_BN <= 128), "chunk promotion keeps BN / 2 accumulator registers per epilogue thread");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   constexpr int CV_STAGES = RESB ? CV_RESB_STAGES : CvCfg<CV_BN>::STAGES, CV_B_BYTES = CvCfg<CV_BN>::B_BYTES;
@@ -138,24 +146,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if constexpr (RESB) {
       if (blockIdx.x < items) { mbar_wait(bres, 0u); fence_after_sync(); }
     }
-    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-      const uint32_t acc = it & 1u;
-      mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
-      fence_after_sync();
-      for (int kb = 0; kb < nkb; ++kb, ++kg) {
-        const int s = kg % CV_STAGES;
-        const uint32_t ph = (kg / CV_STAGES) & 1u;
-        mbar_wait(&full[s], ph);
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+      // one accumulator hand-over per work item, or (CHUNKED) per CV_CHUNK stages; `it` counts hand-overs across items
+      const int span = CHUNKED ? CV_CHUNK : nkb;
+      for (int kb0 = 0; kb0 < nkb; kb0 += span, ++it) {
+        const uint32_t acc = it & 1u;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
         fence_after_sync();
-        const uint64_t ad = smem_desc_k_sw128(sA + s * CV_A_BYTES), bd = smem_desc_k_sw128(sB + (RESB ? kb : s) * CV_B_BYTES);
+        const int kb1 = kb0 + span < nkb ? kb0 + span : nkb;
+        for (int kb = kb0; kb < kb1; ++kb, ++kg) {
+          const int s = kg % CV_STAGES;
+          const uint32_t ph = (kg / CV_STAGES) & 1u;
+          mbar_wait(&full[s], ph);
+          fence_after_sync();
+          const uint64_t ad = smem_desc_k_sw128(sA + s * CV_A_BYTES), bd = smem_desc_k_sw128(sB + (RESB ? kb : s) * CV_B_BYTES);
 #pragma unroll
-        for (int k = 0; k < CV_BK / 16; ++k) {
-          if constexpr (SWAP) mma_f16(tmem_d + acc * CV_BN, bd + (uint64_t)(2 * k), ad + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          else mma_f16(tmem_d + acc * CV_BN, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          for (int k = 0; k < CV_BK / 16; ++k) {
+            if constexpr (SWAP) mma_f16(tmem_d + acc * CV_BN, bd + (uint64_t)(2 * k), ad + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0);
+            else mma_f16(tmem_d + acc * CV_BN, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0);
+          }
+          mma_commit(&empty[s]);
         }
-        mma_commit(&empty[s]);
+        mma_commit(&tmem_full[acc]);
       }
-      mma_commit(&tmem_full[acc]);
     }
   } else if (SWAP && warp >= 4) {
     // ===== swapped epilogue: lane = output channel, columns = the tile's 128 pixels; bias + ReLU + 2x2 max-pool in registers =====
@@ -217,22 +230,52 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int xx = r % a.TW; r /= a.TW;
     const int yy = r % a.TH; r /= a.TH;
     uint32_t it = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+    constexpr int NG = CHUNKED ? (CV_BN / 2 + 31) / 32 : 1;      // 32-column groups this warp owns (CHUNKED: kept in registers)
+    float racc[NG][32];
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
     int b0, y0, x0, n0;
     decode(item, b0, y0, x0, n0);
-    const uint32_t acc = it & 1u;
     const int b = b0 + r, y = y0 + yy, x = x0 + xx;
     const bool valid = b < a.B && y < a.Ho && x < a.Wo;
-    mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
-    fence_after_sync();
-#pragma unroll 1
-    for (int c = (CV_BN / 2) * chalf; c < (CV_BN / 2) * (chalf + 1); c += 32) {
-      float v[32];
-      tmem_ld32(tmem_d + acc * CV_BN + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
-      if (c + 32 == (CV_BN / 2) * (chalf + 1)) {        // last read of this accumulator: hand it back to the MMA warp
+    uint32_t acc = it & 1u;
+    if constexpr (CHUNKED) {
+      // promote every finished chunk of this item into the register accumulators (fp32 round-to-nearest adds)
+      for (int kb0 = 0; kb0 < nkb; kb0 += CV_CHUNK, ++it) {
+        acc = it & 1u;
+        mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
+        fence_after_sync();
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const int c = (CV_BN / 2) * chalf + 32 * g;
+          if (c < (CV_BN / 2) * (chalf + 1)) {
+            float v[32];
+            tmem_ld32(tmem_d + acc * CV_BN + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) racc[g][i] = kb0 == 0 ? v[i] : racc[g][i] + v[i];
+          }
+        }
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
+    } else {
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
+      fence_after_sync();
+      ++it;
+    }
+#pragma unroll
+    for (int g = 0; g < (CV_BN / 2 + 31) / 32; ++g) {
+      const int c = (CV_BN / 2) * chalf + 32 * g;
+      if (c >= (CV_BN / 2) * (chalf + 1)) continue;
+      float vloc[CHUNKED ? 1 : 32];
+      float (&v)[32] = *reinterpret_cast<float (*)[32]>(CHUNKED ? &racc[g][0] : &vloc[0]);     // CHUNKED: work in place on the promoted sums
+      if constexpr (!CHUNKED) {
+        tmem_ld32(tmem_d + acc * CV_BN + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+        if (c + 32 >= (CV_BN / 2) * (chalf + 1)) {        // last read of this accumulator: hand it back to the MMA warp
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
       }
       const int ch = n0 + c;
       if (ch >= a.Cout) continue;
@@ -524,7 +567,8 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   // (split planes: the pixel-major kernels only - the resident-weight variant has no room for two weight planes)
   const bool swap = c.epilogue == 2 && c.Cin == 64 && P == 1 && conv_swap_enabled();       // Cin 128 (layer 2) is faster on 256-wide tiles
   const bool resb = swap && c.Cout <= 128;
-  const bool wide = !swap && c.Cout % 256 == 0;
+  const bool chunked = P > 1;                     // multi-plane precisions promote the accumulator chunk by chunk (BN <= 128)
+  const bool wide = !swap && !chunked && c.Cout % 256 == 0;
   const bool narrow = !swap && c.Cout <= 64;     // e.g. the backward-data convolution into the 64-channel layer-0 output: N = 64 MMAs
   const int BN = wide ? 256 : (narrow ? 64 : 128);
   const uint32_t bB[3] = {CV_BK, (uint32_t)BN, 1};
@@ -538,13 +582,17 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<64>::SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<128>::SMEM));
     AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_RESB_SMEM));
+    AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<128>::SMEM));
+    AUR_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<64, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<64>::SMEM));
     attr.done();
   }
   d.pix_tiles = (int)(img_groups * d.tiles_y * d.tiles_x);
   d.n_tiles = (c.Cout + BN - 1) / BN;
   const long long items = (long long)d.pix_tiles * d.n_tiles;
   const unsigned grid = (unsigned)(items < sm_count() ? items : sm_count());
-  if (resb) conv_igemm_kernel<128, true, true><<<grid, CV_THREADS, CV_RESB_SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
+  if (chunked && narrow) conv_igemm_kernel<64, false, false, true><<<grid, CV_THREADS, CvCfg<64>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
+  else if (chunked) conv_igemm_kernel<128, false, false, true><<<grid, CV_THREADS, CvCfg<128>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
+  else if (resb) conv_igemm_kernel<128, true, true><<<grid, CV_THREADS, CV_RESB_SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
   else if (swap) conv_igemm_kernel<128, true><<<grid, CV_THREADS, CvCfg<128>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
   else if (wide) conv_igemm_kernel<256><<<grid, CV_THREADS, CvCfg<256>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);
   else if (narrow) conv_igemm_kernel<64><<<grid, CV_THREADS, CvCfg<64>::SMEM, (cudaStream_t)stream>>>(tmA, tmB, d);

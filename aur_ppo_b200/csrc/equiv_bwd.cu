@@ -848,6 +848,14 @@ extern "C" int aur_wgrad3x3_bf16(int32_t Cout, int32_t Cin, int64_t Q, const voi
     if (split_k > nkb / 8) split_k = (int)(nkb / 8 > 0 ? nkb / 8 : 1);
     if (split_k < 1) split_k = 1;
   }
+  if (P > 1) {
+    // multi-plane precisions: bound the MMA steps that accumulate in TMEM before the fp32 (round-to-nearest) adds of the
+    // epilogue - the tensor core's accumulator adds truncate, ~2e-8 per step (64 K-blocks x 3 products x 4 steps ~ 2e-5)
+    const long long nkb = (Q + WG_BK - 1) / WG_BK;
+    long long need = (nkb + 63) / 64;
+    if (need > 65535) need = 65535;
+    if (split_k < need) split_k = (int)need;
+  }
   dim3 grid((unsigned)(mt * nt), 3, (unsigned)split_k);
   wgrad3x3_kernel<<<grid, 256, WG_SMEM, (cudaStream_t)stream>>>(tmA, tmB, Cout, Cin, (long long)Q, base_off, Wb, nt, dwmat, tc_terms(P));
   AUR_LAUNCH_OK("wgrad3x3_kernel");

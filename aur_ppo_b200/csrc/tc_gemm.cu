@@ -40,30 +40,37 @@ constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 64, GEMM_STAGES = 4;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2, GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;
 constexpr size_t GEMM_SMEM = (size_t)GEMM_STAGES * (GEMM_A_BYTES + GEMM_B_BYTES) + 1024 + 256;
 
-__global__ void __launch_bounds__(256, 1)
+// `chunk` stages per accumulator hand-over: the tensor core adds each K = 16 step into its fp32 accumulator with truncation
+// (~3e-8 per step: 1.5e-5 over K = 4608 x 3 products), so in the multi-plane precisions the MMA warp alternates between two TMEM
+// accumulators every `chunk` stages and the eight epilogue warps promote every finished chunk into fp32 registers
+// (round-to-nearest adds); single-plane bf16 passes chunk = all stages (one hand-over, as before).
+constexpr int GEMM_THREADS = 384;     // warps: 0 TMA, 1 MMA, 2 TMEM allocator, 4..11 epilogue (lane quarter x column half)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
-                    int M, int N, int K, int ldc, int nterm) {
+                    int M, int N, int K, int ldc, int nterm, int chunk) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   unsigned char* sA = smem;
   unsigned char* sB = smem + GEMM_STAGES * GEMM_A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + GEMM_STAGES * GEMM_B_BYTES);
   uint64_t* empty = full + GEMM_STAGES;
-  uint64_t* tmem_full = empty + GEMM_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + GEMM_STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * GEMM_BN;
-  const int nkb = ((K + GEMM_BK - 1) / GEMM_BK) * nterm;     // split operands: the (hi,hi), (hi,mid), (mid,hi) products are extra K steps
+  const int nkb = ((K + GEMM_BK - 1) / GEMM_BK) * nterm;     // multi-plane operands: the plane products are extra K steps
+  if (chunk <= 0 || chunk > nkb) chunk = nkb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
     mbar_fence_init();
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
   }
-  if (warp == 2) tmem_alloc(tmem_slot, GEMM_BN);
+  if (warp == 2) tmem_alloc(tmem_slot, 2 * GEMM_BN);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -81,41 +88,63 @@ tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1 && lane == 0) {
     constexpr uint32_t idesc = instr_desc(FMT_BF16, GEMM_BM, GEMM_BN, 0, 0);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % GEMM_STAGES;
-      const uint32_t ph = (kb / GEMM_STAGES) & 1u;
-      mbar_wait(&full[s], ph);
+    uint32_t it = 0;
+    for (int kb0 = 0; kb0 < nkb; kb0 += chunk, ++it) {
+      const uint32_t acc = it & 1u;
+      mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
       fence_after_sync();
-      const uint64_t ad = smem_desc_k_sw128(sA + s * GEMM_A_BYTES), bd = smem_desc_k_sw128(sB + s * GEMM_B_BYTES);
+      const int kb1 = kb0 + chunk < nkb ? kb0 + chunk : nkb;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int s = kb % GEMM_STAGES;
+        const uint32_t ph = (kb / GEMM_STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        fence_after_sync();
+        const uint64_t ad = smem_desc_k_sw128(sA + s * GEMM_A_BYTES), bd = smem_desc_k_sw128(sB + s * GEMM_B_BYTES);
 #pragma unroll
-      for (int k = 0; k < GEMM_BK / 16; ++k)          // UMMA_K = 16 bf16 = 32 B: advance the start address by 2 x 16 B
-        mma_f16(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-      mma_commit(&empty[s]);
+        for (int k = 0; k < GEMM_BK / 16; ++k)          // UMMA_K = 16 bf16 = 32 B: advance the start address by 2 x 16 B
+          mma_f16(tmem_d + acc * GEMM_BN, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0);
+        mma_commit(&empty[s]);
+      }
+      mma_commit(&tmem_full[acc]);
     }
-    mma_commit(tmem_full);
   } else if (warp >= 4) {
-    const int q = warp - 4;
-    mbar_wait(tmem_full, 0);
-    fence_after_sync();
+    const int q = (warp - 4) & 3, chalf = (warp - 4) >> 2;
     const int row = m0 + 32 * q + lane;
-#pragma unroll 1
-    for (int c = 0; c < GEMM_BN; c += 32) {
-      float v[32];
-      tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
-      if (row < M) {
+    float racc[2][32];
+    uint32_t it = 0;
+    for (int kb0 = 0; kb0 < nkb; kb0 += chunk, ++it) {
+      const uint32_t acc = it & 1u;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
+      fence_after_sync();
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float v[32];
+        tmem_ld32(tmem_d + acc * GEMM_BN + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * chalf + 32 * g), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) racc[g][i] = kb0 == 0 ? v[i] : racc[g][i] + v[i];
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    if (row < M) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int c = 64 * chalf + 32 * g;
         float* dst = C + (size_t)row * ldc + n0 + c;
         if (n0 + c + 32 <= N && (ldc & 3) == 0) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(racc[g][i], racc[g][i + 1], racc[g][i + 2], racc[g][i + 3]);
         } else {
-          for (int i = 0; i < 32; ++i) if (n0 + c + i < N) dst[i] = v[i];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (n0 + c + i < N) dst[i] = racc[g][i];
         }
       }
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_d, GEMM_BN);
+  if (warp == 2) tmem_dealloc(tmem_d, 2 * GEMM_BN);
 }
 
 }  // namespace tc
@@ -148,7 +177,8 @@ extern "C" int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, 
     attr.done();
   }
   dim3 grid((unsigned)((M + GEMM_BM - 1) / GEMM_BM), (unsigned)((N + GEMM_BN - 1) / GEMM_BN));
-  tc_gemm_bf16_kernel<<<grid, 256, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, C, (int)M, (int)N, (int)K, (int)N, tc_terms(P));
+  tc_gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, C, (int)M, (int)N, (int)K, (int)N, tc_terms(P),
+                                                                         P > 1 ? 8 : 0);
   AUR_LAUNCH_OK("tc_gemm_bf16_kernel");
   return 0;
 }

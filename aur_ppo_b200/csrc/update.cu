@@ -649,8 +649,14 @@ __global__ void __launch_bounds__(1024) adam_kernel(int64_t P, float* __restrict
     // area (grad_reduce_kernel); wait for the flags, add the G vectors in rank order (bit-identical on every
     // rank), keep the global sums in g_in, then clip + Adam as usual on replicated parameters.
     unsigned char* me = dp.peer[dp.rank];
+    const uint64_t t_in = global_timer_ns();
     if ((int)threadIdx.x < dp.world) dp_wait_flag(reinterpret_cast<const uint32_t*>(me + DP_OFF_FLAG_GRAD) + threadIdx.x, dp.seq, me);
     __syncthreads();
+    if (threadIdx.x == 0) {                              // wall time this rank stood still waiting for the slowest peer
+      unsigned long long* w = reinterpret_cast<unsigned long long*>(me + DP_OFF_WAIT) + 4;
+      w[0] += (unsigned long long)(global_timer_ns() - t_in);
+      w[1] += 1ull;
+    }
     const int gs = dp_grad_stride(P);
     const float* rg = reinterpret_cast<const float*>(me + DP_OFF_GRAD) + (size_t)(dp.seq & 1u) * DP_MAX * gs;
     for (int64_t i = threadIdx.x; i < P + AUR_NUM_STATS; i += blockDim.x) {

@@ -24,7 +24,9 @@ constexpr int DP_MAX = 16;
 constexpr int DP_OFF_FLAG_MOM = 0;         // u32 [DP_MAX]
 constexpr int DP_OFF_FLAG_GRAD = 64;       // u32 [DP_MAX]
 constexpr int DP_OFF_STATUS = 128;         // u32: 1 = a wait timed out
-constexpr int DP_OFF_WAIT = 136;           // u64 [4]: ns spent waiting for peers' gradient flags, number of such waits, the same for moment flags
+constexpr int DP_OFF_WAIT = 136;           // u64 [6]: spin ns on peers' gradient flags summed over the spinning threads, number of spins;
+                                           // the same for moment flags; then WALL ns the Adam kernel stood still until every peer's
+                                           // gradients had arrived (entry -> all flags seen), number of Adam launches
 constexpr int DP_OFF_FLAG_MOMX = 192;      // u32 [DP_MAX]: iteration counter of the moments exchanged ahead (aur_ppo_adv_moments_multi)
 constexpr int DP_OFF_MOM = 256;            // f64 [2][DP_MAX][4]
 constexpr int DP_MAXMB = AUR_DP_MAX_MINIBATCHES;

@@ -125,9 +125,10 @@ class PeerExchange:
         """Time this rank's kernels spent spinning on peers' flags (measured on the device, globaltimer) since the last reset."""
         import ctypes
         from . import _lib
-        out = (ctypes.c_uint64 * 4)()
+        out = (ctypes.c_uint64 * 6)()
         _lib.check(self._L.aur_dp_wait_stats(self.own, out, int(reset), None), "aur_dp_wait_stats")
-        return {"grad_wait_us": out[0] / 1e3, "grad_waits": int(out[1]), "moment_wait_us": out[2] / 1e3, "moment_waits": int(out[3])}
+        return {"grad_spin_us_sum": out[0] / 1e3, "grad_spins": int(out[1]), "moment_spin_us_sum": out[2] / 1e3,
+                "moment_spins": int(out[3]), "adam_wall_wait_us": out[4] / 1e3, "adam_launches": int(out[5])}
 
     def close(self) -> None:
         if self._L is None:

@@ -331,15 +331,17 @@ def run_ours(args):
     wait_stats = None
     if agent.exchange is not None:                      # device-measured spin time on peers' flags inside the timed region
         ws_ = agent.exchange.wait_stats()
-        wt = torch.tensor([ws_["grad_wait_us"], ws_["moment_wait_us"]], device=agent.device, dtype=torch.float64)
+        wt = torch.tensor([ws_["adam_wall_wait_us"] / max(ws_["adam_launches"], 1),
+                           ws_["moment_spin_us_sum"] / max(ws_["moment_spins"], 1)], device=agent.device, dtype=torch.float64)
         wmax, wmin = wt.clone(), wt.clone()
         dist.all_reduce(wmax, op=dist.ReduceOp.MAX); dist.all_reduce(wmin, op=dist.ReduceOp.MIN)
-        per = args.steps * n_mb_iter
-        wait_stats = {"rank0": ws_, "grad_wait_us_per_minibatch_max_rank": float(wmax[0]) / per,
-                      "grad_wait_us_per_minibatch_min_rank": float(wmin[0]) / per,
-                      "moment_wait_us_per_iteration_max_rank": float(wmax[1]) / args.steps,
-                      "what": "time the update kernels spent spinning on peers' flags (globaltimer, accumulated in the exchange "
-                              "area); a rank that arrives last waits ~0, the others wait for it"}
+        wait_stats = {"rank0": ws_, "grad_wall_wait_us_per_minibatch_max_rank": float(wmax[0]),
+                      "grad_wall_wait_us_per_minibatch_min_rank": float(wmin[0]),
+                      "moment_spin_us_per_spinning_cta_max_rank": float(wmax[1]),
+                      "what": "measured on the device (globaltimer, accumulated in the exchange area): wall time the clip + Adam kernel "
+                              "of a minibatch stood still until every peer's gradient sums had arrived (the rank that arrives last "
+                              "waits ~0, the others wait for it), and the spin time of the gradient kernels' CTAs on the moment flags "
+                              "(only the first minibatch of an iteration can spin: the moments travel once per iteration)"}
     clocks = sampler.finish()
     ms_total = start.elapsed_time(end)
     t_roll = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps

@@ -231,9 +231,11 @@ int aur_dp_open(const void* ipc_handle, void** area_out);
 int aur_dp_close(void* area);
 int aur_dp_free(void* area);
 int aur_dp_status(const void* area, void* stream);   /* 0 ok, 1 = a kernel timed out waiting for a peer */
-/* Time this rank's kernels spent spinning on peers' flags since the last reset: out4 (host) = {gradient-flag wait ns, number
- * of gradient waits that had to spin, moment-flag wait ns, number}; reset != 0 zeroes the counters.  Synchronises `stream`. */
-int aur_dp_wait_stats(void* area, uint64_t* out4, int32_t reset, void* stream);
+/* Time this rank's kernels spent waiting for peers since the last reset, measured on the device: out6 (host) = {spin ns on
+ * gradient flags summed over the spinning threads, number of spins, the same two for moment flags, WALL ns the clip + Adam
+ * kernels stood still until every peer's gradients had arrived, number of those launches}; reset != 0 zeroes the counters.
+ * Synchronises `stream`. */
+int aur_dp_wait_stats(void* area, uint64_t* out6, int32_t reset, void* stream);
 
 typedef struct {
   aur_policy_desc policy;

@@ -2,10 +2,11 @@
 Multi-plane modes of the tensor-core entry points (aur_tc_set_precision):
   2 planes ("split"):  bf16 hi + mid operand planes, three products, fp32 accumulation in TMEM;
   3 planes ("split3"): hi + mid + lo, six products.
-MEASURED (this file): operand rounding is NOT what limits either mode.  The tensor core adds each K = 16 step into its fp32
-accumulator with truncation, so the error of a contraction grows with the number of MMA steps along K (~3e-8 each): 3e-6 at
-K = 512, 1.5e-5 (2 planes) / 3e-5 (3 planes, twice the steps) at K = 4608.  Two planes are therefore the more accurate AND the
-cheaper mode; three planes stay available and tested, but nothing uses them.  For scale: the reference runs these convolutions
+MEASURED (round 2): the tensor core adds each K = 16 step into its fp32 accumulator with TRUNCATION, so a long contraction
+drifts by ~2e-8 per MMA step - 1.5e-5 (2 planes) / 3.1e-5 (3 planes, twice the steps) at K = 4608 when everything accumulates
+in TMEM, MORE than the operand rounding of the two-plane split.  The multi-plane kernels therefore promote the accumulator
+into fp32 registers (round-to-nearest) every 32 MMA steps (conv, GEMM) or bound the steps per CTA before the fp32 atomics
+(weight gradients); the drift tests below hold that.  For scale: the reference runs these convolutions
 through cuDNN with torch's default `torch.backends.cudnn.allow_tf32 = True` (torch 2.1.1, src/environment.yml:540; never
 changed in src/), i.e. with 10-bit TF32 operands (~5e-4) on any Ampere-or-later GPU.
 
@@ -30,7 +31,7 @@ from oracle import equiv_ref as Q
 
 pytestmark = pytest.mark.gpu
 BAR = 1e-4
-LAYER_BAR = {2: 1e-4, 3: 1e-4}           # per-kernel relative L2 vs float64, by operand planes (measured 3e-6 .. 3e-5)
+LAYER_BAR = {2: 2e-5, 3: 2e-5}           # per-kernel relative L2 vs float64, by operand planes
 
 
 def _rel(a, b):
@@ -55,7 +56,8 @@ def test_tc_gemm_split_matches_fp64(M, N, K, P):
     with kernels.tc_precision(P):
         c = kernels.tc_gemm_bf16(kernels.split_planes(a.cuda(), P), kernels.split_planes(b.cuda(), P))
     want = a.double() @ b.double().T
-    assert _rel(c.cpu(), want) < (2e-5 if P == 2 else 5e-5), _rel(c.cpu(), want)     # accumulator-limited: grows with K x terms
+    print(f"gemm {M}x{N}x{K} planes {P}: rel {_rel(c.cpu(), want):.2e}")
+    assert _rel(c.cpu(), want) < (6e-6 if P == 2 else 2e-6), _rel(c.cpu(), want)
     # the single-plane mode on the same operands is ~300x less accurate: the split is what buys the precision
     with kernels.tc_precision(1):
         c1 = kernels.tc_gemm_bf16(a.cuda().bfloat16(), b.cuda().bfloat16())
@@ -67,7 +69,8 @@ def test_tc_gemm_split_matches_fp64(M, N, K, P):
 
 @pytest.mark.parametrize("B,H,Fi,Fo,pad,pool", [(3, 16, 16, 32, 1, True), (2, 64, 16, 32, 1, True), (5, 8, 32, 64, 1, False),
                                                 (4, 8, 64, 32, 0, True), (2, 32, 32, 16, 1, False), (5, 8, 16, 32, 1, True),
-                                                (1, 32, 32, 48, 1, True), (2, 8, 128, 128, 0, False)])
+                                                (1, 32, 32, 48, 1, True), (2, 8, 128, 128, 0, False),
+                                                (2, 8, 256, 128, 0, False)])          # Cin = 1024: K = 9216 (layer 5)
 @pytest.mark.parametrize("P", [2, 3])
 def test_conv_layer_split_matches_fp64_conv2d(B, H, Fi, Fo, pad, pool, P):
     g = torch.Generator().manual_seed(B * 100 + H)
@@ -91,6 +94,7 @@ def test_conv_layer_split_matches_fp64_conv2d(B, H, Fi, Fo, pad, pool, P):
     if pool:
         ref = F.max_pool2d(ref, 2)
     got = kernels.join_planes(out)[:, 1:1 + Hn, 1:1 + Hn, :].permute(0, 3, 1, 2).cpu()
+    print(f"conv Cin {Cin} Cout {Cout} H {H} planes {P}: rel {_rel(got, ref):.2e}")
     assert _rel(got, ref) < LAYER_BAR[P], _rel(got, ref)
     assert float(out[:, :, 0].abs().max()) == 0 and float(out[:, :, :, -1].abs().max()) == 0      # halos untouched, both planes
     if pool:      # routing: the stored arg-max picks the window element whose value IS the pooled value
@@ -118,7 +122,32 @@ def test_wgrad3x3_split_matches_fp64_autograd(B, H, Cin, Cout, P):
     W = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, requires_grad=True)
     F.conv2d(x.double(), W, padding=1).backward(dy.double())
     want = W.grad.permute(0, 2, 3, 1).reshape(Cout, 9, Cin)
+    print(f"wgrad Cin {Cin} Cout {Cout} planes {P}: rel {_rel(dw.cpu(), want):.2e}")
     assert _rel(dw.cpu(), want) < LAYER_BAR[P], _rel(dw.cpu(), want)
+
+
+def test_weight_gradient_accumulator_drift_at_minibatch_scale():
+    """1.1 M pixel rows (what a 256-sample minibatch gives layer 1; config D has 16x that) with same-signed terms, the worst
+    case for a truncating accumulator: every CTA's TMEM partial must stay short enough that the fp32 result is still within
+    2e-5 of a float64 reference (here torch's float64 convolution backward on the device)."""
+    from aur_ppo_b200.kernels import _stream
+    B, H, Cin, Cout = 256, 64, 64, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand(B, Cin, H, H, generator=g, device="cuda") + 0.5
+    dy = torch.rand(B, Cout, H, H, generator=g, device="cuda") * 0.1 + 0.05
+    Hb = H + 2
+    xb = torch.zeros(2, B, Hb, Hb, Cin, dtype=torch.bfloat16, device="cuda")
+    xb[:, :, 1:1 + H, 1:1 + H, :] = kernels.split_planes(x.permute(0, 2, 3, 1).contiguous())
+    dyb = torch.zeros(2, B, Hb, Hb, Cout, dtype=torch.bfloat16, device="cuda")
+    dyb[:, :, 1:1 + H, 1:1 + H, :] = kernels.split_planes(dy.permute(0, 2, 3, 1).contiguous())
+    dw = torch.zeros(Cout, 9, Cin, device="cuda")
+    with kernels.tc_precision(2):
+        rc = _lib.lib().aur_wgrad3x3_bf16(Cout, Cin, B * Hb * Hb, dyb.data_ptr(), xb.data_ptr(), -(Hb + 1), Hb, dw.data_ptr(), 0, _stream())
+    _lib.check(rc, "aur_wgrad3x3_bf16")
+    want = torch.nn.grad.conv2d_weight(x.double(), (Cout, Cin, 3, 3), dy.double(), padding=1).permute(0, 2, 3, 1).reshape(Cout, 9, Cin)
+    err = _rel(dw.cpu(), want.cpu())
+    print(f"weight-gradient drift at Q = {B * Hb * Hb}: rel {err:.2e}")
+    assert err < 2e-5, err
 
 
 @pytest.mark.parametrize("P", [2, 3])

@@ -25,7 +25,7 @@ import json, glob
 for f in sorted(glob.glob("gpurun_out/r2f/bench_*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
-        print(f.split("/")[-1], "%.4g" % d["value"], "ms %.2f" % d["ms_per_step"], d["phase_ms"], (d.get("dp_wait") or {}).get("grad_wait_us_per_minibatch_max_rank"))
+        print(f.split("/")[-1], "%.4g" % d["value"], "ms %.2f" % d["ms_per_step"], d["phase_ms"], (d.get("dp_wait") or {}).get("grad_wall_wait_us_per_minibatch_max_rank"))
     except Exception as e:
         print(f, "ERR", e)
 PY

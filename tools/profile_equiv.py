@@ -5,6 +5,7 @@ import torch
 from aur_ppo_b200 import equiv, plain_cnn
 B = int(os.environ.get("EQUIV_B", "256"))
 PLAIN = os.environ.get("EQUIV_PLAIN", "0") == "1"
+PREC = os.environ.get("EQUIV_PRECISION", "split")
 if PLAIN:
     params = plain_cnn.init_params(seed=0)
 else:
@@ -16,7 +17,7 @@ obs = torch.rand(B, 1, 128, 128, generator=g, device="cuda") * 0.32
 state = (torch.rand(B, generator=g, device="cuda") > 0.5).float()
 action = torch.randn(B, 5, generator=g, device="cuda")
 adv, ret, vold = (torch.randn(B, generator=g, device="cuda") for _ in range(3))
-model = plain_cnn.PlainActorCritic(params, B) if PLAIN else equiv.EquivActorCritic(params, B)
+model = (plain_cnn.PlainActorCritic if PLAIN else equiv.EquivActorCritic)(params, B, precision=PREC)
 for _ in range(2):
     model.update(state, obs, action, torch.full((B,), -7.0, device="cuda"), adv, ret, vold)
 torch.cuda.synchronize()

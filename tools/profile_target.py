@@ -26,7 +26,9 @@ if "update" in which:
     flat_bufs = (buf.states.reshape(-1, 4), buf.actions.reshape(-1), buf.log_probs.reshape(-1), adv.reshape(-1),
                  ret.reshape(-1), buf.values.reshape(-1))
     rec = kernels.pack_records(*flat_bufs)
+    idx_all = torch.stack([torch.randperm(N * T, device="cuda")[: N * T // 4].to(torch.int32) for _ in range(4)]).contiguous()
+    up.prepare_moments(flat_bufs[3], idx_all)
     for i in range(3):
-        up.step(*flat_bufs, idx, lr=2.5e-4, records=rec)
+        up.step(*flat_bufs, idx_all[i], lr=2.5e-4, records=rec, moments_index=i)
 torch.cuda.synchronize()
 print("profile target done")
