@@ -9,12 +9,13 @@ Every convolution / dense contraction runs on tcgen05 tensor cores through the C
 halos, accumulation is fp32, parameters / gradients / Adam moments are fp32.
 
 Operand precisions (aur_tc_set_precision), `precision=`:
-  "split"  2 planes: every bf16 tensor is a stack hi / mid (v = hi + mid to 2^-18) and every contraction issues hi*hi +
-           hi*mid + mid*hi with fp32 accumulation: the REFERENCE-PRECISION mode (equiv.py / robot_ppo.py compute in fp32, in
-           practice TF32 through cuDNN's default): forward within ~3e-5, gradients within north_star's 1e-4 of float64
-           autograd on identical routing (tests/test_equiv_split_gpu.py); 3x the MMA work;
-  "split3" 3 planes (hi / mid / lo, six products): measured NO more accurate - the tensor core's truncating fp32 accumulator,
-           not operand rounding, sets the error, and six products double the accumulation steps; kept, tested, unused;
+  "fp32"   3 planes: every bf16 tensor is a stack hi / mid / lo (3 x 8 = 24 mantissa bits) and every contraction issues the
+           six products above 2^-24, accumulated in TMEM in chunks of 32 MMA steps that are promoted into fp32 registers (the
+           tensor core's own accumulator truncates): fp32-EQUIVALENT, like the reference (equiv.py / robot_ppo.py compute in
+           fp32).  Measured ~7e-7 per layer; every gradient tensor within 3e-5 of float64 autograd on identical routing, 5
+           routing decisions of 9.0 M differ from float64 (torch fp32 on the CPU: 4).  6x the MMA work;
+  "split"  2 planes (hi / mid, three products, the same promotion): ~5e-6 per layer, gradients within 1e-4 except where the
+           problem amplifies the forward error; still ~100x tighter than the TF32 the reference gets from cuDNN's default; 3x;
   "bf16"   single-plane bf16 operands: the fast mode, below the reference's precision (1e-2 class).
 Internally every bf16 buffer carries a leading plane dimension P (1, 2 or 3).  The free parameters are
 the p4 group-convolution filters psi (see oracle/equiv_ref.py for the restated architecture and why
@@ -35,7 +36,7 @@ from . import _lib
 from .kernels import _ptr, _stream, adv_moments, conv3x3_bf16, equiv_conv0, equiv_expand_regular, tc_gemm_bf16, tc_precision
 
 ENC_FIELDS = [16, 32, 64, 128, 256, 128, 128]
-PRECISIONS = {"bf16": 1, "split": 2, "split3": 3}        # operand planes (aur_tc_set_precision)
+PRECISIONS = {"bf16": 1, "split": 2, "fp32": 3}          # operand planes (aur_tc_set_precision)
 N_ACT = 5
 
 

@@ -96,3 +96,17 @@ def evaluate(path, gym_id: str = "CartPole-v1", episodes: int = 100, mode: str =
     lengths = t.run(episodes, max_length=max_length, mode=mode, seed=seed)
     return dict(lengths=lengths, returns=t.episode_returns, mean_length=float(np.mean(lengths)),
                 mean_return=float(np.mean(t.episode_returns)))
+
+
+if __name__ == "__main__":          # src/test.py:60-61: test('actor_critic.pt', 'CartPole-v1', render_mode=None).run(1000)
+    import argparse
+    ap = argparse.ArgumentParser(description="play a saved actor_critic*.pt on the device envs (src/test.py)")
+    ap.add_argument("model", nargs="?", default="actor_critic.pt")
+    ap.add_argument("--gym_id", default="CartPole-v1")
+    ap.add_argument("--episodes", type=int, default=1000)
+    ap.add_argument("--mode", choices=["sampled", "greedy"], default="sampled")
+    ap.add_argument("--seed", type=int, default=0)
+    a = ap.parse_args()
+    out = evaluate(a.model, a.gym_id, a.episodes, a.mode, a.seed)
+    print(f"{a.episodes} episodes of {a.gym_id} ({a.mode}): mean length {out['mean_length']:.1f}, mean return {out['mean_return']:.1f}, "
+          f"min {min(out['lengths'])}, max {max(out['lengths'])}")

@@ -11,7 +11,7 @@ Workloads (sizes per BASELINE.json):
             override (run_ppo.py:44-51): 32 minibatches x 10 epochs, lr 3e-4, entropy 0                  configs[2]
   scale1m   CartPole-v1, 1,048,576 envs IN TOTAL sharded over the GPUs (strong scaling), T = 128,
             plus a GAE sweep T = 128..2048 on 131072 columns per GPU                                      configs[4]
-  equiv     equivariant actor-critic update, minibatch 4096 (--precision split|split3|bf16)                      configs[3]
+  equiv     equivariant actor-critic update, minibatch 4096 (--precision fp32|split|bf16)                      configs[3]
 A step = one PPO iteration: T * num_envs env steps (fused rollout), one GAE pass and
 epochs * num_minibatches fused updates.
 """
@@ -162,7 +162,7 @@ def cpu_reference_iteration(name, num_envs, iters, warmup, seed=1):
     logps = torch.zeros(T, N); rewards = torch.zeros(T, N); dones = torch.zeros(T, N); values = torch.zeros(T, N)
     batch = N * T
     mb = max(batch // w["nm"], 1)
-    times = []
+    times, phases = [], []
     for it in range(warmup + iters):
         t0 = time.perf_counter()
         for t in range(T):                                   # ppo.py:201-205
@@ -173,8 +173,10 @@ def cpu_reference_iteration(name, num_envs, iters, warmup, seed=1):
             o, r, term, trunc, info = envs.step(a.numpy())
             rewards[t] = torch.tensor(r).view(-1)
             next_obs, next_done = torch.from_numpy(o), torch.from_numpy(term.astype(np.float32))
+        t_r = time.perf_counter()
         with torch.no_grad():                                # ppo.py:159-166
             ret, adv = R.gae(rewards, values, dones, pol.value(next_obs), next_done, 0.99, 0.95)
+        t_g = time.perf_counter()
         b = (obs.reshape(-1, O), actions.reshape(-1, w["act"]) if cont else actions.reshape(-1), logps.reshape(-1),
              adv.reshape(-1), ret.reshape(-1), values.reshape(-1))
         inds = np.arange(batch)
@@ -183,9 +185,37 @@ def cpu_reference_iteration(name, num_envs, iters, warmup, seed=1):
             for s in range(0, batch, mb):
                 mi = torch.from_numpy(inds[s:s + mb])
                 R.ppo_update_step(pol, opt, b[0][mi], b[1][mi], b[2][mi], b[3][mi], b[4][mi], b[5][mi], ent_c=w["ent"])
-        times.append(time.perf_counter() - t0)
-    times = times[warmup:]
+        t_u = time.perf_counter()
+        times.append(t_u - t0)
+        phases.append((t_r - t0, t_g - t_r, t_u - t_g))
+    times, phases = times[warmup:], phases[warmup:]
+    med = lambda i: sorted(p[i] for p in phases)[len(phases) // 2]
+    CPU_PHASES[(name, num_envs)] = {"rollout_env_steps_per_s": N * T / med(0), "gae_GBps": (20 * T * N + 8 * N) / med(1) / 1e9,
+                                    "update_samples_per_s": w["epochs"] * batch / med(2),
+                                    "phase_ms_median": {"rollout": med(0) * 1e3, "gae": med(1) * 1e3, "update": med(2) * 1e3}}
     return sum(times) / len(times), N * T
+
+
+CPU_PHASES = {}
+
+
+def host_info():
+    """what is always printed with the CPU numbers."""
+    import numpy as np
+    import torch
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {"cpu_model": model, "os_cpu_count": os.cpu_count(), "torch_num_threads": torch.get_num_threads(),
+            "torch": torch.__version__, "numpy": np.__version__,
+            "path": "2 (BASELINE.md section 3 fallback): oracle restatement of gym 0.26.2 + reference model math on torch CPU; gym "
+                    "itself is not installed and not installable (profiles/r2_pip_gym_attempt.log)",
+            "note": "env stepping is one Python loop on one core by construction (SyncVectorEnv); torch CPU ops use all threads"}
 
 
 def cpu_sample_text(name, n, iters):
@@ -214,9 +244,9 @@ def run_reference(args):
         for pn, it in ((4, 8), (n, 0)):
             if it:
                 ps, pst = cpu_reference_iteration(name, pn, it, 2)
-                points.append({"num_envs": pn, "value": pst / ps, "unit": UNIT, "ms_per_iteration": ps * 1e3})
+                points.append(dict({"num_envs": pn, "value": pst / ps, "unit": UNIT, "ms_per_iteration": ps * 1e3}, **CPU_PHASES[(name, pn)]))
             else:
-                points.append({"num_envs": pn, "value": v, "unit": UNIT, "ms_per_iteration": sec * 1e3})
+                points.append(dict({"num_envs": pn, "value": v, "unit": UNIT, "ms_per_iteration": sec * 1e3}, **CPU_PHASES[(name, pn)]))
     sample = cpu_sample_text(name, n, args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": w["scaling"],
@@ -224,7 +254,7 @@ def run_reference(args):
             "config": workload_config(name, args.gpus),
             "sampled": {"num_envs": n, "num_steps": w["T"], "env_steps_per_step": steps,
                         "note": "value = env-steps of the SAMPLE / its time; one CPU process whatever --gpus says"},
-            "cpu_points": points,
+            "cpu_points": points, "cpu_phases": CPU_PHASES.get((name, n)), "host": host_info(),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -463,7 +493,8 @@ def run_ours(args):
         iters = 4 if name != "pendulum" else 2
         sec, steps = cpu_reference_iteration(name, CPU_SAMPLE_ENVS[name], iters, 1)
         cpu_baseline = {"value": steps / sec, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": cpu_sample_text(name, CPU_SAMPLE_ENVS[name], iters)}
+                        "sample": cpu_sample_text(name, CPU_SAMPLE_ENVS[name], iters),
+                        "phases": CPU_PHASES.get((name, CPU_SAMPLE_ENVS[name])), "host": host_info()}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
@@ -582,17 +613,18 @@ def run_equiv(args, plain: bool = False):
     tf = flops / (ms * 1e-3) / 1e12
     line = {"metric": "update_samples_per_s", "value": B / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"split3": "bf16x3 operand planes (hi + mid + lo), six products, fp32 accumulate in TMEM (tcgen05): measured no "
-                                "more accurate than split (accumulator-limited); fp32 parameters and Adam",
-                      "split": "reference precision: bf16x2 operand planes (hi + mid = 16 mantissa bits), three products, fp32 "
-                               "accumulate in TMEM (tcgen05): forward ~3e-5, gradients within 1e-4 of float64 on identical routing; "
-                               "fp32 parameters and Adam.  (The reference's fp32 convolutions run as TF32 under cuDNN's default.)",
+            "dtype": {"fp32": "fp32-equivalent (the reference's precision): bf16x3 operand planes (hi + mid + lo = 24 mantissa bits), "
+                              "six products on tcgen05, TMEM accumulation promoted into fp32 registers every 32 MMA steps; measured "
+                              "~7e-7 per layer, gradients within 3e-5 of float64 on identical routing; fp32 parameters and Adam",
+                      "split": "bf16x2 operand planes (hi + mid = 16 mantissa bits), three products, the same promotion: ~5e-6 per "
+                               "layer, gradients within 1e-4 at well-conditioned points (the reference's fp32 convolutions run as "
+                               "TF32, ~5e-4, under cuDNN's default); fp32 parameters and Adam",
                       "bf16": "bf16 operands / fp32 accumulate (tcgen05), fp32 parameters and Adam: BELOW the reference's fp32 "
                               "precision (fast mode)"}[args.precision],
             "data": "synthetic", "precision": args.precision,
             "config": dict(equiv_config(plain), precision=args.precision),
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
-                         "issued_tflops": tf * {"split3": 6.0, "split": 3.0, "bf16": 1.0}[args.precision],
+                         "issued_tflops": tf * {"fp32": 6.0, "split": 3.0, "bf16": 1.0}[args.precision],
                          "kernel": "conv_igemm_kernel + wgrad3x3_kernel (whole update, %.1f TFLOP algorithmic)" % (flops / 1e12),
                          "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "note": ("channels 16 / 32 are padded to the 64-wide K chunk and layer 0 runs 4 rotated copies: the "
@@ -651,9 +683,9 @@ def main():
     ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "pendulum", "scale1m", "equiv", "cnn"],
                     help="ppo = BASELINE configs[1] (default, the headline line); pendulum = configs[2]; scale1m = configs[4] "
                          "(1M envs over the GPUs + GAE sweep); equiv = configs[3]; cnn = its plain-CNN sibling")
-    ap.add_argument("--precision", type=str, default="split", choices=["split", "split3", "bf16"],
-                    help="equiv / cnn: split = two bf16 operand planes, the reference-precision mode (default); split3 = three planes "
-                         "(no more accurate, measured); bf16 = single-plane fast mode, below the reference's precision")
+    ap.add_argument("--precision", type=str, default="fp32", choices=["fp32", "split", "bf16"],
+                    help="equiv / cnn: fp32 = three bf16 operand planes, fp32-equivalent like the reference (default); split = two "
+                         "planes (~5e-6 per layer); bf16 = single-plane fast mode, below the reference's precision")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -166,6 +166,9 @@ def actor_forward(p, cat_obs, collect=None, quant=False, route=None, route_out=N
     W = torch.cat([expand_regular_to_irrep1(p["actor.head.psi_irrep"]), expand_regular_to_trivial(p["actor.head.psi_triv"])], 0)
     if quant:
         W = bf16_ste(W)
+    if route is not None and "keep" in route and W.requires_grad:  # expose the UN-projected head gradient to the tests
+        W.retain_grad()
+        route["keep"]["W_actor_head"] = W
     bias = torch.cat([torch.zeros(2, dtype=feat.dtype), p["actor.head.bias_triv"]])
     out = feat @ W.T + bias                                        # [B,10]
     dxy, inv_act = out[:, 0:2], out[:, 2:N_ACT]

@@ -1,7 +1,7 @@
 """Row X at REFERENCE precision against float64 torch -- north_star's bar for this row: losses and gradients within 1e-4 relative.
 Multi-plane modes of the tensor-core entry points (aur_tc_set_precision):
-  2 planes ("split"):  bf16 hi + mid operand planes, three products, fp32 accumulation in TMEM;
-  3 planes ("split3"): hi + mid + lo, six products.
+  3 planes ("fp32"):  bf16 hi + mid + lo operand planes, six products: fp32-equivalent, the reference-precision mode;
+  2 planes ("split"): hi + mid, three products.
 MEASURED (round 2): the tensor core adds each K = 16 step into its fp32 accumulator with TRUNCATION, so a long contraction
 drifts by ~2e-8 per MMA step - 1.5e-5 (2 planes) / 3.1e-5 (3 planes, twice the steps) at K = 4608 when everything accumulates
 in TMEM, MORE than the operand rounding of the two-plane split.  The multi-plane kernels therefore promote the accumulator
@@ -31,7 +31,7 @@ from oracle import equiv_ref as Q
 
 pytestmark = pytest.mark.gpu
 BAR = 1e-4
-LAYER_BAR = {2: 2e-5, 3: 2e-5}           # per-kernel relative L2 vs float64, by operand planes
+LAYER_BAR = {2: 1e-5, 3: 5e-6}           # per-kernel relative L2 vs float64, by operand planes (measured 4.5e-6 / 7e-7; wgrad 3e-6)
 
 
 def _rel(a, b):
@@ -217,13 +217,14 @@ def _count_flips(dev_route, own_route):
     return flips, total
 
 
-@pytest.mark.parametrize("kind,head_scale,precision", [("equiv", 0.02, "split"), ("equiv", 0.1, "split"), ("plain", 1.0, "split"),
-                                                       ("equiv", 0.02, "split3")])
+@pytest.mark.parametrize("kind,head_scale,precision", [("equiv", 0.02, "fp32"), ("equiv", 0.1, "fp32"), ("plain", 1.0, "fp32"),
+                                                       ("equiv", 0.02, "split"), ("equiv", 0.1, "split"), ("plain", 1.0, "split")])
 def test_full_update_split_gradients_match_fp64_autograd(kind, head_scale, precision):
-    """Bars on identical routing (measured values in brackets): forward log-prob / value and the three loss terms 1e-4; every
-    critic tensor 1e-4 [<= 6.7e-5]; actor tensors 1e-4 at the well-conditioned point [<= 6.8e-5], 2e-4 for the plain CNN
-    [1.1e-4: its forward log-prob error of 9e-5 ABSOLUTE is the relative error of every loss seed], 1e-3 at the ill-conditioned
-    point [6.6e-4]; actor.head.psi_irrep 3e-3 [1.1e-3].
+    """Bars on identical routing (measured values in brackets).  "fp32": EVERY tensor, the forward log-prob / value and the
+    three loss terms within north_star's 1e-4 [<= 2.6e-5].  "split": the same 1e-4 for the critic chain [<= 2e-5] and for the
+    actor at both head scales [<= 7e-5], 3e-4 for the plain CNN's actor [1.7e-4: its forward log-prob error of 1.3e-4
+    ABSOLUTE is the relative error of every loss seed].  actor.head.psi_irrep is measured against the norm of the UN-projected
+    head gradient it is the C4 projection of (the projection cancels ~30x on this input).
     head_scale = factor on the equivariant head filters.  The actor's log_std is a head OUTPUT there (equiv.py:88-90); at 0.1
     it reaches -2 (std 0.13) on this input, where d log_prob / d mean = diff / var amplifies a forward error ~50x into the
     loss seeds of EVERY actor gradient; at 0.02 (|log_std| < 0.5, a freshly initialised policy) it does not.
@@ -263,6 +264,7 @@ def test_full_update_split_gradients_match_fp64_autograd(kind, head_scale, preci
 
     # ---- (a) identical routing: the device's decisions forced on the float64 oracle
     route = _device_route(model, B, real)
+    route["keep"] = {}
     a_out, c_pre, _, _ = model._last_head
     if kind == "equiv":
         hw = (c_pre.cpu() + Q.expand_bias_regular(p32["critic.head1.bias"])).reshape(B, -1, 4)
@@ -277,6 +279,12 @@ def test_full_update_split_gradients_match_fp64_autograd(kind, head_scale, preci
     d_lp = float((model.logp.cpu().double() - lp64).abs().max())
     d_v = float((model.value.cpu().double() - v64).abs().max())
     forced = {k: _rel(model.grads[k].cpu(), p64[k].grad) for k in p64}
+    if kind == "equiv":                      # the irrep head filter: error against the un-projected gradient's norm (see docstring)
+        k = "actor.head.psi_irrep"
+        unproj = route["keep"]["W_actor_head"].grad[0:2]
+        cancel = float(unproj.norm() / p64[k].grad.norm())
+        forced[k] = float((model.grads[k].cpu().double() - p64[k].grad).norm() / unproj.norm())
+        print(f"   actor.head.psi_irrep: projection cancels {cancel:.0f}x; error / |un-projected gradient| = {forced[k]:.1e}")
     worst_a = max(v for k, v in forced.items() if k.startswith("actor"))
     worst_c = max(v for k, v in forced.items() if k.startswith("critic"))
     print(f"[{kind} x{head_scale} {precision}] device vs float64 autograd on identical routing: worst actor {worst_a:.1e}, worst critic "
@@ -286,9 +294,8 @@ def test_full_update_split_gradients_match_fp64_autograd(kind, head_scale, preci
     assert abs(st[1] - st_ref["value_loss"]) < BAR * max(1, abs(st_ref["value_loss"]))
     assert abs(st[2] - st_ref["entropy"]) < BAR * max(1, abs(st_ref["entropy"]))
     assert d_lp < BAR * float(lp64.abs().mean()) and d_v < BAR * max(1.0, float(v64.abs().max()))
-    assert worst_c < (BAR if precision == "split" else 2e-4), forced
-    easy = max(v for k, v in forced.items() if k.startswith("actor") and k != "actor.head.psi_irrep")
-    assert easy < (1e-3 if head_scale == 0.1 else (2e-4 if kind == "plain" or precision == "split3" else BAR)) and worst_a < 3e-3, forced
+    assert worst_c < BAR, forced
+    assert worst_a < (3e-4 if (kind == "plain" and precision == "split") else BAR), forced
 
     # ---- (b) the oracle's own routing in float64 and in float32: flips and what they cost
     own64 = {"actor": [], "critic": []}
@@ -307,10 +314,10 @@ def test_full_update_split_gradients_match_fp64_autograd(kind, head_scale, preci
     print("   own-routing gradient error vs float64: device worst %.2e (median %.2e); torch fp32 CPU worst %.2e (median %.2e)" %
           (max(free_dev.values()), sorted(free_dev.values())[len(free_dev) // 2], max(free_f32.values()),
            sorted(free_f32.values())[len(free_f32) // 2]))
-    assert flips_dev <= max(400, 100 * max(flips_f32, 1)), (flips_dev, flips_f32)
+    assert flips_dev <= (max(20, 4 * max(flips_f32, 1)) if precision == "fp32" else max(400, 100 * max(flips_f32, 1))), (flips_dev, flips_f32)
     assert max(free_dev.values()) < 5e-2, free_dev
 
-    if kind != "equiv" or precision != "split":
+    if kind != "equiv" or precision != "fp32":
         return
     # one Adam step on these gradients (actor-only clip, robot_ppo.py:401-402)
     before = {k: v.clone() for k, v in params.items()}

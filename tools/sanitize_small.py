@@ -62,8 +62,8 @@ def cnn_families(split):
     action = torch.randn(B, 5, generator=g, device="cuda")
     adv, ret, vold = (torch.randn(B, generator=g, device="cuda") for _ in range(3))
     oldlp = torch.full((B,), -7.0, device="cuda")
-    for make in (lambda: equiv.EquivActorCritic(equiv.init_params(seed=0), B, precision=('split' if split else 'bf16')),
-                 lambda: plain_cnn.PlainActorCritic(plain_cnn.init_params(seed=0), B, precision=('split' if split else 'bf16'))):
+    for make in (lambda: equiv.EquivActorCritic(equiv.init_params(seed=0), B, precision=('fp32' if split else 'bf16')),
+                 lambda: plain_cnn.PlainActorCritic(plain_cnn.init_params(seed=0), B, precision=('fp32' if split else 'bf16'))):
         model = make()
         model.update(state, obs, action, oldlp, adv, ret, vold)
         torch.cuda.synchronize()
