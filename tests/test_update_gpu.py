@@ -29,9 +29,18 @@ def _flat_grads(names, grads):
     return flat_from_named({n: g for n, g in zip(names, grads)})
 
 
-def _grad_close(got, want, rtol=1e-4):
-    # relative to the gradient's scale per tensor-sized block: elementwise rtol plus a floor at 1e-4 * max|g|
+def _grad_close(got, want, rtol=1e-4, what=""):
+    """north_star's "gradients within 1e-4 relative", read as: every entry within rtol * (|entry| + max|g|) - small entries
+    are held to 1e-4 of the gradient's SCALE, not of themselves (an entry 1e6 times smaller than its neighbours carries
+    their rounding).  What that leaves open is measured and bounded too: over the entries that matter (above 1e-3 of the
+    scale) the largest ELEMENTWISE relative error must stay below 1e-3, and the relative L2 error of the whole gradient
+    below 1e-4."""
     np.testing.assert_allclose(got, want, rtol=rtol, atol=rtol * float(np.abs(want).max()) + 1e-9)
+    big = np.abs(want) > 1e-3 * float(np.abs(want).max())
+    worst = float((np.abs(got - want)[big] / np.abs(want)[big]).max())
+    l2 = float(np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want))
+    print(f"{what} gradient: relative L2 {l2:.1e}, max elementwise relative error over |g| > 1e-3 max|g|: {worst:.1e} ({int(big.sum())} entries)")
+    assert l2 < 1e-4 and worst < 1e-3, (l2, worst)
 
 
 @pytest.mark.parametrize("tag", ["disc", "disc_big", "cont", "disc_nonorm", "disc_novclip"])
@@ -54,7 +63,7 @@ def test_update_matches_reference_golden(golden_dir, tag):
                         clip_vloss=bool(clip_vloss)).clone()
         stats = up.apply(lr, mgn).cpu().numpy()
         want_g = flat_from_named({n: g[f"{tag}_s{step}_g_{n}"] for n in names})
-        _grad_close(grads[:up.P].cpu().numpy(), want_g)
+        _grad_close(grads[:up.P].cpu().numpy(), want_g, what=f"{tag} step {step}")
         want = g[f"{tag}_s{step}_stats"]    # policy, value, entropy, loss, old_kl, kl, clipfrac, gnorm
         got = [stats[0], stats[1], stats[2], stats[7], stats[3], stats[4], stats[5], stats[6]]
         np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-6)
@@ -212,6 +221,9 @@ def test_full_size_minibatch_properties():
         P = policy_p = kernels.policy_param_count(desc)
         gt, gs = out["tc"][:P].cpu().numpy(), out["simt"][:P].cpu().numpy()
         np.testing.assert_allclose(gt, gs, rtol=1e-4, atol=1e-4 * float(np.abs(gs).max()))
+        l2 = float(np.linalg.norm(gt.astype(np.float64) - gs) / np.linalg.norm(gs))
+        print(f"2.1 M-sample minibatch, tcgen05 vs SIMT fp32 kernel: relative L2 {l2:.1e}")
+        assert l2 < 1e-4          # includes the tensor core's truncating accumulator over 110 tiles per CTA
         np.testing.assert_allclose(out["tc"][P:P + 6].cpu().numpy(), out["simt"][P:P + 6].cpu().numpy(), rtol=1e-4)
     finally:
         L.aur_ppo_update_set_impl(prev)

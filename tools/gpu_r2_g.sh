@@ -8,7 +8,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 300 python tools/profile_target.py > $O/target_plain.log 2>&1; echo "target rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ppo_grad_tc|gae_bulk|rollout_tc|critic_values_tc|adv_moments_multi|grad_reduce|adam_kernel" -c 24 -o $O/mlp_full python tools/profile_target.py > $O/ncu_mlp.log 2>&1; echo "mlp full rc=$?"
 EQUIV_B=1024 timeout 300 python tools/profile_equiv.py > $O/equiv_plain.log 2>&1; echo "equiv target rc=$?"
-EQUIV_B=1024 timeout 1200 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/equiv_split_kernels.csv python tools/profile_equiv.py > $O/ncu_equiv.log 2>&1; echo "equiv list rc=$?"
+EQUIV_B=1024 EQUIV_PRECISION=fp32 timeout 1200 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/equiv_fp32_kernels.csv python tools/profile_equiv.py > $O/ncu_equiv.log 2>&1; echo "equiv list rc=$?"
 EQUIV_B=1024 EQUIV_PRECISION=bf16 timeout 1200 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/equiv_bf16_kernels.csv python tools/profile_equiv.py > $O/ncu_equiv_bf16.log 2>&1; echo "equiv bf16 list rc=$?"
-EQUIV_B=256 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_igemm|wgrad3x3" -c 12 -o $O/equiv_full python tools/profile_equiv.py > $O/ncu_equiv_full.log 2>&1; echo "equiv full rc=$?"
+EQUIV_B=256 EQUIV_PRECISION=fp32 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_igemm|wgrad3x3" -c 12 -o $O/equiv_full python tools/profile_equiv.py > $O/ncu_equiv_full.log 2>&1; echo "equiv full rc=$?"
 ls -la $O
