@@ -255,7 +255,8 @@ typedef struct {
   const float* params;       /* flat parameter buffer */
   float clip_coeff, entropy_coeff, value_coeff, _pad2;
   const double* adv_moments; /* [3] device: sum, sum of squares, count over the WHOLE minibatch; NULL iff !norm_adv */
-  float* workspace;          /* >= aur_ppo_update_workspace_bytes() */
+  float* workspace;          /* >= aur_ppo_update_workspace_bytes(); contents need NOT be initialised (the last-CTA tickets of
+                                the reductions live in a library-owned allocation per (device, stream)) */
   float* grads_out;          /* [P + 16] */
   const aur_dp_ctx* dp;      /* NULL: single GPU */
   uint32_t dp_seq;
