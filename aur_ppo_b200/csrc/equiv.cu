@@ -125,6 +125,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
       int b0, y0, x0, n0;
       decode(item, b0, y0, x0, n0);
+      if constexpr (CHUNKED) {
+        // multi-plane: ONE super-stage per (tap, channel chunk) holds every plane of both operands (P x (A + B) tiles in P
+        // consecutive ring slots), and all the plane products are issued from it - each tile is fetched once instead of once
+        // per product (12 -> 6 tile loads per six-product step)
+        const int P = a.planes, SUPER = CV_STAGES / P;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap - 3 * dy;
+          for (int cc = 0; cc < cchunks; ++cc, ++kg) {
+            const int u = kg % SUPER;
+            const uint32_t ph = (kg / SUPER) & 1u;
+            mbar_wait(&empty[u], ph ^ 1u);
+            mbar_arrive_expect_tx(&full[u], P * (CV_A_BYTES + CV_B_BYTES));
+            for (int pl = 0; pl < P; ++pl) {
+              tma_load_5d(sA + (u * P + pl) * CV_A_BYTES, &tmA, cc * CV_BK, x0 + dx, y0 + dy, b0, pl, &full[u]);
+              tma_load_3d(sB + (u * P + pl) * CV_B_BYTES, &tmB, tap * a.Cin + cc * CV_BK, n0, pl, &full[u]);
+            }
+          }
+        }
+        continue;
+      }
       for (int tap = 0; tap < 9; ++tap) {
         const int dy = tap / 3, dx = tap - 3 * dy;
         for (int cc = 0; cc < cchunks; ++cc) {
@@ -147,8 +167,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (blockIdx.x < items) { mbar_wait(bres, 0u); fence_after_sync(); }
     }
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-      // one accumulator hand-over per work item, or (CHUNKED) per CV_CHUNK stages; `it` counts hand-overs across items
-      const int span = CHUNKED ? CV_CHUNK : nkb;
+      if constexpr (CHUNKED) {
+        // super-stages (see the producer); an accumulator hand-over every `span` of them (~32-48 MMA steps)
+        const int P = a.planes, SUPER = CV_STAGES / P, nks = 9 * cchunks, span = (CV_CHUNK + a.nterm - 1) / a.nterm;
+        for (int ks0 = 0; ks0 < nks; ks0 += span, ++it) {
+          const uint32_t acc = it & 1u;
+          mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
+          fence_after_sync();
+          const int ks1 = ks0 + span < nks ? ks0 + span : nks;
+          for (int ks = ks0; ks < ks1; ++ks, ++kg) {
+            const int u = kg % SUPER;
+            const uint32_t ph = (kg / SUPER) & 1u;
+            mbar_wait(&full[u], ph);
+            fence_after_sync();
+            for (int term = 0; term < a.nterm; ++term) {
+              const uint64_t ad = smem_desc_k_sw128(sA + (u * P + term_plane_a(term)) * CV_A_BYTES);
+              const uint64_t bd = smem_desc_k_sw128(sB + (u * P + term_plane_b(term)) * CV_B_BYTES);
+#pragma unroll
+              for (int k = 0; k < CV_BK / 16; ++k)
+                mma_f16(tmem_d + acc * CV_BN, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, ((ks - ks0) | term | k) != 0);
+            }
+            mma_commit(&empty[u]);
+          }
+          mma_commit(&tmem_full[acc]);
+        }
+        continue;
+      }
+      // one accumulator hand-over per work item; `it` counts hand-overs across items
+      const int span = nkb;
       for (int kb0 = 0; kb0 < nkb; kb0 += span, ++it) {
         const uint32_t acc = it & 1u;
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
@@ -240,7 +286,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc = it & 1u;
     if constexpr (CHUNKED) {
       // promote every finished chunk of this item into the register accumulators (fp32 round-to-nearest adds)
-      for (int kb0 = 0; kb0 < nkb; kb0 += CV_CHUNK, ++it) {
+      const int nks = 9 * cchunks, span = (CV_CHUNK + a.nterm - 1) / a.nterm;     // as the MMA warp counts them
+      for (int kb0 = 0; kb0 < nks; kb0 += span, ++it) {
         acc = it & 1u;
         mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
         fence_after_sync();
