@@ -657,6 +657,9 @@ __global__ void __launch_bounds__(1024) adam_kernel(int64_t P, float* __restrict
       w[0] += (unsigned long long)(global_timer_ns() - t_in);
       w[1] += 1ull;
     }
+    // a wait gave up (a peer is gone): the sums are incomplete - do NOT step the parameters on them; the status word stays set
+    // and the host raises on every rank (ppo.train checks it once per update)
+    if (*reinterpret_cast<volatile uint32_t*>(me + DP_OFF_STATUS) != 0u) return;
     const int gs = dp_grad_stride(P);
     const float* rg = reinterpret_cast<const float*>(me + DP_OFF_GRAD) + (size_t)(dp.seq & 1u) * DP_MAX * gs;
     for (int64_t i = threadIdx.x; i < P + AUR_NUM_STATS; i += blockDim.x) {

@@ -105,9 +105,39 @@ class EquivActorCritic:
         self.B = batch
         self.enc = {"actor": _Enc(batch, self.dev, self.CH, self.FEAT, self.P),
                     "critic": _Enc(batch, self.dev, self.CH, self.FEAT, self.P)}
-        self.grads = {k: torch.zeros_like(v) for k, v in params.items()}
-        self.m1 = {k: torch.zeros_like(v) for k, v in params.items()}
-        self.m2 = {k: torch.zeros_like(v) for k, v in params.items()}
+        # ONE flat fp32 buffer each for parameters, gradients and the Adam moments, clipped group (`actor.*`, robot_ppo.py:401)
+        # first: the clip norm is one launch and Adam two, instead of one per tensor.  The caller's tensors keep their identity -
+        # their storage is re-pointed into the flat buffer (as actor_critic.flat_parameters does), so a module sharing them
+        # (models.robot_actor_critic) sees every update.
+        keys = [k for k in params if k.startswith("actor.")] + [k for k in params if not k.startswith("actor.")]
+        total = sum(params[k].numel() for k in keys)
+        self._n_clip = sum(params[k].numel() for k in keys if k.startswith("actor."))
+        self._flat = {name: torch.zeros(total, device=self.dev) for name in ("g", "m1", "m2")}
+        # (a second engine over the same tensors - another batch size - finds them already laid out and shares the buffer)
+        first, o, laid_out = params[keys[0]], 0, True
+        for k in keys:
+            v = params[k]
+            if v.dtype != torch.float32:
+                raise _lib.AurError(f"parameter {k} must be float32")
+            laid_out = laid_out and v.is_contiguous() and v.data_ptr() == first.data_ptr() + 4 * o and \
+                v.untyped_storage().data_ptr() == first.untyped_storage().data_ptr()
+            o += v.numel()
+        if laid_out and first.untyped_storage().nbytes() >= 4 * (first.storage_offset() + total):
+            self._flat["p"] = torch.empty(0, device=self.dev).set_(first.untyped_storage(), first.storage_offset(), (total,))
+        else:
+            self._flat["p"] = torch.zeros(total, device=self.dev)
+            laid_out = False
+        self.grads, self.m1, self.m2 = {}, {}, {}
+        o = 0
+        for k in keys:
+            v, n = params[k], params[k].numel()
+            if not laid_out:
+                self._flat["p"][o:o + n].copy_(v.detach().reshape(-1))
+                v.data = self._flat["p"][o:o + n].view(v.shape)
+            self.grads[k] = self._flat["g"][o:o + n].view(v.shape)
+            self.m1[k] = self._flat["m1"][o:o + n].view(v.shape)
+            self.m2[k] = self._flat["m2"][o:o + n].view(v.shape)
+            o += n
         self.lr, self.eps, self.betas, self.step_count = lr, eps, betas, 0
         self.stats = torch.zeros(8, device=self.dev)
         self.d_head = torch.zeros(self.D_HEAD, device=self.dev)
@@ -323,8 +353,7 @@ class EquivActorCritic:
                         clip_vloss) -> torch.Tensor:
         L = _lib.lib()
         B = self.B
-        for g in self.grads.values():
-            g.zero_()
+        self._flat["g"].zero_()
         self.stats.zero_(); self.d_head.zero_()
         a_out, c_pre = self._forward(state, obs)
         if norm_adv:
@@ -374,15 +403,16 @@ class EquivActorCritic:
         self.step_count += 1
         lr = self.lr if lr is None else lr
         self.sumsq.zero_()
+        F, nc = self._flat, self._n_clip
+        nr = F["p"].numel() - nc
         with torch.cuda.device(self.dev):
-            for k, g in self.grads.items():
-                if k.startswith("actor."):
-                    _chk(L.aur_sumsq_f32(g.numel(), g.data_ptr(), self.sumsq.data_ptr(), _stream()), "aur_sumsq_f32")
-            for k, p in self.p.items():
-                clip = self.sumsq.data_ptr() if k.startswith("actor.") else None
-                _chk(L.aur_adam_flat(p.numel(), p.data_ptr(), self.grads[k].data_ptr(), self.m1[k].data_ptr(), self.m2[k].data_ptr(),
-                                     lr, self.betas[0], self.betas[1], self.eps, self.step_count, clip, max_grad_norm, _stream()),
-                     "aur_adam_flat")
+            _chk(L.aur_sumsq_f32(nc, F["g"].data_ptr(), self.sumsq.data_ptr(), _stream()), "aur_sumsq_f32")
+            _chk(L.aur_adam_flat(nc, F["p"].data_ptr(), F["g"].data_ptr(), F["m1"].data_ptr(), F["m2"].data_ptr(), lr, self.betas[0],
+                                 self.betas[1], self.eps, self.step_count, self.sumsq.data_ptr(), max_grad_norm, _stream()), "aur_adam_flat")
+            if nr:
+                _chk(L.aur_adam_flat(nr, F["p"].data_ptr() + 4 * nc, F["g"].data_ptr() + 4 * nc, F["m1"].data_ptr() + 4 * nc,
+                                     F["m2"].data_ptr() + 4 * nc, lr, self.betas[0], self.betas[1], self.eps, self.step_count, None,
+                                     max_grad_norm, _stream()), "aur_adam_flat")
 
     def update(self, state, obs, action, oldlp, adv, ret, vold, lr=None, max_grad_norm=0.5, **kw) -> torch.Tensor:
         st = self.loss_and_grads(state, obs, action, oldlp, adv, ret, vold, **kw)

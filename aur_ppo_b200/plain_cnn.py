@@ -146,8 +146,7 @@ class PlainActorCritic(EquivActorCritic):
                         clip_vloss) -> torch.Tensor:
         L = _lib.lib()
         B = self.B
-        for g in self.grads.values():
-            g.zero_()
+        self._flat["g"].zero_()
         self.stats.zero_(); self.d_head.zero_()
         a_out, c_pre = self._forward(state, obs)
         if norm_adv:
@@ -184,19 +183,5 @@ class PlainActorCritic(EquivActorCritic):
         self._encoder_backward("critic", state, obs, dfc)
         return self.stats / B
 
-    def apply(self, lr: Optional[float] = None, max_grad_norm: float = 0.5):
-        """robot_ppo.py:401 clips `self.policy.actor.parameters()`: every actor.* tensor (actor_logstd is a parameter of the
-        policy module, not of `.actor`, so it is not clipped), then one Adam over everything."""
-        L = _lib.lib()
-        self.step_count += 1
-        lr = self.lr if lr is None else lr
-        self.sumsq.zero_()
-        with torch.cuda.device(self.dev):
-            for k, g in self.grads.items():
-                if k.startswith("actor."):
-                    _chk(L.aur_sumsq_f32(g.numel(), g.data_ptr(), self.sumsq.data_ptr(), _stream()), "aur_sumsq_f32")
-            for k, p in self.p.items():
-                clip = self.sumsq.data_ptr() if k.startswith("actor.") else None
-                _chk(L.aur_adam_flat(p.numel(), p.data_ptr(), self.grads[k].data_ptr(), self.m1[k].data_ptr(), self.m2[k].data_ptr(),
-                                     lr, self.betas[0], self.betas[1], self.eps, self.step_count, clip, max_grad_norm, _stream()),
-                     "aur_adam_flat")
+    # apply(): the base class - robot_ppo.py:401 clips `self.policy.actor.parameters()`, i.e. every actor.* tensor (actor_logstd
+    # is a parameter of the policy module, not of `.actor`, so it is not clipped), then one Adam over everything

@@ -152,6 +152,20 @@ class ppo:
             self.exchange.close()
             self.exchange = None
 
+    def _check_exchange(self) -> None:
+        """Data-parallel health check, once per update: if any rank's kernels gave up waiting for a peer (the Adam kernel then
+        skips its step), EVERY rank learns it here (one tiny all-reduce on the control plane) and raises after the collective
+        close, so no rank is left hanging at a barrier."""
+        if self.exchange is None:
+            return
+        bad = torch.tensor([float(self.exchange.status() != 0)])
+        if torch.distributed.get_backend() == "nccl":
+            bad = bad.to(self.device)
+        torch.distributed.all_reduce(bad, op=torch.distributed.ReduceOp.MAX)
+        if float(bad.item()) != 0.0:
+            self.close()
+            raise _lib.AurError("data-parallel exchange: a kernel timed out waiting for a peer rank (update skipped on every rank)")
+
     # ------------------------------------------------------------------ hot path pieces
     def make_env(self, gym_id, idx, capture_video):
         raise _lib.AurError("envs are device-resident here; there are no per-env gym thunks (src/ppo.py:85-99)")
@@ -251,6 +265,7 @@ class ppo:
         for update in range(1, self.num_updates + 1):
             step_base = self._env_step
             out = self.run_update(update)
+            self._check_exchange()
             # ---- episodic statistics (ppo.py:114-122): the first finished env of each step
             ts, _, rets, lens = self.envs.first_finished_episodes()
             gss = (step_base + ts + 1) * self.num_envs
@@ -284,8 +299,6 @@ class ppo:
                 writer.add_scalar("charts/SPS", int(global_step / (time.time() - start_time)), global_step)
 
         self.envs.close()
-        if self.exchange is not None and self.exchange.status() != 0:
-            raise _lib.AurError("data-parallel exchange: a kernel timed out waiting for a peer rank")
         self.close()
         if writer is not None:
             writer.close()
