@@ -42,7 +42,9 @@ class _PsiNet(nn.Module):
                 self._keys.append((k, name))
 
     def tensors(self) -> Dict[str, torch.Tensor]:
-        return {k: getattr(self, name).data for k, name in self._keys}
+        """The Parameters themselves (requires_grad = False): the update engine re-points their storage into its flat
+        parameter buffer (EquivActorCritic.__init__), so the objects must be the module's own, not `.data` aliases."""
+        return {k: getattr(self, name) for k, name in self._keys}
 
 
 class robot_actor_critic(nn.Module):
