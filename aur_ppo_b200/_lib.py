@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("AUR_LIB_PATH", os.path.join(_PKG, "libaurppo.so"))
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "aur_ppo.h")
 
 _lib = None
+ABI_VERSION = 2          # AUR_ABI_VERSION of include/aur_ppo.h
 
 
 class PolicyDesc(ctypes.Structure):
@@ -93,7 +94,8 @@ class AurError(RuntimeError):
 
 def build(verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into aur_ppo_b200/libaurppo.so (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", os.path.join(_PKG, "csrc")], capture_output=True, text=True)
+    jobs = str(max(1, min(os.cpu_count() or 1, 8)))          # ~3.5 min serial, ~1 min on 8 cores
+    r = subprocess.run(["make", "-j", jobs, "-C", os.path.join(_PKG, "csrc")], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout[-4000:])
         print(r.stderr[-4000:])
@@ -118,6 +120,9 @@ def lib() -> ctypes.CDLL:
                        "fallback (run __graft_entry__.build())")
     L = ctypes.CDLL(LIB_PATH)
     L.aur_abi_version.restype = c_int
+    if L.aur_abi_version() != ABI_VERSION:
+        raise AurError(f"{LIB_PATH} has ABI version {L.aur_abi_version()}, this package binds version {ABI_VERSION}: rebuild it "
+                       "(run __graft_entry__.build())")
     L.aur_last_error.restype = c_char_p
     L.aur_launch_count.restype = c_int64
     L.aur_launch_count_reset.restype = None

@@ -40,6 +40,7 @@ struct ConvDev {
   int oHb, oWb, ooff;                      // output buffer geometry
   int nterm;                               // K-step terms per (tap, channel chunk): 1 / 3 / 6 for 1 / 2 / 3 operand planes (tc.cuh)
   int planes;                              // planes of the output stack
+  int chunk;                               // CHUNKED kernels: MMA groups (4 steps each) per promoted accumulator chunk
   size_t out_plane;                        // elements between the output planes
   const float* bias;
   __nv_bfloat16* out;
@@ -169,7 +170,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
       if constexpr (CHUNKED) {
         // super-stages (see the producer); an accumulator hand-over every `span` of them (~32-48 MMA steps)
-        const int P = a.planes, SUPER = CV_STAGES / P, nks = 9 * cchunks, span = (CV_CHUNK + a.nterm - 1) / a.nterm;
+        const int P = a.planes, SUPER = CV_STAGES / P, nks = 9 * cchunks, span = (a.chunk + a.nterm - 1) / a.nterm;
         for (int ks0 = 0; ks0 < nks; ks0 += span, ++it) {
           const uint32_t acc = it & 1u;
           mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
@@ -286,7 +287,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc = it & 1u;
     if constexpr (CHUNKED) {
       // promote every finished chunk of this item into the register accumulators (fp32 round-to-nearest adds)
-      const int nks = 9 * cchunks, span = (CV_CHUNK + a.nterm - 1) / a.nterm;     // as the MMA warp counts them
+      const int nks = 9 * cchunks, span = (a.chunk + a.nterm - 1) / a.nterm;     // as the MMA warp counts them
       for (int kb0 = 0; kb0 < nks; kb0 += span, ++it) {
         acc = it & 1u;
         mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
@@ -591,6 +592,11 @@ extern "C" int aur_conv3x3_bf16(const aur_conv_args* args, void* stream) {
   const int P = tc_planes();
   d.nterm = tc_terms(P);
   d.planes = P;
+  {
+    static int chunk = -1;                 // AUR_CONV_CHUNK: MMA groups per promoted chunk (default CV_CHUNK = 8 -> 32..48 steps)
+    if (chunk < 0) { const char* e = getenv("AUR_CONV_CHUNK"); chunk = e ? atoi(e) : CV_CHUNK; if (chunk < 1) chunk = CV_CHUNK; }
+    d.chunk = chunk;
+  }
   d.out_plane = (size_t)c.B * c.out_Hb * c.out_Wb * c.Cout;
   d.out = (__nv_bfloat16*)c.out; d.pool_arg = c.pool_arg; d.relu_ref = (const __nv_bfloat16*)c.relu_ref; d.rHb = c.ref_Hb; d.rWb = c.ref_Wb; d.roff = c.ref_off;
   if (c.epilogue == 3 && !c.relu_ref) { set_error("aur_conv3x3_bf16: epilogue 3 needs relu_ref"); return AUR_ERR_ARG; }

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define AUR_ABI_VERSION 1
+#define AUR_ABI_VERSION 2   /* 2: operand-plane precision modes, aur_update_args.mom_index / mom_seq, library-owned tickets */
 #define AUR_ERR_ARG (-1)
 #define AUR_ERR_UNSUPPORTED (-2)
 
