@@ -343,8 +343,10 @@ class EquivActorCritic:
 
     # ------------------------------------------------------------------- update
     def loss_and_grads(self, state, obs, action, oldlp, adv, ret, vold, clip_coeff=0.2, entropy_coeff=0.01,
-                       value_coeff=0.5, norm_adv=True, clip_vloss=True) -> torch.Tensor:
-        """Forward + loss + full backward; gradients land in self.grads.  Returns the stats tensor (means)."""
+                       value_coeff=0.5, norm_adv=True, clip_vloss=True, m_total: Optional[int] = None) -> torch.Tensor:
+        """Forward + loss + full backward; gradients land in self.grads.  Returns the stats tensor (means).
+        m_total: size of the whole minibatch this batch is a part of (means divide by it; default: this batch)."""
+        self._m_total = int(m_total) if m_total else self.B
         with tc_precision(self.P):
             return self._loss_and_grads(state, obs, action, oldlp, adv, ret, vold, clip_coeff, entropy_coeff, value_coeff,
                                         norm_adv, clip_vloss)
@@ -363,7 +365,7 @@ class EquivActorCritic:
         a_bias = self._a_bias
         a_bias[2:10].copy_(self.p["actor.head.bias_triv"])
         h = _lib.EquivHeadArgs()
-        h.B, h.clip_vloss, h.m_total = B, int(bool(clip_vloss)), B
+        h.B, h.clip_vloss, h.m_total = B, int(bool(clip_vloss)), getattr(self, "_m_total", B)
         h.a_out, h.a_bias, h.c_pre = a_out.data_ptr(), a_bias.data_ptr(), c_pre.data_ptr()
         h.c_bias1 = self._w["critic.head1"][2].data_ptr()
         w2 = self.p["critic.head2.w"].reshape(-1).contiguous()

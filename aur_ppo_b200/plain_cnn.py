@@ -154,7 +154,7 @@ class PlainActorCritic(EquivActorCritic):
         d_a_out = self._empty(B, 16)
         d_c_h = self._empty(B, 128)
         h = _lib.PlainHeadArgs()
-        h.B, h.clip_vloss, h.m_total = B, int(bool(clip_vloss)), B
+        h.B, h.clip_vloss, h.m_total = B, int(bool(clip_vloss)), getattr(self, "_m_total", B)
         h.a_out, h.a_bias, h.actor_logstd = a_out.data_ptr(), self.p["actor.mean_linear.bias"].data_ptr(), self.p["actor_logstd"].data_ptr()
         h.c_pre, h.c_bias1 = c_pre.data_ptr(), self._w["critic.head1"][2].data_ptr()
         w2 = self.p["critic.critic.2.weight"].reshape(-1).contiguous()

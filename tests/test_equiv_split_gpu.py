@@ -329,3 +329,44 @@ def test_full_update_split_gradients_match_fp64_autograd(kind, head_scale, preci
         step = (params[k] - before[k]).cpu()
         want = -3e-4 / (1 - 0.9) * (0.1 * gk) / ((0.001 * gk * gk).sqrt() / math.sqrt(1 - 0.999) + 1e-5)
         torch.testing.assert_close(step, want, rtol=1e-4, atol=2e-8)      # (params - before) is quantised at ulp(param) ~ 4e-9
+
+
+def test_config_d_full_minibatch_properties():
+    """BASELINE config D at its full size (minibatch 4096, two-plane mode to bound memory) through size-independent properties:
+    (1) a sample's log-prob / value do not depend on what else is in the batch: samples 0..7 of the 4096 match the float64
+    oracle evaluated on those 8 alone; (2) gradient sums are additive over a split of the minibatch (checksum of checksums):
+    grads(4096) == grads(first 2048) + grads(last 2048) with the same 1 / 4096 seeds (advantage normalisation off so that the
+    halves share nothing but the weights) - this also exercises the weight-gradient accumulation at 17.8 M pixel rows."""
+    from aur_ppo_b200 import equiv
+    B = 4096
+    params = equiv.init_params(seed=5, scale=1.1)
+    for k in ("actor.head.psi_triv", "actor.head.psi_irrep", "critic.head2.w"):
+        params[k].mul_(0.02)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    obs = torch.rand(B, 1, 128, 128, generator=g, device="cuda") * 0.32
+    state = (torch.rand(B, generator=g, device="cuda") > 0.5).float()
+    action = torch.randn(B, 5, generator=g, device="cuda")
+    adv, ret, vold = (torch.randn(B, generator=g, device="cuda") for _ in range(3))
+    oldlp = -6.4 + 0.2 * torch.randn(B, generator=g, device="cuda")        # around the new log-probs: ratios on both sides of the clip
+    p32 = {k: v.detach().cpu().clone() for k, v in params.items()}
+    kw = dict(norm_adv=False)
+    whole = equiv.EquivActorCritic(params, B, precision="split")
+    whole.loss_and_grads(state, obs, action, oldlp, adv, ret, vold, **kw)
+    lp_dev, v_dev = whole.logp[:8].cpu().double(), whole.value[:8].cpu().double()
+    g_whole = {k: v.clone() for k, v in whole.grads.items()}
+    del whole
+    torch.cuda.empty_cache()
+    p64 = {k: v.double() for k, v in p32.items()}
+    with torch.no_grad():
+        lp64, _, v64 = Q.evaluate(p64, state[:8].cpu().double(), obs[:8].cpu().double(), action[:8].cpu().double())
+    assert float((lp_dev - lp64).abs().max()) < BAR * float(lp64.abs().mean()), (lp_dev, lp64)
+    assert float((v_dev - v64).abs().max()) < BAR * max(1.0, float(v64.abs().max()))
+    half = equiv.EquivActorCritic(params, B // 2, precision="split")
+    acc = {k: torch.zeros_like(v) for k, v in g_whole.items()}
+    for sl in (slice(0, B // 2), slice(B // 2, B)):
+        half.loss_and_grads(*(t[sl].contiguous() for t in (state, obs, action, oldlp, adv, ret, vold)), m_total=B, **kw)
+        for k in acc:
+            acc[k] += half.grads[k]
+    worst = {k: _rel(acc[k].cpu(), g_whole[k].cpu()) for k in acc}
+    print("config D additivity over halves, worst relative L2:", max(worst.values()))
+    assert max(worst.values()) < BAR, worst
