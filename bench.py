@@ -31,6 +31,8 @@ METRIC = "env_steps_per_s"
 UNIT = "env-steps/s"
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # nominal: 148 SMs x 128 FMA lanes x 2 flop x max SM clock (context, not a measured roofline)
 CPU_SAMPLE_ENVS = {"ppo": 1024, "pendulum": 256, "scale1m": 1024}   # the CPU arm steps a bounded sample of the workload (see reference_arm_note)
+if os.environ.get("AUR_BENCH_CPU_ENVS"):                              # tests shrink the sample (tests/test_bench_contract.py)
+    CPU_SAMPLE_ENVS = {k: int(os.environ["AUR_BENCH_CPU_ENVS"]) for k in CPU_SAMPLE_ENVS}
 
 WORKLOADS = {
     "ppo": dict(gym_id="CartPole-v1", continuous=False, T=128, nm=4, epochs=4, envs_per_gpu=65536, total_envs=None,
