@@ -511,9 +511,43 @@ def run_ours(args):
                     "what": "per step: H2D policy parameters from pinned memory -> ppo.run_update() -> D2H updated "
                             "parameters, per-minibatch statistics, finished-episode log; env state stays in HBM"},
             "gpu_launches": launches, "clocks": clocks}
+    if n_gpus == 1 and name == "ppo" and not args.no_extras:
+        line["other_workloads"] = other_workloads(args)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_workloads(args):
+    """The other BASELINE configs, measured in the SAME default run (N = 1 only) so that they are driver-run numbers too: each
+    is this script in a child process (own CUDA context, the parent has released its memory) with a short step count; its
+    JSON line is condensed into one entry.  The headline `value` is computed before any of this starts."""
+    import subprocess
+    runs = [("pendulum", ["--workload", "pendulum", "--steps", "3"]),
+            ("scale1m", ["--workload", "scale1m", "--steps", "3"]),
+            ("equiv_fp32", ["--workload", "equiv", "--precision", "fp32", "--steps", "3"]),
+            ("equiv_bf16", ["--workload", "equiv", "--precision", "bf16", "--steps", "5"]),
+            ("cnn_fp32", ["--workload", "cnn", "--precision", "fp32", "--steps", "3"])]
+    out = {}
+    for tag, extra in runs:
+        t0 = time.perf_counter()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--gpus", "1", "--warmup", "3", "--no-cpu-baseline", "--no-extras"] + extra,
+                               capture_output=True, text=True, timeout=420)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            e = {k: d.get(k) for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "dtype", "precision", "scaling", "phase_ms",
+                                       "rollout_env_steps_per_s", "update_samples_per_s", "gae_frac_of_hbm_peak", "gpu_launches", "clocks")
+                 if d.get(k) is not None}
+            e["workload"] = d["config"]["workload"]
+            e["e2e"] = {k: d["e2e"].get(k) for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+            e["roofline"] = {k: d["roofline"].get(k) for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "issued_tflops") if k in d["roofline"]}
+            if tag == "scale1m":
+                e["gae_sweep"] = [{"kernel": x["kernel"], "GBps": x["achieved"], "frac": x["frac"], "ms": x["ms"]} for x in d.get("rooflines", [])[3:]]
+            e["wall_s"] = round(time.perf_counter() - t0, 1)
+            out[tag] = e
+        except Exception as ex:      # never let a side measurement take the headline line down
+            out[tag] = {"error": repr(ex)[:300]}
+    return out
 
 
 def equiv_config(plain):
@@ -682,6 +716,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-extras", dest="no_extras", action="store_true",
+                    help="default N = 1 run only: skip the short side measurements of the other BASELINE configs (other_workloads)")
     ap.add_argument("--workload", type=str, default="ppo", choices=["ppo", "pendulum", "scale1m", "equiv", "cnn"],
                     help="ppo = BASELINE configs[1] (default, the headline line); pendulum = configs[2]; scale1m = configs[4] "
                          "(1M envs over the GPUs + GAE sweep); equiv = configs[3]; cnn = its plain-CNN sibling")
