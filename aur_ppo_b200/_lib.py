@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("AUR_LIB_PATH", os.path.join(_PKG, "libaurppo.so"))
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "aur_ppo.h")
 
 _lib = None
-ABI_VERSION = 2          # AUR_ABI_VERSION of include/aur_ppo.h
+ABI_VERSION = 3          # AUR_ABI_VERSION of include/aur_ppo.h
 
 
 class PolicyDesc(ctypes.Structure):
@@ -189,6 +189,9 @@ def lib() -> ctypes.CDLL:
     L.aur_ppo_update_set_impl.restype = c_int
     L.aur_ppo_update_set_impl.argtypes = [c_int]
     L.aur_ppo_update_get_impl.restype = c_int
+    L.aur_ppo_update_set_wide.restype = c_int
+    L.aur_ppo_update_set_wide.argtypes = [c_int]
+    L.aur_ppo_update_get_wide.restype = c_int
     L.aur_ppo_update_apply.restype = c_int
     L.aur_ppo_update_apply.argtypes = [ctypes.POINTER(PolicyDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                        c_double, c_double, c_double, c_int64, c_double, c_int64, c_double, c_double,

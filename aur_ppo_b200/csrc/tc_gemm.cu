@@ -158,15 +158,16 @@ extern "C" int aur_tc_set_precision(int planes) {
 }
 extern "C" int aur_tc_get_precision(void) { return aur::tc::g_tc_planes; }
 
-extern "C" int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, const void* B, float* C, void* stream) {
-  using namespace aur;
-  using namespace aur::tc;
-  const int P = tc_planes();
-  if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) { set_error("aur_tc_gemm_bf16: bad arguments"); return AUR_ERR_ARG; }
-  if (K % 8 != 0) { set_error("aur_tc_gemm_bf16: K must be a multiple of 8 (16-byte row pitch for TMA)"); return AUR_ERR_UNSUPPORTED; }
+namespace aur {
+namespace tc {
+// C[M,N] (fp32, row stride ldc) = A[M,K] * B[N,K]^T for operand stacks of `planes` bf16 planes, a_plane / b_plane ELEMENTS apart
+// (the internal form of aur_tc_gemm_bf16: explicit precision and plane strides; update_wide.cu runs sub-batches out of larger buffers)
+int launch_tc_gemm(int64_t M, int64_t N, int64_t K, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int ldc,
+                   int planes, cudaStream_t stream) {
+  const int P = planes;
   CUtensorMap tmA, tmB;
   const uint64_t dA[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)P}, dB[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)P};
-  const uint64_t stA[2] = {(uint64_t)K * 2, (uint64_t)K * M * 2}, stB[2] = {(uint64_t)K * 2, (uint64_t)K * N * 2};
+  const uint64_t stA[2] = {(uint64_t)K * 2, (uint64_t)a_plane * 2}, stB[2] = {(uint64_t)K * 2, (uint64_t)b_plane * 2};
   const uint32_t boxA[3] = {GEMM_BK, GEMM_BM, 1}, boxB[3] = {GEMM_BK, GEMM_BN, 1};
   int rc;
   if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, A, dA, stA, boxA))) return rc;
@@ -177,10 +178,18 @@ extern "C" int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, 
     attr.done();
   }
   dim3 grid((unsigned)((M + GEMM_BM - 1) / GEMM_BM), (unsigned)((N + GEMM_BN - 1) / GEMM_BN));
-  tc_gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, C, (int)M, (int)N, (int)K, (int)N, tc_terms(P),
-                                                                         P > 1 ? 8 : 0);
+  tc_gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tmA, tmB, C, (int)M, (int)N, (int)K, ldc, tc_terms(P), P > 1 ? 8 : 0);
   AUR_LAUNCH_OK("tc_gemm_bf16_kernel");
   return 0;
+}
+}  // namespace tc
+}  // namespace aur
+
+extern "C" int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, const void* B, float* C, void* stream) {
+  using namespace aur;
+  if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) { set_error("aur_tc_gemm_bf16: bad arguments"); return AUR_ERR_ARG; }
+  if (K % 8 != 0) { set_error("aur_tc_gemm_bf16: K must be a multiple of 8 (16-byte row pitch for TMA)"); return AUR_ERR_UNSUPPORTED; }
+  return tc::launch_tc_gemm(M, N, K, A, (size_t)K * M, B, (size_t)K * N, C, (int)N, tc::tc_planes(), (cudaStream_t)stream);
 }
 
 // Debug/diagnostic: shared-window offset at which dynamic shared memory starts (the first 1 KB of the

@@ -734,6 +734,12 @@ int check_generic_policy(const aur_policy_desc& p, const char* who);
 size_t gen_workspace_floats(const aur_policy_desc& p);
 int gen_pstride(const aur_policy_desc& p);
 int launch_ppo_grad_generic(const UpdDev& d, const aur_policy_desc& p, float* ws, int* gx_out, float** part_out, cudaStream_t s);
+// update_wide.cu: hidden 128 / 256 layer by layer on tensor cores
+bool wide_eligible(const aur_policy_desc& p);
+size_t wide_workspace_bytes(const aur_policy_desc& p);
+int update_wide_enabled();
+void set_update_wide(int on);
+int launch_ppo_grad_wide(const UpdDev& d, const aur_policy_desc& p, float* ws, int* gx_out, float** part_out, cudaStream_t s);
 
 static bool is_headline_shape(const aur_policy_desc& p) {
   return p.hidden_dim == 64 && p.num_layers == 2 && p.obs_dim >= 1 && p.obs_dim <= POL_IN_PAD && p.act_dim >= 1 &&
@@ -751,7 +757,7 @@ extern "C" int64_t aur_ppo_update_workspace_bytes(const aur_policy_desc* desc) {
   int rc = aur::check_update_policy(*desc, "aur_ppo_update_workspace_bytes");
   if (rc) return rc;
   // [specialised kernels' partials | moments partials | tickets] then the generic kernel's staged parameters + slabs
-  return (int64_t)(aur::ws_bytes() + aur::gen_workspace_floats(*desc) * sizeof(float));
+  return (int64_t)(aur::ws_bytes() + aur::gen_workspace_floats(*desc) * sizeof(float) + aur::wide_workspace_bytes(*desc));
 }
 
 namespace aur {
@@ -824,6 +830,12 @@ extern "C" int aur_ppo_update_set_impl(int impl) {
   return 0;
 }
 extern "C" int aur_ppo_update_get_impl(void) { return aur::update_impl(); }
+extern "C" int aur_ppo_update_set_wide(int on) {
+  if (on != 0 && on != 1) { aur::set_error("aur_ppo_update_set_wide: 0 (shape-generic SIMT kernel) or 1 (layer-wise tensor-core path)"); return AUR_ERR_ARG; }
+  aur::set_update_wide(on);
+  return 0;
+}
+extern "C" int aur_ppo_update_get_wide(void) { return aur::update_wide_enabled(); }
 
 extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
   using namespace aur;
@@ -862,7 +874,12 @@ extern "C" int aur_ppo_update_grad(const aur_update_args* args, void* stream) {
   const int impl = is_headline_shape(u.policy) ? update_impl() : 3;
   int gx, pstride = UPD_PSTRIDE;
   const float* partials = u.workspace;
-  if (impl == 3) {
+  if (impl == 3 && wide_eligible(u.policy) && update_wide_enabled()) {
+    float* part = nullptr;
+    int rc2 = launch_ppo_grad_wide(d, u.policy, u.workspace + ws_bytes() / sizeof(float) + gen_workspace_floats(u.policy), &gx, &part, s);
+    if (rc2) return rc2;
+    partials = part; pstride = gen_pstride(u.policy);
+  } else if (impl == 3) {
     float* part = nullptr;
     int rc2 = launch_ppo_grad_generic(d, u.policy, u.workspace + ws_bytes() / sizeof(float), &gx, &part, s);
     if (rc2) return rc2;

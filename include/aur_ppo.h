@@ -29,7 +29,8 @@
 extern "C" {
 #endif
 
-#define AUR_ABI_VERSION 2   /* 2: operand-plane precision modes, aur_update_args.mom_index / mom_seq, library-owned tickets */
+#define AUR_ABI_VERSION 3   /* 2: operand-plane precision modes, aur_update_args.mom_index / mom_seq, library-owned tickets;
+                               3: aur_ppo_update_set_wide (layer-wise tensor-core update for hidden 128 / 256) */
 #define AUR_ERR_ARG (-1)
 #define AUR_ERR_UNSUPPORTED (-2)
 
@@ -315,6 +316,12 @@ int aur_ppo_update_grad(const aur_update_args* args, void* stream);
  * initial choice. */
 int aur_ppo_update_set_impl(int impl);
 int aur_ppo_update_get_impl(void);
+/* `--hidden_dim` 128 / 256 with `--num_layers` >= 2 (src/run_ppo.py:36,38; obs_dim <= 8, act_dim <= 4): 1 (default) = the
+ * layer-wise tensor-core path (update_wide.cu: every H x H contraction of forward, backward-data and weight gradient is a
+ * tcgen05 GEMM over two-plane bf16 operands, activations of a 262,144-sample sub-batch staged in the workspace), 0 = the
+ * shape-generic SIMT kernel (kept as the cross-check).  AUR_UPDATE_WIDE=0|1 sets the initial choice. */
+int aur_ppo_update_set_wide(int on);
+int aur_ppo_update_get_wide(void);
 
 /* params / adam_m / adam_v: [P] fp32 updated in place (torch.optim.Adam single-tensor math, no
  * weight decay, no amsgrad).  step is the 1-based Adam step count.  stats_out [AUR_NUM_STATS]

@@ -24,7 +24,7 @@ def test_exports_every_declared_symbol(built):
 
 
 def test_abi_version_and_error_string(built):
-    assert built.aur_abi_version() == 2
+    assert built.aur_abi_version() == 3
     assert isinstance(built.aur_last_error(), bytes)
 
 
