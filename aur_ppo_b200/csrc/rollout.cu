@@ -12,8 +12,8 @@
 
 namespace aur {
 
-int launch_critic_values_tc(const float* critic, int obs_dim, const float* obs, long long M, float* out, cudaStream_t s);
-int launch_rollout_tc(const RolloutDev& d, int env_kind, cudaStream_t s);
+int launch_critic_values_tc(const float* critic, int obs_dim, int hidden, const float* obs, long long M, float* out, cudaStream_t s);
+int launch_rollout_tc(const RolloutDev& d, int env_kind, int hidden, cudaStream_t s);
 int rollout_impl();
 
 // ENV: CartPole or Pendulum.  E envs per thread (env n = base + e * nthreads_total keeps warps coalesced).
@@ -512,6 +512,16 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
   RolloutDev d = to_dev(a);
   cudaStream_t s = (cudaStream_t)stream;
   const int sms = sm_count();
+  // `--hidden_dim 128` (two layers, widths <= 4) on the envs the tensor-core rollout knows: the same two kernels as the
+  // 64-wide headline shape, operand tiles two K atoms wide
+  if (a.policy.hidden_dim == 128 && a.policy.num_layers == 2 && a.policy.obs_dim <= POL_IN_PAD && a.policy.act_dim <= POL_OUT_MAX &&
+      rollout_impl() == 1 && (a.env_kind == AUR_ENV_CARTPOLE || pend || a.env_kind == AUR_ENV_MOUNTAINCAR)) {
+    if ((rc = launch_rollout_tc(d, a.env_kind, 128, s))) return rc;
+    const float* critic = a.params + net_param_count(a.policy.obs_dim, 128, 2, a.policy.act_dim);
+    if ((rc = launch_critic_values_tc(critic, a.policy.obs_dim, 128, a.obs_buf, (long long)a.T * a.N, a.val_buf, s))) return rc;
+    if (a.next_value && (rc = launch_critic_values_tc(critic, a.policy.obs_dim, 128, a.next_obs, a.N, a.next_value, s))) return rc;
+    return 0;
+  }
   if (!fits_compiled_kernel(a.policy)) {
     // runtime-width policy: one env per thread, both nets in the sequential kernel
     if (((uintptr_t)a.params & 15) != 0) { set_error("aur_rollout: params must be 16-byte aligned"); return AUR_ERR_ARG; }
@@ -553,7 +563,7 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
   } while (0)
   const bool mcar = a.env_kind == AUR_ENV_MOUNTAINCAR, mcc = a.env_kind == AUR_ENV_MOUNTAINCAR_CONT;
   if (split_critic && rollout_impl() == 1 && !mcc) {
-    if ((rc = launch_rollout_tc(d, a.env_kind, s))) return rc;     // actor hidden layer on tcgen05 (rollout_tc.cu)
+    if ((rc = launch_rollout_tc(d, a.env_kind, 64, s))) return rc;     // actor hidden layer on tcgen05 (rollout_tc.cu)
   } else {
     if (pend) AUR_LAUNCH_ROLLOUT(Pendulum, 1);
     else if (mcc) AUR_LAUNCH_ROLLOUT(MountainCarContinuous, 1);
@@ -565,8 +575,8 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
 #undef AUR_LAUNCH_ROLLOUT
   if (split_critic) {
     const float* critic = a.params + net_param_count(a.policy.obs_dim, 64, 2, a.policy.act_dim);
-    if ((rc = launch_critic_values_tc(critic, a.policy.obs_dim, a.obs_buf, (long long)a.T * a.N, a.val_buf, s))) return rc;
-    if (a.next_value && (rc = launch_critic_values_tc(critic, a.policy.obs_dim, a.next_obs, a.N, a.next_value, s))) return rc;
+    if ((rc = launch_critic_values_tc(critic, a.policy.obs_dim, 64, a.obs_buf, (long long)a.T * a.N, a.val_buf, s))) return rc;
+    if (a.next_value && (rc = launch_critic_values_tc(critic, a.policy.obs_dim, 64, a.next_obs, a.N, a.next_value, s))) return rc;
   }
   return 0;
 }

@@ -1,4 +1,4 @@
-// Fused rollout with the actor's hidden layer on tensor cores (rows R, Ec, Ep, Ev, M, D; hidden 64, 2 layers).
+// Fused rollout with the actor's hidden layer on tensor cores (rows R, Ec, Ep, Ev, M, D; hidden 64 or 128, 2 layers).
 // Same contract as rollout_kernel (rollout.cu): T env steps x N envs in one launch, env state in registers, fp64
 // physics bit-identical to the checker, Philox sampling keyed by the global env id.  The difference is where the
 // 64x64 layer of the actor runs: a CTA owns 128 envs (thread = env = TMEM lane), every step the threads write their
@@ -14,54 +14,65 @@
 namespace aur {
 
 constexpr int RT_S = 128;
-constexpr int RT_TILE = RT_S * 128, RT_WTILE = 64 * 128;
-constexpr int RO_H1 = 0;                          // [hi][mid]
-constexpr int RO_W2 = RO_H1 + 2 * RT_TILE;        // [hi][mid]
-constexpr int RO_SMALL = RO_W2 + 2 * RT_WTILE;    // fp32: W1^T [4][64] and b1, b2 pre-scaled for tanh, W3 [4][64], b3 [4], logstd [4]
-constexpr int RO_BAR = RO_SMALL + 768 * 4;
-constexpr size_t RT_SMEM = RO_BAR + 64 + 1024;
-constexpr int RS_W1T = 0, RS_B1 = 256, RS_B2 = 320, RS_W3 = 384, RS_B3 = 640, RS_LS = 644;
+constexpr int RT_TILE = RT_S * 128;               // one K atom of the h1 tile: 128 envs x 64 features (128-B rows)
+// H = 64: four CTAs per SM (52 KB, 64 TMEM columns each).  H = 128 (`--hidden_dim 128`): the operand tiles are two K atoms wide
+// and W2 has 128 rows - 131 KB, one CTA per SM, 128 TMEM columns; still 30x the runtime-width SIMT kernel.
+template <int H>
+struct RtCfg {
+  static constexpr int KA = H / 64;                           // K atoms (64 features each)
+  static constexpr int WTILE = H * 128;                       // one K atom of W2: H rows x 128 B
+  static constexpr int O_H1 = 0;                              // [hi, mid][atom]
+  static constexpr int O_W2 = O_H1 + 2 * KA * RT_TILE;        // [hi, mid][atom]
+  static constexpr int O_SMALL = O_W2 + 2 * KA * WTILE;       // fp32: W1^T [4][H] and b1, b2 pre-scaled for tanh, W3 [4][H], b3 [4], logstd [4]
+  static constexpr int S_W1T = 0, S_B1 = 4 * H, S_B2 = 5 * H, S_W3 = 6 * H, S_B3 = 10 * H, S_LS = 10 * H + 4, S_N = 10 * H + 8;
+  static constexpr int O_BAR = O_SMALL + S_N * 4;
+  static constexpr size_t SMEM = O_BAR + 64 + 1024;
+  static constexpr int CTAS = H == 64 ? 4 : 1;
+};
 
-template <class ENV>
-__global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
+template <class ENV, int H>
+__global__ void __launch_bounds__(RT_S, RtCfg<H>::CTAS) rollout_tc_kernel(RolloutDev a) {
+  using Cfg = RtCfg<H>;
+  constexpr int KA = Cfg::KA;
+  constexpr int RS_W1T = Cfg::S_W1T, RS_B1 = Cfg::S_B1, RS_B2 = Cfg::S_B2, RS_W3 = Cfg::S_W3, RS_B3 = Cfg::S_B3, RS_LS = Cfg::S_LS;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* h1t[2] = {base + RO_H1, base + RO_H1 + RT_TILE};
-  unsigned char* w2t[2] = {base + RO_W2, base + RO_W2 + RT_WTILE};
-  float* sw = reinterpret_cast<float*>(base + RO_SMALL);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(base + RO_BAR);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(base + RO_BAR + 32);
+  unsigned char* h1t[2] = {base + Cfg::O_H1, base + Cfg::O_H1 + KA * RT_TILE};
+  unsigned char* w2t[2] = {base + Cfg::O_W2, base + Cfg::O_W2 + KA * Cfg::WTILE};
+  float* sw = reinterpret_cast<float*>(base + Cfg::O_SMALL);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + Cfg::O_BAR);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(base + Cfg::O_BAR + 32);
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr bool PEND = ENV::CONT;
   const int A = a.act_dim, obs_dim = a.obs_dim;
 
   if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-  if (warp == 0) tc::tmem_alloc(tslot, 64);
+  if (warp == 0) tc::tmem_alloc(tslot, H);
   {
     const float* g = a.params;                    // the actor comes first in the flat buffer
-    const float* gb1 = g + 64 * obs_dim;
-    const float* gW2 = gb1 + 64;
-    const float* gb2 = gW2 + 4096;
-    const float* gW3 = gb2 + 64;
-    const float* gb3 = gW3 + A * 64;
-    for (int e = tid; e < 256; e += RT_S) {
-      const int c = e >> 6, j = e & 63;
+    const float* gb1 = g + H * obs_dim;
+    const float* gW2 = gb1 + H;
+    const float* gb2 = gW2 + H * H;
+    const float* gW3 = gb2 + H;
+    const float* gb3 = gW3 + A * H;
+    for (int e = tid; e < 4 * H; e += RT_S) {
+      const int c = e / H, j = e - c * H;
       sw[RS_W1T + e] = c < obs_dim ? TANH_PRESCALE * g[j * obs_dim + c] : 0.0f;
-      sw[RS_W3 + e] = e < A * 64 ? gW3[e] : 0.0f;
+      sw[RS_W3 + e] = e < A * H ? gW3[e] : 0.0f;
     }
-    if (tid < 64) { sw[RS_B1 + tid] = TANH_PRESCALE * gb1[tid]; sw[RS_B2 + tid] = TANH_PRESCALE * gb2[tid]; }
+    for (int e = tid; e < H; e += RT_S) { sw[RS_B1 + e] = TANH_PRESCALE * gb1[e]; sw[RS_B2 + e] = TANH_PRESCALE * gb2[e]; }
     if (tid < 4) {
       sw[RS_B3 + tid] = tid < A ? gb3[tid] : 0.0f;
-      const int64_t gA = net_param_count(obs_dim, 64, 2, A), gC = net_param_count(obs_dim, 64, 2, 1);
+      const int64_t gA = net_param_count(obs_dim, H, 2, A), gC = net_param_count(obs_dim, H, 2, 1);
       sw[RS_LS + tid] = (a.continuous && tid < A) ? a.params[gA + gC + tid] : 0.0f;
     }
-    const int j = tid & 63, c0 = 4 * (tid >> 6);
 #pragma unroll 1
-    for (int ch = c0; ch < c0 + 4; ++ch) {
+    for (int e = tid; e < H * (H / 8); e += RT_S) {         // W2 row j, 8-feature chunk ch -> K atom ch / 8
+      const int j = e % H, ch = e / H;
       float v[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = gW2[j * 64 + 8 * ch + e];
-      store_split_chunk(w2t[0], w2t[1], j, ch, v);
+      for (int q = 0; q < 8; ++q) v[q] = gW2[j * H + 8 * ch + q];
+      store_split_chunk(w2t[0] + (ch >> 3) * Cfg::WTILE, w2t[1] + (ch >> 3) * Cfg::WTILE, j, ch & 7, v);
     }
   }
   tc::fence_proxy_async();
@@ -70,7 +81,7 @@ __global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
   tc::fence_after_sync();
   const uint32_t tm_z = *tslot;
   const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
-  constexpr uint32_t ID_FWD = tc::instr_desc(tc::FMT_BF16, 128, 64, 0, 0);
+  constexpr uint32_t ID_FWD = tc::instr_desc(tc::FMT_BF16, 128, H, 0, 0);
 
   const long long N = a.N;
   const long long n = (long long)blockIdx.x * RT_S + tid;
@@ -104,7 +115,7 @@ __global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
     }
     // ---- actor, first layer: this env's h1 row straight into the operand tile (8-feature chunks)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < H / 8; ++c) {
       float hv[8];
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
         float2 a01 = make_float2(b.x, b.y), a23 = make_float2(b.z, b.w);
 #pragma unroll
         for (int cc = 0; cc < POL_IN_PAD; ++cc) {
-          const float4 w = lds4(sw + RS_W1T + cc * 64 + f);
+          const float4 w = lds4(sw + RS_W1T + cc * H + f);
           const float2 xx = make_float2(obs[cc], obs[cc]);
           a01 = __ffma2_rn(make_float2(w.x, w.y), xx, a01);
           a23 = __ffma2_rn(make_float2(w.z, w.w), xx, a23);
@@ -121,15 +132,18 @@ __global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
         hv[4 * g] = tanh_prescaled(a01.x); hv[4 * g + 1] = tanh_prescaled(a01.y);
         hv[4 * g + 2] = tanh_prescaled(a23.x); hv[4 * g + 3] = tanh_prescaled(a23.y);
       }
-      store_split_chunk(h1t[0], h1t[1], tid, c, hv);
+      store_split_chunk(h1t[0] + (c >> 3) * RT_TILE, h1t[1] + (c >> 3) * RT_TILE, tid, c & 7, hv);
     }
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();                               // also: every thread has read last step's z2 out of TMEM
     if (tid == 0) {
       tc::fence_after_sync();
-      mma_split4(tm_z, tc::smem_desc_k_sw128(h1t[0]), tc::smem_desc_k_sw128(h1t[1]), tc::smem_desc_k_sw128(w2t[0]),
-                 tc::smem_desc_k_sw128(w2t[1]), ID_FWD, 4, 2, 2, false);
+#pragma unroll
+      for (int ka = 0; ka < KA; ++ka)
+        mma_split4(tm_z, tc::smem_desc_k_sw128(h1t[0] + ka * RT_TILE), tc::smem_desc_k_sw128(h1t[1] + ka * RT_TILE),
+                   tc::smem_desc_k_sw128(w2t[0] + ka * Cfg::WTILE), tc::smem_desc_k_sw128(w2t[1] + ka * Cfg::WTILE), ID_FWD, 4, 2, 2,
+                   ka > 0);
       tc::mma_commit(bar);
     }
     // the step's random numbers do not depend on the logits: draw them while the MMAs run
@@ -146,7 +160,7 @@ __global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
 #pragma unroll
     for (int k = 0; k < POL_OUT_MAX; ++k) head[k] = sw[RS_B3 + k];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < H / 16; ++c) {
       uint32_t zr[16];
       tc::tmem_ld16(tm_z + lane_base + 16 * c, zr);
       float h2[16];
@@ -163,7 +177,7 @@ __global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
         if (k < A) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const float4 w = lds4(sw + RS_W3 + k * 64 + 16 * c + 4 * g);
+            const float4 w = lds4(sw + RS_W3 + k * H + 16 * c + 4 * g);
             head[k] = fmaf(w.x, h2[4 * g], head[k]); head[k] = fmaf(w.y, h2[4 * g + 1], head[k]);
             head[k] = fmaf(w.z, h2[4 * g + 2], head[k]); head[k] = fmaf(w.w, h2[4 * g + 3], head[k]);
           }
@@ -247,7 +261,7 @@ __global__ void __launch_bounds__(RT_S, 4) rollout_tc_kernel(RolloutDev a) {
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tm_z, 64);
+  if (warp == 0) tc::tmem_dealloc(tm_z, H);
 }
 
 // 1 = tensor-core rollout (default for hidden 64 / 2 layers), 0 = SIMT rollout_kernel; AUR_ROLLOUT_IMPL=simt|tc
@@ -261,24 +275,35 @@ int rollout_impl() {
 }
 void set_rollout_impl(int impl) { g_rollout_impl = impl; }
 
-template <class ENV>
+template <class ENV, int H>
 static int rollout_tc_attrs() {
-  AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM));
-  AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<ENV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<ENV, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RtCfg<H>::SMEM));
+  AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<ENV, H>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   return 0;
 }
 
-int launch_rollout_tc(const RolloutDev& d, int env_kind, cudaStream_t s) {
+// hidden = 64 or 128 (two layers, widths <= 4)
+int launch_rollout_tc(const RolloutDev& d, int env_kind, int hidden, cudaStream_t s) {
   static DeviceOnce attr;
   if (attr.first()) {
     int rc;
-    if ((rc = rollout_tc_attrs<CartPole>()) || (rc = rollout_tc_attrs<Pendulum>()) || (rc = rollout_tc_attrs<MountainCar>())) return rc;
+    if ((rc = rollout_tc_attrs<CartPole, 64>()) || (rc = rollout_tc_attrs<Pendulum, 64>()) || (rc = rollout_tc_attrs<MountainCar, 64>()) ||
+        (rc = rollout_tc_attrs<CartPole, 128>()) || (rc = rollout_tc_attrs<Pendulum, 128>()) || (rc = rollout_tc_attrs<MountainCar, 128>()))
+      return rc;
     attr.done();
   }
   const unsigned grid = (unsigned)((d.N + RT_S - 1) / RT_S);
-  if (env_kind == AUR_ENV_PENDULUM) rollout_tc_kernel<Pendulum><<<grid, RT_S, RT_SMEM, s>>>(d);
-  else if (env_kind == AUR_ENV_MOUNTAINCAR) rollout_tc_kernel<MountainCar><<<grid, RT_S, RT_SMEM, s>>>(d);
-  else rollout_tc_kernel<CartPole><<<grid, RT_S, RT_SMEM, s>>>(d);
+  if (hidden == 128) {
+    constexpr size_t SM = RtCfg<128>::SMEM;
+    if (env_kind == AUR_ENV_PENDULUM) rollout_tc_kernel<Pendulum, 128><<<grid, RT_S, SM, s>>>(d);
+    else if (env_kind == AUR_ENV_MOUNTAINCAR) rollout_tc_kernel<MountainCar, 128><<<grid, RT_S, SM, s>>>(d);
+    else rollout_tc_kernel<CartPole, 128><<<grid, RT_S, SM, s>>>(d);
+  } else {
+    constexpr size_t SM = RtCfg<64>::SMEM;
+    if (env_kind == AUR_ENV_PENDULUM) rollout_tc_kernel<Pendulum, 64><<<grid, RT_S, SM, s>>>(d);
+    else if (env_kind == AUR_ENV_MOUNTAINCAR) rollout_tc_kernel<MountainCar, 64><<<grid, RT_S, SM, s>>>(d);
+    else rollout_tc_kernel<CartPole, 64><<<grid, RT_S, SM, s>>>(d);
+  }
   AUR_LAUNCH_OK("rollout_tc_kernel");
   return 0;
 }

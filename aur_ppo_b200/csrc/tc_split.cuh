@@ -60,11 +60,11 @@ __device__ __forceinline__ void mma_split4(uint32_t d, uint64_t a_hi, uint64_t a
 
 // six products of three-term operands (everything above 2^-25): fp32-equivalent contraction
 __device__ __forceinline__ void mma_split6(uint32_t d, const uint64_t (&a)[3], const uint64_t (&b)[3], uint32_t idesc, int ksteps,
-                                           uint32_t a_step, uint32_t b_step) {
+                                           uint32_t a_step, uint32_t b_step, bool accumulate = false) {
   const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
   for (int p = 0; p < 6; ++p)
     for (int k = 0; k < ksteps; ++k)
-      tc::mma_f16(d, a[pa[p]] + (uint64_t)(a_step * k), b[pb[p]] + (uint64_t)(b_step * k), idesc, (p > 0 || k > 0) ? 1u : 0u);
+      tc::mma_f16(d, a[pa[p]] + (uint64_t)(a_step * k), b[pb[p]] + (uint64_t)(b_step * k), idesc, (accumulate || p > 0 || k > 0) ? 1u : 0u);
 }
 
 }  // namespace aur

@@ -178,20 +178,20 @@ struct WideHead {
 // KIND: 0 actor (Categorical), 1 actor (Normal), 2 critic.  One CTA per row of WD_KC samples; the LPS = H / 8 lanes of a sample
 // sit side by side in a warp, the head is a butterfly sum over them (every lane ends up with the same bits), and all of them
 // evaluate the loss redundantly.
-template <int KIND>
+template <int KIND, int OUT>
 __global__ void __launch_bounds__(WD_THREADS, 2) wide_head_kernel(UpdDev u, WideHead a) {
   constexpr bool ACTOR = KIND != 2;
   __shared__ __align__(16) float red[WD_THREADS * 8];
-  __shared__ __align__(16) float sWL[WD_OUT * 256];
+  __shared__ __align__(16) float sWL[4 * 256];
   __shared__ float sred[8];
-  const int H = a.H, OUT = a.OUT, LPS = H >> 3, SPP = WD_THREADS / LPS;
+  const int H = a.H, LPS = H >> 3, SPP = WD_THREADS / LPS;
   const int tid = threadIdx.x, c = tid % LPS, so = tid / LPS;
   const int s_begin = blockIdx.x * WD_KC, s_end = min(a.ms, s_begin + WD_KC);
   float* prow = a.part + (size_t)blockIdx.x * a.pstride;
-  for (int i = tid; i < WD_OUT * H; i += WD_THREADS) sWL[i] = i < OUT * H ? __ldg(a.WL + i) : 0.0f;
-  float bL[WD_OUT], sd[WD_OUT], ls[WD_OUT];
+  for (int i = tid; i < OUT * H; i += WD_THREADS) sWL[i] = __ldg(a.WL + i);
+  float bL[OUT], sd[OUT], ls[OUT];
 #pragma unroll
-  for (int k = 0; k < WD_OUT; ++k) {
+  for (int k = 0; k < OUT; ++k) {
     bL[k] = k < OUT ? __ldg(a.WL + (size_t)OUT * H + k) : 0.0f;
     const float l = (KIND == 1 && k < OUT) ? __ldg(a.logstd + k) : 0.0f;
     sd[k] = expf(l); ls[k] = logf(sd[k]);                 // torch Normal: log(exp(logstd))
@@ -201,9 +201,9 @@ __global__ void __launch_bounds__(WD_THREADS, 2) wide_head_kernel(UpdDev u, Wide
   float bias[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) bias[e] = __ldg(a.bias + 8 * c + e);
-  float dWL[WD_OUT][8], dbh[8], dbL[WD_OUT], gls[WD_OUT];
+  float dWL[OUT][8], dbh[8], dbL[OUT], gls[OUT];
 #pragma unroll
-  for (int k = 0; k < WD_OUT; ++k) {
+  for (int k = 0; k < OUT; ++k) {
     dbL[k] = 0.0f; gls[k] = 0.0f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) dWL[k][e] = 0.0f;
@@ -231,14 +231,16 @@ __global__ void __launch_bounds__(WD_THREADS, 2) wide_head_kernel(UpdDev u, Wide
     const float4 za = za_n, zb = zb_n;
     const long long row = row_n;
     // this sample's scalars (their address needs the row index, which arrived an iteration ago)
-    float e0 = 0.0f, e1 = 0.0f, eact[WD_OUT] = {0.f, 0.f, 0.f, 0.f};
+    float e0 = 0.0f, e1 = 0.0f, eact[OUT];
+#pragma unroll
+    for (int k = 0; k < OUT; ++k) eact[k] = 0.0f;
     if (valid) {
       if (ACTOR) {
         e0 = __ldg(u.logprobs + row); e1 = __ldg(u.advantages + row);
         if (KIND == 0) eact[0] = __ldg(u.actions + row);
         else {
 #pragma unroll
-          for (int k = 0; k < WD_OUT; ++k) if (k < OUT) eact[k] = __ldg(u.actions + row * OUT + k);
+          for (int k = 0; k < OUT; ++k) if (k < OUT) eact[k] = __ldg(u.actions + row * OUT + k);
         }
       } else {
         e0 = __ldg(u.returns + row); e1 = __ldg(u.values + row);
@@ -248,9 +250,9 @@ __global__ void __launch_bounds__(WD_THREADS, 2) wide_head_kernel(UpdDev u, Wide
     float h[8];
     h[0] = tanh_fast(za.x + bias[0]); h[1] = tanh_fast(za.y + bias[1]); h[2] = tanh_fast(za.z + bias[2]); h[3] = tanh_fast(za.w + bias[3]);
     h[4] = tanh_fast(zb.x + bias[4]); h[5] = tanh_fast(zb.y + bias[5]); h[6] = tanh_fast(zb.z + bias[6]); h[7] = tanh_fast(zb.w + bias[7]);
-    float out[WD_OUT], dout[WD_OUT];
+    float out[OUT], dout[OUT];
 #pragma unroll
-    for (int k = 0; k < WD_OUT; ++k) {
+    for (int k = 0; k < OUT; ++k) {
       float o = 0.0f;
       if (k < OUT) {
         const float4 wa = lds4(sWL + k * H + 8 * c), wb = lds4(sWL + k * H + 8 * c + 4);
@@ -265,27 +267,27 @@ __global__ void __launch_bounds__(WD_THREADS, 2) wide_head_kernel(UpdDev u, Wide
       if (ACTOR) {
         const float oldlp = e0, adv = e1;
         float newlogp, entropy;
-        float dlp[WD_OUT], dH[WD_OUT];
+        float dlp[OUT], dH[OUT];
         if (KIND == 0) {
           float m = out[0];
 #pragma unroll
-          for (int k = 1; k < WD_OUT; ++k) if (k < OUT) m = fmaxf(m, out[k]);
+          for (int k = 1; k < OUT; ++k) if (k < OUT) m = fmaxf(m, out[k]);
           float se = 0.0f;
 #pragma unroll
-          for (int k = 0; k < WD_OUT; ++k) if (k < OUT) se += expf(out[k] - m);
+          for (int k = 0; k < OUT; ++k) if (k < OUT) se += expf(out[k] - m);
           const float lse = m + logf(se);
           const int act = (int)eact[0];
-          float lp[WD_OUT], pr[WD_OUT];
+          float lp[OUT], pr[OUT];
           entropy = 0.0f; newlogp = 0.0f;
 #pragma unroll
-          for (int k = 0; k < WD_OUT; ++k) {
+          for (int k = 0; k < OUT; ++k) {
             lp[k] = out[k] - lse;
             pr[k] = k < OUT ? expf(lp[k]) : 0.0f;
             if (k < OUT) entropy -= pr[k] * lp[k];
             if (k == act) newlogp = lp[k];
           }
 #pragma unroll
-          for (int k = 0; k < WD_OUT; ++k) {
+          for (int k = 0; k < OUT; ++k) {
             dlp[k] = k < OUT ? (k == act ? 1.0f : 0.0f) - pr[k] : 0.0f;
             dH[k] = k < OUT ? -pr[k] * (lp[k] + entropy) : 0.0f;
           }
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(WD_THREADS, 2) wide_head_kernel(UpdDev u, Wide
           const float LOG_SQRT_2PI = 0.91893853320467267f;
           newlogp = 0.0f; entropy = 0.0f;
 #pragma unroll
-          for (int k = 0; k < WD_OUT; ++k) {
+          for (int k = 0; k < OUT; ++k) {
             dlp[k] = 0.0f; dH[k] = 0.0f;
             if (k < OUT) {
               const float d = eact[k] - out[k], var = sd[k] * sd[k];
@@ -313,11 +315,11 @@ __global__ void __launch_bounds__(WD_THREADS, 2) wide_head_kernel(UpdDev u, Wide
         const float g_logp = -advn * (w1 + (1.0f - w1) * inr) * ratio * u.inv_m;
         const float g_H = -u.ent_c * u.inv_m;
 #pragma unroll
-        for (int k = 0; k < WD_OUT; ++k) dout[k] = g_logp * dlp[k] + g_H * dH[k];
+        for (int k = 0; k < OUT; ++k) dout[k] = g_logp * dlp[k] + g_H * dH[k];
         if (c == 0) {
           if (KIND == 1) {
 #pragma unroll
-            for (int k = 0; k < WD_OUT; ++k)
+            for (int k = 0; k < OUT; ++k)
               if (k < OUT) {
                 const float d = out[k] - eact[k];
                 gls[k] += g_logp * (d * d / (sd[k] * sd[k]) - 1.0f) + g_H;
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(WD_THREADS, 2) wide_head_kernel(UpdDev u, Wide
 #pragma unroll
       for (int e = 0; e < 8; ++e) dzv[e] = 0.0f;
 #pragma unroll
-      for (int k = 0; k < WD_OUT; ++k) {
+      for (int k = 0; k < OUT; ++k) {
         if (k < OUT) {
           const float4 wa = lds4(sWL + k * H + 8 * c), wb = lds4(sWL + k * H + 8 * c + 4);
           dzv[0] = fmaf(wa.x, dout[k], dzv[0]); dzv[1] = fmaf(wa.y, dout[k], dzv[1]);
@@ -371,14 +373,14 @@ __global__ void __launch_bounds__(WD_THREADS, 2) wide_head_kernel(UpdDev u, Wide
   float v = chunk_col_sum(dbh, red, H);
   if (tid < H) put(prow + a.oBh + tid, v, a.beta);
 #pragma unroll
-  for (int k = 0; k < WD_OUT; ++k) {
+  for (int k = 0; k < OUT; ++k) {
     if (k < OUT) {
       v = chunk_col_sum(dWL[k], red, H);
       if (tid < H) put(prow + a.oWL + (size_t)k * H + tid, v, a.beta);
     }
   }
 #pragma unroll
-  for (int k = 0; k < WD_OUT; ++k) {
+  for (int k = 0; k < OUT; ++k) {
     if (k < OUT) {
       v = block_sum_wide(dbL[k], sred);
       if (tid == 0) put(prow + a.oBL + k, v, a.beta);
@@ -780,9 +782,14 @@ int launch_ppo_grad_wide(const UpdDev& d, const aur_policy_desc& p, float* ws, i
       h.H = H; h.OUT = OUT; h.ms = ms; h.beta = beta; h.pstride = pstride; h.g0 = g0;
       h.dz = dzb[0]; h.plane = L.plane; h.part = npart;
       h.oBh = oWh + (size_t)(NL - 2) * hstride + (size_t)H * H; h.oWL = oWL; h.oBL = oBL; h.oLS = oLS;
-      if (net == 1) wide_head_kernel<2><<<rows, WD_THREADS, 0, s>>>(d, h);
-      else if (p.continuous) wide_head_kernel<1><<<rows, WD_THREADS, 0, s>>>(d, h);
-      else wide_head_kernel<0><<<rows, WD_THREADS, 0, s>>>(d, h);
+      {
+        void (*hk)(UpdDev, WideHead) = wide_head_kernel<2, 1>;
+        if (net == 0) {
+          if (p.continuous) hk = OUT == 1 ? wide_head_kernel<1, 1> : OUT == 2 ? wide_head_kernel<1, 2> : OUT == 3 ? wide_head_kernel<1, 3> : wide_head_kernel<1, 4>;
+          else hk = OUT == 1 ? wide_head_kernel<0, 1> : OUT == 2 ? wide_head_kernel<0, 2> : OUT == 3 ? wide_head_kernel<0, 3> : wide_head_kernel<0, 4>;
+        }
+        hk<<<rows, WD_THREADS, 0, s>>>(d, h);
+      }
       AUR_LAUNCH_OK("wide_head_kernel");
       int cur = 0;
       for (int l = NL - 1; l >= 1; --l) {
