@@ -50,8 +50,12 @@ def num_envs_for(w, n_gpus):
     return w["total_envs"] if w["total_envs"] else w["envs_per_gpu"] * n_gpus
 
 
-def mlp_flops_fwd(w, hidden=64):
+HIDDEN = 64        # --hidden_dim (src/run_ppo.py:36): 64 is the reference default and every BASELINE config; 128 / 256 run the wide kernels
+
+
+def mlp_flops_fwd(w, hidden=None):
     """fp32 FLOPs of one actor + critic forward per sample (2 x multiply-adds)."""
+    hidden = hidden or HIDDEN
     o, a = w["obs"], w["act"]
     return 2 * (o * hidden + hidden * hidden + hidden * a) + 2 * (o * hidden + hidden * hidden + hidden)
 
@@ -61,7 +65,7 @@ def workload_config(name, n_gpus):
     n_envs = num_envs_for(w, n_gpus)
     return {"workload": f"{w['gym_id']} PPO iteration: fused rollout + GAE + update ({w['baseline']})",
             "name": name, "num_envs_per_gpu": n_envs // n_gpus, "num_envs": n_envs, "num_steps": w["T"],
-            "num_minibatches": w["nm"], "update_epochs": w["epochs"], "hidden_dim": 64, "num_layers": 2,
+            "num_minibatches": w["nm"], "update_epochs": w["epochs"], "hidden_dim": HIDDEN, "num_layers": 2,
             "continuous": w["continuous"], "wrappers": w["continuous"],
             "parallelism": f"dp{n_gpus} (env columns sharded; per minibatch one packed [grads|stats] exchange done by the "
                            f"update kernels over NVLink peer memory, AUR_DP_EXCHANGE=nccl selects a library all-reduce)",
@@ -78,7 +82,7 @@ def params(name, n_gpus, total_iters):
             'total_timesteps': n * w["T"] * max(total_iters, 1), 'anneal_lr': True, 'gae_lambda': 0.95,
             'num_update_epochs': w["epochs"], 'num_envs': n, 'num_minibatches': w["nm"], 'entropy_coeff': w["ent"],
             'value_coeff': 0.5, 'clip_coeff': 0.2, 'clip_vloss': True, 'max_grad_norm': 0.5, 'target_kl': None,
-            'norm_adv': True, 'capture_video': False, 'hidden_dim': 64, 'continuous': w["continuous"],
+            'norm_adv': True, 'capture_video': False, 'hidden_dim': HIDDEN, 'continuous': w["continuous"],
             'learning_rate': w["lr"], 'exp_name': 'bench', 'num_layers': 2, 'dropout': 0.0, 'gamma': 0.99, 'track': False,
             'tensorboard': False, 'save': False}
 
@@ -154,7 +158,7 @@ def cpu_reference_iteration(name, num_envs, iters, warmup, seed=1):
     T, cont, O = w["T"], w["continuous"], w["obs"]
     torch.manual_seed(seed)
     np.random.seed(seed)
-    pol, _ = random_policy(O, w["act"], 64, 2, cont, seed=seed)
+    pol, _ = random_policy(O, w["act"], HIDDEN, 2, cont, seed=seed)
     opt = R.RefAdam(pol.tensors(), lr=w["lr"], eps=1e-5)
     envs = G.SyncVectorEnv([G.make_env(w["gym_id"], cont) for _ in range(num_envs)], O)
     next_obs = torch.from_numpy(envs.reset(seed=list(range(num_envs)))[0])
@@ -455,7 +459,7 @@ def run_ours(args):
     # DRAM bytes per launch from the committed `ncu --set full` capture of THIS round's binary (profiles/r2_traffic.json,
     # config-B shapes); null when the workload's shapes differ from the captured ones
     traffic, traffic_src = {}, None
-    if name == "ppo":
+    if name == "ppo" and HIDDEN == 64:
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
             traffic, traffic_src = tj.get("dram_bytes_per_launch", {}), tj.get("source")
@@ -480,7 +484,14 @@ def run_ours(args):
                  "bf16 two-term splits; achieved = ALGORITHMIC fwd+bwd FLOP per sample / time against the measured dense "
                  "bf16 peak.  ncu: the kernel is issue-bound on the per-sample SIMT work, see profiles/"},
     ] + sweep
-    dominant = max(rooflines[:3], key=lambda r: r["ms"] * (n_mb if r["kernel"].startswith("ppo_grad") else 1))
+    if HIDDEN != 64:      # the wide kernels (update_wide.cu; rollout_tc_kernel<ENV, 128> or, at 256, the runtime-width SIMT rollout)
+        rooflines[2]["kernel"] = "layer-wise tensor-core update (update_wide.cu: wide_gemm128 / tc_gemm / tc_gemm_tn + SIMT layers)"
+        rooflines[2]["note"] = ("hidden %d: every H x H contraction is a tcgen05 GEMM over two-plane bf16 operands, activations staged in "
+                                "HBM per 262,144-sample sub-batch; achieved = ALGORITHMIC fwd+bwd FLOP per sample / time" % HIDDEN)
+        rooflines[2].pop("algorithmic_bytes", None)
+        if HIDDEN > 128:
+            rooflines[1]["kernel"] = "rollout_kernel (runtime-width SIMT)"
+    dominant = max(rooflines[:3], key=lambda r: r["ms"] * (n_mb if "update" in r["kernel"] or r["kernel"].startswith("ppo_grad") else 1))
     roofline = {k: dominant[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
     roofline["kernel"] = dominant["kernel"]
     roofline["peak_source"] = peak_src
@@ -527,7 +538,8 @@ def other_workloads(args):
             ("scale1m", ["--workload", "scale1m", "--steps", "3"]),
             ("equiv_fp32", ["--workload", "equiv", "--precision", "fp32", "--steps", "3"]),
             ("equiv_bf16", ["--workload", "equiv", "--precision", "bf16", "--steps", "5"]),
-            ("cnn_fp32", ["--workload", "cnn", "--precision", "fp32", "--steps", "3"])]
+            ("cnn_fp32", ["--workload", "cnn", "--precision", "fp32", "--steps", "3"]),
+            ("ppo_hidden128", ["--workload", "ppo", "--hidden_dim", "128", "--steps", "3"])]
     out = {}
     for tag, extra in runs:
         t0 = time.perf_counter()
@@ -724,7 +736,11 @@ def main():
     ap.add_argument("--precision", type=str, default="fp32", choices=["fp32", "split", "bf16"],
                     help="equiv / cnn: fp32 = three bf16 operand planes, fp32-equivalent like the reference (default); split = two "
                          "planes (~5e-6 per layer); bf16 = single-plane fast mode, below the reference's precision")
+    ap.add_argument("--hidden_dim", type=int, default=64, choices=[64, 128, 256],
+                    help="policy width of the MLP workloads (src/run_ppo.py:36); 64 is every BASELINE config, 128 / 256 exercise the wide kernels")
     args = ap.parse_args()
+    global HIDDEN
+    HIDDEN = args.hidden_dim
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

@@ -56,6 +56,24 @@ def test_wide_config_runs_and_improves():
     assert np.mean(rets[-50:]) > 1.5 * np.mean(rets[:50])
 
 
+def test_hidden_128_runs_the_tensor_core_kernels_and_improves():
+    """`-d 128` (src/run_ppo.py:36): rollout_tc_kernel<ENV, 128> + critic_values_tc_kernel<128> + the layer-wise update
+    (update_wide.cu) behind the unchanged ppo(params).train()."""
+    from aur_ppo_b200 import _lib
+    from aur_ppo_b200.ppo import ppo
+    torch.manual_seed(1)
+    agent = ppo(_params(num_envs=2048, hidden_dim=128, total_timesteps=2048 * 128 * 12))
+    L = _lib.lib()
+    assert L.aur_ppo_update_get_wide() == 1 and L.aur_rollout_get_impl() == 1
+    L.aur_launch_count_reset()
+    rets, lens, xs = agent.train()
+    # 12 iterations x 16 minibatches x >= 14 launches of the layer-wise path (the fused generic kernel needs 4)
+    assert L.aur_launch_count() > 12 * 16 * 14
+    assert agent.num_updates == 12 and len(rets) > 100
+    assert np.mean(rets[-50:]) > 1.5 * np.mean(rets[:50])
+    assert np.isfinite(list(agent.last_stats.values())).all()
+
+
 def test_pendulum_continuous_runs():
     from aur_ppo_b200.ppo import ppo
     torch.manual_seed(1)
