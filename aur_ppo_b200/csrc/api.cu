@@ -63,6 +63,39 @@ unsigned int* stream_tickets(cudaStream_t s) {
   return p;
 }
 
+namespace {
+struct ScratchSlot { int dev; cudaStream_t s; void* p; size_t bytes; };
+std::vector<ScratchSlot> g_scratch;
+}  // namespace
+
+// Library-owned scratch per (device, stream) for the entry points whose C signature carries no workspace (aur_rollout at
+// hidden widths that run layer by layer, rollout_wide.cu): grows on demand (cudaFree synchronises the device, so a buffer is
+// never pulled from under a running kernel), never shrinks; refuses to (re)allocate inside a graph capture.
+void* stream_scratch(cudaStream_t s, size_t bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error("stream_scratch: no current device"); return nullptr; }
+  std::lock_guard<std::mutex> lk(g_ticket_mu);
+  ScratchSlot* slot = nullptr;
+  for (ScratchSlot& t : g_scratch)
+    if (t.dev == dev && t.s == s) slot = &t;
+  if (slot && slot->bytes >= bytes) return slot->p;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+    set_error("stream_scratch: allocation inside a graph capture (run one eager call of this shape on the stream first)");
+    return nullptr;
+  }
+  if (slot) { (void)cudaFree(slot->p); slot->p = nullptr; slot->bytes = 0; }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("stream_scratch: cudaMalloc of %zu bytes failed", bytes);
+    return nullptr;
+  }
+  if (slot) { slot->p = p; slot->bytes = bytes; }
+  else g_scratch.push_back({dev, s, p, bytes});
+  return p;
+}
+
 }  // namespace aur
 
 extern "C" int aur_abi_version(void) { return AUR_ABI_VERSION; }

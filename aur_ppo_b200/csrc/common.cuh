@@ -49,6 +49,8 @@ struct DeviceOnce {
 // caller-provided workspace would have to be zero-initialised by contract (it is not part of the ABI contract).
 // Returns nullptr on failure (error text set).
 unsigned int* stream_tickets(cudaStream_t s);
+// Library-owned, grow-only scratch per (device, stream) for entry points without a workspace argument (api.cu); nullptr on failure.
+void* stream_scratch(cudaStream_t s, size_t bytes);
 
 // ---- mbarrier / bulk-async (TMA 1-D) PTX wrappers -----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

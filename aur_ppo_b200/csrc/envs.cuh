@@ -320,6 +320,8 @@ struct RolloutDev {
   uint64_t seed, step0, env_id0;
   aur_episode_log log;
   double gamma;
+  int t0;                     // first step index of this launch (buffers / episode log); 0 except for the per-step launches of rollout_wide.cu
+  const float* ext_logits;    // [N][4] actor outputs computed outside the kernel (rollout_tc_kernel<ENV, 0>), else nullptr
 };
 
 template <int HID>

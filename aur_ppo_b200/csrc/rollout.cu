@@ -15,6 +15,8 @@ namespace aur {
 int launch_critic_values_tc(const float* critic, int obs_dim, int hidden, const float* obs, long long M, float* out, cudaStream_t s);
 int launch_rollout_tc(const RolloutDev& d, int env_kind, int hidden, cudaStream_t s);
 int rollout_impl();
+bool rollout_wide_eligible(const aur_policy_desc& p, int env_kind);      // rollout_wide.cu: layer-wise actor on tensor cores
+int launch_rollout_wide(const RolloutDev& d, const aur_policy_desc& p, int env_kind, cudaStream_t s);
 
 // ENV: CartPole or Pendulum.  E envs per thread (env n = base + e * nthreads_total keeps warps coalesced).
 // CRITIC = false: the values are filled afterwards by critic_values_tc_kernel (values_tc.cu) from the observation rows.
@@ -477,6 +479,7 @@ static aur::RolloutDev to_dev(const aur_rollout_args& a) {
   d.params = a.params; d.env = a.env;
   d.obs_buf = a.obs_buf; d.act_buf = a.act_buf; d.logp_buf = a.logp_buf; d.val_buf = a.val_buf; d.rew_buf = a.rew_buf;
   d.done_buf = a.done_buf; d.next_obs = a.next_obs; d.next_done = a.next_done; d.next_value = a.next_value;
+  d.t0 = 0; d.ext_logits = nullptr;
   d.actions_in = a.actions_in; d.seed = a.seed; d.step0 = a.step0; d.env_id0 = a.env_id0; d.log = a.log; d.gamma = a.gamma;
   return d;
 }
@@ -522,6 +525,8 @@ extern "C" int aur_rollout(const aur_rollout_args* args, void* stream) {
     if (a.next_value && (rc = launch_critic_values_tc(critic, a.policy.obs_dim, 128, a.next_obs, a.N, a.next_value, s))) return rc;
     return 0;
   }
+  // the other wide shapes (256 units; 128 units with more layers): the actor layer by layer over all envs each step
+  if (rollout_impl() == 1 && rollout_wide_eligible(a.policy, a.env_kind)) return launch_rollout_wide(d, a.policy, a.env_kind, s);
   if (!fits_compiled_kernel(a.policy)) {
     // runtime-width policy: one env per thread, both nets in the sequential kernel
     if (((uintptr_t)a.params & 15) != 0) { set_error("aur_rollout: params must be 16-byte aligned"); return AUR_ERR_ARG; }

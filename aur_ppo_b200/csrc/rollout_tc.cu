@@ -27,12 +27,16 @@ struct RtCfg {
   static constexpr int S_W1T = 0, S_B1 = 4 * H, S_B2 = 5 * H, S_W3 = 6 * H, S_B3 = 10 * H, S_LS = 10 * H + 4, S_N = 10 * H + 8;
   static constexpr int O_BAR = O_SMALL + S_N * 4;
   static constexpr size_t SMEM = O_BAR + 64 + 1024;
-  static constexpr int CTAS = H == 64 ? 4 : 1;
+  static constexpr int CTAS = H == 64 ? 4 : (H == 0 ? 4 : 1);
 };
 
+// H = 0: the actor's outputs come from outside (a.ext_logits [N][4], rollout_wide.cu computes them layer by layer for the widths
+// whose W2 does not fit shared memory); the kernel is then only the per-step env / sampling / bookkeeping part, launched once
+// per step (a.T = 1, a.t0 = step) with the env state round-tripping through its global arrays.
 template <class ENV, int H>
 __global__ void __launch_bounds__(RT_S, RtCfg<H>::CTAS) rollout_tc_kernel(RolloutDev a) {
   using Cfg = RtCfg<H>;
+  constexpr bool EXT = H == 0;
   constexpr int KA = Cfg::KA;
   constexpr int RS_W1T = Cfg::S_W1T, RS_B1 = Cfg::S_B1, RS_B2 = Cfg::S_B2, RS_W3 = Cfg::S_W3, RS_B3 = Cfg::S_B3, RS_LS = Cfg::S_LS;
   extern __shared__ unsigned char smem_raw[];
@@ -46,6 +50,8 @@ __global__ void __launch_bounds__(RT_S, RtCfg<H>::CTAS) rollout_tc_kernel(Rollou
   constexpr bool PEND = ENV::CONT;
   const int A = a.act_dim, obs_dim = a.obs_dim;
 
+  uint32_t tm_z = 0;
+  if constexpr (!EXT) {
   if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   if (warp == 0) tc::tmem_alloc(tslot, H);
   {
@@ -79,7 +85,8 @@ __global__ void __launch_bounds__(RT_S, RtCfg<H>::CTAS) rollout_tc_kernel(Rollou
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tm_z = *tslot;
+  tm_z = *tslot;
+  }
   const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
   constexpr uint32_t ID_FWD = tc::instr_desc(tc::FMT_BF16, 128, H, 0, 0);
 
@@ -99,9 +106,13 @@ __global__ void __launch_bounds__(RT_S, RtCfg<H>::CTAS) rollout_tc_kernel(Rollou
   for (int k = 0; k < POL_IN_PAD; ++k) obs[k] = k < ENV::OBS ? a.next_obs[m0 * ENV::OBS + k] : 0.0f;
   if constexpr (PEND) { if (a.wrappers) nm.load(a.env.norm, N, m0); }
   NormalConsts nc;
-  if (a.continuous) nc = normal_consts(sw + RS_LS, A);
+  if (a.continuous) {
+    if constexpr (EXT) nc = normal_consts(a.params + net_param_count(obs_dim, a.hid, a.nl, A) + net_param_count(obs_dim, a.hid, a.nl, 1), A);
+    else nc = normal_consts(sw + RS_LS, A);
+  }
 
-  for (int t = 0; t < a.T; ++t) {
+  for (int tt = 0; tt < a.T; ++tt) {
+    const int t = a.t0 + tt;
     const size_t o = (size_t)t * (size_t)N + (size_t)n;
     // ---- buffer.states[t] = next_obs; buffer.terminals[t] = next_done (ppo.py:203-204)
     if (live) {
@@ -114,6 +125,7 @@ __global__ void __launch_bounds__(RT_S, RtCfg<H>::CTAS) rollout_tc_kernel(Rollou
       a.done_buf[o] = done_prev;
     }
     // ---- actor, first layer: this env's h1 row straight into the operand tile (8-feature chunks)
+    if constexpr (!EXT) {
 #pragma unroll
     for (int c = 0; c < H / 8; ++c) {
       float hv[8];
@@ -146,6 +158,7 @@ __global__ void __launch_bounds__(RT_S, RtCfg<H>::CTAS) rollout_tc_kernel(Rollou
                    ka > 0);
       tc::mma_commit(bar);
     }
+    }
     // the step's random numbers do not depend on the logits: draw them while the MMAs run
     const uint64_t gid = a.env_id0 + (uint64_t)n, gstep = a.step0 + (uint64_t)t;
     Philox rnd;
@@ -153,10 +166,14 @@ __global__ void __launch_bounds__(RT_S, RtCfg<H>::CTAS) rollout_tc_kernel(Rollou
     if (a.actions_in == nullptr)
       rnd = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)gstep, (uint32_t)(gstep >> 32), (uint32_t)a.seed,
                           (uint32_t)(a.seed >> 32));
-    mbar_wait(bar, (uint32_t)t & 1u);
+    float head[POL_OUT_MAX];
+    if constexpr (EXT) {
+      const float4 lg = live ? __ldg(reinterpret_cast<const float4*>(a.ext_logits) + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+      head[0] = lg.x; head[1] = lg.y; head[2] = lg.z; head[3] = lg.w;
+    } else {
+    mbar_wait(bar, (uint32_t)tt & 1u);
     tc::fence_after_sync();
     // ---- second layer activation + head from this env's TMEM lane
-    float head[POL_OUT_MAX];
 #pragma unroll
     for (int k = 0; k < POL_OUT_MAX; ++k) head[k] = sw[RS_B3 + k];
 #pragma unroll
@@ -183,6 +200,7 @@ __global__ void __launch_bounds__(RT_S, RtCfg<H>::CTAS) rollout_tc_kernel(Rollou
           }
         }
       }
+    }
     }
     if (!live) continue;
     // ---- distribution, env step, bookkeeping: as rollout_kernel (rollout.cu)
@@ -259,9 +277,11 @@ __global__ void __launch_bounds__(RT_S, RtCfg<H>::CTAS) rollout_tc_kernel(Rollou
     for (int k = 0; k < ENV::OBS; ++k) a.next_obs[n * ENV::OBS + k] = obs[k];
     if constexpr (PEND) { if (a.wrappers) nm.store(a.env.norm, N, n); }
   }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tm_z, H);
+  if constexpr (!EXT) {
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tm_z, H);
+  }
 }
 
 // 1 = tensor-core rollout (default for hidden 64 / 2 layers), 0 = SIMT rollout_kernel; AUR_ROLLOUT_IMPL=simt|tc
@@ -279,6 +299,16 @@ template <class ENV, int H>
 static int rollout_tc_attrs() {
   AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<ENV, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RtCfg<H>::SMEM));
   AUR_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<ENV, H>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  return 0;
+}
+
+// one env step of all N envs from externally computed actor outputs (d.ext_logits, d.t0; d.T = 1)
+int launch_rollout_step_ext(const RolloutDev& d, int env_kind, cudaStream_t s) {
+  const unsigned grid = (unsigned)((d.N + RT_S - 1) / RT_S);
+  if (env_kind == AUR_ENV_PENDULUM) rollout_tc_kernel<Pendulum, 0><<<grid, RT_S, 0, s>>>(d);
+  else if (env_kind == AUR_ENV_MOUNTAINCAR) rollout_tc_kernel<MountainCar, 0><<<grid, RT_S, 0, s>>>(d);
+  else rollout_tc_kernel<CartPole, 0><<<grid, RT_S, 0, s>>>(d);
+  AUR_LAUNCH_OK("rollout_tc_kernel (external actor)");
   return 0;
 }
 

@@ -375,11 +375,13 @@ def test_policy_evaluate_runtime_widths_vs_oracle(obs_dim, act_dim, hidden, laye
         assert set(np.unique(a1.cpu().numpy())) <= set(range(act_dim))
 
 
-@pytest.mark.parametrize("hidden,layers,N,T", [(32, 2, 300, 200), (128, 2, 70, 300), (256, 2, 40, 120), (96, 3, 64, 150)])
+@pytest.mark.parametrize("hidden,layers,N,T", [(32, 2, 300, 200), (128, 2, 70, 300), (256, 2, 40, 120), (96, 3, 64, 150), (128, 3, 200, 90),
+                                               (256, 4, 130, 60)])
 def test_cartpole_replay_runtime_width(hidden, layers, N, T, rollout_impl):
     """`--hidden_dim` other than 64: transitions stay bit-exact (same env code), log-probs / values follow the wider MLP.
-    128 x 2 has two kernels (tcgen05 rollout_tc_kernel<ENV, 128> + critic_values_tc_kernel<128>, and the runtime-width SIMT one)."""
-    if rollout_impl != "tc" and not (hidden == 128 and layers == 2):
+    128 / 256 units have two paths: tcgen05 (128 x 2: rollout_tc_kernel<ENV, 128> + critic_values_tc_kernel<128>; otherwise the
+    layer-wise actor of rollout_wide.cu with the env step in rollout_tc_kernel<ENV, 0>) and the runtime-width SIMT kernel."""
+    if rollout_impl != "tc" and hidden not in (128, 256):
         pytest.skip("one kernel behind this path")
     pol, named = random_policy(4, 2, hidden, layers, False, seed=hidden)
     desc = kernels.policy_desc(4, 2, hidden, layers, False)
@@ -414,9 +416,10 @@ def test_cartpole_replay_runtime_width(hidden, layers, N, T, rollout_impl):
     assert np.array_equal(buf2.terminals.cpu().numpy(), done_s)
 
 
-def test_pendulum_replay_runtime_width(rollout_impl):
-    """Pendulum + wrappers at hidden 128: tensor-core kernels (tc) and the runtime-width SIMT kernel (simt)."""
-    N, T, hidden = 50, 260, 128
+@pytest.mark.parametrize("hidden", [128, 256])
+def test_pendulum_replay_runtime_width(hidden, rollout_impl):
+    """Pendulum + wrappers at hidden 128 / 256: tensor-core kernels (tc) and the runtime-width SIMT kernel (simt)."""
+    N, T = 50, 260
     pol, named = random_policy(3, 1, hidden, 2, True, seed=9)
     desc = kernels.policy_desc(3, 1, hidden, 2, True)
     flat = torch.from_numpy(flat_from_named(named)).cuda()

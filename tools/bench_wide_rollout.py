@@ -10,7 +10,10 @@ import torch
 from aur_ppo_b200 import _lib, envs as denv, kernels
 
 CASES = [("CartPole-v1", 4, 2, 64, False, 1), ("CartPole-v1", 4, 2, 128, False, 1), ("CartPole-v1", 4, 2, 128, False, 0),
-         ("Pendulum-v1", 3, 1, 128, True, 1), ("Pendulum-v1", 3, 1, 128, True, 0), ("CartPole-v1", 4, 2, 256, False, 1)]
+         ("Pendulum-v1", 3, 1, 128, True, 1), ("Pendulum-v1", 3, 1, 128, True, 0), ("CartPole-v1", 4, 2, 256, False, 1),
+         ("Pendulum-v1", 3, 1, 256, True, 1)]
+if os.environ.get("SKIP_SIMT"):
+    CASES = [c for c in CASES if c[5] == 1]
 N, T = 65536, 128
 L = _lib.lib()
 for gym_id, obs_dim, act_dim, H, cont, impl in CASES:
@@ -33,6 +36,6 @@ for gym_id, obs_dim, act_dim, H, cont, impl in CASES:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    print(json.dumps({"gym_id": gym_id, "hidden": H, "layers": 2, "kernels": "tcgen05" if (impl and H <= 128) else "simt", "num_envs": N,
+    print(json.dumps({"gym_id": gym_id, "hidden": H, "layers": 2, "kernels": "tcgen05" if impl else "simt", "num_envs": N,
                       "num_steps": T, "ms": round(ms, 3), "env_steps_per_s": N * T / ms * 1e3}), flush=True)
 L.aur_rollout_set_impl(1)
