@@ -89,31 +89,43 @@ __device__ __forceinline__ long long wide_row(const UpdDev& u, long long gi) {
 // thread = (sample, 8-feature chunk); W0 [H][obs_dim] | b0 [H] are this net's first parameters.  The grid stride is a multiple
 // of the chunks per sample, so a thread keeps ONE chunk for its whole loop and holds that chunk's weights in registers (read
 // per item they cost 16 L1 wavefronts per load: 281 us per sub-batch instead of 40).
-__global__ void __launch_bounds__(WD_THREADS) wide_first_kernel(UpdDev u, const float* __restrict__ W0, int H, long long g0, int ms,
-                                                                __nv_bfloat16* __restrict__ hb, size_t plane) {
+template <int IN>
+__global__ void __launch_bounds__(WD_THREADS, IN <= 4 ? 3 : 2) wide_first_kernel(UpdDev u, const float* __restrict__ W0, int H, long long g0, int ms,
+                                                                   __nv_bfloat16* __restrict__ hb, size_t plane) {
   const int LPS = H >> 3, obs_dim = u.obs_dim;
   const float* b0 = W0 + (size_t)H * obs_dim;
   const int c = threadIdx.x % LPS;
-  float w[8][WD_IN], b[8];
+  float w[8][IN], b[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     b[e] = __ldg(b0 + 8 * c + e);
 #pragma unroll
-    for (int k = 0; k < WD_IN; ++k) w[e][k] = k < obs_dim ? __ldg(W0 + (size_t)(8 * c + e) * obs_dim + k) : 0.0f;
+    for (int k = 0; k < IN; ++k) w[e][k] = k < obs_dim ? __ldg(W0 + (size_t)(8 * c + e) * obs_dim + k) : 0.0f;
   }
   const int SPP = WD_THREADS / LPS;
-  for (long long s = (long long)blockIdx.x * SPP + threadIdx.x / LPS; s < ms; s += (long long)gridDim.x * SPP) {
-    const long long row = wide_row(u, g0 + s);
-    float x[WD_IN];
+  const long long stride = (long long)gridDim.x * SPP;
+  // the index -> observation chain of the NEXT sample is in flight while this one is computed and stored
+  float xn[IN];
+  auto fetch = [&](long long s) {
+    if (s < ms) {
+      const long long row = wide_row(u, g0 + s);
 #pragma unroll
-    for (int k = 0; k < WD_IN; ++k) x[k] = k < obs_dim ? __ldg(u.obs + row * obs_dim + k) : 0.0f;
+      for (int k = 0; k < IN; ++k) xn[k] = k < obs_dim ? __ldg(u.obs + row * obs_dim + k) : 0.0f;
+    }
+  };
+  long long s = (long long)blockIdx.x * SPP + threadIdx.x / LPS;
+  fetch(s);
+  for (; s < ms; s += stride) {
+    float x[IN];
+#pragma unroll
+    for (int k = 0; k < IN; ++k) x[k] = xn[k];
+    fetch(s + stride);
     float h[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float z = b[e];
 #pragma unroll
-      for (int k = 0; k < WD_IN; ++k)
-        if (k < obs_dim) z = fmaf(w[e][k], x[k], z);
+      for (int k = 0; k < IN; ++k) z = fmaf(w[e][k], x[k], z);
       h[e] = tanh_fast(z);
     }
     tc::store8_planes(hb + (size_t)s * H + 8 * c, plane, WD_P, h);
@@ -179,7 +191,7 @@ struct WideHead {
 // sit side by side in a warp, the head is a butterfly sum over them (every lane ends up with the same bits), and all of them
 // evaluate the loss redundantly.
 template <int KIND, int OUT>
-__global__ void __launch_bounds__(WD_THREADS, 2) wide_head_kernel(UpdDev u, WideHead a) {
+__global__ void __launch_bounds__(WD_THREADS, (KIND == 2 || OUT == 1) ? 3 : 2) wide_head_kernel(UpdDev u, WideHead a) {
   constexpr bool ACTOR = KIND != 2;
   __shared__ __align__(16) float red[WD_THREADS * 8];
   __shared__ __align__(16) float sWL[4 * 256];
@@ -416,20 +428,20 @@ __device__ __forceinline__ void add_bf16x8(const uint4& q, float (&h)[8]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) { h[2 * j] += __uint_as_float(w[j] << 16); h[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u); }
 }
-template <bool FIRST>
-__global__ void __launch_bounds__(WD_THREADS, 2) wide_dact_kernel(UpdDev u, WideDact a) {
+template <bool FIRST, int IN>
+__global__ void __launch_bounds__(WD_THREADS, IN <= 4 ? 3 : 2) wide_dact_kernel(UpdDev u, WideDact a) {
   __shared__ __align__(16) float red[WD_THREADS * 8];
   const int H = a.H, LPS = H >> 3, SPP = WD_THREADS / LPS, obs_dim = u.obs_dim;
   const int tid = threadIdx.x, c = tid % LPS, so = tid / LPS;
   const int s_begin = blockIdx.x * WD_KC, s_end = min(a.ms, s_begin + WD_KC);
   float* prow = a.part + (size_t)blockIdx.x * a.pstride;
   float dbh[8];
-  float dW0[FIRST ? WD_IN : 1][8];
+  float dW0[FIRST ? IN : 1][8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     dbh[e] = 0.0f;
 #pragma unroll
-    for (int k = 0; k < (FIRST ? WD_IN : 1); ++k) dW0[k][e] = 0.0f;
+    for (int k = 0; k < (FIRST ? IN : 1); ++k) dW0[k][e] = 0.0f;
   }
   for (int s = s_begin + so; s < s_end; s += SPP) {
     const size_t o = (size_t)s * H + 8 * c;
@@ -443,7 +455,7 @@ __global__ void __launch_bounds__(WD_THREADS, 2) wide_dact_kernel(UpdDev u, Wide
     if (FIRST) {
       const long long row = wide_row(u, a.g0 + s);
 #pragma unroll
-      for (int k = 0; k < WD_IN; ++k) {
+      for (int k = 0; k < IN; ++k) {
         if (k < obs_dim) {
           const float x = __ldg(u.obs + row * obs_dim + k);
 #pragma unroll
@@ -458,7 +470,7 @@ __global__ void __launch_bounds__(WD_THREADS, 2) wide_dact_kernel(UpdDev u, Wide
   if (tid < H) put(prow + a.oB + tid, v, a.beta);
   if (FIRST) {
 #pragma unroll
-    for (int k = 0; k < WD_IN; ++k) {
+    for (int k = 0; k < IN; ++k) {
       if (k < obs_dim) {
         v = chunk_col_sum(dW0[FIRST ? k : 0], red, H);
         if (tid < H) put(prow + a.oW0 + (size_t)tid * obs_dim + k, v, a.beta);
@@ -602,7 +614,8 @@ static int launch_gemm_tn(const __nv_bfloat16* A, const __nv_bfloat16* B, size_t
 // TMEM accumulators, and the four epilogue warps store tile t while the tensor core works on t + 1.
 constexpr int SG_ATOM = 128 * 128;                       // 128 rows x 64 K values (128-B rows)
 constexpr int SG_STAGE = WD_P * 2 * SG_ATOM, SG_STAGES = 2;
-constexpr size_t SG_SMEM = (size_t)SG_STAGE * (1 + SG_STAGES) + 1024 + 256;
+constexpr int SG_PATCH = 32 * 33 * 4;                    // per epilogue warp: a 32 x 32 fp32 block, rows padded to 33 words
+constexpr size_t SG_SMEM = (size_t)SG_STAGE * (1 + SG_STAGES) + 4 * SG_PATCH + 1024 + 256;
 __global__ void __launch_bounds__(192, 1)
 wide_gemm128_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C, int M) {
   using namespace tc;
@@ -610,7 +623,8 @@ wide_gemm128_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sB = smem;
   unsigned char* sA = smem + SG_STAGE;
-  uint64_t* bfull = reinterpret_cast<uint64_t*>(sA + SG_STAGES * SG_STAGE);
+  float* patches = reinterpret_cast<float*>(sA + SG_STAGES * SG_STAGE);
+  uint64_t* bfull = reinterpret_cast<uint64_t*>(sA + SG_STAGES * SG_STAGE + 4 * SG_PATCH);
   uint64_t* full = bfull + 1;
   uint64_t* empty = full + SG_STAGES;
   uint64_t* tfull = empty + SG_STAGES;      // [2]
@@ -675,16 +689,21 @@ wide_gemm128_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t acc = it & 1u;
       mbar_wait(&tfull[acc], (it >> 1) & 1u);
       fence_after_sync();
-      const long long row = (long long)tile * 128 + 32 * q + lane;
+      // a thread holds 32 consecutive columns of ITS row; stored like that a warp instruction would touch 32 rows (32 LSU
+      // wavefronts).  The warp transposes each 32 x 32 block through a padded patch instead: every store is one 128-B row segment.
+      const long long row0 = (long long)tile * 128 + 32 * q;
+      float* patch = patches + (warp - 2) * (SG_PATCH / 4);
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
         float v[32];
         tmem_ld32(tmem_d + acc * 128 + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * g), v);
-        if (row < M) {
-          float4* dst = reinterpret_cast<float4*>(C + row * 128 + 32 * g);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
+        for (int i = 0; i < 32; ++i) patch[lane * 33 + i] = v[i];
+        __syncwarp();
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r)
+          if (row0 + r < M) C[(row0 + r) * 128 + 32 * g + lane] = patch[r * 33 + lane];
+        __syncwarp();
       }
       fence_before_sync();
       __syncwarp();
@@ -767,7 +786,8 @@ int launch_ppo_grad_wide(const UpdDev& d, const aur_policy_desc& p, float* ws, i
       const int ms = (int)((m - g0) < WD_MS ? (m - g0) : WD_MS);
       const int rows = (ms + WD_KC - 1) / WD_KC;
       const int beta = g0 > 0 ? 1 : 0;
-      wide_first_kernel<<<ew_grid, WD_THREADS, 0, s>>>(d, np, H, g0, ms, hb(1), L.plane);
+      if (obs_dim <= 4) wide_first_kernel<4><<<ew_grid, WD_THREADS, 0, s>>>(d, np, H, g0, ms, hb(1), L.plane);
+      else wide_first_kernel<8><<<ew_grid, WD_THREADS, 0, s>>>(d, np, H, g0, ms, hb(1), L.plane);
       AUR_LAUNCH_OK("wide_first_kernel");
       for (int l = 1; l <= NL - 1; ++l) {
         if ((rc = wide_gemm(H, hb(l), L.plane, Wp(l), L.wplane, ms, Z, s))) return rc;
@@ -803,11 +823,12 @@ int launch_ppo_grad_wide(const UpdDev& d, const aur_policy_desc& p, float* ws, i
         a.g0 = g0; a.part = npart; a.oW0 = 0;
         if (l > 1) {
           a.oB = oWh + (size_t)(l - 2) * hstride + (size_t)H * H;
-          wide_dact_kernel<false><<<rows, WD_THREADS, 0, s>>>(d, a);
+          wide_dact_kernel<false, 4><<<rows, WD_THREADS, 0, s>>>(d, a);
           cur ^= 1;
         } else {
           a.oB = oB0;
-          wide_dact_kernel<true><<<rows, WD_THREADS, 0, s>>>(d, a);
+          if (obs_dim <= 4) wide_dact_kernel<true, 4><<<rows, WD_THREADS, 0, s>>>(d, a);
+          else wide_dact_kernel<true, 8><<<rows, WD_THREADS, 0, s>>>(d, a);
         }
         AUR_LAUNCH_OK("wide_dact_kernel");
       }
