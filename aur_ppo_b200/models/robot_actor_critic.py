@@ -26,7 +26,7 @@ from torch import nn
 from .. import _lib
 from .. import plain_cnn
 from ..equiv import ENC_FIELDS, N_ACT, EquivActorCritic, init_params
-from ..kernels import _ptr, _stream, tc_gemm_bf16, tc_precision
+from ..kernels import _ptr, _stream, squashed_gaussian_sample, tc_gemm_bf16, tc_precision
 
 
 class _PsiNet(nn.Module):
@@ -164,6 +164,27 @@ class robot_actor_critic(nn.Module):
         """robot_actor_critic.py:104-131 -> (actions, unscaled_actions, log_prob.sum(1), entropy.sum(1), value [B,1])."""
         o = self._run(state, obs, action, True, True)
         return o["scaled"], o["unscaled"], o["logp"], o["ent"], o["value"].reshape(-1, 1)
+
+    def evaluate_pretrain(self, state, obs, action=None):
+        """robot_actor_critic.py:134-149 (the actor alone, for the behaviour-cloning phase): action = tanh(Normal(mean,
+        exp(logstd)).rsample()) - or tanh(action) when one is given - through decodeActions -> (scaled, unscaled), both fp16
+        as in the reference.  The draw is the squashed-Gaussian kernel's Philox stream (aur_squashed_gaussian_sample)."""
+        o = self._run(state, obs, None, True, False)
+        if action is None:
+            self._calls += 1
+            y = squashed_gaussian_sample(o["mean"].contiguous(), o["logstd"].contiguous(), None, seed=self.seed, stream_id=self._calls)[0]
+        else:
+            y = torch.tanh(action.to(self.device, torch.float32).reshape(-1, self.n_a))
+        unscaled, scaled = self.decodeActions(*[y[:, i] for i in range(self.n_a)])
+        return scaled.to(torch.float16), unscaled.to(torch.float16)
+
+    @staticmethod
+    def pretrain_loss(b_actions, b_true_actions, mb_inds):
+        """robot_ppo.py:291-307 `pretrain_update`: mse_loss(b_actions[mb], b_true_actions[mb]).  In the reference the stored
+        actions are buffer tensors with no graph back to the policy (`.requires_grad_(True)` makes them leaves), so
+        `expert_loss.backward()` reaches no parameter and `optimizer.step()` leaves the policy unchanged: the phase's only
+        numerical product is this scalar, which is what is restated here."""
+        return torch.mean((b_actions[mb_inds].float() - b_true_actions[mb_inds].float()) ** 2)
 
     def test_action(self, state, obs):
         """robot_actor_critic.py:152-157: decodeActions(tanh(mean))."""

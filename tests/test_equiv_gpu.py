@@ -274,6 +274,14 @@ def test_robot_actor_critic_facade_matches_oracle_evaluate():
     un_p, sc_p = m.getActionFromPlan(plan)
     assert float(un_p.abs().max()) <= 1.0 + 1e-6
     torch.testing.assert_close(sc_p, plan, rtol=1e-5, atol=1e-7)
+    # evaluate_pretrain (robot_actor_critic.py:134-149): tanh of the given / sampled action through decodeActions, fp16 pair
+    sc16, un16 = m.evaluate_pretrain(state, obs, action.cuda())
+    un_t2, sc_t2 = m.decodeActions(*[torch.tanh(action.cuda())[:, i] for i in range(5)])
+    assert sc16.dtype == un16.dtype == torch.float16 and torch.equal(sc16, sc_t2.half()) and torch.equal(un16, un_t2.half())
+    d1, d2 = m.evaluate_pretrain(state, obs), m.evaluate_pretrain(state, obs)
+    assert not torch.equal(d1[1], d2[1]) and float(d1[1].float().abs().max()) <= 1.0 and bool(torch.isfinite(d1[0].float()).all())
+    mb = torch.arange(4, device="cuda")
+    assert abs(float(m.pretrain_loss(d1[0], d2[0], mb)) - float(torch.nn.functional.mse_loss(d1[0][mb].float(), d2[0][mb].float()))) < 1e-7
     # the update engine trains the module's own storage
     e = m.engine(8)
     assert e.p["actor.enc3.psi"].data_ptr() == m.actor.enc3_psi.data_ptr()
