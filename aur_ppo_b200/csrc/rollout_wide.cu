@@ -13,8 +13,7 @@
 namespace aur {
 
 namespace tc {
-int launch_tc_gemm(int64_t M, int64_t N, int64_t K, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int ldc,
-                   int planes, cudaStream_t stream);
+int launch_wide_gemm(int64_t M, int H, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int planes, cudaStream_t s);
 }
 int launch_rollout_step_ext(const RolloutDev& d, int env_kind, cudaStream_t s);
 
@@ -163,7 +162,7 @@ static int rows_forward(const float* net, const __nv_bfloat16* wp, int obs_dim, 
     rows_first_kernel<<<grid, RW_THREADS, 0, s>>>(X + m0 * obs_dim, obs_dim, net, H, ms, sc.hb[0], sc.plane);
     AUR_LAUNCH_OK("rows_first_kernel");
     for (int l = 1; l <= NL - 1; ++l) {
-      int rc = tc::launch_tc_gemm(ms, H, H, sc.hb[cur], sc.plane, wp + (size_t)(l - 1) * RW_P * wplane, wplane, sc.Z, H, RW_P, s);
+      int rc = tc::launch_wide_gemm(ms, H, sc.hb[cur], sc.plane, wp + (size_t)(l - 1) * RW_P * wplane, wplane, sc.Z, RW_P, s);
       if (rc) return rc;
       if (l < NL - 1) {
         rows_act_kernel<<<grid, RW_THREADS, 0, s>>>(sc.Z, wh + (size_t)(l - 1) * hstride + wplane, H, ms, sc.hb[cur ^ 1], sc.plane);

@@ -185,6 +185,157 @@ int launch_tc_gemm(int64_t M, int64_t N, int64_t K, const void* A, size_t a_plan
 }  // namespace tc
 }  // namespace aur
 
+namespace aur {
+namespace tc {
+// ---- persistent GEMM for the wide-policy paths (update_wide.cu, rollout_wide.cu): C[M][H] = A[M][H] B[H][H]^T, H = 64 KB_, with
+// very tall M and K = H of only 128 / 256.  The per-tile kernel above spends most of such a tile on its own prologue, operand
+// re-loads per plane product and an epilogue that cannot overlap anything (242 us for 536 MB at H = 256).  Here a CTA keeps its
+// NB output columns' worth of B (all planes, all of K) resident in shared memory and walks 128-row tiles: a stage holds every
+// plane of one 64-wide K block of A, all plane products are issued from it, two TMEM accumulators let the four epilogue warps
+// store tile t (transposed through padded patches: every store is a 128-byte row segment) while tile t + 1 multiplies.
+template <int P, int KB_, int NB>
+struct SkCfg {
+  static constexpr int A_ATOM = 128 * 128, B_ATOM = NB * 128;
+  static constexpr int B_BYTES = P * KB_ * B_ATOM, STAGE = P * A_ATOM, STAGES = 2, PATCH = 32 * 33 * 4;
+  static constexpr size_t SMEM = (size_t)B_BYTES + STAGES * STAGE + 4 * PATCH + 1024 + 256;
+};
+template <int P, int KB_, int NB>
+__global__ void __launch_bounds__(192, 1)
+skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C, int M) {
+  using Cfg = SkCfg<P, KB_, NB>;
+  constexpr int H = 64 * KB_, NBLK = H / NB, NT = P == 1 ? 1 : (P == 2 ? 3 : 6);
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sB = smem;
+  unsigned char* sA = smem + Cfg::B_BYTES;
+  float* patches = reinterpret_cast<float*>(sA + Cfg::STAGES * Cfg::STAGE);
+  uint64_t* bfull = reinterpret_cast<uint64_t*>(sA + Cfg::STAGES * Cfg::STAGE + 4 * Cfg::PATCH);
+  uint64_t* full = bfull + 1;
+  uint64_t* empty = full + Cfg::STAGES;
+  uint64_t* tfull = empty + Cfg::STAGES;    // [2]
+  uint64_t* tempty = tfull + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = (M + 127) / 128;
+  const int nb = blockIdx.x % NBLK, t0 = blockIdx.x / NBLK, tstep = gridDim.x / NBLK;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bfull, 1);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_fence_init();
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * NB < 32 ? 32 : 2 * NB);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    mbar_arrive_expect_tx(bfull, Cfg::B_BYTES);
+    for (int p = 0; p < P; ++p)
+      for (int kb = 0; kb < KB_; ++kb) tma_load_3d(sB + (p * KB_ + kb) * Cfg::B_ATOM, &tmB, 64 * kb, nb * NB, p, bfull);
+    uint32_t it = 0;
+    for (int tile = t0; tile < ntiles; tile += tstep)
+      for (int kb = 0; kb < KB_; ++kb, ++it) {
+        const int s = it % Cfg::STAGES;
+        mbar_wait(&empty[s], ((it / Cfg::STAGES) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
+        for (int p = 0; p < P; ++p) tma_load_3d(sA + s * Cfg::STAGE + p * Cfg::A_ATOM, &tmA, 64 * kb, tile * 128, p, &full[s]);
+      }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = instr_desc(FMT_BF16, 128, NB, 0, 0);
+    mbar_wait(bfull, 0);
+    uint32_t it = 0, ti = 0;
+    for (int tile = t0; tile < ntiles; tile += tstep, ++ti) {
+      const uint32_t acc = ti & 1u;
+      mbar_wait(&tempty[acc], ((ti >> 1) & 1u) ^ 1u);
+      fence_after_sync();
+      for (int kb = 0; kb < KB_; ++kb, ++it) {
+        const int s = it % Cfg::STAGES;
+        mbar_wait(&full[s], (it / Cfg::STAGES) & 1u);
+        fence_after_sync();
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const uint64_t ad = smem_desc_k_sw128(sA + s * Cfg::STAGE + term_plane_a(t) * Cfg::A_ATOM);
+          const uint64_t bd = smem_desc_k_sw128(sB + (term_plane_b(t) * KB_ + kb) * Cfg::B_ATOM);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_f16(tmem_d + acc * NB, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | t | k) != 0);
+        }
+        mma_commit(&empty[s]);
+      }
+      mma_commit(&tfull[acc]);
+    }
+  } else if (warp >= 2) {
+    const int q = warp & 3;
+    float* patch = patches + (warp - 2) * (Cfg::PATCH / 4);
+    uint32_t ti = 0;
+    for (int tile = t0; tile < ntiles; tile += tstep, ++ti) {
+      const uint32_t acc = ti & 1u;
+      mbar_wait(&tfull[acc], (ti >> 1) & 1u);
+      fence_after_sync();
+      const long long row0 = (long long)tile * 128 + 32 * q;
+#pragma unroll 1
+      for (int g = 0; g < NB / 32; ++g) {
+        float v[32];
+        tmem_ld32(tmem_d + acc * NB + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * g), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) patch[lane * 33 + i] = v[i];
+        __syncwarp();
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r)
+          if (row0 + r < M) C[(row0 + r) * H + nb * NB + 32 * g + lane] = patch[r * 33 + lane];
+        __syncwarp();
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, 2 * NB < 32 ? 32 : 2 * NB);
+}
+
+template <int P, int KB_, int NB>
+static int launch_skinny(int64_t M, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, cudaStream_t s) {
+  using Cfg = SkCfg<P, KB_, NB>;
+  constexpr int H = 64 * KB_, NBLK = H / NB;
+  static_assert(Cfg::SMEM <= 232448, "skinny GEMM configuration does not fit shared memory");
+  CUtensorMap tmA, tmB;
+  const uint64_t dA[3] = {(uint64_t)H, (uint64_t)M, (uint64_t)P}, dB[3] = {(uint64_t)H, (uint64_t)H, (uint64_t)P};
+  const uint64_t stA[2] = {(uint64_t)H * 2, (uint64_t)a_plane * 2}, stB[2] = {(uint64_t)H * 2, (uint64_t)b_plane * 2};
+  const uint32_t boxA[3] = {64, 128, 1}, boxB[3] = {64, NB, 1};
+  int rc;
+  if ((rc = make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, A, dA, stA, boxA))) return rc;
+  if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, B, dB, stB, boxB))) return rc;
+  static DeviceOnce attr;
+  if (attr.first()) {
+    AUR_CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel<P, KB_, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr.done();
+  }
+  const long long ntiles = (M + 127) / 128;
+  long long per = sm_count() / NBLK;
+  if (per < 1) per = 1;
+  if (per > ntiles) per = ntiles;
+  skinny_gemm_kernel<P, KB_, NB><<<(unsigned)(per * NBLK), 192, Cfg::SMEM, s>>>(tmA, tmB, C, (int)M);
+  AUR_LAUNCH_OK("skinny_gemm_kernel");
+  return 0;
+}
+
+// C[M][H] (fp32, dense rows) = A planes [M][H] x B planes [H][H]^T for the wide-policy paths; shapes without a resident-B
+// configuration fall through to the per-tile kernel
+int launch_wide_gemm(int64_t M, int H, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int planes, cudaStream_t s) {
+  if (H == 256 && planes == 2) return launch_skinny<2, 4, 128>(M, A, a_plane, B, b_plane, C, s);
+  if (H == 256 && planes == 3) return launch_skinny<3, 4, 64>(M, A, a_plane, B, b_plane, C, s);
+  if (H == 128 && planes == 3) return launch_skinny<3, 2, 128>(M, A, a_plane, B, b_plane, C, s);
+  return launch_tc_gemm(M, H, H, A, a_plane, B, b_plane, C, H, planes, s);
+}
+}  // namespace tc
+}  // namespace aur
+
 extern "C" int aur_tc_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, const void* B, float* C, void* stream) {
   using namespace aur;
   if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) { set_error("aur_tc_gemm_bf16: bad arguments"); return AUR_ERR_ARG; }

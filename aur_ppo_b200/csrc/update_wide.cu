@@ -28,6 +28,7 @@ namespace aur {
 namespace tc {
 int launch_tc_gemm(int64_t M, int64_t N, int64_t K, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int ldc,
                    int planes, cudaStream_t stream);
+int launch_wide_gemm(int64_t M, int H, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int planes, cudaStream_t s);
 }
 int gen_pstride(const aur_policy_desc& p);      // update_generic.cu: the partial stride of every non-headline shape
 
@@ -717,7 +718,7 @@ wide_gemm128_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // Z[ms][H] = A planes [ms][H] x B planes [H][H]^T
 static int wide_gemm(int H, const __nv_bfloat16* A, size_t a_plane, const __nv_bfloat16* B, size_t b_plane, int ms, float* Z, cudaStream_t s) {
-  if (H != 128) return tc::launch_tc_gemm(ms, H, H, A, a_plane, B, b_plane, Z, H, WD_P, s);
+  if (H != 128) return tc::launch_wide_gemm(ms, H, A, a_plane, B, b_plane, Z, WD_P, s);
   CUtensorMap tmA, tmB;
   const uint64_t dA[3] = {128, (uint64_t)ms, (uint64_t)WD_P}, dB[3] = {128, 128, (uint64_t)WD_P};
   const uint64_t stA[2] = {256, (uint64_t)a_plane * 2}, stB[2] = {256, (uint64_t)b_plane * 2};
