@@ -1,7 +1,7 @@
 // Rollout for the policy widths whose second-layer weights do not fit shared memory beside an env tile (`--hidden_dim 256`, or
 // 128 with more than two layers; src/run_ppo.py:36,38): the actor runs LAYER BY LAYER over all N envs each step, its H x H
-// contractions as tcgen05 GEMMs over three-plane bf16 operands (hi + mid + lo, six products: fp32-equivalent, the log-probs are
-// compared with the reference at 2e-5), and the env / sampling / bookkeeping part is the tensor-core rollout kernel itself in
+// contractions as tcgen05 GEMMs over two-plane bf16 operands with all four plane products (the precision of rollout_tc_kernel: the
+// log-probs are compared with the reference at 2e-5; the value pass uses three planes / six products, values are compared at 2e-6), and the env / sampling / bookkeeping part is the tensor-core rollout kernel itself in
 // its external-actor mode (rollout_tc_kernel<ENV, 0>: same fp64 physics, Philox streams, autoreset and episode log, so the
 // replay tests do not change).  Per step: rows_first_kernel (first layer -> h planes), tc_gemm, [rows_act_kernel per middle
 // layer], rows_head_kernel (tanh + output layer -> logits [N][4]), rollout step.  The T*N critic values are the same three
@@ -13,11 +13,13 @@
 namespace aur {
 
 namespace tc {
-int launch_wide_gemm(int64_t M, int H, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int planes, cudaStream_t s);
+int launch_wide_gemm(int64_t M, int H, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int planes, cudaStream_t s,
+                     bool mid_mid = false);
 }
 int launch_rollout_step_ext(const RolloutDev& d, int env_kind, cudaStream_t s);
 
-constexpr int RW_P = 3;
+constexpr int RW_P = 3;                      // planes of the value pass (values are compared at 2e-6) and of the scratch layout
+constexpr int RW_P_ACTOR = 2;                // the per-step actor: two planes, four products (hi*hi, hi*mid, mid*hi, mid*mid) like rollout_tc_kernel
 constexpr int RW_MS = 262144;
 constexpr int RW_THREADS = 256;
 
@@ -27,20 +29,20 @@ bool rollout_wide_eligible(const aur_policy_desc& p, int env_kind) {
 }
 
 // hidden-layer weights W_1 .. W_{NL-1} of one net -> operand planes [layer][plane][H][H]
-__global__ void rows_prep_kernel(const float* __restrict__ wh, int nlayers, int H, __nv_bfloat16* __restrict__ wp) {
+__global__ void rows_prep_kernel(const float* __restrict__ wh, int nlayers, int H, __nv_bfloat16* __restrict__ wp, int P) {
   const size_t hstride = (size_t)H * H + H, wplane = (size_t)H * H;
   const long long total = (long long)nlayers * H * H;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int l = (int)(i / (long long)wplane);
     const size_t r = (size_t)(i - (long long)l * (long long)wplane);
-    tc::store_planes(wp + (size_t)l * RW_P * wplane + r, wplane, RW_P, wh[(size_t)l * hstride + r]);
+    tc::store_planes(wp + (size_t)l * P * wplane + r, wplane, P, wh[(size_t)l * hstride + r]);
   }
 }
 
 // first layer over contiguous rows: h = tanh(W0 x + b0) -> planes [P][.][H]; thread = (row, 8-feature chunk), the chunk's weights
 // in registers for the whole loop
 __global__ void __launch_bounds__(RW_THREADS) rows_first_kernel(const float* __restrict__ X, int obs_dim, const float* __restrict__ W0, int H,
-                                                                long long M, __nv_bfloat16* __restrict__ hb, size_t plane) {
+                                                                long long M, __nv_bfloat16* __restrict__ hb, size_t plane, int P) {
   const int LPS = H >> 3, SPP = RW_THREADS / LPS;
   const float* b0 = W0 + (size_t)H * obs_dim;
   const int c = threadIdx.x % LPS;
@@ -63,13 +65,13 @@ __global__ void __launch_bounds__(RW_THREADS) rows_first_kernel(const float* __r
       for (int k = 0; k < POL_IN_PAD; ++k) z = fmaf(w[e][k], x[k], z);
       h[e] = tanh_fast(z);
     }
-    tc::store8_planes(hb + (size_t)r * H + 8 * c, plane, RW_P, h);
+    tc::store8_planes(hb + (size_t)r * H + 8 * c, plane, P, h);
   }
 }
 
 // middle layers: h = tanh(z + b) -> planes
 __global__ void __launch_bounds__(RW_THREADS) rows_act_kernel(const float* __restrict__ Z, const float* __restrict__ bias, int H, long long M,
-                                                              __nv_bfloat16* __restrict__ hb, size_t plane) {
+                                                              __nv_bfloat16* __restrict__ hb, size_t plane, int P) {
   const int LPS = H >> 3;
   const long long items = M * LPS;
   for (long long it = (long long)blockIdx.x * RW_THREADS + threadIdx.x; it < items; it += (long long)gridDim.x * RW_THREADS) {
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(RW_THREADS) rows_act_kernel(const float* __res
     const float* b = bias + 8 * c;
     float h[8] = {tanh_fast(za.x + __ldg(b)), tanh_fast(za.y + __ldg(b + 1)), tanh_fast(za.z + __ldg(b + 2)), tanh_fast(za.w + __ldg(b + 3)),
                   tanh_fast(zb.x + __ldg(b + 4)), tanh_fast(zb.y + __ldg(b + 5)), tanh_fast(zb.z + __ldg(b + 6)), tanh_fast(zb.w + __ldg(b + 7))};
-    tc::store8_planes(hb + it * 8, plane, RW_P, h);
+    tc::store8_planes(hb + it * 8, plane, P, h);
   }
 }
 
@@ -150,8 +152,8 @@ static size_t rw_layout(const aur_policy_desc& p, long long N, unsigned char* ba
 }
 
 // out[M][ldo] = MLP(X[M][obs_dim]) for one net of the flat parameter buffer, hidden layers on tensor cores
-static int rows_forward(const float* net, const __nv_bfloat16* wp, int obs_dim, int H, int NL, int OUT, const float* X, long long M, float* out,
-                        int ldo, const RwScratch& sc, cudaStream_t s) {
+static int rows_forward(const float* net, const __nv_bfloat16* wp, int P, int obs_dim, int H, int NL, int OUT, const float* X, long long M,
+                        float* out, int ldo, const RwScratch& sc, cudaStream_t s) {
   const size_t hstride = (size_t)H * H + H, wplane = (size_t)H * H;
   const float* wh = net + (size_t)H * obs_dim + H;                    // W_1 | b_1 | ...
   const float* WL = wh + (size_t)(NL - 1) * hstride;
@@ -159,13 +161,13 @@ static int rows_forward(const float* net, const __nv_bfloat16* wp, int obs_dim, 
   for (long long m0 = 0; m0 < M; m0 += RW_MS) {
     const long long ms = (M - m0) < RW_MS ? (M - m0) : RW_MS;
     int cur = 0;
-    rows_first_kernel<<<grid, RW_THREADS, 0, s>>>(X + m0 * obs_dim, obs_dim, net, H, ms, sc.hb[0], sc.plane);
+    rows_first_kernel<<<grid, RW_THREADS, 0, s>>>(X + m0 * obs_dim, obs_dim, net, H, ms, sc.hb[0], sc.plane, P);
     AUR_LAUNCH_OK("rows_first_kernel");
     for (int l = 1; l <= NL - 1; ++l) {
-      int rc = tc::launch_wide_gemm(ms, H, sc.hb[cur], sc.plane, wp + (size_t)(l - 1) * RW_P * wplane, wplane, sc.Z, RW_P, s);
+      int rc = tc::launch_wide_gemm(ms, H, sc.hb[cur], sc.plane, wp + (size_t)(l - 1) * P * wplane, wplane, sc.Z, P, s, P == 2);
       if (rc) return rc;
       if (l < NL - 1) {
-        rows_act_kernel<<<grid, RW_THREADS, 0, s>>>(sc.Z, wh + (size_t)(l - 1) * hstride + wplane, H, ms, sc.hb[cur ^ 1], sc.plane);
+        rows_act_kernel<<<grid, RW_THREADS, 0, s>>>(sc.Z, wh + (size_t)(l - 1) * hstride + wplane, H, ms, sc.hb[cur ^ 1], sc.plane, P);
         AUR_LAUNCH_OK("rows_act_kernel");
         cur ^= 1;
       }
@@ -187,21 +189,21 @@ int launch_rollout_wide(const RolloutDev& d, const aur_policy_desc& p, int env_k
   const float* actor = d.params;
   const float* critic = d.params + nA;
   const unsigned pgrid = (unsigned)(((size_t)(NL - 1) * H * H + 255) / 256);
-  rows_prep_kernel<<<pgrid, 256, 0, s>>>(actor + (size_t)H * obs_dim + H, NL - 1, H, sc.wp_actor);
+  rows_prep_kernel<<<pgrid, 256, 0, s>>>(actor + (size_t)H * obs_dim + H, NL - 1, H, sc.wp_actor, RW_P_ACTOR);
   AUR_LAUNCH_OK("rows_prep_kernel");
-  rows_prep_kernel<<<pgrid, 256, 0, s>>>(critic + (size_t)H * obs_dim + H, NL - 1, H, sc.wp_critic);
+  rows_prep_kernel<<<pgrid, 256, 0, s>>>(critic + (size_t)H * obs_dim + H, NL - 1, H, sc.wp_critic, RW_P);
   AUR_LAUNCH_OK("rows_prep_kernel");
   int rc;
   RolloutDev step = d;
   step.T = 1;
   step.ext_logits = sc.logits;
   for (int t = 0; t < d.T; ++t) {
-    if ((rc = rows_forward(actor, sc.wp_actor, obs_dim, H, NL, p.act_dim, d.next_obs, d.N, sc.logits, 4, sc, s))) return rc;
+    if ((rc = rows_forward(actor, sc.wp_actor, RW_P_ACTOR, obs_dim, H, NL, p.act_dim, d.next_obs, d.N, sc.logits, 4, sc, s))) return rc;
     step.t0 = t;
     if ((rc = launch_rollout_step_ext(step, env_kind, s))) return rc;
   }
-  if ((rc = rows_forward(critic, sc.wp_critic, obs_dim, H, NL, 1, d.obs_buf, (long long)d.T * d.N, d.val_buf, 1, sc, s))) return rc;
-  if (d.next_value && (rc = rows_forward(critic, sc.wp_critic, obs_dim, H, NL, 1, d.next_obs, d.N, d.next_value, 1, sc, s))) return rc;
+  if ((rc = rows_forward(critic, sc.wp_critic, RW_P, obs_dim, H, NL, 1, d.obs_buf, (long long)d.T * d.N, d.val_buf, 1, sc, s))) return rc;
+  if (d.next_value && (rc = rows_forward(critic, sc.wp_critic, RW_P, obs_dim, H, NL, 1, d.next_obs, d.N, d.next_value, 1, sc, s))) return rc;
   return 0;
 }
 

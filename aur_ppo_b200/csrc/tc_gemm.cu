@@ -199,11 +199,13 @@ struct SkCfg {
   static constexpr int B_BYTES = P * KB_ * B_ATOM, STAGE = P * A_ATOM, STAGES = 2, PATCH = 32 * 33 * 4;
   static constexpr size_t SMEM = (size_t)B_BYTES + STAGES * STAGE + 4 * PATCH + 1024 + 256;
 };
-template <int P, int KB_, int NB>
+// NT: plane products issued per K step, in the order of term_plane_a / term_plane_b - 3 (hi*hi, hi*mid, mid*hi) or 4 (+ mid*mid,
+// the rollout's log-prob precision) for two planes, 6 for three
+template <int P, int KB_, int NB, int NT>
 __global__ void __launch_bounds__(192, 1)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C, int M) {
   using Cfg = SkCfg<P, KB_, NB>;
-  constexpr int H = 64 * KB_, NBLK = H / NB, NT = P == 1 ? 1 : (P == 2 ? 3 : 6);
+  constexpr int H = 64 * KB_, NBLK = H / NB;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sB = smem;
@@ -299,7 +301,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_d, 2 * NB < 32 ? 32 : 2 * NB);
 }
 
-template <int P, int KB_, int NB>
+template <int P, int KB_, int NB, int NT>
 static int launch_skinny(int64_t M, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, cudaStream_t s) {
   using Cfg = SkCfg<P, KB_, NB>;
   constexpr int H = 64 * KB_, NBLK = H / NB;
@@ -313,24 +315,27 @@ static int launch_skinny(int64_t M, const void* A, size_t a_plane, const void* B
   if ((rc = make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, B, dB, stB, boxB))) return rc;
   static DeviceOnce attr;
   if (attr.first()) {
-    AUR_CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel<P, KB_, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    AUR_CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel<P, KB_, NB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr.done();
   }
   const long long ntiles = (M + 127) / 128;
   long long per = sm_count() / NBLK;
   if (per < 1) per = 1;
   if (per > ntiles) per = ntiles;
-  skinny_gemm_kernel<P, KB_, NB><<<(unsigned)(per * NBLK), 192, Cfg::SMEM, s>>>(tmA, tmB, C, (int)M);
+  skinny_gemm_kernel<P, KB_, NB, NT><<<(unsigned)(per * NBLK), 192, Cfg::SMEM, s>>>(tmA, tmB, C, (int)M);
   AUR_LAUNCH_OK("skinny_gemm_kernel");
   return 0;
 }
 
 // C[M][H] (fp32, dense rows) = A planes [M][H] x B planes [H][H]^T for the wide-policy paths; shapes without a resident-B
 // configuration fall through to the per-tile kernel
-int launch_wide_gemm(int64_t M, int H, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int planes, cudaStream_t s) {
-  if (H == 256 && planes == 2) return launch_skinny<2, 4, 128>(M, A, a_plane, B, b_plane, C, s);
-  if (H == 256 && planes == 3) return launch_skinny<3, 4, 64>(M, A, a_plane, B, b_plane, C, s);
-  if (H == 128 && planes == 3) return launch_skinny<3, 2, 128>(M, A, a_plane, B, b_plane, C, s);
+int launch_wide_gemm(int64_t M, int H, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int planes, cudaStream_t s,
+                     bool mid_mid = false) {
+  if (H == 256 && planes == 2) return mid_mid ? launch_skinny<2, 4, 128, 4>(M, A, a_plane, B, b_plane, C, s) : launch_skinny<2, 4, 128, 3>(M, A, a_plane, B, b_plane, C, s);
+  if (H == 256 && planes == 3) return launch_skinny<3, 4, 64, 6>(M, A, a_plane, B, b_plane, C, s);
+  if (H == 128 && planes == 3) return launch_skinny<3, 2, 128, 6>(M, A, a_plane, B, b_plane, C, s);
+  if (H == 128 && planes == 2 && mid_mid) return launch_skinny<2, 2, 128, 4>(M, A, a_plane, B, b_plane, C, s);
+  if (mid_mid) { set_error("launch_wide_gemm: no four-product configuration for H = %d", H); return AUR_ERR_UNSUPPORTED; }
   return launch_tc_gemm(M, H, H, A, a_plane, B, b_plane, C, H, planes, s);
 }
 }  // namespace tc

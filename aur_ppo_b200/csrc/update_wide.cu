@@ -28,7 +28,8 @@ namespace aur {
 namespace tc {
 int launch_tc_gemm(int64_t M, int64_t N, int64_t K, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int ldc,
                    int planes, cudaStream_t stream);
-int launch_wide_gemm(int64_t M, int H, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int planes, cudaStream_t s);
+int launch_wide_gemm(int64_t M, int H, const void* A, size_t a_plane, const void* B, size_t b_plane, float* C, int planes, cudaStream_t s,
+                     bool mid_mid = false);
 }
 int gen_pstride(const aur_policy_desc& p);      // update_generic.cu: the partial stride of every non-headline shape
 
