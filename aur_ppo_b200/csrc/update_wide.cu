@@ -211,7 +211,11 @@ __global__ void __launch_bounds__(WD_THREADS, (KIND == 2 || OUT == 1) ? 3 : 2) w
     sd[k] = expf(l); ls[k] = logf(sd[k]);                 // torch Normal: log(exp(logstd))
   }
   float adv_mean = 0.0f, adv_den = 1.0f;
-  if (ACTOR && u.norm_adv) adv_norm_consts(u, adv_mean, adv_den);
+  if (ACTOR && u.norm_adv) {           // ONE thread reads the moments (data-parallel: waits for the peers' flags), the CTA shares them
+    if (tid == 0) { adv_norm_consts(u, adv_mean, adv_den); sred[0] = adv_mean; sred[1] = adv_den; }
+    __syncthreads();
+    adv_mean = sred[0]; adv_den = sred[1];
+  }
   float bias[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) bias[e] = __ldg(a.bias + 8 * c + e);
