@@ -489,7 +489,9 @@ __global__ void __launch_bounds__(WD_THREADS, IN <= 4 ? 3 : 2) wide_dact_kernel(
 // A = delta planes, B = activation planes, both [ms][H] row-major (features contiguous): MN-major UMMA operands, a stage holds
 // for BOTH planes of both operands the boxes of 64 samples x 64 features (8 KB, 128-B rows, 128-B swizzle; 8 sample rows form one
 // 1024-B swizzle atom, the 64-feature groups of an operand are 8192 B apart), and the three plane products are issued from it.
-// grid = (rows, H / 128): CTA (r, mb) owns C_r[128 mb .. +128][0 .. N).  Warp 0: TMA, warp 1: MMA, warps 2..5: epilogue.
+// grid = (H / 128, rows): CTA (mb, r) owns C_r[128 mb .. +128][0 .. N); the M blocks of a row are neighbours in launch order, so
+// the B tiles they both read come from DRAM once (with the row index fastest the 256-wide kernel read 872 MB for 536 MB of
+// operands).  Warp 0: TMA, warp 1: MMA, warps 2..5: epilogue.
 constexpr int TN_BK = 64;
 template <int N>
 struct TnCfg {
@@ -510,9 +512,9 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full = empty + Cfg::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k0 = blockIdx.x * WD_KC, k1 = min(K, k0 + WD_KC);
+  const int k0 = blockIdx.y * WD_KC, k1 = min(K, k0 + WD_KC);
   const int nkb = k1 > k0 ? (k1 - k0 + TN_BK - 1) / TN_BK : 0;
-  const int j0 = blockIdx.y * 128;
+  const int j0 = blockIdx.x * 128;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -567,7 +569,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp >= 2) {
     const int q = warp & 3;                                                    // TMEM lane quarter this warp may read
     const int j = j0 + 32 * q + lane;
-    float* dst = C + (size_t)blockIdx.x * c_row_stride + (size_t)j * ldc;
+    float* dst = C + (size_t)blockIdx.y * c_row_stride + (size_t)j * ldc;
     if (nkb > 0) {
       mbar_wait(tmem_full, 0);
       fence_after_sync();
@@ -608,7 +610,7 @@ static int launch_gemm_tn(const __nv_bfloat16* A, const __nv_bfloat16* B, size_t
     AUR_CUDA_OK(cudaFuncSetAttribute(tc_gemm_tn_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr.done();
   }
-  tc_gemm_tn_kernel<N><<<dim3((unsigned)rows, N / 128), 192, Cfg::SMEM, s>>>(tmA, tmB, C, c_row_stride, N, ms, beta);
+  tc_gemm_tn_kernel<N><<<dim3(N / 128, (unsigned)rows), 192, Cfg::SMEM, s>>>(tmA, tmB, C, c_row_stride, N, ms, beta);
   AUR_LAUNCH_OK("tc_gemm_tn_kernel");
   return 0;
 }
