@@ -484,13 +484,13 @@ def run_ours(args):
                  "bf16 two-term splits; achieved = ALGORITHMIC fwd+bwd FLOP per sample / time against the measured dense "
                  "bf16 peak.  ncu: the kernel is issue-bound on the per-sample SIMT work, see profiles/"},
     ] + sweep
-    if HIDDEN != 64:      # the wide kernels (update_wide.cu; rollout_tc_kernel<ENV, 128> or, at 256, the runtime-width SIMT rollout)
+    if HIDDEN != 64:      # the wide kernels (update_wide.cu; rollout_tc_kernel<ENV, 128> or, at 256, the layer-wise rollout of rollout_wide.cu)
         rooflines[2]["kernel"] = "layer-wise tensor-core update (update_wide.cu: wide_gemm128 / tc_gemm / tc_gemm_tn + SIMT layers)"
         rooflines[2]["note"] = ("hidden %d: every H x H contraction is a tcgen05 GEMM over two-plane bf16 operands, activations staged in "
                                 "HBM per 262,144-sample sub-batch; achieved = ALGORITHMIC fwd+bwd FLOP per sample / time" % HIDDEN)
         rooflines[2].pop("algorithmic_bytes", None)
         if HIDDEN > 128:
-            rooflines[1]["kernel"] = "rollout_kernel (runtime-width SIMT)"
+            rooflines[1]["kernel"] = "layer-wise actor per step (rollout_wide.cu: rows_first / skinny_gemm / rows_head) + rollout_tc_kernel<ENV, 0> + value pass"
     dominant = max(rooflines[:3], key=lambda r: r["ms"] * (n_mb if "update" in r["kernel"] or r["kernel"].startswith("ppo_grad") else 1))
     roofline = {k: dominant[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
     roofline["kernel"] = dominant["kernel"]
