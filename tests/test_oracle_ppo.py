@@ -104,3 +104,30 @@ def test_feistel_shuffle_restatement_is_a_permutation():
     a, b = R.feistel_shuffle(4096, 1, 0), R.feistel_shuffle(4096, 1, 1)
     assert (a == b).mean() < 0.01 and np.array_equal(a, R.feistel_shuffle(4096, 1, 0))
     assert abs(np.corrcoef(a, np.arange(4096))[0, 1]) < 0.08
+
+
+@pytest.mark.parametrize("tag", ["disc128", "cont128", "disc128x3"])
+def test_update_step_wide_shapes(golden_dir, tag):
+    """The restated update against the reference's own gradients at 128 hidden units (tests/golden/update_wide.npz, written by
+    oracle/gen_golden_wide.py from the imported reference): pins the checker of the wide GPU paths, not only the 64-wide one."""
+    from tests.helpers import flat_from_named
+    g = np.load(os.path.join(golden_dir, "update_wide.npz"))
+    names = [str(n) for n in g[f"{tag}_names"]]
+    named0 = {}
+    for i, n in enumerate(names):
+        shape = tuple(int(v) for v in g[f"{tag}_pshape_{n}"])
+        k = np.arange(int(np.prod(shape)), dtype=np.float64)
+        named0[n] = torch.from_numpy(0.1 * np.sin(0.37 * k + i)).to(torch.float32).numpy().reshape(shape)
+    pol = R.RefPolicy(named0, bool(g[f"{tag}_shape"][4]))
+    opt = R.RefAdam(pol.tensors(), lr=float(g[f"{tag}_hyper"][4]), eps=1e-5)
+    t = lambda k: torch.from_numpy(g[f"{tag}_{k}"])
+    for step in range(2):
+        stats, raw, _, _ = R.ppo_update_step(pol, opt, t("obs"), t("act"), t("oldlp"), t("adv"), t("ret"), t("vold"), max_grad_norm=0.5)
+        want = flat_from_named({n: g[f"{tag}_s{step}_g_{n}"] for n in names})
+        got = flat_from_named({n: r.numpy() for n, r in zip(pol.p.keys(), raw)})
+        assert float(np.linalg.norm(got - want) / np.linalg.norm(want)) < 1e-6
+        ref = g[f"{tag}_s{step}_stats"]
+        np.testing.assert_allclose([stats[k] for k in ("policy_loss", "value_loss", "entropy", "loss", "old_approx_kl", "approx_kl", "clipfrac",
+                                                       "grad_norm")], ref, rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(flat_from_named({n: pol.p[n].detach().numpy() for n in names}),
+                               flat_from_named({n: g[f"{tag}_final_p_{n}"] for n in names}), rtol=1e-6, atol=1e-7)

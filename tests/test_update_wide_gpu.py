@@ -101,3 +101,41 @@ def test_wide_update_sub_batches_accumulate():
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * float(np.abs(want).max()) + 1e-9)
     for i, k in enumerate(kernels.STAT_NAMES):
         np.testing.assert_allclose(stats[i], stats_ref[k], rtol=1e-4, atol=2e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("tag", ["disc128", "cont128", "disc128x3"])
+def test_wide_update_matches_reference_golden(golden_dir, tag):
+    """tests/golden/update_wide.npz: two minibatch steps of ppo.py:220-269 computed by the REFERENCE'S OWN actor_critic +
+    torch.optim.Adam at 128 hidden units (oracle/gen_golden_wide.py, run where /root/reference exists).  The initial parameters
+    are the generator's closed form, re-created here from the stored names and shapes."""
+    import os
+    g = np.load(os.path.join(golden_dir, "update_wide.npz"))
+    names = [str(n) for n in g[f"{tag}_names"]]
+    obs_dim, act_dim, hidden, layers, cont = [int(v) for v in g[f"{tag}_shape"]]
+    named0 = {}
+    for i, n in enumerate(names):
+        shape = tuple(int(v) for v in g[f"{tag}_pshape_{n}"])
+        k = np.arange(int(np.prod(shape)), dtype=np.float64)
+        named0[n] = torch.from_numpy(0.1 * np.sin(0.37 * k + i)).to(torch.float32).numpy().reshape(shape)   # gen_golden.fill_params
+    clip, ent_c, vf_c, mgn, lr = [float(v) for v in g[f"{tag}_hyper"]]
+    desc = kernels.policy_desc(obs_dim, act_dim, hidden, layers, bool(cont))
+    params = torch.from_numpy(flat_from_named(named0)).cuda()
+    up = kernels.Updater(desc, params)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    bufs = [dev(g[f"{tag}_obs"]), dev(g[f"{tag}_act"].astype(np.float32)), dev(g[f"{tag}_oldlp"]), dev(g[f"{tag}_adv"]),
+            dev(g[f"{tag}_ret"]), dev(g[f"{tag}_vold"])]
+    idx = torch.arange(bufs[0].shape[0], dtype=torch.int32, device="cuda")
+    L = _lib.lib()
+    for step in range(2):
+        L.aur_launch_count_reset()
+        grads = up.grad(*bufs, idx, clip_coeff=clip, entropy_coeff=ent_c, value_coeff=vf_c, norm_adv=True, clip_vloss=True).clone()
+        assert L.aur_launch_count() >= 12                               # the layer-wise path, not the fused generic kernel
+        stats = up.apply(lr, mgn).cpu().numpy()
+        want = flat_from_named({n: g[f"{tag}_s{step}_g_{n}"] for n in names})
+        got = grads[:up.P].cpu().numpy()
+        print(f"{tag} step {step}: rel L2 vs the reference's gradients {_rel_l2(got, want):.2e}")
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * float(np.abs(want).max()) + 1e-9)
+        assert _rel_l2(got, want) < 1e-4
+        ref = g[f"{tag}_s{step}_stats"]
+        np.testing.assert_allclose([stats[0], stats[1], stats[2], stats[7], stats[3], stats[4], stats[5], stats[6]], ref, rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(params.cpu().numpy(), flat_from_named({n: g[f"{tag}_final_p_{n}"] for n in names}), rtol=1e-5, atol=1e-6)
