@@ -22,8 +22,44 @@ CASES = [  # tag, state_dim, action_dim, continuous, hidden, layers, minibatch
 ]
 
 
+def rollout_cases(ref_ac):
+    """Log-probs / values of the reference's actor_critic.evaluate (models/actor_critic.py:31-51) on the observations a seeded
+    rollout visits: the env trajectory under a fixed action tape is deterministic (the checker of oracle/envs.py replays it bit
+    for bit), so the GPU rollout kernels at 128 / 256 units can be compared with the REFERENCE's numbers, not a restatement's."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import envs as E
+    out = {}
+    for tag, kind, sd, ad, cont, hidden in [("cart128", E.CARTPOLE, 4, 2, False, 128), ("pend128", E.PENDULUM, 3, (1,), True, 128),
+                                            ("cart256", E.CARTPOLE, 4, 2, False, 256)]:
+        N, T = 96, 6
+        m = ref_ac.actor_critic(sd, ad, hidden, 2, 0.0, cont)
+        fill_params(m)
+        rng = np.random.default_rng(5)
+        actions = rng.normal(size=(T, N, 1)).astype(np.float32) if cont else rng.integers(0, 2, (T, N))
+        cv = E.CVecEnv(kind, N, wrappers=cont, trig=E.TRIG_CR)
+        cur, _ = cv.reset(list(range(N)))
+        obs = np.zeros((T, N, sd), np.float32)
+        for t in range(T):
+            obs[t] = cur
+            cur = cv.step(actions[t])[0]
+        ot = torch.from_numpy(obs.reshape(-1, sd))
+        at = torch.from_numpy(actions.reshape(-1, 1)) if cont else torch.from_numpy(actions.reshape(-1)).long()
+        with torch.no_grad():
+            _, lp, ent, v = m.evaluate(ot, at)
+            nv = m.value(torch.from_numpy(cur))
+        out[f"{tag}_names"] = np.array([n for n, _ in m.named_parameters()])
+        for n, p in m.named_parameters():
+            out[f"{tag}_pshape_{n}"] = np.array(p.shape)
+        out[f"{tag}_shape"] = np.array([sd, int(np.prod(ad)) if cont else ad, hidden, 2, int(cont), N, T])
+        for k, v_ in dict(actions=actions.astype(np.float32), obs=obs, logp=lp.numpy().reshape(T, N), value=v.numpy().reshape(T, N),
+                          next_value=nv.numpy().reshape(N)).items():
+            out[f"{tag}_{k}"] = v_
+    return out
+
+
 def main():
     _, ref_ac, _ = import_reference()
+    np.savez_compressed(os.path.join(OUT, "rollout_wide.npz"), **rollout_cases(ref_ac))
     out = {}
     for tag, sd, ad, cont, hidden, nl, B in CASES:
         m = ref_ac.actor_critic(sd, ad, hidden, nl, 0.0, cont)

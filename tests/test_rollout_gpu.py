@@ -1,5 +1,7 @@
 """Rollout kernel vs the CPU checker (GPU).  Env transitions, rewards and done flags are
 compared BIT FOR BIT (north_star); log-probs and values within 2e-5 (fp32 MLP, fast tanh)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -529,3 +531,28 @@ def test_mountaincar_continuous_replay_is_bit_exact(wrappers, hidden, rollout_im
         _, lp, _, v = pol.evaluate(torch.from_numpy(obs.reshape(-1, 2)), torch.from_numpy(actions.reshape(-1, 1)))
     np.testing.assert_allclose(buf.log_probs.cpu().numpy().reshape(-1), lp.numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(buf.values.cpu().numpy().reshape(-1), v.numpy().reshape(-1), rtol=2e-5, atol=5e-6)
+
+
+@pytest.mark.parametrize("tag,gym_id", [("cart128", "CartPole-v1"), ("pend128", "Pendulum-v1"), ("cart256", "CartPole-v1")])
+def test_wide_rollout_matches_reference_golden(golden_dir, tag, gym_id, rollout_impl):
+    """tests/golden/rollout_wide.npz (oracle/gen_golden_wide.py): log-probs / values of the REFERENCE'S OWN actor_critic.evaluate
+    at 128 / 256 hidden units on the observations a seeded rollout visits under a fixed action tape.  The device rollout must
+    visit the same observations bit for bit and store the reference's numbers (both kernel families)."""
+    g = np.load(os.path.join(golden_dir, "rollout_wide.npz"))
+    obs_dim, act_dim, hidden, layers, cont, N, T = [int(v) for v in g[f"{tag}_shape"]]
+    named0 = {}
+    for i, n in enumerate(str(x) for x in g[f"{tag}_names"]):
+        shape = tuple(int(v) for v in g[f"{tag}_pshape_{n}"])
+        k = np.arange(int(np.prod(shape)), dtype=np.float64)
+        named0[n] = torch.from_numpy(0.1 * np.sin(0.37 * k + i)).to(torch.float32).numpy().reshape(shape)   # gen_golden.fill_params
+    desc = kernels.policy_desc(obs_dim, act_dim, hidden, layers, bool(cont))
+    flat = torch.from_numpy(flat_from_named(named0)).cuda()
+    env = denv.DeviceVecEnv(gym_id, N, wrappers=bool(cont))
+    env.reset(list(range(N)))
+    buf = kernels.RolloutBuffers(T, N, obs_dim, (act_dim,) if cont else (), "cuda")
+    kernels.rollout(env, desc, flat, buf, seed=1, step0=0, actions_in=torch.from_numpy(g[f"{tag}_actions"]).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.states.cpu().numpy(), g[f"{tag}_obs"])
+    np.testing.assert_allclose(buf.log_probs.cpu().numpy(), g[f"{tag}_logp"], **TOL)
+    np.testing.assert_allclose(buf.values.cpu().numpy(), g[f"{tag}_value"], **TOL)
+    np.testing.assert_allclose(buf.next_value.cpu().numpy(), g[f"{tag}_next_value"], **TOL)
