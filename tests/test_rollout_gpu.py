@@ -556,3 +556,30 @@ def test_wide_rollout_matches_reference_golden(golden_dir, tag, gym_id, rollout_
     np.testing.assert_allclose(buf.log_probs.cpu().numpy(), g[f"{tag}_logp"], **TOL)
     np.testing.assert_allclose(buf.values.cpu().numpy(), g[f"{tag}_value"], **TOL)
     np.testing.assert_allclose(buf.next_value.cpu().numpy(), g[f"{tag}_next_value"], **TOL)
+
+
+def test_layerwise_rollout_more_envs_than_one_sub_batch(rollout_impl):
+    """rollout_wide.cu chunks every per-step actor pass (and the value pass) at 262,144 rows: with more envs than that, the
+    second chunk must see its own rows.  The layer-wise path against the runtime-width SIMT kernel on the same seeds and action
+    tape: identical trajectory, log-probs / values within 2e-5."""
+    if rollout_impl != "tc":
+        pytest.skip("compares the two paths itself")
+    L = _lib.lib()
+    N, T, hidden = 262144 + 4321, 2, 256
+    _, named = random_policy(4, 2, hidden, 2, False, seed=8)
+    desc = kernels.policy_desc(4, 2, hidden, 2, False)
+    flat = torch.from_numpy(flat_from_named(named)).cuda()
+    actions = torch.randint(0, 2, (T, N), generator=torch.Generator().manual_seed(1)).float().cuda()
+    res = {}
+    for impl in (1, 0):
+        assert L.aur_rollout_set_impl(impl) == 0
+        env = denv.DeviceVecEnv("CartPole-v1", N)
+        env.reset(list(range(N)))
+        buf = kernels.RolloutBuffers(T, N, 4, (), "cuda")
+        kernels.rollout(env, desc, flat, buf, seed=1, step0=0, actions_in=actions)
+        torch.cuda.synchronize()
+        res[impl] = (buf.states.clone(), buf.log_probs.clone(), buf.values.clone(), buf.next_value.clone(), env.next_obs.clone())
+    L.aur_rollout_set_impl(1)
+    assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[1][4], res[0][4])
+    for i in (1, 2, 3):
+        torch.testing.assert_close(res[1][i], res[0][i], **TOL)
