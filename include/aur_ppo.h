@@ -193,9 +193,12 @@ typedef struct {
 
 int aur_rollout(const aur_rollout_args* args, void* stream);
 
-/* Kernel behind aur_rollout for hidden 64 / 2 layers: 1 = actor hidden layer on tcgen05 (rollout_tc_kernel, default),
- * 0 = SIMT rollout_kernel (also the path for other layer counts).  Both are followed by the batched tensor-core
- * value pass.  AUR_ROLLOUT_IMPL=simt|tc sets the initial choice. */
+/* Kernel behind aur_rollout: 1 (default) = tensor cores - hidden 64 or 128 with 2 layers: the fused rollout_tc_kernel (actor
+ * hidden layer on tcgen05) followed by the batched tensor-core value pass; hidden 256, or 128 with more layers (obs_dim <= 4,
+ * act_dim <= 4, CartPole / Pendulum / MountainCar): the actor layer by layer over all envs every step (rollout_wide.cu), which
+ * keeps its activation scratch (about 1.1 GB at 256 units) in a library-owned, grow-only allocation per (device, stream) because
+ * this entry point has no workspace argument - make the first call of a shape outside a CUDA-graph capture;
+ * 0 = SIMT rollout_kernel (also the path of every other width / depth).  AUR_ROLLOUT_IMPL=simt|tc sets the initial choice. */
 int aur_rollout_set_impl(int impl);
 int aur_rollout_get_impl(void);
 
