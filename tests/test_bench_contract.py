@@ -63,3 +63,16 @@ def test_own_arm_needs_a_gpu():
         pytest.skip("CUDA present")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_hidden_dim_flag_reaches_config_params_and_flop_count(monkeypatch):
+    """`bench.py --hidden_dim 128 | 256` (src/run_ppo.py:36): the width is named in `config`, handed to ppo(params) and used for
+    the algorithmic FLOP count of the roofline; 64 stays the default of every BASELINE config."""
+    import bench
+    w = bench.WORKLOADS["ppo"]
+    assert bench.HIDDEN == 64 and bench.workload_config("ppo", 1)["hidden_dim"] == 64
+    f64 = bench.mlp_flops_fwd(w)
+    monkeypatch.setattr(bench, "HIDDEN", 128)
+    assert bench.workload_config("ppo", 1)["hidden_dim"] == 128 and bench.params("ppo", 1, 3)["hidden_dim"] == 128
+    o, a = w["obs"], w["act"]
+    assert bench.mlp_flops_fwd(w) == 2 * (o * 128 + 128 * 128 + 128 * a) + 2 * (o * 128 + 128 * 128 + 128) > 3 * f64
